@@ -1,0 +1,253 @@
+"""ctypes binding of the CPU oracle (oracle/libkgw_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(knockoffgwas_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+STREAM_Z, STREAM_ZK, STREAM_HK, STREAM_FAMILY = 0, 1, 2, 3
+RNG_INJECTED, RNG_TAUS88, RNG_PHILOX = 0, 1, 2
+
+
+class _Taus(C.Structure):
+    _fields_ = [("v1", C.c_uint32), ("v2", C.c_uint32), ("v3", C.c_uint32)]
+
+
+class _Problem(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("p", C.c_int32), ("K", C.c_int32), ("W", C.c_int32),
+        ("row_bytes", C.c_int64),
+        ("H", C.c_void_p), ("ref_local", C.c_void_p), ("ref_global", C.c_void_p),
+        ("b", C.c_void_p), ("mu", C.c_void_p), ("groups", C.c_void_p),
+        ("win_start", C.c_void_p), ("win_end", C.c_void_p),
+    ]
+
+
+class _Rng(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("injected", C.c_void_p), ("taus", _Taus),
+        ("seed", C.c_uint64), ("n_draws", C.c_int64),
+    ]
+
+
+def build(force: bool = False) -> Path:
+    so = _HERE / "libkgw_oracle.so"
+    srcs = [_HERE / n for n in ("kgw_oracle.c", "kgw_oracle_family.c", "kgw_rng.c", "kgw_oracle.h", "kgw_rng.h")]
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-C", str(_HERE), "libkgw_oracle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(str(build()))
+        _LIB.kgw_oracle_unrelated.restype = C.c_int
+        _LIB.kgw_oracle_weighted_choice.restype = C.c_int
+        _LIB.kgw_oracle_weighted_choice.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        _LIB.kgw_taus88_seed.argtypes = [C.POINTER(_Taus), C.c_uint32]
+        _LIB.kgw_taus88_next.argtypes = [C.POINTER(_Taus)]
+        _LIB.kgw_taus88_next.restype = C.c_uint32
+        _LIB.kgw_oracle_philox_uniform.restype = C.c_double
+        _LIB.kgw_oracle_philox_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+        _LIB.kgw_oracle_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    return _LIB
+
+
+@dataclass
+class Problem:
+    """Everything the unchanged host code hands to the hot path."""
+    H: np.ndarray                 # uint8 [N][row_bytes], LSB-first
+    p: int
+    K: int
+    ref_local: np.ndarray         # int32 [N][W][K]
+    ref_global: np.ndarray        # int32 [N][K]
+    b: np.ndarray                 # float64 [p]
+    mu: np.ndarray                # float64 [p]
+    groups: np.ndarray            # int32 [p]
+    win_start: np.ndarray = None  # int32 [W]
+    win_end: np.ndarray = None    # int32 [W]
+    unrelated: np.ndarray = None  # int32 sorted haplotype ids
+    families: list = field(default_factory=list)   # list of int32 arrays (haplotype ids)
+    ibd_segments: list = field(default_factory=list)  # list of (hap, j_min, j_max, bp_min, bp_max, ids)
+    bp: np.ndarray = None
+    seed: int = 2020
+    meta: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.H = np.ascontiguousarray(self.H, dtype=np.uint8)
+        self.N = int(self.H.shape[0])
+        self.row_bytes = int(self.H.shape[1])
+        if self.win_start is None:
+            self.win_start = np.array([0], dtype=np.int32)
+            self.win_end = np.array([self.p], dtype=np.int32)
+        self.W = int(len(self.win_start))
+        self.ref_local = np.ascontiguousarray(self.ref_local, dtype=np.int32).reshape(self.N, self.W, self.K)
+        self.ref_global = np.ascontiguousarray(self.ref_global, dtype=np.int32).reshape(self.N, self.K)
+        self.b = np.ascontiguousarray(self.b, dtype=np.float64)
+        self.mu = np.ascontiguousarray(self.mu, dtype=np.float64)
+        self.groups = np.ascontiguousarray(self.groups, dtype=np.int32)
+        self.win_start = np.ascontiguousarray(self.win_start, dtype=np.int32)
+        self.win_end = np.ascontiguousarray(self.win_end, dtype=np.int32)
+        if self.unrelated is None:
+            self.unrelated = np.arange(self.N, dtype=np.int32)
+        self.unrelated = np.ascontiguousarray(self.unrelated, dtype=np.int32)
+
+    def _c(self) -> _Problem:
+        P = _Problem()
+        P.N, P.p, P.K, P.W = self.N, self.p, self.K, self.W
+        P.row_bytes = self.row_bytes
+        P.H = self.H.ctypes.data
+        P.ref_local = self.ref_local.ctypes.data
+        P.ref_global = self.ref_global.ctypes.data
+        P.b = self.b.ctypes.data
+        P.mu = self.mu.ctypes.data
+        P.groups = self.groups.ctypes.data
+        P.win_start = self.win_start.ctypes.data
+        P.win_end = self.win_end.ctypes.data
+        return P
+
+
+def load_probe_dump(d) -> tuple[Problem, np.ndarray, np.ndarray | None]:
+    """Load a directory written by oracle/_ref/snpknock2_probe (wrap_probe.cpp).
+    Returns (problem, Hk_reference uint8 [N][row_bytes], trace int32 [n][2] or None)."""
+    d = Path(d)
+    meta = {}
+    for line in (d / "meta.txt").read_text().splitlines():
+        k, v = line.split(None, 1)
+        meta[k] = v
+    N, p, K, W = (int(meta[k]) for k in ("N", "p", "K", "W"))
+    rb = (p + 7) // 8
+    rd = lambda name, dt: np.fromfile(d / name, dtype=dt)
+    fam_off = rd("fam_offsets.i32", np.int32)
+    fam_mem = rd("fam_members.i32", np.int32)
+    families = [fam_mem[fam_off[f]:fam_off[f + 1]].copy() for f in range(len(fam_off) - 1)]
+    raw = rd("ibd_segments.i32", np.int32)
+    segs, t = [], 0
+    while t < len(raw):
+        hap, jmin, jmax, bpmin, bpmax, n = (int(x) for x in raw[t:t + 6])
+        segs.append((hap, jmin, jmax, bpmin, bpmax, raw[t + 6:t + 6 + n].copy()))
+        t += 6 + n
+    prob = Problem(
+        H=rd("H.u8", np.uint8).reshape(N, rb), p=p, K=K,
+        ref_local=rd("ref_local.i32", np.int32).reshape(N, W, K),
+        ref_global=rd("ref_global.i32", np.int32).reshape(N, K),
+        b=rd("b.f64", np.float64), mu=rd("mu.f64", np.float64), groups=rd("groups.i32", np.int32),
+        win_start=rd("win_start.i32", np.int32), win_end=rd("win_end.i32", np.int32),
+        unrelated=rd("unrelated.i32", np.int32), families=families, ibd_segments=segs,
+        bp=rd("bp.i32", np.int32), seed=int(meta["seed"]), meta=meta)
+    Hk = rd("Hk.u8", np.uint8).reshape(N, rb)
+    trace = None
+    if (d / "trace.i32").exists() and meta.get("traced") == "1":
+        trace = rd("trace.i32", np.int32).reshape(-1, 2)
+    return prob, Hk, trace
+
+
+def taus88_stream(seed: int | None, n: int) -> np.ndarray:
+    """n raw 32-bit outputs of boost taus88; seed None = default-constructed (341)."""
+    g = _Taus()
+    L = lib()
+    L.kgw_taus88_seed(C.byref(g), 341 if seed is None else int(seed) & 0xFFFFFFFF)
+    out = np.empty(n, dtype=np.uint32)
+    for i in range(n):
+        out[i] = L.kgw_taus88_next(C.byref(g))
+    return out
+
+
+def philox_uniform(seed: int, hap: int, stream: int, locus: int) -> float:
+    return lib().kgw_oracle_philox_uniform(int(seed), int(hap), int(stream), int(locus))
+
+
+def philox_uniforms(seed: int, haps: np.ndarray, p: int) -> np.ndarray:
+    """U[len(haps)][3][p] of the keyed generator (numpy restatement, vectorised)."""
+    haps = np.asarray(haps, dtype=np.uint32)
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    nblk = (p + 3) // 4
+    c0 = np.broadcast_to(np.arange(nblk, dtype=np.uint32)[None, None, :], (len(haps), 3, nblk)).copy()
+    c1 = np.broadcast_to(haps[:, None, None], c0.shape).copy()
+    c2 = np.broadcast_to(np.arange(3, dtype=np.uint32)[None, :, None], c0.shape).copy()
+    c3 = np.zeros_like(c0)
+    k0 = np.uint32(seed & 0xFFFFFFFF)
+    k1 = np.uint32((seed >> 32) & 0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = M0 * c0.astype(np.uint64)
+            p1 = M1 * c2.astype(np.uint64)
+            n0 = (p1 >> np.uint64(32)).astype(np.uint32) ^ c1 ^ k0
+            n1 = p1.astype(np.uint32)
+            n2 = (p0 >> np.uint64(32)).astype(np.uint32) ^ c3 ^ k1
+            n3 = p0.astype(np.uint32)
+            c0, c1, c2, c3 = n0, n1, n2, n3
+            k0 = np.uint32((int(k0) + 0x9E3779B9) & 0xFFFFFFFF)
+            k1 = np.uint32((int(k1) + 0xBB67AE85) & 0xFFFFFFFF)
+    words = np.stack([c0, c1, c2, c3], axis=-1).reshape(len(haps), 3, nblk * 4)[:, :, :p]
+    return words.astype(np.float64) / 4294967296.0
+
+
+@dataclass
+class Result:
+    z: np.ndarray
+    zk: np.ndarray
+    hk: np.ndarray
+    beta: np.ndarray | None
+    n_draws: int
+    taus_state: tuple | None = None
+
+
+def run_unrelated(prob: Problem, haps=None, *, mode="philox", seed=None, injected=None,
+                  taus_seed=None, taus_state=None, want_beta=False) -> Result:
+    """Run the restated unrelated-haplotype sampler for `haps` (default: prob.unrelated).
+
+    mode: "philox" (key = seed), "injected" (U[N][3][p], indexed by absolute haplotype id),
+          "taus88" (sequential replay of the reference's stream; taus_seed None = boost default)."""
+    L = lib()
+    haps = prob.unrelated if haps is None else np.ascontiguousarray(haps, dtype=np.int32)
+    n = len(haps)
+    R = _Rng()
+    keep = None
+    if mode == "injected":
+        keep = np.ascontiguousarray(injected, dtype=np.float64)
+        assert keep.shape == (prob.N, 3, prob.p)
+        R.mode, R.injected = RNG_INJECTED, keep.ctypes.data
+    elif mode == "taus88":
+        R.mode = RNG_TAUS88
+        if taus_state is not None:
+            R.taus.v1, R.taus.v2, R.taus.v3 = taus_state
+        else:
+            L.kgw_taus88_seed(C.byref(R.taus), 341 if taus_seed is None else int(taus_seed) & 0xFFFFFFFF)
+    elif mode == "philox":
+        R.mode, R.seed = RNG_PHILOX, int(prob.seed if seed is None else seed)
+    else:
+        raise ValueError(mode)
+    z = np.zeros((n, prob.p), dtype=np.int32)
+    zk = np.zeros((n, prob.p), dtype=np.int32)
+    hk = np.zeros((n, prob.row_bytes), dtype=np.uint8)
+    beta = np.zeros((n, prob.p, prob.K), dtype=np.float64) if want_beta else None
+    P = prob._c()
+    rc = L.kgw_oracle_unrelated(C.byref(P), C.byref(R), C.c_void_p(haps.ctypes.data), C.c_int32(n),
+                                C.c_void_p(z.ctypes.data), C.c_void_p(zk.ctypes.data),
+                                C.c_void_p(hk.ctypes.data),
+                                C.c_void_p(beta.ctypes.data if want_beta else None))
+    if rc != 0:
+        raise RuntimeError(f"kgw_oracle_unrelated failed with {rc}")
+    return Result(z, zk, hk, beta, int(R.n_draws), (R.taus.v1, R.taus.v2, R.taus.v3))
+
+
+def unpack_bits(rows: np.ndarray, p: int) -> np.ndarray:
+    return np.unpackbits(rows, axis=1, bitorder="little")[:, :p]
+
+
+def pack_bits(bits: np.ndarray) -> np.ndarray:
+    return np.packbits(bits.astype(np.uint8), axis=1, bitorder="little")
