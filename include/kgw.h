@@ -1,0 +1,132 @@
+/* include/kgw.h -- C ABI of the B200-native haplotype knockoff sampler.
+ *
+ * Drop-in boundary: the reference (msesia/knockoffgwas, snpknock2) has no plugin /
+ * FFI interface; the seam is the C++ method
+ *
+ *     void Knockoffs::generate(const int num_threads)     snpknock2/src/knockoffs.h:56
+ *                                                          snpknock2/src/knockoffs.cpp:311-327
+ *
+ * called once per (chromosome, resolution) from KnockoffGenerator::generate()
+ * (generator_master.cpp:109-115, main.cpp:159-181).  Everything it reads is host
+ * state that the unchanged snpknock2 code has already prepared; everything it
+ * writes is the packed knockoff matrix Hk.  This header is that seam as plain C:
+ * flat caller-owned buffers in, flat caller-owned buffer out, int status.
+ * INTEGRATION.md shows the 40-line body a maintainer puts in Knockoffs::generate().
+ *
+ * All pointers in kgw_problem are HOST pointers unless a function says otherwise.
+ * The callee never retains a caller pointer past return (kgw_plan_* copies what it
+ * needs to the device).  No torch / C++ types cross this boundary.
+ */
+#ifndef KGW_H
+#define KGW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGW_ABI_VERSION 1
+
+/* status codes (negative = error; kgw_last_error() has the text) */
+enum {
+  KGW_OK = 0,
+  KGW_ERR_INVALID = -1,      /* bad argument / inconsistent problem description          */
+  KGW_ERR_UNSUPPORTED = -2,  /* valid for the reference but outside this build (e.g. K)   */
+  KGW_ERR_CUDA = -3,         /* CUDA runtime failure or no sm_100 device                  */
+  KGW_ERR_NOMEM = -4
+};
+
+/* random streams of the counter-based generator (replaces the per-thread sequential
+ * boost::random::taus88 of knockoffs.cpp:401-406,596-612 -- results no longer depend
+ * on --n_threads).  u(seed, hap, stream, locus) =
+ *     Philox4x32-10(key = {seed lo, seed hi}, ctr = {locus >> 2, hap, stream, 0})[locus & 3] / 2^32
+ * i.e. 32-bit resolution like the reference's uniform_real_distribution over taus88
+ * (uniform_real_distribution.hpp:56-64).  `hap` is the absolute haplotype index.  With
+ * --windows > 0 the padded window passes (knockoffs.cpp:1222-1226) overlap; pass w uses
+ * stream word `stream | (w << 2)` so no uniform is consumed twice. */
+enum { KGW_STREAM_Z = 0, KGW_STREAM_ZK = 1, KGW_STREAM_HK = 2, KGW_STREAM_FAMILY = 3 };
+
+/* What Knockoffs::generate() reads. */
+typedef struct kgw_problem {
+  int32_t abi_version;        /* = KGW_ABI_VERSION                                                   */
+  int32_t N;                  /* Haplotypes::num_haps                       haplotypes.h:38          */
+  int32_t p;                  /* Haplotypes::num_snps                       haplotypes.h:37          */
+  int32_t K;                  /* Knockoffs::K                               knockoffs.h:138          */
+  int32_t W;                  /* metadata.windows.num_windows               windows.h:17             */
+  int32_t reserved0;
+  int64_t row_bytes;          /* bytes per packed row of H / Hk, >= ceil(p/8)                        */
+  const uint8_t *H;           /* [N][row_bytes] Haplotypes::H, chaplotype bit layout
+                                 (bit j at byte j>>3, mask 1<<(j&7))        chaplotype.h:25          */
+  const int32_t *ref_local;   /* [N][W][K] Knockoffs::references_local (sorted) knockoffs.h:139      */
+  const int32_t *ref_global;  /* [N][K]    Knockoffs::references_global     knockoffs.h:141; may be
+                                 NULL when there are no related haplotypes                          */
+  const double *b;            /* [p] Knockoffs::b            knockoffs.h:76, knockoffs.cpp:1508-1517 */
+  const double *mu;           /* [p] Knockoffs::mut_rates    knockoffs.h:77                          */
+  const int32_t *groups;      /* [p] Knockoffs::groups (contiguous runs, 0-based) knockoffs.h:151    */
+  const int32_t *win_start;   /* [W] metadata.windows.start                 windows.h:18             */
+  const int32_t *win_end;     /* [W] metadata.windows.end (exclusive)       windows.h:18             */
+  const int32_t *unrelated;   /* [n_unrelated] metadata.unrelated, ascending metadata.h:101          */
+  int32_t n_unrelated;
+  int32_t reserved1;
+  uint64_t seed;              /* Knockoffs::seed                            knockoffs.h:71           */
+  /* test hook: if non-NULL, U[N][3][p] doubles in [0,1) replace the generator for the
+   * unrelated branch (stream order KGW_STREAM_Z, _ZK, _HK; indexed by absolute haplotype). */
+  const double *injected_u;
+} kgw_problem;
+
+typedef struct kgw_options {
+  int32_t device;        /* CUDA device ordinal (one process per GPU: pass LOCAL_RANK)        */
+  int32_t block_loci;    /* 0 = default; checkpoint spacing of the backward messages          */
+  int32_t lanes_per_hap; /* 0 = auto; 4, 8, 16 or 32 lanes cooperate on one haplotype         */
+  int32_t ctas_per_sm;   /* 0 = auto (occupancy query)                                        */
+  int32_t reserved[4];
+} kgw_options;
+
+/* Optional debug outputs (any pointer may be NULL); rows follow `unrelated` order. */
+typedef struct kgw_debug {
+  int32_t *z;            /* [n_unrelated][p] sampled latent path (knockoffs.cpp:1243,1259)     */
+  int32_t *zk;           /* [n_unrelated][p] knockoff path       (knockoffs.cpp:1421)          */
+  double *beta_ckpt;     /* [n_unrelated][n_ckpt][K] backward messages at the checkpoint loci of
+                            the LAST window pass, normalised to sum 1 (knockoffs.cpp:1069-1073) */
+  int32_t *ckpt_locus;   /* [n_ckpt] the loci those rows belong to                             */
+  int32_t n_ckpt;        /* in: capacity of the two arrays above; out: rows written            */
+  int32_t reserved;
+} kgw_debug;
+
+typedef struct kgw_plan kgw_plan;
+
+int32_t kgw_abi_version(void);
+const char *kgw_last_error(void);
+
+/* One-shot drop-in for Knockoffs::generate(): host buffers in, host buffer out.
+ * hk_out is [N][row_bytes]; only the rows listed in `unrelated` are written (the body of
+ * generate_unrelated, knockoffs.cpp:573-700).  H2D, kernels and D2H all inside. */
+int32_t kgw_generate(const kgw_problem *prob, const kgw_options *opt, uint8_t *hk_out, kgw_debug *dbg);
+
+/* Resident-data path (bench / repeated resolutions): upload once, run many times. */
+int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_plan **plan_out);
+/* Replace the partition (Knockoffs::set_partition, knockoffs.cpp:91-107) without re-uploading H. */
+int32_t kgw_plan_set_groups(kgw_plan *plan, const int32_t *groups);
+/* Launch on the plan's stream; returns after the kernels have been enqueued. */
+int32_t kgw_plan_run(kgw_plan *plan);
+/* Run `iters` times, timed with CUDA events on the launching stream; ms_out = mean ms per run. */
+int32_t kgw_plan_run_timed(kgw_plan *plan, int32_t iters, float *ms_out);
+int32_t kgw_plan_sync(kgw_plan *plan);
+/* D2H of the packed knockoff rows (same layout as kgw_generate's hk_out). */
+int32_t kgw_plan_download(kgw_plan *plan, uint8_t *hk_out, kgw_debug *dbg);
+/* Device pointer of the packed knockoff matrix [N][row_bytes] (for NCCL gathers etc.). */
+void *kgw_plan_device_hk(kgw_plan *plan);
+/* Introspection for bench.py: kernel launches per run, resident CTAs, bytes of scratch. */
+int32_t kgw_plan_info(kgw_plan *plan, int32_t *launches_per_run, int32_t *grid, int32_t *block,
+                      int64_t *scratch_bytes, int32_t *lanes_per_hap, int32_t *states_per_lane);
+void kgw_plan_destroy(kgw_plan *plan);
+
+/* Host replay of the generator (bit-identical to the device code). */
+double kgw_uniform(uint64_t seed, uint32_t hap, uint32_t stream, uint32_t locus);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGW_H */

@@ -1,0 +1,13 @@
+"""knockoffgwas_b200 -- B200-native (sm_100a) replacement for the hot path of snpknock2's
+haplotype knockoff sampler (msesia/knockoffgwas, snpknock2/src/knockoffs.cpp:311 `Knockoffs::generate`).
+
+The product is the C-ABI shared library built from csrc/ (include/kgw.h).  This Python package is
+a thin ctypes binding plus a host-side mirror of the reference's `Knockoffs` interface used by the
+tests and the benchmark.  There is no CPU fallback: without the CUDA library / a B200 every compute
+call raises.
+"""
+from .api import (KgwError, Knockoffs, Options, Plan, abi_version, generate, lib_path, load_library,
+                  uniform)
+
+__all__ = ["KgwError", "Knockoffs", "Options", "Plan", "abi_version", "generate", "lib_path",
+           "load_library", "uniform"]

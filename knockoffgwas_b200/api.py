@@ -1,0 +1,338 @@
+"""ctypes binding of the C ABI (include/kgw.h) and a host-side mirror of the reference's
+`Knockoffs` interface (snpknock2/src/knockoffs.h:22-68) for the hot path.
+
+No CPU fallback: every compute call goes through libkgw.so and fails loudly if the CUDA
+extension is missing or no sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_LIB = None
+
+KGW_ABI_VERSION = 1
+STREAM_Z, STREAM_ZK, STREAM_HK, STREAM_FAMILY = 0, 1, 2, 3
+
+
+class KgwError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"kgw error {code}: {msg}")
+        self.code = code
+
+
+class _Problem(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("N", C.c_int32), ("p", C.c_int32), ("K", C.c_int32),
+        ("W", C.c_int32), ("reserved0", C.c_int32), ("row_bytes", C.c_int64),
+        ("H", C.c_void_p), ("ref_local", C.c_void_p), ("ref_global", C.c_void_p),
+        ("b", C.c_void_p), ("mu", C.c_void_p), ("groups", C.c_void_p),
+        ("win_start", C.c_void_p), ("win_end", C.c_void_p), ("unrelated", C.c_void_p),
+        ("n_unrelated", C.c_int32), ("reserved1", C.c_int32), ("seed", C.c_uint64),
+        ("injected_u", C.c_void_p),
+    ]
+
+
+class _Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("block_loci", C.c_int32), ("lanes_per_hap", C.c_int32),
+                ("ctas_per_sm", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+class _Debug(C.Structure):
+    _fields_ = [("z", C.c_void_p), ("zk", C.c_void_p), ("beta_ckpt", C.c_void_p), ("ckpt_locus", C.c_void_p),
+                ("n_ckpt", C.c_int32), ("reserved", C.c_int32)]
+
+
+@dataclass
+class Options:
+    device: int = 0
+    block_loci: int = 0
+    lanes_per_hap: int = 0
+    ctas_per_sm: int = 0
+
+    def _c(self) -> _Options:
+        o = _Options()
+        o.device, o.block_loci, o.lanes_per_hap, o.ctas_per_sm = self.device, self.block_loci, self.lanes_per_hap, self.ctas_per_sm
+        return o
+
+
+def lib_path() -> Path:
+    return _PKG / "lib" / "libkgw.so"
+
+
+def load_library():
+    """Load libkgw.so (built in-tree by knockoffgwas_b200.build / __graft_entry__.build)."""
+    global _LIB
+    if _LIB is None:
+        pth = lib_path()
+        if not pth.exists():
+            raise KgwError(-3, f"{pth} is missing: build the CUDA extension first "
+                               f"(python -m knockoffgwas_b200.build); there is no CPU fallback")
+        L = C.CDLL(str(pth))
+        L.kgw_abi_version.restype = C.c_int32
+        L.kgw_last_error.restype = C.c_char_p
+        L.kgw_uniform.restype = C.c_double
+        L.kgw_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.kgw_generate.restype = C.c_int32
+        L.kgw_generate.argtypes = [C.POINTER(_Problem), C.POINTER(_Options), C.c_void_p, C.POINTER(_Debug)]
+        L.kgw_plan_create.restype = C.c_int32
+        L.kgw_plan_create.argtypes = [C.POINTER(_Problem), C.POINTER(_Options), C.POINTER(C.c_void_p)]
+        L.kgw_plan_set_groups.restype = C.c_int32
+        L.kgw_plan_set_groups.argtypes = [C.c_void_p, C.c_void_p]
+        L.kgw_plan_run.restype = C.c_int32
+        L.kgw_plan_run.argtypes = [C.c_void_p]
+        L.kgw_plan_run_timed.restype = C.c_int32
+        L.kgw_plan_run_timed.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]
+        L.kgw_plan_sync.restype = C.c_int32
+        L.kgw_plan_sync.argtypes = [C.c_void_p]
+        L.kgw_plan_download.restype = C.c_int32
+        L.kgw_plan_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Debug)]
+        L.kgw_plan_device_hk.restype = C.c_void_p
+        L.kgw_plan_device_hk.argtypes = [C.c_void_p]
+        L.kgw_plan_info.restype = C.c_int32
+        L.kgw_plan_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3 + [C.POINTER(C.c_int64)] + [C.POINTER(C.c_int32)] * 2
+        L.kgw_plan_destroy.restype = None
+        L.kgw_plan_destroy.argtypes = [C.c_void_p]
+        if L.kgw_abi_version() != KGW_ABI_VERSION:
+            raise KgwError(-1, "libkgw.so ABI version mismatch")
+        _LIB = L
+    return _LIB
+
+
+def abi_version() -> int:
+    return load_library().kgw_abi_version()
+
+
+def uniform(seed: int, hap: int, stream: int, locus: int) -> float:
+    """Host replay of the device generator."""
+    return load_library().kgw_uniform(int(seed), int(hap), int(stream), int(locus))
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise KgwError(rc, (load_library().kgw_last_error() or b"").decode())
+
+
+class _Held:
+    """Keeps the numpy buffers behind a kgw_problem alive."""
+
+    def __init__(self, H, p, K, ref_local, b, mu, groups, win_start=None, win_end=None, unrelated=None,
+                 ref_global=None, seed=2020, injected_u=None):
+        self.H = np.ascontiguousarray(H, dtype=np.uint8)
+        assert self.H.ndim == 2
+        self.N, self.row_bytes = (int(x) for x in self.H.shape)
+        self.p, self.K = int(p), int(K)
+        if win_start is None:
+            win_start, win_end = [0], [self.p]
+        self.win_start = np.ascontiguousarray(win_start, dtype=np.int32)
+        self.win_end = np.ascontiguousarray(win_end, dtype=np.int32)
+        self.W = len(self.win_start)
+        self.ref_local = np.ascontiguousarray(ref_local, dtype=np.int32).reshape(self.N, self.W, self.K)
+        self.ref_global = None if ref_global is None else np.ascontiguousarray(ref_global, dtype=np.int32).reshape(self.N, self.K)
+        self.b = np.ascontiguousarray(b, dtype=np.float64)
+        self.mu = np.ascontiguousarray(mu, dtype=np.float64)
+        self.groups = np.ascontiguousarray(groups, dtype=np.int32)
+        assert self.b.shape == (self.p,) and self.mu.shape == (self.p,) and self.groups.shape == (self.p,)
+        self.unrelated = np.arange(self.N, dtype=np.int32) if unrelated is None else np.ascontiguousarray(unrelated, dtype=np.int32)
+        self.seed = int(seed)
+        self.injected_u = None
+        if injected_u is not None:
+            self.injected_u = np.ascontiguousarray(injected_u, dtype=np.float64)
+            assert self.injected_u.shape == (self.N, 3, self.p)
+
+    def c(self) -> _Problem:
+        P = _Problem()
+        P.abi_version = KGW_ABI_VERSION
+        P.N, P.p, P.K, P.W = self.N, self.p, self.K, self.W
+        P.row_bytes = self.row_bytes
+        P.H = self.H.ctypes.data
+        P.ref_local = self.ref_local.ctypes.data
+        P.ref_global = None if self.ref_global is None else self.ref_global.ctypes.data
+        P.b, P.mu, P.groups = self.b.ctypes.data, self.mu.ctypes.data, self.groups.ctypes.data
+        P.win_start, P.win_end = self.win_start.ctypes.data, self.win_end.ctypes.data
+        P.unrelated = self.unrelated.ctypes.data
+        P.n_unrelated = len(self.unrelated)
+        P.seed = self.seed
+        P.injected_u = None if self.injected_u is None else self.injected_u.ctypes.data
+        return P
+
+
+@dataclass
+class DebugOut:
+    z: np.ndarray | None = None
+    zk: np.ndarray | None = None
+    beta_ckpt: np.ndarray | None = None
+    ckpt_locus: np.ndarray | None = None
+
+
+def _make_debug(held: _Held, want_paths: bool, want_beta: bool):
+    if not (want_paths or want_beta):
+        return None, None
+    n = len(held.unrelated)
+    out = DebugOut()
+    d = _Debug()
+    if want_paths:
+        out.z = np.zeros((n, held.p), dtype=np.int32)
+        out.zk = np.zeros((n, held.p), dtype=np.int32)
+        d.z, d.zk = out.z.ctypes.data, out.zk.ctypes.data
+    if want_beta:
+        cap = (held.p + 3) // 4
+        out.beta_ckpt = np.zeros((n, cap, held.K), dtype=np.float64)
+        out.ckpt_locus = np.full(cap, -1, dtype=np.int32)
+        d.beta_ckpt, d.ckpt_locus, d.n_ckpt = out.beta_ckpt.ctypes.data, out.ckpt_locus.ctypes.data, cap
+    return d, out
+
+
+def _finish_debug(d, out, held):
+    if out is not None and out.beta_ckpt is not None:
+        n = int(d.n_ckpt)
+        # the library wrote rows with stride n (its own nblk), re-view accordingly
+        flat = out.beta_ckpt.reshape(-1)[: len(held.unrelated) * n * held.K]
+        out.beta_ckpt = flat.reshape(len(held.unrelated), n, held.K).copy()
+        out.ckpt_locus = out.ckpt_locus[:n].copy()
+    return out
+
+
+def generate(H, p, K, ref_local, b, mu, groups, *, win_start=None, win_end=None, unrelated=None, ref_global=None,
+             seed=2020, injected_u=None, options: Options | None = None, debug_paths=False, debug_beta=False):
+    """One-shot drop-in for Knockoffs::generate() (host buffers in, host buffer out).
+    Returns (Hk uint8 [N][row_bytes], DebugOut | None)."""
+    L = load_library()
+    held = _Held(H, p, K, ref_local, b, mu, groups, win_start, win_end, unrelated, ref_global, seed, injected_u)
+    P = held.c()
+    o = (options or Options())._c()
+    hk = np.zeros_like(held.H)
+    d, out = _make_debug(held, debug_paths, debug_beta)
+    _check(L.kgw_generate(C.byref(P), C.byref(o), hk.ctypes.data, C.byref(d) if d is not None else None))
+    return hk, _finish_debug(d, out, held)
+
+
+class Plan:
+    """Resident-data plan: inputs stay in HBM across runs / partitions (kgw_plan_*)."""
+
+    def __init__(self, H, p, K, ref_local, b, mu, groups, *, win_start=None, win_end=None, unrelated=None,
+                 ref_global=None, seed=2020, injected_u=None, options: Options | None = None):
+        self._L = load_library()
+        self._held = _Held(H, p, K, ref_local, b, mu, groups, win_start, win_end, unrelated, ref_global, seed, injected_u)
+        P = self._held.c()
+        o = (options or Options())._c()
+        self._h = C.c_void_p()
+        _check(self._L.kgw_plan_create(C.byref(P), C.byref(o), C.byref(self._h)))
+
+    def set_groups(self, groups):
+        g = np.ascontiguousarray(groups, dtype=np.int32)
+        assert g.shape == (self._held.p,)
+        self._held.groups = g
+        _check(self._L.kgw_plan_set_groups(self._h, g.ctypes.data))
+
+    def run(self):
+        _check(self._L.kgw_plan_run(self._h))
+
+    def run_timed(self, iters=1) -> float:
+        ms = C.c_float()
+        _check(self._L.kgw_plan_run_timed(self._h, int(iters), C.byref(ms)))
+        return float(ms.value)
+
+    def sync(self):
+        _check(self._L.kgw_plan_sync(self._h))
+
+    def download(self, debug_paths=False, debug_beta=False, out=None):
+        hk = np.zeros_like(self._held.H) if out is None else out
+        d, dbg = _make_debug(self._held, debug_paths, debug_beta)
+        _check(self._L.kgw_plan_download(self._h, hk.ctypes.data, C.byref(d) if d is not None else None))
+        return hk, _finish_debug(d, dbg, self._held)
+
+    def device_hk_ptr(self) -> int:
+        return int(self._L.kgw_plan_device_hk(self._h) or 0)
+
+    def info(self) -> dict:
+        a = [C.c_int32() for _ in range(3)]
+        sb = C.c_int64()
+        l, s = C.c_int32(), C.c_int32()
+        _check(self._L.kgw_plan_info(self._h, C.byref(a[0]), C.byref(a[1]), C.byref(a[2]), C.byref(sb), C.byref(l), C.byref(s)))
+        return dict(launches_per_run=a[0].value, grid=a[1].value, block=a[2].value, scratch_bytes=sb.value,
+                    lanes_per_hap=l.value, states_per_lane=s.value)
+
+    def close(self):
+        if self._h:
+            self._L.kgw_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Knockoffs:
+    """Host-side mirror of the reference's `Knockoffs` object for the hot path
+    (snpknock2/src/knockoffs.h:22-68): same method names and argument meaning; `generate()`
+    is the call that runs on the B200.  Everything else stays cheap host logic."""
+
+    def __init__(self, H_packed, num_snps, K, seed=2020, genetic_dist=None, partitions=None,
+                 win_start=None, win_end=None, unrelated=None, options: Options | None = None):
+        self.H = np.ascontiguousarray(H_packed, dtype=np.uint8)
+        self.num_haps, self.num_snps, self.K, self.seed = self.H.shape[0], int(num_snps), int(K), int(seed)
+        self.genetic_dist = None if genetic_dist is None else np.asarray(genetic_dist, dtype=np.float64)
+        self.partitions = partitions
+        self.win_start = [0] if win_start is None else list(win_start)
+        self.win_end = [self.num_snps] if win_end is None else list(win_end)
+        self.num_windows = len(self.win_start)
+        self.unrelated = unrelated
+        self.options = options
+        self.references_local = None
+        self.references_global = None
+        self.b = self.mut_rates = self.rec_rates = None
+        self.groups = np.arange(self.num_snps, dtype=np.int32)
+        self.Hk = None
+        if partitions is not None:
+            self.set_partition(0)
+        if self.genetic_dist is not None:
+            self.init_hmm(self.K, 1.0, 1.0e-4)  # knockoffs.cpp:60 (constructor default)
+
+    def set_references(self, references_local):
+        """knockoffs.cpp:109-126: each K-list is sorted ascending."""
+        r = np.asarray(references_local, dtype=np.int32).reshape(self.num_haps, self.num_windows, self.K)
+        self.references_local = np.sort(r, axis=2)
+
+    def set_references_global(self, references_global):
+        r = np.asarray(references_global, dtype=np.int32).reshape(self.num_haps, self.K)
+        self.references_global = np.sort(r, axis=1)
+
+    def init_hmm(self, K, rho, lam):
+        """knockoffs.cpp:1508-1525: b_j = exp(-rho d_j), b_0 = 0, mu_j = lambda."""
+        assert self.genetic_dist is not None
+        self.rec_rates = np.ones(self.num_snps)
+        self.rec_rates[1:] = rho * self.genetic_dist[1:]
+        self.b = np.zeros(self.num_snps)
+        self.b[1:] = np.exp(-self.rec_rates[1:])
+        self.mut_rates = np.full(self.num_snps, float(lam))
+
+    def load_hmm(self, rec_rates, mut_rates):
+        """knockoffs.cpp:1593-1610: b_j = exp(-rec_j) for every j; mu clamped to [1e-6, 1e-3]."""
+        self.rec_rates = np.asarray(rec_rates, dtype=np.float64).copy()
+        self.b = np.exp(-self.rec_rates)
+        self.mut_rates = np.maximum(1e-6, np.minimum(np.asarray(mut_rates, dtype=np.float64), 1e-3))
+
+    def set_partition(self, r):
+        self.set_groups(self.partitions[r])
+
+    def set_groups(self, groups):
+        self.groups = np.ascontiguousarray(groups, dtype=np.int32)
+
+    def num_groups(self):
+        return int(self.groups[-1]) + 1
+
+    def generate(self, num_threads=1):
+        """Knockoffs::generate (knockoffs.cpp:311).  num_threads is accepted for signature parity
+        and ignored: the result no longer depends on it."""
+        assert self.references_local is not None and self.b is not None
+        self.Hk, _ = generate(self.H, self.num_snps, self.K, self.references_local, self.b, self.mut_rates,
+                              self.groups, win_start=self.win_start, win_end=self.win_end, unrelated=self.unrelated,
+                              ref_global=self.references_global, seed=self.seed, options=self.options)
+        return self.Hk

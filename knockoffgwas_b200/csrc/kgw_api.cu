@@ -1,0 +1,552 @@
+// knockoffgwas_b200/csrc/kgw_api.cu -- extern "C" launch layer (include/kgw.h).
+//
+// Replaces the body of Knockoffs::generate() (snpknock2/src/knockoffs.cpp:311-327) for the
+// unrelated branch: flat host buffers in, per-locus tables built on the host in the reference's
+// own evaluation order, kernels of kgw_device.cuh, packed Hk out.  There is NO CPU fallback:
+// without an sm_100 device every compute entry point returns KGW_ERR_CUDA.
+#include "../../include/kgw.h"
+#include "kgw_device.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define KGW_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+  } while (0)
+
+typedef void (*kernel_fn)(const KgwParams);
+
+struct KernelVariant {
+  int L, S, threads;
+  kernel_fn fn;
+  size_t (*smem)(int B, int threads);
+};
+
+template <int L, int S>
+size_t smem_bytes(int B, int threads) {
+  return kgw::Smem<L, S>::bytes(B) * (size_t)(threads / L);
+}
+
+constexpr int THREADS = 128;
+#define KGW_VARIANT(L, S) \
+  { L, S, THREADS, kgw::unrelated_kernel<L, S, THREADS, 1>, smem_bytes<L, S> }
+
+// (lanes per haplotype, states per lane): K <= L*S.  Default family L=8.
+const KernelVariant g_variants[] = {
+    KGW_VARIANT(8, 2),  KGW_VARIANT(8, 4),  KGW_VARIANT(8, 7),  KGW_VARIANT(8, 8),
+    KGW_VARIANT(8, 13), KGW_VARIANT(8, 16), KGW_VARIANT(4, 13), KGW_VARIANT(16, 16),
+};
+
+const KernelVariant *pick_variant(int K, int lanes) {
+  const KernelVariant *best = nullptr;
+  for (const KernelVariant &v : g_variants) {
+    if (v.L * v.S < K) continue;
+    if (lanes > 0 && v.L != lanes) continue;
+    if (lanes <= 0 && v.L != 8 && K <= 128) continue;  // default family
+    if (!best || v.L * v.S < best->L * best->S) best = &v;
+  }
+  return best;
+}
+
+struct Tables {
+  std::vector<KgwLocusHMM> hmm;
+  std::vector<KgwLocusKO> ko;
+  std::vector<KgwEmit> emit;
+  std::vector<KgwPass> passes;
+};
+
+// Per-locus tables, every formula in the reference's left-to-right evaluation order
+// (compiled with -ffp-contract=off).
+int build_tables(int p, int K, int W, const double *b, const double *mu, const int32_t *groups,
+                 const int32_t *win_start, const int32_t *win_end, Tables &T, bool hmm_too) {
+  const double alpha = 1.0 / K;  // knockoffs.cpp:75
+  if (hmm_too) {
+    T.hmm.resize(p);
+    T.emit.resize(p);
+    for (int j = 0; j < p; j++) {
+      KgwLocusHMM &h = T.hmm[j];
+      h.omm = 1.0 - mu[j];
+      h.mu = mu[j];
+      h.mup = 1.0 - (1.0 - mu[j]);
+      h.a = (1.0 - b[j]) * alpha;
+      h.b = b[j];
+      h.pad = 0.0;
+      // sample_emission_copula, lambda = 0.5 (knockoffs.cpp:1469-1502, call site :677)
+      const double lambda = 0.5;
+      for (int c = 0; c < 8; c++) {
+        const int hbit = c & 1, rz = (c >> 1) & 1, rzk = (c >> 2) & 1;
+        const double p_orig1 = rz ? (1.0 - mu[j]) : mu[j];
+        const double p_ko1 = rzk ? (1.0 - mu[j]) : mu[j];
+        double temp = p_orig1 - (1.0 - p_ko1);
+        double temp2 = 0.0;
+        if (temp < 0) { temp2 = -temp; temp = 0.0; }
+        double w0, w1;
+        if (hbit == 0) {
+          w1 = 1.0 - temp2 / (1.0 - p_orig1);
+          w0 = temp2 / (1.0 - p_orig1);
+        } else {
+          w1 = temp / (p_orig1);
+          w0 = 1.0 - temp / (p_orig1);
+        }
+        w0 = lambda * w0 + (1 - lambda) * (1 - p_ko1);
+        w1 = lambda * w1 + (1 - lambda) * p_ko1;
+        double sum = 0.0;
+        sum += w0;
+        sum += w1;  // std::accumulate(w.begin(), w.end(), 0.0), utils.cpp:691
+        T.emit[j].w0[c] = w0;
+        T.emit[j].sum[c] = sum;
+      }
+    }
+  }
+  // groups -> first/last locus (set_groups, knockoffs.cpp:96-107)
+  if (groups[0] != 0) return fail(KGW_ERR_INVALID, "groups[0] must be 0");
+  const int G = groups[p - 1] + 1;
+  std::vector<int> gfirst(G, -1), glast(G, -1);
+  for (int j = 0; j < p; j++) {
+    const int g = groups[j];
+    if (g < 0 || g >= G || (j > 0 && (g < groups[j - 1] || g > groups[j - 1] + 1)))
+      return fail(KGW_ERR_INVALID, "groups must be contiguous, non-decreasing and dense");
+    if (gfirst[g] < 0) gfirst[g] = j;
+    glast[g] = j;
+  }
+  T.passes.clear();
+  T.ko.clear();
+  std::vector<double> vstar, vbar;
+  for (int w = 0; w < W; w++) {
+    KgwPass ps;
+    ps.js = (w > 0) ? win_start[w - 1] : win_start[w];       // knockoffs.cpp:1222-1226
+    ps.je = (w < W - 1) ? win_end[w + 1] : win_end[w];
+    ps.cs = win_start[w];
+    ps.ce = win_end[w];
+    ps.w = w;
+    ps.ko_off = (int)T.ko.size();
+    ps.pad0 = ps.pad1 = 0;
+    if (ps.js < 0 || ps.je > p || ps.js >= ps.je || ps.cs < ps.js || ps.ce > ps.je || ps.cs >= ps.ce)
+      return fail(KGW_ERR_INVALID, "inconsistent window boundaries");
+    const int g_start = groups[ps.js], g_end = groups[ps.je - 1] + 1;  // :1282-1283
+    if (gfirst[g_start] != ps.js || glast[g_end - 1] != ps.je - 1)
+      return fail(KGW_ERR_UNSUPPORTED,
+                  "a variant group straddles a window boundary (the reference defines windows at "
+                  "boundaries of the coarsest partition, metadata.cpp:86-108)");
+    T.ko.resize(T.ko.size() + (size_t)(ps.je - ps.js));
+    for (int g = g_start; g < g_end; g++) {
+      const int e0 = gfirst[g];
+      const int m = glast[g] - e0 + 1;
+      vstar.assign(m, 0.0);
+      vbar.assign(m, 0.0);
+      for (int t = m - 1; t >= 0; t--) {  // :1298-1313
+        if (t < m - 1) vstar[t] = vstar[t + 1] * b[e0 + t + 1];
+        else vstar[t] = (g < g_end - 1) ? b[e0] : 0.0;
+      }
+      for (int t = m - 1; t >= 0; t--) {  // :1315-1339
+        double sum_a = 0;
+        if (t < m - 1) {
+          for (int l = 0; l < K; l++) sum_a += (1.0 - b[e0 + t + 1]) * alpha;
+          vbar[t] = vbar[t + 1] * (sum_a + b[e0 + t + 1]);
+          vbar[t] += vstar[t + 1] * (1.0 - b[e0 + t + 1]) * alpha;
+        } else {
+          vbar[t] = (g < g_end - 1) ? (1.0 - b[gfirst[g + 1]]) * alpha : 1.0;
+        }
+      }
+      for (int t = 0; t < m; t++) {
+        const int j = e0 + t;
+        KgwLocusKO &k = T.ko[(size_t)ps.ko_off + (j - ps.js)];
+        memset(&k, 0, sizeof(k));
+        k.vs = vstar[t];
+        k.vb = vbar[t];
+        k.a = (1.0 - b[j]) * alpha;
+        k.apb = (1.0 - b[j]) * alpha + b[j] * 1.0;
+        k.aa = k.a * k.a;
+        k.ab = k.apb * k.a;
+        k.bb = k.apb * k.apb;
+        double sa = 0;
+        for (int l = 0; l < K; l++) sa += (1.0 - b[j]) * alpha;  // :1348-1349
+        k.sa = sa;
+        k.g0 = vstar[0] * (1.0 - b[j]) * alpha;                  // :1364 (only read when t == 0)
+        k.flags = (t == 0 ? KGW_KO_FIRST : 0) | (g == g_end - 1 ? KGW_KO_LASTGRP : 0) |
+                  (g == 0 ? KGW_KO_GZERO : 0) | (g == g_start ? KGW_KO_GSTART : 0) |
+                  (t == m - 1 ? KGW_KO_LASTINGRP : 0);
+        k.z1_idx = (g < g_end - 1) ? gfirst[g + 1] : -1;
+        k.z1_next = (g + 1 < g_end - 1) ? gfirst[g + 2] : -1;
+      }
+    }
+    T.passes.push_back(ps);
+  }
+  return KGW_OK;
+}
+
+}  // namespace
+
+struct kgw_plan {
+  int device = 0;
+  int N = 0, p = 0, K = 0, W = 0, n_haps = 0;
+  int64_t row_bytes = 0;
+  int stride_w = 0;
+  int B = 8, nblk = 0;
+  const KernelVariant *var = nullptr;
+  int grid = 0;
+  size_t smem = 0;
+  size_t scratch_bytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<double> b, mu;
+  std::vector<int32_t> win_start, win_end;
+  // device buffers
+  uint32_t *dHw = nullptr, *dHk = nullptr;
+  int32_t *dref = nullptr, *dhaps = nullptr;
+  KgwLocusHMM *dhmm = nullptr;
+  KgwLocusKO *dko = nullptr;
+  KgwEmit *demit = nullptr;
+  KgwPass *dpass = nullptr;
+  double *dckpt = nullptr, *dinj = nullptr;
+  uint8_t *dz = nullptr, *dzk = nullptr;
+  int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
+  double *ddbg_beta = nullptr;
+  size_t ko_capacity = 0;
+  KgwParams P{};
+  std::vector<int32_t> haps;
+
+  ~kgw_plan() {
+    cudaSetDevice(device);
+    cudaFree(dHw); cudaFree(dHk); cudaFree(dref); cudaFree(dhaps); cudaFree(dhmm); cudaFree(dko);
+    cudaFree(demit); cudaFree(dpass); cudaFree(dckpt); cudaFree(dinj); cudaFree(dz); cudaFree(dzk);
+    cudaFree(ddbg_z); cudaFree(ddbg_zk); cudaFree(ddbg_beta);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int upload_partition(kgw_plan *pl, const int32_t *groups, bool hmm_too) {
+  Tables T;
+  int rc = build_tables(pl->p, pl->K, pl->W, pl->b.data(), pl->mu.data(), groups, pl->win_start.data(),
+                        pl->win_end.data(), T, hmm_too);
+  if (rc != KGW_OK) return rc;
+  if (hmm_too) {
+    KGW_CUDA(cudaMalloc(&pl->dhmm, sizeof(KgwLocusHMM) * pl->p));
+    KGW_CUDA(cudaMalloc(&pl->demit, sizeof(KgwEmit) * pl->p));
+    KGW_CUDA(cudaMemcpyAsync(pl->dhmm, T.hmm.data(), sizeof(KgwLocusHMM) * pl->p, cudaMemcpyHostToDevice, pl->stream));
+    KGW_CUDA(cudaMemcpyAsync(pl->demit, T.emit.data(), sizeof(KgwEmit) * pl->p, cudaMemcpyHostToDevice, pl->stream));
+    KGW_CUDA(cudaMalloc(&pl->dpass, sizeof(KgwPass) * pl->W));
+  }
+  if (T.ko.size() > pl->ko_capacity) {
+    KGW_CUDA(cudaStreamSynchronize(pl->stream));
+    cudaFree(pl->dko);
+    pl->dko = nullptr;
+    KGW_CUDA(cudaMalloc(&pl->dko, sizeof(KgwLocusKO) * T.ko.size()));
+    pl->ko_capacity = T.ko.size();
+  }
+  KGW_CUDA(cudaMemcpyAsync(pl->dko, T.ko.data(), sizeof(KgwLocusKO) * T.ko.size(), cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA(cudaMemcpyAsync(pl->dpass, T.passes.data(), sizeof(KgwPass) * T.passes.size(), cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA(cudaStreamSynchronize(pl->stream));  // T goes out of scope
+  pl->P.hmm = pl->dhmm;
+  pl->P.emit = pl->demit;
+  pl->P.ko = pl->dko;
+  pl->P.passes = pl->dpass;
+  pl->P.n_passes = (int)T.passes.size();
+  return KGW_OK;
+}
+
+int launch(kgw_plan *pl) {
+  if (pl->n_haps == 0) return KGW_OK;
+  pl->var->fn<<<pl->grid, pl->var->threads, pl->smem, pl->stream>>>(pl->P);
+  KGW_CUDA(cudaGetLastError());
+  return KGW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t kgw_abi_version(void) { return KGW_ABI_VERSION; }
+const char *kgw_last_error(void) { return g_err.c_str(); }
+
+double kgw_uniform(uint64_t seed, uint32_t hap, uint32_t stream, uint32_t locus) {
+  const kgw_u32x4 r = kgw_philox_block(seed, hap, stream, locus >> 2);
+  const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+  return kgw_word_to_uniform(w4[locus & 3u]);
+}
+
+int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_plan **plan_out) {
+  if (!prob || !plan_out) return fail(KGW_ERR_INVALID, "null argument");
+  *plan_out = nullptr;
+  if (prob->abi_version != KGW_ABI_VERSION) return fail(KGW_ERR_INVALID, "abi_version mismatch");
+  const int N = prob->N, p = prob->p, K = prob->K, W = prob->W;
+  if (N <= 0 || p <= 0 || K <= 0 || W <= 0) return fail(KGW_ERR_INVALID, "N, p, K, W must be positive");
+  if (prob->row_bytes < (p + 7) / 8) return fail(KGW_ERR_INVALID, "row_bytes < ceil(p/8)");
+  if (!prob->H || !prob->ref_local || !prob->b || !prob->mu || !prob->groups || !prob->win_start || !prob->win_end)
+    return fail(KGW_ERR_INVALID, "null input buffer");
+  if (prob->n_unrelated < 0 || (prob->n_unrelated > 0 && !prob->unrelated))
+    return fail(KGW_ERR_INVALID, "bad unrelated list");
+  if (prob->injected_u && W != 1) return fail(KGW_ERR_UNSUPPORTED, "injected uniforms are defined for a single window only");
+  if (K > 256) return fail(KGW_ERR_UNSUPPORTED, "K > 256 is not built (latent states are stored as bytes)");
+  kgw_options o{};
+  if (opt) o = *opt;
+  const KernelVariant *var = pick_variant(K, o.lanes_per_hap);
+  if (!var) return fail(KGW_ERR_UNSUPPORTED, "no kernel variant for this K / lanes_per_hap");
+  int B = o.block_loci > 0 ? o.block_loci : 8;
+  if (B != 4 && B != 8 && B != 16 && B != 32) return fail(KGW_ERR_INVALID, "block_loci must be 4, 8, 16 or 32");
+  for (int i = 0; i < prob->n_unrelated; i++) {
+    if (prob->unrelated[i] < 0 || prob->unrelated[i] >= N) return fail(KGW_ERR_INVALID, "unrelated index out of range");
+  }
+  for (size_t t = 0; t < (size_t)N * W * K; t++) {
+    if (prob->ref_local[t] < 0 || prob->ref_local[t] >= N) return fail(KGW_ERR_INVALID, "reference index out of range");
+  }
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(KGW_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (o.device < 0 || o.device >= ndev) return fail(KGW_ERR_INVALID, "bad device ordinal");
+  KGW_CUDA(cudaSetDevice(o.device));
+  cudaDeviceProp dp;
+  KGW_CUDA(cudaGetDeviceProperties(&dp, o.device));
+  if (dp.major != 10) return fail(KGW_ERR_CUDA, "kernels are built for sm_100a only (found sm_" + std::to_string(dp.major) + std::to_string(dp.minor) + ")");
+
+  kgw_plan *pl = new kgw_plan();
+  pl->device = o.device;
+  pl->N = N; pl->p = p; pl->K = K; pl->W = W;
+  pl->n_haps = prob->n_unrelated;
+  pl->row_bytes = prob->row_bytes;
+  pl->stride_w = (int)(((size_t)prob->row_bytes + 15) / 16 * 4);  // rows padded to 16 B
+  pl->B = B;
+  pl->nblk = (p + B - 1) / B;
+  pl->var = var;
+  pl->b.assign(prob->b, prob->b + p);
+  pl->mu.assign(prob->mu, prob->mu + p);
+  pl->win_start.assign(prob->win_start, prob->win_start + W);
+  pl->win_end.assign(prob->win_end, prob->win_end + W);
+  pl->haps.assign(prob->unrelated, prob->unrelated + prob->n_unrelated);
+
+  auto guard_fail = [&](int rc) { delete pl; return rc; };
+#define KGW_CUDA_PL(call)                                                                                  \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess) return guard_fail(fail(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
+  } while (0)
+
+  KGW_CUDA_PL(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  KGW_CUDA_PL(cudaEventCreate(&pl->ev0));
+  KGW_CUDA_PL(cudaEventCreate(&pl->ev1));
+
+  // occupancy-driven persistent grid
+  pl->smem = var->smem(B, var->threads);
+  KGW_CUDA_PL(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  int occ = 0;
+  KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, var->threads, pl->smem));
+  if (occ <= 0) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
+  if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
+  const int gpc = var->threads / var->L;
+  const int max_grid = occ * dp.multiProcessorCount;
+  const long long max_slots = (long long)max_grid * gpc;
+  const long long rounds = std::max(1LL, (pl->n_haps + max_slots - 1) / max_slots);
+  const long long per_round = (pl->n_haps + rounds - 1) / rounds;
+  pl->grid = (int)std::max(1LL, std::min((long long)max_grid, (per_round + gpc - 1) / gpc));
+  const size_t slots = (size_t)pl->grid * gpc;
+
+  // inputs
+  const size_t hw_bytes = (size_t)N * pl->stride_w * 4;
+  KGW_CUDA_PL(cudaMalloc(&pl->dHw, hw_bytes));
+  KGW_CUDA_PL(cudaMalloc(&pl->dHk, hw_bytes));
+  KGW_CUDA_PL(cudaMemsetAsync(pl->dHw, 0, hw_bytes, pl->stream));
+  KGW_CUDA_PL(cudaMemsetAsync(pl->dHk, 0, hw_bytes, pl->stream));
+  KGW_CUDA_PL(cudaMemcpy2DAsync(pl->dHw, (size_t)pl->stride_w * 4, prob->H, (size_t)prob->row_bytes,
+                                (size_t)(p + 7) / 8, N, cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA_PL(cudaMalloc(&pl->dref, sizeof(int32_t) * (size_t)N * W * K));
+  KGW_CUDA_PL(cudaMemcpyAsync(pl->dref, prob->ref_local, sizeof(int32_t) * (size_t)N * W * K, cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA_PL(cudaMalloc(&pl->dhaps, sizeof(int32_t) * std::max(1, pl->n_haps)));
+  if (pl->n_haps)
+    KGW_CUDA_PL(cudaMemcpyAsync(pl->dhaps, pl->haps.data(), sizeof(int32_t) * pl->n_haps, cudaMemcpyHostToDevice, pl->stream));
+  if (prob->injected_u) {
+    const size_t ub = sizeof(double) * (size_t)N * 3 * p;
+    KGW_CUDA_PL(cudaMalloc(&pl->dinj, ub));
+    KGW_CUDA_PL(cudaMemcpyAsync(pl->dinj, prob->injected_u, ub, cudaMemcpyHostToDevice, pl->stream));
+  }
+  // scratch: checkpoints + latent paths, one slot per resident haplotype group
+  const size_t ckpt_stride = (size_t)pl->nblk * var->S * var->L;
+  const size_t z_stride = ((size_t)p + 63) / 64 * 64;
+  KGW_CUDA_PL(cudaMalloc(&pl->dckpt, sizeof(double) * ckpt_stride * slots));
+  KGW_CUDA_PL(cudaMalloc(&pl->dz, z_stride * slots));
+  KGW_CUDA_PL(cudaMalloc(&pl->dzk, z_stride * slots));
+  KGW_CUDA_PL(cudaMemsetAsync(pl->dz, 0, z_stride * slots, pl->stream));
+  KGW_CUDA_PL(cudaMemsetAsync(pl->dzk, 0, z_stride * slots, pl->stream));
+  pl->scratch_bytes = sizeof(double) * ckpt_stride * slots + 2 * z_stride * slots;
+
+  KgwParams &P = pl->P;
+  P.N = N; P.p = p; P.K = K; P.W = W;
+  P.n_haps = pl->n_haps;
+  P.stride_w = pl->stride_w;
+  P.B = B;
+  P.Hw = pl->dHw;
+  P.ref_local = pl->dref;
+  P.haps = pl->dhaps;
+  P.Hk = pl->dHk;
+  P.ckpt = pl->dckpt;
+  P.ckpt_stride = ckpt_stride;
+  P.zbuf = pl->dz;
+  P.zkbuf = pl->dzk;
+  P.z_stride = z_stride;
+  P.seed = prob->seed;
+  P.injected_u = pl->dinj;
+  P.dbg_z = P.dbg_zk = nullptr;
+  P.dbg_beta = nullptr;
+  P.dbg_nblk = 0;
+
+  int rc = upload_partition(pl, prob->groups, true);
+  if (rc != KGW_OK) return guard_fail(rc);
+  KGW_CUDA_PL(cudaStreamSynchronize(pl->stream));
+  *plan_out = pl;
+  return KGW_OK;
+}
+
+int32_t kgw_plan_set_groups(kgw_plan *pl, const int32_t *groups) {
+  if (!pl || !groups) return fail(KGW_ERR_INVALID, "null argument");
+  KGW_CUDA(cudaSetDevice(pl->device));
+  return upload_partition(pl, groups, false);
+}
+
+int32_t kgw_plan_run(kgw_plan *pl) {
+  if (!pl) return fail(KGW_ERR_INVALID, "null plan");
+  KGW_CUDA(cudaSetDevice(pl->device));
+  return launch(pl);
+}
+
+int32_t kgw_plan_run_timed(kgw_plan *pl, int32_t iters, float *ms_out) {
+  if (!pl || iters <= 0 || !ms_out) return fail(KGW_ERR_INVALID, "bad argument");
+  KGW_CUDA(cudaSetDevice(pl->device));
+  KGW_CUDA(cudaStreamSynchronize(pl->stream));
+  KGW_CUDA(cudaEventRecord(pl->ev0, pl->stream));
+  for (int i = 0; i < iters; i++) {
+    int rc = launch(pl);
+    if (rc != KGW_OK) return rc;
+  }
+  KGW_CUDA(cudaEventRecord(pl->ev1, pl->stream));
+  KGW_CUDA(cudaEventSynchronize(pl->ev1));
+  float ms = 0.f;
+  KGW_CUDA(cudaEventElapsedTime(&ms, pl->ev0, pl->ev1));
+  *ms_out = ms / iters;
+  return KGW_OK;
+}
+
+int32_t kgw_plan_sync(kgw_plan *pl) {
+  if (!pl) return fail(KGW_ERR_INVALID, "null plan");
+  KGW_CUDA(cudaSetDevice(pl->device));
+  KGW_CUDA(cudaStreamSynchronize(pl->stream));
+  return KGW_OK;
+}
+
+void *kgw_plan_device_hk(kgw_plan *pl) { return pl ? (void *)pl->dHk : nullptr; }
+
+int32_t kgw_plan_info(kgw_plan *pl, int32_t *launches_per_run, int32_t *grid, int32_t *block, int64_t *scratch_bytes,
+                      int32_t *lanes_per_hap, int32_t *states_per_lane) {
+  if (!pl) return fail(KGW_ERR_INVALID, "null plan");
+  if (launches_per_run) *launches_per_run = pl->n_haps > 0 ? 1 : 0;
+  if (grid) *grid = pl->grid;
+  if (block) *block = pl->var->threads;
+  if (scratch_bytes) *scratch_bytes = (int64_t)pl->scratch_bytes;
+  if (lanes_per_hap) *lanes_per_hap = pl->var->L;
+  if (states_per_lane) *states_per_lane = pl->var->S;
+  return KGW_OK;
+}
+
+// debug outputs are produced by one extra run with the debug pointers set
+static int run_debug(kgw_plan *pl, kgw_debug *dbg) {
+  const size_t np = (size_t)pl->n_haps * pl->p;
+  if (dbg->z) KGW_CUDA(cudaMalloc(&pl->ddbg_z, sizeof(int32_t) * std::max<size_t>(np, 1)));
+  if (dbg->zk) KGW_CUDA(cudaMalloc(&pl->ddbg_zk, sizeof(int32_t) * std::max<size_t>(np, 1)));
+  int nck = 0;
+  if (dbg->beta_ckpt) {
+    nck = std::min(dbg->n_ckpt, pl->nblk);
+    KGW_CUDA(cudaMalloc(&pl->ddbg_beta, sizeof(double) * std::max<size_t>((size_t)pl->n_haps * nck * pl->K, 1)));
+    KGW_CUDA(cudaMemsetAsync(pl->ddbg_beta, 0, sizeof(double) * (size_t)pl->n_haps * nck * pl->K, pl->stream));
+  }
+  pl->P.dbg_z = pl->ddbg_z;
+  pl->P.dbg_zk = pl->ddbg_zk;
+  pl->P.dbg_beta = pl->ddbg_beta;
+  pl->P.dbg_nblk = nck;
+  int rc = launch(pl);
+  pl->P.dbg_z = pl->P.dbg_zk = nullptr;
+  pl->P.dbg_beta = nullptr;
+  pl->P.dbg_nblk = 0;
+  if (rc != KGW_OK) return rc;
+  KGW_CUDA(cudaStreamSynchronize(pl->stream));
+  if (dbg->z) KGW_CUDA(cudaMemcpy(dbg->z, pl->ddbg_z, sizeof(int32_t) * np, cudaMemcpyDeviceToHost));
+  if (dbg->zk) KGW_CUDA(cudaMemcpy(dbg->zk, pl->ddbg_zk, sizeof(int32_t) * np, cudaMemcpyDeviceToHost));
+  if (dbg->beta_ckpt) {
+    KGW_CUDA(cudaMemcpy(dbg->beta_ckpt, pl->ddbg_beta, sizeof(double) * (size_t)pl->n_haps * nck * pl->K, cudaMemcpyDeviceToHost));
+    // checkpoint n of the last pass holds beta at locus min((n+1)*B, je) - 1 (js..je = last pass's padded range)
+    const int W = pl->W;
+    const int js = (W > 1) ? pl->win_start[W - 2] : pl->win_start[W - 1];
+    const int je = pl->win_end[W - 1];
+    if (dbg->ckpt_locus) {
+      for (int n = 0; n < nck; n++) {
+        const int top = std::min((n + 1) * pl->B, je) - 1;
+        dbg->ckpt_locus[n] = (n >= js / pl->B && top >= js) ? top : -1;
+      }
+    }
+  }
+  dbg->n_ckpt = nck;
+  cudaFree(pl->ddbg_z); pl->ddbg_z = nullptr;
+  cudaFree(pl->ddbg_zk); pl->ddbg_zk = nullptr;
+  cudaFree(pl->ddbg_beta); pl->ddbg_beta = nullptr;
+  return KGW_OK;
+}
+
+int32_t kgw_plan_download(kgw_plan *pl, uint8_t *hk_out, kgw_debug *dbg) {
+  if (!pl) return fail(KGW_ERR_INVALID, "null plan");
+  KGW_CUDA(cudaSetDevice(pl->device));
+  if (dbg && (dbg->z || dbg->zk || dbg->beta_ckpt)) {
+    int rc = run_debug(pl, dbg);
+    if (rc != KGW_OK) return rc;
+  }
+  KGW_CUDA(cudaStreamSynchronize(pl->stream));
+  if (hk_out && pl->n_haps > 0) {
+    // only the rows of the processed haplotypes are written back (generate_unrelated touches only those)
+    const size_t rb = (size_t)(pl->p + 7) / 8;
+    bool contiguous = true;
+    for (int i = 1; i < pl->n_haps; i++)
+      if (pl->haps[i] != pl->haps[i - 1] + 1) { contiguous = false; break; }
+    if (contiguous) {
+      const int h0 = pl->haps[0];
+      KGW_CUDA(cudaMemcpy2D(hk_out + (size_t)h0 * pl->row_bytes, (size_t)pl->row_bytes,
+                            pl->dHk + (size_t)h0 * pl->stride_w, (size_t)pl->stride_w * 4, rb, pl->n_haps,
+                            cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<uint8_t> tmp((size_t)pl->N * rb);
+      KGW_CUDA(cudaMemcpy2D(tmp.data(), rb, pl->dHk, (size_t)pl->stride_w * 4, rb, pl->N, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < pl->n_haps; i++)
+        memcpy(hk_out + (size_t)pl->haps[i] * pl->row_bytes, tmp.data() + (size_t)pl->haps[i] * rb, rb);
+    }
+  }
+  return KGW_OK;
+}
+
+void kgw_plan_destroy(kgw_plan *pl) { delete pl; }
+
+int32_t kgw_generate(const kgw_problem *prob, const kgw_options *opt, uint8_t *hk_out, kgw_debug *dbg) {
+  kgw_plan *pl = nullptr;
+  int rc = kgw_plan_create(prob, opt, &pl);
+  if (rc != KGW_OK) return rc;
+  rc = kgw_plan_run(pl);
+  if (rc == KGW_OK) rc = kgw_plan_download(pl, hk_out, dbg);
+  kgw_plan_destroy(pl);
+  return rc;
+}
+
+}  // extern "C"

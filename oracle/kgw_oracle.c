@@ -20,7 +20,7 @@ static inline double mutate(int h, double mut_rate) {
   return (h == 1) ? (1.0 - mut_rate) : mut_rate;
 }
 
-static double next_uniform(kgw_oracle_rng *rng, int hap, int stream, int locus, int p) {
+static double next_uniform(kgw_oracle_rng *rng, int hap, int stream, int locus, int p, int w) {
   rng->n_draws++;
   switch (rng->mode) {
     case KGW_ORACLE_RNG_INJECTED:
@@ -28,7 +28,9 @@ static double next_uniform(kgw_oracle_rng *rng, int hap, int stream, int locus, 
     case KGW_ORACLE_RNG_TAUS88:
       return kgw_taus88_uniform(&rng->taus);
     default:
-      return kgw_oracle_philox_uniform(rng->seed, (uint32_t)hap, (uint32_t)stream, (uint32_t)locus);
+      /* window pass w in the upper bits of the stream word: overlapping padded passes of
+       * knockoffs.cpp:1222-1226 never reuse a uniform (include/kgw.h) */
+      return kgw_oracle_philox_uniform(rng->seed, (uint32_t)hap, (uint32_t)stream | ((uint32_t)w << 2), (uint32_t)locus);
   }
 }
 
@@ -99,7 +101,7 @@ static void sample_posterior_MC(const kgw_oracle_problem *P, kgw_oracle_rng *rng
     if (hap_bit(P, i, js) == 1) weights[k] = a_0_k * theta_0_k * backward[(int64_t)js * K + k];
     else weights[k] = a_0_k * (1.0 - theta_0_k) * backward[(int64_t)js * K + k];
   }
-  z[js] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_Z, js, P->p));
+  z[js] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_Z, js, P->p, w));
 
   for (int j = js + 1; j < je; j++) { /* :1245-1260 */
     const double bj = P->b[j];
@@ -113,7 +115,7 @@ static void sample_posterior_MC(const kgw_oracle_problem *P, kgw_oracle_rng *rng
       else
         weights[k] = (a_j_k + bj * (double)(k == z[j - 1])) * (1.0 - theta_j_k) * backward[(int64_t)j * K + k];
     }
-    z[j] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_Z, j, P->p));
+    z[j] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_Z, j, P->p, w));
   }
 }
 
@@ -226,14 +228,14 @@ static void sample_knockoff_MC(const kgw_oracle_problem *P, kgw_oracle_rng *rng,
         }
         weights[k] = wk;
       }
-      zk[j] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_ZK, j, P->p));
+      zk[j] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_ZK, j, P->p, w));
     }
     for (int k = 0; k < K; k++) N_old[k] = N[k]; /* :1424-1426 */
   }
 }
 
 /* sample_emission_copula (knockoffs.cpp:1469-1502), lambda = 0.5 at the call site (:677) */
-static void sample_emission_copula(const kgw_oracle_problem *P, kgw_oracle_rng *rng, int i,
+static void sample_emission_copula(const kgw_oracle_problem *P, kgw_oracle_rng *rng, int i, int w,
                                    const int32_t *z, const int32_t *zk, const int32_t *ref,
                                    int32_t *out, double lambda, int j_start, int j_end) {
   double wb[2];
@@ -254,7 +256,7 @@ static void sample_emission_copula(const kgw_oracle_problem *P, kgw_oracle_rng *
     }
     wb[0] = lambda * wb[0] + (1 - lambda) * (1 - p_ko1);
     wb[1] = lambda * wb[1] + (1 - lambda) * p_ko1;
-    out[j] = kgw_oracle_weighted_choice(wb, 2, next_uniform(rng, i, KGW_STREAM_HK, j, P->p));
+    out[j] = kgw_oracle_weighted_choice(wb, 2, next_uniform(rng, i, KGW_STREAM_HK, j, P->p, w));
   }
 }
 
@@ -299,7 +301,7 @@ int kgw_oracle_unrelated(const kgw_oracle_problem *P, kgw_oracle_rng *rng, const
       const int32_t *ref = P->ref_local + ((int64_t)i * P->W + w) * K;
       sample_posterior_MC(P, rng, i, w, z, backward, weights);
       sample_knockoff_MC(P, rng, i, w, z, zk, grp_first, grp_last, weights, N, N_old, vstar, vbar);
-      sample_emission_copula(P, rng, i, z, zk, ref, hk_tmp, 0.5, P->win_start[w], P->win_end[w]);
+      sample_emission_copula(P, rng, i, w, z, zk, ref, hk_tmp, 0.5, P->win_start[w], P->win_end[w]);
       for (int j = P->win_start[w]; j < P->win_end[w]; j++) hk[j] = hk_tmp[j];
     }
     if (z_out) memcpy(z_out + (int64_t)t * p, z, sizeof(int32_t) * p);
