@@ -81,7 +81,9 @@ typedef struct kgw_options {
   int32_t block_loci;    /* 0 = default; checkpoint spacing of the backward messages          */
   int32_t lanes_per_hap; /* 0 = auto; 4, 8, 16 or 32 lanes cooperate on one haplotype         */
   int32_t ctas_per_sm;   /* 0 = auto (occupancy query)                                        */
-  int32_t reserved[4];
+  void *stream;          /* cudaStream_t to launch on (caller-owned); NULL = the plan creates
+                            its own non-blocking stream                                       */
+  int32_t reserved[2];
 } kgw_options;
 
 /* Optional debug outputs (any pointer may be NULL); rows follow `unrelated` order. */
@@ -118,9 +120,18 @@ int32_t kgw_plan_sync(kgw_plan *plan);
 int32_t kgw_plan_download(kgw_plan *plan, uint8_t *hk_out, kgw_debug *dbg);
 /* Device pointer of the packed knockoff matrix [N][row_bytes] (for NCCL gathers etc.). */
 void *kgw_plan_device_hk(kgw_plan *plan);
-/* Introspection for bench.py: kernel launches per run, resident CTAs, bytes of scratch. */
-int32_t kgw_plan_info(kgw_plan *plan, int32_t *launches_per_run, int32_t *grid, int32_t *block,
-                      int64_t *scratch_bytes, int32_t *lanes_per_hap, int32_t *states_per_lane);
+/* Introspection for bench.py. */
+typedef struct kgw_plan_info_t {
+  int32_t launches_per_run;   /* kernel launches per kgw_plan_run()                            */
+  int32_t grid, block;        /* persistent grid / CTA size of the sampler kernel              */
+  int32_t lanes_per_hap;      /* lanes cooperating on one haplotype                            */
+  int32_t states_per_lane;    /* HMM states held in registers per lane                         */
+  int32_t block_loci;         /* checkpoint spacing of the backward messages                   */
+  int64_t scratch_bytes;      /* checkpoint + latent-path scratch in HBM                       */
+  int64_t row_stride_bytes;   /* bytes between rows of the DEVICE Hk matrix (kgw_plan_device_hk) */
+  int64_t smem_bytes;         /* dynamic shared memory per CTA                                 */
+} kgw_plan_info_t;
+int32_t kgw_plan_info(kgw_plan *plan, kgw_plan_info_t *out);
 void kgw_plan_destroy(kgw_plan *plan);
 
 /* Host replay of the generator (bit-identical to the device code). */

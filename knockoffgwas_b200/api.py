@@ -39,7 +39,13 @@ class _Problem(C.Structure):
 
 class _Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("block_loci", C.c_int32), ("lanes_per_hap", C.c_int32),
-                ("ctas_per_sm", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p), ("reserved", C.c_int32 * 2)]
+
+
+class _PlanInfo(C.Structure):
+    _fields_ = [("launches_per_run", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32),
+                ("lanes_per_hap", C.c_int32), ("states_per_lane", C.c_int32), ("block_loci", C.c_int32),
+                ("scratch_bytes", C.c_int64), ("row_stride_bytes", C.c_int64), ("smem_bytes", C.c_int64)]
 
 
 class _Debug(C.Structure):
@@ -53,10 +59,12 @@ class Options:
     block_loci: int = 0
     lanes_per_hap: int = 0
     ctas_per_sm: int = 0
+    stream: int = 0   # cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); 0 = plan-owned
 
     def _c(self) -> _Options:
         o = _Options()
         o.device, o.block_loci, o.lanes_per_hap, o.ctas_per_sm = self.device, self.block_loci, self.lanes_per_hap, self.ctas_per_sm
+        o.stream = self.stream or None
         return o
 
 
@@ -94,7 +102,7 @@ def load_library():
         L.kgw_plan_device_hk.restype = C.c_void_p
         L.kgw_plan_device_hk.argtypes = [C.c_void_p]
         L.kgw_plan_info.restype = C.c_int32
-        L.kgw_plan_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3 + [C.POINTER(C.c_int64)] + [C.POINTER(C.c_int32)] * 2
+        L.kgw_plan_info.argtypes = [C.c_void_p, C.POINTER(_PlanInfo)]
         L.kgw_plan_destroy.restype = None
         L.kgw_plan_destroy.argtypes = [C.c_void_p]
         if L.kgw_abi_version() != KGW_ABI_VERSION:
@@ -211,6 +219,20 @@ def generate(H, p, K, ref_local, b, mu, groups, *, win_start=None, win_end=None,
     return hk, _finish_debug(d, out, held)
 
 
+def generate_into(H, p, K, ref_local, b, mu, groups, *, out, win_start=None, win_end=None, unrelated=None,
+                  ref_global=None, seed=2020, options: Options | None = None):
+    """kgw_generate() straight on caller buffers (no copies on the Python side when the arrays are
+    already contiguous and of the right dtype -- e.g. views of pinned torch tensors); `out` is
+    uint8 [N][row_bytes] and receives the rows listed in `unrelated`."""
+    L = load_library()
+    held = _Held(H, p, K, ref_local, b, mu, groups, win_start, win_end, unrelated, ref_global, seed, None)
+    assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == held.H.shape
+    P = held.c()
+    o = (options or Options())._c()
+    _check(L.kgw_generate(C.byref(P), C.byref(o), out.ctypes.data, None))
+    return out
+
+
 class Plan:
     """Resident-data plan: inputs stay in HBM across runs / partitions (kgw_plan_*)."""
 
@@ -250,12 +272,9 @@ class Plan:
         return int(self._L.kgw_plan_device_hk(self._h) or 0)
 
     def info(self) -> dict:
-        a = [C.c_int32() for _ in range(3)]
-        sb = C.c_int64()
-        l, s = C.c_int32(), C.c_int32()
-        _check(self._L.kgw_plan_info(self._h, C.byref(a[0]), C.byref(a[1]), C.byref(a[2]), C.byref(sb), C.byref(l), C.byref(s)))
-        return dict(launches_per_run=a[0].value, grid=a[1].value, block=a[2].value, scratch_bytes=sb.value,
-                    lanes_per_hap=l.value, states_per_lane=s.value)
+        pi = _PlanInfo()
+        _check(self._L.kgw_plan_info(self._h, C.byref(pi)))
+        return {name: int(getattr(pi, name)) for name, _ in _PlanInfo._fields_}
 
     def close(self):
         if self._h:

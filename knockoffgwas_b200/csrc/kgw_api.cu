@@ -203,6 +203,7 @@ struct kgw_plan {
   size_t smem = 0;
   size_t scratch_bytes = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<double> b, mu;
   std::vector<int32_t> win_start, win_end;
@@ -228,7 +229,7 @@ struct kgw_plan {
     cudaFree(ddbg_z); cudaFree(ddbg_zk); cudaFree(ddbg_beta);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    if (stream && own_stream) cudaStreamDestroy(stream);
   }
 };
 
@@ -341,7 +342,12 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
     if (e_ != cudaSuccess) return guard_fail(fail(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
   } while (0)
 
-  KGW_CUDA_PL(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  if (o.stream) {
+    pl->stream = (cudaStream_t)o.stream;
+  } else {
+    KGW_CUDA_PL(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    pl->own_stream = true;
+  }
   KGW_CUDA_PL(cudaEventCreate(&pl->ev0));
   KGW_CUDA_PL(cudaEventCreate(&pl->ev1));
 
@@ -453,15 +459,17 @@ int32_t kgw_plan_sync(kgw_plan *pl) {
 
 void *kgw_plan_device_hk(kgw_plan *pl) { return pl ? (void *)pl->dHk : nullptr; }
 
-int32_t kgw_plan_info(kgw_plan *pl, int32_t *launches_per_run, int32_t *grid, int32_t *block, int64_t *scratch_bytes,
-                      int32_t *lanes_per_hap, int32_t *states_per_lane) {
-  if (!pl) return fail(KGW_ERR_INVALID, "null plan");
-  if (launches_per_run) *launches_per_run = pl->n_haps > 0 ? 1 : 0;
-  if (grid) *grid = pl->grid;
-  if (block) *block = pl->var->threads;
-  if (scratch_bytes) *scratch_bytes = (int64_t)pl->scratch_bytes;
-  if (lanes_per_hap) *lanes_per_hap = pl->var->L;
-  if (states_per_lane) *states_per_lane = pl->var->S;
+int32_t kgw_plan_info(kgw_plan *pl, kgw_plan_info_t *out) {
+  if (!pl || !out) return fail(KGW_ERR_INVALID, "null argument");
+  out->launches_per_run = pl->n_haps > 0 ? 1 : 0;
+  out->grid = pl->grid;
+  out->block = pl->var->threads;
+  out->lanes_per_hap = pl->var->L;
+  out->states_per_lane = pl->var->S;
+  out->block_loci = pl->B;
+  out->scratch_bytes = (int64_t)pl->scratch_bytes;
+  out->row_stride_bytes = (int64_t)pl->stride_w * 4;
+  out->smem_bytes = (int64_t)pl->smem;
   return KGW_OK;
 }
 

@@ -1,0 +1,93 @@
+"""Deterministic synthetic inputs for the hot path: Li-Stephens mosaic
+haplotypes, in-block sorted reference lists, HMM tables as `init_hmm(rho, lambda)` builds them
+(snpknock2/src/knockoffs.cpp:1508-1525) and contiguous variant groups.  Used by bench.py and
+the tests; nothing here touches the device."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class SynthProblem:
+    H: np.ndarray            # uint8 [N][row_bytes], chaplotype layout (LSB-first, chaplotype.h:25)
+    p: int
+    K: int
+    ref: np.ndarray          # int32 [N][K], sorted ascending (knockoffs.cpp:116,140)
+    b: np.ndarray            # float64 [p]
+    mu: np.ndarray           # float64 [p]
+    groups: np.ndarray       # int32 [p]
+    cm: np.ndarray           # float64 [p] cumulative genetic position (> 0)
+    bp: np.ndarray           # int64 [p] strictly increasing physical position
+    seed: int = 2020
+    families: list = field(default_factory=list)
+    segments: list = field(default_factory=list)
+
+    @property
+    def N(self) -> int:
+        return int(self.H.shape[0])
+
+
+def make_groups(p: int, mean_group: float, rng) -> np.ndarray:
+    """Contiguous groups with geometric sizes of the given mean (1 = singletons)."""
+    if mean_group <= 1.0:
+        return np.arange(p, dtype=np.int32)
+    cuts = rng.random(p) < 1.0 / mean_group
+    cuts[0] = False
+    return np.cumsum(cuts).astype(np.int32)
+
+
+def make_references(N: int, K: int, rng, block: int = 5000) -> np.ndarray:
+    """K distinct non-self indices inside the haplotype's block of `block` consecutive
+    haplotypes (mimics --cluster_size_max), sorted ascending."""
+    ref = np.empty((N, K), dtype=np.int32)
+    for b0 in range(0, N, block):
+        b1 = min(N, b0 + block)
+        m = b1 - b0
+        if m - 1 < K:
+            raise ValueError(f"block of {m} haplotypes cannot supply K={K} references")
+        for i in range(b0, b1):
+            c = rng.choice(m - 1, size=K, replace=False)
+            c += (c >= i - b0)
+            c.sort()
+            ref[i] = c + b0
+    return ref
+
+
+def make_problem(n_haps: int, p: int, K: int, seed: int = 2020, mean_group: float = 1.0, rho: float = 1.0,
+                 lam: float = 1e-3, n_founders: int = 2000, mean_dist_cm: float = 0.005, flip: float = 1e-3,
+                 block: int = 5000, hap_seed: int | None = None, chunk: int = 1024) -> SynthProblem:
+    """`seed` fixes everything that is per-SNP (allele frequencies, founders, map, groups);
+    `hap_seed` (default = seed) fixes the haplotype rows and their reference lists, so that the
+    ranks of a multi-GPU run can draw disjoint shards of one population."""
+    rng = np.random.default_rng(seed)
+    freq = rng.uniform(0.05, 0.5, size=p)
+    founders = (rng.random((n_founders, p)) < freq).astype(np.uint8)
+    d = np.maximum(rng.exponential(mean_dist_cm, size=p), 1e-9)
+    d[0] = 0.0
+    cm = 1.0 + np.cumsum(d)
+    bp = 1_000_000 + np.cumsum(np.maximum(1, np.rint(d * 1e6).astype(np.int64)))
+    groups = make_groups(p, mean_group, rng)
+    b = np.exp(-rho * d)
+    b[0] = 0.0                                        # knockoffs.cpp:1513
+    mu = np.full(p, float(lam))
+
+    hrng = np.random.default_rng([seed, 7919 if hap_seed is None else hap_seed])
+    psw = (1.0 - np.exp(-d)).astype(np.float32)
+    row_bytes = (p + 7) // 8
+    H = np.empty((n_haps, row_bytes), dtype=np.uint8)
+    cols = np.arange(p, dtype=np.int32)
+    for c0 in range(0, n_haps, chunk):
+        m = min(chunk, n_haps - c0)
+        sw = hrng.random((m, p), dtype=np.float32) < psw
+        sw[:, 0] = True
+        ids = hrng.integers(0, n_founders, size=(m, p), dtype=np.int32)
+        pos = np.where(sw, cols, 0)
+        np.maximum.accumulate(pos, axis=1, out=pos)
+        cur = np.take_along_axis(ids, pos, axis=1)
+        bits = founders[cur, cols[None, :]]
+        bits ^= (hrng.random((m, p), dtype=np.float32) < flip).astype(np.uint8)
+        H[c0:c0 + m] = np.packbits(bits, axis=1, bitorder="little")
+    ref = make_references(n_haps, K, hrng, block=min(block, n_haps))
+    return SynthProblem(H=H, p=p, K=K, ref=ref, b=b, mu=mu, groups=groups, cm=cm, bp=bp, seed=seed)
