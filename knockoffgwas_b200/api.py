@@ -188,7 +188,7 @@ def _make_debug(held: _Held, want_paths: bool, want_beta: bool):
         out.zk = np.zeros((n, held.p), dtype=np.int32)
         d.z, d.zk = out.z.ctypes.data, out.zk.ctypes.data
     if want_beta:
-        cap = (held.p + 3) // 4
+        cap = held.p
         out.beta_ckpt = np.zeros((n, cap, held.K), dtype=np.float64)
         out.ckpt_locus = np.full(cap, -1, dtype=np.int32)
         d.beta_ckpt, d.ckpt_locus, d.n_ckpt = out.beta_ckpt.ctypes.data, out.ckpt_locus.ctypes.data, cap

@@ -15,8 +15,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # host-side tables must follow the reference's evaluation order: no FMA contraction, no fast-math
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
-    "-shared",
 ]
+OBJDIR = PKG / "build"
 
 
 def sources():
@@ -31,19 +31,38 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def _compile(args):
+    nvcc, src, obj, verbose = args
+    import os
+    fast = ["-DKGW_FAST"] if os.environ.get("KGW_FAST") == "1" else []   # development: benchmark variants only
+    cmd = [nvcc] + NVCC_FLAGS + fast + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", str(obj), str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """One object per translation unit, compiled in parallel (the kernel instantiations are split by
+    lanes-per-haplotype so that the build takes about as long as its slowest unit), then one link."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not Path(nvcc).exists():
         raise RuntimeError("nvcc not found: cannot build knockoffgwas_b200/lib/libkgw.so")
     LIBDIR.mkdir(exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB)] + [str(s) for s in sources()]
+    OBJDIR.mkdir(exist_ok=True)
+    jobs = [(nvcc, s, OBJDIR / (s.stem + ".o"), verbose) for s in sources()]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        results = list(ex.map(_compile, jobs))
+    for src, r in results:
+        if verbose:
+            sys.stderr.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name}:\n" + r.stdout + r.stderr)
+    cmd = [nvcc, "-shared", "-o", str(LIB)] + [str(j[2]) for j in jobs]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

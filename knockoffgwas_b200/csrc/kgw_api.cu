@@ -6,6 +6,7 @@
 // without an sm_100 device every compute entry point returns KGW_ERR_CUDA.
 #include "../../include/kgw.h"
 #include "kgw_device.cuh"
+#include "kgw_variants.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -29,36 +30,29 @@ int fail(int code, const std::string &msg) {
       return fail(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
   } while (0)
 
-typedef void (*kernel_fn)(const KgwParams);
-
-struct KernelVariant {
-  int L, S, threads;
-  kernel_fn fn;
-  size_t (*smem)(int B, int threads);
-};
-
-template <int L, int S>
-size_t smem_bytes(int B, int threads) {
-  return kgw::Smem<L, S>::bytes(B) * (size_t)(threads / L);
-}
-
-constexpr int THREADS = 128;
-#define KGW_VARIANT(L, S) \
-  { L, S, THREADS, kgw::unrelated_kernel<L, S, THREADS, 1>, smem_bytes<L, S> }
-
-// (lanes per haplotype, states per lane): K <= L*S.  Default family L=8.
-const KernelVariant g_variants[] = {
-    KGW_VARIANT(8, 2),  KGW_VARIANT(8, 4),  KGW_VARIANT(8, 7),  KGW_VARIANT(8, 8),
-    KGW_VARIANT(8, 13), KGW_VARIANT(8, 16), KGW_VARIANT(4, 13), KGW_VARIANT(16, 16),
-};
-
-const KernelVariant *pick_variant(int K, int lanes) {
-  const KernelVariant *best = nullptr;
-  for (const KernelVariant &v : g_variants) {
-    if (v.L * v.S < K) continue;
-    if (lanes > 0 && v.L != lanes) continue;
-    if (lanes <= 0 && v.L != 8 && K <= 128) continue;  // default family
-    if (!best || v.L * v.S < best->L * best->S) best = &v;
+// pick the compiled instantiation: smallest lane count whose states-per-lane fit 32 registers-pairs,
+// then the smallest S that holds K, then the requested checkpoint spacing
+const KgwVariant *pick_variant(int K, int lanes, int B) {
+  int L = lanes;
+  if (L <= 0) {
+    L = 1;
+    while (L < 8 && (K + L - 1) / L > 32) L *= 2;
+  }
+  int n = 0;
+  const KgwVariant *tab = nullptr;
+  switch (L) {
+    case 1: tab = kgw_variants_L1(&n); break;
+    case 2: tab = kgw_variants_L2(&n); break;
+    case 4: tab = kgw_variants_L4(&n); break;
+    case 8: tab = kgw_variants_L8(&n); break;
+    default: return nullptr;
+  }
+  const KgwVariant *best = nullptr;
+  for (int i = 0; i < n; i++) {
+    const KgwVariant &v = tab[i];
+    if (v.L * v.S < K || v.B != B) continue;
+    if (!v.pad && v.L * v.S != K) continue;
+    if (!best || v.S < best->S || (v.S == best->S && !v.pad)) best = &v;
   }
   return best;
 }
@@ -85,7 +79,9 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
       h.mup = 1.0 - (1.0 - mu[j]);
       h.a = (1.0 - b[j]) * alpha;
       h.b = b[j];
-      h.pad = 0.0;
+      h.aomm = h.a * h.omm;   // (a_j_k + 0) * theta, knockoffs.cpp:1254
+      h.amu = h.a * h.mu;
+      h.amup = h.a * h.mup;
       // sample_emission_copula, lambda = 0.5 (knockoffs.cpp:1469-1502, call site :677)
       const double lambda = 0.5;
       for (int c = 0; c < 8; c++) {
@@ -115,6 +111,11 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
   }
   // groups -> first/last locus (set_groups, knockoffs.cpp:96-107)
   if (groups[0] != 0) return fail(KGW_ERR_INVALID, "groups[0] must be 0");
+  for (int j = 0; j < p; j++) {
+    if (!(b[j] >= 0.0) || !(1.0 - b[j] > 0.0))
+      return fail(KGW_ERR_UNSUPPORTED, "b[j] must lie in [0, 1): a locus with zero recombination weight (1 - b_j == 0) is not supported");
+    if (!(mu[j] > 0.0) || !(mu[j] < 1.0)) return fail(KGW_ERR_INVALID, "mut_rates[j] must lie in (0, 1)");
+  }
   const int G = groups[p - 1] + 1;
   std::vector<int> gfirst(G, -1), glast(G, -1);
   for (int j = 0; j < p; j++) {
@@ -171,13 +172,17 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
         k.vb = vbar[t];
         k.a = (1.0 - b[j]) * alpha;
         k.apb = (1.0 - b[j]) * alpha + b[j] * 1.0;
-        k.aa = k.a * k.a;
-        k.ab = k.apb * k.a;
-        k.bb = k.apb * k.apb;
+        const double aa = k.a * k.a, ab = k.apb * k.a, bb = k.apb * k.apb;  // T_k(z0)*T_k(z0k), :1352-1354
+        k.tg = (g == 0) ? k.a : aa;
+        k.f1 = ab / aa;
+        k.f2 = bb / aa;
+        k.fz1 = (g < g_end - 1) ? 1.0 + k.vs / k.vb : 0.0;
         double sa = 0;
         for (int l = 0; l < K; l++) sa += (1.0 - b[j]) * alpha;  // :1348-1349
         k.sa = sa;
-        k.g0 = vstar[0] * (1.0 - b[j]) * alpha;                  // :1364 (only read when t == 0)
+        k.vstg = vstar[0] * k.tg;                                // :1364 / :1373 (only read when t == 0)
+        k.gw = k.a * k.vb;
+        k.rgw = 1.0 / k.gw;
         k.flags = (t == 0 ? KGW_KO_FIRST : 0) | (g == g_end - 1 ? KGW_KO_LASTGRP : 0) |
                   (g == 0 ? KGW_KO_GZERO : 0) | (g == g_start ? KGW_KO_GSTART : 0) |
                   (t == m - 1 ? KGW_KO_LASTINGRP : 0);
@@ -198,7 +203,8 @@ struct kgw_plan {
   int64_t row_bytes = 0;
   int stride_w = 0;
   int B = 8, nblk = 0;
-  const KernelVariant *var = nullptr;
+  const KgwVariant *var = nullptr;
+  int G = 0, n_tasks = 0;
   int grid = 0;
   size_t smem = 0;
   size_t scratch_bytes = 0;
@@ -214,7 +220,7 @@ struct kgw_plan {
   KgwLocusKO *dko = nullptr;
   KgwEmit *demit = nullptr;
   KgwPass *dpass = nullptr;
-  double *dckpt = nullptr, *dinj = nullptr;
+  double *dckpt = nullptr, *dinj = nullptr, *dse = nullptr;
   uint8_t *dz = nullptr, *dzk = nullptr;
   int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
   double *ddbg_beta = nullptr;
@@ -225,7 +231,7 @@ struct kgw_plan {
   ~kgw_plan() {
     cudaSetDevice(device);
     cudaFree(dHw); cudaFree(dHk); cudaFree(dref); cudaFree(dhaps); cudaFree(dhmm); cudaFree(dko);
-    cudaFree(demit); cudaFree(dpass); cudaFree(dckpt); cudaFree(dinj); cudaFree(dz); cudaFree(dzk);
+    cudaFree(demit); cudaFree(dpass); cudaFree(dckpt); cudaFree(dinj); cudaFree(dse); cudaFree(dz); cudaFree(dzk);
     cudaFree(ddbg_z); cudaFree(ddbg_zk); cudaFree(ddbg_beta);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -300,10 +306,13 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   if (K > 256) return fail(KGW_ERR_UNSUPPORTED, "K > 256 is not built (latent states are stored as bytes)");
   kgw_options o{};
   if (opt) o = *opt;
-  const KernelVariant *var = pick_variant(K, o.lanes_per_hap);
-  if (!var) return fail(KGW_ERR_UNSUPPORTED, "no kernel variant for this K / lanes_per_hap");
-  int B = o.block_loci > 0 ? o.block_loci : 8;
-  if (B != 4 && B != 8 && B != 16 && B != 32) return fail(KGW_ERR_INVALID, "block_loci must be 4, 8, 16 or 32");
+  if (o.lanes_per_hap != 0 && o.lanes_per_hap != 1 && o.lanes_per_hap != 2 && o.lanes_per_hap != 4 && o.lanes_per_hap != 8)
+    return fail(KGW_ERR_INVALID, "lanes_per_hap must be 0 (auto), 1, 2, 4 or 8");
+  if (o.block_loci != 0 && o.block_loci != 2 && o.block_loci != 8)
+    return fail(KGW_ERR_INVALID, "block_loci must be 0 (auto), 2 or 8");
+  int B = o.block_loci;  // 0: decided below from the scratch budget
+  if (!pick_variant(K, o.lanes_per_hap, 2) && !pick_variant(K, o.lanes_per_hap, 8))
+    return fail(KGW_ERR_UNSUPPORTED, "no kernel variant for this K / lanes_per_hap");
   for (int i = 0; i < prob->n_unrelated; i++) {
     if (prob->unrelated[i] < 0 || prob->unrelated[i] >= N) return fail(KGW_ERR_INVALID, "unrelated index out of range");
   }
@@ -326,9 +335,6 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   pl->n_haps = prob->n_unrelated;
   pl->row_bytes = prob->row_bytes;
   pl->stride_w = (int)(((size_t)prob->row_bytes + 15) / 16 * 4);  // rows padded to 16 B
-  pl->B = B;
-  pl->nblk = (p + B - 1) / B;
-  pl->var = var;
   pl->b.assign(prob->b, prob->b + p);
   pl->mu.assign(prob->mu, prob->mu + p);
   pl->win_start.assign(prob->win_start, prob->win_start + W);
@@ -351,20 +357,34 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   KGW_CUDA_PL(cudaEventCreate(&pl->ev0));
   KGW_CUDA_PL(cudaEventCreate(&pl->ev1));
 
-  // occupancy-driven persistent grid
-  pl->smem = var->smem(B, var->threads);
-  KGW_CUDA_PL(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-  int occ = 0;
-  KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, var->threads, pl->smem));
-  if (occ <= 0) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
-  if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
-  const int gpc = var->threads / var->L;
-  const int max_grid = occ * dp.multiProcessorCount;
-  const long long max_slots = (long long)max_grid * gpc;
-  const long long rounds = std::max(1LL, (pl->n_haps + max_slots - 1) / max_slots);
-  const long long per_round = (pl->n_haps + rounds - 1) / rounds;
-  pl->grid = (int)std::max(1LL, std::min((long long)max_grid, (per_round + gpc - 1) / gpc));
-  const size_t slots = (size_t)pl->grid * gpc;
+  // variant, occupancy-driven persistent grid (one scratch slot per resident warp)
+  size_t free_b = 0, total_b = 0;
+  KGW_CUDA_PL(cudaMemGetInfo(&free_b, &total_b));
+  const size_t hw_bytes_est = 2 * (size_t)N * (((size_t)prob->row_bytes + 15) / 16 * 16) + sizeof(int32_t) * (size_t)N * W * K;
+  for (int pass = 0; pass < 2; pass++) {
+    const int Btry = B ? B : (pass == 0 ? 2 : 8);
+    const KgwVariant *var = pick_variant(K, o.lanes_per_hap, Btry);
+    if (!var && !B && pass == 0) continue;
+    if (!var) return guard_fail(fail(KGW_ERR_UNSUPPORTED, "no kernel variant for this K / lanes_per_hap / block_loci"));
+    KGW_CUDA_PL(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var->smem));
+    int occ = 0;
+    KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, var->threads, var->smem));
+    if (occ <= 0) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
+    if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
+    const int G = 32 / var->L, wpc = var->threads / 32;
+    const int n_tasks = (pl->n_haps + G - 1) / G;
+    const int grid = std::max(1, std::min(occ * dp.multiProcessorCount, (n_tasks + wpc - 1) / wpc));
+    const size_t slots = (size_t)grid * wpc;
+    const size_t nblk = ((size_t)p + Btry - 1) / Btry;
+    const size_t per_slot = sizeof(double) * (nblk * var->L * var->S * G + (size_t)p * 32) + 2 * (((size_t)p + 31) / 32 * 32) * G;
+    pl->var = var; pl->B = Btry; pl->G = G; pl->n_tasks = n_tasks; pl->grid = grid;
+    pl->smem = var->smem; pl->nblk = (int)nblk;
+    pl->scratch_bytes = per_slot * slots;
+    if (B || pl->scratch_bytes + hw_bytes_est < (size_t)(0.6 * (double)free_b)) break;  // fits: keep the denser checkpoints
+  }
+  const KgwVariant *var = pl->var;
+  const int G = pl->G;
+  const size_t slots = (size_t)pl->grid * (var->threads / 32);
 
   // inputs
   const size_t hw_bytes = (size_t)N * pl->stride_w * 4;
@@ -384,27 +404,30 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
     KGW_CUDA_PL(cudaMalloc(&pl->dinj, ub));
     KGW_CUDA_PL(cudaMemcpyAsync(pl->dinj, prob->injected_u, ub, cudaMemcpyHostToDevice, pl->stream));
   }
-  // scratch: checkpoints + latent paths, one slot per resident haplotype group
-  const size_t ckpt_stride = (size_t)pl->nblk * var->S * var->L;
-  const size_t z_stride = ((size_t)p + 63) / 64 * 64;
+  // scratch: checkpoints, per-locus partial sums and latent paths, one slot per resident warp
+  const size_t ckpt_stride = (size_t)pl->nblk * var->L * var->S * G;
+  const size_t se_stride = (size_t)p * 32;
+  const size_t z_stride = ((size_t)p + 31) / 32 * 32 * G;
   KGW_CUDA_PL(cudaMalloc(&pl->dckpt, sizeof(double) * ckpt_stride * slots));
+  KGW_CUDA_PL(cudaMalloc(&pl->dse, sizeof(double) * se_stride * slots));
   KGW_CUDA_PL(cudaMalloc(&pl->dz, z_stride * slots));
   KGW_CUDA_PL(cudaMalloc(&pl->dzk, z_stride * slots));
   KGW_CUDA_PL(cudaMemsetAsync(pl->dz, 0, z_stride * slots, pl->stream));
   KGW_CUDA_PL(cudaMemsetAsync(pl->dzk, 0, z_stride * slots, pl->stream));
-  pl->scratch_bytes = sizeof(double) * ckpt_stride * slots + 2 * z_stride * slots;
 
   KgwParams &P = pl->P;
   P.N = N; P.p = p; P.K = K; P.W = W;
   P.n_haps = pl->n_haps;
   P.stride_w = pl->stride_w;
-  P.B = B;
+  P.n_tasks = pl->n_tasks;
   P.Hw = pl->dHw;
   P.ref_local = pl->dref;
   P.haps = pl->dhaps;
   P.Hk = pl->dHk;
   P.ckpt = pl->dckpt;
   P.ckpt_stride = ckpt_stride;
+  P.sebuf = pl->dse;
+  P.se_stride = se_stride;
   P.zbuf = pl->dz;
   P.zkbuf = pl->dzk;
   P.z_stride = z_stride;

@@ -5,45 +5,52 @@
 //  compute_hmm_backward :1041, sample_posterior_MC :1215, sample_knockoff_MC :1270,
 //  sample_emission_copula :1469; categorical draws = weighted_choice, utils.cpp:690).
 //
-// Mapping.  L lanes (4/8/16/32) of a warp cooperate on one haplotype; lane l owns the S
-// consecutive HMM states k = l*S .. l*S+S-1 in registers (K <= L*S).  All haplotypes of a warp
-// walk the chromosome in lock step, so every shuffle is a full-mask, width-L segmented shuffle.
-// Per haplotype, per window pass:
-//   sweep 1  backward messages beta_j (unnormalised, exactly rescaled by powers of two),
-//            checkpointed every B loci to HBM;
-//   sweep 2  per block of B loci: recompute beta from the checkpoint into shared memory, then draw
-//            the latent path z_j forward through the block (prefix-scan categorical draw);
-//   sweep 3  group knockoff path zk_j (partition-function recursion N_k carried in registers),
-//            then knockoff alleles for each 32-locus word with lanes mapped to loci, packed and
-//            stored as one 32-bit word.
-// The O(K) per-locus recurrence is FP64 / issue bound; the backward table is never spilled
-// (HBM sees only checkpoints: 16*K/B bytes per haplotype-SNP instead of 16*K).
+// Mapping.  A warp carries G = 32/L haplotypes; L lanes (1, 2, 4 or 8) cooperate on one haplotype
+// and lane `lig` owns the S consecutive HMM states k = lig*S .. lig*S+S-1 in registers (K <= L*S).
+// Lane index = lig*G + g, so that for a fixed state the G haplotypes of a warp touch consecutive
+// 8-byte words in shared memory and in the HBM scratch (conflict-free / coalesced).  Warps are
+// independent (no CTA barrier); each resident warp owns one scratch slot and walks a strided list
+// of haplotype batches.  Per batch and window pass:
+//   sweep 1  backward messages beta_j (unnormalised, power-of-two rescaled every 8 loci), a
+//            checkpoint every B loci and the per-lane emission-weighted sum of every locus to HBM;
+//   sweep 2  per block of B loci: checkpoint -> shared-memory rows (B-1 recomputed steps), then the
+//            latent path z_j left to right, one pass per locus (the locus total is known from sweep 1);
+//   sweep 3  group knockoff path zk_j: at the first locus of a group the partition function N_k
+//            (registers) and its reciprocals (one shared-memory row, patched at the <= 3 special
+//            states) are updated; inside a group the draw has a closed form; knockoff alleles are
+//            drawn per 32-locus word and stored packed.
+// The O(K) per-locus recurrences are FP64-issue bound; HBM sees 16*K/B + 8*L bytes per haplotype-SNP.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "kgw_philox.h"
 
-struct __align__(16) KgwLocusHMM {
-  double omm;  // 1.0 - mu_j
-  double mu;   // mu_j
-  double mup;  // 1.0 - (1.0 - mu_j)   (knockoffs.cpp:1251-1256 quirk: emission for h=0, ref=1)
-  double a;    // (1.0 - b_j) * alpha,  alpha = 1.0/K (knockoffs.cpp:75)
-  double b;    // b_j
-  double pad;
+struct __align__(16) KgwLocusHMM {  // per locus, built on the host in the reference's evaluation order
+  double omm;   // 1.0 - mu_j
+  double mu;    // mu_j
+  double mup;   // 1.0 - (1.0 - mu_j)   (knockoffs.cpp:1251-1256 quirk: emission for h=0, ref=1)
+  double a;     // (1.0 - b_j) * alpha,  alpha = 1.0/K (knockoffs.cpp:75)
+  double b;     // b_j
+  double aomm;  // a * omm
+  double amu;   // a * mu
+  double amup;  // a * mup
 };
 
 enum { KGW_KO_FIRST = 1, KGW_KO_LASTGRP = 2, KGW_KO_GZERO = 4, KGW_KO_GSTART = 8, KGW_KO_LASTINGRP = 16 };
 
 struct __align__(16) KgwLocusKO {  // per (window pass, locus of the padded range)
-  double vs;    // vstar[t]                       knockoffs.cpp:1298-1313
-  double vb;    // vbar[t][.] (same for every state because alpha is uniform)  :1315-1339
-  double a;     // (1-b_j)*alpha
-  double apb;   // (1-b_j)*alpha + b_j*1.0
-  double aa;    // a*a                 T_k(z0)*T_k(z0k), k notin {z0,z0k}     :1352-1354
-  double ab;    // (a+b)*a             k equals exactly one of z0, z0k
-  double bb;    // (a+b)*(a+b)         k == z0 == z0k
-  double sa;    // sum_k (1-b_j)*alpha (K sequential terms): N_sum when g == g_start  :1348-1349
-  double g0;    // (vstar[0]*(1-b_j))*alpha: N update when g == 0            :1363-1365
+  double vs;     // vstar[t]                                          knockoffs.cpp:1298-1313
+  double vb;     // vbar[t][.] (same for every state: alpha uniform)   :1315-1339
+  double a;      // (1-b_j)*alpha
+  double apb;    // (1-b_j)*alpha + b_j*1.0
+  double tg;     // first locus of a group: T_k(z0)*T_k(z0k) for k notin {z0,z0k} (= a*a), or a when g == 0
+  double f1;     // ((a+b)*a) / (a*a)       weight ratio of a state equal to exactly one of z0, z0k
+  double f2;     // ((a+b)*(a+b)) / (a*a)   weight ratio of k == z0 == z0k
+  double fz1;    // 1 + vs/vb               weight ratio of k == z1 in the draw (0 in the last group)
+  double sa;     // sum_k (1-b_j)*alpha, K sequential terms: N_sum when g == g_start   :1348-1349
+  double vstg;   // vs * tg: coefficient of 1/N_old in the partition-function update   :1361-1375
+  double gw;     // a * vb: weight of a generic state inside a group (t > 0)           :1397-1419
+  double rgw;    // 1 / gw
   int32_t flags;
   int32_t z1_idx;   // locus holding z1 for this locus's group (first locus of group g+1), -1 if none
   int32_t z1_next;  // same for group g+1 (prefetched one group ahead), -1 if none
@@ -68,7 +75,7 @@ struct KgwParams {
   int32_t N, p, K, W;
   int32_t n_haps, n_passes;
   int32_t stride_w;  // 32-bit words per packed row
-  int32_t B;         // checkpoint spacing (4, 8, 16 or 32)
+  int32_t n_tasks;   // haplotype batches (G haplotypes each)
   const uint32_t *Hw;
   const int32_t *ref_local;  // [N][W][K]
   const int32_t *haps;       // [n_haps]
@@ -77,9 +84,11 @@ struct KgwParams {
   const KgwEmit *emit;       // [p]
   const KgwPass *passes;
   uint32_t *Hk;              // [N][stride_w]
-  double *ckpt;              // [slots][ckpt_stride]
+  double *ckpt;              // [slots][nblk][L*S][G]
   unsigned long long ckpt_stride;
-  uint8_t *zbuf, *zkbuf;     // [slots][z_stride]
+  double *sebuf;             // [slots][p][32]   per-lane emission-weighted sums of sweep 1
+  unsigned long long se_stride;
+  uint8_t *zbuf, *zkbuf;     // [slots][p][G]
   unsigned long long z_stride;
   unsigned long long seed;
   const double *injected_u;  // [N][3][p] or null
@@ -94,428 +103,541 @@ namespace kgw {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int STREAM_Z = 0, STREAM_ZK = 1, STREAM_HK = 2;  // include/kgw.h KGW_STREAM_*
 constexpr double N_MIN = 1.0e-10;  // knockoffs.cpp:1295
+constexpr int RESCALE = 8;         // loci between power-of-two rescales of the backward messages
 
+// ---- reductions over the L lanes of one haplotype (lane = lig*G + g, G = 32/L)
 template <int L>
 __device__ __forceinline__ double group_sum(double v) {
+  constexpr int G = 32 / L;
 #pragma unroll
-  for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o, L);
+  for (int o = 16; o >= G; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
-
 template <int L>
 __device__ __forceinline__ int group_sum_int(int v) {
+  constexpr int G = 32 / L;
 #pragma unroll
-  for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o, L);
+  for (int o = 16; o >= G; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
-
 template <int L>
 __device__ __forceinline__ unsigned group_or(unsigned v) {
+  constexpr int G = 32 / L;
 #pragma unroll
-  for (int o = L / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(FULL, v, o, L);
+  for (int o = 16; o >= G; o >>= 1) v |= __shfl_xor_sync(FULL, v, o);
   return v;
 }
-
-// exclusive prefix of `v` over the L lanes of a group (lane order), plus the group total
+// exclusive prefix over lig (ascending) and the group total
 template <int L>
-__device__ __forceinline__ double group_excl_scan(double v, int lig, double &total) {
+__device__ __forceinline__ double group_excl(double v, int lane, double &total) {
+  constexpr int G = 32 / L;
+  if (L == 1) { total = v; return 0.0; }
   double inc = v;
 #pragma unroll
-  for (int o = 1; o < L; o <<= 1) {
-    const double t = __shfl_up_sync(FULL, inc, o, L);
-    if (lig >= o) inc += t;
+  for (int o = G; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += t;
   }
-  total = __shfl_sync(FULL, inc, L - 1, L);
-  const double prev = __shfl_up_sync(FULL, inc, 1, L);
-  return lig == 0 ? 0.0 : prev;
+  total = __shfl_sync(FULL, inc, (L - 1) * G + (lane % G));
+  const double prev = __shfl_up_sync(FULL, inc, G);
+  return lane < G ? 0.0 : prev;
 }
 
-template <int L, int S>
-struct Smem {
-  // per haplotype group: beta block [B][S][L] doubles, uniforms [32] doubles, z chunk, zk chunk
-  __host__ __device__ static constexpr size_t bytes(int B) {
-    // + 64 B so that consecutive groups start 16 banks apart (8-byte accesses, half-warp phases)
-    return (size_t)B * S * L * 8 + 32 * 8 + 64 + 64;
+__device__ __forceinline__ double fast_rcp(double x) {
+  // x in [1e-10, ~1e3]: hardware seed + two Newton steps (relative error ~1e-16)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int L, int S, int B>
+struct Cfg {
+  static constexpr int G = 32 / L;
+  static constexpr int KP = L * S;
+  // per-warp shared memory: B message rows + 1 checkpoint staging row (sweep 2) / 1 reciprocal row
+  // (sweep 3), two reference-word tiles, two staging tiles of per-lane sums, two latent-path tiles
+  static constexpr size_t rows_bytes = (size_t)(B + 1) * KP * G * 8;
+  static constexpr size_t refw_bytes = (size_t)2 * KP * G * 4;
+  static constexpr size_t se_bytes = (size_t)2 * B * 32 * 8;
+  static constexpr size_t tile_bytes = (size_t)2 * 32 * G;
+  __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + refw_bytes + se_bytes + tile_bytes; }
+};
+
+// uniform of (hap, stream, locus j): Philox block cached per 4 loci
+struct UniformSrc {
+  const double *inj;  // injected row or null
+  unsigned long long seed;
+  uint32_t hap, stream;
+  kgw_u32x4 blk;
+  int cur;
+  __device__ __forceinline__ void init(const KgwParams &P, int hap_, int stream_, int w) {
+    inj = P.injected_u ? P.injected_u + ((size_t)hap_ * 3 + stream_) * (size_t)P.p : nullptr;
+    seed = P.seed;
+    hap = (uint32_t)hap_;
+    stream = (uint32_t)(stream_ | (w << 2));
+    cur = -1;
+  }
+  __device__ __forceinline__ double get(int j) {
+    if (inj) return inj[j];
+    if ((j >> 2) != cur) {
+      cur = j >> 2;
+      blk = kgw_philox_block(seed, hap, stream, (uint32_t)cur);
+    }
+    const int q = j & 3;
+    const uint32_t w = q == 0 ? blk.x : (q == 1 ? blk.y : (q == 2 ? blk.z : blk.w));
+    return kgw_word_to_uniform(w);
   }
 };
 
-// one backward step: beta <- beta_{m-1} from beta_m using locus m (knockoffs.cpp:1047-1074,
-// unnormalised; the reference's per-locus normalisation is a positive scale that cancels in every draw)
-template <int L, int S>
-__device__ __forceinline__ double backward_step(double (&beta)[S], const uint32_t (&mw)[S], int bit,
-                                                const KgwLocusHMM &h, int k0, int K) {
-  double e[S];
-  double acc = 0.0;
+// emission-weighted messages e = beta * E and their in-lane sum (knockoffs.cpp:1052-1060 without the
+// constant factor a); beta is overwritten by e.
+template <int S, bool PAD>
+__device__ __forceinline__ double emit_and_sum(double (&beta)[S], const uint32_t (&mw)[S], uint32_t bm,
+                                               double omm, double mu, int ns) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
   for (int s = 0; s < S; s++) {
-    const bool match = (mw[s] >> bit) & 1u;
-    e[s] = beta[s] * (match ? h.omm : h.mu);
-    acc += e[s];
+    double e = beta[s] * mu;
+    if (mw[s] & bm) e = beta[s] * omm;
+    beta[s] = (!PAD || s < ns) ? e : 0.0;
+    if ((s & 3) == 0) a0 += beta[s];
+    else if ((s & 3) == 1) a1 += beta[s];
+    else if ((s & 3) == 2) a2 += beta[s];
+    else a3 += beta[s];
   }
-  const double Se = group_sum<L>(acc);
-  const double c = h.a * Se;
-#pragma unroll
-  for (int s = 0; s < S; s++)
-    if (k0 + s < K) beta[s] = fma(h.b, e[s], c);
-  return Se;
+  return (a0 + a1) + (a2 + a3);
 }
 
-template <int L, int S>
-__device__ __forceinline__ void load_match_words(uint32_t (&mw)[S], const uint32_t *__restrict__ Hw,
-                                                 const size_t (&roff)[S], size_t hoff, int wi, uint32_t &hw) {
-  hw = __ldg(Hw + hoff + wi);
-#pragma unroll
-  for (int s = 0; s < S; s++) mw[s] = ~(hw ^ __ldg(Hw + roff[s] + wi));
-}
-
-// uniforms of one 32-locus chunk of one stream into shared memory (one double per locus)
-template <int L>
-__device__ __forceinline__ void fill_uniforms(double *su, const KgwParams &P, int hap, int stream, int wi, int lig) {
-  constexpr int LPL = 32 / L;  // loci per lane
-  if (P.injected_u != nullptr) {
-    const double *U = P.injected_u + ((size_t)hap * 3 + (stream & 3)) * (size_t)P.p;
-#pragma unroll
-    for (int c = 0; c < LPL; c++) {
-      const int idx = lig * LPL + c;
-      const int j = (wi << 5) + idx;
-      su[idx] = (j < P.p) ? U[j] : 0.0;
-    }
-  } else if (LPL >= 4) {
-#pragma unroll
-    for (int c = 0; c < (LPL >= 4 ? LPL / 4 : 1); c++) {
-      const int idx = lig * LPL + 4 * c;
-      const kgw_u32x4 r = kgw_philox_block(P.seed, (uint32_t)hap, (uint32_t)stream, (uint32_t)(((wi << 5) + idx) >> 2));
-      su[idx + 0] = kgw_word_to_uniform(r.x);
-      su[idx + 1] = kgw_word_to_uniform(r.y);
-      su[idx + 2] = kgw_word_to_uniform(r.z);
-      su[idx + 3] = kgw_word_to_uniform(r.w);
-    }
-  } else {
-    const int idx = lig * LPL;
-    const kgw_u32x4 r = kgw_philox_block(P.seed, (uint32_t)hap, (uint32_t)stream, (uint32_t)(((wi << 5) + idx) >> 2));
-    const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int c = 0; c < LPL; c++) su[idx + c] = kgw_word_to_uniform(w4[(idx + c) & 3]);
-  }
-}
-
-template <int L, int S, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) unrelated_kernel(const __grid_constant__ KgwParams P) {
-  constexpr int GPC = THREADS / L;  // haplotype groups per CTA
-  constexpr int GPW = 32 / L;       // haplotype groups per warp
-  constexpr int LPL = 32 / L;       // loci per lane in lane<->locus phases
-  const int lig = threadIdx.x % L;
-  const int gic = threadIdx.x / L;
-  const int slot = blockIdx.x * GPC + gic;
-  const int nslots = gridDim.x * GPC;
-  const int K = P.K;
-  const int B = P.B;
-  const int Bm = B - 1;
+// PAD = false asserts K == L*S (no padded states: the per-state guards compile away);
+// WPC = maximum warps per CTA, fewer may be launched
+template <int L, int S, int B, bool PAD, int WPC>
+__global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant__ KgwParams P) {
+  using C = Cfg<L, S, B>;
+  constexpr int G = C::G;
+  constexpr int KP = C::KP;
+  const int lane = threadIdx.x & 31;
+  const int wic = threadIdx.x >> 5;
+  const int g = lane % G;
+  const int lig = lane / G;
   const int k0 = lig * S;
+  const int K = P.K;
+  const int ns = PAD ? min(S, max(0, K - k0)) : S;  // states owned by this lane
+  const int wpc = blockDim.x >> 5;
+  const int slot = blockIdx.x * wpc + wic;
+  const int nslots = gridDim.x * wpc;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned char *gs = smem_raw + (size_t)gic * Smem<L, S>::bytes(B);
-  double *sbeta = reinterpret_cast<double *>(gs);           // [B][S][L]
-  double *su = sbeta + (size_t)B * S * L;                   // [32]
-  uint8_t *sz = reinterpret_cast<uint8_t *>(su + 32);       // [32]
-  uint8_t *szk = sz + 32;                                   // [32]
+  unsigned char *ws = smem_raw + (size_t)wic * C::warp_bytes();
+  double *rows = reinterpret_cast<double *>(ws);                                  // [B+1][KP][G]
+  double *ckst = rows + (size_t)B * KP * G;                                       // checkpoint staging row
+  uint32_t *refw = reinterpret_cast<uint32_t *>(ws + C::rows_bytes);              // [2][KP][G]
+  double *sest = reinterpret_cast<double *>(ws + C::rows_bytes + C::refw_bytes);  // [2][B][32]
+  uint8_t *ztile = ws + C::rows_bytes + C::refw_bytes + C::se_bytes;              // [32][G]
+  uint8_t *zktile = ztile + 32 * G;                                               // [32][G]
 
-  double *ck = P.ckpt + (size_t)slot * P.ckpt_stride;       // [nblk][S][L]
-  uint8_t *zb = P.zbuf + (size_t)slot * P.z_stride;
+  double *ck = P.ckpt + (size_t)slot * P.ckpt_stride;    // [nblk][KP][G]
+  double *se = P.sebuf + (size_t)slot * P.se_stride;     // [p][32]
+  uint8_t *zb = P.zbuf + (size_t)slot * P.z_stride;      // [p][G]
   uint8_t *zkb = P.zkbuf + (size_t)slot * P.z_stride;
 
-  const int warp_first = blockIdx.x * GPC + (threadIdx.x >> 5) * GPW;
-  for (int t0 = warp_first, t = slot; t0 < P.n_haps; t0 += nslots, t += nslots) {
-    const bool active = t < P.n_haps;
-    const int tt = active ? t : P.n_haps - 1;
+  for (int task = slot; task < P.n_tasks; task += nslots) {
+    const int tidx = task * G + g;
+    const bool active = tidx < P.n_haps;
+    const int tt = active ? tidx : P.n_haps - 1;
     const int hap = __ldg(P.haps + tt);
     const size_t hoff = (size_t)hap * P.stride_w;
 
     for (int ip = 0; ip < P.n_passes; ip++) {
       const KgwPass ps = P.passes[ip];
       const int js = ps.js, je = ps.je;
+      const int wlo = js >> 5, whi = (je - 1) >> 5;
       const int32_t *ref = P.ref_local + ((size_t)hap * P.W + ps.w) * K;
-      size_t roff[S];
+      __syncwarp();
+
+      // asynchronous prefetch of the reference words of 32-locus word `w` into tile `buf`
+      auto prefetch_words = [&](int w, int buf) {
 #pragma unroll
-      for (int s = 0; s < S; s++) roff[s] = (size_t)((k0 + s < K) ? __ldg(ref + k0 + s) : hap) * P.stride_w;
+        for (int s = 0; s < S; s++) {
+          const int id = (!PAD || s < ns) ? __ldg(ref + k0 + s) : hap;
+          cp_async4(refw + buf * KP * G + (k0 + s) * G + g, P.Hw + (size_t)id * P.stride_w + w);
+        }
+      };
 
       // ------------------------------------------------------------------ sweep 1: backward + checkpoints
       {
         double beta[S];
+        uint32_t mw[S];
 #pragma unroll
-        for (int s = 0; s < S; s++) beta[s] = (k0 + s < K) ? 1.0 / K : 0.0;  // knockoffs.cpp:1046
+        for (int s = 0; s < S; s++) beta[s] = (!PAD || s < ns) ? 1.0 / K : 0.0;  // knockoffs.cpp:1046
         {
           const int n = (je - 1) / B;
 #pragma unroll
-          for (int s = 0; s < S; s++) ck[((size_t)n * S + s) * L + lig] = beta[s];
+          for (int s = 0; s < S; s++) ck[((size_t)n * KP + k0 + s) * G + g] = beta[s];
         }
-        int wi = (je - 1) >> 5;
-        const int wlo = js >> 5;
-        uint32_t mw[S], nx[S], hw;
-        load_match_words<L, S>(mw, P.Hw, roff, hoff, wi, hw);
-        if (wi > wlo) load_match_words<L, S>(nx, P.Hw, roff, hoff, wi - 1, hw);
-        for (int m = je - 1; m > js; m--) {
+        int wi = whi;
+        prefetch_words(wi, wi & 1);
+        cp_async_wait_all();
+        __syncwarp();
+        uint32_t hw = __ldg(P.Hw + hoff + wi);
+#pragma unroll
+        for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
+        if (wi > wlo) prefetch_words(wi - 1, (wi - 1) & 1);
+        KgwLocusHMM h = P.hmm[je - 1];
+        for (int m = je - 1; m >= js; m--) {
           if ((m >> 5) != wi) {
             wi = m >> 5;
+            cp_async_wait_all();
+            __syncwarp();
+            hw = __ldg(P.Hw + hoff + wi);
 #pragma unroll
-            for (int s = 0; s < S; s++) mw[s] = nx[s];
-            if (wi > wlo) load_match_words<L, S>(nx, P.Hw, roff, hoff, wi - 1, hw);
+            for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
+            if (wi > wlo) prefetch_words(wi - 1, (wi - 1) & 1);
           }
-          const KgwLocusHMM h = P.hmm[m];
-          const double Se = backward_step<L, S>(beta, mw, m & 31, h, k0, K);
-          const int j = m - 1;
-          if ((j & Bm) == Bm) {
-            // exact power-of-two rescale so that sum_k beta_j(k) lands in [1,2)
-            const int ex = (__double2hiint(Se) >> 20) & 0x7ff;
-            if (ex > 0 && ex < 2046) {
-              const double sc = __hiloint2double((2046 - ex) << 20, 0);
+          const KgwLocusHMM hn = P.hmm[m > js ? m - 1 : js];
+          const uint32_t bm = 1u << (m & 31);
+          const double pl = emit_and_sum<S, PAD>(beta, mw, bm, h.omm, h.mu, ns);  // beta := e
+          se[(size_t)m * 32 + lane] = pl;
+          if (m == js) {
+            break;
+          }
+          const double Se = group_sum<L>(pl);
+          const double c = h.a * Se;
 #pragma unroll
-              for (int s = 0; s < S; s++) beta[s] *= sc;
+          for (int s = 0; s < S; s++) beta[s] = (!PAD || s < ns) ? fma(h.b, beta[s], c) : 0.0;  // :1062-1068
+          const int j = m - 1;
+          if ((j % B) == B - 1) {
+            if ((j % RESCALE) == RESCALE - 1) {
+              // exact power-of-two rescale so that sum_k beta_j(k) stays near 1
+              const int ex = (__double2hiint(Se) >> 20) & 0x7ff;
+              if (ex > 0 && ex < 2046) {
+                const double sc = __hiloint2double((2046 - ex) << 20, 0);
+#pragma unroll
+                for (int s = 0; s < S; s++) beta[s] *= sc;
+              }
             }
             const int n = j / B;
 #pragma unroll
-            for (int s = 0; s < S; s++) ck[((size_t)n * S + s) * L + lig] = beta[s];
+            for (int s = 0; s < S; s++) ck[((size_t)n * KP + k0 + s) * G + g] = beta[s];
           }
+          h = hn;
         }
       }
+      __syncwarp();
 
       // debug: normalised backward messages at the checkpoint loci of the last pass
       if (P.dbg_beta != nullptr && ip == P.n_passes - 1) {
-        __syncwarp();
         for (int n = js / B; n <= (je - 1) / B; n++) {
           double v[S];
           double acc = 0.0;
 #pragma unroll
-          for (int s = 0; s < S; s++) { v[s] = ck[((size_t)n * S + s) * L + lig]; acc += v[s]; }
+          for (int s = 0; s < S; s++) { v[s] = ck[((size_t)n * KP + k0 + s) * G + g]; acc += v[s]; }
           const double tot = group_sum<L>(acc);
           if (active && n < P.dbg_nblk) {
 #pragma unroll
             for (int s = 0; s < S; s++)
-              if (k0 + s < K) P.dbg_beta[((size_t)tt * P.dbg_nblk + n) * K + k0 + s] = v[s] / tot;
+              if (!PAD || s < ns) P.dbg_beta[((size_t)tt * P.dbg_nblk + n) * K + k0 + s] = v[s] / tot;
           }
         }
       }
 
       // ------------------------------------------------------------------ sweep 2: recompute + draw z
       {
-        int zprev = -1;
-        int wi = -1;
-        const int whi = (je - 1) >> 5;
-        uint32_t mw[S], nx[S], hw = 0, hwn = 0;
-        load_match_words<L, S>(nx, P.Hw, roff, hoff, js >> 5, hwn);
-        for (int n = js / B; n <= (je - 1) / B; n++) {
-          const int lo = max(n * B, js);
-          const int top = min(n * B + B, je) - 1;
-          if ((lo >> 5) != wi) {
-            wi = lo >> 5;
+        double beta[S];
+        uint32_t mw[S];
+        UniformSrc us;
+        us.init(P, hap, STREAM_Z, ps.w);
+        int zprev = 0;
+        int wi = wlo;
+        prefetch_words(wi, wi & 1);
+        cp_async_wait_all();
+        __syncwarp();
+        uint32_t hw = __ldg(P.Hw + hoff + wi);
 #pragma unroll
-            for (int s = 0; s < S; s++) mw[s] = nx[s];
-            hw = hwn;
-            if (wi < whi) load_match_words<L, S>(nx, P.Hw, roff, hoff, wi + 1, hwn);
-            __syncwarp();
-            fill_uniforms<L>(su, P, hap, STREAM_Z | (ps.w << 2), wi, lig);
-            __syncwarp();
-          }
-          double beta[S];
+        for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
+        if (wi < whi) prefetch_words(wi + 1, (wi + 1) & 1);
+        // loci of this word outside [js, je) keep the values of earlier window passes
+        for (int i = lane; i < 8 * G; i += 32)
+          reinterpret_cast<uint32_t *>(ztile)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
+        __syncwarp();
+        // checkpoint and per-lane sums of block n -> staging (asynchronous, one block ahead)
+        auto prefetch_block = [&](int n) {
 #pragma unroll
-          for (int s = 0; s < S; s++) beta[s] = ck[((size_t)n * S + s) * L + lig];
+          for (int s = 0; s < S; s++)
+            cp_async8(ckst + (k0 + s) * G + g, ck + ((size_t)n * KP + k0 + s) * G + g);
+          const int lo_n = max(n * B, js), top_n = min(n * B + B, je) - 1;
+          for (int j = lo_n; j <= top_n; j++)
+            cp_async8(sest + ((n & 1) * B + (j - n * B)) * 32 + lane, se + (size_t)j * 32 + lane);
+        };
+        const int n_last = (je - 1) / B;
+        prefetch_block(js / B);
+        KgwLocusHMM hj = P.hmm[js];
+        for (int n = js / B; n <= n_last; n++) {
           const int nb = n * B;
-          if (top > lo) {
+          const int lo = max(nb, js);
+          const int top = min(nb + B, je) - 1;
+          if ((lo >> 5) != wi) {
+            // flush the finished z tile, then switch to the next 32-locus word
+            __syncwarp();
+            for (int i = lane; i < 8 * G; i += 32)
+              reinterpret_cast<uint32_t *>(zb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(ztile)[i];
+            wi = lo >> 5;
+            cp_async_wait_all();
+            __syncwarp();
+            for (int i = lane; i < 8 * G; i += 32)
+              reinterpret_cast<uint32_t *>(ztile)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
+            hw = __ldg(P.Hw + hoff + wi);
 #pragma unroll
-            for (int s = 0; s < S; s++) sbeta[((size_t)(top - nb) * S + s) * L + lig] = beta[s];
+            for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
+            if (wi < whi) prefetch_words(wi + 1, (wi + 1) & 1);
           }
-          for (int m = top; m > lo; m--) {
-            const KgwLocusHMM h = P.hmm[m];
-            backward_step<L, S>(beta, mw, m & 31, h, k0, K);
-            if (m - 1 > lo) {
+          // staged checkpoint -> registers and the row of the block's top locus, then B-1 recomputed steps
+          cp_async_wait_all();
+          __syncwarp();
 #pragma unroll
-              for (int s = 0; s < S; s++) sbeta[((size_t)(m - 1 - nb) * S + s) * L + lig] = beta[s];
+          for (int s = 0; s < S; s++) {
+            beta[s] = ckst[(k0 + s) * G + g];
+            rows[((top - nb) * KP + k0 + s) * G + g] = beta[s];
+          }
+          __syncwarp();
+          if (n < n_last) prefetch_block(n + 1);
+          if (B > 1) {
+            for (int m = top; m > lo; m--) {
+              const KgwLocusHMM h = P.hmm[m];
+              const double pl = emit_and_sum<S, PAD>(beta, mw, 1u << (m & 31), h.omm, h.mu, ns);
+              const double Se = group_sum<L>(pl);
+              const double c = h.a * Se;
+#pragma unroll
+              for (int s = 0; s < S; s++) {
+                beta[s] = (!PAD || s < ns) ? fma(h.b, beta[s], c) : 0.0;
+                rows[((m - 1 - nb) * KP + k0 + s) * G + g] = beta[s];
+              }
             }
           }
+          __syncwarp();
           // forward draws through the block (knockoffs.cpp:1232-1260)
           for (int j = lo; j <= top; j++) {
-            if (j > lo) {
-#pragma unroll
-              for (int s = 0; s < S; s++) beta[s] = sbeta[((size_t)(j - nb) * S + s) * L + lig];
+            const KgwLocusHMM h = hj;
+            hj = P.hmm[j + 1 < je ? j + 1 : j];
+            const uint32_t bm = 1u << (j & 31);
+            const bool hbit = hw & bm;
+            const double amis = hbit ? h.amu : h.amup;
+            const double *row = rows + (size_t)(j - nb) * KP * G;
+            const double pl = sest[((n & 1) * B + (j - nb)) * 32 + lane];
+            double Se;
+            const double base = group_excl<L>(pl, lane, Se);
+            // the one state whose transition weight carries b_j: k == z_{j-1}
+            double X = 0.0;
+            if (j > js) {
+              const double bz = row[zprev * G + g];
+              const uint32_t wz = ~(hw ^ refw[(wi & 1) * KP * G + zprev * G + g]);
+              X = h.b * (bz * ((wz & bm) ? h.omm : (hbit ? h.mu : h.mup)));
             }
-            const KgwLocusHMM h = P.hmm[j];
-            const int bit = j & 31;
-            const bool hbit = (hw >> bit) & 1u;
-            const double mis = hbit ? h.mu : h.mup;
-            double pre[S];
-            double run = 0.0, ez = 0.0;
+            const double R = us.get(j) * fma(h.a, Se, X);
+            const double tA = R, tB = R - X;
+            double run = h.a * base;
+            int cA = 0, cB = 0;
 #pragma unroll
             for (int s = 0; s < S; s++) {
-              const bool match = (mw[s] >> bit) & 1u;
-              const double e = (match ? h.omm : mis) * beta[s];
-              if (k0 + s == zprev) ez = e;
+              const double e = row[(k0 + s) * G + g] * ((mw[s] & bm) ? h.aomm : amis);
               run += e;
-              pre[s] = run;
+              cA += (run <= tA) ? 1 : 0;
+              cB += (run <= tB) ? 1 : 0;
             }
-            double total;
-            const double base = group_excl_scan<L>(run, lig, total);
-            const bool first = (j == js);
-            ez = __shfl_sync(FULL, ez, first ? 0 : zprev / S, L);
-            const double X = first ? 0.0 : h.b * ez;
-            const double R = su[bit] * fma(h.a, total, X);
-            int cnt = 0;
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-              const double C = fma(h.a, base + pre[s], (!first && k0 + s >= zprev) ? X : 0.0);
-              cnt += (R >= C) ? 1 : 0;
-            }
-            cnt = group_sum_int<L>(cnt);
-            const int z = min(cnt, K - 1);
+            const int cc = group_sum_int<L>(cA | (cB << 16));
+            const int k1 = cc & 0xffff, k2 = cc >> 16;
+            int z = (k1 < zprev) ? k1 : max(k2, zprev);
+            z = min(z, K - 1);
             zprev = z;
-            if (lig == 0) sz[bit] = (uint8_t)z;
-          }
-          if ((top & 31) == 31 || top == je - 1) {
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < LPL; c++) {
-              const int idx = lig * LPL + c;
-              const int j = (wi << 5) + idx;
-              if (j >= js && j < je) zb[j] = sz[idx];
-            }
-            __syncwarp();
+            if (lig == 0) ztile[(j & 31) * G + g] = (uint8_t)z;
           }
         }
+        __syncwarp();
+        for (int i = lane; i < 8 * G; i += 32)
+          reinterpret_cast<uint32_t *>(zb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(ztile)[i];
       }
       __syncwarp();
 
       // ------------------------------------------------------------------ sweep 3: knockoff path + alleles
       {
-        double Nold[S], Iv[S];
+        double Nv[S];
 #pragma unroll
-        for (int s = 0; s < S; s++) { Nold[s] = (k0 + s < K) ? 1.0 : 0.0; Iv[s] = Nold[s]; }  // :1293-1294
-        int z0 = -1, z0k = -1, zkprev = -1;
-        if (js > 0) { z0 = zb[js - 1]; z0k = zkb[js - 1]; }
+        for (int s = 0; s < S; s++) Nv[s] = 1.0;  // knockoffs.cpp:1293-1294 (N == N_old between groups)
+        double *rrow = rows;                      // [KP][G] reciprocals 1/N_old, patched per group
+        UniformSrc us, uh;
+        us.init(P, hap, STREAM_ZK, ps.w);
+        uh.init(P, hap, STREAM_HK, ps.w);
+        int z0 = 0, z0k = 0, zkprev = 0;
+        if (js > 0) { z0 = zb[(size_t)(js - 1) * G + g]; z0k = zkb[(size_t)(js - 1) * G + g]; }
         const KgwLocusKO *ko_tab = P.ko + ps.ko_off - js;
         int z1 = 0, z1_pref = 0;
         {
-          const KgwLocusKO &k = ko_tab[js];
-          if (k.z1_idx >= 0) z1_pref = zb[k.z1_idx];
+          const int zi = ko_tab[js].z1_idx;
+          if (zi >= 0) z1_pref = zb[(size_t)zi * G + g];
         }
-        const int wlo = js >> 5, whi = (je - 1) >> 5;
+        prefetch_words(wlo, wlo & 1);
         for (int wi = wlo; wi <= whi; wi++) {
           const int lo = max(wi << 5, js), hi = min((wi << 5) + 32, je);
           __syncwarp();
-          fill_uniforms<L>(su, P, hap, STREAM_ZK | (ps.w << 2), wi, lig);
-#pragma unroll
-          for (int c = 0; c < LPL; c++) {
-            const int idx = lig * LPL + c;
-            const int j = (wi << 5) + idx;
-            sz[idx] = (j >= js && j < je) ? zb[j] : (uint8_t)0;
-          }
+          for (int i = lane; i < 8 * G; i += 32)
+            reinterpret_cast<uint32_t *>(ztile)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
+          for (int i = lane; i < 8 * G; i += 32)
+            reinterpret_cast<uint32_t *>(zktile)[i] = reinterpret_cast<const uint32_t *>(zkb + (size_t)(wi << 5) * G)[i];
+          cp_async_wait_all();
           __syncwarp();
+          if (wi < whi) prefetch_words(wi + 1, (wi + 1) & 1);
+          KgwLocusKO k = ko_tab[lo];
           for (int j = lo; j < hi; j++) {
-            const KgwLocusKO k = ko_tab[j];
+            const KgwLocusKO kn = ko_tab[j + 1 < je ? j + 1 : j];
             const int bit = j & 31;
-            const int zj = sz[bit];
-            double q[S], pre[S];
-            double run = 0.0, ez1 = 0.0;
+            const int zj = ztile[bit * G + g];
+            const bool lastg = k.flags & KGW_KO_LASTGRP;
+            const double u = us.get(j);
+            int zk;
             if (k.flags & KGW_KO_FIRST) {
               z1 = z1_pref;
-              if (k.z1_next >= 0) z1_pref = zb[k.z1_next];
-              const bool gzero = k.flags & KGW_KO_GZERO;
+              if (k.z1_next >= 0) z1_pref = zb[(size_t)k.z1_next * G + g];
+              const bool gz = k.flags & KGW_KO_GZERO;
+              // pass A: reciprocals of N_old and their sum
+              double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
               for (int s = 0; s < S; s++) {
-                const int ks = k0 + s;
-                const double tt = gzero ? k.a
-                                        : ((ks == z0) ? ((ks == z0k) ? k.bb : k.ab) : ((ks == z0k) ? k.ab : k.aa));
-                q[s] = tt * Iv[s];
-                if (ks == z1) ez1 = q[s];
-                run += q[s];
-                pre[s] = run;
+                const double r = (!PAD || s < ns) ? fast_rcp(Nv[s]) : 0.0;
+                rrow[(k0 + s) * G + g] = r;
+                if ((s & 3) == 0) a0 += r;
+                else if ((s & 3) == 1) a1 += r;
+                else if ((s & 3) == 2) a2 += r;
+                else a3 += r;
               }
-            } else {
-#pragma unroll
-              for (int s = 0; s < S; s++) {
-                const int ks = k0 + s;
-                q[s] = (ks < K) ? ((ks == zkprev) ? k.apb : k.a) : 0.0;
-                if (ks == z1) ez1 = q[s];
-                run += q[s];
-                pre[s] = run;
+              double pls = (a0 + a1) + (a2 + a3);
+              __syncwarp();
+              // the (at most two) states equal to z0 / z0k carry T_k(z0)*T_k(z0k) != tg  (:1350-1354)
+              if (!gz) {
+                const double r0 = rrow[z0 * G + g];
+                double n0, n0k = 0.0, r0k = 0.0;
+                if (z0 == z0k) {
+                  n0 = r0 * k.f2;
+                } else {
+                  n0 = r0 * k.f1;
+                  r0k = rrow[z0k * G + g];
+                  n0k = r0k * k.f1;
+                }
+                __syncwarp();
+                if (lig == 0) {
+                  rrow[z0 * G + g] = n0;
+                  if (z0 != z0k) rrow[z0k * G + g] = n0k;
+                }
+                if (z0 / S == lig) pls += n0 - r0;
+                if (z0 != z0k && z0k / S == lig) pls += n0k - r0k;
               }
-            }
-            double Qtot;
-            const double base = group_excl_scan<L>(run, lig, Qtot);
-            if (k.flags & KGW_KO_FIRST) {
-              // partition function update (knockoffs.cpp:1345-1390)
-              const double Nsum = (k.flags & KGW_KO_GSTART) ? k.sa : Qtot;
-              double part = 0.0;
-              const bool upd = !(k.flags & KGW_KO_LASTGRP);
-              const bool gzero = k.flags & KGW_KO_GZERO;
+              __syncwarp();
+              const double Sr = group_sum<L>(pls);
+              const double Nsum = (k.flags & KGW_KO_GSTART) ? k.sa : k.tg * Sr;  // :1345-1358
               const double c2 = k.vb * Nsum;
+              // pass B: partition function update and normaliser (:1360-1390)
+              double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
 #pragma unroll
               for (int s = 0; s < S; s++) {
-                if (k0 + s < K) {
-                  double Nv = Nold[s];
-                  if (upd) {
-                    Nv += c2;
-                    Nv += gzero ? k.g0 : k.vs * q[s];
-                  }
-                  Nv = fmax(Nv, N_MIN);
-                  Nold[s] = Nv;
-                  part += Nv;
-                }
+                double nv = Nv[s];
+                if (!lastg) nv = fma(k.vstg, rrow[(k0 + s) * G + g], nv + c2);
+                nv = (!PAD || s < ns) ? nv : 0.0;
+                Nv[s] = nv;
+                if ((s & 3) == 0) b0 += nv;
+                else if ((s & 3) == 1) b1 += nv;
+                else if ((s & 3) == 2) b2 += nv;
+                else b3 += nv;
               }
-              const double rN = 1.0 / group_sum<L>(part);
+              const double rN = 1.0 / group_sum<L>((b0 + b1) + (b2 + b3));
 #pragma unroll
               for (int s = 0; s < S; s++) {
-                if (k0 + s < K) {
-                  const double Nv = fmax(Nold[s] * rN, N_MIN);
-                  Nold[s] = Nv;
-                  Iv[s] = __drcp_rn(Nv);
-                }
+                const double v = Nv[s] * rN;
+                Nv[s] = (v < N_MIN) ? N_MIN : v;  // (the pre-normalisation clamp of :1380 cannot fire: N only grows)
               }
-            }
-            // categorical draw (knockoffs.cpp:1392-1421)
-            const bool lastgrp = k.flags & KGW_KO_LASTGRP;
-            ez1 = __shfl_sync(FULL, ez1, lastgrp ? 0 : z1 / S, L);
-            const double X = lastgrp ? 0.0 : k.vs * ez1;
-            const double R = su[bit] * fma(k.vb, Qtot, X);
-            int cnt = 0;
+              // the state equal to z1 carries the extra vstar term in the draw (:1413-1419)
+              __syncwarp();
+              if (!lastg) {
+                const double rz = rrow[z1 * G + g];
+                const double nz = rz * k.fz1;
+                __syncwarp();
+                if (lig == 0) rrow[z1 * G + g] = nz;
+                if (z1 / S == lig) pls += nz - rz;
+              }
+              __syncwarp();
+              double St;
+              const double base = group_excl<L>(pls, lane, St);
+              const double t = u * St;
+              // pass D: inverse-CDF search (weighted_choice, utils.cpp:690-698) in units of vb*tg
+              double run = base;
+              int cnt = 0;
 #pragma unroll
-            for (int s = 0; s < S; s++) {
-              const double C = fma(k.vb, base + pre[s], (!lastgrp && k0 + s >= z1) ? X : 0.0);
-              cnt += (R >= C) ? 1 : 0;
+              for (int s = 0; s < S; s++) {
+                run += rrow[(k0 + s) * G + g];
+                cnt += ((!PAD || s < ns) && run <= t) ? 1 : 0;
+              }
+              zk = min(group_sum_int<L>(cnt), K - 1);
+            } else {
+              // inside a group every state has weight a*vb except k == zk_{j-1} and k == z1 (:1397-1419)
+              const double wp = k.apb * ((!lastg && z1 == zkprev) ? (k.vb + k.vs) : k.vb);
+              int pa = zkprev, pb = K;
+              double ea = wp - k.gw, eb = 0.0;
+              if (!lastg && z1 != zkprev) {
+                const double e1 = k.a * (k.vb + k.vs) - k.gw;
+                if (z1 < zkprev) { pa = z1; pb = zkprev; eb = ea; ea = e1; }
+                else { pb = z1; eb = e1; }
+              }
+              const double total = fma((double)K, k.gw, ea + eb);
+              const double R = u * total;
+              auto F = [&](double tval) -> int {  // #{k in [0,K): (k+1)*gw <= tval}
+                if (tval < 0.0) return 0;
+                if (k.gw <= 0.0) return K;
+                double q = tval * k.rgw;
+                int kf = q >= (double)K ? K : (int)q;
+                if (kf < K && (double)(kf + 1) * k.gw <= tval) kf++;
+                if (kf > 0 && (double)kf * k.gw > tval) kf--;
+                return kf;
+              };
+              int ans = F(R);
+              if (ans >= pa) {
+                ans = max(F(R - ea), pa);
+                if (ans >= pb) ans = max(F(R - ea - eb), pb);
+              }
+              zk = min(ans, K - 1);
             }
-            cnt = group_sum_int<L>(cnt);
-            const int zk = min(cnt, K - 1);
             zkprev = zk;
             if (k.flags & KGW_KO_LASTINGRP) { z0 = zj; z0k = zk; }
-            if (lig == 0) szk[bit] = (uint8_t)zk;
+            if (lig == 0) zktile[bit * G + g] = (uint8_t)zk;
+            k = kn;
           }
           __syncwarp();
-          // flush zk chunk, then knockoff alleles for the core loci of this word (lanes <-> loci)
-          unsigned bits = 0u, mask = 0u;
+          // flush the zk tile, then knockoff alleles of the core loci of this word (:1469-1502)
+          for (int i = lane; i < 8 * G; i += 32)
+            reinterpret_cast<uint32_t *>(zkb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(zktile)[i];
           const uint32_t hw = __ldg(P.Hw + hoff + wi);
-#pragma unroll
-          for (int c = 0; c < LPL; c++) {
-            const int idx = lig * LPL + c;
-            const int j = (wi << 5) + idx;
-            if (j >= lo && j < hi) {
-              const int zj = sz[idx], zkj = szk[idx];
-              zkb[j] = (uint8_t)zkj;
-              if (j >= ps.cs && j < ps.ce) {
-                const uint32_t w1 = __ldg(P.Hw + (size_t)__ldg(ref + zj) * P.stride_w + wi);
-                const uint32_t w2 = __ldg(P.Hw + (size_t)__ldg(ref + zkj) * P.stride_w + wi);
-                const int combo = ((hw >> idx) & 1u) | (((w1 >> idx) & 1u) << 1) | (((w2 >> idx) & 1u) << 2);
-                double u;
-                if (P.injected_u != nullptr) {
-                  u = P.injected_u[((size_t)hap * 3 + STREAM_HK) * (size_t)P.p + j];
-                } else {
-                  const kgw_u32x4 r = kgw_philox_block(P.seed, (uint32_t)hap, (uint32_t)(STREAM_HK | (ps.w << 2)), (uint32_t)(j >> 2));
-                  const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
-                  u = kgw_word_to_uniform(w4[j & 3]);
-                }
-                const KgwEmit &em = P.emit[j];
-                const unsigned hk = (u * em.sum[combo] < em.w0[combo]) ? 0u : 1u;  // weighted_choice, 2 weights
-                bits |= hk << idx;
-                mask |= 1u << idx;
-              }
-            }
+          const uint32_t *rw = refw + (wi & 1) * KP * G;
+          unsigned bits = 0u, mask = 0u;
+          const int elo = max(lo, ps.cs), ehi = min(hi, ps.ce);
+          for (int j = elo + lig; j < ehi; j += L) {
+            const int bit = j & 31;
+            const uint32_t w1 = rw[ztile[bit * G + g] * G + g];
+            const uint32_t w2 = rw[zktile[bit * G + g] * G + g];
+            const int combo = ((hw >> bit) & 1u) | (((w1 >> bit) & 1u) << 1) | (((w2 >> bit) & 1u) << 2);
+            const KgwEmit &em = P.emit[j];
+            const unsigned hk = (uh.get(j) * em.sum[combo] < em.w0[combo]) ? 0u : 1u;  // weighted_choice, 2 weights
+            bits |= hk << bit;
+            mask |= 1u << bit;
           }
           bits = group_or<L>(bits);
           mask = group_or<L>(mask);
@@ -532,8 +654,8 @@ __global__ void __launch_bounds__(THREADS, MINB) unrelated_kernel(const __grid_c
     if (active && (P.dbg_z != nullptr || P.dbg_zk != nullptr)) {
       __syncwarp();
       for (int j = lig; j < P.p; j += L) {
-        if (P.dbg_z) P.dbg_z[(size_t)tt * P.p + j] = zb[j];
-        if (P.dbg_zk) P.dbg_zk[(size_t)tt * P.p + j] = zkb[j];
+        if (P.dbg_z) P.dbg_z[(size_t)tt * P.p + j] = zb[(size_t)j * G + g];
+        if (P.dbg_zk) P.dbg_zk[(size_t)tt * P.p + j] = zkb[(size_t)j * G + g];
       }
     }
     __syncwarp();

@@ -1,0 +1,16 @@
+// knockoffgwas_b200/csrc/kgw_variants.h -- registry of the compiled sampler-kernel instantiations.
+#pragma once
+#include <stddef.h>
+struct KgwParams;
+typedef void (*kgw_kernel_fn)(const KgwParams);
+struct KgwVariant {
+  int L, S, B;              // lanes per haplotype, states per lane, checkpoint spacing
+  bool pad;                 // false: compiled for K == L*S exactly (no padded states)
+  int threads;              // CTA size
+  kgw_kernel_fn fn;
+  size_t smem;              // dynamic shared memory per CTA
+};
+const KgwVariant *kgw_variants_L1(int *n);
+const KgwVariant *kgw_variants_L2(int *n);
+const KgwVariant *kgw_variants_L4(int *n);
+const KgwVariant *kgw_variants_L8(int *n);

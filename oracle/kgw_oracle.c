@@ -20,7 +20,7 @@ static inline double mutate(int h, double mut_rate) {
   return (h == 1) ? (1.0 - mut_rate) : mut_rate;
 }
 
-static double next_uniform(kgw_oracle_rng *rng, int hap, int stream, int locus, int p, int w) {
+double kgw_oracle_next_uniform(kgw_oracle_rng *rng, int hap, int stream, int locus, int p, int w) {
   rng->n_draws++;
   switch (rng->mode) {
     case KGW_ORACLE_RNG_INJECTED:
@@ -101,7 +101,7 @@ static void sample_posterior_MC(const kgw_oracle_problem *P, kgw_oracle_rng *rng
     if (hap_bit(P, i, js) == 1) weights[k] = a_0_k * theta_0_k * backward[(int64_t)js * K + k];
     else weights[k] = a_0_k * (1.0 - theta_0_k) * backward[(int64_t)js * K + k];
   }
-  z[js] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_Z, js, P->p, w));
+  z[js] = kgw_oracle_weighted_choice(weights, K, kgw_oracle_next_uniform(rng, i, KGW_STREAM_Z, js, P->p, w));
 
   for (int j = js + 1; j < je; j++) { /* :1245-1260 */
     const double bj = P->b[j];
@@ -115,7 +115,7 @@ static void sample_posterior_MC(const kgw_oracle_problem *P, kgw_oracle_rng *rng
       else
         weights[k] = (a_j_k + bj * (double)(k == z[j - 1])) * (1.0 - theta_j_k) * backward[(int64_t)j * K + k];
     }
-    z[j] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_Z, j, P->p, w));
+    z[j] = kgw_oracle_weighted_choice(weights, K, kgw_oracle_next_uniform(rng, i, KGW_STREAM_Z, j, P->p, w));
   }
 }
 
@@ -228,7 +228,7 @@ static void sample_knockoff_MC(const kgw_oracle_problem *P, kgw_oracle_rng *rng,
         }
         weights[k] = wk;
       }
-      zk[j] = kgw_oracle_weighted_choice(weights, K, next_uniform(rng, i, KGW_STREAM_ZK, j, P->p, w));
+      zk[j] = kgw_oracle_weighted_choice(weights, K, kgw_oracle_next_uniform(rng, i, KGW_STREAM_ZK, j, P->p, w));
     }
     for (int k = 0; k < K; k++) N_old[k] = N[k]; /* :1424-1426 */
   }
@@ -256,7 +256,7 @@ static void sample_emission_copula(const kgw_oracle_problem *P, kgw_oracle_rng *
     }
     wb[0] = lambda * wb[0] + (1 - lambda) * (1 - p_ko1);
     wb[1] = lambda * wb[1] + (1 - lambda) * p_ko1;
-    out[j] = kgw_oracle_weighted_choice(wb, 2, next_uniform(rng, i, KGW_STREAM_HK, j, P->p, w));
+    out[j] = kgw_oracle_weighted_choice(wb, 2, kgw_oracle_next_uniform(rng, i, KGW_STREAM_HK, j, P->p, w));
   }
 }
 

@@ -57,6 +57,31 @@ int kgw_oracle_unrelated(const kgw_oracle_problem *P, kgw_oracle_rng *rng,
                          const int32_t *haps, int32_t n,
                          int32_t *z, int32_t *zk, uint8_t *hk, double *beta);
 
+/* One IBD-sharing family as generate_related_cluster() sees it (knockoffs.cpp:465-481):
+ * member list + TIDIED segments (the unchanged host code runs IbdCluster::tidy, ibd.cpp:99-189). */
+typedef struct {
+  int32_t n_members;
+  const int32_t *members;    /* absolute haplotype ids, order of metadata.related_families[f]    */
+  int32_t n_segs;
+  const int32_t *seg_jmin;   /* [n_segs] first SNP of the segment                                 */
+  const int32_t *seg_jmax;   /* [n_segs] last SNP (inclusive)                                     */
+  const int32_t *seg_off;    /* [n_segs+1] CSR offsets into seg_ids                               */
+  const int32_t *seg_ids;    /* absolute haplotype ids of each segment, ascending (std::set<int>) */
+} kgw_oracle_family;
+
+/* Related haplotypes of one family (generate_related_cluster, knockoffs.cpp:465-571: FamilyBP::run,
+ * FamilyKnockoffs::run, sample_emission with references_global).  Outputs indexed by position in
+ * F->members; any may be NULL.  z, zk: int32 [n_members][p]; hk: uint8 [n_members][row_bytes].
+ * Draws are keyed (absolute haplotype, stream, locus) exactly like the unrelated branch; in
+ * taus88 mode they are consumed in the reference's call order.
+ * Returns 0, -10 / -11 where the reference aborts ("Missing knockoff variants" /
+ * "Inconsistency found on Zk", family_knockoffs.cpp:272-291), other negatives on bad input. */
+int kgw_oracle_family_run(const kgw_oracle_problem *P, kgw_oracle_rng *rng, const kgw_oracle_family *F,
+                          int32_t *z, int32_t *zk, uint8_t *hk, int64_t *bp_sweeps);
+
+/* next uniform of the selected source (shared by both branches) */
+double kgw_oracle_next_uniform(kgw_oracle_rng *rng, int hap, int stream, int locus, int p, int w);
+
 /* weighted_choice restated (utils.cpp:690-698), exposed for unit tests. */
 int kgw_oracle_weighted_choice(const double *w, int n, double u);
 

@@ -42,6 +42,11 @@ class _Rng(C.Structure):
     ]
 
 
+class _Family(C.Structure):
+    _fields_ = [("n_members", C.c_int32), ("members", C.c_void_p), ("n_segs", C.c_int32),
+                ("seg_jmin", C.c_void_p), ("seg_jmax", C.c_void_p), ("seg_off", C.c_void_p), ("seg_ids", C.c_void_p)]
+
+
 def build(force: bool = False) -> Path:
     so = _HERE / "libkgw_oracle.so"
     srcs = [_HERE / n for n in ("kgw_oracle.c", "kgw_oracle_family.c", "kgw_rng.c", "kgw_oracle.h", "kgw_rng.h")]
@@ -55,6 +60,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(str(build()))
         _LIB.kgw_oracle_unrelated.restype = C.c_int
+        _LIB.kgw_oracle_family_run.restype = C.c_int
         _LIB.kgw_oracle_weighted_choice.restype = C.c_int
         _LIB.kgw_oracle_weighted_choice.argtypes = [C.c_void_p, C.c_int, C.c_double]
         _LIB.kgw_taus88_seed.argtypes = [C.POINTER(_Taus), C.c_uint32]
@@ -82,6 +88,10 @@ class Problem:
     unrelated: np.ndarray = None  # int32 sorted haplotype ids
     families: list = field(default_factory=list)   # list of int32 arrays (haplotype ids)
     ibd_segments: list = field(default_factory=list)  # list of (hap, j_min, j_max, bp_min, bp_max, ids)
+    # families in the reference's single-thread processing order with their TIDIED segments
+    # (IbdCluster::tidy, ibd.cpp:99-189, run by the unchanged host code): list of
+    # (members int32[], [(j_min, j_max, bp_min, bp_max, ids int32[]), ...])
+    fam_clusters: list = field(default_factory=list)
     bp: np.ndarray = None
     seed: int = 2020
     meta: dict = field(default_factory=dict)
@@ -120,6 +130,25 @@ class Problem:
         return P
 
 
+def parse_fam_clusters(raw) -> list:
+    """Inverse of the fam_clusters.i32 record written by oracle/ref_shims/wrap_probe.cpp."""
+    raw = np.asarray(raw, dtype=np.int32)
+    if len(raw) == 0:
+        return []
+    out, t = [], 1
+    for _ in range(int(raw[0])):
+        n = int(raw[t]); members = raw[t + 1:t + 1 + n].copy(); t += 1 + n
+        ns = int(raw[t]); t += 1
+        segs = []
+        for _ in range(ns):
+            jmin, jmax, bpmin, bpmax, m = (int(x) for x in raw[t:t + 5])
+            segs.append((jmin, jmax, bpmin, bpmax, raw[t + 5:t + 5 + m].copy()))
+            t += 5 + m
+        out.append((members, segs))
+    assert t == len(raw)
+    return out
+
+
 def load_probe_dump(d) -> tuple[Problem, np.ndarray, np.ndarray | None]:
     """Load a directory written by oracle/_ref/snpknock2_probe (wrap_probe.cpp).
     Returns (problem, Hk_reference uint8 [N][row_bytes], trace int32 [n][2] or None)."""
@@ -140,6 +169,7 @@ def load_probe_dump(d) -> tuple[Problem, np.ndarray, np.ndarray | None]:
         hap, jmin, jmax, bpmin, bpmax, n = (int(x) for x in raw[t:t + 6])
         segs.append((hap, jmin, jmax, bpmin, bpmax, raw[t + 6:t + 6 + n].copy()))
         t += 6 + n
+    clusters = parse_fam_clusters(rd("fam_clusters.i32", np.int32)) if (d / "fam_clusters.i32").exists() else []
     prob = Problem(
         H=rd("H.u8", np.uint8).reshape(N, rb), p=p, K=K,
         ref_local=rd("ref_local.i32", np.int32).reshape(N, W, K),
@@ -147,7 +177,7 @@ def load_probe_dump(d) -> tuple[Problem, np.ndarray, np.ndarray | None]:
         b=rd("b.f64", np.float64), mu=rd("mu.f64", np.float64), groups=rd("groups.i32", np.int32),
         win_start=rd("win_start.i32", np.int32), win_end=rd("win_end.i32", np.int32),
         unrelated=rd("unrelated.i32", np.int32), families=families, ibd_segments=segs,
-        bp=rd("bp.i32", np.int32), seed=int(meta["seed"]), meta=meta)
+        bp=rd("bp.i32", np.int32), seed=int(meta["seed"]), meta=meta, fam_clusters=clusters)
     Hk = rd("Hk.u8", np.uint8).reshape(N, rb)
     trace = None
     if (d / "trace.i32").exists() and meta.get("traced") == "1":
@@ -243,6 +273,64 @@ def run_unrelated(prob: Problem, haps=None, *, mode="philox", seed=None, injecte
     if rc != 0:
         raise RuntimeError(f"kgw_oracle_unrelated failed with {rc}")
     return Result(z, zk, hk, beta, int(R.n_draws), (R.taus.v1, R.taus.v2, R.taus.v3))
+
+
+def make_rng(prob: Problem, mode="philox", seed=None, injected=None, taus_seed=None, taus_state=None):
+    """Uniform source shared by run_unrelated / run_family.  Returns (_Rng, keep-alive object)."""
+    L = lib()
+    R = _Rng()
+    keep = None
+    if mode == "injected":
+        keep = np.ascontiguousarray(injected, dtype=np.float64)
+        assert keep.shape == (prob.N, 3, prob.p)
+        R.mode, R.injected = RNG_INJECTED, keep.ctypes.data
+    elif mode == "taus88":
+        R.mode = RNG_TAUS88
+        if taus_state is not None:
+            R.taus.v1, R.taus.v2, R.taus.v3 = taus_state
+        else:
+            L.kgw_taus88_seed(C.byref(R.taus), 341 if taus_seed is None else int(taus_seed) & 0xFFFFFFFF)
+    elif mode == "philox":
+        R.mode, R.seed = RNG_PHILOX, int(prob.seed if seed is None else seed)
+    else:
+        raise ValueError(mode)
+    return R, keep
+
+
+@dataclass
+class FamilyResult:
+    members: np.ndarray
+    z: np.ndarray
+    zk: np.ndarray
+    hk: np.ndarray
+    bp_sweeps: int
+
+
+def run_family(prob: Problem, members, segments, rng: "_Rng") -> FamilyResult:
+    """Restated generate_related_cluster for one family.  `segments`: tidied
+    [(j_min, j_max, bp_min, bp_max, ids), ...] in the reference's std::set order; `rng` from make_rng
+    (sequential modes carry their state across calls)."""
+    L = lib()
+    members = np.ascontiguousarray(members, dtype=np.int32)
+    n = len(members)
+    jmin = np.array([s[0] for s in segments], dtype=np.int32)
+    jmax = np.array([s[1] for s in segments], dtype=np.int32)
+    ids = [np.asarray(s[4], dtype=np.int32) for s in segments]
+    off = np.concatenate([[0], np.cumsum([len(x) for x in ids])]).astype(np.int32)
+    flat = np.concatenate(ids).astype(np.int32) if ids else np.zeros(0, np.int32)
+    F = _Family()
+    F.n_members, F.members, F.n_segs = n, members.ctypes.data, len(segments)
+    F.seg_jmin, F.seg_jmax, F.seg_off, F.seg_ids = jmin.ctypes.data, jmax.ctypes.data, off.ctypes.data, flat.ctypes.data
+    z = np.zeros((n, prob.p), dtype=np.int32)
+    zk = np.zeros((n, prob.p), dtype=np.int32)
+    hk = np.zeros((n, prob.row_bytes), dtype=np.uint8)
+    sweeps = C.c_int64(0)
+    P = prob._c()
+    rc = L.kgw_oracle_family_run(C.byref(P), C.byref(rng), C.byref(F), C.c_void_p(z.ctypes.data),
+                                 C.c_void_p(zk.ctypes.data), C.c_void_p(hk.ctypes.data), C.byref(sweeps))
+    if rc != 0:
+        raise RuntimeError(f"kgw_oracle_family_run failed with {rc}")
+    return FamilyResult(members, z, zk, hk, int(sweeps.value))
 
 
 def unpack_bits(rows: np.ndarray, p: int) -> np.ndarray:

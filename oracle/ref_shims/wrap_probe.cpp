@@ -151,6 +151,42 @@ void wrap_generate(Knockoffs *self, int num_threads) {
     write_raw(dir + "/ibd_segments.i32", ibd);
     std::vector<int32_t> bp(self->metadata.legend_filter.bp.begin(), self->metadata.legend_filter.bp.end());
     write_raw(dir + "/bp.i32", bp);
+    // Families in the order generate_related() processes them with one thread (knockoffs.cpp:331-372:
+    // std::set of member lists -> vector -> std::sort by size, descending), and for each family the
+    // tidied IBD segments exactly as generate_related_cluster() hands them to FamilyBP / FamilyKnockoffs
+    // (knockoffs.cpp:474-481): built here by calling the reference's own IbdCluster constructor.
+    // record per family: n_members, members..., n_segments, then per segment
+    //   j_min, j_max, bp_min, bp_max, n_ids, ids...   (segment order = std::set<IbdSeg> iteration order)
+    {
+      std::set<std::vector<int> > famset;
+      for (size_t f = 0; f < self->metadata.related_families.size(); f++) {
+        if (self->metadata.related_families[f].size() <= 1) continue;
+        famset.insert(self->metadata.related_families[f]);
+      }
+      std::vector<std::vector<int> > famvec(famset.begin(), famset.end());
+      std::sort(famvec.begin(), famvec.end(),
+                [](const std::vector<int> &a, const std::vector<int> &b) { return a.size() > b.size(); });
+      std::vector<int32_t> out;
+      out.push_back((int32_t)famvec.size());
+      for (const std::vector<int> &fam : famvec) {
+        out.push_back((int32_t)fam.size());
+        for (int i : fam) out.push_back(i);
+        std::set<IbdSeg> segs;
+        for (int i : fam)
+          for (const IbdSeg &sg : self->metadata.ibd_segments[i]) segs.insert(sg);
+        IbdCluster cluster(segs);
+        out.push_back((int32_t)cluster.size());
+        for (int t = 0; t < cluster.size(); t++) {
+          IbdSeg sg;
+          cluster.get(t, sg);
+          out.push_back(sg.j_min); out.push_back(sg.j_max);
+          out.push_back(sg.bp_min); out.push_back(sg.bp_max);
+          out.push_back((int32_t)sg.indices.size());
+          for (int id : sg.indices) out.push_back(id);
+        }
+      }
+      write_raw(dir + "/fam_clusters.i32", out);
+    }
   }
 
   const auto t0 = std::chrono::steady_clock::now();

@@ -108,7 +108,8 @@ def save_call(dump_dir: Path, name: str, note: str):
         H=prob.H, Hk=Hk, ref_local=prob.ref_local, ref_global=prob.ref_global, b=prob.b, mu=prob.mu,
         groups=prob.groups, win_start=prob.win_start, win_end=prob.win_end, unrelated=prob.unrelated,
         fam_sizes=fam_sizes, fam_members=fam_members, ibd_segments=np.array(segs, dtype=np.int32),
-        bp=prob.bp, z_unrelated=z, zk_unrelated=zk, trace_related=tr_rel)
+        bp=prob.bp, z_unrelated=z, zk_unrelated=zk, trace_related=tr_rel,
+        fam_clusters=np.fromfile(dump_dir / "fam_clusters.i32", dtype=np.int32))
     print(f"  {name}.npz  N={prob.N} p={p} K={prob.K} W={prob.W} groups={prob.groups[-1] + 1} "
           f"unrelated={nu} related_draws={len(tr_rel)}")
 

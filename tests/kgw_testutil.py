@@ -26,7 +26,8 @@ def load_golden(name: str):
         t += 6 + n
     prob = ko.Problem(H=f["H"], p=int(f["p"]), K=int(f["K"]), ref_local=f["ref_local"], ref_global=f["ref_global"],
                       b=f["b"], mu=f["mu"], groups=f["groups"], win_start=f["win_start"], win_end=f["win_end"],
-                      unrelated=f["unrelated"], families=fam, ibd_segments=segs, bp=f["bp"], seed=int(f["seed"]))
+                      unrelated=f["unrelated"], families=fam, ibd_segments=segs, bp=f["bp"], seed=int(f["seed"]),
+                      fam_clusters=ko.parse_fam_clusters(f["fam_clusters"]) if "fam_clusters" in f else [])
     return prob, f
 
 

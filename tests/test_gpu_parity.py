@@ -68,15 +68,21 @@ CASES = [
     dict(N=70, p=300, K=29, mean_group=8.0),
     dict(N=90, p=200, K=50, mean_group=1.0),
     dict(N=90, p=200, K=50, mean_group=1.0, lanes=4),
+    dict(N=90, p=200, K=50, mean_group=1.0, lanes=8, block=2),
+    dict(N=90, p=230, K=50, mean_group=4.0, lanes=2, block=8),
+    dict(N=70, p=200, K=25, mean_group=1.0, lanes=1),
+    dict(N=70, p=200, K=32, mean_group=3.0, lanes=1, block=8),
+    dict(N=33, p=70, K=10, mean_group=1.0, lanes=1),
+    dict(N=33, p=70, K=10, mean_group=2.0, lanes=8),
     dict(N=90, p=260, K=56, mean_group=2.0, tiny_dist_frac=0.5),
     dict(N=120, p=190, K=64, mean_group=5.0),
     dict(N=150, p=150, K=100, mean_group=1.0),
     dict(N=150, p=150, K=128, mean_group=30.0),
     dict(N=300, p=96, K=200, mean_group=1.0),
     dict(N=60, p=400, K=12, mean_group=4.0, W=3),
-    dict(N=60, p=333, K=50, mean_group=2.0, W=4, block=4),
-    dict(N=50, p=300, K=20, mean_group=1.0, block=16),
-    dict(N=50, p=300, K=20, mean_group=6.0, block=32),
+    dict(N=60, p=333, K=50, mean_group=2.0, W=4, block=2),
+    dict(N=50, p=300, K=20, mean_group=1.0, block=8),
+    dict(N=50, p=300, K=20, mean_group=6.0, block=2),
     dict(N=30, p=1, K=5, mean_group=1.0),
     dict(N=30, p=2, K=5, mean_group=1.0),
     dict(N=30, p=33, K=5, mean_group=50.0),
@@ -126,7 +132,7 @@ def test_shard_independence_and_determinism():
     sub, _ = kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups,
                          unrelated=part, seed=prob.seed)
     assert np.array_equal(sub[part], full[part])
-    alt, _ = _run(prob, options=kg.Options(lanes_per_hap=4, block_loci=16))
+    alt, _ = _run(prob, options=kg.Options(lanes_per_hap=4, block_loci=8))
     assert np.array_equal(alt, full)
 
 

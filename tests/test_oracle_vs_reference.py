@@ -78,3 +78,28 @@ def test_weighted_choice_semantics():
     assert pick(0.999999) == 3
     z = np.zeros(3)
     assert L.kgw_oracle_weighted_choice(z.ctypes.data, 3, C.c_double(0.3)) == 2  # fallback: last index
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_oracle_reproduces_reference_related(name):
+    """IBD-conditioned branch (FamilyBP + FamilyKnockoffs + sample_emission): with --n_threads 1 the
+    reference seeds one taus88 with --seed (knockoffs.cpp:419-420) and walks the families in the order
+    dumped by the probe.  Replaying that stream through oracle/kgw_oracle_family.c must reproduce the
+    related haplotypes' knockoffs bit for bit and consume exactly as many draws as the reference made."""
+    prob, f = load_golden(name)
+    assert len(prob.fam_clusters) > 0
+    rng, _ = ko.make_rng(prob, mode="taus88", taus_seed=prob.seed)
+    seen = []
+    for members, segs in prob.fam_clusters:
+        r = ko.run_family(prob, members, segs, rng)
+        assert np.array_equal(r.hk, f["Hk"][members]), f"family {members.tolist()}: knockoffs differ from reference"
+        # Z / Zk agree on every IBD segment (the reference aborts otherwise, family_knockoffs.cpp:282-291)
+        loc = {int(h): i for i, h in enumerate(members)}
+        for (jmin, jmax, _, _, ids) in segs:
+            rows = [loc[int(h)] for h in ids]
+            assert (r.z[rows, jmin:jmax + 1] == r.z[rows[0], jmin:jmax + 1]).all()
+            assert (r.zk[rows, jmin:jmax + 1] == r.zk[rows[0], jmin:jmax + 1]).all()
+        seen += members.tolist()
+    assert rng.n_draws == len(f["trace_related"])
+    related = np.setdiff1d(np.arange(prob.N), prob.unrelated)
+    assert sorted(seen) == related.tolist()
