@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--skip-sweeps", type=int, default=0, help="development only: timing experiments, results invalid")
     return ap.parse_args()
 
 
@@ -221,7 +222,7 @@ def run_b200_arm(a, rank, local_rank, world):
 
     stream = torch.cuda.Stream(device=dev)
     opts = kg.Options(device=local_rank, block_loci=a.block_loci, lanes_per_hap=a.lanes, ctas_per_sm=a.ctas_per_sm,
-                      stream=stream.cuda_stream)
+                      stream=stream.cuda_stream, skip_sweeps=a.skip_sweeps)
     plan = kg.Plan(prob.H, p, K, prob.ref[:, None, :], prob.b, prob.mu, prob.groups, seed=prob.seed, options=opts)
     info = plan.info()
     hk_bytes = N * info["row_stride_bytes"]

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGW_ABI_VERSION 1
+#define KGW_ABI_VERSION 2
 
 /* status codes (negative = error; kgw_last_error() has the text) */
 enum {
@@ -47,6 +47,23 @@ enum {
  * --windows > 0 the padded window passes (knockoffs.cpp:1222-1226) overlap; pass w uses
  * stream word `stream | (w << 2)` so no uniform is consumed twice. */
 enum { KGW_STREAM_Z = 0, KGW_STREAM_ZK = 1, KGW_STREAM_HK = 2, KGW_STREAM_FAMILY = 3 };
+
+/* IBD-sharing families for the related branch (Knockoffs::generate_related, knockoffs.cpp:329-571).
+ * The unchanged host code builds, per family, the member list (metadata.related_families,
+ * metadata.cpp:242-293) and its TIDIED segments (IbdCluster(ibd_segments), knockoffs.cpp:474-481,
+ * ibd.cpp:99-189) and passes them flat; segment order = iteration order of the reference's
+ * std::set<IbdSeg> (IbdCluster::get(s), s = 0..size-1). */
+typedef struct kgw_families {
+  int32_t n_families;
+  int32_t reserved;
+  const int32_t *fam_off;      /* [n_families+1] CSR into fam_members                                */
+  const int32_t *fam_members;  /* absolute haplotype ids, order of metadata.related_families[f]      */
+  const int32_t *seg_off;      /* [n_families+1] CSR into seg_jmin / seg_jmax / seg_ids_off          */
+  const int32_t *seg_jmin;     /* [n_segments] IbdSeg::j_min                                         */
+  const int32_t *seg_jmax;     /* [n_segments] IbdSeg::j_max (inclusive)                             */
+  const int32_t *seg_ids_off;  /* [n_segments+1] CSR into seg_ids                                    */
+  const int32_t *seg_ids;      /* IbdSeg::indices (absolute haplotype ids, ascending)                */
+} kgw_families;
 
 /* What Knockoffs::generate() reads. */
 typedef struct kgw_problem {
@@ -74,6 +91,9 @@ typedef struct kgw_problem {
   /* test hook: if non-NULL, U[N][3][p] doubles in [0,1) replace the generator for the
    * unrelated branch (stream order KGW_STREAM_Z, _ZK, _HK; indexed by absolute haplotype). */
   const double *injected_u;
+  /* related haplotypes (NULL or n_families == 0: none).  Needs ref_global.  Their draws use the same
+   * keyed generator: (member haplotype, KGW_STREAM_Z / _ZK / _HK, locus). */
+  const kgw_families *families;
 } kgw_problem;
 
 typedef struct kgw_options {
@@ -103,8 +123,10 @@ int32_t kgw_abi_version(void);
 const char *kgw_last_error(void);
 
 /* One-shot drop-in for Knockoffs::generate(): host buffers in, host buffer out.
- * hk_out is [N][row_bytes]; only the rows listed in `unrelated` are written (the body of
- * generate_unrelated, knockoffs.cpp:573-700).  H2D, kernels and D2H all inside. */
+ * hk_out is [N][row_bytes]; the rows listed in `unrelated` (generate_unrelated, knockoffs.cpp:573-700)
+ * and the members of `families` (generate_related, :329-571) are written.  H2D, kernels and D2H all
+ * inside.  Returns KGW_ERR_INVALID with the reference's own message where the reference aborts
+ * ("Missing knockoff variants" / "Inconsistency found on Zk", family_knockoffs.cpp:272-291). */
 int32_t kgw_generate(const kgw_problem *prob, const kgw_options *opt, uint8_t *hk_out, kgw_debug *dbg);
 
 /* Resident-data path (bench / repeated resolutions): upload once, run many times. */
@@ -133,6 +155,10 @@ typedef struct kgw_plan_info_t {
 } kgw_plan_info_t;
 int32_t kgw_plan_info(kgw_plan *plan, kgw_plan_info_t *out);
 void kgw_plan_destroy(kgw_plan *plan);
+
+/* A destroyed plan parks its scratch slab (tens of GB) for the next plan on the same device, because
+ * Knockoffs::generate() runs once per resolution (main.cpp:159-181); this frees the parked slabs. */
+void kgw_release_workspace(void);
 
 /* Host replay of the generator (bit-identical to the device code). */
 double kgw_uniform(uint64_t seed, uint32_t hap, uint32_t stream, uint32_t locus);

@@ -7,7 +7,7 @@ tests and the benchmark.  There is no CPU fallback: without the CUDA library / a
 call raises.
 """
 from .api import (KgwError, Knockoffs, Options, Plan, abi_version, generate, generate_into, lib_path, load_library,
-                  uniform)
+                  release_workspace, uniform)
 
 __all__ = ["KgwError", "Knockoffs", "Options", "Plan", "abi_version", "generate", "generate_into", "lib_path",
-           "load_library", "uniform"]
+           "load_library", "release_workspace", "uniform"]

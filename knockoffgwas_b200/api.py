@@ -60,11 +60,13 @@ class Options:
     lanes_per_hap: int = 0
     ctas_per_sm: int = 0
     stream: int = 0   # cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); 0 = plan-owned
+    skip_sweeps: int = 0  # development timing experiments only: bit s set = skip sweep s+1 (results invalid)
 
     def _c(self) -> _Options:
         o = _Options()
         o.device, o.block_loci, o.lanes_per_hap, o.ctas_per_sm = self.device, self.block_loci, self.lanes_per_hap, self.ctas_per_sm
         o.stream = self.stream or None
+        o.reserved[0] = self.skip_sweeps
         return o
 
 
@@ -103,6 +105,7 @@ def load_library():
         L.kgw_plan_device_hk.argtypes = [C.c_void_p]
         L.kgw_plan_info.restype = C.c_int32
         L.kgw_plan_info.argtypes = [C.c_void_p, C.POINTER(_PlanInfo)]
+        L.kgw_release_workspace.restype = None
         L.kgw_plan_destroy.restype = None
         L.kgw_plan_destroy.argtypes = [C.c_void_p]
         if L.kgw_abi_version() != KGW_ABI_VERSION:
@@ -118,6 +121,11 @@ def abi_version() -> int:
 def uniform(seed: int, hap: int, stream: int, locus: int) -> float:
     """Host replay of the device generator."""
     return load_library().kgw_uniform(int(seed), int(hap), int(stream), int(locus))
+
+
+def release_workspace():
+    """Free the scratch slabs parked by destroyed plans (kgw_release_workspace)."""
+    load_library().kgw_release_workspace()
 
 
 def _check(rc: int):

@@ -9,6 +9,7 @@
 #include "kgw_variants.h"
 
 #include <algorithm>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -57,6 +58,40 @@ const KgwVariant *pick_variant(int K, int lanes, int B) {
   return best;
 }
 
+// Scratch slab cache: the checkpoint / partial-sum / latent-path scratch of a plan is tens of GB and
+// cudaMalloc + cudaFree of it costs more than the kernel; Knockoffs::generate() is called once per
+// resolution (main.cpp:159-181), so a destroyed plan parks its slab here for the next one on that device.
+struct SlabCache {
+  std::mutex mu;
+  void *ptr[16] = {};
+  size_t bytes[16] = {};
+  void *take(int dev, size_t need, size_t *got) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 16 || !ptr[dev]) return nullptr;
+    void *p = ptr[dev];
+    *got = bytes[dev];
+    ptr[dev] = nullptr;
+    bytes[dev] = 0;
+    if (*got >= need) return p;
+    cudaFree(p);
+    return nullptr;
+  }
+  void give(int dev, void *p, size_t n) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 16 || (ptr[dev] && bytes[dev] >= n)) { cudaFree(p); return; }
+    if (ptr[dev]) cudaFree(ptr[dev]);
+    ptr[dev] = p;
+    bytes[dev] = n;
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (int d = 0; d < 16; d++)
+      if (ptr[d]) { cudaSetDevice(d); cudaFree(ptr[d]); ptr[d] = nullptr; bytes[d] = 0; }
+  }
+};
+SlabCache g_slabs;
+
 struct Tables {
   std::vector<KgwLocusHMM> hmm;
   std::vector<KgwLocusKO> ko;
@@ -104,8 +139,8 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
         double sum = 0.0;
         sum += w0;
         sum += w1;  // std::accumulate(w.begin(), w.end(), 0.0), utils.cpp:691
-        T.emit[j].w0[c] = w0;
-        T.emit[j].sum[c] = sum;
+        T.emit[j].ws[c].x = w0;
+        T.emit[j].ws[c].y = sum;
       }
     }
   }
@@ -221,6 +256,8 @@ struct kgw_plan {
   KgwEmit *demit = nullptr;
   KgwPass *dpass = nullptr;
   double *dckpt = nullptr, *dinj = nullptr, *dse = nullptr;
+  void *slab = nullptr;      // one allocation behind dckpt / dse / dz / dzk
+  size_t slab_bytes = 0;
   uint8_t *dz = nullptr, *dzk = nullptr;
   int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
   double *ddbg_beta = nullptr;
@@ -231,7 +268,9 @@ struct kgw_plan {
   ~kgw_plan() {
     cudaSetDevice(device);
     cudaFree(dHw); cudaFree(dHk); cudaFree(dref); cudaFree(dhaps); cudaFree(dhmm); cudaFree(dko);
-    cudaFree(demit); cudaFree(dpass); cudaFree(dckpt); cudaFree(dinj); cudaFree(dse); cudaFree(dz); cudaFree(dzk);
+    cudaFree(demit); cudaFree(dpass); cudaFree(dinj);
+    if (stream) cudaStreamSynchronize(stream);
+    g_slabs.give(device, slab, slab_bytes);
     cudaFree(ddbg_z); cudaFree(ddbg_zk); cudaFree(ddbg_beta);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -308,8 +347,8 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   if (opt) o = *opt;
   if (o.lanes_per_hap != 0 && o.lanes_per_hap != 1 && o.lanes_per_hap != 2 && o.lanes_per_hap != 4 && o.lanes_per_hap != 8)
     return fail(KGW_ERR_INVALID, "lanes_per_hap must be 0 (auto), 1, 2, 4 or 8");
-  if (o.block_loci != 0 && o.block_loci != 2 && o.block_loci != 8)
-    return fail(KGW_ERR_INVALID, "block_loci must be 0 (auto), 2 or 8");
+  if (o.block_loci != 0 && o.block_loci != 1 && o.block_loci != 2 && o.block_loci != 8)
+    return fail(KGW_ERR_INVALID, "block_loci must be 0 (auto), 1, 2 or 8");
   int B = o.block_loci;  // 0: decided below from the scratch budget
   if (!pick_variant(K, o.lanes_per_hap, 2) && !pick_variant(K, o.lanes_per_hap, 8))
     return fail(KGW_ERR_UNSUPPORTED, "no kernel variant for this K / lanes_per_hap");
@@ -408,10 +447,22 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   const size_t ckpt_stride = (size_t)pl->nblk * var->L * var->S * G;
   const size_t se_stride = (size_t)p * 32;
   const size_t z_stride = ((size_t)p + 31) / 32 * 32 * G;
-  KGW_CUDA_PL(cudaMalloc(&pl->dckpt, sizeof(double) * ckpt_stride * slots));
-  KGW_CUDA_PL(cudaMalloc(&pl->dse, sizeof(double) * se_stride * slots));
-  KGW_CUDA_PL(cudaMalloc(&pl->dz, z_stride * slots));
-  KGW_CUDA_PL(cudaMalloc(&pl->dzk, z_stride * slots));
+  {
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t b_ck = up(sizeof(double) * ckpt_stride * slots), b_se = up(sizeof(double) * se_stride * slots);
+    const size_t b_z = up(z_stride * slots);
+    const size_t need = b_ck + b_se + 2 * b_z;
+    pl->slab = g_slabs.take(pl->device, need, &pl->slab_bytes);
+    if (!pl->slab) {
+      KGW_CUDA_PL(cudaMalloc(&pl->slab, need));
+      pl->slab_bytes = need;
+    }
+    unsigned char *base = (unsigned char *)pl->slab;
+    pl->dckpt = (double *)base;
+    pl->dse = (double *)(base + b_ck);
+    pl->dz = base + b_ck + b_se;
+    pl->dzk = base + b_ck + b_se + b_z;
+  }
   KGW_CUDA_PL(cudaMemsetAsync(pl->dz, 0, z_stride * slots, pl->stream));
   KGW_CUDA_PL(cudaMemsetAsync(pl->dzk, 0, z_stride * slots, pl->stream));
 
@@ -436,6 +487,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   P.dbg_z = P.dbg_zk = nullptr;
   P.dbg_beta = nullptr;
   P.dbg_nblk = 0;
+  P.skip_sweeps = o.reserved[0];  // development timing experiments only (0 in production)
 
   int rc = upload_partition(pl, prob->groups, true);
   if (rc != KGW_OK) return guard_fail(rc);
@@ -569,6 +621,8 @@ int32_t kgw_plan_download(kgw_plan *pl, uint8_t *hk_out, kgw_debug *dbg) {
 }
 
 void kgw_plan_destroy(kgw_plan *pl) { delete pl; }
+
+void kgw_release_workspace(void) { g_slabs.clear(); }
 
 int32_t kgw_generate(const kgw_problem *prob, const kgw_options *opt, uint8_t *hk_out, kgw_debug *dbg) {
   kgw_plan *pl = nullptr;

@@ -59,9 +59,8 @@ struct __align__(16) KgwLocusKO {  // per (window pass, locus of the padded rang
 };
 
 struct __align__(16) KgwEmit {  // sample_emission_copula (knockoffs.cpp:1469-1502) tabulated per locus:
-  double w0[8];                 // weights_binary[0] for combo c = h | r_z<<1 | r_zk<<2
-  double sum[8];                // 0.0 + weights_binary[0] + weights_binary[1]
-};
+  double2 ws[8];                // combo c = h | r_z<<1 | r_zk<<2:  x = weights_binary[0],
+};                              //                                   y = 0.0 + weights_binary[0] + weights_binary[1]
 
 struct KgwPass {
   int32_t js, je;   // padded range [js, je)           knockoffs.cpp:1222-1226
@@ -95,7 +94,7 @@ struct KgwParams {
   int32_t *dbg_z, *dbg_zk;   // [n_haps][p] or null
   double *dbg_beta;          // [n_haps][nblk][K] or null (last pass)
   int32_t dbg_nblk;
-  int32_t pad;
+  int32_t skip_sweeps;       // development only: bit s set = skip sweep s+1 (timing experiments; results invalid)
 };
 
 namespace kgw {
@@ -154,6 +153,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return y;
 }
 
+// cnt += (v <= t): one DSETP and one predicated integer add (the compiler otherwise builds bit masks)
+__device__ __forceinline__ void count_le(int &cnt, double v, double t) {
+  asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "d"(v), "d"(t));
+}
+
 __device__ __forceinline__ void cp_async4(void *dst, const void *src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
@@ -168,7 +172,7 @@ template <int L, int S, int B>
 struct Cfg {
   static constexpr int G = 32 / L;
   static constexpr int KP = L * S;
-  // per-warp shared memory: B message rows + 1 checkpoint staging row (sweep 2) / 1 reciprocal row
+  // per-warp shared memory: B-1 recomputed message rows + 2 checkpoint staging rows (sweep 2) / 1 reciprocal row
   // (sweep 3), two reference-word tiles, two staging tiles of per-lane sums, two latent-path tiles
   static constexpr size_t rows_bytes = (size_t)(B + 1) * KP * G * 8;
   static constexpr size_t refw_bytes = (size_t)2 * KP * G * 4;
@@ -224,8 +228,8 @@ __device__ __forceinline__ double emit_and_sum(double (&beta)[S], const uint32_t
 
 // PAD = false asserts K == L*S (no padded states: the per-state guards compile away);
 // WPC = maximum warps per CTA, fewer may be launched
-template <int L, int S, int B, bool PAD, int WPC>
-__global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant__ KgwParams P) {
+template <int L, int S, int B, bool PAD, int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_constant__ KgwParams P) {
   using C = Cfg<L, S, B>;
   constexpr int G = C::G;
   constexpr int KP = C::KP;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *ws = smem_raw + (size_t)wic * C::warp_bytes();
   double *rows = reinterpret_cast<double *>(ws);                                  // [B+1][KP][G]
-  double *ckst = rows + (size_t)B * KP * G;                                       // checkpoint staging row
+  double *ckst = rows + (size_t)(B - 1) * KP * G;                                 // [2][KP][G] checkpoint staging
   uint32_t *refw = reinterpret_cast<uint32_t *>(ws + C::rows_bytes);              // [2][KP][G]
   double *sest = reinterpret_cast<double *>(ws + C::rows_bytes + C::refw_bytes);  // [2][B][32]
   uint8_t *ztile = ws + C::rows_bytes + C::refw_bytes + C::se_bytes;              // [32][G]
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
       };
 
       // ------------------------------------------------------------------ sweep 1: backward + checkpoints
-      {
+      if (!(P.skip_sweeps & 1)) {
         double beta[S];
         uint32_t mw[S];
 #pragma unroll
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
       }
 
       // ------------------------------------------------------------------ sweep 2: recompute + draw z
-      {
+      if (!(P.skip_sweeps & 2)) {
         double beta[S];
         uint32_t mw[S];
         UniformSrc us;
@@ -373,11 +377,13 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
         for (int i = lane; i < 8 * G; i += 32)
           reinterpret_cast<uint32_t *>(ztile)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
         __syncwarp();
-        // checkpoint and per-lane sums of block n -> staging (asynchronous, one block ahead)
+        // checkpoint (= messages of the block's top locus) and per-lane sums of block n -> staging
+        // (asynchronous, one block ahead)
         auto prefetch_block = [&](int n) {
+          double *dst = ckst + (size_t)(n & 1) * KP * G;
 #pragma unroll
           for (int s = 0; s < S; s++)
-            cp_async8(ckst + (k0 + s) * G + g, ck + ((size_t)n * KP + k0 + s) * G + g);
+            cp_async8(dst + (k0 + s) * G + g, ck + ((size_t)n * KP + k0 + s) * G + g);
           const int lo_n = max(n * B, js), top_n = min(n * B + B, je) - 1;
           for (int j = lo_n; j <= top_n; j++)
             cp_async8(sest + ((n & 1) * B + (j - n * B)) * 32 + lane, se + (size_t)j * 32 + lane);
@@ -385,6 +391,7 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
         const int n_last = (je - 1) / B;
         prefetch_block(js / B);
         KgwLocusHMM hj = P.hmm[js];
+        KgwLocusHMM hrec = P.hmm[min((js / B) * B + B, je) - 1];
         for (int n = js / B; n <= n_last; n++) {
           const int nb = n * B;
           const int lo = max(nb, js);
@@ -404,19 +411,19 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
             for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
             if (wi < whi) prefetch_words(wi + 1, (wi + 1) & 1);
           }
-          // staged checkpoint -> registers and the row of the block's top locus, then B-1 recomputed steps
           cp_async_wait_all();
           __syncwarp();
-#pragma unroll
-          for (int s = 0; s < S; s++) {
-            beta[s] = ckst[(k0 + s) * G + g];
-            rows[((top - nb) * KP + k0 + s) * G + g] = beta[s];
-          }
-          __syncwarp();
           if (n < n_last) prefetch_block(n + 1);
+          const double *toprow = ckst + (size_t)(n & 1) * KP * G;
+          const KgwLocusHMM hrec_next = P.hmm[min(nb + 2 * B, je) - 1];  // top locus of the next block
           if (B > 1) {
+            // B-1 recomputed steps below the staged top row
+#pragma unroll
+            for (int s = 0; s < S; s++) beta[s] = toprow[(k0 + s) * G + g];
+            KgwLocusHMM hr = hrec;
             for (int m = top; m > lo; m--) {
-              const KgwLocusHMM h = P.hmm[m];
+              const KgwLocusHMM h = hr;
+              hr = P.hmm[m - 1];
               const double pl = emit_and_sum<S, PAD>(beta, mw, 1u << (m & 31), h.omm, h.mu, ns);
               const double Se = group_sum<L>(pl);
               const double c = h.a * Se;
@@ -426,8 +433,9 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
                 rows[((m - 1 - nb) * KP + k0 + s) * G + g] = beta[s];
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
+          hrec = hrec_next;
           // forward draws through the block (knockoffs.cpp:1232-1260)
           for (int j = lo; j <= top; j++) {
             const KgwLocusHMM h = hj;
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
             const uint32_t bm = 1u << (j & 31);
             const bool hbit = hw & bm;
             const double amis = hbit ? h.amu : h.amup;
-            const double *row = rows + (size_t)(j - nb) * KP * G;
+            const double *row = (j == top) ? toprow : rows + (size_t)(j - nb) * KP * G;
             const double pl = sest[((n & 1) * B + (j - nb)) * 32 + lane];
             double Se;
             const double base = group_excl<L>(pl, lane, Se);
@@ -454,8 +462,8 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
             for (int s = 0; s < S; s++) {
               const double e = row[(k0 + s) * G + g] * ((mw[s] & bm) ? h.aomm : amis);
               run += e;
-              cA += (run <= tA) ? 1 : 0;
-              cB += (run <= tB) ? 1 : 0;
+              count_le(cA, run, tA);
+              count_le(cB, run, tB);
             }
             const int cc = group_sum_int<L>(cA | (cB << 16));
             const int k1 = cc & 0xffff, k2 = cc >> 16;
@@ -472,7 +480,7 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
       __syncwarp();
 
       // ------------------------------------------------------------------ sweep 3: knockoff path + alleles
-      {
+      if (!(P.skip_sweeps & 4)) {
         double Nv[S];
 #pragma unroll
         for (int s = 0; s < S; s++) Nv[s] = 1.0;  // knockoffs.cpp:1293-1294 (N == N_old between groups)
@@ -489,13 +497,30 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
           if (zi >= 0) z1_pref = zb[(size_t)zi * G + g];
         }
         prefetch_words(wlo, wlo & 1);
+        constexpr int TW = (8 * G + 31) / 32;  // 32-bit words of a latent-path tile per lane
+        uint32_t zreg[TW], zkreg[TW];
+#pragma unroll
+        for (int i = 0; i < TW; i++) {
+          const bool in = (G >= 4) || (lane + 32 * i < 8 * G);
+          zreg[i] = in ? reinterpret_cast<const uint32_t *>(zb + (size_t)(wlo << 5) * G)[lane + 32 * i] : 0u;
+          zkreg[i] = in ? reinterpret_cast<const uint32_t *>(zkb + (size_t)(wlo << 5) * G)[lane + 32 * i] : 0u;
+        }
         for (int wi = wlo; wi <= whi; wi++) {
           const int lo = max(wi << 5, js), hi = min((wi << 5) + 32, je);
           __syncwarp();
-          for (int i = lane; i < 8 * G; i += 32)
-            reinterpret_cast<uint32_t *>(ztile)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
-          for (int i = lane; i < 8 * G; i += 32)
-            reinterpret_cast<uint32_t *>(zktile)[i] = reinterpret_cast<const uint32_t *>(zkb + (size_t)(wi << 5) * G)[i];
+          // latent-path tiles of this word (loaded into registers one word ahead), then prefetch the next
+#pragma unroll
+          for (int i = 0; i < TW; i++) {
+            reinterpret_cast<uint32_t *>(ztile)[lane + 32 * i] = zreg[i];
+            reinterpret_cast<uint32_t *>(zktile)[lane + 32 * i] = zkreg[i];
+          }
+          if (wi < whi) {
+#pragma unroll
+            for (int i = 0; i < TW; i++) {
+              zreg[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)((wi + 1) << 5) * G)[lane + 32 * i];
+              zkreg[i] = reinterpret_cast<const uint32_t *>(zkb + (size_t)((wi + 1) << 5) * G)[lane + 32 * i];
+            }
+          }
           cp_async_wait_all();
           __syncwarp();
           if (wi < whi) prefetch_words(wi + 1, (wi + 1) & 1);
@@ -547,12 +572,14 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
               const double Sr = group_sum<L>(pls);
               const double Nsum = (k.flags & KGW_KO_GSTART) ? k.sa : k.tg * Sr;  // :1345-1358
               const double c2 = k.vb * Nsum;
-              // pass B: partition function update and normaliser (:1360-1390)
+              // pass B: partition function update and normaliser (:1360-1390).  The last group keeps N
+              // (zero coefficients make the update an exact identity) but still renormalises it.
+              const double c2u = lastg ? 0.0 : c2;
+              const double vsu = lastg ? 0.0 : k.vstg;
               double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
 #pragma unroll
               for (int s = 0; s < S; s++) {
-                double nv = Nv[s];
-                if (!lastg) nv = fma(k.vstg, rrow[(k0 + s) * G + g], nv + c2);
+                double nv = fma(vsu, rrow[(k0 + s) * G + g], Nv[s] + c2u);
                 nv = (!PAD || s < ns) ? nv : 0.0;
                 Nv[s] = nv;
                 if ((s & 3) == 0) b0 += nv;
@@ -561,10 +588,18 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
                 else b3 += nv;
               }
               const double rN = 1.0 / group_sum<L>((b0 + b1) + (b2 + b3));
+              // pass C: normalise; clamp to N_min (:1386-1389; the pre-normalisation clamp of :1380 cannot
+              // fire because N only grows).  The clamp is exact but rarely needed: a cheap integer minimum of
+              // the high words decides whether any state can be below N_min.
+              int hmin = 0x7fffffff;
 #pragma unroll
               for (int s = 0; s < S; s++) {
-                const double v = Nv[s] * rN;
-                Nv[s] = (v < N_MIN) ? N_MIN : v;  // (the pre-normalisation clamp of :1380 cannot fire: N only grows)
+                Nv[s] *= rN;
+                if (!PAD || s < ns) hmin = min(hmin, __double2hiint(Nv[s]));
+              }
+              if (hmin <= __double2hiint(N_MIN)) {
+#pragma unroll
+                for (int s = 0; s < S; s++) Nv[s] = (Nv[s] < N_MIN) ? N_MIN : Nv[s];
               }
               // the state equal to z1 carries the extra vstar term in the draw (:1413-1419)
               __syncwarp();
@@ -585,7 +620,7 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
 #pragma unroll
               for (int s = 0; s < S; s++) {
                 run += rrow[(k0 + s) * G + g];
-                cnt += ((!PAD || s < ns) && run <= t) ? 1 : 0;
+                if (!PAD || s < ns) count_le(cnt, run, t);
               }
               zk = min(group_sum_int<L>(cnt), K - 1);
             } else {
@@ -629,13 +664,14 @@ __global__ void __launch_bounds__(32 * WPC) sampler_kernel(const __grid_constant
           const uint32_t *rw = refw + (wi & 1) * KP * G;
           unsigned bits = 0u, mask = 0u;
           const int elo = max(lo, ps.cs), ehi = min(hi, ps.ce);
+#pragma unroll 4
           for (int j = elo + lig; j < ehi; j += L) {
             const int bit = j & 31;
             const uint32_t w1 = rw[ztile[bit * G + g] * G + g];
             const uint32_t w2 = rw[zktile[bit * G + g] * G + g];
             const int combo = ((hw >> bit) & 1u) | (((w1 >> bit) & 1u) << 1) | (((w2 >> bit) & 1u) << 2);
-            const KgwEmit &em = P.emit[j];
-            const unsigned hk = (uh.get(j) * em.sum[combo] < em.w0[combo]) ? 0u : 1u;  // weighted_choice, 2 weights
+            const double2 em = P.emit[j].ws[combo];
+            const unsigned hk = (uh.get(j) * em.y < em.x) ? 0u : 1u;  // weighted_choice with 2 weights
             bits |= hk << bit;
             mask |= 1u << bit;
           }
