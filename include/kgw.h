@@ -115,6 +115,9 @@ typedef struct kgw_debug {
   int32_t *ckpt_locus;   /* [n_ckpt] the loci those rows belong to                             */
   int32_t n_ckpt;        /* in: capacity of the two arrays above; out: rows written            */
   int32_t reserved;
+  int32_t *fam_z;        /* [total family members][p] latent paths of the related haplotypes, rows in
+                            fam_members order (FamilyBP::run, family_bp.cpp:79)                  */
+  int32_t *fam_zk;       /* [total family members][p] their knockoff paths (family_knockoffs.cpp:77) */
 } kgw_debug;
 
 typedef struct kgw_plan kgw_plan;

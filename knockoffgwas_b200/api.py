@@ -15,7 +15,7 @@ import numpy as np
 _PKG = Path(__file__).resolve().parent
 _LIB = None
 
-KGW_ABI_VERSION = 1
+KGW_ABI_VERSION = 2
 STREAM_Z, STREAM_ZK, STREAM_HK, STREAM_FAMILY = 0, 1, 2, 3
 
 
@@ -23,6 +23,12 @@ class KgwError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"kgw error {code}: {msg}")
         self.code = code
+
+
+class _Families(C.Structure):
+    _fields_ = [("n_families", C.c_int32), ("reserved", C.c_int32), ("fam_off", C.c_void_p), ("fam_members", C.c_void_p),
+                ("seg_off", C.c_void_p), ("seg_jmin", C.c_void_p), ("seg_jmax", C.c_void_p),
+                ("seg_ids_off", C.c_void_p), ("seg_ids", C.c_void_p)]
 
 
 class _Problem(C.Structure):
@@ -33,7 +39,7 @@ class _Problem(C.Structure):
         ("b", C.c_void_p), ("mu", C.c_void_p), ("groups", C.c_void_p),
         ("win_start", C.c_void_p), ("win_end", C.c_void_p), ("unrelated", C.c_void_p),
         ("n_unrelated", C.c_int32), ("reserved1", C.c_int32), ("seed", C.c_uint64),
-        ("injected_u", C.c_void_p),
+        ("injected_u", C.c_void_p), ("families", C.POINTER(_Families)),
     ]
 
 
@@ -50,7 +56,7 @@ class _PlanInfo(C.Structure):
 
 class _Debug(C.Structure):
     _fields_ = [("z", C.c_void_p), ("zk", C.c_void_p), ("beta_ckpt", C.c_void_p), ("ckpt_locus", C.c_void_p),
-                ("n_ckpt", C.c_int32), ("reserved", C.c_int32)]
+                ("n_ckpt", C.c_int32), ("reserved", C.c_int32), ("fam_z", C.c_void_p), ("fam_zk", C.c_void_p)]
 
 
 @dataclass
@@ -137,7 +143,7 @@ class _Held:
     """Keeps the numpy buffers behind a kgw_problem alive."""
 
     def __init__(self, H, p, K, ref_local, b, mu, groups, win_start=None, win_end=None, unrelated=None,
-                 ref_global=None, seed=2020, injected_u=None):
+                 ref_global=None, seed=2020, injected_u=None, families=None):
         self.H = np.ascontiguousarray(H, dtype=np.uint8)
         assert self.H.ndim == 2
         self.N, self.row_bytes = (int(x) for x in self.H.shape)
@@ -159,6 +165,27 @@ class _Held:
         if injected_u is not None:
             self.injected_u = np.ascontiguousarray(injected_u, dtype=np.float64)
             assert self.injected_u.shape == (self.N, 3, self.p)
+        self.fam = None
+        if families:
+            # families: [(members, [(j_min, j_max, ..., ids) | (j_min, j_max, ids), ...]), ...] -- member lists in
+            # metadata.related_families order, TIDIED segments in the reference's std::set<IbdSeg> order
+            i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
+            mem = [i32(m) for m, _ in families]
+            segs = [sg for _, sl in families for sg in sl]
+            ids = [i32(sg[-1]) for sg in segs]
+            self._fam_arrays = dict(
+                fam_off=i32(np.concatenate([[0], np.cumsum([len(m) for m in mem])])),
+                fam_members=i32(np.concatenate(mem)),
+                seg_off=i32(np.concatenate([[0], np.cumsum([len(sl) for _, sl in families])])),
+                seg_jmin=i32([sg[0] for sg in segs]), seg_jmax=i32([sg[1] for sg in segs]),
+                seg_ids_off=i32(np.concatenate([[0], np.cumsum([len(x) for x in ids])])),
+                seg_ids=i32(np.concatenate(ids)) if ids else i32([]))
+            self.fam = _Families()
+            self.fam.n_families = len(families)
+            for k, v in self._fam_arrays.items():
+                setattr(self.fam, k, v.ctypes.data)
+            self.n_family_members = int(len(self._fam_arrays["fam_members"]))
+            self.family_members = self._fam_arrays["fam_members"]
 
     def c(self) -> _Problem:
         P = _Problem()
@@ -174,6 +201,7 @@ class _Held:
         P.n_unrelated = len(self.unrelated)
         P.seed = self.seed
         P.injected_u = None if self.injected_u is None else self.injected_u.ctypes.data
+        P.families = C.pointer(self.fam) if self.fam is not None else None
         return P
 
 
@@ -183,6 +211,8 @@ class DebugOut:
     zk: np.ndarray | None = None
     beta_ckpt: np.ndarray | None = None
     ckpt_locus: np.ndarray | None = None
+    fam_z: np.ndarray | None = None     # [family members in input order][p]
+    fam_zk: np.ndarray | None = None
 
 
 def _make_debug(held: _Held, want_paths: bool, want_beta: bool):
@@ -195,6 +225,10 @@ def _make_debug(held: _Held, want_paths: bool, want_beta: bool):
         out.z = np.zeros((n, held.p), dtype=np.int32)
         out.zk = np.zeros((n, held.p), dtype=np.int32)
         d.z, d.zk = out.z.ctypes.data, out.zk.ctypes.data
+        if held.fam is not None:
+            out.fam_z = np.zeros((held.n_family_members, held.p), dtype=np.int32)
+            out.fam_zk = np.zeros((held.n_family_members, held.p), dtype=np.int32)
+            d.fam_z, d.fam_zk = out.fam_z.ctypes.data, out.fam_zk.ctypes.data
     if want_beta:
         cap = held.p
         out.beta_ckpt = np.zeros((n, cap, held.K), dtype=np.float64)
@@ -214,11 +248,13 @@ def _finish_debug(d, out, held):
 
 
 def generate(H, p, K, ref_local, b, mu, groups, *, win_start=None, win_end=None, unrelated=None, ref_global=None,
-             seed=2020, injected_u=None, options: Options | None = None, debug_paths=False, debug_beta=False):
+             seed=2020, injected_u=None, families=None, options: Options | None = None, debug_paths=False,
+             debug_beta=False):
     """One-shot drop-in for Knockoffs::generate() (host buffers in, host buffer out).
     Returns (Hk uint8 [N][row_bytes], DebugOut | None)."""
     L = load_library()
-    held = _Held(H, p, K, ref_local, b, mu, groups, win_start, win_end, unrelated, ref_global, seed, injected_u)
+    held = _Held(H, p, K, ref_local, b, mu, groups, win_start, win_end, unrelated, ref_global, seed, injected_u,
+                 families)
     P = held.c()
     o = (options or Options())._c()
     hk = np.zeros_like(held.H)
@@ -245,9 +281,10 @@ class Plan:
     """Resident-data plan: inputs stay in HBM across runs / partitions (kgw_plan_*)."""
 
     def __init__(self, H, p, K, ref_local, b, mu, groups, *, win_start=None, win_end=None, unrelated=None,
-                 ref_global=None, seed=2020, injected_u=None, options: Options | None = None):
+                 ref_global=None, seed=2020, injected_u=None, families=None, options: Options | None = None):
         self._L = load_library()
-        self._held = _Held(H, p, K, ref_local, b, mu, groups, win_start, win_end, unrelated, ref_global, seed, injected_u)
+        self._held = _Held(H, p, K, ref_local, b, mu, groups, win_start, win_end, unrelated, ref_global, seed,
+                           injected_u, families)
         P = self._held.c()
         o = (options or Options())._c()
         self._h = C.c_void_p()
@@ -311,6 +348,7 @@ class Knockoffs:
         self.win_end = [self.num_snps] if win_end is None else list(win_end)
         self.num_windows = len(self.win_start)
         self.unrelated = unrelated
+        self.families = None          # [(members, tidied segments)] as generate_related_cluster sees them
         self.options = options
         self.references_local = None
         self.references_global = None
@@ -361,5 +399,6 @@ class Knockoffs:
         assert self.references_local is not None and self.b is not None
         self.Hk, _ = generate(self.H, self.num_snps, self.K, self.references_local, self.b, self.mut_rates,
                               self.groups, win_start=self.win_start, win_end=self.win_end, unrelated=self.unrelated,
-                              ref_global=self.references_global, seed=self.seed, options=self.options)
+                              ref_global=self.references_global, seed=self.seed, families=self.families,
+                              options=self.options)
         return self.Hk

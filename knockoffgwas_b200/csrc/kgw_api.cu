@@ -7,6 +7,9 @@
 #include "../../include/kgw.h"
 #include "kgw_device.cuh"
 #include "kgw_variants.h"
+#include "kgw_family.cuh"
+
+#include <cmath>
 
 #include <algorithm>
 #include <mutex>
@@ -232,6 +235,158 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
 
 }  // namespace
 
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Related branch (generate_related, knockoffs.cpp:329-571): host pre-processing of the families into
+// the flat structures of kgw_family.cuh.
+struct FamilyState {
+  int n_families = 0, n_max = 0, members_total = 0, SF = 1, grid = 0, threads = 128;
+  size_t smem = 0;
+  std::vector<int32_t> h_members;                 // concatenated, family order
+  std::vector<int32_t> h_fam_off, h_seg_off, h_seg_jmin, h_seg_jmax, h_seg_ids_off, h_seg_ids;
+  // device
+  KgwFamDesc *dfams = nullptr;
+  int32_t *dmembers = nullptr, *divstart = nullptr, *dgroups = nullptr, *dgfirst = nullptr, *dglast = nullptr, *dstatus = nullptr;
+  int32_t *dref_global = nullptr;
+  KgwFamInterval *divs = nullptr;
+  KgwFamOp *dops = nullptr;
+  KgwFamLocus *dloc = nullptr;
+  KgwLocusKO *dko = nullptr;
+  double *demtab = nullptr, *dmsg = nullptr;
+  uint8_t *dpat = nullptr, *dbytes = nullptr;
+  int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
+  std::vector<KgwFamDesc> fams;                   // op_off / n_ops are refreshed by set_groups
+  KgwFamParams P{};
+  ~FamilyState() {
+    cudaFree(dfams); cudaFree(dmembers); cudaFree(divstart); cudaFree(dgroups); cudaFree(dgfirst); cudaFree(dglast);
+    cudaFree(dstatus); cudaFree(dref_global); cudaFree(divs); cudaFree(dops); cudaFree(dloc); cudaFree(dko);
+    cudaFree(demtab); cudaFree(dmsg); cudaFree(dpat); cudaFree(dbytes); cudaFree(ddbg_z); cudaFree(ddbg_zk);
+  }
+};
+
+// std::set_difference on the inputs as they are (family_bp.cpp:365-378)
+int fam_set_difference(const std::vector<int> &A, const std::vector<int> &B, int32_t *out) {
+  size_t ia = 0, ib = 0;
+  int no = 0;
+  while (ia < A.size() && ib < B.size()) {
+    if (A[ia] < B[ib]) out[no++] = A[ia++];
+    else if (B[ib] < A[ia]) ib++;
+    else { ia++; ib++; }
+  }
+  while (ia < A.size()) out[no++] = A[ia++];
+  return no;
+}
+
+// neighbour intervals of every member of family f (family_bp.cpp:41-61 run-length encoded along j)
+int fam_build_intervals(const FamilyState &F, int f, int p, std::vector<std::vector<KgwFamInterval>> &out) {
+  const int m0 = F.h_fam_off[f], n = F.h_fam_off[f + 1] - m0;
+  auto local = [&](int id) { for (int i = 0; i < n; i++) if (F.h_members[m0 + i] == id) return i; return -1; };
+  const int s0 = F.h_seg_off[f], s1 = F.h_seg_off[f + 1];
+  out.assign(n, {});
+  for (int i = 0; i < n; i++) {
+    std::vector<int> cuts = {0, p};
+    for (int s = s0; s < s1; s++) {
+      bool member = false;
+      for (int a = F.h_seg_ids_off[s]; a < F.h_seg_ids_off[s + 1]; a++) member |= (local(F.h_seg_ids[a]) == i);
+      if (member) { cuts.push_back(F.h_seg_jmin[s]); cuts.push_back(F.h_seg_jmax[s] + 1); }
+    }
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    std::vector<std::vector<int>> lists;
+    std::vector<std::pair<int, int>> ranges;
+    for (size_t c = 0; c + 1 < cuts.size(); c++) {
+      const int j0 = cuts[c], j1 = cuts[c + 1] - 1;
+      if (j0 < 0 || j1 >= p || j0 > j1) return fail(KGW_ERR_INVALID, "IBD segment outside [0, p)");
+      std::vector<int> nb;  // neighbors[i][j0], push_back order: segments in order, members in id order
+      for (int s = s0; s < s1; s++) {
+        if (j0 < F.h_seg_jmin[s] || j0 > F.h_seg_jmax[s]) continue;
+        bool member = false;
+        for (int a = F.h_seg_ids_off[s]; a < F.h_seg_ids_off[s + 1]; a++) member |= (local(F.h_seg_ids[a]) == i);
+        if (!member) continue;
+        for (int a = F.h_seg_ids_off[s]; a < F.h_seg_ids_off[s + 1]; a++) {
+          const int i2 = local(F.h_seg_ids[a]);
+          if (i2 < 0) return fail(KGW_ERR_INVALID, "IBD segment lists a haplotype outside its family");
+          if (i2 != i) nb.push_back(i2);
+        }
+      }
+      if (!lists.empty() && lists.back() == nb) ranges.back().second = j1;
+      else { lists.push_back(nb); ranges.push_back({j0, j1}); }
+    }
+    for (size_t c = 0; c < lists.size(); c++) {
+      if ((int)lists[c].size() > KGW_FAM_MAXNB)
+        return fail(KGW_ERR_UNSUPPORTED, "a node with more than 7 IBD neighbours is not built");
+      KgwFamInterval iv;
+      memset(&iv, 0, sizeof(iv));
+      iv.j0 = ranges[c].first; iv.j1 = ranges[c].second; iv.nn = (int)lists[c].size();
+      for (int t = 0; t < iv.nn; t++) iv.nb[t] = lists[c][t];
+      if (c > 0) iv.ndl = fam_set_difference(lists[c], lists[c - 1], iv.dl);
+      if (c + 1 < lists.size()) iv.ndr = fam_set_difference(lists[c], lists[c + 1], iv.dr);
+      out[i].push_back(iv);
+    }
+  }
+  return KGW_OK;
+}
+
+// FamilyKnockoffs::run (family_knockoffs.cpp:155-270) as a flat list of operations
+void fam_build_ops(const FamilyState &F, int f, const int32_t *groups, const std::vector<int> &gfirst,
+                   const std::vector<int> &glast, std::vector<KgwFamOp> &ops) {
+  const int num_groups = (int)gfirst.size();
+  const int m0 = F.h_fam_off[f], n = F.h_fam_off[f + 1] - m0;
+  auto local = [&](int id) { for (int i = 0; i < n; i++) if (F.h_members[m0 + i] == id) return i; return -1; };
+  const int s0 = F.h_seg_off[f], s1 = F.h_seg_off[f + 1];
+  auto push = [&](int kind, int i, int a, int b, int src) {
+    KgwFamOp op;
+    memset(&op, 0, sizeof(op));
+    op.kind = kind; op.i = i; op.a = a; op.b = b; op.src = src;
+    ops.push_back(op);
+  };
+  for (int s = s0; s < s1; s++) {  // trivial knockoffs in the groups of the segment end points (:155-168)
+    const int g_min = groups[F.h_seg_jmin[s]], g_max = groups[F.h_seg_jmax[s]];
+    for (int a = F.h_seg_ids_off[s]; a < F.h_seg_ids_off[s + 1]; a++) {
+      const int i = local(F.h_seg_ids[a]);
+      push(KGW_FOP_COPYZ, i, gfirst[g_min], glast[g_min], 0);
+      push(KGW_FOP_COPYZ, i, gfirst[g_max], glast[g_max], 0);
+    }
+  }
+  for (int s = s0; s < s1; s++) {  // one draw inside each segment, copied to the other members (:172-193)
+    const int i0 = local(F.h_seg_ids[F.h_seg_ids_off[s]]);
+    const int j_min = F.h_seg_jmin[s], j_max = F.h_seg_jmax[s];
+    int g_begin = groups[j_min] + 1;
+    if (groups[j_min] == 0) g_begin = 0;
+    int g_end = groups[j_max] - 1;
+    if (groups[j_max] == num_groups - 1) g_end = groups[j_max];
+    if (g_end >= g_begin) {
+      push(KGW_FOP_DRAW, i0, g_begin, g_end, 0);
+      for (int a = F.h_seg_ids_off[s] + 1; a < F.h_seg_ids_off[s + 1]; a++)
+        push(KGW_FOP_COPYZK, local(F.h_seg_ids[a]), gfirst[g_begin], glast[g_end], i0);
+    }
+  }
+  for (int i = 0; i < n; i++) {  // complement ranges (:196-270)
+    std::vector<int> gl, gr;
+    for (int s = s0; s < s1; s++) {
+      bool member = false;
+      for (int a = F.h_seg_ids_off[s]; a < F.h_seg_ids_off[s + 1]; a++) member |= (local(F.h_seg_ids[a]) == i);
+      if (member) { gl.push_back(groups[F.h_seg_jmin[s]]); gr.push_back(groups[F.h_seg_jmax[s]]); }
+    }
+    std::sort(gl.begin(), gl.end());
+    std::sort(gr.begin(), gr.end());
+    int g_begin = 0, g_end = num_groups - 1;
+    for (size_t q = 0; q < gl.size(); q++) {
+      g_end = gl[q] - 1;
+      if (g_end >= 0 && g_begin <= g_end) push(KGW_FOP_DRAW, i, g_begin, g_end, 0);
+      g_begin = gr[q] + 1;
+    }
+    if (g_end < num_groups) {
+      g_end = num_groups - 1;
+      if (g_begin < num_groups && g_begin <= g_end) push(KGW_FOP_DRAW, i, g_begin, g_end, 0);
+    }
+  }
+}
+
+}  // namespace
+
 struct kgw_plan {
   int device = 0;
   int N = 0, p = 0, K = 0, W = 0, n_haps = 0;
@@ -264,12 +419,15 @@ struct kgw_plan {
   size_t ko_capacity = 0;
   KgwParams P{};
   std::vector<int32_t> haps;
+  FamilyState *fam = nullptr;      // related branch (null when the problem has no families)
+  std::vector<int32_t> out_rows;   // rows of Hk written by this plan: unrelated + family members
 
   ~kgw_plan() {
     cudaSetDevice(device);
     cudaFree(dHw); cudaFree(dHk); cudaFree(dref); cudaFree(dhaps); cudaFree(dhmm); cudaFree(dko);
     cudaFree(demit); cudaFree(dpass); cudaFree(dinj);
     if (stream) cudaStreamSynchronize(stream);
+    delete fam;
     g_slabs.give(device, slab, slab_bytes);
     cudaFree(ddbg_z); cudaFree(ddbg_zk); cudaFree(ddbg_beta);
     if (ev0) cudaEventDestroy(ev0);
@@ -279,6 +437,179 @@ struct kgw_plan {
 };
 
 namespace {
+
+
+int fam_upload_partition(kgw_plan *pl, const int32_t *groups) {
+  FamilyState *F = pl->fam;
+  const int p = pl->p;
+  std::vector<int32_t> one_start(1, 0), one_end(1, p);
+  Tables T;
+  int rc = build_tables(p, pl->K, 1, pl->b.data(), pl->mu.data(), groups, one_start.data(), one_end.data(), T, false);
+  if (rc != KGW_OK) return rc;
+  const int G = groups[p - 1] + 1;
+  std::vector<int> gfirst(G, -1), glast(G, -1);
+  for (int j = 0; j < p; j++) { if (gfirst[groups[j]] < 0) gfirst[groups[j]] = j; glast[groups[j]] = j; }
+  std::vector<KgwFamOp> ops;
+  for (int f = 0; f < F->n_families; f++) {
+    F->fams[f].op_off = (int)ops.size();
+    fam_build_ops(*F, f, groups, gfirst, glast, ops);
+    F->fams[f].n_ops = (int)ops.size() - F->fams[f].op_off;
+  }
+  std::vector<int32_t> gf(gfirst.begin(), gfirst.end()), gl(glast.begin(), glast.end());
+  KGW_CUDA(cudaStreamSynchronize(pl->stream));
+  cudaFree(F->dops); F->dops = nullptr;
+  cudaFree(F->dgfirst); F->dgfirst = nullptr;
+  cudaFree(F->dglast); F->dglast = nullptr;
+  KGW_CUDA(cudaMalloc(&F->dops, sizeof(KgwFamOp) * std::max<size_t>(ops.size(), 1)));
+  KGW_CUDA(cudaMalloc(&F->dgfirst, sizeof(int32_t) * G));
+  KGW_CUDA(cudaMalloc(&F->dglast, sizeof(int32_t) * G));
+  if (!F->dko) KGW_CUDA(cudaMalloc(&F->dko, sizeof(KgwLocusKO) * p));
+  if (!F->dgroups) KGW_CUDA(cudaMalloc(&F->dgroups, sizeof(int32_t) * p));
+  KGW_CUDA(cudaMemcpy(F->dops, ops.data(), sizeof(KgwFamOp) * ops.size(), cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dgfirst, gf.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dglast, gl.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dko, T.ko.data(), sizeof(KgwLocusKO) * p, cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dgroups, groups, sizeof(int32_t) * p, cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dfams, F->fams.data(), sizeof(KgwFamDesc) * F->n_families, cudaMemcpyHostToDevice));
+  F->P.ops = F->dops; F->P.grp_first = F->dgfirst; F->P.grp_last = F->dglast; F->P.ko = F->dko;
+  F->P.groups = F->dgroups; F->P.n_groups = G;
+  return KGW_OK;
+}
+
+int fam_create(kgw_plan *pl, const kgw_problem *prob, const cudaDeviceProp &dp) {
+  const kgw_families *fi = prob->families;
+  const int p = pl->p, K = pl->K, N = pl->N;
+  if (!prob->ref_global) return fail(KGW_ERR_INVALID, "families need ref_global (references_global, knockoffs.h:141)");
+  if (!fi->fam_off || !fi->fam_members || !fi->seg_off || !fi->seg_jmin || !fi->seg_jmax || !fi->seg_ids_off || !fi->seg_ids)
+    return fail(KGW_ERR_INVALID, "null array in kgw_families");
+  FamilyState *F = new FamilyState();
+  pl->fam = F;
+  F->n_families = fi->n_families;
+  F->h_fam_off.assign(fi->fam_off, fi->fam_off + fi->n_families + 1);
+  F->h_seg_off.assign(fi->seg_off, fi->seg_off + fi->n_families + 1);
+  const int nseg = F->h_seg_off.back();
+  F->h_members.assign(fi->fam_members, fi->fam_members + F->h_fam_off.back());
+  F->h_seg_jmin.assign(fi->seg_jmin, fi->seg_jmin + nseg);
+  F->h_seg_jmax.assign(fi->seg_jmax, fi->seg_jmax + nseg);
+  F->h_seg_ids_off.assign(fi->seg_ids_off, fi->seg_ids_off + nseg + 1);
+  F->h_seg_ids.assign(fi->seg_ids, fi->seg_ids + F->h_seg_ids_off.back());
+  F->members_total = (int)F->h_members.size();
+  for (int id : F->h_members) if (id < 0 || id >= N) return fail(KGW_ERR_INVALID, "family member out of range");
+  for (size_t t = 0; t < (size_t)N * K; t++)
+    if (prob->ref_global[t] < 0 || prob->ref_global[t] >= N) return fail(KGW_ERR_INVALID, "global reference index out of range");
+
+  for (int f = 0; f < F->n_families; f++) {
+    for (int sg = F->h_seg_off[f]; sg < F->h_seg_off[f + 1]; sg++) {
+      if (F->h_seg_jmin[sg] < 0 || F->h_seg_jmax[sg] >= p || F->h_seg_jmin[sg] > F->h_seg_jmax[sg])
+        return fail(KGW_ERR_INVALID, "IBD segment outside [0, p)");
+      for (int a = F->h_seg_ids_off[sg]; a < F->h_seg_ids_off[sg + 1]; a++) {
+        bool found = false;
+        for (int m = F->h_fam_off[f]; m < F->h_fam_off[f + 1]; m++) found |= (F->h_members[m] == F->h_seg_ids[a]);
+        if (!found) return fail(KGW_ERR_INVALID, "IBD segment lists a haplotype outside its family");
+      }
+    }
+  }
+  std::vector<KgwFamInterval> ivs;
+  std::vector<int32_t> iv_start;
+  F->fams.resize(F->n_families);
+  for (int f = 0; f < F->n_families; f++) {
+    const int n = F->h_fam_off[f + 1] - F->h_fam_off[f];
+    if (n < 1 || n > KGW_FAM_MAXN) return fail(KGW_ERR_UNSUPPORTED, "families of more than 8 haplotypes are not built");
+    F->n_max = std::max(F->n_max, n);
+    std::vector<std::vector<KgwFamInterval>> per;
+    int rc = fam_build_intervals(*F, f, p, per);
+    if (rc != KGW_OK) return rc;
+    KgwFamDesc &d = F->fams[f];
+    memset(&d, 0, sizeof(d));
+    d.n = n; d.mem_off = F->h_fam_off[f]; d.out_off = F->h_fam_off[f];
+    for (int i = 0; i < n; i++) {
+      iv_start.push_back((int32_t)ivs.size());
+      ivs.insert(ivs.end(), per[i].begin(), per[i].end());
+    }
+    iv_start.push_back((int32_t)ivs.size());  // sentinel: iv_start index = mem_off + f + i
+  }
+  // node emission table (family_bp.cpp:437-454) when mu is the same at every locus (init_hmm, knockoffs.cpp:1520)
+  bool uniform = true;
+  for (int j = 1; j < p; j++) uniform &= (pl->mu[j] == pl->mu[0]);
+  std::vector<double> emtab(8 * 256, 0.0);
+  if (uniform) {
+    const double mu = pl->mu[0];
+    for (int nn = 0; nn < 8; nn++)
+      for (int pt = 0; pt < (1 << (nn + 1)); pt++) {
+        double v = (pt & 1) ? 1.0 - mu : mu;                                  // emission_prob, family_bp.cpp:628
+        for (int t = 0; t < nn; t++) v *= ((pt >> (t + 1)) & 1) ? 1.0 - mu : mu;
+        if (nn > 0) { const double num_neighbors = nn + 1; v = std::pow(v, 1.0 / num_neighbors); }
+        emtab[nn * 256 + pt] = v;
+      }
+  }
+  std::vector<KgwFamLocus> loc(p);
+  const double alpha = 1.0 / K;
+  for (int j = 0; j < p; j++) {
+    loc[j].b = pl->b[j];
+    loc[j].a_bp = (1.0 - pl->b[j]) / (double)K;
+    loc[j].a_al = (1.0 - pl->b[j]) * alpha;
+    loc[j].mu = pl->mu[j];
+  }
+  KGW_CUDA(cudaMalloc(&F->dfams, sizeof(KgwFamDesc) * F->n_families));
+  KGW_CUDA(cudaMalloc(&F->dmembers, sizeof(int32_t) * F->members_total));
+  KGW_CUDA(cudaMalloc(&F->divstart, sizeof(int32_t) * iv_start.size()));
+  KGW_CUDA(cudaMalloc(&F->divs, sizeof(KgwFamInterval) * ivs.size()));
+  KGW_CUDA(cudaMalloc(&F->dloc, sizeof(KgwFamLocus) * p));
+  KGW_CUDA(cudaMalloc(&F->demtab, sizeof(double) * emtab.size()));
+  KGW_CUDA(cudaMalloc(&F->dref_global, sizeof(int32_t) * (size_t)N * K));
+  KGW_CUDA(cudaMalloc(&F->dstatus, sizeof(int32_t)));
+  KGW_CUDA(cudaMemcpy(F->dmembers, F->h_members.data(), sizeof(int32_t) * F->members_total, cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->divstart, iv_start.data(), sizeof(int32_t) * iv_start.size(), cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->divs, ivs.data(), sizeof(KgwFamInterval) * ivs.size(), cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dloc, loc.data(), sizeof(KgwFamLocus) * p, cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->demtab, emtab.data(), sizeof(double) * emtab.size(), cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dref_global, prob->ref_global, sizeof(int32_t) * (size_t)N * K, cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemset(F->dstatus, 0, sizeof(int32_t)));
+
+  // one warp per resident family; scratch slots bounded by a third of the free memory
+  F->SF = (K + 31) / 32 <= 1 ? 1 : ((K + 31) / 32 <= 2 ? 2 : ((K + 31) / 32 <= 4 ? 4 : 8));
+  F->threads = 128;
+  F->smem = (size_t)(F->threads / 32) * 8 * 256 * sizeof(double);
+  const size_t per_slot = (size_t)F->n_max * p * ((size_t)K * 17 + 3);
+  size_t free_b = 0, total_b = 0;
+  KGW_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  long long slots = std::min<long long>(F->n_families, (long long)dp.multiProcessorCount * 8);
+  slots = std::max<long long>(1, std::min<long long>(slots, (long long)((double)free_b / 3.0 / (double)per_slot)));
+  const int wpc = F->threads / 32;
+  F->grid = (int)((slots + wpc - 1) / wpc);
+  const size_t nslots = (size_t)F->grid * wpc;
+  KGW_CUDA(cudaMalloc(&F->dmsg, sizeof(double) * 2 * F->n_max * (size_t)p * K * nslots));
+  KGW_CUDA(cudaMalloc(&F->dpat, (size_t)F->n_max * p * K * nslots));
+  KGW_CUDA(cudaMalloc(&F->dbytes, (size_t)3 * F->n_max * p * nslots));
+
+  KgwFamParams &P = F->P;
+  P.N = N; P.p = p; P.K = K; P.n_families = F->n_families; P.stride_w = pl->stride_w; P.n_max = F->n_max;
+  P.uniform_mu = uniform ? 1 : 0;
+  P.Hw = pl->dHw; P.ref_global = F->dref_global; P.fams = F->dfams; P.members = F->dmembers; P.iv_start = F->divstart;
+  P.ivs = F->divs; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.msg = F->dmsg; P.pat = F->dpat;
+  P.bytes = F->dbytes; P.seed = pl->P.seed; P.injected_u = pl->dinj; P.dbg_z = P.dbg_zk = nullptr; P.status = F->dstatus;
+  return KGW_OK;
+}
+
+int fam_launch(kgw_plan *pl) {
+  FamilyState *F = pl->fam;
+  if (!F || F->n_families == 0) return KGW_OK;
+  void (*fn)(const KgwFamParams) = F->SF == 1 ? kgw::family_kernel<1> : (F->SF == 2 ? kgw::family_kernel<2> : (F->SF == 4 ? kgw::family_kernel<4> : kgw::family_kernel<8>));
+  KGW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
+  fn<<<F->grid, F->threads, F->smem, pl->stream>>>(F->P);
+  KGW_CUDA(cudaGetLastError());
+  return KGW_OK;
+}
+
+int fam_check_status(kgw_plan *pl) {
+  FamilyState *F = pl->fam;
+  if (!F || F->n_families == 0) return KGW_OK;
+  int32_t st = 0;
+  KGW_CUDA(cudaMemcpy(&st, F->dstatus, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (st == -10) return fail(KGW_ERR_INVALID, "Missing knockoff variants (family_knockoffs.cpp:272-277)");
+  if (st == -11) return fail(KGW_ERR_INVALID, "Inconsistency found on Zk (family_knockoffs.cpp:280-291)");
+  return KGW_OK;
+}
 
 int upload_partition(kgw_plan *pl, const int32_t *groups, bool hmm_too) {
   Tables T;
@@ -307,14 +638,16 @@ int upload_partition(kgw_plan *pl, const int32_t *groups, bool hmm_too) {
   pl->P.ko = pl->dko;
   pl->P.passes = pl->dpass;
   pl->P.n_passes = (int)T.passes.size();
+  if (pl->fam && pl->fam->n_families > 0) return fam_upload_partition(pl, groups);
   return KGW_OK;
 }
 
 int launch(kgw_plan *pl) {
-  if (pl->n_haps == 0) return KGW_OK;
-  pl->var->fn<<<pl->grid, pl->var->threads, pl->smem, pl->stream>>>(pl->P);
-  KGW_CUDA(cudaGetLastError());
-  return KGW_OK;
+  if (pl->n_haps > 0) {
+    pl->var->fn<<<pl->grid, pl->var->threads, pl->smem, pl->stream>>>(pl->P);
+    KGW_CUDA(cudaGetLastError());
+  }
+  return fam_launch(pl);
 }
 
 }  // namespace
@@ -489,6 +822,14 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   P.dbg_nblk = 0;
   P.skip_sweeps = o.reserved[0];  // development timing experiments only (0 in production)
 
+  pl->out_rows = pl->haps;
+  if (prob->families && prob->families->n_families > 0) {
+    int rcf = fam_create(pl, prob, dp);
+    if (rcf != KGW_OK) return guard_fail(rcf);
+    pl->out_rows.insert(pl->out_rows.end(), pl->fam->h_members.begin(), pl->fam->h_members.end());
+    std::sort(pl->out_rows.begin(), pl->out_rows.end());
+    pl->out_rows.erase(std::unique(pl->out_rows.begin(), pl->out_rows.end()), pl->out_rows.end());
+  }
   int rc = upload_partition(pl, prob->groups, true);
   if (rc != KGW_OK) return guard_fail(rc);
   KGW_CUDA_PL(cudaStreamSynchronize(pl->stream));
@@ -536,7 +877,7 @@ void *kgw_plan_device_hk(kgw_plan *pl) { return pl ? (void *)pl->dHk : nullptr; 
 
 int32_t kgw_plan_info(kgw_plan *pl, kgw_plan_info_t *out) {
   if (!pl || !out) return fail(KGW_ERR_INVALID, "null argument");
-  out->launches_per_run = pl->n_haps > 0 ? 1 : 0;
+  out->launches_per_run = (pl->n_haps > 0 ? 1 : 0) + ((pl->fam && pl->fam->n_families > 0) ? 1 : 0);
   out->grid = pl->grid;
   out->block = pl->var->threads;
   out->lanes_per_hap = pl->var->L;
@@ -563,7 +904,13 @@ static int run_debug(kgw_plan *pl, kgw_debug *dbg) {
   pl->P.dbg_zk = pl->ddbg_zk;
   pl->P.dbg_beta = pl->ddbg_beta;
   pl->P.dbg_nblk = nck;
+  FamilyState *F = pl->fam;
+  const size_t fnp = F ? (size_t)F->members_total * pl->p : 0;
+  if (F && dbg->fam_z) KGW_CUDA(cudaMalloc(&F->ddbg_z, sizeof(int32_t) * std::max<size_t>(fnp, 1)));
+  if (F && dbg->fam_zk) KGW_CUDA(cudaMalloc(&F->ddbg_zk, sizeof(int32_t) * std::max<size_t>(fnp, 1)));
+  if (F) { F->P.dbg_z = F->ddbg_z; F->P.dbg_zk = F->ddbg_zk; }
   int rc = launch(pl);
+  if (F) { F->P.dbg_z = F->P.dbg_zk = nullptr; }
   pl->P.dbg_z = pl->P.dbg_zk = nullptr;
   pl->P.dbg_beta = nullptr;
   pl->P.dbg_nblk = 0;
@@ -585,6 +932,9 @@ static int run_debug(kgw_plan *pl, kgw_debug *dbg) {
     }
   }
   dbg->n_ckpt = nck;
+  if (F && dbg->fam_z) KGW_CUDA(cudaMemcpy(dbg->fam_z, F->ddbg_z, sizeof(int32_t) * fnp, cudaMemcpyDeviceToHost));
+  if (F && dbg->fam_zk) KGW_CUDA(cudaMemcpy(dbg->fam_zk, F->ddbg_zk, sizeof(int32_t) * fnp, cudaMemcpyDeviceToHost));
+  if (F) { cudaFree(F->ddbg_z); F->ddbg_z = nullptr; cudaFree(F->ddbg_zk); F->ddbg_zk = nullptr; }
   cudaFree(pl->ddbg_z); pl->ddbg_z = nullptr;
   cudaFree(pl->ddbg_zk); pl->ddbg_zk = nullptr;
   cudaFree(pl->ddbg_beta); pl->ddbg_beta = nullptr;
@@ -594,27 +944,30 @@ static int run_debug(kgw_plan *pl, kgw_debug *dbg) {
 int32_t kgw_plan_download(kgw_plan *pl, uint8_t *hk_out, kgw_debug *dbg) {
   if (!pl) return fail(KGW_ERR_INVALID, "null plan");
   KGW_CUDA(cudaSetDevice(pl->device));
-  if (dbg && (dbg->z || dbg->zk || dbg->beta_ckpt)) {
+  if (dbg && (dbg->z || dbg->zk || dbg->beta_ckpt || dbg->fam_z || dbg->fam_zk)) {
     int rc = run_debug(pl, dbg);
     if (rc != KGW_OK) return rc;
   }
   KGW_CUDA(cudaStreamSynchronize(pl->stream));
-  if (hk_out && pl->n_haps > 0) {
-    // only the rows of the processed haplotypes are written back (generate_unrelated touches only those)
+  int rcs = fam_check_status(pl);
+  if (rcs != KGW_OK) return rcs;
+  const std::vector<int32_t> &rows = pl->out_rows;
+  if (hk_out && !rows.empty()) {
+    // only the rows of the processed haplotypes are written back (generate() touches only those)
     const size_t rb = (size_t)(pl->p + 7) / 8;
     bool contiguous = true;
-    for (int i = 1; i < pl->n_haps; i++)
-      if (pl->haps[i] != pl->haps[i - 1] + 1) { contiguous = false; break; }
+    for (size_t i = 1; i < rows.size(); i++)
+      if (rows[i] != rows[i - 1] + 1) { contiguous = false; break; }
     if (contiguous) {
-      const int h0 = pl->haps[0];
+      const int h0 = rows[0];
       KGW_CUDA(cudaMemcpy2D(hk_out + (size_t)h0 * pl->row_bytes, (size_t)pl->row_bytes,
-                            pl->dHk + (size_t)h0 * pl->stride_w, (size_t)pl->stride_w * 4, rb, pl->n_haps,
+                            pl->dHk + (size_t)h0 * pl->stride_w, (size_t)pl->stride_w * 4, rb, rows.size(),
                             cudaMemcpyDeviceToHost));
     } else {
       std::vector<uint8_t> tmp((size_t)pl->N * rb);
       KGW_CUDA(cudaMemcpy2D(tmp.data(), rb, pl->dHk, (size_t)pl->stride_w * 4, rb, pl->N, cudaMemcpyDeviceToHost));
-      for (int i = 0; i < pl->n_haps; i++)
-        memcpy(hk_out + (size_t)pl->haps[i] * pl->row_bytes, tmp.data() + (size_t)pl->haps[i] * rb, rb);
+      for (size_t i = 0; i < rows.size(); i++)
+        memcpy(hk_out + (size_t)rows[i] * pl->row_bytes, tmp.data() + (size_t)rows[i] * rb, rb);
     }
   }
   return KGW_OK;

@@ -22,16 +22,21 @@ static inline double mutate(int h, double mut_rate) {
 
 double kgw_oracle_next_uniform(kgw_oracle_rng *rng, int hap, int stream, int locus, int p, int w) {
   rng->n_draws++;
+  double u;
   switch (rng->mode) {
     case KGW_ORACLE_RNG_INJECTED:
-      return rng->injected[((int64_t)hap * 3 + stream) * p + locus];
+      u = rng->injected[((int64_t)hap * 3 + stream) * p + locus];
+      break;
     case KGW_ORACLE_RNG_TAUS88:
-      return kgw_taus88_uniform(&rng->taus);
+      u = kgw_taus88_uniform(&rng->taus);
+      break;
     default:
       /* window pass w in the upper bits of the stream word: overlapping padded passes of
        * knockoffs.cpp:1222-1226 never reuse a uniform (include/kgw.h) */
-      return kgw_oracle_philox_uniform(rng->seed, (uint32_t)hap, (uint32_t)stream | ((uint32_t)w << 2), (uint32_t)locus);
+      u = kgw_oracle_philox_uniform(rng->seed, (uint32_t)hap, (uint32_t)stream | ((uint32_t)w << 2), (uint32_t)locus);
   }
+  if (rng->record) rng->record[((int64_t)hap * 3 + stream) * p + locus] = u;
+  return u;
 }
 
 /* weighted_choice (utils.cpp:690-698): S = sum left to right from 0.0, R = u*S,

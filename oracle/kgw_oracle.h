@@ -44,6 +44,9 @@ typedef struct {
   kgw_taus88 taus;          /* mode 1: sequential stream, consumed in reference call order */
   uint64_t seed;            /* mode 2: Philox key                                          */
   int64_t n_draws;          /* bookkeeping                                                 */
+  double *record;           /* optional U[N][3][p]: every uniform handed out is also written at
+                               its (haplotype, stream, locus) key (lets a sequential taus88 replay
+                               be re-fed to the CUDA path as injected uniforms)                     */
 } kgw_oracle_rng;
 
 /* Unrelated haplotypes (generate_unrelated_worker, knockoffs.cpp:636-700).

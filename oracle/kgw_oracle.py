@@ -38,7 +38,7 @@ class _Problem(C.Structure):
 class _Rng(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("injected", C.c_void_p), ("taus", _Taus),
-        ("seed", C.c_uint64), ("n_draws", C.c_int64),
+        ("seed", C.c_uint64), ("n_draws", C.c_int64), ("record", C.c_void_p),
     ]
 
 
@@ -275,11 +275,15 @@ def run_unrelated(prob: Problem, haps=None, *, mode="philox", seed=None, injecte
     return Result(z, zk, hk, beta, int(R.n_draws), (R.taus.v1, R.taus.v2, R.taus.v3))
 
 
-def make_rng(prob: Problem, mode="philox", seed=None, injected=None, taus_seed=None, taus_state=None):
-    """Uniform source shared by run_unrelated / run_family.  Returns (_Rng, keep-alive object)."""
+def make_rng(prob: Problem, mode="philox", seed=None, injected=None, taus_seed=None, taus_state=None, record=None):
+    """Uniform source shared by run_unrelated / run_family.  Returns (_Rng, keep-alive object).
+    record: optional float64 [N][3][p] array that receives every uniform at its (hap, stream, locus) key."""
     L = lib()
     R = _Rng()
     keep = None
+    if record is not None:
+        assert record.dtype == np.float64 and record.flags.c_contiguous and record.shape == (prob.N, 3, prob.p)
+        R.record = record.ctypes.data
     if mode == "injected":
         keep = np.ascontiguousarray(injected, dtype=np.float64)
         assert keep.shape == (prob.N, 3, prob.p)

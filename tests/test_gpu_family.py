@@ -1,0 +1,85 @@
+"""GPU parity of the IBD-conditioned (related) branch -- FamilyBP + FamilyKnockoffs + sample_emission
+(knockoffs.cpp:329-571, family_bp.cpp, family_knockoffs.cpp) -- called through the C ABI.
+
+(a) keyed generator: CUDA == CPU oracle on every golden fixture's families;
+(b) reference binary: the oracle replays the reference's own sequential taus88 stream (and is pinned to
+    the reference bit for bit in tests/test_oracle_vs_reference.py) while recording each uniform at its
+    (haplotype, stream, locus) key; fed those uniforms, the CUDA path must reproduce the reference's
+    knockoffs of the related haplotypes bit for bit.
+"""
+import numpy as np
+import pytest
+
+import kgw_oracle as ko
+from kgw_testutil import GOLDEN_NAMES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+kg = pytest.importorskip("knockoffgwas_b200")
+
+
+def _families(prob):
+    return [(m, [(s[0], s[1], s[4]) for s in segs]) for m, segs in prob.fam_clusters]
+
+
+def _run(prob, **kw):
+    return kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups,
+                       win_start=prob.win_start, win_end=prob.win_end, unrelated=np.zeros(0, np.int32),
+                       ref_global=prob.ref_global, seed=prob.seed, families=_families(prob), **kw)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_family_kernel_matches_oracle_counter_rng(name):
+    prob, _ = load_golden(name)
+    hk, dbg = _run(prob, debug_paths=True)
+    rng, _ = ko.make_rng(prob, mode="philox")
+    row = 0
+    for members, segs in prob.fam_clusters:
+        r = ko.run_family(prob, members, segs, rng)
+        n = len(members)
+        assert np.array_equal(dbg.fam_z[row:row + n], r.z), f"Z of family {members.tolist()}"
+        assert np.array_equal(dbg.fam_zk[row:row + n], r.zk), f"Zk of family {members.tolist()}"
+        assert np.array_equal(hk[members], r.hk), f"Hk of family {members.tolist()}"
+        row += n
+    related = np.concatenate([m for m, _ in prob.fam_clusters])
+    rest = np.setdiff1d(np.arange(prob.N), related)
+    assert not hk[rest].any()
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_NAMES if "windows" not in n])
+def test_family_kernel_reproduces_reference_binary(name):
+    prob, f = load_golden(name)
+    U = np.zeros((prob.N, 3, prob.p))
+    rng, _ = ko.make_rng(prob, mode="taus88", taus_seed=prob.seed, record=U)
+    for members, segs in prob.fam_clusters:
+        r = ko.run_family(prob, members, segs, rng)
+        assert np.array_equal(r.hk, f["Hk"][members])        # the oracle itself is pinned to the reference
+    hk, _ = _run(prob, injected_u=U)
+    related = np.concatenate([m for m, _ in prob.fam_clusters])
+    assert np.array_equal(hk[related], f["Hk"][related]), "related knockoffs differ from the reference binary"
+
+
+def test_whole_generate_call_matches_reference_binary():
+    """Unrelated + related haplotypes in one kgw_generate() call == the reference's complete Hk."""
+    prob, f = load_golden("toy_chr22_K10_res2")
+    nu, p = len(prob.unrelated), prob.p
+    U = np.zeros((prob.N, 3, p))
+    rng, _ = ko.make_rng(prob, mode="taus88", taus_seed=prob.seed, record=U)
+    for members, segs in prob.fam_clusters:
+        ko.run_family(prob, members, segs, rng)
+    raw = ko.taus88_stream(None, nu * 3 * p).astype(np.float64) / 4294967296.0   # unrelated: default-seeded engine
+    U[prob.unrelated] = raw.reshape(nu, 3, p)
+    hk, _ = kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, unrelated=prob.unrelated,
+                        ref_global=prob.ref_global, seed=prob.seed, families=_families(prob), injected_u=U)
+    assert np.array_equal(hk, f["Hk"])
+
+
+def test_family_errors():
+    prob, _ = load_golden("toy_chr21_K50_res5")
+    fam = _families(prob)
+    with pytest.raises(kg.KgwError):   # families need the global references
+        kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, families=fam)
+    bad = [(fam[0][0], [(fam[0][1][0][0], fam[0][1][0][1], np.array([0, 1], np.int32))])]
+    with pytest.raises(kg.KgwError):   # a segment listing haplotypes outside its family
+        kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, ref_global=prob.ref_global,
+                    families=bad)
