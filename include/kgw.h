@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGW_ABI_VERSION 2
+#define KGW_ABI_VERSION 3
 
 /* status codes (negative = error; kgw_last_error() has the text) */
 enum {
@@ -98,12 +98,14 @@ typedef struct kgw_problem {
 
 typedef struct kgw_options {
   int32_t device;        /* CUDA device ordinal (one process per GPU: pass LOCAL_RANK)        */
-  int32_t block_loci;    /* 0 = default; checkpoint spacing of the backward messages          */
+  int32_t block_loci;    /* 0 = default (4); 2, 4 or 8: spacing of the stored backward-message rows */
   int32_t lanes_per_hap; /* 0 = auto; 4, 8, 16 or 32 lanes cooperate on one haplotype         */
   int32_t ctas_per_sm;   /* 0 = auto (occupancy query)                                        */
   void *stream;          /* cudaStream_t to launch on (caller-owned); NULL = the plan creates
                             its own non-blocking stream                                       */
-  int32_t reserved[2];
+  int32_t reserved;
+  int32_t segment_loci;  /* 0 = auto (whole chromosome when the scratch fits); otherwise a multiple of
+                            32: loci per segment of the backward/forward sweeps                */
 } kgw_options;
 
 /* Optional debug outputs (any pointer may be NULL); rows follow `unrelated` order. */
@@ -151,7 +153,9 @@ typedef struct kgw_plan_info_t {
   int32_t grid, block;        /* persistent grid / CTA size of the sampler kernel              */
   int32_t lanes_per_hap;      /* lanes cooperating on one haplotype                            */
   int32_t states_per_lane;    /* HMM states held in registers per lane                         */
-  int32_t block_loci;         /* checkpoint spacing of the backward messages                   */
+  int32_t block_loci;         /* spacing of the stored backward-message rows                   */
+  int32_t segment_loci;       /* loci per segment of sweeps 1-2 (>= p: one segment)            */
+  int32_t reserved;
   int64_t scratch_bytes;      /* checkpoint + latent-path scratch in HBM                       */
   int64_t row_stride_bytes;   /* bytes between rows of the DEVICE Hk matrix (kgw_plan_device_hk) */
   int64_t smem_bytes;         /* dynamic shared memory per CTA                                 */

@@ -15,7 +15,7 @@ import numpy as np
 _PKG = Path(__file__).resolve().parent
 _LIB = None
 
-KGW_ABI_VERSION = 2
+KGW_ABI_VERSION = 3
 STREAM_Z, STREAM_ZK, STREAM_HK, STREAM_FAMILY = 0, 1, 2, 3
 
 
@@ -45,13 +45,13 @@ class _Problem(C.Structure):
 
 class _Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("block_loci", C.c_int32), ("lanes_per_hap", C.c_int32),
-                ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p), ("reserved", C.c_int32 * 2)]
+                ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p), ("reserved", C.c_int32), ("segment_loci", C.c_int32)]
 
 
 class _PlanInfo(C.Structure):
     _fields_ = [("launches_per_run", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32),
                 ("lanes_per_hap", C.c_int32), ("states_per_lane", C.c_int32), ("block_loci", C.c_int32),
-                ("scratch_bytes", C.c_int64), ("row_stride_bytes", C.c_int64), ("smem_bytes", C.c_int64)]
+                ("segment_loci", C.c_int32), ("reserved", C.c_int32), ("scratch_bytes", C.c_int64), ("row_stride_bytes", C.c_int64), ("smem_bytes", C.c_int64)]
 
 
 class _Debug(C.Structure):
@@ -66,13 +66,15 @@ class Options:
     lanes_per_hap: int = 0
     ctas_per_sm: int = 0
     stream: int = 0   # cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); 0 = plan-owned
+    segment_loci: int = 0  # 0 = auto; multiple of 32: loci per segment of the backward/forward sweeps
     skip_sweeps: int = 0  # development timing experiments only: bit s set = skip sweep s+1 (results invalid)
 
     def _c(self) -> _Options:
         o = _Options()
         o.device, o.block_loci, o.lanes_per_hap, o.ctas_per_sm = self.device, self.block_loci, self.lanes_per_hap, self.ctas_per_sm
         o.stream = self.stream or None
-        o.reserved[0] = self.skip_sweeps
+        o.reserved = self.skip_sweeps
+        o.segment_loci = self.segment_loci
         return o
 
 

@@ -114,12 +114,10 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
       KgwLocusHMM &h = T.hmm[j];
       h.omm = 1.0 - mu[j];
       h.mu = mu[j];
-      h.mup = 1.0 - (1.0 - mu[j]);
       h.a = (1.0 - b[j]) * alpha;
       h.b = b[j];
-      h.aomm = h.a * h.omm;   // (a_j_k + 0) * theta, knockoffs.cpp:1254
-      h.amu = h.a * h.mu;
-      h.amup = h.a * h.mup;
+      // the draw's 1.0 - (1.0 - mu) (knockoffs.cpp:1251-1256) and the products a * theta (:1254) are
+      // single IEEE operations on these four numbers and are formed on the device
       // sample_emission_copula, lambda = 0.5 (knockoffs.cpp:1469-1502, call site :677)
       const double lambda = 0.5;
       for (int c = 0; c < 8; c++) {
@@ -392,7 +390,8 @@ struct kgw_plan {
   int N = 0, p = 0, K = 0, W = 0, n_haps = 0;
   int64_t row_bytes = 0;
   int stride_w = 0;
-  int B = 8, nblk = 0;
+  int B = 4, nblk = 0;
+  int seg_loci = 0, nseg = 1;
   const KgwVariant *var = nullptr;
   int G = 0, n_tasks = 0;
   int grid = 0;
@@ -410,7 +409,8 @@ struct kgw_plan {
   KgwLocusKO *dko = nullptr;
   KgwEmit *demit = nullptr;
   KgwPass *dpass = nullptr;
-  double *dckpt = nullptr, *dinj = nullptr, *dse = nullptr;
+  double *dckpt = nullptr, *dinj = nullptr, *dse = nullptr, *dcs = nullptr, *dsegck = nullptr;
+  uint32_t *dmw = nullptr;
   void *slab = nullptr;      // one allocation behind dckpt / dse / dz / dzk
   size_t slab_bytes = 0;
   uint8_t *dz = nullptr, *dzk = nullptr;
@@ -680,11 +680,13 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   if (opt) o = *opt;
   if (o.lanes_per_hap != 0 && o.lanes_per_hap != 1 && o.lanes_per_hap != 2 && o.lanes_per_hap != 4 && o.lanes_per_hap != 8)
     return fail(KGW_ERR_INVALID, "lanes_per_hap must be 0 (auto), 1, 2, 4 or 8");
-  if (o.block_loci != 0 && o.block_loci != 1 && o.block_loci != 2 && o.block_loci != 8)
-    return fail(KGW_ERR_INVALID, "block_loci must be 0 (auto), 1, 2 or 8");
-  int B = o.block_loci;  // 0: decided below from the scratch budget
-  if (!pick_variant(K, o.lanes_per_hap, 2) && !pick_variant(K, o.lanes_per_hap, 8))
-    return fail(KGW_ERR_UNSUPPORTED, "no kernel variant for this K / lanes_per_hap");
+  if (o.block_loci != 0 && o.block_loci != 2 && o.block_loci != 4 && o.block_loci != 8)
+    return fail(KGW_ERR_INVALID, "block_loci must be 0 (auto), 2, 4 or 8");
+  if (o.segment_loci < 0 || (o.segment_loci % 32) != 0)
+    return fail(KGW_ERR_INVALID, "segment_loci must be 0 (auto) or a positive multiple of 32");
+  const int B = o.block_loci ? o.block_loci : 4;
+  if (!pick_variant(K, o.lanes_per_hap, B))
+    return fail(KGW_ERR_UNSUPPORTED, "no kernel variant for this K / lanes_per_hap / block_loci");
   for (int i = 0; i < prob->n_unrelated; i++) {
     if (prob->unrelated[i] < 0 || prob->unrelated[i] >= N) return fail(KGW_ERR_INVALID, "unrelated index out of range");
   }
@@ -729,34 +731,47 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   KGW_CUDA_PL(cudaEventCreate(&pl->ev0));
   KGW_CUDA_PL(cudaEventCreate(&pl->ev1));
 
-  // variant, occupancy-driven persistent grid (one scratch slot per resident warp)
+  // variant, occupancy-driven persistent grid (one scratch slot per resident warp); the chromosome is cut
+  // into segments when the per-slot scratch of a whole pass would not fit in 60 % of the free memory
   size_t free_b = 0, total_b = 0;
   KGW_CUDA_PL(cudaMemGetInfo(&free_b, &total_b));
   const size_t hw_bytes_est = 2 * (size_t)N * (((size_t)prob->row_bytes + 15) / 16 * 16) + sizeof(int32_t) * (size_t)N * W * K;
-  for (int pass = 0; pass < 2; pass++) {
-    const int Btry = B ? B : (pass == 0 ? 2 : 8);
-    const KgwVariant *var = pick_variant(K, o.lanes_per_hap, Btry);
-    if (!var && !B && pass == 0) continue;
-    if (!var) return guard_fail(fail(KGW_ERR_UNSUPPORTED, "no kernel variant for this K / lanes_per_hap / block_loci"));
+  const KgwVariant *var = pick_variant(K, o.lanes_per_hap, B);
+  const int G = 32 / var->L;
+  const size_t p32 = ((size_t)p + 31) / 32 * 32;
+  const size_t SPR = (size_t)(var->S + 1) / 2 * 2, SPW = (size_t)(var->S + 3) / 4 * 4;
+  const size_t ROW = (size_t)var->L * SPR * G, TILE = (size_t)var->L * SPW * G;
+  size_t slots = 0;
+  {
     KGW_CUDA_PL(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var->smem));
     int occ = 0;
     KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, var->threads, var->smem));
     if (occ <= 0) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
     if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
-    const int G = 32 / var->L, wpc = var->threads / 32;
     const int n_tasks = (pl->n_haps + G - 1) / G;
-    const int grid = std::max(1, std::min(occ * dp.multiProcessorCount, (n_tasks + wpc - 1) / wpc));
-    const size_t slots = (size_t)grid * wpc;
-    const size_t nblk = ((size_t)p + Btry - 1) / Btry;
-    const size_t per_slot = sizeof(double) * (nblk * var->L * var->S * G + (size_t)p * 32) + 2 * (((size_t)p + 31) / 32 * 32) * G;
-    pl->var = var; pl->B = Btry; pl->G = G; pl->n_tasks = n_tasks; pl->grid = grid;
-    pl->smem = var->smem; pl->nblk = (int)nblk;
-    pl->scratch_bytes = per_slot * slots;
-    if (B || pl->scratch_bytes + hw_bytes_est < (size_t)(0.6 * (double)free_b)) break;  // fits: keep the denser checkpoints
+    const int grid = std::max(1, std::min(occ * dp.multiProcessorCount, n_tasks));
+    slots = (size_t)grid;
+    pl->var = var; pl->B = B; pl->G = G; pl->n_tasks = n_tasks; pl->grid = grid;
+    pl->smem = var->smem; pl->nblk = (int)((p + B - 1) / B);
   }
-  const KgwVariant *var = pl->var;
-  const int G = pl->G;
-  const size_t slots = (size_t)pl->grid * (var->threads / 32);
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  // bytes per slot: fixed part (match words, latent paths) and the part proportional to the segment length
+  const size_t fixed_slot = up(sizeof(uint32_t) * (size_t)pl->stride_w * TILE) + 2 * up(p32 * G);
+  auto seg_slot = [&](size_t ps) {   // rows every B loci, partial sums, totals, segment-top rows
+    const size_t nseg = (p32 + ps - 1) / ps;
+    return up(sizeof(double) * (ps / B) * ROW) + up(sizeof(double) * ps * 128) + up(sizeof(double) * ps * G) +
+           up(sizeof(double) * (nseg > 1 ? nseg : 1) * ROW);
+  };
+  size_t PS = p32;
+  if (o.segment_loci > 0) {
+    PS = std::min<size_t>(p32, (size_t)o.segment_loci);
+  } else {
+    const double budget = 0.6 * (double)free_b - (double)hw_bytes_est;
+    while (PS > 1024 && (double)slots * (double)(fixed_slot + seg_slot(PS)) > budget) PS = ((PS / 2) + 31) / 32 * 32;
+  }
+  pl->seg_loci = (int)PS;
+  pl->nseg = (int)((p32 + PS - 1) / PS);
+  pl->scratch_bytes = slots * (fixed_slot + seg_slot(PS));
 
   // inputs
   const size_t hw_bytes = (size_t)N * pl->stride_w * 4;
@@ -776,25 +791,31 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
     KGW_CUDA_PL(cudaMalloc(&pl->dinj, ub));
     KGW_CUDA_PL(cudaMemcpyAsync(pl->dinj, prob->injected_u, ub, cudaMemcpyHostToDevice, pl->stream));
   }
-  // scratch: checkpoints, per-locus partial sums and latent paths, one slot per resident warp
-  const size_t ckpt_stride = (size_t)pl->nblk * var->L * var->S * G;
-  const size_t se_stride = (size_t)p * 32;
-  const size_t z_stride = ((size_t)p + 31) / 32 * 32 * G;
+  // scratch, one slot per resident warp
+  const size_t mw_stride = up(sizeof(uint32_t) * (size_t)pl->stride_w * TILE) / sizeof(uint32_t);
+  const size_t ckpt_stride = up(sizeof(double) * (PS / B) * ROW) / sizeof(double);
+  const size_t cs_stride = up(sizeof(double) * PS * 128) / sizeof(double);
+  const size_t se_stride = up(sizeof(double) * PS * G) / sizeof(double);
+  const size_t segck_stride = up(sizeof(double) * (pl->nseg > 1 ? pl->nseg : 1) * ROW) / sizeof(double);
+  const size_t z_stride = up(p32 * G);
   {
-    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-    const size_t b_ck = up(sizeof(double) * ckpt_stride * slots), b_se = up(sizeof(double) * se_stride * slots);
-    const size_t b_z = up(z_stride * slots);
-    const size_t need = b_ck + b_se + 2 * b_z;
+    const size_t b_mw = mw_stride * sizeof(uint32_t) * slots, b_ck = ckpt_stride * sizeof(double) * slots;
+    const size_t b_cs = cs_stride * sizeof(double) * slots, b_se = se_stride * sizeof(double) * slots;
+    const size_t b_sg = segck_stride * sizeof(double) * slots, b_z = z_stride * slots;
+    const size_t need = b_mw + b_ck + b_cs + b_se + b_sg + 2 * b_z;
     pl->slab = g_slabs.take(pl->device, need, &pl->slab_bytes);
     if (!pl->slab) {
       KGW_CUDA_PL(cudaMalloc(&pl->slab, need));
       pl->slab_bytes = need;
     }
     unsigned char *base = (unsigned char *)pl->slab;
-    pl->dckpt = (double *)base;
-    pl->dse = (double *)(base + b_ck);
-    pl->dz = base + b_ck + b_se;
-    pl->dzk = base + b_ck + b_se + b_z;
+    pl->dmw = (uint32_t *)base; base += b_mw;
+    pl->dckpt = (double *)base; base += b_ck;
+    pl->dcs = (double *)base; base += b_cs;
+    pl->dse = (double *)base; base += b_se;
+    pl->dsegck = (double *)base; base += b_sg;
+    pl->dz = base; base += b_z;
+    pl->dzk = base;
   }
   KGW_CUDA_PL(cudaMemsetAsync(pl->dz, 0, z_stride * slots, pl->stream));
   KGW_CUDA_PL(cudaMemsetAsync(pl->dzk, 0, z_stride * slots, pl->stream));
@@ -808,8 +829,15 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   P.ref_local = pl->dref;
   P.haps = pl->dhaps;
   P.Hk = pl->dHk;
+  P.seg_loci = pl->seg_loci;
+  P.mwbuf = pl->dmw;
+  P.mw_stride = mw_stride;
   P.ckpt = pl->dckpt;
   P.ckpt_stride = ckpt_stride;
+  P.segck = pl->dsegck;
+  P.segck_stride = segck_stride;
+  P.csbuf = pl->dcs;
+  P.cs_stride = cs_stride;
   P.sebuf = pl->dse;
   P.se_stride = se_stride;
   P.zbuf = pl->dz;
@@ -820,7 +848,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   P.dbg_z = P.dbg_zk = nullptr;
   P.dbg_beta = nullptr;
   P.dbg_nblk = 0;
-  P.skip_sweeps = o.reserved[0];  // development timing experiments only (0 in production)
+  P.skip_sweeps = o.reserved;  // development timing experiments only (0 in production)
 
   pl->out_rows = pl->haps;
   if (prob->families && prob->families->n_families > 0) {
@@ -883,6 +911,8 @@ int32_t kgw_plan_info(kgw_plan *pl, kgw_plan_info_t *out) {
   out->lanes_per_hap = pl->var->L;
   out->states_per_lane = pl->var->S;
   out->block_loci = pl->B;
+  out->segment_loci = pl->seg_loci;
+  out->reserved = 0;
   out->scratch_bytes = (int64_t)pl->scratch_bytes;
   out->row_stride_bytes = (int64_t)pl->stride_w * 4;
   out->smem_bytes = (int64_t)pl->smem;

@@ -5,21 +5,29 @@
 //  compute_hmm_backward :1041, sample_posterior_MC :1215, sample_knockoff_MC :1270,
 //  sample_emission_copula :1469; categorical draws = weighted_choice, utils.cpp:690).
 //
-// Mapping.  A warp carries G = 32/L haplotypes; L lanes (1, 2, 4 or 8) cooperate on one haplotype
-// and lane `lig` owns the S consecutive HMM states k = lig*S .. lig*S+S-1 in registers (K <= L*S).
-// Lane index = lig*G + g, so that for a fixed state the G haplotypes of a warp touch consecutive
-// 8-byte words in shared memory and in the HBM scratch (conflict-free / coalesced).  Warps are
-// independent (no CTA barrier); each resident warp owns one scratch slot and walks a strided list
-// of haplotype batches.  Per batch and window pass:
-//   sweep 1  backward messages beta_j (unnormalised, power-of-two rescaled every 8 loci), a
-//            checkpoint every B loci and the per-lane emission-weighted sum of every locus to HBM;
-//   sweep 2  per block of B loci: checkpoint -> shared-memory rows (B-1 recomputed steps), then the
-//            latent path z_j left to right, one pass per locus (the locus total is known from sweep 1);
-//   sweep 3  group knockoff path zk_j: at the first locus of a group the partition function N_k
-//            (registers) and its reciprocals (one shared-memory row, patched at the <= 3 special
-//            states) are updated; inside a group the draw has a closed form; knockoff alleles are
-//            drawn per 32-locus word and stored packed.
-// The O(K) per-locus recurrences are FP64-issue bound; HBM sees 16*K/B + 8*L bytes per haplotype-SNP.
+// Mapping.  A warp carries G = 32/L haplotypes; L lanes (1, 2, 4 or 8) cooperate on one haplotype and
+// lane `lig` owns the S consecutive HMM states k = lig*S .. lig*S+S-1 in registers (K <= L*S).
+// Lane index = lig*G + g.  Warps are independent (one-warp CTAs, no CTA barrier); each resident warp
+// owns one HBM scratch slot and walks a strided list of haplotype batches.  Per batch and window pass:
+//   gather   match words ~(H[i] ^ H[ref_k]) of every (state, 32-locus word) -> slot scratch, once; the
+//            sweeps stream them back tile by tile with 16-byte cp.async (double-buffered in shared memory);
+//   sweep 0  (only when the chromosome is cut into segments because the scratch would not fit) backward
+//            messages over the whole range, keeping the message row at the top locus of every segment;
+//   then per segment, left to right:
+//   sweep 1  backward messages beta_j (unnormalised, exact power-of-two rescale every 8 loci): a message
+//            row every B loci, four partial sums of the emission-weighted messages per lane and locus,
+//            and the locus total, to HBM;
+//   sweep 2  latent path z_j left to right.  The categorical draw is a two-level inverse-CDF search: the
+//            partial sums of sweep 1 locate the chunk of <= 8 states that holds the target, and only those
+//            states' messages are rebuilt, from the staged message row of the block's top locus by the
+//            O(1)-per-state recurrence beta_{m-1}(k) = c_m + b_m e_m(k) (c_m from the stored totals);
+//   and finally
+//   sweep 3  group knockoff path zk_j: at the first locus of a group the partition function N_k (registers)
+//            and its reciprocals (one shared-memory row, patched at the <= 3 special states) are updated,
+//            the draw is again two-level (chunk sums of the reciprocals, then one chunk); inside a group
+//            the draw has a closed form; knockoff alleles are drawn per 32-locus word and stored packed.
+// Shared-memory rows keep two states per 16-byte unit ([state pair][haplotype][2]), so that the owner
+// lane moves its S states with ceil(S/2) 128-bit accesses and a chunk is 2 or 4 such units.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,12 +36,8 @@
 struct __align__(16) KgwLocusHMM {  // per locus, built on the host in the reference's evaluation order
   double omm;   // 1.0 - mu_j
   double mu;    // mu_j
-  double mup;   // 1.0 - (1.0 - mu_j)   (knockoffs.cpp:1251-1256 quirk: emission for h=0, ref=1)
   double a;     // (1.0 - b_j) * alpha,  alpha = 1.0/K (knockoffs.cpp:75)
   double b;     // b_j
-  double aomm;  // a * omm
-  double amu;   // a * mu
-  double amup;  // a * mup
 };
 
 enum { KGW_KO_FIRST = 1, KGW_KO_LASTGRP = 2, KGW_KO_GZERO = 4, KGW_KO_GSTART = 8, KGW_KO_LASTINGRP = 16 };
@@ -73,8 +77,10 @@ struct KgwPass {
 struct KgwParams {
   int32_t N, p, K, W;
   int32_t n_haps, n_passes;
-  int32_t stride_w;  // 32-bit words per packed row
+  int32_t stride_w;  // 32-bit words per packed row (multiple of 4)
   int32_t n_tasks;   // haplotype batches (G haplotypes each)
+  int32_t seg_loci;  // loci per segment (multiple of 32); >= p means one segment
+  int32_t pad0;
   const uint32_t *Hw;
   const int32_t *ref_local;  // [N][W][K]
   const int32_t *haps;       // [n_haps]
@@ -83,11 +89,18 @@ struct KgwParams {
   const KgwEmit *emit;       // [p]
   const KgwPass *passes;
   uint32_t *Hk;              // [N][stride_w]
-  double *ckpt;              // [slots][nblk][L*S][G]
+  // per-slot scratch
+  uint32_t *mwbuf;           // [slots][stride_w][TILE]         match words
+  unsigned long long mw_stride;
+  double *ckpt;              // [slots][seg_loci/B][ROW]        message rows of the current segment
   unsigned long long ckpt_stride;
-  double *sebuf;             // [slots][p][32]   per-lane emission-weighted sums of sweep 1
+  double *segck;             // [slots][nseg][ROW]              message rows at segment tops (sweep 0)
+  unsigned long long segck_stride;
+  double *csbuf;             // [slots][seg_loci][2][32][2]     partial sums of sweep 1
+  unsigned long long cs_stride;
+  double *sebuf;             // [slots][seg_loci][G]            locus totals of sweep 1
   unsigned long long se_stride;
-  uint8_t *zbuf, *zkbuf;     // [slots][p][G]
+  uint8_t *zbuf, *zkbuf;     // [slots][p32][G]
   unsigned long long z_stride;
   unsigned long long seed;
   const double *injected_u;  // [N][3][p] or null
@@ -143,14 +156,13 @@ __device__ __forceinline__ double group_excl(double v, int lane, double &total) 
 }
 
 __device__ __forceinline__ double fast_rcp(double x) {
-  // x in [1e-10, ~1e3]: hardware seed + two Newton steps (relative error ~1e-16)
+  // x in [1e-10, ~1e3]: hardware seed (upper 32 bits of x, >= 20 good bits) and one third-order step
+  // y (1 + e + e^2), e = 1 - x y: relative error e^3 plus rounding
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
 }
 
 // cnt += (v <= t): one DSETP and one predicated integer add (the compiler otherwise builds bit masks)
@@ -158,27 +170,52 @@ __device__ __forceinline__ void count_le(int &cnt, double v, double t) {
   asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "d"(v), "d"(t));
 }
 
-__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// streaming stores / loads of the scratch (written once, read once: keep it out of L1)
+__device__ __forceinline__ void st_cg(double2 *p, double x, double y) {
+  asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void st_cg(double *p, double x) {
+  asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory");
+}
+__device__ __forceinline__ void st_cg(uint4 *p, uint4 v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ double2 ld_cg(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_cg(const double *p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 
 template <int L, int S, int B>
 struct Cfg {
   static constexpr int G = 32 / L;
   static constexpr int KP = L * S;
-  // per-warp shared memory: B-1 recomputed message rows + 2 checkpoint staging rows (sweep 2) / 1 reciprocal row
-  // (sweep 3), two reference-word tiles, two staging tiles of per-lane sums, two latent-path tiles
-  static constexpr size_t rows_bytes = (size_t)(B + 1) * KP * G * 8;
-  static constexpr size_t refw_bytes = (size_t)2 * KP * G * 4;
-  static constexpr size_t se_bytes = (size_t)2 * B * 32 * 8;
-  static constexpr size_t tile_bytes = (size_t)2 * 32 * G;
-  __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + refw_bytes + se_bytes + tile_bytes; }
+  static constexpr int SPR = (S + 1) / 2 * 2;   // state slots per lane in a message row
+  static constexpr int SPW = (S + 3) / 4 * 4;   // state slots per lane in a match-word tile
+  static constexpr int NQ = SPW / 4;            // 16-byte units of a lane in a match-word tile
+  static constexpr int NP = SPR / 2;            // 16-byte units of a lane in a message row
+  static constexpr int CS = S <= 16 ? 4 : 8;    // states per chunk (4 chunks per lane)
+  static constexpr int NC = 4;
+  static constexpr int ROW = L * SPR * G;       // doubles per message row
+  static constexpr int TILE = L * SPW * G;      // 32-bit words per match-word tile
+  // per-warp shared memory: two message rows (sweep 2: staged top rows of two blocks; sweep 3: the
+  // reciprocal row and the two latent-path tiles), one match-word tile, the latent-path tile of sweep 2
+  static constexpr size_t rows_bytes = (size_t)2 * ROW * 8;
+  static constexpr size_t tiles_bytes = (size_t)TILE * 4;
+  static constexpr size_t ztile_bytes = (size_t)32 * G;
+  __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + tiles_bytes + ztile_bytes; }
+  static_assert(2 * 32 * G <= ROW * 8, "latent-path tiles of sweep 3 must fit in the second row buffer");
 };
 
 // uniform of (hap, stream, locus j): Philox block cached per 4 loci
@@ -207,56 +244,52 @@ struct UniformSrc {
   }
 };
 
-// emission-weighted messages e = beta * E and their in-lane sum (knockoffs.cpp:1052-1060 without the
-// constant factor a); beta is overwritten by e.
-template <int S, bool PAD>
-__device__ __forceinline__ double emit_and_sum(double (&beta)[S], const uint32_t (&mw)[S], uint32_t bm,
-                                               double omm, double mu, int ns) {
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-  for (int s = 0; s < S; s++) {
-    double e = beta[s] * mu;
-    if (mw[s] & bm) e = beta[s] * omm;
-    beta[s] = (!PAD || s < ns) ? e : 0.0;
-    if ((s & 3) == 0) a0 += beta[s];
-    else if ((s & 3) == 1) a1 += beta[s];
-    else if ((s & 3) == 2) a2 += beta[s];
-    else a3 += beta[s];
-  }
-  return (a0 + a1) + (a2 + a3);
-}
-
-// PAD = false asserts K == L*S (no padded states: the per-state guards compile away);
-// WPC = maximum warps per CTA, fewer may be launched
-template <int L, int S, int B, bool PAD, int WPC, int MINB>
-__global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_constant__ KgwParams P) {
+// PAD = false asserts K == L*S (no padded states: the per-state guards compile away)
+template <int L, int S, int B, bool PAD, int MINB>
+__global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant__ KgwParams P) {
   using C = Cfg<L, S, B>;
   constexpr int G = C::G;
-  constexpr int KP = C::KP;
+  constexpr int SPR = C::SPR, SPW = C::SPW, NQ = C::NQ, NP = C::NP, CS = C::CS, NC = C::NC, ROW = C::ROW, TILE = C::TILE;
+  constexpr int NCT = L * NC;  // chunks per haplotype
+  static_assert(RESCALE % B == 0 && 32 % B == 0, "blocks must not straddle words or rescale points");
   const int lane = threadIdx.x & 31;
-  const int wic = threadIdx.x >> 5;
   const int g = lane % G;
   const int lig = lane / G;
   const int k0 = lig * S;
   const int K = P.K;
   const int ns = PAD ? min(S, max(0, K - k0)) : S;  // states owned by this lane
-  const int wpc = blockDim.x >> 5;
-  const int slot = blockIdx.x * wpc + wic;
-  const int nslots = gridDim.x * wpc;
+  const int slot = blockIdx.x;
+  const int nslots = gridDim.x;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned char *ws = smem_raw + (size_t)wic * C::warp_bytes();
-  double *rows = reinterpret_cast<double *>(ws);                                  // [B+1][KP][G]
-  double *ckst = rows + (size_t)(B - 1) * KP * G;                                 // [2][KP][G] checkpoint staging
-  uint32_t *refw = reinterpret_cast<uint32_t *>(ws + C::rows_bytes);              // [2][KP][G]
-  double *sest = reinterpret_cast<double *>(ws + C::rows_bytes + C::refw_bytes);  // [2][B][32]
-  uint8_t *ztile = ws + C::rows_bytes + C::refw_bytes + C::se_bytes;              // [32][G]
-  uint8_t *zktile = ztile + 32 * G;                                               // [32][G]
+  double *rowbuf = reinterpret_cast<double *>(smem_raw);                         // [2][ROW]
+  uint32_t *mwt = reinterpret_cast<uint32_t *>(smem_raw + C::rows_bytes);        // [TILE]
+  uint8_t *ztile2 = smem_raw + C::rows_bytes + C::tiles_bytes;                   // [32][G]   (sweep 2)
+  uint8_t *ztile3 = reinterpret_cast<uint8_t *>(rowbuf + ROW);                   // [32][G]   (sweep 3, in row 1)
+  uint8_t *zktile3 = ztile3 + 32 * G;                                            // [32][G]
 
-  double *ck = P.ckpt + (size_t)slot * P.ckpt_stride;    // [nblk][KP][G]
-  double *se = P.sebuf + (size_t)slot * P.se_stride;     // [p][32]
-  uint8_t *zb = P.zbuf + (size_t)slot * P.z_stride;      // [p][G]
+  uint32_t *mw = P.mwbuf + (size_t)slot * P.mw_stride;   // [stride_w][TILE]
+  double *ck = P.ckpt + (size_t)slot * P.ckpt_stride;    // [seg_loci/B][ROW]
+  double *sgk = P.segck + (size_t)slot * P.segck_stride; // [nseg][ROW]
+  double *csb = P.csbuf + (size_t)slot * P.cs_stride;    // [seg_loci][128]
+  double *seb = P.sebuf + (size_t)slot * P.se_stride;    // [seg_loci][G]
+  uint8_t *zb = P.zbuf + (size_t)slot * P.z_stride;      // [p32][G]
   uint8_t *zkb = P.zkbuf + (size_t)slot * P.z_stride;
+
+  // 16-byte units owned by this lane: pair q of a row at rowoff + q*G, quad q of a tile at mwoff + q*G
+  const int rowoff = lig * NP * G + g;
+  const int mwoff = lig * NQ * G + g;
+  // dynamic addressing of state k of this lane's haplotype (slot index = k + (k/S) * padding of a lane)
+  auto row_idx = [&](int k) {
+    const int kl = (SPR == S) ? k : k + (k / S) * (SPR - S);
+    return ((kl >> 1) * G + g) * 2 + (kl & 1);
+  };
+  auto mw_idx = [&](int k) {
+    const int kl = (SPW == S) ? k : k + (k / S) * (SPW - S);
+    return ((kl >> 2) * G + g) * 4 + (kl & 3);
+  };
+
+  const int PS = P.seg_loci;
 
   for (int task = slot; task < P.n_tasks; task += nslots) {
     const int tidx = task * G + g;
@@ -272,53 +305,106 @@ __global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_co
       const int32_t *ref = P.ref_local + ((size_t)hap * P.W + ps.w) * K;
       __syncwarp();
 
-      // asynchronous prefetch of the reference words of 32-locus word `w` into tile `buf`
-      auto prefetch_words = [&](int w, int buf) {
+      // ------------------------------------------------------------------ gather: match words -> scratch
+      for (int wq = wlo >> 2; wq <= (whi >> 2); wq++) {
+        const uint4 hw4 = __ldg(reinterpret_cast<const uint4 *>(P.Hw + hoff) + wq);
 #pragma unroll
-        for (int s = 0; s < S; s++) {
-          const int id = (!PAD || s < ns) ? __ldg(ref + k0 + s) : hap;
-          cp_async4(refw + buf * KP * G + (k0 + s) * G + g, P.Hw + (size_t)id * P.stride_w + w);
+        for (int q = 0; q < NQ; q++) {
+          uint4 v[4];
+          bool ok[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int s = 4 * q + i;
+            ok[i] = (s < S) && (!PAD || s < ns);
+            const int id = ok[i] ? __ldg(ref + k0 + s) : hap;
+            v[i] = __ldg(reinterpret_cast<const uint4 *>(P.Hw + (size_t)id * P.stride_w) + wq);
+          }
+          uint4 o0, o1, o2, o3;  // one per word of the quad; components = the four states
+          o0.x = ok[0] ? ~(hw4.x ^ v[0].x) : 0u; o0.y = ok[1] ? ~(hw4.x ^ v[1].x) : 0u;
+          o0.z = ok[2] ? ~(hw4.x ^ v[2].x) : 0u; o0.w = ok[3] ? ~(hw4.x ^ v[3].x) : 0u;
+          o1.x = ok[0] ? ~(hw4.y ^ v[0].y) : 0u; o1.y = ok[1] ? ~(hw4.y ^ v[1].y) : 0u;
+          o1.z = ok[2] ? ~(hw4.y ^ v[2].y) : 0u; o1.w = ok[3] ? ~(hw4.y ^ v[3].y) : 0u;
+          o2.x = ok[0] ? ~(hw4.z ^ v[0].z) : 0u; o2.y = ok[1] ? ~(hw4.z ^ v[1].z) : 0u;
+          o2.z = ok[2] ? ~(hw4.z ^ v[2].z) : 0u; o2.w = ok[3] ? ~(hw4.z ^ v[3].z) : 0u;
+          o3.x = ok[0] ? ~(hw4.w ^ v[0].w) : 0u; o3.y = ok[1] ? ~(hw4.w ^ v[1].w) : 0u;
+          o3.z = ok[2] ? ~(hw4.w ^ v[2].w) : 0u; o3.w = ok[3] ? ~(hw4.w ^ v[3].w) : 0u;
+          uint4 *dst = reinterpret_cast<uint4 *>(mw + (size_t)(4 * wq) * TILE) + mwoff + q * G;
+          st_cg(dst, o0);
+          st_cg(dst + TILE / 4, o1);
+          st_cg(dst + 2 * (TILE / 4), o2);
+          st_cg(dst + 3 * (TILE / 4), o3);
+        }
+      }
+      __syncwarp();
+
+      // asynchronous copy of this lane's quads of match-word tile `w` into buffer `buf`
+      auto prefetch_tile = [&](int w) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(mw + (size_t)w * TILE) + mwoff;
+        uint4 *dst = reinterpret_cast<uint4 *>(mwt) + mwoff;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) cp_async16(dst + q * G, src + q * G);
+      };
+      // this lane's match words of the staged tile -> registers
+      auto load_mw = [&](uint32_t (&mwr)[S]) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(mwt) + mwoff;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const uint4 t = src[q * G];
+          if (4 * q + 0 < S) mwr[4 * q + 0] = t.x;
+          if (4 * q + 1 < S) mwr[(4 * q + 1 < S) ? 4 * q + 1 : 0] = t.y;
+          if (4 * q + 2 < S) mwr[(4 * q + 2 < S) ? 4 * q + 2 : 0] = t.z;
+          if (4 * q + 3 < S) mwr[(4 * q + 3 < S) ? 4 * q + 3 : 0] = t.w;
         }
       };
+      // message row registers -> global row (this lane's pairs; padded slots are written as zero)
+      auto store_row = [&](const double (&beta)[S], double *row) {
+        double2 *dst = reinterpret_cast<double2 *>(row) + rowoff;
+#pragma unroll
+        for (int q = 0; q < NP; q++) st_cg(dst + q * G, beta[2 * q], (2 * q + 1 < S) ? beta[(2 * q + 1 < S) ? 2 * q + 1 : 0] : 0.0);
+      };
 
-      // ------------------------------------------------------------------ sweep 1: backward + checkpoints
-      if (!(P.skip_sweeps & 1)) {
-        double beta[S];
-        uint32_t mw[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) beta[s] = (!PAD || s < ns) ? 1.0 / K : 0.0;  // knockoffs.cpp:1046
-        {
-          const int n = (je - 1) / B;
-#pragma unroll
-          for (int s = 0; s < S; s++) ck[((size_t)n * KP + k0 + s) * G + g] = beta[s];
-        }
-        int wi = whi;
-        prefetch_words(wi, wi & 1);
+      // backward recursion from locus `hi_m` (messages of hi_m in `beta`) down to `lo_m`; FULLSTORE:
+      // rows every B loci + partial sums + totals (sweep 1, scratch relative to seg0); otherwise only
+      // the rows at segment tops (sweep 0).
+      auto backward = [&](double (&beta)[S], int lo_m, int hi_m, int seg0, bool fullstore) {
+        uint32_t mwr[S];
+        int wi = hi_m >> 5;
+        const int wl = lo_m >> 5;
+        prefetch_tile(wi);
         cp_async_wait_all();
-        __syncwarp();
-        uint32_t hw = __ldg(P.Hw + hoff + wi);
-#pragma unroll
-        for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
-        if (wi > wlo) prefetch_words(wi - 1, (wi - 1) & 1);
-        KgwLocusHMM h = P.hmm[je - 1];
-        for (int m = je - 1; m >= js; m--) {
+        load_mw(mwr);
+        if (wi > wl) prefetch_tile(wi - 1);   // this lane's quads are in registers: the buffer is free
+        KgwLocusHMM h = P.hmm[hi_m];
+        for (int m = hi_m; m >= lo_m; m--) {
           if ((m >> 5) != wi) {
             wi = m >> 5;
             cp_async_wait_all();
-            __syncwarp();
-            hw = __ldg(P.Hw + hoff + wi);
-#pragma unroll
-            for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
-            if (wi > wlo) prefetch_words(wi - 1, (wi - 1) & 1);
+            load_mw(mwr);
+            if (wi > wl) prefetch_tile(wi - 1);
           }
-          const KgwLocusHMM hn = P.hmm[m > js ? m - 1 : js];
+          const KgwLocusHMM hn = P.hmm[m > lo_m ? m - 1 : lo_m];
           const uint32_t bm = 1u << (m & 31);
-          const double pl = emit_and_sum<S, PAD>(beta, mw, bm, h.omm, h.mu, ns);  // beta := e
-          se[(size_t)m * 32 + lane] = pl;
-          if (m == js) {
-            break;
+          // emission-weighted messages e = beta * E (knockoffs.cpp:1052-1060 without the constant factor a)
+          double cs[NC];
+#pragma unroll
+          for (int c = 0; c < NC; c++) cs[c] = 0.0;
+#pragma unroll
+          for (int s = 0; s < S; s++) {
+            double e = beta[s] * h.mu;
+            if (mwr[s] & bm) e = beta[s] * h.omm;
+            if (PAD && s >= ns) e = 0.0;
+            beta[s] = e;
+            cs[s / CS] += e;
           }
+          const double pl = (cs[0] + cs[1]) + (cs[2] + cs[3]);
           const double Se = group_sum<L>(pl);
+          if (fullstore) {
+            double2 *d = reinterpret_cast<double2 *>(csb + (size_t)(m - seg0) * 128);
+            st_cg(d + lane, cs[0], cs[1]);
+            st_cg(d + 32 + lane, cs[2], cs[3]);
+            if (lig == 0) st_cg(seb + (size_t)(m - seg0) * G + g, Se);
+          }
+          if (m == lo_m) break;
           const double c = h.a * Se;
 #pragma unroll
           for (int s = 0; s < S; s++) beta[s] = (!PAD || s < ns) ? fma(h.b, beta[s], c) : 0.0;  // :1062-1068
@@ -333,158 +419,247 @@ __global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_co
                 for (int s = 0; s < S; s++) beta[s] *= sc;
               }
             }
-            const int n = j / B;
-#pragma unroll
-            for (int s = 0; s < S; s++) ck[((size_t)n * KP + k0 + s) * G + g] = beta[s];
+            if (fullstore) store_row(beta, ck + (size_t)((j - seg0) / B) * ROW);
+            else if ((j % PS) == PS - 1) store_row(beta, sgk + (size_t)(j / PS) * ROW);
           }
           h = hn;
         }
-      }
-      __syncwarp();
+      };
 
-      // debug: normalised backward messages at the checkpoint loci of the last pass
-      if (P.dbg_beta != nullptr && ip == P.n_passes - 1) {
-        for (int n = js / B; n <= (je - 1) / B; n++) {
-          double v[S];
-          double acc = 0.0;
+      const int seg_first = js / PS, seg_last = (je - 1) / PS;
+      // ------------------------------------------------------------------ sweep 0: segment-top rows
+      if (seg_last > seg_first && !(P.skip_sweeps & 1)) {
+        double beta[S];
 #pragma unroll
-          for (int s = 0; s < S; s++) { v[s] = ck[((size_t)n * KP + k0 + s) * G + g]; acc += v[s]; }
-          const double tot = group_sum<L>(acc);
-          if (active && n < P.dbg_nblk) {
+        for (int s = 0; s < S; s++) beta[s] = (!PAD || s < ns) ? 1.0 / K : 0.0;  // knockoffs.cpp:1046
+        backward(beta, seg_first * PS + PS - 1, je - 1, 0, false);
+        __syncwarp();
+      }
+
+      UniformSrc usz;
+      usz.init(P, hap, STREAM_Z, ps.w);
+      int zprev = 0;
+
+      for (int sg = seg_first; sg <= seg_last; sg++) {
+        const int seg0 = sg * PS;                 // scratch origin of this segment
+        const int slo = max(seg0, js), shi = min(seg0 + PS, je);   // [slo, shi)
+        __syncwarp();
+        // ---------------------------------------------------------------- sweep 1: backward + stores
+        if (!(P.skip_sweeps & 1)) {
+          double beta[S];
+          if (sg == seg_last) {
 #pragma unroll
-            for (int s = 0; s < S; s++)
-              if (!PAD || s < ns) P.dbg_beta[((size_t)tt * P.dbg_nblk + n) * K + k0 + s] = v[s] / tot;
+            for (int s = 0; s < S; s++) beta[s] = (!PAD || s < ns) ? 1.0 / K : 0.0;  // knockoffs.cpp:1046
+          } else {
+            const double2 *src = reinterpret_cast<const double2 *>(sgk + (size_t)sg * ROW) + rowoff;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+              const double2 t = ld_cg(src + q * G);
+              beta[2 * q] = t.x;
+              if (2 * q + 1 < S) beta[(2 * q + 1 < S) ? 2 * q + 1 : 0] = t.y;
+            }
+          }
+          store_row(beta, ck + (size_t)((shi - 1 - seg0) / B) * ROW);
+          backward(beta, slo, shi - 1, seg0, true);
+        }
+        __syncwarp();
+
+        // debug: normalised backward messages at the block-top loci of the last pass
+        if (P.dbg_beta != nullptr && ip == P.n_passes - 1) {
+          for (int n = slo / B; n <= (shi - 1) / B; n++) {
+            double v[S];
+            double acc = 0.0;
+            const double2 *src = reinterpret_cast<const double2 *>(ck + (size_t)(n - seg0 / B) * ROW) + rowoff;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+              const double2 t = ld_cg(src + q * G);
+              v[2 * q] = t.x;
+              if (2 * q + 1 < S) v[(2 * q + 1 < S) ? 2 * q + 1 : 0] = t.y;
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) acc += v[s];
+            const double tot = group_sum<L>(acc);
+            if (active && n < P.dbg_nblk) {
+#pragma unroll
+              for (int s = 0; s < S; s++)
+                if (!PAD || s < ns) P.dbg_beta[((size_t)tt * P.dbg_nblk + n) * K + k0 + s] = v[s] / tot;
+            }
           }
         }
-      }
 
-      // ------------------------------------------------------------------ sweep 2: recompute + draw z
-      if (!(P.skip_sweeps & 2)) {
-        double beta[S];
-        uint32_t mw[S];
-        UniformSrc us;
-        us.init(P, hap, STREAM_Z, ps.w);
-        int zprev = 0;
-        int wi = wlo;
-        prefetch_words(wi, wi & 1);
-        cp_async_wait_all();
-        __syncwarp();
-        uint32_t hw = __ldg(P.Hw + hoff + wi);
+        // ---------------------------------------------------------------- sweep 2: latent path z
+        if (!(P.skip_sweeps & 2)) {
+          int wi = slo >> 5;
+          // top row of block n (in segment-relative block index) -> row buffer (n & 1), this lane's pairs
+          auto prefetch_row = [&](int n) {
+            const double2 *src = reinterpret_cast<const double2 *>(ck + (size_t)(n - seg0 / B) * ROW) + rowoff;
+            double2 *dst = reinterpret_cast<double2 *>(rowbuf + (size_t)(n & 1) * ROW) + rowoff;
 #pragma unroll
-        for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
-        if (wi < whi) prefetch_words(wi + 1, (wi + 1) & 1);
-        // loci of this word outside [js, je) keep the values of earlier window passes
-        for (int i = lane; i < 8 * G; i += 32)
-          reinterpret_cast<uint32_t *>(ztile)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
-        __syncwarp();
-        // checkpoint (= messages of the block's top locus) and per-lane sums of block n -> staging
-        // (asynchronous, one block ahead)
-        auto prefetch_block = [&](int n) {
-          double *dst = ckst + (size_t)(n & 1) * KP * G;
-#pragma unroll
-          for (int s = 0; s < S; s++)
-            cp_async8(dst + (k0 + s) * G + g, ck + ((size_t)n * KP + k0 + s) * G + g);
-          const int lo_n = max(n * B, js), top_n = min(n * B + B, je) - 1;
-          for (int j = lo_n; j <= top_n; j++)
-            cp_async8(sest + ((n & 1) * B + (j - n * B)) * 32 + lane, se + (size_t)j * 32 + lane);
-        };
-        const int n_last = (je - 1) / B;
-        prefetch_block(js / B);
-        KgwLocusHMM hj = P.hmm[js];
-        KgwLocusHMM hrec = P.hmm[min((js / B) * B + B, je) - 1];
-        for (int n = js / B; n <= n_last; n++) {
-          const int nb = n * B;
-          const int lo = max(nb, js);
-          const int top = min(nb + B, je) - 1;
-          if ((lo >> 5) != wi) {
-            // flush the finished z tile, then switch to the next 32-locus word
-            __syncwarp();
-            for (int i = lane; i < 8 * G; i += 32)
-              reinterpret_cast<uint32_t *>(zb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(ztile)[i];
-            wi = lo >> 5;
-            cp_async_wait_all();
-            __syncwarp();
-            for (int i = lane; i < 8 * G; i += 32)
-              reinterpret_cast<uint32_t *>(ztile)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
-            hw = __ldg(P.Hw + hoff + wi);
-#pragma unroll
-            for (int s = 0; s < S; s++) mw[s] = ~(hw ^ refw[(wi & 1) * KP * G + (k0 + s) * G + g]);
-            if (wi < whi) prefetch_words(wi + 1, (wi + 1) & 1);
-          }
+            for (int q = 0; q < NP; q++) cp_async16(dst + q * G, src + q * G);
+          };
+          prefetch_tile(wi);
+          prefetch_row(slo / B);
+          // loci of this word outside the pass keep the values of earlier window passes
+          for (int i = lane; i < 8 * G; i += 32)
+            reinterpret_cast<uint32_t *>(ztile2)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
           cp_async_wait_all();
           __syncwarp();
-          if (n < n_last) prefetch_block(n + 1);
-          const double *toprow = ckst + (size_t)(n & 1) * KP * G;
-          const KgwLocusHMM hrec_next = P.hmm[min(nb + 2 * B, je) - 1];  // top locus of the next block
-          if (B > 1) {
-            // B-1 recomputed steps below the staged top row
+          uint32_t hw = __ldg(P.Hw + hoff + wi);
+          const int n_last = (shi - 1) / B;
+          for (int n = slo / B; n <= n_last; n++) {
+            const int nb = n * B;
+            const int lo = max(nb, slo);
+            const int top = min(nb + B, shi) - 1;
+            // per-locus constants of the block; loci above `top` get the identity step
+            double tb[B], tmu[B], tomm[B], ta[B], tcm[B], tse[B];
 #pragma unroll
-            for (int s = 0; s < S; s++) beta[s] = toprow[(k0 + s) * G + g];
-            KgwLocusHMM hr = hrec;
-            for (int m = top; m > lo; m--) {
-              const KgwLocusHMM h = hr;
-              hr = P.hmm[m - 1];
-              const double pl = emit_and_sum<S, PAD>(beta, mw, 1u << (m & 31), h.omm, h.mu, ns);
-              const double Se = group_sum<L>(pl);
-              const double c = h.a * Se;
-#pragma unroll
-              for (int s = 0; s < S; s++) {
-                beta[s] = (!PAD || s < ns) ? fma(h.b, beta[s], c) : 0.0;
-                rows[((m - 1 - nb) * KP + k0 + s) * G + g] = beta[s];
+            for (int mm = 0; mm < B; mm++) {
+              const int m = nb + mm;
+              if (m >= lo && m <= top) {
+                const KgwLocusHMM h = P.hmm[m];
+                tb[mm] = h.b; tmu[mm] = h.mu; tomm[mm] = h.omm; ta[mm] = h.a;
+                tse[mm] = ld_cg(seb + (size_t)(m - seg0) * G + g);
+                tcm[mm] = h.a * tse[mm];
+              } else {
+                tb[mm] = 1.0; tmu[mm] = 1.0; tomm[mm] = 1.0; ta[mm] = 0.0; tcm[mm] = 0.0; tse[mm] = 0.0;
               }
             }
-            __syncwarp();
-          }
-          hrec = hrec_next;
-          // forward draws through the block (knockoffs.cpp:1232-1260)
-          for (int j = lo; j <= top; j++) {
-            const KgwLocusHMM h = hj;
-            hj = P.hmm[j + 1 < je ? j + 1 : j];
-            const uint32_t bm = 1u << (j & 31);
-            const bool hbit = hw & bm;
-            const double amis = hbit ? h.amu : h.amup;
-            const double *row = (j == top) ? toprow : rows + (size_t)(j - nb) * KP * G;
-            const double pl = sest[((n & 1) * B + (j - nb)) * 32 + lane];
-            double Se;
-            const double base = group_excl<L>(pl, lane, Se);
-            // the one state whose transition weight carries b_j: k == z_{j-1}
-            double X = 0.0;
-            if (j > js) {
-              const double bz = row[zprev * G + g];
-              const uint32_t wz = ~(hw ^ refw[(wi & 1) * KP * G + zprev * G + g]);
-              X = h.b * (bz * ((wz & bm) ? h.omm : (hbit ? h.mu : h.mup)));
+            if ((lo >> 5) != wi) {
+              // flush the finished z tile, then switch to the next 32-locus word
+              __syncwarp();
+              for (int i = lane; i < 8 * G; i += 32)
+                reinterpret_cast<uint32_t *>(zb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(ztile2)[i];
+              wi = lo >> 5;
+              for (int i = lane; i < 8 * G; i += 32)
+                reinterpret_cast<uint32_t *>(ztile2)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
+              hw = __ldg(P.Hw + hoff + wi);
+              prefetch_tile(wi);   // every lane is past the barrier above: the old tile is no longer read
+              cp_async_wait_all();
+              __syncwarp();
+            } else {
+              cp_async_wait_all();
+              __syncwarp();
             }
-            const double R = us.get(j) * fma(h.a, Se, X);
-            const double tA = R, tB = R - X;
-            double run = h.a * base;
-            int cA = 0, cB = 0;
+            if (n < n_last) prefetch_row(n + 1);
+            const double *row = rowbuf + (size_t)(n & 1) * ROW;
+            const uint32_t *tile = mwt;
+            const int bit0 = nb & 31;
+
 #pragma unroll
-            for (int s = 0; s < S; s++) {
-              const double e = row[(k0 + s) * G + g] * ((mw[s] & bm) ? h.aomm : amis);
-              run += e;
-              count_le(cA, run, tA);
-              count_le(cB, run, tB);
+            for (int jj = 0; jj < B; jj++) {
+              const int j = nb + jj;
+              if (j < lo || j > top) continue;
+              const int bit = bit0 + jj;
+              const bool hbit = (hw >> bit) & 1u;
+              const double aj = ta[jj], bj = tb[jj], ommj = tomm[jj], muj = tmu[jj];
+              const double mupj = __dsub_rn(1.0, ommj);              // knockoffs.cpp:1251-1256 quirk
+              const double aomm = __dmul_rn(aj, ommj);
+              const double amis = hbit ? __dmul_rn(aj, muj) : __dmul_rn(aj, mupj);
+              // partial sums of this locus: the L lanes of the haplotype, four chunks each
+              double csv[NCT];
+              {
+                const double2 *d = reinterpret_cast<const double2 *>(csb + (size_t)(j - seg0) * 128);
+#pragma unroll
+                for (int lg = 0; lg < L; lg++) {
+                  const double2 t0 = ld_cg(d + lg * G + g), t1 = ld_cg(d + 32 + lg * G + g);
+                  csv[lg * NC + 0] = t0.x; csv[lg * NC + 1] = t0.y; csv[lg * NC + 2] = t1.x; csv[lg * NC + 3] = t1.y;
+                }
+              }
+              // message of locus j at one state: staged top row, then the steps top -> j
+              auto chain = [&](double v, uint32_t mword) {
+#pragma unroll
+                for (int mm = B - 1; mm > jj; mm--) {
+                  const double E = ((mword >> (bit0 + mm)) & 1u) ? tomm[mm] : tmu[mm];
+                  v = fma(tb[mm], v * E, tcm[mm]);
+                }
+                return v;
+              };
+              // the one state whose transition weight carries b_j: k == z_{j-1}
+              double X = 0.0;
+              if (j > js) {
+                const uint32_t mwz = tile[mw_idx(zprev)];
+                const double bz = chain(row[row_idx(zprev)], mwz);
+                X = bj * (bz * (((mwz >> bit) & 1u) ? ommj : (hbit ? muj : mupj)));
+              }
+              const double R = usz.get(j) * fma(aj, tse[jj], X);
+              const double tA = R, tB = R - X;
+              // chunk level: #chunks whose end prefix is <= threshold
+              int CA = 0, CB = 0;
+              {
+                double T = 0.0;
+#pragma unroll
+                for (int c = 0; c < NCT; c++) {
+                  T += csv[c];
+                  const double PT = aj * T;
+                  count_le(CA, PT, tA);
+                  count_le(CB, PT, tB);
+                }
+              }
+              const int lgz = zprev / S;
+              const int cz = lgz * NC + (zprev - lgz * S) / CS;
+              const int csel = (CA > cz) ? CB : CA;
+              const int cst = min(csel, NCT - 1);
+              double Tb = 0.0;
+#pragma unroll
+              for (int c = 0; c < NCT - 1; c++) if (c < cst) Tb += csv[c];
+              const int lgs = cst / NC, ci = cst - lgs * NC;
+              const int nss = PAD ? min(S, max(0, K - lgs * S)) : S;
+              const int n_in = min(CS, nss - ci * CS);       // valid states of the chunk (may be <= 0)
+              const int kb = lgs * S + ci * CS;
+              const int klr = lgs * SPR + ci * CS, klw = lgs * SPW + ci * CS;
+              double run = aj * Tb;
+              int cA = 0, cB = 0;
+              {
+                const double2 *r2 = reinterpret_cast<const double2 *>(row) + (klr >> 1) * G + g;
+                const uint4 *t4 = reinterpret_cast<const uint4 *>(tile) + (klw >> 2) * G + g;
+#pragma unroll
+                for (int qq = 0; qq < CS / 4; qq++) {
+                  if (4 * qq < n_in) {
+                    const uint4 mq = t4[qq * G];
+                    const double2 va = r2[(2 * qq) * G];
+                    const double2 vb = (4 * qq + 2 < n_in) ? r2[(2 * qq + 1) * G] : make_double2(0.0, 0.0);
+                    const double v4[4] = {va.x, va.y, vb.x, vb.y};
+                    const uint32_t m4[4] = {mq.x, mq.y, mq.z, mq.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                      if (4 * qq + i < n_in) {
+                        const double bv = chain(v4[i], m4[i]);
+                        run += bv * (((m4[i] >> bit) & 1u) ? aomm : amis);
+                        count_le(cA, run, tA);
+                        count_le(cB, run, tB);
+                      }
+                    }
+                  }
+                }
+              }
+              int z;
+              if (CA > cz) {
+                z = max(kb + cB, zprev);
+              } else {
+                const int k1 = kb + cA;
+                const int k2 = (CB == CA) ? kb + cB : 0;
+                z = (k1 < zprev) ? k1 : max(k2, zprev);
+              }
+              z = min(z, K - 1);
+              zprev = z;
+              if (lig == 0) ztile2[bit * G + g] = (uint8_t)z;
             }
-            const int cc = group_sum_int<L>(cA | (cB << 16));
-            const int k1 = cc & 0xffff, k2 = cc >> 16;
-            int z = (k1 < zprev) ? k1 : max(k2, zprev);
-            z = min(z, K - 1);
-            zprev = z;
-            if (lig == 0) ztile[(j & 31) * G + g] = (uint8_t)z;
           }
+          __syncwarp();
+          for (int i = lane; i < 8 * G; i += 32)
+            reinterpret_cast<uint32_t *>(zb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(ztile2)[i];
         }
         __syncwarp();
-        for (int i = lane; i < 8 * G; i += 32)
-          reinterpret_cast<uint32_t *>(zb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(ztile)[i];
-      }
-      __syncwarp();
+      }  // segments
 
       // ------------------------------------------------------------------ sweep 3: knockoff path + alleles
       if (!(P.skip_sweeps & 4)) {
         double Nv[S];
 #pragma unroll
-        for (int s = 0; s < S; s++) Nv[s] = 1.0;  // knockoffs.cpp:1293-1294 (N == N_old between groups)
-        double *rrow = rows;                      // [KP][G] reciprocals 1/N_old, patched per group
+        for (int s = 0; s < S; s++) Nv[s] = (!PAD || s < ns) ? 1.0 : 0.0;  // knockoffs.cpp:1293-1294 (N == N_old between groups)
+        double sumN = (double)K;                                          // sum_k N_k of this haplotype
+        double *rrow = rowbuf;                                            // [ROW] reciprocals 1/N_old, patched per group
+        double2 *rrow2 = reinterpret_cast<double2 *>(rrow);
         UniformSrc us, uh;
         us.init(P, hap, STREAM_ZK, ps.w);
         uh.init(P, hap, STREAM_HK, ps.w);
@@ -496,7 +671,6 @@ __global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_co
           const int zi = ko_tab[js].z1_idx;
           if (zi >= 0) z1_pref = zb[(size_t)zi * G + g];
         }
-        prefetch_words(wlo, wlo & 1);
         constexpr int TW = (8 * G + 31) / 32;  // 32-bit words of a latent-path tile per lane
         uint32_t zreg[TW], zkreg[TW];
 #pragma unroll
@@ -511,24 +685,27 @@ __global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_co
           // latent-path tiles of this word (loaded into registers one word ahead), then prefetch the next
 #pragma unroll
           for (int i = 0; i < TW; i++) {
-            reinterpret_cast<uint32_t *>(ztile)[lane + 32 * i] = zreg[i];
-            reinterpret_cast<uint32_t *>(zktile)[lane + 32 * i] = zkreg[i];
+            if ((G >= 4) || (lane + 32 * i < 8 * G)) {
+              reinterpret_cast<uint32_t *>(ztile3)[lane + 32 * i] = zreg[i];
+              reinterpret_cast<uint32_t *>(zktile3)[lane + 32 * i] = zkreg[i];
+            }
           }
           if (wi < whi) {
 #pragma unroll
             for (int i = 0; i < TW; i++) {
-              zreg[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)((wi + 1) << 5) * G)[lane + 32 * i];
-              zkreg[i] = reinterpret_cast<const uint32_t *>(zkb + (size_t)((wi + 1) << 5) * G)[lane + 32 * i];
+              if ((G >= 4) || (lane + 32 * i < 8 * G)) {
+                zreg[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)((wi + 1) << 5) * G)[lane + 32 * i];
+                zkreg[i] = reinterpret_cast<const uint32_t *>(zkb + (size_t)((wi + 1) << 5) * G)[lane + 32 * i];
+              }
             }
           }
-          cp_async_wait_all();
+          prefetch_tile(wi);   // needed by the allele draws at the end of this word
           __syncwarp();
-          if (wi < whi) prefetch_words(wi + 1, (wi + 1) & 1);
           KgwLocusKO k = ko_tab[lo];
           for (int j = lo; j < hi; j++) {
             const KgwLocusKO kn = ko_tab[j + 1 < je ? j + 1 : j];
             const int bit = j & 31;
-            const int zj = ztile[bit * G + g];
+            const int zj = ztile3[bit * G + g];
             const bool lastg = k.flags & KGW_KO_LASTGRP;
             const double u = us.get(j);
             int zk;
@@ -536,93 +713,132 @@ __global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_co
               z1 = z1_pref;
               if (k.z1_next >= 0) z1_pref = zb[(size_t)k.z1_next * G + g];
               const bool gz = k.flags & KGW_KO_GZERO;
-              // pass A: reciprocals of N_old and their sum
-              double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+              // pass A: reciprocals of N_old -> shared row, chunk sums
+              double cs[NC];
 #pragma unroll
-              for (int s = 0; s < S; s++) {
-                const double r = (!PAD || s < ns) ? fast_rcp(Nv[s]) : 0.0;
-                rrow[(k0 + s) * G + g] = r;
-                if ((s & 3) == 0) a0 += r;
-                else if ((s & 3) == 1) a1 += r;
-                else if ((s & 3) == 2) a2 += r;
-                else a3 += r;
+              for (int c = 0; c < NC; c++) cs[c] = 0.0;
+#pragma unroll
+              for (int q = 0; q < NP; q++) {
+                const int s0 = 2 * q, s1 = 2 * q + 1;
+                const double r0 = (!PAD || s0 < ns) ? fast_rcp(Nv[s0]) : 0.0;
+                const double r1 = (s1 < S && (!PAD || s1 < ns)) ? fast_rcp(Nv[(s1 < S) ? s1 : 0]) : 0.0;
+                rrow2[rowoff + q * G] = make_double2(r0, r1);
+                cs[s0 / CS] += r0;
+                if (s1 < S) cs[((s1 < S) ? s1 : 0) / CS] += r1;
               }
-              double pls = (a0 + a1) + (a2 + a3);
               __syncwarp();
               // the (at most two) states equal to z0 / z0k carry T_k(z0)*T_k(z0k) != tg  (:1350-1354)
               if (!gz) {
-                const double r0 = rrow[z0 * G + g];
+                const double r0 = rrow[row_idx(z0)];
                 double n0, n0k = 0.0, r0k = 0.0;
                 if (z0 == z0k) {
                   n0 = r0 * k.f2;
                 } else {
                   n0 = r0 * k.f1;
-                  r0k = rrow[z0k * G + g];
+                  r0k = rrow[row_idx(z0k)];
                   n0k = r0k * k.f1;
                 }
                 __syncwarp();
                 if (lig == 0) {
-                  rrow[z0 * G + g] = n0;
-                  if (z0 != z0k) rrow[z0k * G + g] = n0k;
+                  rrow[row_idx(z0)] = n0;
+                  if (z0 != z0k) rrow[row_idx(z0k)] = n0k;
                 }
-                if (z0 / S == lig) pls += n0 - r0;
-                if (z0 != z0k && z0k / S == lig) pls += n0k - r0k;
+                const int lg0 = z0 / S, c0 = (z0 - lg0 * S) / CS;
+                const int lg0k = z0k / S, c0k = (z0k - lg0k * S) / CS;
+                const double d0 = (lg0 == lig) ? n0 - r0 : 0.0;
+                const double d0k = (z0 != z0k && lg0k == lig) ? n0k - r0k : 0.0;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                  if (c == c0) cs[c] += d0;
+                  if (c == c0k) cs[c] += d0k;
+                }
               }
               __syncwarp();
-              const double Sr = group_sum<L>(pls);
+              const double Sr = group_sum<L>((cs[0] + cs[1]) + (cs[2] + cs[3]));
               const double Nsum = (k.flags & KGW_KO_GSTART) ? k.sa : k.tg * Sr;  // :1345-1358
               const double c2 = k.vb * Nsum;
-              // pass B: partition function update and normaliser (:1360-1390).  The last group keeps N
-              // (zero coefficients make the update an exact identity) but still renormalises it.
+              // pass B: partition function update, normalised (:1360-1390).  The last group keeps N (zero
+              // coefficients make the update an exact identity) but still renormalises it.  The normaliser
+              // sum_k (N_k + c2 + vstg r_k) is formed from the haplotype's running sum_k N_k.
               const double c2u = lastg ? 0.0 : c2;
               const double vsu = lastg ? 0.0 : k.vstg;
-              double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+              const double norm = fma(vsu, Sr, fma((double)K, c2u, sumN));
+              const double rN = fast_rcp(norm);
+              const double cA_ = vsu * rN, cC_ = c2u * rN;
 #pragma unroll
-              for (int s = 0; s < S; s++) {
-                double nv = fma(vsu, rrow[(k0 + s) * G + g], Nv[s] + c2u);
-                nv = (!PAD || s < ns) ? nv : 0.0;
-                Nv[s] = nv;
-                if ((s & 3) == 0) b0 += nv;
-                else if ((s & 3) == 1) b1 += nv;
-                else if ((s & 3) == 2) b2 += nv;
-                else b3 += nv;
+              for (int q = 0; q < NP; q++) {
+                const int s0 = 2 * q, s1 = 2 * q + 1;
+                const double2 rr = rrow2[rowoff + q * G];
+                Nv[s0] = (!PAD || s0 < ns) ? fma(cA_, rr.x, fma(Nv[s0], rN, cC_)) : 0.0;
+                if (s1 < S) Nv[(s1 < S) ? s1 : 0] = (!PAD || s1 < ns) ? fma(cA_, rr.y, fma(Nv[(s1 < S) ? s1 : 0], rN, cC_)) : 0.0;
               }
-              const double rN = 1.0 / group_sum<L>((b0 + b1) + (b2 + b3));
-              // pass C: normalise; clamp to N_min (:1386-1389; the pre-normalisation clamp of :1380 cannot
-              // fire because N only grows).  The clamp is exact but rarely needed: a cheap integer minimum of
-              // the high words decides whether any state can be below N_min.
-              int hmin = 0x7fffffff;
+              // clamp to N_min (:1386-1389; the pre-normalisation clamp of :1380 cannot fire because N only
+              // grows).  Every N_k is at least cC_, so the clamp pass runs only when cC_ < N_min.
+              sumN = 1.0;
+              if (__any_sync(FULL, cC_ < N_MIN)) {
+                double acc = 0.0;
 #pragma unroll
-              for (int s = 0; s < S; s++) {
-                Nv[s] *= rN;
-                if (!PAD || s < ns) hmin = min(hmin, __double2hiint(Nv[s]));
-              }
-              if (hmin <= __double2hiint(N_MIN)) {
-#pragma unroll
-                for (int s = 0; s < S; s++) Nv[s] = (Nv[s] < N_MIN) ? N_MIN : Nv[s];
+                for (int s = 0; s < S; s++) {
+                  if (!PAD || s < ns) {
+                    Nv[s] = (Nv[s] < N_MIN) ? N_MIN : Nv[s];
+                    acc += Nv[s];
+                  }
+                }
+                acc = group_sum<L>(acc);
+                if (cC_ < N_MIN) sumN = acc;
               }
               // the state equal to z1 carries the extra vstar term in the draw (:1413-1419)
               __syncwarp();
               if (!lastg) {
-                const double rz = rrow[z1 * G + g];
+                const double rz = rrow[row_idx(z1)];
                 const double nz = rz * k.fz1;
                 __syncwarp();
-                if (lig == 0) rrow[z1 * G + g] = nz;
-                if (z1 / S == lig) pls += nz - rz;
+                if (lig == 0) rrow[row_idx(z1)] = nz;
+                const int lg1 = z1 / S, c1 = (z1 - lg1 * S) / CS;
+                const double d1 = (lg1 == lig) ? nz - rz : 0.0;
+#pragma unroll
+                for (int c = 0; c < NC; c++) if (c == c1) cs[c] += d1;
               }
               __syncwarp();
+              // two-level inverse-CDF search (weighted_choice, utils.cpp:690-698) in units of vb*tg
               double St;
-              const double base = group_excl<L>(pls, lane, St);
+              const double base = group_excl<L>((cs[0] + cs[1]) + (cs[2] + cs[3]), lane, St);
               const double t = u * St;
-              // pass D: inverse-CDF search (weighted_choice, utils.cpp:690-698) in units of vb*tg
-              double run = base;
               int cnt = 0;
+              {
+                double run = base;
 #pragma unroll
-              for (int s = 0; s < S; s++) {
-                run += rrow[(k0 + s) * G + g];
-                if (!PAD || s < ns) count_le(cnt, run, t);
+                for (int c = 0; c < NC; c++) {
+                  run += cs[c];
+                  count_le(cnt, run, t);
+                }
               }
-              zk = min(group_sum_int<L>(cnt), K - 1);
+              const int cst = min(group_sum_int<L>(cnt), NCT - 1);
+              const int lgs = cst / NC, ci = cst - lgs * NC;
+              double tb_own = base;
+#pragma unroll
+              for (int c = 0; c < NC - 1; c++) if (c < ci) tb_own += cs[c];
+              double run = __shfl_sync(FULL, tb_own, lgs * G + g);
+              const int nss = PAD ? min(S, max(0, K - lgs * S)) : S;
+              const int n_in = min(CS, nss - ci * CS);
+              const int klr = lgs * SPR + ci * CS;
+              int c2n = 0;
+              {
+                const double2 *r2 = rrow2 + (klr >> 1) * G + g;
+#pragma unroll
+                for (int q = 0; q < CS / 2; q++) {
+                  if (2 * q < n_in) {
+                    const double2 rr = r2[q * G];
+                    run += rr.x;
+                    count_le(c2n, run, t);
+                    if (2 * q + 1 < n_in) {
+                      run += rr.y;
+                      count_le(c2n, run, t);
+                    }
+                  }
+                }
+              }
+              zk = min(lgs * S + ci * CS + c2n, K - 1);
             } else {
               // inside a group every state has weight a*vb except k == zk_{j-1} and k == z1 (:1397-1419)
               const double wp = k.apb * ((!lastg && z1 == zkprev) ? (k.vb + k.vs) : k.vb);
@@ -653,22 +869,24 @@ __global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_co
             }
             zkprev = zk;
             if (k.flags & KGW_KO_LASTINGRP) { z0 = zj; z0k = zk; }
-            if (lig == 0) zktile[bit * G + g] = (uint8_t)zk;
+            if (lig == 0) zktile3[bit * G + g] = (uint8_t)zk;
             k = kn;
           }
+          cp_async_wait_all();
           __syncwarp();
           // flush the zk tile, then knockoff alleles of the core loci of this word (:1469-1502)
           for (int i = lane; i < 8 * G; i += 32)
-            reinterpret_cast<uint32_t *>(zkb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(zktile)[i];
+            reinterpret_cast<uint32_t *>(zkb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(zktile3)[i];
           const uint32_t hw = __ldg(P.Hw + hoff + wi);
-          const uint32_t *rw = refw + (wi & 1) * KP * G;
+          const uint32_t *tile = mwt;
           unsigned bits = 0u, mask = 0u;
           const int elo = max(lo, ps.cs), ehi = min(hi, ps.ce);
 #pragma unroll 4
           for (int j = elo + lig; j < ehi; j += L) {
             const int bit = j & 31;
-            const uint32_t w1 = rw[ztile[bit * G + g] * G + g];
-            const uint32_t w2 = rw[zktile[bit * G + g] * G + g];
+            // reference bit = target bit where the match word says "equal", its complement elsewhere
+            const uint32_t w1 = ~(tile[mw_idx(ztile3[bit * G + g])] ^ hw);
+            const uint32_t w2 = ~(tile[mw_idx(zktile3[bit * G + g])] ^ hw);
             const int combo = ((hw >> bit) & 1u) | (((w1 >> bit) & 1u) << 1) | (((w2 >> bit) & 1u) << 2);
             const double2 em = P.emit[j].ws[combo];
             const unsigned hk = (uh.get(j) * em.y < em.x) ? 0u : 1u;  // weighted_choice with 2 weights
@@ -687,8 +905,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) sampler_kernel(const __grid_co
       __syncwarp();
     }  // passes
 
+    __syncwarp();
     if (active && (P.dbg_z != nullptr || P.dbg_zk != nullptr)) {
-      __syncwarp();
       for (int j = lig; j < P.p; j += L) {
         if (P.dbg_z) P.dbg_z[(size_t)tt * P.p + j] = zb[(size_t)j * G + g];
         if (P.dbg_zk) P.dbg_zk[(size_t)tt * P.p + j] = zkb[(size_t)j * G + g];

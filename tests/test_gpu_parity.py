@@ -83,6 +83,11 @@ CASES = [
     dict(N=60, p=333, K=50, mean_group=2.0, W=4, block=2),
     dict(N=50, p=300, K=20, mean_group=1.0, block=8),
     dict(N=50, p=300, K=20, mean_group=6.0, block=2),
+    dict(N=90, p=300, K=50, mean_group=1.0, block=4, seg=64),
+    dict(N=90, p=301, K=50, mean_group=3.0, lanes=4, block=8, seg=128),
+    dict(N=60, p=333, K=50, mean_group=2.0, W=4, block=2, seg=32),
+    dict(N=50, p=257, K=20, mean_group=1.0, seg=96),
+    dict(N=40, p=200, K=7, mean_group=1.0, lanes=2, block=4),
     dict(N=30, p=1, K=5, mean_group=1.0),
     dict(N=30, p=2, K=5, mean_group=1.0),
     dict(N=30, p=33, K=5, mean_group=50.0),
@@ -92,10 +97,11 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
 def test_kernel_matches_oracle_synthetic(case):
     c = dict(case)
-    lanes, block = c.pop("lanes", 0), c.pop("block", 0)
+    lanes, block, seg = c.pop("lanes", 0), c.pop("block", 0), c.pop("seg", 0)
     prob = synthetic_problem(seed=len(repr(case)), **c)
     res = ko.run_unrelated(prob, mode="philox", want_beta=True)
-    hk, dbg = _run(prob, options=kg.Options(lanes_per_hap=lanes, block_loci=block), debug_paths=True, debug_beta=True)
+    hk, dbg = _run(prob, options=kg.Options(lanes_per_hap=lanes, block_loci=block, segment_loci=seg),
+                   debug_paths=True, debug_beta=True)
     assert np.array_equal(dbg.z, res.z)
     assert np.array_equal(dbg.zk, res.zk)
     assert np.array_equal(hk, res.hk)
