@@ -211,11 +211,13 @@ struct Cfg {
   static constexpr int TILE = L * SPW * G;      // 32-bit words per match-word tile
   // per-warp shared memory: two message rows (sweep 2: staged top rows of two blocks; sweep 3: the
   // reciprocal row and the two latent-path tiles), one match-word tile, the latent-path tile of sweep 2
-  static constexpr size_t rows_bytes = (size_t)2 * ROW * 8;
+  // (sweep 3 lays the reciprocal row, its two latent-path tiles and the 32 knockoff-table rows of the
+  // current word over the same bytes)
+  static constexpr size_t s3_bytes = (size_t)ROW * 8 + 2 * 32 * G + 32 * sizeof(KgwLocusKO);
+  static constexpr size_t rows_bytes = (size_t)2 * ROW * 8 > s3_bytes ? (size_t)2 * ROW * 8 : s3_bytes;
   static constexpr size_t tiles_bytes = (size_t)TILE * 4;
   static constexpr size_t ztile_bytes = (size_t)32 * G;
   __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + tiles_bytes + ztile_bytes; }
-  static_assert(2 * 32 * G <= ROW * 8, "latent-path tiles of sweep 3 must fit in the second row buffer");
 };
 
 // uniform of (hap, stream, locus j): Philox block cached per 4 loci
@@ -265,8 +267,9 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
   double *rowbuf = reinterpret_cast<double *>(smem_raw);                         // [2][ROW]
   uint32_t *mwt = reinterpret_cast<uint32_t *>(smem_raw + C::rows_bytes);        // [TILE]
   uint8_t *ztile2 = smem_raw + C::rows_bytes + C::tiles_bytes;                   // [32][G]   (sweep 2)
-  uint8_t *ztile3 = reinterpret_cast<uint8_t *>(rowbuf + ROW);                   // [32][G]   (sweep 3, in row 1)
+  uint8_t *ztile3 = reinterpret_cast<uint8_t *>(rowbuf + ROW);                   // [32][G]   (sweep 3, after row 0)
   uint8_t *zktile3 = ztile3 + 32 * G;                                            // [32][G]
+  KgwLocusKO *kot = reinterpret_cast<KgwLocusKO *>(zktile3 + 32 * G);            // [32]      (sweep 3)
 
   uint32_t *mw = P.mwbuf + (size_t)slot * P.mw_stride;   // [stride_w][TILE]
   double *ck = P.ckpt + (size_t)slot * P.ckpt_stride;    // [seg_loci/B][ROW]
@@ -280,12 +283,13 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
   const int rowoff = lig * NP * G + g;
   const int mwoff = lig * NQ * G + g;
   // dynamic addressing of state k of this lane's haplotype (slot index = k + (k/S) * padding of a lane)
+  auto lane_of = [&](int k) { return L == 1 ? 0 : (L == 2 ? (int)(k >= S) : k / S); };
   auto row_idx = [&](int k) {
-    const int kl = (SPR == S) ? k : k + (k / S) * (SPR - S);
+    const int kl = (SPR == S) ? k : k + lane_of(k) * (SPR - S);
     return ((kl >> 1) * G + g) * 2 + (kl & 1);
   };
   auto mw_idx = [&](int k) {
-    const int kl = (SPW == S) ? k : k + (k / S) * (SPW - S);
+    const int kl = (SPW == S) ? k : k + lane_of(k) * (SPW - S);
     return ((kl >> 2) * G + g) * 4 + (kl & 3);
   };
 
@@ -506,12 +510,14 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
           __syncwarp();
           uint32_t hw = __ldg(P.Hw + hoff + wi);
           const int n_last = (shi - 1) / B;
+          double csn[NCT];
           for (int n = slo / B; n <= n_last; n++) {
             const int nb = n * B;
             const int lo = max(nb, slo);
             const int top = min(nb + B, shi) - 1;
-            // per-locus constants of the block; loci above `top` get the identity step
-            double tb[B], tmu[B], tomm[B], ta[B], tcm[B], tse[B];
+            // per-locus constants of the block; loci above `top` get the identity step of the recurrence
+            // beta_{m-1}(k) = (b_m E_m(k)) beta_m(k) + a_m Se_m
+            double tb[B], tmu[B], tomm[B], ta[B], tse[B], tbo[B], tbm[B], tcm[B];
 #pragma unroll
             for (int mm = 0; mm < B; mm++) {
               const int m = nb + mm;
@@ -519,9 +525,11 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
                 const KgwLocusHMM h = P.hmm[m];
                 tb[mm] = h.b; tmu[mm] = h.mu; tomm[mm] = h.omm; ta[mm] = h.a;
                 tse[mm] = ld_cg(seb + (size_t)(m - seg0) * G + g);
+                tbo[mm] = h.b * h.omm; tbm[mm] = h.b * h.mu;
                 tcm[mm] = h.a * tse[mm];
               } else {
-                tb[mm] = 1.0; tmu[mm] = 1.0; tomm[mm] = 1.0; ta[mm] = 0.0; tcm[mm] = 0.0; tse[mm] = 0.0;
+                tb[mm] = 1.0; tmu[mm] = 1.0; tomm[mm] = 1.0; ta[mm] = 0.0; tse[mm] = 0.0;
+                tbo[mm] = 1.0; tbm[mm] = 1.0; tcm[mm] = 0.0;
               }
             }
             if ((lo >> 5) != wi) {
@@ -544,6 +552,16 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
             const double *row = rowbuf + (size_t)(n & 1) * ROW;
             const uint32_t *tile = mwt;
             const int bit0 = nb & 31;
+            // partial sums of a locus: the L lanes of the haplotype, four chunks each (fetched one locus ahead)
+            auto load_cs = [&](double (&dst)[NCT], int j) {
+              const double2 *d = reinterpret_cast<const double2 *>(csb + (size_t)(j - seg0) * 128);
+#pragma unroll
+              for (int lg = 0; lg < L; lg++) {
+                const double2 t0 = ld_cg(d + lg * G + g), t1 = ld_cg(d + 32 + lg * G + g);
+                dst[lg * NC + 0] = t0.x; dst[lg * NC + 1] = t0.y; dst[lg * NC + 2] = t1.x; dst[lg * NC + 3] = t1.y;
+              }
+            };
+            if (n == slo / B) load_cs(csn, lo);
 
 #pragma unroll
             for (int jj = 0; jj < B; jj++) {
@@ -555,23 +573,15 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
               const double mupj = __dsub_rn(1.0, ommj);              // knockoffs.cpp:1251-1256 quirk
               const double aomm = __dmul_rn(aj, ommj);
               const double amis = hbit ? __dmul_rn(aj, muj) : __dmul_rn(aj, mupj);
-              // partial sums of this locus: the L lanes of the haplotype, four chunks each
               double csv[NCT];
-              {
-                const double2 *d = reinterpret_cast<const double2 *>(csb + (size_t)(j - seg0) * 128);
 #pragma unroll
-                for (int lg = 0; lg < L; lg++) {
-                  const double2 t0 = ld_cg(d + lg * G + g), t1 = ld_cg(d + 32 + lg * G + g);
-                  csv[lg * NC + 0] = t0.x; csv[lg * NC + 1] = t0.y; csv[lg * NC + 2] = t1.x; csv[lg * NC + 3] = t1.y;
-                }
-              }
+              for (int c = 0; c < NCT; c++) csv[c] = csn[c];
+              if (j + 1 < shi) load_cs(csn, j + 1);
               // message of locus j at one state: staged top row, then the steps top -> j
               auto chain = [&](double v, uint32_t mword) {
 #pragma unroll
-                for (int mm = B - 1; mm > jj; mm--) {
-                  const double E = ((mword >> (bit0 + mm)) & 1u) ? tomm[mm] : tmu[mm];
-                  v = fma(tb[mm], v * E, tcm[mm]);
-                }
+                for (int mm = B - 1; mm > jj; mm--)
+                  v = ((mword >> (bit0 + mm)) & 1u) ? fma(v, tbo[mm], tcm[mm]) : fma(v, tbm[mm], tcm[mm]);
                 return v;
               };
               // the one state whose transition weight carries b_j: k == z_{j-1}
@@ -595,7 +605,7 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
                   count_le(CB, PT, tB);
                 }
               }
-              const int lgz = zprev / S;
+              const int lgz = lane_of(zprev);
               const int cz = lgz * NC + (zprev - lgz * S) / CS;
               const int csel = (CA > cz) ? CB : CA;
               const int cst = min(csel, NCT - 1);
@@ -700,10 +710,16 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
             }
           }
           prefetch_tile(wi);   // needed by the allele draws at the end of this word
+          {
+            // knockoff-table rows of this word's loci (8 x 16 bytes each)
+            const uint4 *src = reinterpret_cast<const uint4 *>(ko_tab + lo);
+            uint4 *dst = reinterpret_cast<uint4 *>(kot + (lo & 31));
+            const int n16 = (hi - lo) * (int)(sizeof(KgwLocusKO) / 16);
+            for (int i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
+          }
           __syncwarp();
-          KgwLocusKO k = ko_tab[lo];
           for (int j = lo; j < hi; j++) {
-            const KgwLocusKO kn = ko_tab[j + 1 < je ? j + 1 : j];
+            const KgwLocusKO &k = kot[j & 31];
             const int bit = j & 31;
             const int zj = ztile3[bit * G + g];
             const bool lastg = k.flags & KGW_KO_LASTGRP;
@@ -870,7 +886,6 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
             zkprev = zk;
             if (k.flags & KGW_KO_LASTINGRP) { z0 = zj; z0k = zk; }
             if (lig == 0) zktile3[bit * G + g] = (uint8_t)zk;
-            k = kn;
           }
           cp_async_wait_all();
           __syncwarp();
