@@ -10,6 +10,8 @@
 #include "kgw_family.cuh"
 
 #include <cmath>
+#include <chrono>
+#include <cstdlib>
 
 #include <algorithm>
 #include <mutex>
@@ -33,6 +35,41 @@ int fail(int code, const std::string &msg) {
     if (e_ != cudaSuccess)                                                                      \
       return fail(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
   } while (0)
+
+// KGW_TIMING=1: stage timings of the host-side entry points on stderr (development aid)
+struct StageTimer {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageTimer(cudaStream_t s) : on(getenv("KGW_TIMING") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[kgw] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
+// Packed rows travel over PCIe as ONE contiguous copy; these kernels convert between the caller's
+// row pitch and the 16-byte-aligned device pitch (a pitched cudaMemcpy2D issues one small DMA per row).
+__global__ void rows_to_pitched(const uint8_t *__restrict__ src, size_t src_pitch, uint8_t *__restrict__ dst,
+                                size_t dst_pitch, size_t row_len, size_t n_rows) {
+  const size_t total = n_rows * dst_pitch;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / dst_pitch, c = i - r * dst_pitch;
+    dst[i] = c < row_len ? src[r * src_pitch + c] : (uint8_t)0;
+  }
+}
+__global__ void rows_from_pitched(const uint8_t *__restrict__ src, size_t src_pitch, const int32_t *__restrict__ rows,
+                                  int64_t row0, uint8_t *__restrict__ dst, size_t row_len, size_t n_rows) {
+  const size_t total = n_rows * row_len;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / row_len, c = i - r * row_len;
+    const size_t sr = rows ? (size_t)rows[r] : (size_t)row0 + r;
+    dst[i] = src[sr * src_pitch + c];
+  }
+}
 
 // pick the compiled instantiation: smallest lane count whose states-per-lane fit 32 registers-pairs,
 // then the smallest S that holds K, then the requested checkpoint spacing
@@ -61,39 +98,73 @@ const KgwVariant *pick_variant(int K, int lanes, int B) {
   return best;
 }
 
-// Scratch slab cache: the checkpoint / partial-sum / latent-path scratch of a plan is tens of GB and
-// cudaMalloc + cudaFree of it costs more than the kernel; Knockoffs::generate() is called once per
-// resolution (main.cpp:159-181), so a destroyed plan parks its slab here for the next one on that device.
-struct SlabCache {
+// Device-buffer pool.  Knockoffs::generate() is called once per (chromosome, resolution)
+// (main.cpp:159-181) with identical shapes; cudaMalloc + cudaFree of a plan's buffers (the scratch slab
+// alone is tens of GB) costs as much as the kernel.  A destroyed plan parks its buffers here, keyed by
+// (device, size); the next plan of the same shape takes them back.  kgw_release_workspace() frees them.
+struct DevPool {
+  struct Item { int dev; size_t bytes; void *ptr; };
   std::mutex mu;
-  void *ptr[16] = {};
-  size_t bytes[16] = {};
+  std::vector<Item> items;
+  // a buffer of at least `need` bytes and at most 1.25 x that (exact shapes in practice), or nullptr
   void *take(int dev, size_t need, size_t *got) {
     std::lock_guard<std::mutex> lk(mu);
-    if (dev < 0 || dev >= 16 || !ptr[dev]) return nullptr;
-    void *p = ptr[dev];
-    *got = bytes[dev];
-    ptr[dev] = nullptr;
-    bytes[dev] = 0;
-    if (*got >= need) return p;
-    cudaFree(p);
-    return nullptr;
+    int best = -1;
+    for (int i = 0; i < (int)items.size(); i++)
+      if (items[i].dev == dev && items[i].bytes >= need && items[i].bytes <= need + need / 4 + 4096 &&
+          (best < 0 || items[i].bytes < items[best].bytes)) best = i;
+    if (best < 0) return nullptr;
+    void *p = items[best].ptr;
+    *got = items[best].bytes;
+    items.erase(items.begin() + best);
+    return p;
   }
   void give(int dev, void *p, size_t n) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(mu);
-    if (dev < 0 || dev >= 16 || (ptr[dev] && bytes[dev] >= n)) { cudaFree(p); return; }
-    if (ptr[dev]) cudaFree(ptr[dev]);
-    ptr[dev] = p;
-    bytes[dev] = n;
+    if (items.size() >= 64) {   // bounded: drop the oldest entry
+      cudaSetDevice(items[0].dev);
+      cudaFree(items[0].ptr);
+      items.erase(items.begin());
+      cudaSetDevice(dev);
+    }
+    items.push_back({dev, n, p});
   }
-  void clear() {
+  // free everything parked for `dev` (all devices if dev < 0); returns the number of bytes released
+  size_t clear(int dev = -1) {
     std::lock_guard<std::mutex> lk(mu);
-    for (int d = 0; d < 16; d++)
-      if (ptr[d]) { cudaSetDevice(d); cudaFree(ptr[d]); ptr[d] = nullptr; bytes[d] = 0; }
+    size_t freed = 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (size_t i = 0; i < items.size();) {
+      if (dev < 0 || items[i].dev == dev) {
+        cudaSetDevice(items[i].dev);
+        cudaFree(items[i].ptr);
+        freed += items[i].bytes;
+        items.erase(items.begin() + i);
+      } else {
+        i++;
+      }
+    }
+    cudaSetDevice(cur);
+    return freed;
   }
 };
-SlabCache g_slabs;
+DevPool g_pool;
+
+// cudaMalloc through the pool; on out-of-memory the parked buffers of the device are released first
+cudaError_t pool_alloc(int dev, void **out, size_t bytes, size_t *got) {
+  if (bytes == 0) bytes = 16;
+  *out = g_pool.take(dev, bytes, got);
+  if (*out) return cudaSuccess;
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation && g_pool.clear(dev) > 0) {
+    cudaGetLastError();
+    e = cudaMalloc(out, bytes);
+  }
+  *got = bytes;
+  return e;
+}
 
 struct Tables {
   std::vector<KgwLocusHMM> hmm;
@@ -411,7 +482,10 @@ struct kgw_plan {
   KgwPass *dpass = nullptr;
   double *dckpt = nullptr, *dinj = nullptr, *dse = nullptr, *dcs = nullptr, *dsegck = nullptr;
   uint32_t *dmw = nullptr;
-  void *slab = nullptr;      // one allocation behind dckpt / dse / dz / dzk
+  uint8_t *dstage = nullptr;       // contiguous staging of packed rows (H in, Hk out)
+  size_t stage_bytes = 0;
+  int32_t *dout_rows = nullptr;
+  unsigned char *slab = nullptr;      // one allocation behind the per-slot scratch arrays
   size_t slab_bytes = 0;
   uint8_t *dz = nullptr, *dzk = nullptr;
   int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
@@ -422,13 +496,28 @@ struct kgw_plan {
   FamilyState *fam = nullptr;      // related branch (null when the problem has no families)
   std::vector<int32_t> out_rows;   // rows of Hk written by this plan: unrelated + family members
 
+  std::vector<std::pair<void *, size_t>> owned;   // pooled device buffers of this plan
+  template <typename T>
+  cudaError_t alloc(T **out, size_t bytes) {
+    void *p = nullptr;
+    size_t got = 0;
+    cudaError_t e = pool_alloc(device, &p, bytes, &got);
+    if (e == cudaSuccess) owned.push_back({p, got});
+    *out = (T *)p;
+    return e;
+  }
+  template <typename T>
+  void release(T *&ptr) {   // back to the pool before the plan dies (buffers that are re-sized)
+    for (size_t i = 0; i < owned.size(); i++)
+      if (owned[i].first == (void *)ptr) { g_pool.give(device, owned[i].first, owned[i].second); owned.erase(owned.begin() + i); break; }
+    ptr = nullptr;
+  }
+
   ~kgw_plan() {
     cudaSetDevice(device);
-    cudaFree(dHw); cudaFree(dHk); cudaFree(dref); cudaFree(dhaps); cudaFree(dhmm); cudaFree(dko);
-    cudaFree(demit); cudaFree(dpass); cudaFree(dinj);
     if (stream) cudaStreamSynchronize(stream);
     delete fam;
-    g_slabs.give(device, slab, slab_bytes);
+    for (auto &o : owned) g_pool.give(device, o.first, o.second);
     cudaFree(ddbg_z); cudaFree(ddbg_zk); cudaFree(ddbg_beta);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -476,7 +565,9 @@ int fam_upload_partition(kgw_plan *pl, const int32_t *groups) {
   return KGW_OK;
 }
 
-int fam_create(kgw_plan *pl, const kgw_problem *prob, const cudaDeviceProp &dp) {
+struct DevInfo { int major = 0, minor = 0, multiProcessorCount = 0; };
+
+int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   const kgw_families *fi = prob->families;
   const int p = pl->p, K = pl->K, N = pl->N;
   if (!prob->ref_global) return fail(KGW_ERR_INVALID, "families need ref_global (references_global, knockoffs.h:141)");
@@ -617,17 +708,16 @@ int upload_partition(kgw_plan *pl, const int32_t *groups, bool hmm_too) {
                         pl->win_end.data(), T, hmm_too);
   if (rc != KGW_OK) return rc;
   if (hmm_too) {
-    KGW_CUDA(cudaMalloc(&pl->dhmm, sizeof(KgwLocusHMM) * pl->p));
-    KGW_CUDA(cudaMalloc(&pl->demit, sizeof(KgwEmit) * pl->p));
+    KGW_CUDA(pl->alloc(&pl->dhmm, sizeof(KgwLocusHMM) * pl->p));
+    KGW_CUDA(pl->alloc(&pl->demit, sizeof(KgwEmit) * pl->p));
     KGW_CUDA(cudaMemcpyAsync(pl->dhmm, T.hmm.data(), sizeof(KgwLocusHMM) * pl->p, cudaMemcpyHostToDevice, pl->stream));
     KGW_CUDA(cudaMemcpyAsync(pl->demit, T.emit.data(), sizeof(KgwEmit) * pl->p, cudaMemcpyHostToDevice, pl->stream));
-    KGW_CUDA(cudaMalloc(&pl->dpass, sizeof(KgwPass) * pl->W));
+    KGW_CUDA(pl->alloc(&pl->dpass, sizeof(KgwPass) * pl->W));
   }
   if (T.ko.size() > pl->ko_capacity) {
     KGW_CUDA(cudaStreamSynchronize(pl->stream));
-    cudaFree(pl->dko);
-    pl->dko = nullptr;
-    KGW_CUDA(cudaMalloc(&pl->dko, sizeof(KgwLocusKO) * T.ko.size()));
+    pl->release(pl->dko);
+    KGW_CUDA(pl->alloc(&pl->dko, sizeof(KgwLocusKO) * T.ko.size()));
     pl->ko_capacity = T.ko.size();
   }
   KGW_CUDA(cudaMemcpyAsync(pl->dko, T.ko.data(), sizeof(KgwLocusKO) * T.ko.size(), cudaMemcpyHostToDevice, pl->stream));
@@ -665,6 +755,7 @@ double kgw_uniform(uint64_t seed, uint32_t hap, uint32_t stream, uint32_t locus)
 
 int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_plan **plan_out) {
   if (!prob || !plan_out) return fail(KGW_ERR_INVALID, "null argument");
+  StageTimer tm(nullptr);
   *plan_out = nullptr;
   if (prob->abi_version != KGW_ABI_VERSION) return fail(KGW_ERR_INVALID, "abi_version mismatch");
   const int N = prob->N, p = prob->p, K = prob->K, W = prob->W;
@@ -699,8 +790,10 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
     return fail(KGW_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
   if (o.device < 0 || o.device >= ndev) return fail(KGW_ERR_INVALID, "bad device ordinal");
   KGW_CUDA(cudaSetDevice(o.device));
-  cudaDeviceProp dp;
-  KGW_CUDA(cudaGetDeviceProperties(&dp, o.device));
+  DevInfo dp;   // (cudaGetDeviceProperties costs tens of milliseconds per call; three attributes suffice)
+  KGW_CUDA(cudaDeviceGetAttribute(&dp.major, cudaDevAttrComputeCapabilityMajor, o.device));
+  KGW_CUDA(cudaDeviceGetAttribute(&dp.minor, cudaDevAttrComputeCapabilityMinor, o.device));
+  KGW_CUDA(cudaDeviceGetAttribute(&dp.multiProcessorCount, cudaDevAttrMultiProcessorCount, o.device));
   if (dp.major != 10) return fail(KGW_ERR_CUDA, "kernels are built for sm_100a only (found sm_" + std::to_string(dp.major) + std::to_string(dp.minor) + ")");
 
   kgw_plan *pl = new kgw_plan();
@@ -730,6 +823,8 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   }
   KGW_CUDA_PL(cudaEventCreate(&pl->ev0));
   KGW_CUDA_PL(cudaEventCreate(&pl->ev1));
+  tm.st = pl->stream;
+  tm.lap("validate + stream");
 
   // variant, occupancy-driven persistent grid (one scratch slot per resident warp); the chromosome is cut
   // into segments when the per-slot scratch of a whole pass would not fit in 60 % of the free memory
@@ -773,24 +868,30 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   pl->nseg = (int)((p32 + PS - 1) / PS);
   pl->scratch_bytes = slots * (fixed_slot + seg_slot(PS));
 
+  tm.lap("variant + occupancy");
   // inputs
   const size_t hw_bytes = (size_t)N * pl->stride_w * 4;
-  KGW_CUDA_PL(cudaMalloc(&pl->dHw, hw_bytes));
-  KGW_CUDA_PL(cudaMalloc(&pl->dHk, hw_bytes));
-  KGW_CUDA_PL(cudaMemsetAsync(pl->dHw, 0, hw_bytes, pl->stream));
+  KGW_CUDA_PL(pl->alloc(&pl->dHw, hw_bytes));
+  KGW_CUDA_PL(pl->alloc(&pl->dHk, hw_bytes));
   KGW_CUDA_PL(cudaMemsetAsync(pl->dHk, 0, hw_bytes, pl->stream));
-  KGW_CUDA_PL(cudaMemcpy2DAsync(pl->dHw, (size_t)pl->stride_w * 4, prob->H, (size_t)prob->row_bytes,
-                                (size_t)(p + 7) / 8, N, cudaMemcpyHostToDevice, pl->stream));
-  KGW_CUDA_PL(cudaMalloc(&pl->dref, sizeof(int32_t) * (size_t)N * W * K));
+  pl->stage_bytes = (size_t)N * (size_t)prob->row_bytes;
+  KGW_CUDA_PL(pl->alloc(&pl->dstage, pl->stage_bytes));
+  KGW_CUDA_PL(cudaMemcpyAsync(pl->dstage, prob->H, pl->stage_bytes, cudaMemcpyHostToDevice, pl->stream));
+  rows_to_pitched<<<dp.multiProcessorCount * 8, 256, 0, pl->stream>>>(pl->dstage, (size_t)prob->row_bytes, (uint8_t *)pl->dHw,
+                                                                    (size_t)pl->stride_w * 4, (size_t)(p + 7) / 8, (size_t)N);
+  KGW_CUDA_PL(cudaGetLastError());
+  tm.lap("H upload + re-pitch");
+  KGW_CUDA_PL(pl->alloc(&pl->dref, sizeof(int32_t) * (size_t)N * W * K));
   KGW_CUDA_PL(cudaMemcpyAsync(pl->dref, prob->ref_local, sizeof(int32_t) * (size_t)N * W * K, cudaMemcpyHostToDevice, pl->stream));
-  KGW_CUDA_PL(cudaMalloc(&pl->dhaps, sizeof(int32_t) * std::max(1, pl->n_haps)));
+  KGW_CUDA_PL(pl->alloc(&pl->dhaps, sizeof(int32_t) * std::max(1, pl->n_haps)));
   if (pl->n_haps)
     KGW_CUDA_PL(cudaMemcpyAsync(pl->dhaps, pl->haps.data(), sizeof(int32_t) * pl->n_haps, cudaMemcpyHostToDevice, pl->stream));
   if (prob->injected_u) {
     const size_t ub = sizeof(double) * (size_t)N * 3 * p;
-    KGW_CUDA_PL(cudaMalloc(&pl->dinj, ub));
+    KGW_CUDA_PL(pl->alloc(&pl->dinj, ub));
     KGW_CUDA_PL(cudaMemcpyAsync(pl->dinj, prob->injected_u, ub, cudaMemcpyHostToDevice, pl->stream));
   }
+  tm.lap("refs / haps upload");
   // scratch, one slot per resident warp
   const size_t mw_stride = up(sizeof(uint32_t) * (size_t)pl->stride_w * TILE) / sizeof(uint32_t);
   const size_t ckpt_stride = up(sizeof(double) * (PS / B) * ROW) / sizeof(double);
@@ -803,11 +904,8 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
     const size_t b_cs = cs_stride * sizeof(double) * slots, b_se = se_stride * sizeof(double) * slots;
     const size_t b_sg = segck_stride * sizeof(double) * slots, b_z = z_stride * slots;
     const size_t need = b_mw + b_ck + b_cs + b_se + b_sg + 2 * b_z;
-    pl->slab = g_slabs.take(pl->device, need, &pl->slab_bytes);
-    if (!pl->slab) {
-      KGW_CUDA_PL(cudaMalloc(&pl->slab, need));
-      pl->slab_bytes = need;
-    }
+    KGW_CUDA_PL(pl->alloc(&pl->slab, need));
+    pl->slab_bytes = need;
     unsigned char *base = (unsigned char *)pl->slab;
     pl->dmw = (uint32_t *)base; base += b_mw;
     pl->dckpt = (double *)base; base += b_ck;
@@ -820,6 +918,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   KGW_CUDA_PL(cudaMemsetAsync(pl->dz, 0, z_stride * slots, pl->stream));
   KGW_CUDA_PL(cudaMemsetAsync(pl->dzk, 0, z_stride * slots, pl->stream));
 
+  tm.lap("scratch slab");
   KgwParams &P = pl->P;
   P.N = N; P.p = p; P.K = K; P.W = W;
   P.n_haps = pl->n_haps;
@@ -861,6 +960,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   int rc = upload_partition(pl, prob->groups, true);
   if (rc != KGW_OK) return guard_fail(rc);
   KGW_CUDA_PL(cudaStreamSynchronize(pl->stream));
+  tm.lap("tables");
   *plan_out = pl;
   return KGW_OK;
 }
@@ -983,37 +1083,57 @@ int32_t kgw_plan_download(kgw_plan *pl, uint8_t *hk_out, kgw_debug *dbg) {
   if (rcs != KGW_OK) return rcs;
   const std::vector<int32_t> &rows = pl->out_rows;
   if (hk_out && !rows.empty()) {
-    // only the rows of the processed haplotypes are written back (generate() touches only those)
+    // only the rows of the processed haplotypes are written back (generate() touches only those):
+    // packed on the device into [n][row bytes], one contiguous D2H copy, scattered on the host if the
+    // rows are not consecutive
+    StageTimer tm(pl->stream);
     const size_t rb = (size_t)(pl->p + 7) / 8;
+    const size_t n = rows.size();
     bool contiguous = true;
-    for (size_t i = 1; i < rows.size(); i++)
+    for (size_t i = 1; i < n; i++)
       if (rows[i] != rows[i - 1] + 1) { contiguous = false; break; }
-    if (contiguous) {
-      const int h0 = rows[0];
-      KGW_CUDA(cudaMemcpy2D(hk_out + (size_t)h0 * pl->row_bytes, (size_t)pl->row_bytes,
-                            pl->dHk + (size_t)h0 * pl->stride_w, (size_t)pl->stride_w * 4, rb, rows.size(),
-                            cudaMemcpyDeviceToHost));
-    } else {
-      std::vector<uint8_t> tmp((size_t)pl->N * rb);
-      KGW_CUDA(cudaMemcpy2D(tmp.data(), rb, pl->dHk, (size_t)pl->stride_w * 4, rb, pl->N, cudaMemcpyDeviceToHost));
-      for (size_t i = 0; i < rows.size(); i++)
-        memcpy(hk_out + (size_t)rows[i] * pl->row_bytes, tmp.data() + (size_t)rows[i] * rb, rb);
+    if (n * rb > pl->stage_bytes) {
+      pl->release(pl->dstage);
+      KGW_CUDA(pl->alloc(&pl->dstage, n * rb));
+      pl->stage_bytes = n * rb;
     }
+    if (!contiguous && !pl->dout_rows) {
+      KGW_CUDA(pl->alloc(&pl->dout_rows, sizeof(int32_t) * n));
+      KGW_CUDA(cudaMemcpyAsync(pl->dout_rows, rows.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, pl->stream));
+    }
+    rows_from_pitched<<<148 * 8, 256, 0, pl->stream>>>((const uint8_t *)pl->dHk, (size_t)pl->stride_w * 4,
+                                                       contiguous ? nullptr : pl->dout_rows, rows[0], pl->dstage, rb, n);
+    KGW_CUDA(cudaGetLastError());
+    if (contiguous && (size_t)pl->row_bytes == rb) {
+      KGW_CUDA(cudaMemcpyAsync(hk_out + (size_t)rows[0] * pl->row_bytes, pl->dstage, n * rb, cudaMemcpyDeviceToHost, pl->stream));
+      KGW_CUDA(cudaStreamSynchronize(pl->stream));
+    } else {
+      std::vector<uint8_t> tmp(n * rb);
+      KGW_CUDA(cudaMemcpyAsync(tmp.data(), pl->dstage, n * rb, cudaMemcpyDeviceToHost, pl->stream));
+      KGW_CUDA(cudaStreamSynchronize(pl->stream));
+      for (size_t i = 0; i < n; i++) memcpy(hk_out + (size_t)rows[i] * pl->row_bytes, tmp.data() + i * rb, rb);
+    }
+    tm.lap("Hk pack + download");
   }
   return KGW_OK;
 }
 
 void kgw_plan_destroy(kgw_plan *pl) { delete pl; }
 
-void kgw_release_workspace(void) { g_slabs.clear(); }
+void kgw_release_workspace(void) { g_pool.clear(); }
 
 int32_t kgw_generate(const kgw_problem *prob, const kgw_options *opt, uint8_t *hk_out, kgw_debug *dbg) {
   kgw_plan *pl = nullptr;
   int rc = kgw_plan_create(prob, opt, &pl);
   if (rc != KGW_OK) return rc;
+  StageTimer tm(pl->stream);
   rc = kgw_plan_run(pl);
+  tm.lap("kernels");
   if (rc == KGW_OK) rc = kgw_plan_download(pl, hk_out, dbg);
+  tm.t0 = std::chrono::steady_clock::now();
   kgw_plan_destroy(pl);
+  tm.st = nullptr;
+  tm.lap("destroy");
   return rc;
 }
 
