@@ -294,7 +294,7 @@ def run_b200_arm(a, rank, local_rank, world):
         dt = float(te.item())
         if not np.array_equal(t_out.numpy(), hk_plan):
             raise SystemExit("bench.py: one-shot and resident-plan knockoffs differ")
-        tables = p * (32 + 128 + 128)  # KgwLocusHMM + KgwLocusKO + KgwEmit rows
+        tables = p * (16 + 128 + 128)  # KgwLocusHMM + KgwLocusKO + KgwEmit rows
         e2e = {"value": units * world * a.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(prob.H.nbytes + prob.ref.nbytes + tables + 4 * N),
                "d2h_bytes_per_step": int(N * ((p + 7) // 8)), "steps": a.e2e_steps,

@@ -183,12 +183,10 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
     T.emit.resize(p);
     for (int j = 0; j < p; j++) {
       KgwLocusHMM &h = T.hmm[j];
-      h.omm = 1.0 - mu[j];
-      h.mu = mu[j];
-      h.a = (1.0 - b[j]) * alpha;
       h.b = b[j];
-      // the draw's 1.0 - (1.0 - mu) (knockoffs.cpp:1251-1256) and the products a * theta (:1254) are
-      // single IEEE operations on these four numbers and are formed on the device
+      h.mu = mu[j];
+      // 1.0 - mu, the draw's 1.0 - (1.0 - mu) (knockoffs.cpp:1251-1256), (1.0 - b) * alpha and the products
+      // a * theta (:1254) are single IEEE operations on these numbers and are formed on the device
       // sample_emission_copula, lambda = 0.5 (knockoffs.cpp:1469-1502, call site :677)
       const double lambda = 0.5;
       for (int c = 0; c < 8; c++) {
@@ -465,7 +463,7 @@ struct kgw_plan {
   int seg_loci = 0, nseg = 1;
   const KgwVariant *var = nullptr;
   int G = 0, n_tasks = 0;
-  int grid = 0;
+  int grid = 0, threads = 32;
   size_t smem = 0;
   size_t scratch_bytes = 0;
   cudaStream_t stream = nullptr;
@@ -734,7 +732,7 @@ int upload_partition(kgw_plan *pl, const int32_t *groups, bool hmm_too) {
 
 int launch(kgw_plan *pl) {
   if (pl->n_haps > 0) {
-    pl->var->fn<<<pl->grid, pl->var->threads, pl->smem, pl->stream>>>(pl->P);
+    pl->var->fn<<<pl->grid, pl->threads, pl->smem, pl->stream>>>(pl->P);
     KGW_CUDA(cudaGetLastError());
   }
   return fam_launch(pl);
@@ -838,16 +836,26 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   const size_t ROW = (size_t)var->L * SPR * G, TILE = (size_t)var->L * SPW * G;
   size_t slots = 0;
   {
-    KGW_CUDA_PL(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var->smem));
-    int occ = 0;
-    KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, var->threads, var->smem));
+    // CTA shape: single-warp CTAs spread a partial wave most evenly over the SMs; CTAs of max_wpc warps
+    // fit more warps per SM (the 1 KB per-CTA shared-memory reservation is paid once) and are used when the
+    // single-warp grid cannot hold every haplotype batch at once
+    const int n_tasks = (pl->n_haps + G - 1) / G;
+    KGW_CUDA_PL(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(var->smem_warp * var->max_wpc)));
+    int wpc = 1, occ = 0;
+    KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, 32, var->smem_warp));
+    if (occ * dp.multiProcessorCount < n_tasks && var->max_wpc > 1) {
+      int occ2 = 0;
+      KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, var->fn, 32 * var->max_wpc, var->smem_warp * var->max_wpc));
+      if (occ2 * var->max_wpc > occ) { wpc = var->max_wpc; occ = occ2; }
+    }
     if (occ <= 0) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
     if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
-    const int n_tasks = (pl->n_haps + G - 1) / G;
-    const int grid = std::max(1, std::min(occ * dp.multiProcessorCount, n_tasks));
-    slots = (size_t)grid;
+    const int grid = std::max(1, std::min(occ * dp.multiProcessorCount, (n_tasks + wpc - 1) / wpc));
+    slots = (size_t)grid * wpc;
+    pl->threads = 32 * wpc;
+    pl->smem = var->smem_warp * wpc;
     pl->var = var; pl->B = B; pl->G = G; pl->n_tasks = n_tasks; pl->grid = grid;
-    pl->smem = var->smem; pl->nblk = (int)((p + B - 1) / B);
+    pl->nblk = (int)((p + B - 1) / B);
   }
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   // bytes per slot: fixed part (match words, latent paths) and the part proportional to the segment length
@@ -929,6 +937,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   P.haps = pl->dhaps;
   P.Hk = pl->dHk;
   P.seg_loci = pl->seg_loci;
+  P.alpha = 1.0 / K;   // knockoffs.cpp:75
   P.mwbuf = pl->dmw;
   P.mw_stride = mw_stride;
   P.ckpt = pl->dckpt;
@@ -1007,7 +1016,7 @@ int32_t kgw_plan_info(kgw_plan *pl, kgw_plan_info_t *out) {
   if (!pl || !out) return fail(KGW_ERR_INVALID, "null argument");
   out->launches_per_run = (pl->n_haps > 0 ? 1 : 0) + ((pl->fam && pl->fam->n_families > 0) ? 1 : 0);
   out->grid = pl->grid;
-  out->block = pl->var->threads;
+  out->block = pl->threads;
   out->lanes_per_hap = pl->var->L;
   out->states_per_lane = pl->var->S;
   out->block_loci = pl->B;

@@ -7,7 +7,7 @@
 //
 // Mapping.  A warp carries G = 32/L haplotypes; L lanes (1, 2, 4 or 8) cooperate on one haplotype and
 // lane `lig` owns the S consecutive HMM states k = lig*S .. lig*S+S-1 in registers (K <= L*S).
-// Lane index = lig*G + g.  Warps are independent (one-warp CTAs, no CTA barrier); each resident warp
+// Lane index = lig*G + g.  Warps are independent (no CTA barrier anywhere); each resident warp
 // owns one HBM scratch slot and walks a strided list of haplotype batches.  Per batch and window pass:
 //   gather   match words ~(H[i] ^ H[ref_k]) of every (state, 32-locus word) -> slot scratch, once; the
 //            sweeps stream them back tile by tile with 16-byte cp.async (double-buffered in shared memory);
@@ -33,11 +33,9 @@
 #include <stdint.h>
 #include "kgw_philox.h"
 
-struct __align__(16) KgwLocusHMM {  // per locus, built on the host in the reference's evaluation order
-  double omm;   // 1.0 - mu_j
-  double mu;    // mu_j
-  double a;     // (1.0 - b_j) * alpha,  alpha = 1.0/K (knockoffs.cpp:75)
-  double b;     // b_j
+struct __align__(16) KgwLocusHMM {  // per locus.  The derived constants of the reference, 1.0 - mu_j and
+  double b;     // b_j                   // (1.0 - b_j) * alpha with alpha = 1.0/K (knockoffs.cpp:75), are single
+  double mu;    // mu_j                  // IEEE operations and are formed on the device (hmm_consts)
 };
 
 enum { KGW_KO_FIRST = 1, KGW_KO_LASTGRP = 2, KGW_KO_GZERO = 4, KGW_KO_GSTART = 8, KGW_KO_LASTINGRP = 16 };
@@ -81,6 +79,7 @@ struct KgwParams {
   int32_t n_tasks;   // haplotype batches (G haplotypes each)
   int32_t seg_loci;  // loci per segment (multiple of 32); >= p means one segment
   int32_t pad0;
+  double alpha;      // 1.0 / K  (knockoffs.cpp:75), formed on the host
   const uint32_t *Hw;
   const int32_t *ref_local;  // [N][W][K]
   const int32_t *haps;       // [n_haps]
@@ -109,6 +108,10 @@ struct KgwParams {
   int32_t dbg_nblk;
   int32_t skip_sweeps;       // development only: bit s set = skip sweep s+1 (timing experiments; results invalid)
 };
+
+#ifndef KGW_WPC
+#define KGW_WPC 2   // maximum warps per CTA (two halve the per-CTA shared-memory reservation per warp)
+#endif
 
 namespace kgw {
 
@@ -155,6 +158,20 @@ __device__ __forceinline__ double group_excl(double v, int lane, double &total) 
   return lane < G ? 0.0 : prev;
 }
 
+// group total and exclusive prefix over lig in one exchange (the total is the same in every lane:
+// floating-point addition is commutative and every lane adds the same two partial results per step)
+template <int L>
+__device__ __forceinline__ double group_total_excl(double v, int lane, double &total) {
+  constexpr int G = 32 / L;
+  if (L == 1) { total = v; return 0.0; }
+  if (L == 2) {
+    const double o = __shfl_xor_sync(FULL, v, 16);
+    total = v + o;
+    return lane < G ? 0.0 : o;
+  }
+  return group_excl<L>(v, lane, total);
+}
+
 __device__ __forceinline__ double fast_rcp(double x) {
   // x in [1e-10, ~1e3]: hardware seed (upper 32 bits of x, >= 20 good bits) and one third-order step
   // y (1 + e + e^2), e = 1 - x y: relative error e^3 plus rounding
@@ -170,9 +187,25 @@ __device__ __forceinline__ void count_le(int &cnt, double v, double t) {
   asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "d"(v), "d"(t));
 }
 
+// acc += v when a == b / a < b: one ISETP and one predicated DADD
+__device__ __forceinline__ void add_if_eq(double &acc, int a, int b, double v) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p add.f64 %0, %0, %3;\n\t}" : "+d"(acc) : "r"(a), "r"(b), "d"(v));
+}
+__device__ __forceinline__ void add_if_lt(double &acc, int a, int b, double v) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, %2;\n\t@p add.f64 %0, %0, %3;\n\t}" : "+d"(acc) : "r"(a), "r"(b), "d"(v));
+}
+
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -210,14 +243,15 @@ struct Cfg {
   static constexpr int ROW = L * SPR * G;       // doubles per message row
   static constexpr int TILE = L * SPW * G;      // 32-bit words per match-word tile
   // per-warp shared memory: two message rows (sweep 2: staged top rows of two blocks; sweep 3: the
-  // reciprocal row and the two latent-path tiles), one match-word tile, the latent-path tile of sweep 2
+  // reciprocal row and the two latent-path tiles), one match-word tile, the staging buffers of sweep 2
   // (sweep 3 lays the reciprocal row, its two latent-path tiles and the 32 knockoff-table rows of the
   // current word over the same bytes)
-  static constexpr size_t s3_bytes = (size_t)ROW * 8 + 2 * 32 * G + 32 * sizeof(KgwLocusKO);
+  static constexpr size_t s3_bytes = (size_t)ROW * 8 + 4 * 32 * G + 32 * sizeof(KgwLocusKO);
   static constexpr size_t rows_bytes = (size_t)2 * ROW * 8 > s3_bytes ? (size_t)2 * ROW * 8 : s3_bytes;
   static constexpr size_t tiles_bytes = (size_t)TILE * 4;
-  static constexpr size_t ztile_bytes = (size_t)32 * G;
-  __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + tiles_bytes + ztile_bytes; }
+  // sweep-2 staging: partial sums of one locus (+ injected uniforms), totals and table rows of one block
+  static constexpr size_t stage_bytes = (size_t)128 * 8 + (size_t)G * 8 + (size_t)B * G * 8 + (size_t)B * 16;
+  __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + tiles_bytes + stage_bytes; }
 };
 
 // uniform of (hap, stream, locus j): Philox block cached per 4 loci
@@ -246,9 +280,19 @@ struct UniformSrc {
   }
 };
 
+struct HmmConsts { double b, mu, omm, a; };
+__device__ __forceinline__ HmmConsts hmm_consts(const KgwLocusHMM h, double alpha) {
+  HmmConsts c;
+  c.b = h.b;
+  c.mu = h.mu;
+  c.omm = __dsub_rn(1.0, h.mu);
+  c.a = __dmul_rn(__dsub_rn(1.0, h.b), alpha);
+  return c;
+}
+
 // PAD = false asserts K == L*S (no padded states: the per-state guards compile away)
 template <int L, int S, int B, bool PAD, int MINB>
-__global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant__ KgwParams P) {
+__global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __grid_constant__ KgwParams P) {
   using C = Cfg<L, S, B>;
   constexpr int G = C::G;
   constexpr int SPR = C::SPR, SPW = C::SPW, NQ = C::NQ, NP = C::NP, CS = C::CS, NC = C::NC, ROW = C::ROW, TILE = C::TILE;
@@ -260,16 +304,24 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
   const int k0 = lig * S;
   const int K = P.K;
   const int ns = PAD ? min(S, max(0, K - k0)) : S;  // states owned by this lane
-  const int slot = blockIdx.x;
-  const int nslots = gridDim.x;
+  // warps are independent (no CTA barrier anywhere); the host launches CTAs of 1 or KGW_WPC warps
+  const int wpc = blockDim.x >> 5;
+  const int slot = blockIdx.x * wpc + (threadIdx.x >> 5);
+  const int nslots = gridDim.x * wpc;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  unsigned char *smem_raw = smem_all + (size_t)(threadIdx.x >> 5) * C::warp_bytes();
   double *rowbuf = reinterpret_cast<double *>(smem_raw);                         // [2][ROW]
   uint32_t *mwt = reinterpret_cast<uint32_t *>(smem_raw + C::rows_bytes);        // [TILE]
-  uint8_t *ztile2 = smem_raw + C::rows_bytes + C::tiles_bytes;                   // [32][G]   (sweep 2)
-  uint8_t *ztile3 = reinterpret_cast<uint8_t *>(rowbuf + ROW);                   // [32][G]   (sweep 3, after row 0)
-  uint8_t *zktile3 = ztile3 + 32 * G;                                            // [32][G]
-  KgwLocusKO *kot = reinterpret_cast<KgwLocusKO *>(zktile3 + 32 * G);            // [32]      (sweep 3)
+  double *loc_cs = reinterpret_cast<double *>(smem_raw + C::rows_bytes + C::tiles_bytes);   // [2][32][2]   (sweep 2)
+  double *loc_u = loc_cs + 128;                                                   // [G]
+  double *blk_se = loc_u + G;                                                     // [B][G]
+  KgwLocusHMM *blk_h = reinterpret_cast<KgwLocusHMM *>(blk_se + B * G);           // [B]
+  uint8_t *ztile3 = reinterpret_cast<uint8_t *>(rowbuf + ROW);                   // [2][32][G] (sweep 3, after row 0)
+  uint8_t *zktile3 = ztile3 + 2 * 32 * G;                                        // [2][32][G]
+  KgwLocusKO *kot = reinterpret_cast<KgwLocusKO *>(zktile3 + 2 * 32 * G);        // [32]       (sweep 3)
+  uint32_t *z1slot = reinterpret_cast<uint32_t *>(loc_cs);                       // [32]       (sweep 3)
+  double *uslot = loc_cs + 16;                                                   // [32]       (sweep 3, test mode)
 
   uint32_t *mw = P.mwbuf + (size_t)slot * P.mw_stride;   // [stride_w][TILE]
   double *ck = P.ckpt + (size_t)slot * P.ckpt_stride;    // [seg_loci/B][ROW]
@@ -374,19 +426,25 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
         uint32_t mwr[S];
         int wi = hi_m >> 5;
         const int wl = lo_m >> 5;
+        // table rows of the 32 loci of word w -> hmt[w & 1] (the row buffers are idle during sweeps 0 and 1)
+        KgwLocusHMM *hmt = reinterpret_cast<KgwLocusHMM *>(rowbuf);   // [2][32]
+        auto stage_hmm = [&](int w) { cp_async16(hmt + (w & 1) * 32 + lane, P.hmm + min(max((w << 5) + lane, lo_m), hi_m)); };
+        __syncwarp();
         prefetch_tile(wi);
+        stage_hmm(wi);
         cp_async_wait_all();
+        __syncwarp();
         load_mw(mwr);
-        if (wi > wl) prefetch_tile(wi - 1);   // this lane's quads are in registers: the buffer is free
-        KgwLocusHMM h = P.hmm[hi_m];
+        if (wi > wl) { prefetch_tile(wi - 1); stage_hmm(wi - 1); }   // this lane's quads are in registers: the tile buffer is free
         for (int m = hi_m; m >= lo_m; m--) {
           if ((m >> 5) != wi) {
             wi = m >> 5;
             cp_async_wait_all();
+            __syncwarp();
             load_mw(mwr);
-            if (wi > wl) prefetch_tile(wi - 1);
+            if (wi > wl) { prefetch_tile(wi - 1); stage_hmm(wi - 1); }
           }
-          const KgwLocusHMM hn = P.hmm[m > lo_m ? m - 1 : lo_m];
+          const HmmConsts h = hmm_consts(hmt[(wi & 1) * 32 + (m & 31)], P.alpha);
           const uint32_t bm = 1u << (m & 31);
           // emission-weighted messages e = beta * E (knockoffs.cpp:1052-1060 without the constant factor a)
           double cs[NC];
@@ -426,7 +484,6 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
             if (fullstore) store_row(beta, ck + (size_t)((j - seg0) / B) * ROW);
             else if ((j % PS) == PS - 1) store_row(beta, sgk + (size_t)(j / PS) * ROW);
           }
-          h = hn;
         }
       };
 
@@ -492,6 +549,9 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
         }
 
         // ---------------------------------------------------------------- sweep 2: latent path z
+        // No register-destination global load sits in this loop: everything it reads from HBM arrives by
+        // cp.async (message rows a block ahead, block constants a block ahead, partial sums a locus ahead),
+        // so that no scoreboard wait of the draw's arithmetic is tied to a load in flight.
         if (!(P.skip_sweeps & 2)) {
           int wi = slo >> 5;
           // top row of block n (in segment-relative block index) -> row buffer (n & 1), this lane's pairs
@@ -501,20 +561,45 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
 #pragma unroll
             for (int q = 0; q < NP; q++) cp_async16(dst + q * G, src + q * G);
           };
+          // table rows and locus totals of the loci nb0 .. nb0+B-1 (clamped into the segment) -> blk_*
+          auto stage_block = [&](int nb0) {
+            if (lane < B) cp_async16(blk_h + lane, P.hmm + min(max(nb0 + lane, slo), shi - 1));
+            if (lig == 0) {
+#pragma unroll
+              for (int mm = 0; mm < B; mm++) {
+                const int m = min(max(nb0 + mm, slo), shi - 1);
+                cp_async8(blk_se + mm * G + g, seb + (size_t)(m - seg0) * G + g);
+              }
+            }
+          };
+          // partial sums (and the injected uniform, test mode) of locus j -> loc_*
+          auto stage_locus = [&](int j) {
+            const double2 *d = reinterpret_cast<const double2 *>(csb + (size_t)(j - seg0) * 128);
+            double2 *t = reinterpret_cast<double2 *>(loc_cs);
+            cp_async16(t + lane, d + lane);
+            cp_async16(t + 32 + lane, d + 32 + lane);
+            if (usz.inj != nullptr && lig == 0) cp_async8(loc_u + g, usz.inj + j);
+          };
+          __syncwarp();
           prefetch_tile(wi);
           prefetch_row(slo / B);
-          // loci of this word outside the pass keep the values of earlier window passes
-          for (int i = lane; i < 8 * G; i += 32)
-            reinterpret_cast<uint32_t *>(ztile2)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
-          cp_async_wait_all();
-          __syncwarp();
+          stage_block((slo / B) * B);
+          stage_locus(slo);
           uint32_t hw = __ldg(P.Hw + hoff + wi);
           const int n_last = (shi - 1) / B;
-          double csn[NCT];
           for (int n = slo / B; n <= n_last; n++) {
             const int nb = n * B;
             const int lo = max(nb, slo);
             const int top = min(nb + B, shi) - 1;
+            if ((lo >> 5) != wi) {
+              // next 32-locus word (the barrier keeps the old match-word tile intact until every lane is done)
+              wi = lo >> 5;
+              hw = __ldg(P.Hw + hoff + wi);
+              __syncwarp();
+              prefetch_tile(wi);
+            }
+            cp_async_wait_all();
+            __syncwarp();
             // per-locus constants of the block; loci above `top` get the identity step of the recurrence
             // beta_{m-1}(k) = (b_m E_m(k)) beta_m(k) + a_m Se_m
             double tb[B], tmu[B], tomm[B], ta[B], tse[B], tbo[B], tbm[B], tcm[B];
@@ -522,9 +607,9 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
             for (int mm = 0; mm < B; mm++) {
               const int m = nb + mm;
               if (m >= lo && m <= top) {
-                const KgwLocusHMM h = P.hmm[m];
+                const HmmConsts h = hmm_consts(blk_h[mm], P.alpha);
                 tb[mm] = h.b; tmu[mm] = h.mu; tomm[mm] = h.omm; ta[mm] = h.a;
-                tse[mm] = ld_cg(seb + (size_t)(m - seg0) * G + g);
+                tse[mm] = blk_se[mm * G + g];
                 tbo[mm] = h.b * h.omm; tbm[mm] = h.b * h.mu;
                 tcm[mm] = h.a * tse[mm];
               } else {
@@ -532,51 +617,39 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
                 tbo[mm] = 1.0; tbm[mm] = 1.0; tcm[mm] = 0.0;
               }
             }
-            if ((lo >> 5) != wi) {
-              // flush the finished z tile, then switch to the next 32-locus word
-              __syncwarp();
-              for (int i = lane; i < 8 * G; i += 32)
-                reinterpret_cast<uint32_t *>(zb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(ztile2)[i];
-              wi = lo >> 5;
-              for (int i = lane; i < 8 * G; i += 32)
-                reinterpret_cast<uint32_t *>(ztile2)[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)(wi << 5) * G)[i];
-              hw = __ldg(P.Hw + hoff + wi);
-              prefetch_tile(wi);   // every lane is past the barrier above: the old tile is no longer read
-              cp_async_wait_all();
-              __syncwarp();
-            } else {
-              cp_async_wait_all();
-              __syncwarp();
-            }
-            if (n < n_last) prefetch_row(n + 1);
             const double *row = rowbuf + (size_t)(n & 1) * ROW;
             const uint32_t *tile = mwt;
             const int bit0 = nb & 31;
-            // partial sums of a locus: the L lanes of the haplotype, four chunks each (fetched one locus ahead)
-            auto load_cs = [&](double (&dst)[NCT], int j) {
-              const double2 *d = reinterpret_cast<const double2 *>(csb + (size_t)(j - seg0) * 128);
-#pragma unroll
-              for (int lg = 0; lg < L; lg++) {
-                const double2 t0 = ld_cg(d + lg * G + g), t1 = ld_cg(d + 32 + lg * G + g);
-                dst[lg * NC + 0] = t0.x; dst[lg * NC + 1] = t0.y; dst[lg * NC + 2] = t1.x; dst[lg * NC + 3] = t1.y;
-              }
-            };
-            if (n == slo / B) load_cs(csn, lo);
 
 #pragma unroll
             for (int jj = 0; jj < B; jj++) {
               const int j = nb + jj;
               if (j < lo || j > top) continue;
+              if (j > lo) {
+                cp_async_wait_all();
+                __syncwarp();
+              }
+              // partial sums of this locus: the L lanes of the haplotype, four chunks each
+              double csv[NCT];
+#pragma unroll
+              for (int lg = 0; lg < L; lg++) {
+                const double2 t0 = reinterpret_cast<const double2 *>(loc_cs)[lg * G + g];
+                const double2 t1 = reinterpret_cast<const double2 *>(loc_cs)[32 + lg * G + g];
+                csv[lg * NC + 0] = t0.x; csv[lg * NC + 1] = t0.y; csv[lg * NC + 2] = t1.x; csv[lg * NC + 3] = t1.y;
+              }
+              const double u = (usz.inj != nullptr) ? loc_u[g] : usz.get(j);
+              __syncwarp();   // the staging buffers have been read by every lane
+              if (j + 1 < shi) stage_locus(j + 1);
+              if (j == lo && n < n_last) {
+                prefetch_row(n + 1);
+                stage_block(nb + B);
+              }
               const int bit = bit0 + jj;
               const bool hbit = (hw >> bit) & 1u;
               const double aj = ta[jj], bj = tb[jj], ommj = tomm[jj], muj = tmu[jj];
               const double mupj = __dsub_rn(1.0, ommj);              // knockoffs.cpp:1251-1256 quirk
               const double aomm = __dmul_rn(aj, ommj);
               const double amis = hbit ? __dmul_rn(aj, muj) : __dmul_rn(aj, mupj);
-              double csv[NCT];
-#pragma unroll
-              for (int c = 0; c < NCT; c++) csv[c] = csn[c];
-              if (j + 1 < shi) load_cs(csn, j + 1);
               // message of locus j at one state: staged top row, then the steps top -> j
               auto chain = [&](double v, uint32_t mword) {
 #pragma unroll
@@ -591,7 +664,7 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
                 const double bz = chain(row[row_idx(zprev)], mwz);
                 X = bj * (bz * (((mwz >> bit) & 1u) ? ommj : (hbit ? muj : mupj)));
               }
-              const double R = usz.get(j) * fma(aj, tse[jj], X);
+              const double R = u * fma(aj, tse[jj], X);
               const double tA = R, tB = R - X;
               // chunk level: #chunks whose end prefix is <= threshold
               int CA = 0, CB = 0;
@@ -611,7 +684,7 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
               const int cst = min(csel, NCT - 1);
               double Tb = 0.0;
 #pragma unroll
-              for (int c = 0; c < NCT - 1; c++) if (c < cst) Tb += csv[c];
+              for (int c = 0; c < NCT - 1; c++) add_if_lt(Tb, c, cst, csv[c]);
               const int lgs = cst / NC, ci = cst - lgs * NC;
               const int nss = PAD ? min(S, max(0, K - lgs * S)) : S;
               const int n_in = min(CS, nss - ci * CS);       // valid states of the chunk (may be <= 0)
@@ -652,12 +725,9 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
               }
               z = min(z, K - 1);
               zprev = z;
-              if (lig == 0) ztile2[bit * G + g] = (uint8_t)z;
+              if (lig == 0) zb[(size_t)j * G + g] = (uint8_t)z;
             }
           }
-          __syncwarp();
-          for (int i = lane; i < 8 * G; i += 32)
-            reinterpret_cast<uint32_t *>(zb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(ztile2)[i];
         }
         __syncwarp();
       }  // segments
@@ -676,58 +746,61 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
         int z0 = 0, z0k = 0, zkprev = 0;
         if (js > 0) { z0 = zb[(size_t)(js - 1) * G + g]; z0k = zkb[(size_t)(js - 1) * G + g]; }
         const KgwLocusKO *ko_tab = P.ko + ps.ko_off - js;
-        int z1 = 0, z1_pref = 0;
+        // As in sweep 2, everything the per-locus loop reads from global memory arrives by cp.async:
+        // the latent-path tiles of the next word, the knockoff-table rows of the word, the byte z1 of the
+        // next group (one group ahead) and, in test mode, the injected uniform of the next locus.
+        auto stage_ztiles = [&](int w) {
+          for (int i = lane; i < 2 * G; i += 32) {
+            cp_async16(ztile3 + (size_t)(w & 1) * 32 * G + 16 * i, zb + (size_t)(w << 5) * G + 16 * i);
+            cp_async16(zktile3 + (size_t)(w & 1) * 32 * G + 16 * i, zkb + (size_t)(w << 5) * G + 16 * i);
+          }
+        };
+        int z1 = 0, z1_byte = 0;
+        auto stage_z1 = [&](int locus) {   // the aligned 4 bytes holding z[locus] of this lane's haplotype
+          const size_t off = (size_t)locus * G + g;
+          z1_byte = (int)(off & 3);
+          cp_async4(z1slot + lane, zb + (off & ~(size_t)3));
+        };
+        __syncwarp();
         {
           const int zi = ko_tab[js].z1_idx;
-          if (zi >= 0) z1_pref = zb[(size_t)zi * G + g];
+          if (zi >= 0) stage_z1(zi);
         }
-        constexpr int TW = (8 * G + 31) / 32;  // 32-bit words of a latent-path tile per lane
-        uint32_t zreg[TW], zkreg[TW];
-#pragma unroll
-        for (int i = 0; i < TW; i++) {
-          const bool in = (G >= 4) || (lane + 32 * i < 8 * G);
-          zreg[i] = in ? reinterpret_cast<const uint32_t *>(zb + (size_t)(wlo << 5) * G)[lane + 32 * i] : 0u;
-          zkreg[i] = in ? reinterpret_cast<const uint32_t *>(zkb + (size_t)(wlo << 5) * G)[lane + 32 * i] : 0u;
-        }
+        if (us.inj != nullptr) cp_async8(uslot + lane, us.inj + js);
+        stage_ztiles(wlo);
         for (int wi = wlo; wi <= whi; wi++) {
           const int lo = max(wi << 5, js), hi = min((wi << 5) + 32, je);
-          __syncwarp();
-          // latent-path tiles of this word (loaded into registers one word ahead), then prefetch the next
-#pragma unroll
-          for (int i = 0; i < TW; i++) {
-            if ((G >= 4) || (lane + 32 * i < 8 * G)) {
-              reinterpret_cast<uint32_t *>(ztile3)[lane + 32 * i] = zreg[i];
-              reinterpret_cast<uint32_t *>(zktile3)[lane + 32 * i] = zkreg[i];
-            }
-          }
-          if (wi < whi) {
-#pragma unroll
-            for (int i = 0; i < TW; i++) {
-              if ((G >= 4) || (lane + 32 * i < 8 * G)) {
-                zreg[i] = reinterpret_cast<const uint32_t *>(zb + (size_t)((wi + 1) << 5) * G)[lane + 32 * i];
-                zkreg[i] = reinterpret_cast<const uint32_t *>(zkb + (size_t)((wi + 1) << 5) * G)[lane + 32 * i];
-              }
-            }
-          }
+          __syncwarp();   // the previous word is finished in every lane (tile reads of its allele draws)
           prefetch_tile(wi);   // needed by the allele draws at the end of this word
           {
             // knockoff-table rows of this word's loci (8 x 16 bytes each)
             const uint4 *src = reinterpret_cast<const uint4 *>(ko_tab + lo);
             uint4 *dst = reinterpret_cast<uint4 *>(kot + (lo & 31));
             const int n16 = (hi - lo) * (int)(sizeof(KgwLocusKO) / 16);
-            for (int i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
+            for (int i = lane; i < n16; i += 32) cp_async16(dst + i, src + i);
           }
+          cp_async_wait_all();
           __syncwarp();
+          if (wi < whi) stage_ztiles(wi + 1);
+          uint8_t *zt = ztile3 + (size_t)(wi & 1) * 32 * G, *zkt = zktile3 + (size_t)(wi & 1) * 32 * G;
           for (int j = lo; j < hi; j++) {
             const KgwLocusKO &k = kot[j & 31];
             const int bit = j & 31;
-            const int zj = ztile3[bit * G + g];
+            const int zj = zt[bit * G + g];
             const bool lastg = k.flags & KGW_KO_LASTGRP;
-            const double u = us.get(j);
+            double u;
+            if (us.inj != nullptr) {
+              cp_async_wait_all();
+              u = uslot[lane];
+              if (j + 1 < je) cp_async8(uslot + lane, us.inj + j + 1);
+            } else {
+              u = us.get(j);
+            }
             int zk;
             if (k.flags & KGW_KO_FIRST) {
-              z1 = z1_pref;
-              if (k.z1_next >= 0) z1_pref = zb[(size_t)k.z1_next * G + g];
+              cp_async_wait_all();   // z1 of this group was requested at the first locus of the previous one
+              z1 = (k.z1_idx >= 0) ? (int)reinterpret_cast<const uint8_t *>(z1slot + lane)[z1_byte] : 0;
+              if (k.z1_next >= 0) stage_z1(k.z1_next);
               const bool gz = k.flags & KGW_KO_GZERO;
               // pass A: reciprocals of N_old -> shared row, chunk sums
               double cs[NC];
@@ -743,34 +816,43 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
                 if (s1 < S) cs[((s1 < S) ? s1 : 0) / CS] += r1;
               }
               __syncwarp();
-              // the (at most two) states equal to z0 / z0k carry T_k(z0)*T_k(z0k) != tg  (:1350-1354)
+              // Special states, read by every lane of the haplotype.  k == z0 / z0k carry T_k(z0)*T_k(z0k) != tg
+              // (:1350-1354) in the N update and in the draw; k == z1 carries the extra vstar term in the draw
+              // only (:1413-1419), on top of the former if the states coincide.
+              double n0 = 0.0, n0k = 0.0, d0 = 0.0, d0k = 0.0, nz = 0.0, d1 = 0.0;
               if (!gz) {
                 const double r0 = rrow[row_idx(z0)];
-                double n0, n0k = 0.0, r0k = 0.0;
                 if (z0 == z0k) {
                   n0 = r0 * k.f2;
                 } else {
                   n0 = r0 * k.f1;
-                  r0k = rrow[row_idx(z0k)];
+                  const double r0k = rrow[row_idx(z0k)];
                   n0k = r0k * k.f1;
+                  d0k = n0k - r0k;
                 }
-                __syncwarp();
-                if (lig == 0) {
-                  rrow[row_idx(z0)] = n0;
-                  if (z0 != z0k) rrow[row_idx(z0k)] = n0k;
-                }
-                const int lg0 = z0 / S, c0 = (z0 - lg0 * S) / CS;
-                const int lg0k = z0k / S, c0k = (z0k - lg0k * S) / CS;
-                const double d0 = (lg0 == lig) ? n0 - r0 : 0.0;
-                const double d0k = (z0 != z0k && lg0k == lig) ? n0k - r0k : 0.0;
+                d0 = n0 - r0;
+              }
+              if (!lastg) {
+                const double rz = (!gz && z1 == z0) ? n0 : ((!gz && z1 == z0k) ? n0k : rrow[row_idx(z1)]);
+                nz = rz * k.fz1;
+                d1 = nz - rz;
+              }
+              __syncwarp();   // every lane has read the unpatched row
+              const int lg0 = lane_of(z0), lg0k = lane_of(z0k), lg1 = lane_of(z1);
+              if (!gz) {
+                // the owner lane patches its entries (it re-reads them in pass B) and its chunk sums
+                if (lg0 == lig) rrow[row_idx(z0)] = n0;
+                if (z0 != z0k && lg0k == lig) rrow[row_idx(z0k)] = n0k;
+                const int c0 = (lg0 == lig) ? (z0 - lg0 * S) / CS : -1;
+                const int c0k = (z0 != z0k && lg0k == lig) ? (z0k - lg0k * S) / CS : -1;
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                  if (c == c0) cs[c] += d0;
-                  if (c == c0k) cs[c] += d0k;
+                  add_if_eq(cs[c], c0, c, d0);
+                  add_if_eq(cs[c], c0k, c, d0k);
                 }
               }
-              __syncwarp();
-              const double Sr = group_sum<L>((cs[0] + cs[1]) + (cs[2] + cs[3]));
+              double Sr;
+              const double base0 = group_total_excl<L>((cs[0] + cs[1]) + (cs[2] + cs[3]), lane, Sr);
               const double Nsum = (k.flags & KGW_KO_GSTART) ? k.sa : k.tg * Sr;  // :1345-1358
               const double c2 = k.vb * Nsum;
               // pass B: partition function update, normalised (:1360-1390).  The last group keeps N (zero
@@ -803,22 +885,17 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
                 acc = group_sum<L>(acc);
                 if (cC_ < N_MIN) sumN = acc;
               }
-              // the state equal to z1 carries the extra vstar term in the draw (:1413-1419)
-              __syncwarp();
+              // the draw: weights r_k (patched), in units of vb*tg
               if (!lastg) {
-                const double rz = rrow[row_idx(z1)];
-                const double nz = rz * k.fz1;
-                __syncwarp();
-                if (lig == 0) rrow[row_idx(z1)] = nz;
-                const int lg1 = z1 / S, c1 = (z1 - lg1 * S) / CS;
-                const double d1 = (lg1 == lig) ? nz - rz : 0.0;
+                if (lg1 == lig) rrow[row_idx(z1)] = nz;   // after this lane's pass B reads
+                const int c1 = (lg1 == lig) ? (z1 - lg1 * S) / CS : -1;
 #pragma unroll
-                for (int c = 0; c < NC; c++) if (c == c1) cs[c] += d1;
+                for (int c = 0; c < NC; c++) add_if_eq(cs[c], c1, c, d1);
               }
               __syncwarp();
-              // two-level inverse-CDF search (weighted_choice, utils.cpp:690-698) in units of vb*tg
-              double St;
-              const double base = group_excl<L>((cs[0] + cs[1]) + (cs[2] + cs[3]), lane, St);
+              // two-level inverse-CDF search (weighted_choice, utils.cpp:690-698)
+              const double St = Sr + d1;
+              const double base = base0 + ((!lastg && lg1 < lig) ? d1 : 0.0);
               const double t = u * St;
               int cnt = 0;
               {
@@ -833,8 +910,8 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
               const int lgs = cst / NC, ci = cst - lgs * NC;
               double tb_own = base;
 #pragma unroll
-              for (int c = 0; c < NC - 1; c++) if (c < ci) tb_own += cs[c];
-              double run = __shfl_sync(FULL, tb_own, lgs * G + g);
+              for (int c = 0; c < NC - 1; c++) add_if_lt(tb_own, c, ci, cs[c]);
+              double run = (L == 1) ? tb_own : __shfl_sync(FULL, tb_own, lgs * G + g);
               const int nss = PAD ? min(S, max(0, K - lgs * S)) : S;
               const int n_in = min(CS, nss - ci * CS);
               const int klr = lgs * SPR + ci * CS;
@@ -855,6 +932,7 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
                 }
               }
               zk = min(lgs * S + ci * CS + c2n, K - 1);
+              __syncwarp();   // the row is rewritten at the next group
             } else {
               // inside a group every state has weight a*vb except k == zk_{j-1} and k == z1 (:1397-1419)
               const double wp = k.apb * ((!lastg && z1 == zkprev) ? (k.vb + k.vs) : k.vb);
@@ -885,13 +963,13 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
             }
             zkprev = zk;
             if (k.flags & KGW_KO_LASTINGRP) { z0 = zj; z0k = zk; }
-            if (lig == 0) zktile3[bit * G + g] = (uint8_t)zk;
+            if (lig == 0) zkt[bit * G + g] = (uint8_t)zk;
           }
           cp_async_wait_all();
           __syncwarp();
           // flush the zk tile, then knockoff alleles of the core loci of this word (:1469-1502)
           for (int i = lane; i < 8 * G; i += 32)
-            reinterpret_cast<uint32_t *>(zkb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(zktile3)[i];
+            reinterpret_cast<uint32_t *>(zkb + (size_t)(wi << 5) * G)[i] = reinterpret_cast<uint32_t *>(zkt)[i];
           const uint32_t hw = __ldg(P.Hw + hoff + wi);
           const uint32_t *tile = mwt;
           unsigned bits = 0u, mask = 0u;
@@ -900,8 +978,8 @@ __global__ void __launch_bounds__(32, MINB) sampler_kernel(const __grid_constant
           for (int j = elo + lig; j < ehi; j += L) {
             const int bit = j & 31;
             // reference bit = target bit where the match word says "equal", its complement elsewhere
-            const uint32_t w1 = ~(tile[mw_idx(ztile3[bit * G + g])] ^ hw);
-            const uint32_t w2 = ~(tile[mw_idx(zktile3[bit * G + g])] ^ hw);
+            const uint32_t w1 = ~(tile[mw_idx(zt[bit * G + g])] ^ hw);
+            const uint32_t w2 = ~(tile[mw_idx(zkt[bit * G + g])] ^ hw);
             const int combo = ((hw >> bit) & 1u) | (((w1 >> bit) & 1u) << 1) | (((w2 >> bit) & 1u) << 2);
             const double2 em = P.emit[j].ws[combo];
             const unsigned hk = (uh.get(j) * em.y < em.x) ? 0u : 1u;  // weighted_choice with 2 weights

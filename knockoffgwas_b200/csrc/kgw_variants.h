@@ -6,9 +6,9 @@ typedef void (*kgw_kernel_fn)(const KgwParams);
 struct KgwVariant {
   int L, S, B;              // lanes per haplotype, states per lane, checkpoint spacing
   bool pad;                 // false: compiled for K == L*S exactly (no padded states)
-  int threads;              // CTA size
+  int max_wpc;              // the kernel may be launched with CTAs of 1 .. max_wpc warps
   kgw_kernel_fn fn;
-  size_t smem;              // dynamic shared memory per CTA
+  size_t smem_warp;         // dynamic shared memory per warp
 };
 const KgwVariant *kgw_variants_L1(int *n);
 const KgwVariant *kgw_variants_L2(int *n);
