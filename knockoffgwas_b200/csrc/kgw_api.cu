@@ -514,6 +514,18 @@ struct kgw_plan {
   ~kgw_plan() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+#ifdef KGW_PHASES
+    if (P.phase_cycles) {
+      long long h[16];
+      cudaMemcpy(h, P.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost);
+      static const char *nm[12] = {"gather", "sweep1", "s2 wait+stage", "s2 X term", "s2 chunk level", "s2 refinement",
+                                   "s3 head+passA", "s3 specials", "s3 reduction", "s3 passB+z1", "s3 draw", "s3 word tail"};
+      long long tot = 0;
+      for (int i = 0; i < 12; i++) tot += h[i];
+      for (int i = 0; i < 12; i++) fprintf(stderr, "[kgw phases] %-16s %12lld cycles  %5.1f %%\n", nm[i], h[i], 100.0 * h[i] / (double)tot);
+      cudaFree(P.phase_cycles);
+    }
+#endif
     delete fam;
     for (auto &o : owned) g_pool.give(device, o.first, o.second);
     cudaFree(ddbg_z); cudaFree(ddbg_zk); cudaFree(ddbg_beta);
@@ -956,7 +968,12 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   P.dbg_z = P.dbg_zk = nullptr;
   P.dbg_beta = nullptr;
   P.dbg_nblk = 0;
-  P.skip_sweeps = o.reserved;  // development timing experiments only (0 in production)
+  P.skip_sweeps = o.reserved;
+  P.phase_cycles = nullptr;
+#ifdef KGW_PHASES
+  KGW_CUDA_PL(cudaMalloc(&P.phase_cycles, sizeof(long long) * 16));
+  KGW_CUDA_PL(cudaMemset(P.phase_cycles, 0, sizeof(long long) * 16));
+#endif  // development timing experiments only (0 in production)
 
   pl->out_rows = pl->haps;
   if (prob->families && prob->families->n_families > 0) {

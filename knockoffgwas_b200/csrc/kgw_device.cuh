@@ -107,7 +107,17 @@ struct KgwParams {
   double *dbg_beta;          // [n_haps][nblk][K] or null (last pass)
   int32_t dbg_nblk;
   int32_t skip_sweeps;       // development only: bit s set = skip sweep s+1 (timing experiments; results invalid)
+  long long *phase_cycles;   // development only (-DKGW_PHASES): [16] clock64 sums of slot 0, or null
 };
+
+// development only: per-phase cycle counters of the warp in slot 0
+#ifdef KGW_PHASES
+#define KGW_PH_DECL long long ph_t0 = clock64();
+#define KGW_PH(i) do { if (slot == 0 && P.phase_cycles) { const long long t_ = clock64(); if (lane == 0) P.phase_cycles[i] += t_ - ph_t0; ph_t0 = clock64(); } } while (0)
+#else
+#define KGW_PH_DECL
+#define KGW_PH(i) do { } while (0)
+#endif
 
 #ifndef KGW_WPC
 #define KGW_WPC 2   // maximum warps per CTA (two halve the per-CTA shared-memory reservation per warp)
@@ -186,6 +196,13 @@ __device__ __forceinline__ double fast_rcp(double x) {
 __device__ __forceinline__ void count_le(int &cnt, double v, double t) {
   asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "d"(v), "d"(t));
 }
+
+// cnt += (ok && v <= t)
+__device__ __forceinline__ void count_le_if(int &cnt, double v, double t, bool ok) {
+  asm("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %3, 0;\n\tsetp.le.and.f64 p, %1, %2, q;\n\t@p add.s32 %0, %0, 1;\n\t}"
+      : "+r"(cnt) : "d"(v), "d"(t), "r"((int)ok));
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // acc += v when a == b / a < b: one ISETP and one predicated DADD
 __device__ __forceinline__ void add_if_eq(double &acc, int a, int b, double v) {
@@ -354,6 +371,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
     const int hap = __ldg(P.haps + tt);
     const size_t hoff = (size_t)hap * P.stride_w;
 
+    KGW_PH_DECL
     for (int ip = 0; ip < P.n_passes; ip++) {
       const KgwPass ps = P.passes[ip];
       const int js = ps.js, je = ps.je;
@@ -393,6 +411,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
       }
       __syncwarp();
 
+      KGW_PH(0);   // gather
       // asynchronous copy of this lane's quads of match-word tile `w` into buffer `buf`
       auto prefetch_tile = [&](int w) {
         const uint4 *src = reinterpret_cast<const uint4 *>(mw + (size_t)w * TILE) + mwoff;
@@ -524,6 +543,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
           backward(beta, slo, shi - 1, seg0, true);
         }
         __syncwarp();
+        KGW_PH(1);   // sweep 1
 
         // debug: normalised backward messages at the block-top loci of the last pass
         if (P.dbg_beta != nullptr && ip == P.n_passes - 1) {
@@ -600,20 +620,18 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
             }
             cp_async_wait_all();
             __syncwarp();
-            // per-locus constants of the block; loci above `top` get the identity step of the recurrence
-            // beta_{m-1}(k) = (b_m E_m(k)) beta_m(k) + a_m Se_m
-            double tb[B], tmu[B], tomm[B], ta[B], tse[B], tbo[B], tbm[B], tcm[B];
+            // constants of the recurrence beta_{m-1}(k) = (b_m E_m(k)) beta_m(k) + a_m Se_m for the loci of the
+            // block (loci above `top` get the identity step); the staged table rows and totals stay in shared
+            // memory until the block's last locus
+            double tbo[B], tbm[B], tcm[B];
 #pragma unroll
-            for (int mm = 0; mm < B; mm++) {
+            for (int mm = 1; mm < B; mm++) {
               const int m = nb + mm;
               if (m >= lo && m <= top) {
                 const HmmConsts h = hmm_consts(blk_h[mm], P.alpha);
-                tb[mm] = h.b; tmu[mm] = h.mu; tomm[mm] = h.omm; ta[mm] = h.a;
-                tse[mm] = blk_se[mm * G + g];
                 tbo[mm] = h.b * h.omm; tbm[mm] = h.b * h.mu;
-                tcm[mm] = h.a * tse[mm];
+                tcm[mm] = h.a * blk_se[mm * G + g];
               } else {
-                tb[mm] = 1.0; tmu[mm] = 1.0; tomm[mm] = 1.0; ta[mm] = 0.0; tse[mm] = 0.0;
                 tbo[mm] = 1.0; tbm[mm] = 1.0; tcm[mm] = 0.0;
               }
             }
@@ -638,15 +656,20 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
                 csv[lg * NC + 0] = t0.x; csv[lg * NC + 1] = t0.y; csv[lg * NC + 2] = t1.x; csv[lg * NC + 3] = t1.y;
               }
               const double u = (usz.inj != nullptr) ? loc_u[g] : usz.get(j);
-              __syncwarp();   // the staging buffers have been read by every lane
+              const HmmConsts hj = hmm_consts(blk_h[jj], P.alpha);
+              const double sej = blk_se[jj * G + g];
+              __syncwarp();   // the staging buffers of the locus have been read by every lane
               if (j + 1 < shi) stage_locus(j + 1);
+              if (j + 6 < shi) prefetch_l2(csb + (size_t)(j + 6 - seg0) * 128 + lane * 4);   // HBM -> L2, six loci ahead
               if (j == lo && n < n_last) {
                 prefetch_row(n + 1);
-                stage_block(nb + B);
+                if (lig == 0 && lane < B) prefetch_l2(seb + (size_t)(min(nb + B + lane, shi - 1) - seg0) * G);
               }
+              if (j == top && n < n_last) stage_block(nb + B);   // every lane is past its reads of this block's rows
+              KGW_PH(2);   // sweep 2: waits + staging reads
               const int bit = bit0 + jj;
               const bool hbit = (hw >> bit) & 1u;
-              const double aj = ta[jj], bj = tb[jj], ommj = tomm[jj], muj = tmu[jj];
+              const double aj = hj.a, bj = hj.b, ommj = hj.omm, muj = hj.mu;
               const double mupj = __dsub_rn(1.0, ommj);              // knockoffs.cpp:1251-1256 quirk
               const double aomm = __dmul_rn(aj, ommj);
               const double amis = hbit ? __dmul_rn(aj, muj) : __dmul_rn(aj, mupj);
@@ -664,8 +687,9 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
                 const double bz = chain(row[row_idx(zprev)], mwz);
                 X = bj * (bz * (((mwz >> bit) & 1u) ? ommj : (hbit ? muj : mupj)));
               }
-              const double R = u * fma(aj, tse[jj], X);
+              const double R = u * fma(aj, sej, X);
               const double tA = R, tB = R - X;
+              KGW_PH(3);   // sweep 2: X term
               // chunk level: #chunks whose end prefix is <= threshold
               int CA = 0, CB = 0;
               {
@@ -689,29 +713,32 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               const int nss = PAD ? min(S, max(0, K - lgs * S)) : S;
               const int n_in = min(CS, nss - ci * CS);       // valid states of the chunk (may be <= 0)
               const int kb = lgs * S + ci * CS;
+              KGW_PH(4);   // sweep 2: chunk level
               const int klr = lgs * SPR + ci * CS, klw = lgs * SPW + ci * CS;
               double run = aj * Tb;
               int cA = 0, cB = 0;
               {
+                // every lane walks all CS slots of its chunk (invalid ones contribute zero weight and are not
+                // counted; their reads are redirected to the chunk's first units): no divergent branch
                 const double2 *r2 = reinterpret_cast<const double2 *>(row) + (klr >> 1) * G + g;
                 const uint4 *t4 = reinterpret_cast<const uint4 *>(tile) + (klw >> 2) * G + g;
 #pragma unroll
                 for (int qq = 0; qq < CS / 4; qq++) {
-                  if (4 * qq < n_in) {
-                    const uint4 mq = t4[qq * G];
-                    const double2 va = r2[(2 * qq) * G];
-                    const double2 vb = (4 * qq + 2 < n_in) ? r2[(2 * qq + 1) * G] : make_double2(0.0, 0.0);
-                    const double v4[4] = {va.x, va.y, vb.x, vb.y};
-                    const uint32_t m4[4] = {mq.x, mq.y, mq.z, mq.w};
+                  const int qa = (4 * qq < n_in) ? qq : 0;
+                  const int pb = (4 * qq + 2 < n_in) ? 2 * qq + 1 : 0;
+                  const uint4 mq = t4[qa * G];
+                  const double2 va = r2[(2 * qa) * G];
+                  const double2 vb = r2[pb * G];
+                  const double v4[4] = {va.x, va.y, vb.x, vb.y};
+                  const uint32_t m4[4] = {mq.x, mq.y, mq.z, mq.w};
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                      if (4 * qq + i < n_in) {
-                        const double bv = chain(v4[i], m4[i]);
-                        run += bv * (((m4[i] >> bit) & 1u) ? aomm : amis);
-                        count_le(cA, run, tA);
-                        count_le(cB, run, tB);
-                      }
-                    }
+                  for (int i = 0; i < 4; i++) {
+                    const bool ok = 4 * qq + i < n_in;
+                    const double bv = chain(v4[i], m4[i]);
+                    const double e = bv * (((m4[i] >> bit) & 1u) ? aomm : amis);
+                    run += ok ? e : 0.0;
+                    count_le_if(cA, run, tA, ok);
+                    count_le_if(cB, run, tB, ok);
                   }
                 }
               }
@@ -726,6 +753,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               z = min(z, K - 1);
               zprev = z;
               if (lig == 0) zb[(size_t)j * G + g] = (uint8_t)z;
+              KGW_PH(5);   // sweep 2: refinement
             }
           }
         }
@@ -816,41 +844,33 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
                 if (s1 < S) cs[((s1 < S) ? s1 : 0) / CS] += r1;
               }
               __syncwarp();
+              KGW_PH(6);   // sweep 3: loop head + pass A
               // Special states, read by every lane of the haplotype.  k == z0 / z0k carry T_k(z0)*T_k(z0k) != tg
               // (:1350-1354) in the N update and in the draw; k == z1 carries the extra vstar term in the draw
               // only (:1413-1419), on top of the former if the states coincide.
-              double n0 = 0.0, n0k = 0.0, d0 = 0.0, d0k = 0.0, nz = 0.0, d1 = 0.0;
-              if (!gz) {
-                const double r0 = rrow[row_idx(z0)];
-                if (z0 == z0k) {
-                  n0 = r0 * k.f2;
-                } else {
-                  n0 = r0 * k.f1;
-                  const double r0k = rrow[row_idx(z0k)];
-                  n0k = r0k * k.f1;
-                  d0k = n0k - r0k;
-                }
-                d0 = n0 - r0;
-              }
-              if (!lastg) {
-                const double rz = (!gz && z1 == z0) ? n0 : ((!gz && z1 == z0k) ? n0k : rrow[row_idx(z1)]);
-                nz = rz * k.fz1;
-                d1 = nz - rz;
-              }
+              const bool same = (z0 == z0k);
+              const double r0 = rrow[row_idx(z0)], r0k = rrow[row_idx(z0k)], rz1 = rrow[row_idx(z1)];
+              const double n0 = r0 * (same ? k.f2 : k.f1), n0k = r0k * k.f1;
+              const double d0 = gz ? 0.0 : n0 - r0;
+              const double d0k = (gz || same) ? 0.0 : n0k - r0k;
+              const double rz = (!gz && z1 == z0) ? n0 : ((!gz && z1 == z0k) ? n0k : rz1);
+              const double nz = rz * k.fz1;
+              const double d1 = lastg ? 0.0 : nz - rz;
               __syncwarp();   // every lane has read the unpatched row
               const int lg0 = lane_of(z0), lg0k = lane_of(z0k), lg1 = lane_of(z1);
-              if (!gz) {
+              {
                 // the owner lane patches its entries (it re-reads them in pass B) and its chunk sums
-                if (lg0 == lig) rrow[row_idx(z0)] = n0;
-                if (z0 != z0k && lg0k == lig) rrow[row_idx(z0k)] = n0k;
-                const int c0 = (lg0 == lig) ? (z0 - lg0 * S) / CS : -1;
-                const int c0k = (z0 != z0k && lg0k == lig) ? (z0k - lg0k * S) / CS : -1;
+                if (!gz && lg0 == lig) rrow[row_idx(z0)] = n0;
+                if (!gz && !same && lg0k == lig) rrow[row_idx(z0k)] = n0k;
+                const int c0 = (!gz && lg0 == lig) ? (z0 - lg0 * S) / CS : -1;
+                const int c0k = (!gz && !same && lg0k == lig) ? (z0k - lg0k * S) / CS : -1;
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                   add_if_eq(cs[c], c0, c, d0);
                   add_if_eq(cs[c], c0k, c, d0k);
                 }
               }
+              KGW_PH(7);   // sweep 3: specials
               double Sr;
               const double base0 = group_total_excl<L>((cs[0] + cs[1]) + (cs[2] + cs[3]), lane, Sr);
               const double Nsum = (k.flags & KGW_KO_GSTART) ? k.sa : k.tg * Sr;  // :1345-1358
@@ -863,6 +883,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               const double norm = fma(vsu, Sr, fma((double)K, c2u, sumN));
               const double rN = fast_rcp(norm);
               const double cA_ = vsu * rN, cC_ = c2u * rN;
+              KGW_PH(8);   // sweep 3: reduction + scalars
 #pragma unroll
               for (int q = 0; q < NP; q++) {
                 const int s0 = 2 * q, s1 = 2 * q + 1;
@@ -886,13 +907,14 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
                 if (cC_ < N_MIN) sumN = acc;
               }
               // the draw: weights r_k (patched), in units of vb*tg
-              if (!lastg) {
-                if (lg1 == lig) rrow[row_idx(z1)] = nz;   // after this lane's pass B reads
-                const int c1 = (lg1 == lig) ? (z1 - lg1 * S) / CS : -1;
+              {
+                if (!lastg && lg1 == lig) rrow[row_idx(z1)] = nz;   // after this lane's pass B reads
+                const int c1 = (!lastg && lg1 == lig) ? (z1 - lg1 * S) / CS : -1;
 #pragma unroll
                 for (int c = 0; c < NC; c++) add_if_eq(cs[c], c1, c, d1);
               }
               __syncwarp();
+              KGW_PH(9);   // sweep 3: pass B + clamp + z1 patch
               // two-level inverse-CDF search (weighted_choice, utils.cpp:690-698)
               const double St = Sr + d1;
               const double base = base0 + ((!lastg && lg1 < lig) ? d1 : 0.0);
@@ -920,19 +942,16 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
                 const double2 *r2 = rrow2 + (klr >> 1) * G + g;
 #pragma unroll
                 for (int q = 0; q < CS / 2; q++) {
-                  if (2 * q < n_in) {
-                    const double2 rr = r2[q * G];
-                    run += rr.x;
-                    count_le(c2n, run, t);
-                    if (2 * q + 1 < n_in) {
-                      run += rr.y;
-                      count_le(c2n, run, t);
-                    }
-                  }
+                  const double2 rr = r2[((2 * q < n_in) ? q : 0) * G];
+                  run += (2 * q < n_in) ? rr.x : 0.0;
+                  count_le_if(c2n, run, t, 2 * q < n_in);
+                  run += (2 * q + 1 < n_in) ? rr.y : 0.0;
+                  count_le_if(c2n, run, t, 2 * q + 1 < n_in);
                 }
               }
               zk = min(lgs * S + ci * CS + c2n, K - 1);
               __syncwarp();   // the row is rewritten at the next group
+              KGW_PH(10);  // sweep 3: draw
             } else {
               // inside a group every state has weight a*vb except k == zk_{j-1} and k == z1 (:1397-1419)
               const double wp = k.apb * ((!lastg && z1 == zkprev) ? (k.vb + k.vs) : k.vb);
@@ -974,20 +993,38 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
           const uint32_t *tile = mwt;
           unsigned bits = 0u, mask = 0u;
           const int elo = max(lo, ps.cs), ehi = min(hi, ps.ce);
-#pragma unroll 4
-          for (int j = elo + lig; j < ehi; j += L) {
-            const int bit = j & 31;
-            // reference bit = target bit where the match word says "equal", its complement elsewhere
-            const uint32_t w1 = ~(tile[mw_idx(zt[bit * G + g])] ^ hw);
-            const uint32_t w2 = ~(tile[mw_idx(zkt[bit * G + g])] ^ hw);
-            const int combo = ((hw >> bit) & 1u) | (((w1 >> bit) & 1u) << 1) | (((w2 >> bit) & 1u) << 2);
-            const double2 em = P.emit[j].ws[combo];
-            const unsigned hk = (uh.get(j) * em.y < em.x) ? 0u : 1u;  // weighted_choice with 2 weights
-            bits |= hk << bit;
-            mask |= 1u << bit;
+          // emission-table rows of the word's core loci -> over the knockoff-table rows (done for this word)
+          static_assert(sizeof(KgwEmit) == sizeof(KgwLocusKO), "the two per-locus tables share a shared-memory tile");
+          KgwEmit *emt = reinterpret_cast<KgwEmit *>(kot);   // [32], indexed by bit
+          if (ehi > elo) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.emit + elo);
+            uint4 *dst = reinterpret_cast<uint4 *>(emt + (elo & 31));
+            const int n16 = (ehi - elo) * (int)(sizeof(KgwEmit) / 16);
+            for (int i = lane; i < n16; i += 32) cp_async16(dst + i, src + i);
+          }
+          cp_async_wait_all();
+          __syncwarp();
+          // a lane draws the alleles of whole groups of four loci (one Philox block each)
+          for (int q4 = lig; q4 < 8; q4 += L) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int bit = 4 * q4 + i;
+              const int j = (wi << 5) + bit;
+              if (j >= elo && j < ehi) {
+                // reference bit = target bit where the match word says "equal", its complement elsewhere
+                const uint32_t w1 = ~(tile[mw_idx(zt[bit * G + g])] ^ hw);
+                const uint32_t w2 = ~(tile[mw_idx(zkt[bit * G + g])] ^ hw);
+                const int combo = ((hw >> bit) & 1u) | (((w1 >> bit) & 1u) << 1) | (((w2 >> bit) & 1u) << 2);
+                const double2 em = emt[bit].ws[combo];
+                const unsigned hk = (uh.get(j) * em.y < em.x) ? 0u : 1u;  // weighted_choice with 2 weights
+                bits |= hk << bit;
+                mask |= 1u << bit;
+              }
+            }
           }
           bits = group_or<L>(bits);
           mask = group_or<L>(mask);
+          KGW_PH(11);  // sweep 3: word tail (flush + alleles)
           if (lig == 0 && active && mask != 0u) {
             uint32_t *dst = P.Hk + hoff + wi;
             if (mask == 0xffffffffu) *dst = bits;
