@@ -331,6 +331,21 @@ def run_b200_arm(a, rank, local_rank, world):
             "kernel": {k: info[k] for k in ("grid", "block", "lanes_per_hap", "states_per_lane", "scratch_bytes", "block_loci", "segment_loci")},
             "wall_s_timed_region": t_wall}
 
+    # ---- next row of the scope table (outside the timed step, reported beside it): device-side .bed body of
+    # the resident H / Hk (kgw_plan_encode_bed replaces writeBED, plink_interface.cpp:67-103)
+    if rank == 0 and not a.no_e2e:
+        try:
+            body, _ = plan.encode_bed()                      # warm-up
+            t0 = time.perf_counter()
+            body, bed_ms = plan.encode_bed(out=body)
+            bed_wall = time.perf_counter() - t0
+            line["bed_writer"] = {"kernel_ms": bed_ms, "call_ms_with_d2h": bed_wall * 1e3, "output_bytes": int(body.nbytes),
+                                  "input_bytes": int(2 * N * ((p + 7) // 8)),
+                                  "kernel_GBps": (body.nbytes + 2 * N * ((p + 7) // 8)) / (bed_ms * 1e-3) / 1e9 if bed_ms > 0 else None,
+                                  "note": "2-bit SNP-major columns of H and Hk with the reference's swap pattern; not part of `value`"}
+        except Exception as e:
+            line["bed_writer"] = {"error": repr(e)[:200]}
+
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             line["cpu_baseline"], _, _ = cpu_baseline_dict(a, 3, 1, a.cpu_threads)

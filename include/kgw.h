@@ -163,6 +163,23 @@ typedef struct kgw_plan_info_t {
 int32_t kgw_plan_info(kgw_plan *plan, kgw_plan_info_t *out);
 void kgw_plan_destroy(kgw_plan *plan);
 
+/* ---- PLINK .bed body ---------------------------------------------------
+ * Replaces the data loops of writeBED / writeBED_variant (plink_interface.cpp:10-35, 67-103), called from
+ * Knockoffs::write (knockoffs.cpp:181-186) through plink::write_binary (:255-284) right after generate():
+ * SNP-major 2-bit genotype columns of kgw_bed_column_bytes(N) = ceil(N/2/4) bytes each, sample s =
+ * haplotypes 2s, 2s+1.  The caller writes the magic 6c 1b 01 and then this buffer.
+ *   include_genotypes != 0:  2p columns, SNP j -> (H, Hk), or (Hk, H) where swap[j] != 0; `swap` = the
+ *       coin flips of plink::write_binary (mt19937_64(2019), uniform_int_distribution<int>(0,1), :267-274),
+ *       drawn by the unchanged host code, which also writes the matching .bim / .fam;
+ *   include_genotypes == 0:  p columns of Hk (the "<out>_tilde" file), swap ignored.
+ * kgw_plan_encode_bed uses the matrices resident in the plan (H as uploaded, Hk as last generated);
+ * kernel_ms (may be NULL) receives the device time of the transpose.  kgw_bed_encode is the one-shot form
+ * from host matrices [N][row_bytes]; pass H == NULL for the Hk-only file. */
+int64_t kgw_bed_column_bytes(int32_t N);
+int32_t kgw_plan_encode_bed(kgw_plan *plan, const uint8_t *swap, int32_t include_genotypes, uint8_t *bed_out, float *kernel_ms);
+int32_t kgw_bed_encode(int32_t N, int32_t p, int64_t row_bytes, const uint8_t *H, const uint8_t *Hk, const uint8_t *swap,
+                       int32_t device, uint8_t *bed_out);
+
 /* A destroyed plan parks its scratch slab (tens of GB) for the next plan on the same device, because
  * Knockoffs::generate() runs once per resolution (main.cpp:159-181); this frees the parked slabs. */
 void kgw_release_workspace(void);

@@ -116,6 +116,12 @@ def load_library():
         L.kgw_release_workspace.restype = None
         L.kgw_plan_destroy.restype = None
         L.kgw_plan_destroy.argtypes = [C.c_void_p]
+        L.kgw_bed_column_bytes.restype = C.c_int64
+        L.kgw_bed_column_bytes.argtypes = [C.c_int32]
+        L.kgw_plan_encode_bed.restype = C.c_int32
+        L.kgw_plan_encode_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
+        L.kgw_bed_encode.restype = C.c_int32
+        L.kgw_bed_encode.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         if L.kgw_abi_version() != KGW_ABI_VERSION:
             raise KgwError(-1, "libkgw.so ABI version mismatch")
         _LIB = L
@@ -279,6 +285,59 @@ def generate_into(H, p, K, ref_local, b, mu, groups, *, out, win_start=None, win
     return out
 
 
+def swap_flags(num_snps: int, seed: int = 2019) -> np.ndarray:
+    """The column-order coin flips of plink::write_binary (plink_interface.cpp:267-274):
+    std::mt19937_64(2019) through std::uniform_int_distribution<int>(0, 1).  With a 64-bit engine libstdc++
+    (GCC >= 11, bits/uniform_int_dist.h) maps one draw x to the high half of the 128-bit product x * 2,
+    i.e. the top bit of x."""
+    n, w, m, r = 312, 64, 156, 31
+    a = 0xB5026F5AA96619E9
+    mask = (1 << 64) - 1
+    mt = [0] * n
+    mt[0] = seed & mask
+    for i in range(1, n):
+        mt[i] = (6364136223846793005 * (mt[i - 1] ^ (mt[i - 1] >> 62)) + i) & mask
+    idx = n
+    out = np.zeros(num_snps, dtype=np.uint8)
+    lower, upper = (1 << r) - 1, mask ^ ((1 << r) - 1)
+    for j in range(num_snps):
+        if idx >= n:
+            for i in range(n):
+                x = (mt[i] & upper) | (mt[(i + 1) % n] & lower)
+                xa = x >> 1
+                if x & 1:
+                    xa ^= a
+                mt[i] = mt[(i + m) % n] ^ xa
+            idx = 0
+        y = mt[idx]
+        idx += 1
+        y ^= (y >> 29) & 0x5555555555555555
+        y ^= (y << 17) & 0x71D67FFFEDA60000
+        y ^= (y << 37) & 0xFFF7EEE000000000
+        y ^= y >> 43
+        out[j] = (y & mask) >> 63
+    return out
+
+
+def bed_encode(H, Hk, p, swap=None, device=0):
+    """One-shot kgw_bed_encode from host matrices; H may be None for the Hk-only file."""
+    L = load_library()
+    Hk = np.ascontiguousarray(Hk, dtype=np.uint8)
+    N, row_bytes = Hk.shape
+    both = H is not None
+    if both:
+        H = np.ascontiguousarray(H, dtype=np.uint8)
+        assert H.shape == Hk.shape
+    nb = (N // 2 + 3) // 4
+    bed = np.empty((2 * p if both else p, nb), dtype=np.uint8)
+    sw = None
+    if both:
+        sw = np.ascontiguousarray(swap_flags(p) if swap is None else swap, dtype=np.uint8)
+    _check(L.kgw_bed_encode(N, int(p), row_bytes, H.ctypes.data if both else None, Hk.ctypes.data,
+                            None if sw is None else sw.ctypes.data, int(device), bed.ctypes.data))
+    return bed
+
+
 class Plan:
     """Resident-data plan: inputs stay in HBM across runs / partitions (kgw_plan_*)."""
 
@@ -314,6 +373,23 @@ class Plan:
         d, dbg = _make_debug(self._held, debug_paths, debug_beta)
         _check(self._L.kgw_plan_download(self._h, hk.ctypes.data, C.byref(d) if d is not None else None))
         return hk, _finish_debug(d, dbg, self._held)
+
+    def encode_bed(self, swap=None, include_genotypes=True, out=None):
+        """Body of `<out>_res<r>.bed` (writeBED, plink_interface.cpp:67-103) from the matrices resident in the
+        plan; returns (uint8 [columns][ceil(N/2/4)], device milliseconds of the transpose)."""
+        N, p = self._held.N, self._held.p
+        nb = (N // 2 + 3) // 4
+        ncols = 2 * p if include_genotypes else p
+        bed = np.empty((ncols, nb), dtype=np.uint8) if out is None else out
+        assert bed.shape == (ncols, nb) and bed.dtype == np.uint8 and bed.flags.c_contiguous
+        sw = None
+        if include_genotypes:
+            sw = np.ascontiguousarray(swap_flags(p) if swap is None else swap, dtype=np.uint8)
+            assert sw.shape == (p,)
+        ms = C.c_float()
+        _check(self._L.kgw_plan_encode_bed(self._h, None if sw is None else sw.ctypes.data, int(bool(include_genotypes)),
+                                           bed.ctypes.data, C.byref(ms)))
+        return bed, float(ms.value)
 
     def device_hk_ptr(self) -> int:
         return int(self._L.kgw_plan_device_hk(self._h) or 0)

@@ -752,6 +752,13 @@ int launch(kgw_plan *pl) {
 
 }  // namespace
 
+// shared with kgw_bed.cu
+int kgw_fail_(int code, const std::string &msg) { return fail(code, msg); }
+void *kgw_plan_device_h_(kgw_plan *pl, int *N, int *p, int *stride_w, int *device, void **stream) {
+  *N = pl->N; *p = pl->p; *stride_w = pl->stride_w; *device = pl->device; *stream = (void *)pl->stream;
+  return (void *)pl->dHw;
+}
+
 extern "C" {
 
 int32_t kgw_abi_version(void) { return KGW_ABI_VERSION; }

@@ -343,3 +343,34 @@ def unpack_bits(rows: np.ndarray, p: int) -> np.ndarray:
 
 def pack_bits(bits: np.ndarray) -> np.ndarray:
     return np.packbits(bits.astype(np.uint8), axis=1, bitorder="little")
+
+
+def bed_body(H, Hk, p: int, swap=None) -> np.ndarray:
+    """Bytes of `<out>.bed` after the magic, restating writeBED / writeBED_variant
+    (snpknock2/src/plink_interface.cpp:10-35, 67-103): per SNP j the columns (H, Hk), or (Hk, H) where
+    swap[j]; with H None the p columns of Hk (write_binary(basename, Hk), :240-246).  A column holds
+    ceil(N/2/4) bytes; sample s = haplotypes 2s, 2s+1 -> bits 2(s%4), 2(s%4)+1 of byte s/4:
+    both alleles set -> 11, exactly one -> 10 (the HIGH bit), none -> 00 (:20-28)."""
+    def columns(M):
+        bits = unpack_bits(np.asarray(M, dtype=np.uint8), p).astype(np.uint8)   # [N][p]
+        N = bits.shape[0]
+        assert N % 2 == 0
+        b0, b1 = bits[0::2], bits[1::2]                                         # [N/2][p]
+        code = (b0 & b1) | ((b0 | b1) << 1)                                     # 2-bit genotype codes
+        ns = N // 2
+        nb = (ns + 3) // 4
+        pad = np.zeros((4 * nb, p), dtype=np.uint8)
+        pad[:ns] = code
+        q = pad.reshape(nb, 4, p)
+        byte = q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)       # [nb][p]
+        return np.ascontiguousarray(byte.T)                                     # [p][nb]
+    ck = columns(Hk)
+    if H is None:
+        return ck
+    ch = columns(H)
+    sw = np.zeros(p, dtype=bool) if swap is None else np.asarray(swap).astype(bool)
+    out = np.empty((2 * p, ck.shape[1]), dtype=np.uint8)
+    out[0::2] = np.where(sw[:, None], ck, ch)
+    out[1::2] = np.where(sw[:, None], ch, ck)
+    return out
+

@@ -8,7 +8,7 @@ import numpy as np
 import kgw_oracle as ko
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-GOLDEN_NAMES = sorted(pth.stem for pth in GOLDEN.glob("*.npz"))
+GOLDEN_NAMES = sorted(pth.stem for pth in GOLDEN.glob("toy_*.npz"))
 
 
 def load_golden(name: str):
