@@ -68,7 +68,7 @@ def workload_config(a, world):
                     f"one partition resolution (mean group size {a.mean_group:g}), unrelated haplotypes",
         "haplotypes_per_gpu": a.haps, "snps": a.snps, "K": a.K, "mean_group_size": a.mean_group,
         "haplotypes_total": a.haps * world, "hmm_rho": RHO, "hmm_lambda": LAMBDA,
-        "sharding": "by haplotype, no data-path collective; NCCL all-gather of packed Hk rows in-step" if world > 1 else "single GPU",
+        "sharding": "by haplotype, no data-path collective; NCCL all-gather of the packed Hk rows of step i on a side stream, overlapped with the kernel of step i+1, the last one inside the timed region" if world > 1 else "single GPU",
         "l2": "256 MiB buffer rewritten between timed steps (L2 flush)",
     }
 
@@ -228,12 +228,27 @@ def run_b200_arm(a, rank, local_rank, world):
     hk_bytes = N * info["row_stride_bytes"]
     hk_dev = torch.as_tensor(_DevBuf(plan.device_hk_ptr(), hk_bytes), device=dev)
     gathered = torch.empty(world * hk_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
+    staged = torch.empty(hk_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gather_done = [None]
 
     def step():
+        # The gather of the packed knockoff rows (the only collective, NCCL over NVLink) runs on a side stream
+        # from a staged copy, overlapped with the next step's kernel; it is inside the timed region (the end
+        # event is recorded after the last gather).
         plan.run()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, hk_dev)
+            if gather_done[0] is not None:
+                stream.wait_event(gather_done[0])      # the previous gather has read `staged`
+            staged.copy_(hk_dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                dist.all_gather_into_tensor(gathered, staged)
+                gather_done[0] = torch.cuda.Event()
+                gather_done[0].record(comm)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -250,20 +265,34 @@ def run_b200_arm(a, rank, local_rank, world):
         sampler = ClockSampler(local_rank)
         sampler.start()
         t_wall0 = time.perf_counter()
+        ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_start.record(stream)
         for i in range(a.steps):
             flush.zero_()
             ev[i][0].record(stream)
             plan.run()
             ev[i][1].record(stream)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, hk_dev)
+                if gather_done[0] is not None:
+                    stream.wait_event(gather_done[0])
+                staged.copy_(hk_dev, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(stream)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ready)
+                    dist.all_gather_into_tensor(gathered, staged)
+                    gather_done[0] = torch.cuda.Event()
+                    gather_done[0].record(comm)
             ev[i][2].record(stream)
+        if world > 1:
+            stream.wait_event(gather_done[0])          # the last gather is part of the timed region
+        ev_end.record(stream)
         barrier()
         t_wall = time.perf_counter() - t_wall0
         clocks = sampler.stop()
     step_ms = [ev[i][0].elapsed_time(ev[i][2]) for i in range(a.steps)]
     kern_ms = [ev[i][0].elapsed_time(ev[i][1]) for i in range(a.steps)]
-    total_ms = float(sum(step_ms))
+    total_ms = float(ev_start.elapsed_time(ev_end))   # K steps incl. the L2 flushes and, at N > 1, every gather
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
