@@ -375,6 +375,24 @@ def run_b200_arm(a, rank, local_rank, world):
         except Exception as e:
             line["bed_writer"] = {"error": repr(e)[:200]}
 
+    # ---- the row before the path (outside the timed step): K nearest haplotypes inside kinship clusters of 5000
+    # consecutive haplotypes on the thinned chromosome (kgw_assign_references replaces findNeighbors,
+    # kinship_computer.cpp:174-233)
+    if rank == 0 and not a.no_e2e:
+        try:
+            csize = 5000
+            clusters = [np.arange(c0, min(c0 + csize, N), dtype=np.int32) for c0 in range(0, N, csize)]
+            kg.assign_references(prob.H, p, K, clusters)                  # warm-up
+            nn, ref_ms = kg.assign_references(prob.H, p, K, clusters)
+            pt = (p + 9) // 10
+            pair_words = float(sum(len(c) ** 2 for c in clusters)) * ((pt + 31) // 32)
+            line["reference_selection"] = {"device_ms": ref_ms, "pairs": float(sum(len(c) ** 2 for c in clusters)),
+                                           "thinned_snps": pt, "Gpair_words_per_s": pair_words / (ref_ms * 1e-3) / 1e9,
+                                           "note": "thin + all-pairs Hamming (xor/popc) + K-smallest with ties in cluster order; "
+                                                   "device time incl. kernel launches, excl. H2D of H; not part of `value`"}
+        except Exception as e:
+            line["reference_selection"] = {"error": repr(e)[:200]}
+
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             line["cpu_baseline"], _, _ = cpu_baseline_dict(a, 3, 1, a.cpu_threads)

@@ -180,6 +180,23 @@ int32_t kgw_plan_encode_bed(kgw_plan *plan, const uint8_t *swap, int32_t include
 int32_t kgw_bed_encode(int32_t N, int32_t p, int64_t row_bytes, const uint8_t *H, const uint8_t *Hk, const uint8_t *swap,
                        int32_t device, uint8_t *bed_out);
 
+/* ---- reference selection ------------------------------------------------
+ * Replaces the worker loop of KinshipComputer::assign_references (kinship_computer.cpp:856-881 ->
+ * findNeighbors :174-233) for one window (--windows 0, and the global references): for every haplotype the K
+ * members of its kinship cluster with the smallest Hamming distance on the thinned chromosome (every
+ * `compression`-th SNP, metadata.cpp:563-580; main.cpp:101 uses 10), IBD relatives pushed to distance 1e6,
+ * ties in cluster order.  ref_out[i][0..K) is in (distance, cluster position) order, -1 where the cluster
+ * has fewer than K+1 members; the unchanged host code then runs combine_references_families (:765-835) and
+ * its sanity checks (:887-928) on it.
+ *   clust_off [n_clusters+1], clust_members: the kinship clusters in the order of clusters[chr][c] (:693-711)
+ *   family_of [N] or NULL: a label shared by the haplotypes of metadata.related_families[i], negative for
+ *   haplotypes without relatives.
+ * (With --windows > 0 the reference applies full-resolution window bounds to the thinned rows and reads past
+ * their end, distance_hap_window :78-104; that mode has no defined result and is not offered.) */
+int32_t kgw_assign_references(int32_t N, int32_t p, int64_t row_bytes, const uint8_t *H, int32_t K, int32_t compression,
+                              int32_t n_clusters, const int32_t *clust_off, const int32_t *clust_members,
+                              const int32_t *family_of, int32_t device, int32_t *ref_out, float *kernel_ms);
+
 /* A destroyed plan parks its scratch slab (tens of GB) for the next plan on the same device, because
  * Knockoffs::generate() runs once per resolution (main.cpp:159-181); this frees the parked slabs. */
 void kgw_release_workspace(void);

@@ -120,6 +120,9 @@ def load_library():
         L.kgw_bed_column_bytes.argtypes = [C.c_int32]
         L.kgw_plan_encode_bed.restype = C.c_int32
         L.kgw_plan_encode_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
+        L.kgw_assign_references.restype = C.c_int32
+        L.kgw_assign_references.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
         L.kgw_bed_encode.restype = C.c_int32
         L.kgw_bed_encode.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         if L.kgw_abi_version() != KGW_ABI_VERSION:
@@ -336,6 +339,60 @@ def bed_encode(H, Hk, p, swap=None, device=0):
     _check(L.kgw_bed_encode(N, int(p), row_bytes, H.ctypes.data if both else None, Hk.ctypes.data,
                             None if sw is None else sw.ctypes.data, int(device), bed.ctypes.data))
     return bed
+
+
+def assign_references(H, p, K, clusters, family_of=None, compression=10, device=0):
+    """kgw_assign_references: K nearest haplotypes inside the kinship cluster (findNeighbors,
+    kinship_computer.cpp:174-233) for every haplotype; returns (int32 [N][K] in (distance, cluster position)
+    order, device milliseconds).  `clusters` = list of haplotype-id arrays in the reference's cluster order."""
+    L = load_library()
+    H = np.ascontiguousarray(H, dtype=np.uint8)
+    N, row_bytes = H.shape
+    off = np.concatenate([[0], np.cumsum([len(c) for c in clusters])]).astype(np.int32)
+    mem = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in clusters]), dtype=np.int32)
+    fam = None if family_of is None else np.ascontiguousarray(family_of, dtype=np.int32)
+    out = np.empty((N, int(K)), dtype=np.int32)
+    ms = C.c_float()
+    _check(L.kgw_assign_references(N, int(p), row_bytes, H.ctypes.data, int(K), int(compression), len(clusters),
+                                   off.ctypes.data, mem.ctypes.data, None if fam is None else fam.ctypes.data,
+                                   int(device), out.ctypes.data, C.byref(ms)))
+    return out, float(ms.value)
+
+
+def combine_references_families(ref, families):
+    """Host step after kgw_assign_references, KinshipComputer::combine_references_families
+    (kinship_computer.cpp:765-835): lists sorted ascending; the members of an IBD family share the intersection of
+    their lists, topped up round-robin with each member's next-closest reference until it holds K.
+    ref: int32 [N][K] in distance order; families[i] = metadata.related_families[i]."""
+    ref = np.asarray(ref, dtype=np.int32)
+    N, K = ref.shape
+    out = np.sort(ref, axis=1)
+    done = np.zeros(N, dtype=bool)
+    for i1 in range(N):
+        if done[i1]:
+            continue
+        fam = [int(x) for x in families[i1]]
+        done[i1] = True
+        done[fam] = True
+        if len(fam) <= 1:
+            continue
+        inter = set(int(x) for x in out[i1])
+        for i2 in fam:
+            if i2 != i1:
+                inter &= set(int(x) for x in out[i2])
+        inter = sorted(inter)
+        i = k = 0
+        while len(inter) < K:
+            cand = int(ref[fam[i], k])
+            if cand not in inter:
+                inter.append(cand)
+                inter.sort()
+            if i + 1 < len(fam):
+                i += 1
+            else:
+                i, k = 0, k + 1
+        out[fam] = inter
+    return out
 
 
 class Plan:

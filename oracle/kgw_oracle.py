@@ -374,3 +374,88 @@ def bed_body(H, Hk, p: int, swap=None) -> np.ndarray:
     out[1::2] = np.where(sw[:, None], ch, ck)
     return out
 
+
+def thin_haplotypes(H, p: int, compression: int = 10) -> tuple[np.ndarray, int]:
+    """The thinned copy of the chromosome that KinshipComputer measures distances on (Dataset(metadata,
+    num_threads, compression), kinship_computer.cpp:19; Metadata::thin keeps the SNPs with j % compression == 0,
+    metadata.cpp:563-580; main.cpp:101 fixes compression = 10): packed rows of ceil(p / compression) bits."""
+    bits = unpack_bits(np.asarray(H, dtype=np.uint8), p)[:, ::compression]
+    return pack_bits(bits), bits.shape[1]
+
+
+def find_neighbors(H, p: int, K: int, clusters, family_of, compression: int = 10) -> np.ndarray:
+    """KinshipComputer::findNeighbors for every haplotype with one window (kinship_computer.cpp:174-233): within
+    the haplotype's kinship cluster, the K members with the smallest Hamming distance on the thinned chromosome
+    (chaplotype::hamming over whole bytes, chaplotype.cpp:62-66), members of the same IBD family pushed to
+    distance 1e6 (:197-199), ties kept in cluster order (multimap insertion order and the strict
+    `dij < top_key` test, :207-218).  Returns int32 [N][K] in (distance, cluster position) order, -1 where a
+    cluster has fewer than K+1 members.  family_of[i] = label shared by the haplotypes of
+    metadata.related_families[i], negative for singletons.
+    (With --windows > 0 the reference applies the full-resolution window bounds to the thinned rows,
+    distance_hap_window :78-104, and reads past the end of the byte vectors; that mode has no defined result
+    and is not restated.)"""
+    Ht, pt = thin_haplotypes(H, p, compression)
+    N = Ht.shape[0]
+    bits = unpack_bits(Ht, pt).astype(np.int32)
+    family_of = np.asarray(family_of)
+    ref = np.full((N, K), -1, dtype=np.int32)
+    for members in clusters:
+        members = np.asarray(members, dtype=np.int64)
+        n = len(members)
+        fam = family_of[members]
+        related = (fam[:, None] == fam[None, :]) & (fam[:, None] >= 0)
+        X = bits[members]
+        D = (X @ (1 - X).T + (1 - X) @ X.T).astype(np.int64)
+        D[related] = 1000000
+        D[np.arange(n), np.arange(n)] = np.iinfo(np.int64).max     # `if(i==j) continue`
+        order = np.argsort(D, axis=1, kind="stable")[:, :min(K, n - 1)]
+        ref[members, :order.shape[1]] = members[order]
+    return ref
+
+
+def combine_references_families(ref_in: np.ndarray, families) -> np.ndarray:
+    """KinshipComputer::combine_references_families (kinship_computer.cpp:765-835): every list sorted ascending;
+    the members of an IBD family share the intersection of their lists, topped up round-robin with each
+    member's next-closest reference (in the ORIGINAL distance order) until it holds K.
+    families[i] = metadata.related_families[i] (list of haplotype ids, itself included)."""
+    if ref_in.ndim == 2:
+        return combine_references_families(ref_in[:, None, :], families)[:, 0, :]
+    N, W, K = ref_in.shape
+    ref = np.sort(ref_in, axis=2)
+    for w in range(W):
+        done = np.zeros(N, dtype=bool)
+        for i1 in range(N):
+            if done[i1]:
+                continue
+            fam = [int(x) for x in families[i1]]
+            done[i1] = True
+            for i2 in fam:
+                done[i2] = True
+            if len(fam) <= 1:
+                continue
+            inter = list(ref[i1, w])
+            for i2 in fam:
+                if i2 == i1:
+                    continue
+                s2 = set(int(x) for x in ref[i2, w])
+                inter = [x for x in inter if int(x) in s2]
+            inter = sorted(set(int(x) for x in inter))
+            i = k = 0
+            while len(inter) < K:
+                cand = int(ref_in[fam[i], w, k])
+                if cand not in inter:
+                    inter.append(cand)
+                    inter.sort()
+                if i + 1 < len(fam):
+                    i += 1
+                else:
+                    i, k = 0, k + 1
+            for i2 in fam:
+                ref[i2, w] = inter
+    return ref
+
+
+def family_labels(families) -> np.ndarray:
+    """haplotype -> label shared within metadata.related_families[i] (the smallest member), -1 for singletons."""
+    return np.array([min(int(x) for x in f) if len(f) > 1 else -1 for f in families], dtype=np.int32)
+
