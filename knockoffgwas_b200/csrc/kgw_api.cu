@@ -462,6 +462,7 @@ struct kgw_plan {
   int B = 4, nblk = 0;
   int seg_loci = 0, nseg = 1;
   const KgwVariant *var = nullptr;
+  kgw_kernel_fn fn = nullptr;      // the compiled form of the variant chosen for this problem
   int G = 0, n_tasks = 0;
   int grid = 0, threads = 32;
   size_t smem = 0;
@@ -744,7 +745,7 @@ int upload_partition(kgw_plan *pl, const int32_t *groups, bool hmm_too) {
 
 int launch(kgw_plan *pl) {
   if (pl->n_haps > 0) {
-    pl->var->fn<<<pl->grid, pl->threads, pl->smem, pl->stream>>>(pl->P);
+    pl->fn<<<pl->grid, pl->threads, pl->smem, pl->stream>>>(pl->P);
     KGW_CUDA(cudaGetLastError());
   }
   return fam_launch(pl);
@@ -855,19 +856,42 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   const size_t ROW = (size_t)var->L * SPR * G, TILE = (size_t)var->L * SPW * G;
   size_t slots = 0;
   {
-    // CTA shape: single-warp CTAs spread a partial wave most evenly over the SMs; CTAs of max_wpc warps
-    // fit more warps per SM (the 1 KB per-CTA shared-memory reservation is paid once) and are used when the
-    // single-warp grid cannot hold every haplotype batch at once
+    // Two compiled forms of the kernel: `fn` for the densest residency (12 or 16 warps per SM, 168 / 128
+    // registers) and `fn_wide` for 8 warps per SM with 255 registers, whose warps finish a batch in about 0.65
+    // of the time (measured, K = 50).  Pick the form with the lower modelled time: waves x time per batch.
+    // CTA shape: single-warp CTAs spread a partial wave most evenly over the SMs; CTAs of max_wpc warps fit more
+    // warps per SM (the 1 KB per-CTA shared-memory reservation is paid once) and are used when the single-warp
+    // grid cannot hold every haplotype batch at once.
     const int n_tasks = (pl->n_haps + G - 1) / G;
-    KGW_CUDA_PL(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(var->smem_warp * var->max_wpc)));
-    int wpc = 1, occ = 0;
-    KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, 32, var->smem_warp));
-    if (occ * dp.multiProcessorCount < n_tasks && var->max_wpc > 1) {
-      int occ2 = 0;
-      KGW_CUDA_PL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, var->fn, 32 * var->max_wpc, var->smem_warp * var->max_wpc));
-      if (occ2 * var->max_wpc > occ) { wpc = var->max_wpc; occ = occ2; }
-    }
+    auto shape = [&](kgw_kernel_fn fn, int *wpc_out, int *occ_out) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(var->smem_warp * var->max_wpc));
+      if (e != cudaSuccess) return e;
+      int wpc = 1, occ = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, var->smem_warp);
+      if (e != cudaSuccess) return e;
+      if (occ * dp.multiProcessorCount < n_tasks && var->max_wpc > 1) {
+        int occ2 = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, 32 * var->max_wpc, var->smem_warp * var->max_wpc);
+        if (e != cudaSuccess) return e;
+        if (occ2 * var->max_wpc > occ) { wpc = var->max_wpc; occ = occ2; }
+      }
+      *wpc_out = wpc; *occ_out = occ;
+      return cudaSuccess;
+    };
+    int wpc = 1, occ = 0, wpc_w = 1, occ_w = 0;
+    KGW_CUDA_PL(shape(var->fn, &wpc, &occ));
     if (occ <= 0) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
+    pl->fn = var->fn;
+    if (var->fn_wide != var->fn) {
+      KGW_CUDA_PL(shape(var->fn_wide, &wpc_w, &occ_w));
+      const char *force = getenv("KGW_FORCE_WIDE");   // development: "0" / "1"
+      if (occ_w > 0) {
+        const double slots_d = (double)occ * wpc * dp.multiProcessorCount, slots_w = (double)occ_w * wpc_w * dp.multiProcessorCount;
+        const double cost_d = std::ceil(n_tasks / slots_d) * 1.0, cost_w = std::ceil(n_tasks / slots_w) * 0.65;
+        const bool wide = force ? (force[0] == '1') : (cost_w < cost_d);
+        if (wide) { pl->fn = var->fn_wide; wpc = wpc_w; occ = occ_w; }
+      }
+    }
     if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
     const int grid = std::max(1, std::min(occ * dp.multiProcessorCount, (n_tasks + wpc - 1) / wpc));
     slots = (size_t)grid * wpc;
