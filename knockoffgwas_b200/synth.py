@@ -91,3 +91,57 @@ def make_problem(n_haps: int, p: int, K: int, seed: int = 2020, mean_group: floa
         H[c0:c0 + m] = np.packbits(bits, axis=1, bitorder="little")
     ref = make_references(n_haps, K, hrng, block=min(block, n_haps))
     return SynthProblem(H=H, p=p, K=K, ref=ref, b=b, mu=mu, groups=groups, cm=cm, bp=bp, seed=seed)
+
+
+def add_ibd_pairs(prob: SynthProblem, n_pairs: int, seed: int = 5, mean_len_cm: float = 20.0,
+                  min_len_bp: int = 100_000, max_segments: int = 3) -> SynthProblem:
+    """Synthetic RaPID-style IBD: `n_pairs` disjoint pairs of haplotypes from
+    different samples, 1..max_segments segments per pair, length ~ Exp(mean_len_cm) and at least
+    `min_len_bp`; the alleles of the first member are copied onto the second on every segment so that
+    H is truly identical there, and neither member keeps the other as a reference.  Segments of a
+    pair are disjoint and do not touch, so IbdCluster::tidy (ibd.cpp:99-189) leaves them as they are;
+    they are listed in the std::set<IbdSeg> order (ibd.cpp:482-: same index set -> ascending j_min).
+    Fills prob.families = [(members, [(j_min, j_max, ids), ...]), ...] as knockoffgwas_b200.api takes them."""
+    rng = np.random.default_rng([prob.seed, seed])
+    N, p = prob.N, prob.p
+    if 2 * n_pairs > N // 2:
+        raise ValueError("too many pairs for this population")
+    samples = rng.choice(N // 2, size=2 * n_pairs, replace=False)
+    bits = None
+    fams = []
+    for q in range(n_pairs):
+        i1 = int(2 * samples[2 * q] + rng.integers(2))
+        i2 = int(2 * samples[2 * q + 1] + rng.integers(2))
+        a, c = (i1, i2) if i1 < i2 else (i2, i1)
+        nseg = int(rng.integers(1, max_segments + 1))
+        segs, tries = [], 0
+        while len(segs) < nseg and tries < 50:
+            tries += 1
+            j0 = int(rng.integers(1, p - 2))
+            end_cm = prob.cm[j0] + rng.exponential(mean_len_cm)
+            j1 = int(min(p - 2, np.searchsorted(prob.cm, end_cm)))
+            while j1 < p - 2 and prob.bp[j1] - prob.bp[j0] < min_len_bp:
+                j1 += 1
+            if prob.bp[j1] - prob.bp[j0] < min_len_bp:
+                continue
+            if any(not (j1 + 2 < s0 or j0 > s1 + 2) for s0, s1 in segs):
+                continue
+            segs.append((j0, j1))
+        segs.sort()
+        ids = np.array([a, c], dtype=np.int32)
+        for j0, j1 in segs:
+            ra = np.unpackbits(prob.H[a], bitorder="little")
+            rc = np.unpackbits(prob.H[c], bitorder="little")
+            rc[j0:j1 + 1] = ra[j0:j1 + 1]
+            prob.H[c] = np.packbits(rc, bitorder="little")
+        for me, other in ((a, c), (c, a)):          # relatives are never references (kinship_computer.cpp:196-203)
+            hit = np.flatnonzero(prob.ref[me] == other)
+            if len(hit):
+                cand = other
+                while cand == other or cand == me or cand in prob.ref[me]:
+                    cand = int(rng.integers(max(0, me - 2000), min(N, me + 2000)))
+                prob.ref[me, hit[0]] = cand
+                prob.ref[me].sort()
+        fams.append((ids, [(j0, j1, ids) for j0, j1 in segs]))
+    prob.families = fams
+    return prob
