@@ -316,6 +316,8 @@ struct FamilyState {
   // device
   KgwFamDesc *dfams = nullptr;
   int32_t *dmembers = nullptr, *divstart = nullptr, *dgroups = nullptr, *dgfirst = nullptr, *dglast = nullptr, *dstatus = nullptr;
+  int32_t *dwork = nullptr;
+  KgwFamRange *dranges = nullptr;
   int32_t *dref_global = nullptr;
   KgwFamInterval *divs = nullptr;
   KgwFamOp *dops = nullptr;
@@ -330,6 +332,7 @@ struct FamilyState {
     cudaFree(dfams); cudaFree(dmembers); cudaFree(divstart); cudaFree(dgroups); cudaFree(dgfirst); cudaFree(dglast);
     cudaFree(dstatus); cudaFree(dref_global); cudaFree(divs); cudaFree(dops); cudaFree(dloc); cudaFree(dko);
     cudaFree(demtab); cudaFree(dmsg); cudaFree(dpat); cudaFree(dbytes); cudaFree(ddbg_z); cudaFree(ddbg_zk);
+    cudaFree(dwork); cudaFree(dranges);
   }
 };
 
@@ -613,6 +616,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   }
   std::vector<KgwFamInterval> ivs;
   std::vector<int32_t> iv_start;
+  std::vector<KgwFamRange> ranges;
   F->fams.resize(F->n_families);
   for (int f = 0; f < F->n_families; f++) {
     const int n = F->h_fam_off[f + 1] - F->h_fam_off[f];
@@ -624,11 +628,22 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     KgwFamDesc &d = F->fams[f];
     memset(&d, 0, sizeof(d));
     d.n = n; d.mem_off = F->h_fam_off[f]; d.out_off = F->h_fam_off[f];
+    std::vector<int> bnd;   // loci b > 0 where some member's neighbour list changes between b-1 and b
     for (int i = 0; i < n; i++) {
       iv_start.push_back((int32_t)ivs.size());
       ivs.insert(ivs.end(), per[i].begin(), per[i].end());
+      for (const KgwFamInterval &iv : per[i]) if (iv.j0 > 0) bnd.push_back(iv.j0);
     }
     iv_start.push_back((int32_t)ivs.size());  // sentinel: iv_start index = mem_off + f + i
+    // special loci [b-2, b+1] (kgw_family.cuh): junction nodes, pinned nodes and their consumers
+    std::sort(bnd.begin(), bnd.end());
+    d.rng_off = (int32_t)ranges.size();
+    for (int b : bnd) {
+      const int s0 = std::max(0, b - 2), s1 = std::min(p - 1, b + 1);
+      if ((int)ranges.size() > d.rng_off && s0 <= ranges.back().s1 + 1) ranges.back().s1 = std::max(ranges.back().s1, s1);
+      else ranges.push_back(KgwFamRange{s0, s1});
+    }
+    d.n_rng = (int32_t)ranges.size() - d.rng_off;
   }
   // node emission table (family_bp.cpp:437-454) when mu is the same at every locus (init_hmm, knockoffs.cpp:1520)
   bool uniform = true;
@@ -660,6 +675,9 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMalloc(&F->demtab, sizeof(double) * emtab.size()));
   KGW_CUDA(cudaMalloc(&F->dref_global, sizeof(int32_t) * (size_t)N * K));
   KGW_CUDA(cudaMalloc(&F->dstatus, sizeof(int32_t)));
+  KGW_CUDA(cudaMalloc(&F->dwork, sizeof(int32_t)));
+  KGW_CUDA(cudaMalloc(&F->dranges, sizeof(KgwFamRange) * std::max<size_t>(ranges.size(), 1)));
+  KGW_CUDA(cudaMemcpy(F->dranges, ranges.data(), sizeof(KgwFamRange) * ranges.size(), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->dmembers, F->h_members.data(), sizeof(int32_t) * F->members_total, cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->divstart, iv_start.data(), sizeof(int32_t) * iv_start.size(), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->divs, ivs.data(), sizeof(KgwFamInterval) * ivs.size(), cudaMemcpyHostToDevice));
@@ -668,28 +686,30 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMemcpy(F->dref_global, prob->ref_global, sizeof(int32_t) * (size_t)N * K, cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemset(F->dstatus, 0, sizeof(int32_t)));
 
-  // one warp per resident family; scratch slots bounded by a third of the free memory
+  // one warp per resident family (16 warps per SM), scratch slots bounded by 60 % of the free memory
   F->SF = (K + 31) / 32 <= 1 ? 1 : ((K + 31) / 32 <= 2 ? 2 : ((K + 31) / 32 <= 4 ? 4 : 8));
   F->threads = 128;
-  F->smem = (size_t)(F->threads / 32) * 8 * 256 * sizeof(double);
-  const size_t per_slot = (size_t)F->n_max * p * ((size_t)K * 17 + 3);
+  const int wpc = F->threads / 32;
+  F->smem = (size_t)8 * 256 * sizeof(double) + (size_t)wpc * F->n_max * F->SF * 32 * sizeof(double);
+  const size_t per_slot = (size_t)F->n_max * p * ((size_t)K * 17 + 2);
   size_t free_b = 0, total_b = 0;
   KGW_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  long long slots = std::min<long long>(F->n_families, (long long)dp.multiProcessorCount * 8);
-  slots = std::max<long long>(1, std::min<long long>(slots, (long long)((double)free_b / 3.0 / (double)per_slot)));
-  const int wpc = F->threads / 32;
-  F->grid = (int)((slots + wpc - 1) / wpc);
+  const long long slots_mem = std::max<long long>(wpc, (long long)((double)free_b * 0.6 / (double)per_slot));
+  const long long want = std::min<long long>(F->n_families, (long long)dp.multiProcessorCount * 16);
+  long long ctas = (want + wpc - 1) / wpc;
+  if (ctas * wpc > slots_mem) ctas = slots_mem / wpc;
+  F->grid = (int)std::max<long long>(1, ctas);
   const size_t nslots = (size_t)F->grid * wpc;
   KGW_CUDA(cudaMalloc(&F->dmsg, sizeof(double) * 2 * F->n_max * (size_t)p * K * nslots));
   KGW_CUDA(cudaMalloc(&F->dpat, (size_t)F->n_max * p * K * nslots));
-  KGW_CUDA(cudaMalloc(&F->dbytes, (size_t)3 * F->n_max * p * nslots));
+  KGW_CUDA(cudaMalloc(&F->dbytes, (size_t)2 * F->n_max * p * nslots));
 
   KgwFamParams &P = F->P;
   P.N = N; P.p = p; P.K = K; P.n_families = F->n_families; P.stride_w = pl->stride_w; P.n_max = F->n_max;
   P.uniform_mu = uniform ? 1 : 0;
   P.Hw = pl->dHw; P.ref_global = F->dref_global; P.fams = F->dfams; P.members = F->dmembers; P.iv_start = F->divstart;
   P.ivs = F->divs; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.msg = F->dmsg; P.pat = F->dpat;
-  P.bytes = F->dbytes; P.seed = pl->P.seed; P.injected_u = pl->dinj; P.dbg_z = P.dbg_zk = nullptr; P.status = F->dstatus;
+  P.bytes = F->dbytes; P.work = F->dwork; P.ranges = F->dranges; P.seed = pl->P.seed; P.injected_u = pl->dinj; P.dbg_z = P.dbg_zk = nullptr; P.status = F->dstatus;
   return KGW_OK;
 }
 
@@ -698,6 +718,7 @@ int fam_launch(kgw_plan *pl) {
   if (!F || F->n_families == 0) return KGW_OK;
   void (*fn)(const KgwFamParams) = F->SF == 1 ? kgw::family_kernel<1> : (F->SF == 2 ? kgw::family_kernel<2> : (F->SF == 4 ? kgw::family_kernel<4> : kgw::family_kernel<8>));
   KGW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
+  KGW_CUDA(cudaMemsetAsync(F->dwork, 0, sizeof(int32_t), pl->stream));
   fn<<<F->grid, F->threads, F->smem, pl->stream>>>(F->P);
   KGW_CUDA(cudaGetLastError());
   return KGW_OK;

@@ -6,13 +6,26 @@
 //   FamilyKnockoffs                       snpknock2/src/family_knockoffs.cpp:77-454
 //   Knockoffs::sample_emission            snpknock2/src/knockoffs.cpp:1430-1441
 //
-// Mapping: one warp per IBD family (families are independent, knockoffs.cpp:440-445); lane l owns the
-// HMM states k = l, l+32, ... (SF = ceil(K/32) per lane).  The BP messages of a family,
-// double [2][members][p][K], and the per-(member, locus, state) emission pattern bytes live in an HBM
-// scratch slot owned by the warp; neighbour sets are piecewise constant along the chromosome and come
-// from the host as intervals (with the junction differences of family_bp.cpp:352-378 precomputed).
-// Node emissions are table look-ups: the reference's pow(prod, 1/(n+1)) (family_bp.cpp:441-454) takes
-// one of 2^(n+1) values, tabulated on the host with the reference's own operation order.
+// Mapping: one warp per IBD family (families are independent, knockoffs.cpp:440-445), families handed out
+// through an atomic counter; lane l owns the HMM states k = l, l+32, ... (SF = ceil(K/32) per lane), so
+// no message entry is ever touched by two lanes.  The BP messages of a family, double [2][members][p][K],
+// and the per-(member, locus, state) emission pattern bytes live in an HBM scratch slot owned by the
+// warp; neighbour sets are piecewise constant along the chromosome and come from the host as intervals
+// (with the junction differences of family_bp.cpp:352-378 precomputed).  Node emissions are table
+// look-ups: the reference's pow(prod, 1/(n+1)) (family_bp.cpp:441-454) takes one of 2^(n+1) values,
+// tabulated on the host with the reference's own operation order.
+//
+// Exact work skipping in run_bp (family_bp.cpp:318-419).  A message is a deterministic function of its
+// inputs: the neighbouring message on its own chain and, only at a junction, messages of other members.
+// Recomputing it from bit-identical inputs returns the stored bits and adds exactly 0 to the
+// convergence sum.  Interval boundaries b (a member's neighbour list changes between b-1 and b) define
+// "special" loci [b-2, b+1]: every junction node, every node pinned by condition_on (:236-255) and every
+// consumer of a pinned or cross-chain message lies there.  A sweep recomputes (1) everything in the
+// very first iteration, (2) the special loci, (3) a node whose own-chain input changed bits earlier in
+// the same sweep; all other nodes are skipped.  The perturbation from a junction dies out bit for bit
+// after a few hundred loci, so iterations after the first cost a few per cent of a full sweep (85 % of
+// the reference's message updates are such no-ops on the synthetic pairs; rule checked on the CPU
+// against the oracle: 0 violations).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,6 +44,8 @@ struct KgwFamInterval {  // maximal run of loci over which neighbors[i][j] is co
   int32_t pad;
 };
 
+struct KgwFamRange { int32_t s0, s1; };  // special loci, inclusive; sorted, disjoint
+
 enum { KGW_FOP_COPYZ = 0, KGW_FOP_DRAW = 1, KGW_FOP_COPYZK = 2 };
 struct KgwFamOp {  // FamilyKnockoffs::run (family_knockoffs.cpp:155-270) flattened in execution order
   int32_t kind;    // COPYZ: Zk[i][a..b] = Z[i][a..b];  DRAW: sample_knockoff_MC(i, groups a..b);  COPYZK: Zk[i][a..b] = Zk[src][a..b]
@@ -43,7 +58,8 @@ struct KgwFamDesc {
   int32_t mem_off;    // into members[] and iv_start[] (iv_start has one extra entry per family)
   int32_t op_off, n_ops;
   int32_t out_off;    // row offset of this family in the debug outputs
-  int32_t pad[3];
+  int32_t rng_off, n_rng;   // special ranges of this family
+  int32_t pad;
 };
 
 struct KgwFamLocus {  // per locus
@@ -61,6 +77,7 @@ struct KgwFamParams {
   const int32_t *members;      // absolute ids
   const int32_t *iv_start;     // per (family, member): first interval; one sentinel per family
   const KgwFamInterval *ivs;
+  const KgwFamRange *ranges;
   const KgwFamOp *ops;
   const KgwFamLocus *loc;      // [p]
   const KgwLocusKO *ko;        // [p] single-window table (vstar / vbar / flags of every locus)
@@ -71,7 +88,8 @@ struct KgwFamParams {
   uint32_t *Hk;                // [N][stride_w]
   double *msg;                 // [slots][2][n_max][p][K]
   uint8_t *pat;                // [slots][n_max][p][K]
-  uint8_t *bytes;              // [slots][3][n_max][p]   inactive, Z, Zk
+  uint8_t *bytes;              // [slots][2][n_max][p]   Z (255 = node still active), Zk
+  int32_t *work;               // next family to hand out (zeroed before every launch)
   unsigned long long seed;
   const double *injected_u;    // [N][3][p] or null
   int32_t *dbg_z, *dbg_zk;     // [members total][p] or null
@@ -85,6 +103,15 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+__device__ __forceinline__ void warp_sum2(double &a, double &b) {   // two sums in one shuffle tree
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ta = __shfl_xor_sync(FULL, a, o);
+    const double tb = __shfl_xor_sync(FULL, b, o);
+    a += ta;
+    b += tb;
+  }
+}
 __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -94,6 +121,11 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
   return v;
 }
 
+// L2 prefetch of the `bytes` starting at `ptr` (one 128-byte line per lane)
+__device__ __forceinline__ void fam_prefetch(const void *ptr, int bytes, int lane) {
+  if (lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(ptr) + lane * 128));
+}
+
 __device__ __forceinline__ double fam_uniform(const KgwFamParams &P, int hap, int stream, int j) {
   if (P.injected_u) return P.injected_u[((size_t)hap * 3 + stream) * (size_t)P.p + j];
   const kgw_u32x4 r = kgw_philox_block(P.seed, (uint32_t)hap, (uint32_t)stream, (uint32_t)(j >> 2));
@@ -101,53 +133,62 @@ __device__ __forceinline__ double fam_uniform(const KgwFamParams &P, int hap, in
   return kgw_word_to_uniform(q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w)));
 }
 
-// weighted_choice (utils.cpp:690-698) over states k = s*32 + lane: first k with u*S < cumulative weight
+// weighted_choice (utils.cpp:690-698) over states k = s*32 + lane: first k with u*S < cumulative weight.
+// The cumulative sums are non-decreasing in k, so the count of prefixes <= R is one ballot per s.
 template <int SF>
 __device__ __forceinline__ int warp_choice(const double (&w)[SF], double u, int K, int lane) {
   double tot = 0.0;
   double inc[SF];
 #pragma unroll
+  for (int s = 0; s < SF; s++) inc[s] = warp_incl_scan(w[s], lane);
+#pragma unroll
   for (int s = 0; s < SF; s++) {
-    const double c = warp_incl_scan(w[s], lane);
+    const double c = inc[s];
     inc[s] = tot + c;
     tot += __shfl_sync(FULL, c, 31);
   }
   const double R = u * tot;
   int cnt = 0;
 #pragma unroll
-  for (int s = 0; s < SF; s++) cnt += (s * 32 + lane < K && inc[s] <= R) ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+  for (int s = 0; s < SF; s++) cnt += __popc(__ballot_sync(FULL, s * 32 + lane < K && inc[s] <= R));
   return min(cnt, K - 1);
 }
 
 template <int SF>
-__global__ void __launch_bounds__(128) family_kernel(const __grid_constant__ KgwFamParams P) {
+__global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ KgwFamParams P) {
+  constexpr int KP = SF * 32;
   const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
-  const int slot = blockIdx.x * wpc + (threadIdx.x >> 5);
-  const int nslots = gridDim.x * wpc;
+  const int slot = blockIdx.x * wpc + wid;
   const int p = P.p, K = P.K;
   const size_t pK = (size_t)p * K;
   double *mr_base = P.msg + (size_t)slot * 2 * P.n_max * pK;   // messages_right [n][p][K]
   double *ml_base = mr_base + (size_t)P.n_max * pK;            // messages_left
   uint8_t *pat_base = P.pat + (size_t)slot * P.n_max * pK;
-  uint8_t *inact = P.bytes + (size_t)slot * 3 * P.n_max * p;
-  uint8_t *Zb = inact + (size_t)P.n_max * p;
+  uint8_t *Zb = P.bytes + (size_t)slot * 2 * P.n_max * p;     // 255 = not drawn yet = node still active
   uint8_t *Zkb = Zb + (size_t)P.n_max * p;
 
   extern __shared__ __align__(16) unsigned char fam_smem[];
-  double *tab = reinterpret_cast<double *>(fam_smem) + (size_t)(threadIdx.x >> 5) * 8 * 256;
+  double *tab = reinterpret_cast<double *>(fam_smem);                       // [8][256], shared by the CTA
+  double *pm = tab + 8 * 256 + (size_t)wid * P.n_max * KP;                  // [n_max][KP] last message of each chain
   if (P.uniform_mu) {
-    for (int t = lane; t < 8 * 256; t += 32) tab[t] = P.emtab[t];
+    for (int t = threadIdx.x; t < 8 * 256; t += blockDim.x) tab[t] = P.emtab[t];
   }
-  __syncwarp();
+  __syncthreads();
+  const double p0 = 1.0 / ((double)K);   // initial value of every message (family_bp.cpp:421-427)
 
-  for (int f = slot; f < P.n_families; f += nslots) {
+  for (;;) {
+    int f = 0;
+    if (lane == 0) f = atomicAdd(P.work, 1);
+    f = __shfl_sync(FULL, f, 0);
+    if (f >= P.n_families) break;
     const KgwFamDesc fd = P.fams[f];
     const int n = fd.n;
     const int32_t *mem = P.members + fd.mem_off;
     const int32_t *ivs0 = P.iv_start + fd.mem_off + f;   // n+1 entries for this family
+    const KgwFamRange *rngs = P.ranges + fd.rng_off;
+    const int nrng = fd.n_rng;
 
     auto find_iv = [&](int i, int j) -> const KgwFamInterval * {
       const KgwFamInterval *iv = P.ivs + ivs0[i];
@@ -155,8 +196,7 @@ __global__ void __launch_bounds__(128) family_kernel(const __grid_constant__ Kgw
       return iv;
     };
     // emission of node (i, j) for state k (family_bp.cpp:437-454)
-    auto node_emission = [&](int i, int j, int k, int nn) -> double {
-      const unsigned pt = pat_base[((size_t)i * p + j) * K + k];
+    auto emission_of = [&](unsigned pt, int j, int nn) -> double {
       if (P.uniform_mu) return tab[nn * 256 + pt];
       const double mu = P.loc[j].mu;
       double v = (pt & 1u) ? 1.0 - mu : mu;
@@ -165,102 +205,171 @@ __global__ void __launch_bounds__(128) family_kernel(const __grid_constant__ Kgw
       return v;
     };
 
-    // ---- initialise: match patterns, messages 1/K (family_bp.cpp:421-427), nothing inactive, Z unset
-    const double p0 = 1.0 / ((double)K);
+    // ---- initialise: nothing drawn, match patterns.  The messages are NOT written: the first BP
+    //      iteration substitutes their initial value 1/K wherever the reference would read it.
     for (int i = 0; i < n; i++) {
       const int i_abs = mem[i];
       const int32_t *ref = P.ref_global + (size_t)i_abs * K;
-      for (int j = lane; j < p; j += 32) { inact[(size_t)i * p + j] = 0; Zb[(size_t)i * p + j] = 255; Zkb[(size_t)i * p + j] = 255; }
+      for (int j = lane; j < p; j += 32) { Zb[(size_t)i * p + j] = 255; Zkb[(size_t)i * p + j] = 255; }
       for (int k = lane; k < K; k += 32) {
         const size_t rrow = (size_t)__ldg(ref + k) * P.stride_w;
         const KgwFamInterval *iv = P.ivs + ivs0[i];
+        int ivj1 = iv->j1, ivnn = iv->nn;
         for (int w = 0; w <= (p - 1) >> 5; w++) {
           const uint32_t rw = __ldg(P.Hw + rrow + w);
           const uint32_t m0 = ~(rw ^ __ldg(P.Hw + (size_t)i_abs * P.stride_w + w));
-          const int jhi = min((w << 5) + 32, p);
-          for (int j = w << 5; j < jhi; j++) {
-            while (iv->j1 < j) iv++;
-            unsigned pt = (m0 >> (j & 31)) & 1u;
-            for (int t = 0; t < iv->nn; t++) {
-              const uint32_t hw2 = __ldg(P.Hw + (size_t)mem[iv->nb[t]] * P.stride_w + w);
-              pt |= ((~(rw ^ hw2) >> (j & 31)) & 1u) << (t + 1);
+          const int jlo = w << 5, jhi = min(jlo + 32, p);
+          uint8_t *dst = pat_base + ((size_t)i * p + jlo) * K + k;
+          while (ivj1 < jlo) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
+          if (ivj1 >= jhi - 1) {   // one neighbour list for the whole word
+            uint32_t mt[KGW_FAM_MAXNB];
+#pragma unroll
+            for (int t = 0; t < KGW_FAM_MAXNB; t++)
+              mt[t] = (t < ivnn) ? ~(rw ^ __ldg(P.Hw + (size_t)mem[iv->nb[t]] * P.stride_w + w)) : 0u;
+            for (int j = jlo; j < jhi; j++) {
+              const int q = j & 31;
+              unsigned pt = (m0 >> q) & 1u;
+#pragma unroll
+              for (int t = 0; t < KGW_FAM_MAXNB; t++) pt |= ((mt[t] >> q) & 1u) << (t + 1);
+              *dst = (uint8_t)pt;
+              dst += K;
             }
-            const size_t o = ((size_t)i * p + j) * K + k;
-            pat_base[o] = (uint8_t)pt;
-            mr_base[o] = p0;
-            ml_base[o] = p0;
+          } else {
+            for (int j = jlo; j < jhi; j++) {
+              while (ivj1 < j) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
+              unsigned pt = (m0 >> (j & 31)) & 1u;
+              for (int t = 0; t < ivnn; t++) {
+                const uint32_t hw2 = __ldg(P.Hw + (size_t)mem[iv->nb[t]] * P.stride_w + w);
+                pt |= ((~(rw ^ hw2) >> (j & 31)) & 1u) << (t + 1);
+              }
+              *dst = (uint8_t)pt;
+              dst += K;
+            }
           }
         }
       }
     }
     __syncwarp();
 
-    // one BP message (family_bp.cpp:429-559): dir 0 = right (writes messages_right[i][j]), 1 = left.
-    // Returns this lane's share of sum_k |new - old|.
-    auto send_message = [&](int i, int j, int dir, const KgwFamInterval *iv) -> double {
-      const bool jl = (j == iv->j0) && j > 0, jr = (j == iv->j1) && j < p - 1;
-      const int ndl = jl ? iv->ndl : 0, ndr = jr ? iv->ndr : 0;
-      const KgwFamLocus lc = P.loc[dir == 0 ? j + 1 : j];
-      double cst[SF], msg[SF];
-      double csum = 0.0;
-#pragma unroll
-      for (int s = 0; s < SF; s++) {
-        const int k = s * 32 + lane;
-        cst[s] = 0.0;
-        msg[s] = 0.0;
-        if (k < K) {
-          const double fk = node_emission(i, j, k, iv->nn);
-          double c = lc.a_bp * fk, m = lc.b * fk;
-          if (dir == 0) {
-            if (j > 0) { const double v = mr_base[((size_t)i * p + j - 1) * K + k]; c *= v; m *= v; }
-            for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
-            for (int t = 0; t < ndr; t++) { const double v = ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
-          } else {
-            if (j < p - 1) { const double v = ml_base[((size_t)i * p + j + 1) * K + k]; c *= v; m *= v; }
-            for (int t = 0; t < ndr; t++) { const double v = ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
-            for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
-          }
-          cst[s] = c;
-          msg[s] = m;
-          csum += c;
-        }
-      }
-      const double const_msg = warp_sum(csum);
-      double msum = 0.0;
-#pragma unroll
-      for (int s = 0; s < SF; s++) {
-        if (s * 32 + lane < K) { msg[s] = const_msg + msg[s]; msum += msg[s]; }
-      }
-      const double inv = 1.0 / warp_sum(msum);
-      double *dst = (dir == 0 ? mr_base : ml_base) + ((size_t)i * p + j) * K;
+    // One direction of one BP iteration (family_bp.cpp:341-405 and the message formulas :429-559):
+    // dir 0 = right (writes messages_right[i][j], j = 0 .. p-2), 1 = left (messages_left[i][j], j = p-1 .. 1).
+    // `full`: first iteration of the first run_bp -- every node is computed and the "old" value of every
+    // message (also of the left messages read at a junction by the first right sweep) is 1/K.
+    // Returns this lane's share of sum |new - old|.
+    auto sweep = [&](const int dir, const bool full) -> double {
       double diff = 0.0;
-#pragma unroll
-      for (int s = 0; s < SF; s++) {
-        const int k = s * 32 + lane;
-        if (k < K) {
-          const double v = msg[s] * inv;
-          diff += fabs(v - dst[k]);
-          dst[k] = v;
+      unsigned comp_prev = 0, chg_prev = 0;   // members whose message one locus back was computed / changed bits in this sweep
+      int r = (dir == 0) ? 0 : nrng - 1;      // first special range not yet behind the sweep
+      int rs0, rs1;
+      if (dir == 0) { if (r < nrng) { rs0 = rngs[r].s0; rs1 = rngs[r].s1; } else { rs0 = rs1 = 0x7fffffff; } }
+      else { if (r >= 0) { rs0 = rngs[r].s0; rs1 = rngs[r].s1; } else { rs0 = rs1 = -1; } }
+      int j = (dir == 0) ? 0 : p - 1;
+      const int step = (dir == 0) ? 1 : -1;
+      unsigned nnpack = 0;                    // neighbour count of every member at the current locus, 3 bits each
+      for (int i = 0; i < n; i++) nnpack |= (unsigned)find_iv(i, j)->nn << (3 * i);
+      double *dstb = (dir == 0) ? mr_base : ml_base;
+      while (dir == 0 ? (j < p - 1) : (j > 0)) {
+        if (dir == 0) {
+          while (j > rs1) { r++; if (r < nrng) { rs0 = rngs[r].s0; rs1 = rngs[r].s1; } else { rs0 = rs1 = 0x7fffffff; } }
+        } else {
+          while (j < rs0) { r--; if (r >= 0) { rs0 = rngs[r].s0; rs1 = rngs[r].s1; } else { rs0 = rs1 = -1; } }
         }
+        const bool special = (j >= rs0 && j <= rs1);
+        if (!full && !special && chg_prev == 0) {   // nothing can change before the next special range
+          if (dir == 0) { if (rs0 == 0x7fffffff) break; j = rs0; }
+          else { if (rs1 < 0) break; j = rs1; }
+          comp_prev = 0;
+          continue;
+        }
+        const KgwFamLocus lc = P.loc[dir == 0 ? j + 1 : j];
+        const bool has_prev = (dir == 0) ? (j > 0) : (j < p - 1);
+        unsigned comp_cur = 0, chg_cur = 0;
+        for (int i = 0; i < n; i++) {
+          int nn, ndl = 0, ndr = 0;
+          const KgwFamInterval *iv = nullptr;
+          if (special) {
+            iv = find_iv(i, j);
+            nn = iv->nn;
+            nnpack = (nnpack & ~(7u << (3 * i))) | ((unsigned)nn << (3 * i));
+            if (Zb[(size_t)i * p + j] != 255) continue;   // pinned by condition_on: inactive node
+            if (j == iv->j0 && j > 0) ndl = iv->ndl;
+            if (j == iv->j1 && j < p - 1) ndr = iv->ndr;
+          } else {
+            if (!full && !((chg_prev >> i) & 1u)) continue;
+            nn = (int)((nnpack >> (3 * i)) & 7u);
+          }
+          const size_t rowo = ((size_t)i * p + j) * K;
+          const double *prevg = dstb + rowo - (ptrdiff_t)step * K;   // own chain, one locus back in sweep order
+          if ((unsigned)(j + 8 * step) < (unsigned)p) {              // rows this chain needs eight loci further on
+            const ptrdiff_t ahead = (ptrdiff_t)step * 8 * K;
+            fam_prefetch(pat_base + rowo + ahead, K, lane);
+            if (!full) fam_prefetch(dstb + rowo + ahead, 8 * K, lane);
+          }
+          const bool prev_sm = (comp_prev >> i) & 1u;
+          double cst[SF], msg[SF], oldv[SF];
+          double csum = 0.0, msum = 0.0;
+#pragma unroll
+          for (int s = 0; s < SF; s++) {
+            const int k = s * 32 + lane;
+            cst[s] = 0.0;
+            msg[s] = 0.0;
+            oldv[s] = 0.0;
+            if (k < K) {
+              const double fk = emission_of(pat_base[rowo + k], j, nn);
+              oldv[s] = full ? p0 : dstb[rowo + k];
+              double c = lc.a_bp * fk, m = lc.b * fk;
+              if (has_prev) { const double v = prev_sm ? pm[i * KP + k] : prevg[k]; c *= v; m *= v; }
+              if (dir == 0) {
+                for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
+                for (int t = 0; t < ndr; t++) { const double v = full ? p0 : ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
+              } else {
+                for (int t = 0; t < ndr; t++) { const double v = ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
+                for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
+              }
+              cst[s] = c;
+              msg[s] = m;
+              csum += c;
+              msum += m;
+            }
+          }
+          warp_sum2(csum, msum);
+          const double const_msg = csum;
+          const double inv = 1.0 / ((double)K * const_msg + msum);   // sum_k (const_msg + msg_k)
+          bool ne = false;
+#pragma unroll
+          for (int s = 0; s < SF; s++) {
+            if (s * 32 + lane < K) {
+              const double v = (const_msg + msg[s]) * inv;
+              diff += fabs(v - oldv[s]);
+              ne |= (v != oldv[s]);
+              msg[s] = v;
+            }
+          }
+          const bool ch = __any_sync(FULL, ne);
+#pragma unroll
+          for (int s = 0; s < SF; s++) {
+            const int k = s * 32 + lane;
+            if (k < K) {
+              if (full || ch) dstb[rowo + k] = msg[s];
+              pm[i * KP + k] = msg[s];
+            }
+          }
+          comp_cur |= 1u << i;
+          if (ch) chg_cur |= 1u << i;
+        }
+        comp_prev = comp_cur;
+        chg_prev = chg_cur;
+        j += step;
       }
       return diff;
     };
 
     // run_bp (family_bp.cpp:318-419)
-    auto run_bp = [&]() {
+    auto run_bp = [&](const bool first) {
       for (int it = 0; it < 20; it++) {
         double diff = 0.0;
         for (int dir = 0; dir < 2; dir++) {
-          double dt = 0.0;
-          for (int jj = 0; jj < p; jj++) {
-            const int j = (dir == 0) ? jj : p - 1 - jj;
-            if (dir == 0 ? (j >= p - 1) : (j <= 0)) continue;
-            for (int i = 0; i < n; i++) {
-              if (inact[(size_t)i * p + j]) continue;
-              dt += send_message(i, j, dir, find_iv(i, j));
-            }
-            __syncwarp();
-          }
+          double dt = sweep(dir, first && it == 0);
           dt = warp_sum(dt) / (double)((size_t)p * (size_t)n);
           diff += dt;
         }
@@ -268,32 +377,31 @@ __global__ void __launch_bounds__(128) family_kernel(const __grid_constant__ Kgw
       }
     };
 
-    // condition_on (family_bp.cpp:236-255)
-    auto condition_on = [&](int i, int j, int kz, bool forward) {
+    // condition_on (family_bp.cpp:236-255), forward = false (the final pass keeps its pins in registers)
+    auto condition_on = [&](int i, int j, int kz) {
       for (int l = lane; l < K; l += 32) {
         if (j < p - 1) {
           const KgwFamLocus lc = P.loc[j + 1];
           mr_base[((size_t)i * p + j) * K + l] = lc.a_al + lc.b * (double)(l == kz);
         }
-        if (!forward && j > 0) {
+        if (j > 0) {
           const KgwFamLocus lc = P.loc[j];
           ml_base[((size_t)i * p + j) * K + l] = lc.a_al + lc.b * (double)(l == kz);
         }
       }
-      if (lane == 0) inact[(size_t)i * p + j] = 1;
+      if (lane == 0) Zb[(size_t)i * p + j] = (uint8_t)kz;
     };
 
-    // sample_posterior_joint (family_bp.cpp:569-601)
-    auto draw_node = [&](int i, int j, const KgwFamInterval *iv, bool junction) -> int {
-      const bool jl = junction && (j == iv->j0) && j > 0, jr = junction && (j == iv->j1) && j < p - 1;
-      const int ndl = jl ? iv->ndl : 0, ndr = jr ? iv->ndr : 0;
+    // sample_posterior_joint at a junction node (family_bp.cpp:569-601)
+    auto draw_junction = [&](int i, int j, const KgwFamInterval *iv) -> int {
+      const int ndl = (j == iv->j0 && j > 0) ? iv->ndl : 0, ndr = (j == iv->j1 && j < p - 1) ? iv->ndr : 0;
       double w[SF];
 #pragma unroll
       for (int s = 0; s < SF; s++) {
         const int k = s * 32 + lane;
         w[s] = 0.0;
         if (k < K) {
-          double v = node_emission(i, j, k, iv->nn);
+          double v = emission_of(pat_base[((size_t)i * p + j) * K + k], j, iv->nn);
           if (j > 0) {
             v *= mr_base[((size_t)i * p + j - 1) * K + k];
             for (int t = 0; t < ndl; t++) v *= mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k];
@@ -309,41 +417,102 @@ __global__ void __launch_bounds__(128) family_kernel(const __grid_constant__ Kgw
     };
 
     // ---- FamilyBP::run (family_bp.cpp:79-100) and sample_posterior (:160-230)
-    run_bp();
+    run_bp(true);
+    // junction nodes first, (member, locus) ascending; they sit at interval ends (:168-193)
     for (int i = 0; i < n; i++) {
-      for (int j = 0; j < p; j++) {
-        if (inact[(size_t)i * p + j]) continue;
-        const KgwFamInterval *iv = find_iv(i, j);
-        const bool jl = (j == iv->j0) && j > 0, jr = (j == iv->j1) && j < p - 1;
-        if (!((jl && iv->ndl > 0) || (jr && iv->ndr > 0))) continue;  // not a junction (:176-193)
-        const int kz = draw_node(i, j, iv, true);
-        __syncwarp();
-        if (lane == 0) Zb[(size_t)i * p + j] = (uint8_t)kz;
-        condition_on(i, j, kz, false);
-        for (int t = 0; t < iv->nn; t++) {
-          const int i2 = iv->nb[t];
-          if (lane == 0) Zb[(size_t)i2 * p + j] = (uint8_t)kz;
-          condition_on(i2, j, kz, false);
+      const KgwFamInterval *iv_end = P.ivs + ivs0[i + 1];
+      for (const KgwFamInterval *iv = P.ivs + ivs0[i]; iv < iv_end; iv++) {
+        for (int e = 0; e < 2; e++) {
+          const int j = (e == 0) ? iv->j0 : iv->j1;
+          if (e == 1 && iv->j1 == iv->j0) break;
+          const bool jl = (j == iv->j0) && j > 0 && iv->ndl > 0, jr = (j == iv->j1) && j < p - 1 && iv->ndr > 0;
+          if (!(jl || jr)) continue;
+          if (Zb[(size_t)i * p + j] != 255) continue;
+          const int kz = draw_junction(i, j, iv);
+          __syncwarp();
+          condition_on(i, j, kz);
+          for (int t = 0; t < iv->nn; t++) condition_on(iv->nb[t], j, kz);
+          __syncwarp();
+          run_bp(false);
         }
-        __syncwarp();
-        run_bp();
       }
     }
+    // every remaining node, member by member, loci ascending (:217-229).  By then every node to the left on
+    // the same chain has been drawn, so messages_right[i][j-1] is the point-mass transition condition_on
+    // would have stored (:243-246) and is formed from the previous draw; nothing reads the right messages
+    // afterwards, so they are not written.  messages_left[i][j+1] and the pattern bytes are fetched one
+    // locus ahead of the (serial) draw.
     for (int i = 0; i < n; i++) {
-      for (int j = 0; j < p; j++) {
-        if (inact[(size_t)i * p + j]) continue;
-        const KgwFamInterval *iv = find_iv(i, j);
-        const int kz = draw_node(i, j, iv, false);
-        __syncwarp();
-        if (lane == 0) Zb[(size_t)i * p + j] = (uint8_t)kz;
-        condition_on(i, j, kz, true);
-        for (int t = 0; t < iv->nn; t++) {
-          const int i2 = iv->nb[t];
-          if (lane == 0) Zb[(size_t)i2 * p + j] = (uint8_t)kz;
-          condition_on(i2, j, kz, true);
-        }
-        __syncwarp();
+      const KgwFamInterval *iv = P.ivs + ivs0[i];
+      int ivj1 = iv->j1, ivnn = iv->nn;
+      unsigned nbpack = 0;
+      for (int t = 0; t < ivnn; t++) nbpack |= (unsigned)iv->nb[t] << (3 * t);
+      const uint8_t *zrow = Zb + (size_t)i * p;
+      const double *mlrow = ml_base + (size_t)i * pK;
+      const uint8_t *ptrow = pat_base + (size_t)i * pK;
+      int zprev = 0;
+      double ml_c[SF];
+      unsigned pt_c[SF];
+#pragma unroll
+      for (int s = 0; s < SF; s++) {
+        const int k = s * 32 + lane;
+        pt_c[s] = (k < K) ? ptrow[k] : 0u;
+        ml_c[s] = (k < K && p > 1) ? mlrow[(size_t)K + k] : 1.0;
       }
+      for (int w = 0; w <= (p - 1) >> 5; w++) {
+        const int jw = (w << 5) + lane;
+        const int zw = (jw < p) ? zrow[jw] : 0;
+        const int jhi = min(32, p - (w << 5));
+        for (int q = 0; q < jhi; q++) {
+          const int j = (w << 5) + q;
+          double ml_n[SF];
+          unsigned pt_n[SF];
+#pragma unroll
+          for (int s = 0; s < SF; s++) {   // next locus: pattern j+1, left message j+2
+            const int k = s * 32 + lane;
+            pt_n[s] = (k < K && j + 1 < p) ? ptrow[(size_t)(j + 1) * K + k] : 0u;
+            ml_n[s] = (k < K && j + 2 < p) ? mlrow[(size_t)(j + 2) * K + k] : 1.0;
+          }
+          if (j + 10 < p) {
+            fam_prefetch(ptrow + (size_t)(j + 9) * K, K, lane);
+            fam_prefetch(mlrow + (size_t)(j + 10) * K, 8 * K, lane);
+          }
+          const int zj = __shfl_sync(FULL, zw, q);
+          if (zj != 255) {
+            zprev = zj;
+          } else {
+            while (ivj1 < j) {
+              iv++;
+              ivj1 = iv->j1;
+              ivnn = iv->nn;
+              nbpack = 0;
+              for (int t = 0; t < ivnn; t++) nbpack |= (unsigned)iv->nb[t] << (3 * t);
+            }
+            const KgwFamLocus lc = P.loc[j];
+            double wv[SF];
+#pragma unroll
+            for (int s = 0; s < SF; s++) {
+              const int k = s * 32 + lane;
+              wv[s] = 0.0;
+              if (k < K) {
+                double v = emission_of(pt_c[s], j, ivnn);
+                if (j > 0) v *= lc.a_al + lc.b * (double)(k == zprev);
+                if (j < p - 1) v *= ml_c[s];
+                wv[s] = v;
+              }
+            }
+            const int kz = warp_choice<SF>(wv, fam_uniform(P, mem[i], STREAM_Z, j), K, lane);
+            if (lane == 0) {
+              Zb[(size_t)i * p + j] = (uint8_t)kz;
+              for (int t = 0; t < ivnn; t++) Zb[(size_t)((nbpack >> (3 * t)) & 7u) * p + j] = (uint8_t)kz;
+            }
+            zprev = kz;
+          }
+#pragma unroll
+          for (int s = 0; s < SF; s++) { pt_c[s] = pt_n[s]; ml_c[s] = ml_n[s]; }
+        }
+      }
+      __syncwarp();
     }
 
     // ---- FamilyKnockoffs::run (family_knockoffs.cpp:77-293) as a flat op list
@@ -362,12 +531,13 @@ __global__ void __launch_bounds__(128) family_kernel(const __grid_constant__ Kgw
         double Nv[SF], No[SF];
 #pragma unroll
         for (int s = 0; s < SF; s++) { Nv[s] = 1.0; No[s] = 1.0; }
+        int zk_last = (g_begin > 0) ? zk[P.grp_first[g_begin] - 1] : 0;   // zk of the locus before the range
         for (int g = g_begin; g <= g_end; g++) {
           const int e0 = P.grp_first[g], e1 = P.grp_last[g];
           const KgwLocusKO k0v = P.ko[e0];
           const bool lastg = (g == P.n_groups - 1);
           const int z0 = (g > 0) ? z[e0 - 1] : 0;
-          const int z0k = (g > 0) ? zk[e0 - 1] : 0;
+          const int z0k = zk_last;
           const int z1 = lastg ? 0 : z[e1 + 1];
           // T_k for the first locus of the group (:358-375, :378-398, :423-436)
           double tq[SF];
@@ -417,7 +587,7 @@ __global__ void __launch_bounds__(128) family_kernel(const __grid_constant__ Kgw
             zkprev = warp_choice<SF>(w, fam_uniform(P, mem[i], STREAM_ZK, j), K, lane);
             if (lane == 0) zk[j] = (uint8_t)zkprev;
           }
-          __syncwarp();
+          zk_last = zkprev;
 #pragma unroll
           for (int s = 0; s < SF; s++) No[s] = Nv[s];
         }
