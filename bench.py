@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--block-loci", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--related-pairs", type=int, default=2368, help="synthetic IBD pairs of the related-branch leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
@@ -207,6 +208,7 @@ def run_b200_arm(a, rank, local_rank, world):
     import torch.distributed as dist
 
     import knockoffgwas_b200 as kg
+    from knockoffgwas_b200 import synth
     from knockoffgwas_b200.synth import make_problem
 
     if not torch.cuda.is_available():
@@ -392,6 +394,28 @@ def run_b200_arm(a, rank, local_rank, world):
                                                    "device time incl. kernel launches, excl. H2D of H; not part of `value`"}
         except Exception as e:
             line["reference_selection"] = {"error": repr(e)[:200]}
+
+    # ---- the IBD-conditioned branch of the same generate() call (generate_related, knockoffs.cpp:329-571) on
+    # synthetic related pairs (SURVEY.md 8d C5 recipe) drawn inside the same population; reported beside `value`
+    if rank == 0 and world == 1 and not a.no_e2e and a.related_pairs > 0:
+        try:
+            import copy
+            rp = copy.copy(prob)
+            rp.H, rp.ref = prob.H.copy(), prob.ref.copy()
+            synth.add_ibd_pairs(rp, min(a.related_pairs, N // 4))
+            fplan = kg.Plan(rp.H, p, K, rp.ref[:, None, :], rp.b, rp.mu, rp.groups, unrelated=np.zeros(0, np.int32),
+                            ref_global=rp.ref, seed=rp.seed, families=rp.families)
+            fplan.run(); fplan.sync()
+            fam_ms = fplan.run_timed(2)
+            fplan.close()
+            n_rel = 2 * len(rp.families)
+            line["related_branch"] = {"kernel_ms": fam_ms, "pairs": len(rp.families), "haplotypes": n_rel,
+                                      "hap_snps_per_s": n_rel * p / (fam_ms * 1e-3),
+                                      "segments_per_pair": float(np.mean([len(sl) for _, sl in rp.families])),
+                                      "note": "kgw::family_kernel (loopy BP + junction draws + family knockoffs), one warp per "
+                                              "family, related haplotypes only; not part of `value`"}
+        except Exception as e:
+            line["related_branch"] = {"error": repr(e)[:200]}
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:

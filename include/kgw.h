@@ -197,6 +197,24 @@ int32_t kgw_assign_references(int32_t N, int32_t p, int64_t row_bytes, const uin
                               int32_t n_clusters, const int32_t *clust_off, const int32_t *clust_members,
                               const int32_t *family_of, int32_t device, int32_t *ref_out, float *kernel_ms);
 
+/* ---- phased BGEN -> packed haplotype matrix -----------------------------
+ * Replaces the data loop of BgenReader::read_worker (bgen_reader.cpp:139-261) behind BgenReader::read
+ * (:66-80), the producer of Haplotypes::H (dataset.cpp).  `file` is the whole .bgen image (v1.2, layout 2,
+ * zstd / zlib / no compression); the unchanged host code keeps the sample and variant bookkeeping:
+ *   sample_idx     [n_samples] row of the BGEN sample block for output sample i (match_indices, :167-168)
+ *   variant_of_col [p]         position in file order of the variant stored in output column j
+ *                              (the two std::find on rsid, :183,191-201)
+ * H_out [2 n_samples][row_bytes]: chaplotype rows (bit j at byte j>>3, mask 1<<(j&7)), haplotypes 2i, 2i+1 of
+ * sample i as H[2*i].set / H[2*i+1].set fill them (:207-210).  A probability that is not exactly 0 or 1, a
+ * missing sample or a block that is not phased / diploid / biallelic returns KGW_ERR_INVALID -- the
+ * reference throws "Incorrect input" from prob_to_hap (:48-63).  The selected blocks are inflated on
+ * `host_threads` host threads (0 = all; system libzstd.so.1 / libz.so.1, loaded on first use) and decoded and
+ * transposed on the device; kernel_ms (may be NULL) receives the device time of that kernel. */
+int32_t kgw_bgen_variant_count(const uint8_t *file, int64_t file_bytes, int32_t *n_variants, int32_t *n_samples);
+int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples, const int32_t *sample_idx, int32_t p,
+                      const int32_t *variant_of_col, int32_t host_threads, int32_t device, int64_t row_bytes, uint8_t *H_out,
+                      float *kernel_ms);
+
 /* A destroyed plan parks its scratch slab (tens of GB) for the next plan on the same device, because
  * Knockoffs::generate() runs once per resolution (main.cpp:159-181); this frees the parked slabs. */
 void kgw_release_workspace(void);

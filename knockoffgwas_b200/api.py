@@ -120,6 +120,9 @@ def load_library():
         L.kgw_bed_column_bytes.argtypes = [C.c_int32]
         L.kgw_plan_encode_bed.restype = C.c_int32
         L.kgw_plan_encode_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
+        L.kgw_bgen_read.restype = C.c_int32
+        L.kgw_bgen_read.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int64, C.c_void_p, C.POINTER(C.c_float)]
         L.kgw_assign_references.restype = C.c_int32
         L.kgw_assign_references.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
@@ -357,6 +360,83 @@ def assign_references(H, p, K, clusters, family_of=None, compression=10, device=
                                    off.ctypes.data, mem.ctypes.data, None if fam is None else fam.ctypes.data,
                                    int(device), out.ctypes.data, C.byref(ms)))
     return out, float(ms.value)
+
+
+class BgenReader:
+    """Host mirror of the reference's BgenReader (bgen_reader.h, bgen_reader.cpp:8-80): opens `<prefix>.bgen`
+    (+ `<prefix>.sample`, two header lines then `ID_1 ID_2 ...`, metadata.cpp:131-147), keeps the variant ids of
+    the file, and `read(sample_ids, snp_ids)` returns the packed haplotype matrix uint8 [2 len(sample_ids)]
+    [ceil(len(snp_ids)/8)] in chaplotype layout through kgw_bgen_read.  The id bookkeeping (match_indices,
+    the rsid look-ups) is host work as in the reference, with dictionaries instead of std::find."""
+
+    def __init__(self, prefix, sample_file=None):
+        import struct
+        self.path = str(prefix) if str(prefix).endswith(".bgen") else str(prefix) + ".bgen"
+        self.image = np.fromfile(self.path, dtype=np.uint8)
+        d = self.image.tobytes()
+        if len(d) < 24:
+            raise KgwError(-1, "BGEN image shorter than its header")
+        offset, hlen, M, N = struct.unpack_from("<IIII", d, 0)
+        self.n_variants, self.n_samples = int(M), int(N)
+        rsid, pos = [], 4 + offset
+        for _ in range(M):                      # variant identifying data (BGEN v1.2): id, rsid, chromosome, position, alleles
+            (l,) = struct.unpack_from("<H", d, pos); pos += 2 + l
+            (l,) = struct.unpack_from("<H", d, pos); rsid.append(d[pos + 2:pos + 2 + l].decode()); pos += 2 + l
+            (l,) = struct.unpack_from("<H", d, pos); pos += 2 + l
+            (_, nall) = struct.unpack_from("<IH", d, pos); pos += 6
+            for _a in range(nall):
+                (l,) = struct.unpack_from("<I", d, pos); pos += 4 + l
+            (c,) = struct.unpack_from("<I", d, pos); pos += 4 + c
+        self.variant_ids = rsid
+        sf = sample_file if sample_file is not None else self.path[:-5] + ".sample"
+        self.sample_ids = None
+        try:
+            with open(sf) as fh:
+                rows = [ln.split() for ln in fh.read().splitlines() if ln.strip()]
+            self.sample_ids = [r[0] for r in rows[2:]]
+        except OSError:
+            pass
+        if self.sample_ids is not None and len(self.sample_ids) != self.n_samples:
+            raise KgwError(-1, "Error loading BGEN file: the number of samples does not match.")   # bgen_reader.cpp:31-34
+
+    def read(self, sample_ids=None, snp_ids=None, device=0, host_threads=0, return_ms=False):
+        if sample_ids is None:
+            sidx = np.arange(self.n_samples, dtype=np.int32)
+        else:
+            if self.sample_ids is None:
+                raise KgwError(-1, "sample ids requested but no .sample file was found")
+            where = {}
+            for i, sid in enumerate(self.sample_ids):
+                where.setdefault(sid, i)
+            try:
+                sidx = np.array([where[str(x)] for x in sample_ids], dtype=np.int32)
+            except KeyError as e:
+                raise KgwError(-1, f"sample {e.args[0]} is not in the BGEN sample file") from None
+        if snp_ids is None:
+            vcol = np.arange(self.n_variants, dtype=np.int32)
+        else:
+            first = {}
+            for v, rid in enumerate(self.variant_ids):
+                first.setdefault(rid, v)
+            try:
+                vcol = np.array([first[str(x)] for x in snp_ids], dtype=np.int32)
+            except KeyError:
+                raise KgwError(-1, "Error loading BGEN file. Some requested variants were not found.") from None   # :238-241
+        return read_bgen_image(self.image, sidx, vcol, device=device, host_threads=host_threads, return_ms=return_ms)
+
+
+def read_bgen_image(image, sample_idx, variant_of_col, device=0, host_threads=0, return_ms=False):
+    """kgw_bgen_read on an in-memory .bgen image: uint8 [2 n_samples][ceil(p/8)] chaplotype rows."""
+    L = load_library()
+    image = np.ascontiguousarray(image, dtype=np.uint8)
+    sidx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+    vcol = np.ascontiguousarray(variant_of_col, dtype=np.int32)
+    p = len(vcol)
+    H = np.zeros((2 * len(sidx), (p + 7) // 8), dtype=np.uint8)
+    ms = C.c_float()
+    _check(L.kgw_bgen_read(image.ctypes.data, image.nbytes, len(sidx), sidx.ctypes.data, p, vcol.ctypes.data, int(host_threads),
+                           int(device), H.shape[1], H.ctypes.data, C.byref(ms)))
+    return (H, float(ms.value)) if return_ms else H
 
 
 def combine_references_families(ref, families):

@@ -318,6 +318,7 @@ struct FamilyState {
   int32_t *dmembers = nullptr, *divstart = nullptr, *dgroups = nullptr, *dgfirst = nullptr, *dglast = nullptr, *dstatus = nullptr;
   int32_t *dwork = nullptr;
   KgwFamRange *dranges = nullptr;
+  long long *dphase = nullptr;
   int32_t *dref_global = nullptr;
   KgwFamInterval *divs = nullptr;
   KgwFamOp *dops = nullptr;
@@ -332,6 +333,17 @@ struct FamilyState {
     cudaFree(dfams); cudaFree(dmembers); cudaFree(divstart); cudaFree(dgroups); cudaFree(dgfirst); cudaFree(dglast);
     cudaFree(dstatus); cudaFree(dref_global); cudaFree(divs); cudaFree(dops); cudaFree(dloc); cudaFree(dko);
     cudaFree(demtab); cudaFree(dmsg); cudaFree(dpat); cudaFree(dbytes); cudaFree(ddbg_z); cudaFree(ddbg_zk);
+#ifdef KGW_PHASES
+    if (dphase) {
+      long long h[8];
+      cudaMemcpy(h, dphase, sizeof(h), cudaMemcpyDeviceToHost);
+      static const char *nm[7] = {"init patterns", "BP first iteration", "BP later sweeps", "junction draws", "final draws", "knockoff ops", "checks+alleles"};
+      long long tot = 0;
+      for (int i = 0; i < 7; i++) tot += h[i];
+      for (int i = 0; i < 7; i++) fprintf(stderr, "[kgw family phases] %-20s %14lld cycles  %5.1f %%\n", nm[i], h[i], 100.0 * h[i] / (double)tot);
+      cudaFree(dphase);
+    }
+#endif
     cudaFree(dwork); cudaFree(dranges);
   }
 };
@@ -581,6 +593,13 @@ int fam_upload_partition(kgw_plan *pl, const int32_t *groups) {
 
 struct DevInfo { int major = 0, minor = 0, multiProcessorCount = 0; };
 
+typedef void (*fam_kernel_fn)(const KgwFamParams);
+fam_kernel_fn fam_kernel_for(int SF, bool uniform_mu) {
+  if (uniform_mu)
+    return SF == 1 ? kgw::family_kernel<1, true> : (SF == 2 ? kgw::family_kernel<2, true> : (SF == 4 ? kgw::family_kernel<4, true> : kgw::family_kernel<8, true>));
+  return SF == 1 ? kgw::family_kernel<1, false> : (SF == 2 ? kgw::family_kernel<2, false> : (SF == 4 ? kgw::family_kernel<4, false> : kgw::family_kernel<8, false>));
+}
+
 int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   const kgw_families *fi = prob->families;
   const int p = pl->p, K = pl->K, N = pl->N;
@@ -686,16 +705,24 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMemcpy(F->dref_global, prob->ref_global, sizeof(int32_t) * (size_t)N * K, cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemset(F->dstatus, 0, sizeof(int32_t)));
 
-  // one warp per resident family (16 warps per SM), scratch slots bounded by 60 % of the free memory
+  // one warp per resident family, as many CTAs as the kernel's registers / shared memory keep resident;
+  // scratch slots bounded by 60 % of the free memory
   F->SF = (K + 31) / 32 <= 1 ? 1 : ((K + 31) / 32 <= 2 ? 2 : ((K + 31) / 32 <= 4 ? 4 : 8));
   F->threads = 128;
   const int wpc = F->threads / 32;
   F->smem = (size_t)8 * 256 * sizeof(double) + (size_t)wpc * F->n_max * F->SF * 32 * sizeof(double);
+  int ctas_per_sm = 4;
+  {
+    void (*fnq)(const KgwFamParams) = fam_kernel_for(F->SF, uniform);
+    KGW_CUDA(cudaFuncSetAttribute(fnq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
+    KGW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fnq, F->threads, F->smem));
+    ctas_per_sm = std::max(1, ctas_per_sm);
+  }
   const size_t per_slot = (size_t)F->n_max * p * ((size_t)K * 17 + 2);
   size_t free_b = 0, total_b = 0;
   KGW_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const long long slots_mem = std::max<long long>(wpc, (long long)((double)free_b * 0.6 / (double)per_slot));
-  const long long want = std::min<long long>(F->n_families, (long long)dp.multiProcessorCount * 16);
+  const long long want = std::min<long long>(F->n_families, (long long)dp.multiProcessorCount * ctas_per_sm * wpc);
   long long ctas = (want + wpc - 1) / wpc;
   if (ctas * wpc > slots_mem) ctas = slots_mem / wpc;
   F->grid = (int)std::max<long long>(1, ctas);
@@ -709,6 +736,12 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   P.uniform_mu = uniform ? 1 : 0;
   P.Hw = pl->dHw; P.ref_global = F->dref_global; P.fams = F->dfams; P.members = F->dmembers; P.iv_start = F->divstart;
   P.ivs = F->divs; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.msg = F->dmsg; P.pat = F->dpat;
+  P.phase_cycles = nullptr;
+#ifdef KGW_PHASES
+  KGW_CUDA(cudaMalloc(&F->dphase, sizeof(long long) * 8));
+  KGW_CUDA(cudaMemset(F->dphase, 0, sizeof(long long) * 8));
+  P.phase_cycles = F->dphase;
+#endif
   P.bytes = F->dbytes; P.work = F->dwork; P.ranges = F->dranges; P.seed = pl->P.seed; P.injected_u = pl->dinj; P.dbg_z = P.dbg_zk = nullptr; P.status = F->dstatus;
   return KGW_OK;
 }
@@ -716,7 +749,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
 int fam_launch(kgw_plan *pl) {
   FamilyState *F = pl->fam;
   if (!F || F->n_families == 0) return KGW_OK;
-  void (*fn)(const KgwFamParams) = F->SF == 1 ? kgw::family_kernel<1> : (F->SF == 2 ? kgw::family_kernel<2> : (F->SF == 4 ? kgw::family_kernel<4> : kgw::family_kernel<8>));
+  void (*fn)(const KgwFamParams) = fam_kernel_for(F->SF, F->P.uniform_mu != 0);
   KGW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
   KGW_CUDA(cudaMemsetAsync(F->dwork, 0, sizeof(int32_t), pl->stream));
   fn<<<F->grid, F->threads, F->smem, pl->stream>>>(F->P);

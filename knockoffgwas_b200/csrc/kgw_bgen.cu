@@ -1,0 +1,292 @@
+// knockoffgwas_b200/csrc/kgw_bgen.cu -- phased BGEN -> packed haplotype matrix on the device
+// (the step before the path, producer of Haplotypes::H).
+//
+// Replaces the data loop of BgenReader::read_worker (snpknock2/src/bgen_reader.cpp:139-261): the reference
+// walks the file variant by variant, std::find()s the rsid among the requested ones (O(p^2) string compares),
+// expands the probability block into vector<vector<double>> (one double per haplotype and allele), converts
+// with prob_to_hap (:48-63) and sets single bits of the haplotype-major chaplotype rows (:207-210).
+// Here the host only indexes the variant blocks and inflates the selected ones (zstd / zlib, host threads);
+// the uncompressed BGEN v1.2 "layout 2" probability blocks go to HBM as they are and one kernel decodes
+// and transposes them into the [2 n_samples][stride] bit matrix the sampler reads:
+//   block = N u32 | alleles u16 | min ploidy u8 | max ploidy u8 | N x (missing << 7 | ploidy) u8 |
+//           phased u8 | B u8 | 2N values of B bits (P(first allele) of haplotype 2s, 2s+1), little-endian bit stream
+//   prob_to_hap: P(first allele) == 1 -> bit 0;  == 0 -> bit 1;  anything else (or a missing sample) is
+//   "Incorrect input" in the reference (a throw that nothing catches) and an error status here.
+// HBM-bound byte work: per variant ~ (2 B/8 + 1) N bytes read, 2N/8 bytes written.
+#include "../../include/kgw.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+int kgw_fail_(int code, const std::string &msg);   // kgw_api.cu
+
+namespace {
+
+enum { BGEN_BAD_HEADER = 1, BGEN_BAD_PLOIDY = 2, BGEN_BAD_PROB = 4 };
+
+// One warp: 32 output haplotypes (lane = haplotype) x 128 output loci (4 words, one 16-byte store per lane).
+// Consecutive lanes read consecutive haplotype values of the same variant block (coalesced when the kept
+// samples are consecutive in the file, the usual case).
+__global__ void __launch_bounds__(256) bgen_unpack_kernel(const uint8_t *__restrict__ blocks, const long long *__restrict__ col_off,
+                                                          const int32_t *__restrict__ sample_idx, int n_samples_bgen, int n_haps,
+                                                          int p, int stride_w, uint32_t *__restrict__ Hw, int *__restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int hap = (blockIdx.y * 8 + warp) * 32 + lane;
+  const int w0 = blockIdx.x * 4;   // first 32-locus word of this warp's 128 loci
+  const bool live = hap < n_haps;
+  const int s_file = live ? sample_idx[hap >> 1] : 0;
+  const long long q = 2ll * s_file + (hap & 1);   // index of the haplotype's value in a block
+  int bad = 0;
+  uint32_t words[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int ww = 0; ww < 4; ww++) {
+    const int jbase = (w0 + ww) << 5;
+    if (jbase >= p) break;
+    const int jn = min(32, p - jbase);
+    uint32_t acc = 0;
+    for (int jj = 0; jj < jn; jj++) {
+      const uint8_t *blk = blocks + col_off[jbase + jj];
+      // block header (same for every lane: broadcast loads)
+      const uint32_t nfile = (uint32_t)blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+      const uint32_t nall = (uint32_t)blk[4] | ((uint32_t)blk[5] << 8);
+      const uint32_t pmin = blk[6], pmax = blk[7];
+      const uint32_t phased = blk[8 + n_samples_bgen], B = blk[9 + n_samples_bgen];
+      if (nfile != (uint32_t)n_samples_bgen || nall != 2u || pmin != 2u || pmax != 2u || phased != 1u || B < 1u || B > 32u) {
+        bad |= BGEN_BAD_HEADER;
+        continue;
+      }
+      if (!live) continue;
+      if (blk[8 + s_file] != 2u) bad |= BGEN_BAD_PLOIDY;   // missing flag set or ploidy != 2
+      const uint8_t *pr = blk + 10 + n_samples_bgen;
+      uint32_t v;
+      if (B == 8u) {
+        v = pr[q];
+      } else {
+        const long long bit0 = q * (long long)B;
+        const uint8_t *b0 = pr + (bit0 >> 3);
+        const int sh = (int)(bit0 & 7);
+        const int nbytes = (sh + (int)B + 7) >> 3;   // <= 5
+        unsigned long long acc64 = 0;
+        for (int t = 0; t < nbytes; t++) acc64 |= (unsigned long long)b0[t] << (8 * t);
+        v = (uint32_t)((acc64 >> sh) & ((B == 32u) ? 0xffffffffull : ((1ull << B) - 1ull)));
+      }
+      const uint32_t ones = (B == 32u) ? 0xffffffffu : ((1u << B) - 1u);
+      if (v == 0u) acc |= 1u << jj;            // P(first allele) = 0 -> second allele -> bit 1
+      else if (v != ones) bad |= BGEN_BAD_PROB;
+    }
+    words[ww] = acc;
+  }
+  if (live) {
+    uint32_t *dst = Hw + (size_t)hap * stride_w + w0;
+    if (w0 + 4 <= stride_w) {
+      *reinterpret_cast<uint4 *>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+    } else {
+      for (int ww = 0; ww < 4 && w0 + ww < stride_w; ww++) dst[ww] = words[ww];
+    }
+  }
+  if (bad) atomicOr(status, bad);
+}
+
+// ---- host side: container walk and block decompression -------------------------------------------------
+typedef size_t (*zstd_decompress_fn)(void *, size_t, const void *, size_t);
+typedef unsigned (*zstd_iserror_fn)(size_t);
+typedef int (*zlib_uncompress_fn)(unsigned char *, unsigned long *, const unsigned char *, unsigned long);
+
+struct Codecs {
+  zstd_decompress_fn zstd = nullptr;
+  zstd_iserror_fn zstd_err = nullptr;
+  zlib_uncompress_fn zlib = nullptr;
+};
+
+Codecs &codecs() {
+  static Codecs c;
+  static std::atomic<bool> done{false};
+  if (!done.load()) {
+    if (void *h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_GLOBAL)) {
+      c.zstd = (zstd_decompress_fn)dlsym(h, "ZSTD_decompress");
+      c.zstd_err = (zstd_iserror_fn)dlsym(h, "ZSTD_isError");
+    }
+    if (void *h = dlopen("libz.so.1", RTLD_NOW | RTLD_GLOBAL)) c.zlib = (zlib_uncompress_fn)dlsym(h, "uncompress");
+    done.store(true);
+  }
+  return c;
+}
+
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+struct VariantBlock { int64_t data_off; int64_t comp_len; int64_t raw_len; };
+
+// header + variant identifying data (BGEN v1.2 spec); fills the probability-block index in file order
+int bgen_index(const uint8_t *f, int64_t nbytes, uint32_t *n_samples, uint32_t *compression, std::vector<VariantBlock> &out) {
+  if (nbytes < 24) return kgw_fail_(KGW_ERR_INVALID, "BGEN image shorter than its header");
+  const uint32_t offset = rd32(f), hlen = rd32(f + 4), M = rd32(f + 8), N = rd32(f + 12);
+  if (hlen < 20 || 4ll + hlen > nbytes || 4ll + offset > nbytes) return kgw_fail_(KGW_ERR_INVALID, "BGEN header lengths outside the file");
+  if (memcmp(f + 16, "bgen", 4) != 0 && rd32(f + 16) != 0u) return kgw_fail_(KGW_ERR_INVALID, "not a BGEN file (magic)");
+  const uint32_t flags = rd32(f + 4 + hlen - 4);
+  *compression = flags & 3u;
+  const uint32_t layout = (flags >> 2) & 15u;
+  if (layout != 2u) return kgw_fail_(KGW_ERR_UNSUPPORTED, "only BGEN layout 2 (v1.2) is built; the reference data and UK Biobank use it");
+  if (*compression > 2u) return kgw_fail_(KGW_ERR_INVALID, "unknown BGEN compression flag");
+  *n_samples = N;
+  out.resize(M);
+  int64_t pos = 4ll + offset;
+  for (uint32_t v = 0; v < M; v++) {
+    for (int t = 0; t < 3; t++) {   // variant id, rsid, chromosome
+      if (pos + 2 > nbytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+      pos += 2 + rd16(f + pos);
+    }
+    if (pos + 6 > nbytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+    const uint16_t nall = rd16(f + pos + 4);
+    pos += 6;
+    for (uint16_t a = 0; a < nall; a++) {
+      if (pos + 4 > nbytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+      pos += 4 + (int64_t)rd32(f + pos);
+    }
+    if (pos + 4 > nbytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+    const int64_t C = rd32(f + pos);
+    pos += 4;
+    if (pos + C > nbytes) return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block runs past the end of the file");
+    if (*compression == 0u) out[v] = {pos, C, C};
+    else {
+      if (C < 4) return kgw_fail_(KGW_ERR_INVALID, "BGEN compressed block shorter than its length field");
+      out[v] = {pos + 4, C - 4, (int64_t)rd32(f + pos)};
+    }
+    pos += C;
+  }
+  return KGW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t kgw_bgen_variant_count(const uint8_t *file, int64_t file_bytes, int32_t *n_variants, int32_t *n_samples) {
+  if (!file || file_bytes < 24) return kgw_fail_(KGW_ERR_INVALID, "BGEN image shorter than its header");
+  if (n_variants) *n_variants = (int32_t)rd32(file + 8);
+  if (n_samples) *n_samples = (int32_t)rd32(file + 12);
+  return KGW_OK;
+}
+
+int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples, const int32_t *sample_idx, int32_t p,
+                      const int32_t *variant_of_col, int32_t host_threads, int32_t device, int64_t row_bytes, uint8_t *H_out,
+                      float *kernel_ms) {
+  if (!file || !sample_idx || !variant_of_col || !H_out) return kgw_fail_(KGW_ERR_INVALID, "null argument");
+  if (n_samples < 1 || p < 1) return kgw_fail_(KGW_ERR_INVALID, "n_samples and p must be positive");
+  if (row_bytes < (p + 7) / 8) return kgw_fail_(KGW_ERR_INVALID, "row_bytes < ceil(p/8)");
+  uint32_t nfile = 0, compression = 0;
+  std::vector<VariantBlock> idx;
+  int rc = bgen_index(file, file_bytes, &nfile, &compression, idx);
+  if (rc != KGW_OK) return rc;
+  for (int i = 0; i < n_samples; i++)
+    if (sample_idx[i] < 0 || (uint32_t)sample_idx[i] >= nfile) return kgw_fail_(KGW_ERR_INVALID, "sample index outside the BGEN sample block");
+  std::vector<long long> col_off(p);
+  long long total = 0;
+  for (int j = 0; j < p; j++) {
+    const int v = variant_of_col[j];
+    if (v < 0 || (size_t)v >= idx.size()) return kgw_fail_(KGW_ERR_INVALID, "variant index outside the BGEN file");
+    if (idx[v].raw_len < 10 + (int64_t)nfile) return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block shorter than its header");
+    col_off[j] = total;
+    total += (idx[v].raw_len + 15) & ~15ll;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return kgw_fail_(KGW_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+#define KGW_CUDA_B(call)                                                                                     \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess) {                                                                                 \
+      cudaFreeHost(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus); \
+      return kgw_fail_(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+    }                                                                                                        \
+  } while (0)
+  uint8_t *stage = nullptr, *dblocks = nullptr;
+  long long *doff = nullptr;
+  int32_t *dsidx = nullptr;
+  uint32_t *dH = nullptr;
+  int *dstatus = nullptr;
+  KGW_CUDA_B(cudaSetDevice(device));
+  KGW_CUDA_B(cudaMallocHost(&stage, (size_t)total + 16));
+
+  // inflate the selected blocks (host threads; the reference does this inside genfile::bgen, one variant at a time)
+  const Codecs &cd = codecs();
+  if (compression == 2u && (!cd.zstd || !cd.zstd_err)) { cudaFreeHost(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zstd-compressed BGEN but libzstd.so.1 could not be loaded"); }
+  if (compression == 1u && !cd.zlib) { cudaFreeHost(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zlib-compressed BGEN but libz.so.1 could not be loaded"); }
+  int nt = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, std::min(p, 64)));
+  std::atomic<int> next{0}, failed{0};
+  auto worker = [&]() {
+    for (;;) {
+      const int j0 = next.fetch_add(64);
+      if (j0 >= p) break;
+      for (int j = j0; j < std::min(p, j0 + 64); j++) {
+        const VariantBlock &vb = idx[variant_of_col[j]];
+        uint8_t *dst = stage + col_off[j];
+        if (compression == 0u) memcpy(dst, file + vb.data_off, (size_t)vb.raw_len);
+        else if (compression == 2u) {
+          const size_t got = cd.zstd(dst, (size_t)vb.raw_len, file + vb.data_off, (size_t)vb.comp_len);
+          if (cd.zstd_err(got) || got != (size_t)vb.raw_len) failed.store(1);
+        } else {
+          unsigned long dl = (unsigned long)vb.raw_len;
+          if (cd.zlib(dst, &dl, file + vb.data_off, (unsigned long)vb.comp_len) != 0 || dl != (unsigned long)vb.raw_len) failed.store(1);
+        }
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+  }
+  if (failed.load()) { cudaFreeHost(stage); return kgw_fail_(KGW_ERR_INVALID, "a BGEN probability block did not decompress to its stated length"); }
+
+  const int n_haps = 2 * n_samples;
+  const int stride_w = (((p + 31) / 32) + 3) & ~3;   // rows padded to 16 bytes
+  KGW_CUDA_B(cudaMalloc(&dblocks, (size_t)total + 16));
+  KGW_CUDA_B(cudaMalloc(&doff, sizeof(long long) * p));
+  KGW_CUDA_B(cudaMalloc(&dsidx, sizeof(int32_t) * n_samples));
+  KGW_CUDA_B(cudaMalloc(&dH, sizeof(uint32_t) * (size_t)n_haps * stride_w));
+  KGW_CUDA_B(cudaMalloc(&dstatus, sizeof(int)));
+  KGW_CUDA_B(cudaMemcpy(dblocks, stage, (size_t)total, cudaMemcpyHostToDevice));
+  KGW_CUDA_B(cudaMemcpy(doff, col_off.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
+  KGW_CUDA_B(cudaMemcpy(dsidx, sample_idx, sizeof(int32_t) * n_samples, cudaMemcpyHostToDevice));
+  KGW_CUDA_B(cudaMemset(dstatus, 0, sizeof(int)));
+  cudaEvent_t e0, e1;
+  KGW_CUDA_B(cudaEventCreate(&e0));
+  KGW_CUDA_B(cudaEventCreate(&e1));
+  const dim3 grid((unsigned)((stride_w + 3) / 4), (unsigned)((n_haps + 255) / 256));
+  KGW_CUDA_B(cudaEventRecord(e0));
+  bgen_unpack_kernel<<<grid, 256>>>(dblocks, doff, dsidx, (int)nfile, n_haps, p, stride_w, dH, dstatus);
+  KGW_CUDA_B(cudaGetLastError());
+  KGW_CUDA_B(cudaEventRecord(e1));
+  KGW_CUDA_B(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (kernel_ms) *kernel_ms = ms;
+  int st = 0;
+  KGW_CUDA_B(cudaMemcpy(&st, dstatus, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st == 0)
+    KGW_CUDA_B(cudaMemcpy2D(H_out, (size_t)row_bytes, dH, sizeof(uint32_t) * (size_t)stride_w, (size_t)((p + 7) / 8), (size_t)n_haps,
+                            cudaMemcpyDeviceToHost));
+  cudaFreeHost(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus);
+#undef KGW_CUDA_B
+  if (st & BGEN_BAD_HEADER)
+    return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block is not phased diploid biallelic layout-2 data of the stated sample count");
+  if (st & (BGEN_BAD_PLOIDY | BGEN_BAD_PROB))
+    return kgw_fail_(KGW_ERR_INVALID, "Incorrect input: a haplotype probability is not exactly 0 or 1, or a sample is missing (bgen_reader.cpp:48-63)");
+  // bits of the last partial byte beyond p stay 0, as in chaplotype (chaplotype.cpp:25-29)
+  return KGW_OK;
+}
+
+}  // extern "C"

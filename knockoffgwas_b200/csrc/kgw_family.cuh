@@ -29,10 +29,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "kgw_device.cuh"
 
 #define KGW_FAM_MAXN 8   // members per family
 #define KGW_FAM_MAXNB 7  // neighbours of a node
+#ifndef KGW_FAM_MINB
+#define KGW_FAM_MINB 4   // resident CTAs of 4 warps per SM the register allocation aims at
+#endif
 
 struct KgwFamInterval {  // maximal run of loci over which neighbors[i][j] is constant (family_bp.cpp:41-61)
   int32_t j0, j1;        // inclusive
@@ -94,7 +98,14 @@ struct KgwFamParams {
   const double *injected_u;    // [N][3][p] or null
   int32_t *dbg_z, *dbg_zk;     // [members total][p] or null
   int32_t *status;             // 0 ok; -10 missing knockoff variants; -11 inconsistency on Zk
+  long long *phase_cycles;     // -DKGW_PHASES: [8] summed lane-0 clock64 deltas per phase, else null
 };
+
+#ifdef KGW_PHASES
+#define KGW_FAM_PHASE(idx) do { if (P.phase_cycles) { const long long t_ = clock64(); if (lane == 0) atomicAdd((unsigned long long *)&P.phase_cycles[idx], (unsigned long long)(t_ - fam_t0)); fam_t0 = clock64(); } } while (0)
+#else
+#define KGW_FAM_PHASE(idx) do { } while (0)
+#endif
 
 namespace kgw {
 
@@ -154,8 +165,10 @@ __device__ __forceinline__ int warp_choice(const double (&w)[SF], double u, int 
   return min(cnt, K - 1);
 }
 
-template <int SF>
-__global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ KgwFamParams P) {
+// SF: states per lane; UMU: mu is the same at every locus (init_hmm, knockoffs.cpp:1520) and node emissions
+// come from the shared-memory table, else they are formed per state with pow() as the reference does
+template <int SF, bool UMU>
+__global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_constant__ KgwFamParams P) {
   constexpr int KP = SF * 32;
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
   extern __shared__ __align__(16) unsigned char fam_smem[];
   double *tab = reinterpret_cast<double *>(fam_smem);                       // [8][256], shared by the CTA
   double *pm = tab + 8 * 256 + (size_t)wid * P.n_max * KP;                  // [n_max][KP] last message of each chain
-  if (P.uniform_mu) {
+  if (UMU) {
     for (int t = threadIdx.x; t < 8 * 256; t += blockDim.x) tab[t] = P.emtab[t];
   }
   __syncthreads();
@@ -189,6 +202,9 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
     const int32_t *ivs0 = P.iv_start + fd.mem_off + f;   // n+1 entries for this family
     const KgwFamRange *rngs = P.ranges + fd.rng_off;
     const int nrng = fd.n_rng;
+#ifdef KGW_PHASES
+    long long fam_t0 = clock64();
+#endif
 
     auto find_iv = [&](int i, int j) -> const KgwFamInterval * {
       const KgwFamInterval *iv = P.ivs + ivs0[i];
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
     };
     // emission of node (i, j) for state k (family_bp.cpp:437-454)
     auto emission_of = [&](unsigned pt, int j, int nn) -> double {
-      if (P.uniform_mu) return tab[nn * 256 + pt];
+      if (UMU) return tab[nn * 256 + pt];
       const double mu = P.loc[j].mu;
       double v = (pt & 1u) ? 1.0 - mu : mu;
       for (int t = 0; t < nn; t++) v *= ((pt >> (t + 1)) & 1u) ? 1.0 - mu : mu;
@@ -221,7 +237,14 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
           const int jlo = w << 5, jhi = min(jlo + 32, p);
           uint8_t *dst = pat_base + ((size_t)i * p + jlo) * K + k;
           while (ivj1 < jlo) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
-          if (ivj1 >= jhi - 1) {   // one neighbour list for the whole word
+          if (ivj1 >= jhi - 1 && ivnn <= 1) {   // one neighbour list for the whole word, pairs
+            const uint32_t m1 = (ivnn == 1) ? ~(rw ^ __ldg(P.Hw + (size_t)mem[iv->nb[0]] * P.stride_w + w)) : 0u;
+            for (int j = jlo; j < jhi; j++) {
+              const int q = j & 31;
+              *dst = (uint8_t)(((m0 >> q) & 1u) | (((m1 >> q) & 1u) << 1));
+              dst += K;
+            }
+          } else if (ivj1 >= jhi - 1) {   // one neighbour list for the whole word
             uint32_t mt[KGW_FAM_MAXNB];
 #pragma unroll
             for (int t = 0; t < KGW_FAM_MAXNB; t++)
@@ -250,116 +273,199 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
       }
     }
     __syncwarp();
+    KGW_FAM_PHASE(0);
 
     // One direction of one BP iteration (family_bp.cpp:341-405 and the message formulas :429-559):
     // dir 0 = right (writes messages_right[i][j], j = 0 .. p-2), 1 = left (messages_left[i][j], j = p-1 .. 1).
     // `full`: first iteration of the first run_bp -- every node is computed and the "old" value of every
     // message (also of the left messages read at a junction by the first right sweep) is 1/K.
+    // The sweep alternates between the special ranges (locus by locus, members in order, junction terms,
+    // pinned nodes) and the plain stretches between them.  In a plain stretch every node depends on its own
+    // chain only, so the members are taken one after the other with the running message in registers; a
+    // chain is followed only while its message changes bits (or everywhere when `full`).
     // Returns this lane's share of sum |new - old|.
-    auto sweep = [&](const int dir, const bool full) -> double {
+    auto sweep = [&](auto dir_tag, const bool full) -> double {
+      constexpr int dir = decltype(dir_tag)::value;
       double diff = 0.0;
-      unsigned comp_prev = 0, chg_prev = 0;   // members whose message one locus back was computed / changed bits in this sweep
-      int r = (dir == 0) ? 0 : nrng - 1;      // first special range not yet behind the sweep
-      int rs0, rs1;
-      if (dir == 0) { if (r < nrng) { rs0 = rngs[r].s0; rs1 = rngs[r].s1; } else { rs0 = rs1 = 0x7fffffff; } }
-      else { if (r >= 0) { rs0 = rngs[r].s0; rs1 = rngs[r].s1; } else { rs0 = rs1 = -1; } }
+      unsigned comp_prev = 0, chg_prev = 0;   // members whose message one locus back was computed (value in pm) / changed bits in this sweep
+      constexpr int step = (dir == 0) ? 1 : -1;
+      const int jlast = (dir == 0) ? p - 2 : 1;   // last locus of the sweep
       int j = (dir == 0) ? 0 : p - 1;
-      const int step = (dir == 0) ? 1 : -1;
       unsigned nnpack = 0;                    // neighbour count of every member at the current locus, 3 bits each
       for (int i = 0; i < n; i++) nnpack |= (unsigned)find_iv(i, j)->nn << (3 * i);
       double *dstb = (dir == 0) ? mr_base : ml_base;
-      while (dir == 0 ? (j < p - 1) : (j > 0)) {
-        if (dir == 0) {
-          while (j > rs1) { r++; if (r < nrng) { rs0 = rngs[r].s0; rs1 = rngs[r].s1; } else { rs0 = rs1 = 0x7fffffff; } }
-        } else {
-          while (j < rs0) { r--; if (r >= 0) { rs0 = rngs[r].s0; rs1 = rngs[r].s1; } else { rs0 = rs1 = -1; } }
+      bool valid[SF];
+#pragma unroll
+      for (int s = 0; s < SF; s++) valid[s] = (s * 32 + lane < K);
+
+      for (int rr = 0; rr <= nrng; rr++) {
+        int s_first = 0, s_last = -1;
+        if (rr < nrng) {
+          const KgwFamRange rg = rngs[dir == 0 ? rr : nrng - 1 - rr];
+          s_first = (dir == 0) ? rg.s0 : rg.s1;
+          s_last = (dir == 0) ? rg.s1 : rg.s0;
         }
-        const bool special = (j >= rs0 && j <= rs1);
-        if (!full && !special && chg_prev == 0) {   // nothing can change before the next special range
-          if (dir == 0) { if (rs0 == 0x7fffffff) break; j = rs0; }
-          else { if (rs1 < 0) break; j = rs1; }
-          comp_prev = 0;
-          continue;
+        // ---- plain stretch j .. e (sweep order)
+        int e = (rr < nrng) ? s_first - step : jlast;
+        if (dir == 0 ? (e > jlast) : (e < jlast)) e = jlast;
+        const int len = (e - j) * step + 1;
+        if (len > 0) {
+          const unsigned todo = full ? ((1u << n) - 1u) : chg_prev;
+          unsigned comp_new = 0, chg_new = 0;
+          for (int i = 0; i < n; i++) {
+            if (!((todo >> i) & 1u)) continue;
+            const int nn = (int)((nnpack >> (3 * i)) & 7u);
+            const size_t rowo = ((size_t)i * p + j) * K + lane;
+            const ptrdiff_t sK = (ptrdiff_t)step * K;
+            const uint8_t *pp = pat_base + rowo;
+            double *dp = dstb + rowo;
+            const KgwFamLocus *lp = P.loc + (dir == 0 ? j + 1 : j);
+            bool hasv = (dir == 0) ? (j > 0) : (j < p - 1);
+            double v[SF];
+            unsigned ptc[SF];
+#pragma unroll
+            for (int s = 0; s < SF; s++) {
+              v[s] = 0.0;
+              if (valid[s] && hasv) v[s] = ((comp_prev >> i) & 1u) ? pm[i * KP + s * 32 + lane] : dp[s * 32 - sK];
+              ptc[s] = valid[s] ? pp[s * 32] : 0u;
+            }
+            double la = lp->a_bp, lb = lp->b;
+            bool ch = true;
+            int t = 0;
+            for (; t < len; t++) {
+              // fetches for the next locus of this chain, and L2 prefetches further ahead
+              unsigned ptn[SF];
+              double oldv[SF];
+              const bool more = (t + 1 < len);
+#pragma unroll
+              for (int s = 0; s < SF; s++) {
+                ptn[s] = (valid[s] && more) ? pp[sK + s * 32] : 0u;
+                oldv[s] = (valid[s] && !full) ? dp[s * 32] : (valid[s] ? p0 : 0.0);
+              }
+              const double lan = more ? lp[step].a_bp : 0.0, lbn = more ? lp[step].b : 0.0;
+              if ((t & 3) == 0 && t + 12 < len) {   // rows t+8 .. t+11 of this chain (contiguous in memory)
+                fam_prefetch(pp + (dir == 0 ? 8 : 11) * sK - lane, 4 * K, lane);
+                if (!full) fam_prefetch(dp + (dir == 0 ? 8 : 11) * sK - lane, 32 * K, lane);
+              }
+              double mm[SF];
+              double csum = 0.0, msum = 0.0;
+#pragma unroll
+              for (int s = 0; s < SF; s++) {
+                mm[s] = 0.0;
+                if (valid[s]) {
+                  const double fk = emission_of(ptc[s], j + t * step, nn);
+                  double c = la * fk, m = lb * fk;
+                  if (hasv) { c *= v[s]; m *= v[s]; }
+                  csum += c;
+                  msum += m;
+                  mm[s] = m;
+                }
+              }
+              warp_sum2(csum, msum);
+              const double inv = 1.0 / ((double)K * csum + msum);   // sum_k (const_msg + msg_k)
+              bool ne = false;
+#pragma unroll
+              for (int s = 0; s < SF; s++) {
+                if (valid[s]) {
+                  const double nv = (csum + mm[s]) * inv;
+                  diff += fabs(nv - oldv[s]);
+                  ne |= (nv != oldv[s]);
+                  v[s] = nv;
+                }
+              }
+              ch = __any_sync(FULL, ne);
+              if (full || ch) {
+#pragma unroll
+                for (int s = 0; s < SF; s++) if (valid[s]) dp[s * 32] = v[s];
+              }
+              hasv = true;
+              pp += sK;
+              dp += sK;
+              lp += step;
+              la = lan;
+              lb = lbn;
+#pragma unroll
+              for (int s = 0; s < SF; s++) ptc[s] = ptn[s];
+              if (!full && !ch) { t++; break; }   // bit-identical message: everything further along this chain is clean
+            }
+            if (t == len) {   // the chain reached the end of the stretch: hand its last message to the next range
+#pragma unroll
+              for (int s = 0; s < SF; s++) if (valid[s]) pm[i * KP + s * 32 + lane] = v[s];
+              comp_new |= 1u << i;
+              if (ch) chg_new |= 1u << i;
+            }
+          }
+          comp_prev = comp_new;
+          chg_prev = chg_new;
+          j = e + step;
         }
-        const KgwFamLocus lc = P.loc[dir == 0 ? j + 1 : j];
-        const bool has_prev = (dir == 0) ? (j > 0) : (j < p - 1);
-        unsigned comp_cur = 0, chg_cur = 0;
-        for (int i = 0; i < n; i++) {
-          int nn, ndl = 0, ndr = 0;
-          const KgwFamInterval *iv = nullptr;
-          if (special) {
-            iv = find_iv(i, j);
-            nn = iv->nn;
+        if (rr == nrng) break;
+        // ---- special range s_first .. s_last, locus by locus
+        for (; (dir == 0) ? (j <= s_last && j <= jlast) : (j >= s_last && j >= jlast); j += step) {
+          const KgwFamLocus lc = P.loc[dir == 0 ? j + 1 : j];
+          const bool has_prev = (dir == 0) ? (j > 0) : (j < p - 1);
+          unsigned comp_cur = 0, chg_cur = 0;
+          for (int i = 0; i < n; i++) {
+            const KgwFamInterval *iv = find_iv(i, j);
+            const int nn = iv->nn;
             nnpack = (nnpack & ~(7u << (3 * i))) | ((unsigned)nn << (3 * i));
             if (Zb[(size_t)i * p + j] != 255) continue;   // pinned by condition_on: inactive node
-            if (j == iv->j0 && j > 0) ndl = iv->ndl;
-            if (j == iv->j1 && j < p - 1) ndr = iv->ndr;
-          } else {
-            if (!full && !((chg_prev >> i) & 1u)) continue;
-            nn = (int)((nnpack >> (3 * i)) & 7u);
-          }
-          const size_t rowo = ((size_t)i * p + j) * K;
-          const double *prevg = dstb + rowo - (ptrdiff_t)step * K;   // own chain, one locus back in sweep order
-          if ((unsigned)(j + 8 * step) < (unsigned)p) {              // rows this chain needs eight loci further on
-            const ptrdiff_t ahead = (ptrdiff_t)step * 8 * K;
-            fam_prefetch(pat_base + rowo + ahead, K, lane);
-            if (!full) fam_prefetch(dstb + rowo + ahead, 8 * K, lane);
-          }
-          const bool prev_sm = (comp_prev >> i) & 1u;
-          double cst[SF], msg[SF], oldv[SF];
-          double csum = 0.0, msum = 0.0;
+            const int ndl = (j == iv->j0 && j > 0) ? iv->ndl : 0;
+            const int ndr = (j == iv->j1 && j < p - 1) ? iv->ndr : 0;
+            const size_t rowo = ((size_t)i * p + j) * K;
+            const double *prevg = dstb + rowo - (ptrdiff_t)step * K;   // own chain, one locus back in sweep order
+            const bool prev_sm = (comp_prev >> i) & 1u;
+            double msg[SF], oldv[SF];
+            double csum = 0.0, msum = 0.0;
 #pragma unroll
-          for (int s = 0; s < SF; s++) {
-            const int k = s * 32 + lane;
-            cst[s] = 0.0;
-            msg[s] = 0.0;
-            oldv[s] = 0.0;
-            if (k < K) {
-              const double fk = emission_of(pat_base[rowo + k], j, nn);
-              oldv[s] = full ? p0 : dstb[rowo + k];
-              double c = lc.a_bp * fk, m = lc.b * fk;
-              if (has_prev) { const double v = prev_sm ? pm[i * KP + k] : prevg[k]; c *= v; m *= v; }
-              if (dir == 0) {
-                for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
-                for (int t = 0; t < ndr; t++) { const double v = full ? p0 : ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
-              } else {
-                for (int t = 0; t < ndr; t++) { const double v = ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
-                for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
+            for (int s = 0; s < SF; s++) {
+              const int k = s * 32 + lane;
+              msg[s] = 0.0;
+              oldv[s] = 0.0;
+              if (k < K) {
+                const double fk = emission_of(pat_base[rowo + k], j, nn);
+                oldv[s] = full ? p0 : dstb[rowo + k];
+                double c = lc.a_bp * fk, m = lc.b * fk;
+                if (has_prev) { const double v = prev_sm ? pm[i * KP + k] : prevg[k]; c *= v; m *= v; }
+                if (dir == 0) {
+                  for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
+                  for (int t = 0; t < ndr; t++) { const double v = full ? p0 : ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
+                } else {
+                  for (int t = 0; t < ndr; t++) { const double v = ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
+                  for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
+                }
+                msg[s] = m;
+                csum += c;
+                msum += m;
               }
-              cst[s] = c;
-              msg[s] = m;
-              csum += c;
-              msum += m;
             }
-          }
-          warp_sum2(csum, msum);
-          const double const_msg = csum;
-          const double inv = 1.0 / ((double)K * const_msg + msum);   // sum_k (const_msg + msg_k)
-          bool ne = false;
+            warp_sum2(csum, msum);
+            const double inv = 1.0 / ((double)K * csum + msum);   // sum_k (const_msg + msg_k)
+            bool ne = false;
 #pragma unroll
-          for (int s = 0; s < SF; s++) {
-            if (s * 32 + lane < K) {
-              const double v = (const_msg + msg[s]) * inv;
-              diff += fabs(v - oldv[s]);
-              ne |= (v != oldv[s]);
-              msg[s] = v;
+            for (int s = 0; s < SF; s++) {
+              if (s * 32 + lane < K) {
+                const double nv = (csum + msg[s]) * inv;
+                diff += fabs(nv - oldv[s]);
+                ne |= (nv != oldv[s]);
+                msg[s] = nv;
+              }
             }
-          }
-          const bool ch = __any_sync(FULL, ne);
+            const bool ch = __any_sync(FULL, ne);
 #pragma unroll
-          for (int s = 0; s < SF; s++) {
-            const int k = s * 32 + lane;
-            if (k < K) {
-              if (full || ch) dstb[rowo + k] = msg[s];
-              pm[i * KP + k] = msg[s];
+            for (int s = 0; s < SF; s++) {
+              const int k = s * 32 + lane;
+              if (k < K) {
+                if (full || ch) dstb[rowo + k] = msg[s];
+                pm[i * KP + k] = msg[s];
+              }
             }
+            comp_cur |= 1u << i;
+            if (ch) chg_cur |= 1u << i;
           }
-          comp_cur |= 1u << i;
-          if (ch) chg_cur |= 1u << i;
+          comp_prev = comp_cur;
+          chg_prev = chg_cur;
         }
-        comp_prev = comp_cur;
-        chg_prev = chg_cur;
-        j += step;
       }
       return diff;
     };
@@ -369,7 +475,9 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
       for (int it = 0; it < 20; it++) {
         double diff = 0.0;
         for (int dir = 0; dir < 2; dir++) {
-          double dt = sweep(dir, first && it == 0);
+          double dt = (dir == 0) ? sweep(std::integral_constant<int, 0>{}, first && it == 0)
+                                 : sweep(std::integral_constant<int, 1>{}, first && it == 0);
+          KGW_FAM_PHASE((first && it == 0) ? 1 : 2);
           dt = warp_sum(dt) / (double)((size_t)p * (size_t)n);
           diff += dt;
         }
@@ -433,6 +541,7 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
           condition_on(i, j, kz);
           for (int t = 0; t < iv->nn; t++) condition_on(iv->nb[t], j, kz);
           __syncwarp();
+          KGW_FAM_PHASE(3);
           run_bp(false);
         }
       }
@@ -451,6 +560,7 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
       const double *mlrow = ml_base + (size_t)i * pK;
       const uint8_t *ptrow = pat_base + (size_t)i * pK;
       int zprev = 0;
+      double la_c = P.loc[0].a_al, lb_c = P.loc[0].b;
       double ml_c[SF];
       unsigned pt_c[SF];
 #pragma unroll
@@ -462,6 +572,7 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
       for (int w = 0; w <= (p - 1) >> 5; w++) {
         const int jw = (w << 5) + lane;
         const int zw = (jw < p) ? zrow[jw] : 0;
+        const double uw = (jw < p) ? fam_uniform(P, mem[i], STREAM_Z, jw) : 0.0;   // lane q holds the uniform of locus 32 w + q
         const int jhi = min(32, p - (w << 5));
         for (int q = 0; q < jhi; q++) {
           const int j = (w << 5) + q;
@@ -473,9 +584,10 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
             pt_n[s] = (k < K && j + 1 < p) ? ptrow[(size_t)(j + 1) * K + k] : 0u;
             ml_n[s] = (k < K && j + 2 < p) ? mlrow[(size_t)(j + 2) * K + k] : 1.0;
           }
-          if (j + 10 < p) {
-            fam_prefetch(ptrow + (size_t)(j + 9) * K, K, lane);
-            fam_prefetch(mlrow + (size_t)(j + 10) * K, 8 * K, lane);
+          const double la_n = (j + 1 < p) ? P.loc[j + 1].a_al : 0.0, lb_n = (j + 1 < p) ? P.loc[j + 1].b : 0.0;
+          if ((q & 3) == 0 && j + 14 < p) {
+            fam_prefetch(ptrow + (size_t)(j + 9) * K, 4 * K, lane);
+            fam_prefetch(mlrow + (size_t)(j + 10) * K, 32 * K, lane);
           }
           const int zj = __shfl_sync(FULL, zw, q);
           if (zj != 255) {
@@ -488,7 +600,6 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
               nbpack = 0;
               for (int t = 0; t < ivnn; t++) nbpack |= (unsigned)iv->nb[t] << (3 * t);
             }
-            const KgwFamLocus lc = P.loc[j];
             double wv[SF];
 #pragma unroll
             for (int s = 0; s < SF; s++) {
@@ -496,12 +607,12 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
               wv[s] = 0.0;
               if (k < K) {
                 double v = emission_of(pt_c[s], j, ivnn);
-                if (j > 0) v *= lc.a_al + lc.b * (double)(k == zprev);
+                if (j > 0) v *= la_c + lb_c * (double)(k == zprev);
                 if (j < p - 1) v *= ml_c[s];
                 wv[s] = v;
               }
             }
-            const int kz = warp_choice<SF>(wv, fam_uniform(P, mem[i], STREAM_Z, j), K, lane);
+            const int kz = warp_choice<SF>(wv, __shfl_sync(FULL, uw, q), K, lane);
             if (lane == 0) {
               Zb[(size_t)i * p + j] = (uint8_t)kz;
               for (int t = 0; t < ivnn; t++) Zb[(size_t)((nbpack >> (3 * t)) & 7u) * p + j] = (uint8_t)kz;
@@ -510,11 +621,14 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
           }
 #pragma unroll
           for (int s = 0; s < SF; s++) { pt_c[s] = pt_n[s]; ml_c[s] = ml_n[s]; }
+          la_c = la_n;
+          lb_c = lb_n;
         }
       }
       __syncwarp();
     }
 
+    KGW_FAM_PHASE(4);
     // ---- FamilyKnockoffs::run (family_knockoffs.cpp:77-293) as a flat op list
     const KgwFamOp *ops = P.ops + fd.op_off;
     for (int q = 0; q < fd.n_ops; q++) {
@@ -528,10 +642,14 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
         const int i = op.i, g_begin = op.a, g_end = op.b;
         const uint8_t *z = Zb + (size_t)i * p;
         uint8_t *zk = Zkb + (size_t)i * p;
-        double Nv[SF], No[SF];
+        // N_old enters only through 1/N_old: its reciprocal is formed once per group and multiplied in
+        // (x * (1/y) instead of x / y moves a weight by an ulp, see DESIGN.md "Arithmetic vs the reference")
+        double Nv[SF], rNo[SF];
 #pragma unroll
-        for (int s = 0; s < SF; s++) { Nv[s] = 1.0; No[s] = 1.0; }
-        int zk_last = (g_begin > 0) ? zk[P.grp_first[g_begin] - 1] : 0;   // zk of the locus before the range
+        for (int s = 0; s < SF; s++) { Nv[s] = 1.0; rNo[s] = 1.0; }
+        int zk_last = 0;
+        int uw_word = -1;
+        double uw = 0.0;   // lane q holds the uniform of locus 32 uw_word + q
         for (int g = g_begin; g <= g_end; g++) {
           const int e0 = P.grp_first[g], e1 = P.grp_last[g];
           const KgwLocusKO k0v = P.ko[e0];
@@ -550,8 +668,8 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
               tmp = (k == z0) ? k0v.apb : k0v.a;
               if (g != g_begin) tmp = tmp * ((k == z0k) ? k0v.apb : k0v.a);
             }
-            tq[s] = tmp;
-            if (k < K) part += (g == 0) ? tmp : tmp / No[s];
+            tq[s] = (g == 0) ? tmp : tmp * rNo[s];   // T_k / N_old[k]
+            if (k < K) part += tq[s];
           }
           const double N_sum = warp_sum(part);
           double nn_part = 0.0;
@@ -560,41 +678,47 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
             const int k = s * 32 + lane;
             if (!lastg) {
               Nv[s] += k0v.vb * N_sum;
-              Nv[s] += (g == 0) ? (k0v.vs * tq[s]) : (k0v.vs * tq[s] / No[s]);   // vstar[0] == vs of the first locus
+              Nv[s] += k0v.vs * tq[s];   // vstar[0] == vs of the first locus
             }
             if (Nv[s] < N_MIN) Nv[s] = N_MIN;
             if (k < K) nn_part += Nv[s];
           }
-          const double N_norm = warp_sum(nn_part);
+          const double r_norm = 1.0 / warp_sum(nn_part);
 #pragma unroll
           for (int s = 0; s < SF; s++) {
-            Nv[s] /= N_norm;
+            Nv[s] *= r_norm;
             if (Nv[s] < N_MIN) Nv[s] = N_MIN;
           }
           int zkprev = 0;
           for (int j = e0; j <= e1; j++) {
             const KgwLocusKO kv = P.ko[j];
+            if ((j >> 5) != uw_word) {
+              uw_word = j >> 5;
+              const int jl = (uw_word << 5) + lane;
+              uw = (jl < p) ? fam_uniform(P, mem[i], STREAM_ZK, jl) : 0.0;
+            }
             double w[SF];
 #pragma unroll
             for (int s = 0; s < SF; s++) {
               const int k = s * 32 + lane;
               double wk;
               if (j > e0) wk = (k == zkprev) ? kv.apb : kv.a;
-              else wk = tq[s] / No[s];
+              else wk = (g == 0) ? tq[s] * rNo[s] : tq[s];
               wk *= lastg ? kv.vb : (kv.vb + kv.vs * (double)(k == z1));
               w[s] = (k < K) ? wk : 0.0;
             }
-            zkprev = warp_choice<SF>(w, fam_uniform(P, mem[i], STREAM_ZK, j), K, lane);
+            zkprev = warp_choice<SF>(w, __shfl_sync(FULL, uw, j & 31), K, lane);
             if (lane == 0) zk[j] = (uint8_t)zkprev;
           }
           zk_last = zkprev;
 #pragma unroll
-          for (int s = 0; s < SF; s++) No[s] = Nv[s];
+          for (int s = 0; s < SF; s++) rNo[s] = 1.0 / Nv[s];
         }
       }
       __syncwarp();
     }
 
+    KGW_FAM_PHASE(5);
     // ---- the reference's final checks (family_knockoffs.cpp:272-291)
     int bad = 0;
     for (int i = 0; i < n; i++) {
@@ -640,6 +764,7 @@ __global__ void __launch_bounds__(128, 4) family_kernel(const __grid_constant__ 
       }
     }
     __syncwarp();
+    KGW_FAM_PHASE(6);
   }
 }
 

@@ -459,3 +459,110 @@ def family_labels(families) -> np.ndarray:
     """haplotype -> label shared within metadata.related_families[i] (the smallest member), -1 for singletons."""
     return np.array([min(int(x) for x in f) if len(f) > 1 else -1 for f in families], dtype=np.int32)
 
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Phased BGEN -> haplotype matrix (SURVEY.md 8f rank 4).  Restates BgenReader::read_worker / prob_to_hap
+# (snpknock2/src/bgen_reader.cpp:48-63, 139-261) on top of the BGEN v1.2 container (layout 2): the genfile::bgen
+# library the reference links is vendored there (snpknock2/include/bgen); its read_probs() hands prob_to_hap, per
+# sample, [P(h1 = first allele), P(h1 = second), P(h2 = first), P(h2 = second)] with P = stored / (2^B - 1).
+def _zstd_decompress(buf: bytes, raw_len: int) -> bytes:
+    z = C.CDLL("libzstd.so.1")
+    z.ZSTD_decompress.restype = C.c_size_t
+    z.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    out = C.create_string_buffer(raw_len)
+    got = z.ZSTD_decompress(out, raw_len, buf, len(buf))
+    if got != raw_len:
+        raise ValueError("zstd block did not inflate to its stated length")
+    return out.raw
+
+
+def bgen_variants(image: bytes):
+    """[(rsid, raw probability block bytes)] in file order."""
+    import struct
+    import zlib
+    d = bytes(image)
+    offset, hlen, M, N = struct.unpack_from("<IIII", d, 0)
+    (flags,) = struct.unpack_from("<I", d, 4 + hlen - 4)
+    comp, layout = flags & 3, (flags >> 2) & 15
+    if layout != 2:
+        raise ValueError("layout 2 only")
+    out, pos = [], 4 + offset
+    for _ in range(M):
+        (l,) = struct.unpack_from("<H", d, pos); pos += 2 + l
+        (l,) = struct.unpack_from("<H", d, pos); rsid = d[pos + 2:pos + 2 + l].decode(); pos += 2 + l
+        (l,) = struct.unpack_from("<H", d, pos); pos += 2 + l
+        (_, nall) = struct.unpack_from("<IH", d, pos); pos += 6
+        for _a in range(nall):
+            (l,) = struct.unpack_from("<I", d, pos); pos += 4 + l
+        (c,) = struct.unpack_from("<I", d, pos); pos += 4
+        if comp == 0:
+            raw = d[pos:pos + c]
+        else:
+            (dl,) = struct.unpack_from("<I", d, pos)
+            blk = d[pos + 4:pos + c]
+            raw = zlib.decompress(blk) if comp == 1 else _zstd_decompress(blk, dl)
+            if len(raw) != dl:
+                raise ValueError("block length mismatch")
+        pos += c
+        out.append((rsid, raw))
+    return out, N
+
+
+def bgen_read(image, sample_idx, variant_of_col) -> np.ndarray:
+    """uint8 [2 len(sample_idx)][ceil(p/8)]: H[2i + a][j] = prob_to_hap of haplotype a of file sample
+    sample_idx[i] at file variant variant_of_col[j]; raises ValueError("Incorrect input") where the reference
+    throws (probability not exactly 0 / 1, missing sample)."""
+    import struct
+    variants, N = bgen_variants(image)
+    sample_idx = np.asarray(sample_idx, dtype=np.int64)
+    p = len(variant_of_col)
+    bits = np.zeros((2 * len(sample_idx), p), dtype=np.uint8)
+    for j, v in enumerate(variant_of_col):
+        raw = variants[int(v)][1]
+        n, nall, pmin, pmax = struct.unpack_from("<IHBB", raw, 0)
+        ploidy = np.frombuffer(raw, dtype=np.uint8, count=n, offset=8)
+        phased, B = raw[8 + n], raw[9 + n]
+        if n != N or nall != 2 or pmin != 2 or pmax != 2 or phased != 1 or not (1 <= B <= 32):
+            raise ValueError("not phased diploid biallelic data")
+        stream = np.unpackbits(np.frombuffer(raw, dtype=np.uint8, offset=10 + n), bitorder="little")
+        vals = stream[:2 * n * B].reshape(2 * n, B).astype(np.uint64)
+        vals = (vals << np.arange(B, dtype=np.uint64)).sum(axis=1)          # little-endian bit stream, B bits each
+        ones = np.uint64((1 << B) - 1)
+        for a in (0, 1):
+            q = vals[2 * sample_idx + a]
+            if np.any(ploidy[sample_idx] != 2) or np.any((q != 0) & (q != ones)):
+                raise ValueError("Incorrect input")                            # bgen_reader.cpp:54-60
+            bits[2 * np.arange(len(sample_idx)) + a, j] = (q == 0)            # P(first allele) == 0 -> second allele -> 1
+    return pack_bits(bits)
+
+
+def bgen_write(bits: np.ndarray, rsids, B: int = 8, compression: int = 1, missing=None, bad_prob=None) -> bytes:
+    """Synthetic phased BGEN v1.2 image (layout 2) for tests: bits uint8 [2 n][p]; compression 0 none / 1 zlib;
+    `missing` = (sample, variant) flagged missing, `bad_prob` = (haplotype, variant) given probability 1/2."""
+    import struct
+    import zlib
+    nh, p = bits.shape
+    n = nh // 2
+    body = b""
+    for j in range(p):
+        vals = np.where(bits[:, j] == 0, (1 << B) - 1, 0).astype(np.uint64)
+        if bad_prob is not None and bad_prob[1] == j:
+            vals[bad_prob[0]] = (1 << B) // 2
+        ploidy = np.full(n, 2, dtype=np.uint8)
+        if missing is not None and missing[1] == j:
+            ploidy[missing[0]] = 0x82
+            vals[2 * missing[0]:2 * missing[0] + 2] = 0
+        st = ((vals[:, None] >> np.arange(B, dtype=np.uint64)) & np.uint64(1)).astype(np.uint8).reshape(-1)
+        raw = struct.pack("<IHBB", n, 2, 2, 2) + ploidy.tobytes() + bytes([1, B]) + np.packbits(st, bitorder="little").tobytes()
+        ident = b"".join(struct.pack("<H", len(x)) + x for x in (b"", rsids[j].encode(), b"22"))
+        ident += struct.pack("<IH", 1000 + j, 2) + struct.pack("<I", 1) + b"A" + struct.pack("<I", 1) + b"G"
+        if compression == 0:
+            blk = struct.pack("<I", len(raw)) + raw
+        else:
+            z = zlib.compress(raw)
+            blk = struct.pack("<II", len(z) + 4, len(raw)) + z
+        body += ident + blk
+    flags = compression | (2 << 2)
+    header = struct.pack("<III", 20, p, n) + b"bgen" + struct.pack("<I", flags)
+    return struct.pack("<I", 20) + header + body

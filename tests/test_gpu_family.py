@@ -83,3 +83,30 @@ def test_family_errors():
     with pytest.raises(kg.KgwError):   # a segment listing haplotypes outside its family
         kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, ref_global=prob.ref_global,
                     families=bad)
+
+
+def _synthetic_pairs(n_haps, p, K, pairs, mean_group=1.0, seed=3):
+    from knockoffgwas_b200 import synth
+    sp = synth.make_problem(n_haps, p, K, seed=seed, n_founders=60, mean_group=mean_group)
+    synth.add_ibd_pairs(sp, pairs)
+    prob = ko.Problem(H=sp.H, p=p, K=K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu,
+                      groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
+    return sp, prob
+
+
+@pytest.mark.parametrize("K,mean_group", [(50, 1.0), (100, 4.0), (20, 1.0)])
+def test_family_kernel_synthetic_pairs(K, mean_group):
+    """Synthetic RaPID-style pairs (1-3 segments, SURVEY.md 8d C5 recipe), more families than resident warps'
+    worth of work per CTA: Z, Zk and Hk of every family equal the oracle's.  Exercises the exact work skipping
+    of the BP sweeps on chromosomes long enough for the perturbations to die out."""
+    sp, prob = _synthetic_pairs(600, 3000, K, 24, mean_group)
+    hk, dbg = kg.generate(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=np.zeros(0, np.int32),
+                          ref_global=sp.ref, seed=sp.seed, families=sp.families, debug_paths=True)
+    rng, _ = ko.make_rng(prob, mode="philox")
+    row = 0
+    for mem, segs in sp.families:
+        r = ko.run_family(prob, mem, [(s[0], s[1], 0, 0, s[2]) for s in segs], rng)
+        assert np.array_equal(dbg.fam_z[row:row + 2], r.z), f"Z of pair {mem.tolist()}"
+        assert np.array_equal(dbg.fam_zk[row:row + 2], r.zk), f"Zk of pair {mem.tolist()}"
+        assert np.array_equal(hk[mem], r.hk), f"Hk of pair {mem.tolist()}"
+        row += 2
