@@ -395,6 +395,25 @@ def run_b200_arm(a, rank, local_rank, world):
         except Exception as e:
             line["reference_selection"] = {"error": repr(e)[:200]}
 
+    # ---- the producer of H (outside the timed step): phased BGEN image of the benchmark's own population ->
+    # packed haplotype matrix (kgw_bgen_read replaces the loop of BgenReader::read_worker, bgen_reader.cpp:139-261)
+    if rank == 0 and world == 1 and not a.no_e2e:
+        try:
+            image = synth.write_bgen_image(prob.H, p, compression=0)
+            sidx, vcol = np.arange(N // 2, dtype=np.int32), np.arange(p, dtype=np.int32)
+            kg.read_bgen_image(image, sidx, vcol)                          # warm-up
+            t0 = time.perf_counter()
+            Hb, bg_ms = kg.read_bgen_image(image, sidx, vcol, return_ms=True)
+            bg_wall = time.perf_counter() - t0
+            blk_bytes = p * (10 + N // 2 + N)
+            line["bgen_ingest"] = {"kernel_ms": bg_ms, "call_ms": bg_wall * 1e3, "identical_to_H": bool(np.array_equal(Hb, prob.H)),
+                                   "block_bytes": int(blk_bytes), "output_bytes": int(Hb.nbytes),
+                                   "kernel_GBps": (blk_bytes + Hb.nbytes) / (bg_ms * 1e-3) / 1e9 if bg_ms > 0 else None,
+                                   "note": "uncompressed layout-2 blocks, 8-bit probabilities; call = index + staging + H2D + kernel + D2H; "
+                                           "not part of `value`"}
+        except Exception as e:
+            line["bgen_ingest"] = {"error": repr(e)[:200]}
+
     # ---- the IBD-conditioned branch of the same generate() call (generate_related, knockoffs.cpp:329-571) on
     # synthetic related pairs (SURVEY.md 8d C5 recipe) drawn inside the same population; reported beside `value`
     if rank == 0 and world == 1 and not a.no_e2e and a.related_pairs > 0:

@@ -145,3 +145,29 @@ def add_ibd_pairs(prob: SynthProblem, n_pairs: int, seed: int = 5, mean_len_cm: 
         fams.append((ids, [(j0, j1, ids) for j0, j1 in segs]))
     prob.families = fams
     return prob
+
+
+def write_bgen_image(H: np.ndarray, p: int, compression: int = 0, level: int = 1) -> np.ndarray:
+    """Phased BGEN v1.2 image (layout 2, 8-bit probabilities) of the packed haplotype matrix H [2n][ceil(p/8)]:
+    what `qctool`/UK Biobank ship and BgenReader (bgen_reader.cpp) ingests.  compression 0 = none, 1 = zlib.
+    Used by bench.py to time the ingest kernel on the benchmark's own population."""
+    import struct
+    import zlib
+    bits = np.unpackbits(np.ascontiguousarray(H, dtype=np.uint8), axis=1, bitorder="little")[:, :p]
+    nh = bits.shape[0]
+    n = nh // 2
+    vals = np.where(bits.T == 0, 255, 0).astype(np.uint8)          # [p][2n]: P(first allele) as 8 bits
+    head = struct.pack("<IHBB", n, 2, 2, 2) + bytes([2]) * n + bytes([1, 8])
+    parts = [struct.pack("<I", 20), struct.pack("<III", 20, p, n), b"bgen", struct.pack("<I", compression | (2 << 2))]
+    for j in range(p):
+        rsid = b"rs%d" % j
+        ident = struct.pack("<H", 0) + struct.pack("<H", len(rsid)) + rsid + struct.pack("<H", 2) + b"22"
+        ident += struct.pack("<IH", 1000 + j, 2) + struct.pack("<I", 1) + b"A" + struct.pack("<I", 1) + b"G"
+        raw = head + vals[j].tobytes()
+        if compression == 0:
+            blk = struct.pack("<I", len(raw)) + raw
+        else:
+            z = zlib.compress(raw, level)
+            blk = struct.pack("<II", len(z) + 4, len(raw)) + z
+        parts.append(ident + blk)
+    return np.frombuffer(b"".join(parts), dtype=np.uint8)

@@ -1,0 +1,57 @@
+"""Parity at the benchmark's full size (BASELINE.json configs[1]: 20 000 haplotypes x 10 000 SNPs, K=50, singleton
+groups, the workload bench.py times).  The oracle cannot run all of it in seconds, so:
+  * rows sampled across the launch (first / last haplotype of warps, batches and slots) are compared bit for bit
+    with the oracle run at the full chromosome length;
+  * both compiled forms of the sampler kernel (dense / wide, kgw_api.cu) must produce the same complete matrix;
+  * a second run reproduces the matrix, and a shard of the haplotypes reproduces its rows (no cross-row state)."""
+import numpy as np
+import pytest
+
+import kgw_oracle as ko
+
+pytestmark = pytest.mark.gpu
+kg = pytest.importorskip("knockoffgwas_b200")
+
+N, P, K = 20000, 10000, 50
+
+
+@pytest.fixture(scope="module")
+def workload():
+    from knockoffgwas_b200 import synth
+    return synth.make_problem(N, P, K, seed=2020, mean_group=1.0, rho=1.0, lam=1e-3, hap_seed=0)
+
+
+def _run(sp, unrelated=None):
+    plan = kg.Plan(sp.H, sp.p, sp.K, sp.ref[:, None, :], sp.b, sp.mu, sp.groups, seed=sp.seed, unrelated=unrelated)
+    plan.run()
+    hk, _ = plan.download()
+    info = plan.info()
+    plan.close()
+    return hk, info
+
+
+def test_full_size_rows_match_oracle_and_forms_agree(workload, monkeypatch):
+    sp = workload
+    monkeypatch.setenv("KGW_FORCE_WIDE", "0")
+    dense, info = _run(sp)
+    assert info["lanes_per_hap"] == 2 and info["states_per_lane"] == 25
+    again, _ = _run(sp)
+    assert np.array_equal(dense, again), "two runs of the same plan input differ"
+    monkeypatch.setenv("KGW_FORCE_WIDE", "1")
+    wide, _ = _run(sp)
+    assert np.array_equal(dense, wide), "dense and wide forms of the sampler kernel differ"
+    monkeypatch.delenv("KGW_FORCE_WIDE")
+
+    rows = np.array([0, 1, 15, 16, 17, 31, 32, 4999, 5000, 9471, 9472, 12345, 18943, 18944, 19983, 19984, 19998, 19999], dtype=np.int32)
+    prob = ko.Problem(H=sp.H, p=P, K=K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu, groups=sp.groups,
+                      win_start=None, win_end=None, seed=sp.seed, unrelated=rows)
+    want = ko.run_unrelated(prob, mode="philox")
+    assert np.array_equal(dense[rows], want.hk), "sampled rows differ from the oracle at full chromosome length"
+
+    shard = np.arange(3, N, 7, dtype=np.int32)
+    sub, _ = _run(sp, unrelated=shard)
+    assert np.array_equal(sub[shard], dense[shard]), "a shard of the haplotypes does not reproduce its rows"
+    rest = np.setdiff1d(np.arange(N), shard)
+    assert not sub[rest].any()
+    # knockoffs are not copies: about half of the ~35 % polymorphic-ish cells should differ somewhere
+    assert 0.01 < np.mean(np.unpackbits(dense ^ sp.H)) < 0.5
