@@ -685,6 +685,8 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     loc[j].a_bp = (1.0 - pl->b[j]) / (double)K;
     loc[j].a_al = (1.0 - pl->b[j]) * alpha;
     loc[j].mu = pl->mu[j];
+    loc[j].w = (double)K * loc[j].a_bp + loc[j].b;
+    loc[j].r1 = loc[j].a_bp / loc[j].w;
   }
   KGW_CUDA(cudaMalloc(&F->dfams, sizeof(KgwFamDesc) * F->n_families));
   KGW_CUDA(cudaMalloc(&F->dmembers, sizeof(int32_t) * F->members_total));

@@ -71,6 +71,8 @@ struct KgwFamLocus {  // per locus
   double a_bp;   // (1.0 - b_j) / (double)K        family_bp.cpp:458,530
   double a_al;   // (1.0 - b_j) * alpha            family_bp.cpp:243,249; family_knockoffs.cpp
   double mu;     // mut_rates[j]
+  double w;      // K * a_bp + b  (= 1 up to rounding): sum over k of the unnormalised transition weights
+  double r1;     // a_bp / w
 };
 
 struct KgwFamParams {
@@ -113,15 +115,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
-}
-__device__ __forceinline__ void warp_sum2(double &a, double &b) {   // two sums in one shuffle tree
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ta = __shfl_xor_sync(FULL, a, o);
-    const double tb = __shfl_xor_sync(FULL, b, o);
-    a += ta;
-    b += tb;
-  }
 }
 __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 #pragma unroll
@@ -283,6 +276,10 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     // pinned nodes) and the plain stretches between them.  In a plain stretch every node depends on its own
     // chain only, so the members are taken one after the other with the running message in registers; a
     // chain is followed only while its message changes bits (or everywhere when `full`).
+    // Message formula (:456-497): with q_k = f_k * (product of the incoming messages at k) and S = sum_k q_k the
+    // reference forms const = sum_k a q_k, m_k = const + b q_k and divides by sum_k m_k = S (K a + b); here
+    // new_k = a / (K a + b) + (b / (S (K a + b))) q_k: one multiply and one fused multiply-add per state and
+    // one warp reduction per message (the same number up to rounding; sums over k are tree-ordered anyway).
     // Returns this lane's share of sum |new - old|.
     auto sweep = [&](auto dir_tag, const bool full) -> double {
       constexpr int dir = decltype(dir_tag)::value;
@@ -320,16 +317,16 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             const uint8_t *pp = pat_base + rowo;
             double *dp = dstb + rowo;
             const KgwFamLocus *lp = P.loc + (dir == 0 ? j + 1 : j);
-            bool hasv = (dir == 0) ? (j > 0) : (j < p - 1);
+            const bool hasv = (dir == 0) ? (j > 0) : (j < p - 1);
             double v[SF];
             unsigned ptc[SF];
 #pragma unroll
             for (int s = 0; s < SF; s++) {
-              v[s] = 0.0;
+              v[s] = 1.0;   // no incoming message at the first node of the sweep
               if (valid[s] && hasv) v[s] = ((comp_prev >> i) & 1u) ? pm[i * KP + s * 32 + lane] : dp[s * 32 - sK];
               ptc[s] = valid[s] ? pp[s * 32] : 0u;
             }
-            double la = lp->a_bp, lb = lp->b;
+            double lb = lp->b, lw = lp->w, lr1 = lp->r1;
             bool ch = true;
             int t = 0;
             for (; t < len; t++) {
@@ -342,32 +339,28 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
                 ptn[s] = (valid[s] && more) ? pp[sK + s * 32] : 0u;
                 oldv[s] = (valid[s] && !full) ? dp[s * 32] : (valid[s] ? p0 : 0.0);
               }
-              const double lan = more ? lp[step].a_bp : 0.0, lbn = more ? lp[step].b : 0.0;
+              const double lbn = more ? lp[step].b : 0.0, lwn = more ? lp[step].w : 1.0, lr1n = more ? lp[step].r1 : 0.0;
               if ((t & 3) == 0 && t + 12 < len) {   // rows t+8 .. t+11 of this chain (contiguous in memory)
                 fam_prefetch(pp + (dir == 0 ? 8 : 11) * sK - lane, 4 * K, lane);
                 if (!full) fam_prefetch(dp + (dir == 0 ? 8 : 11) * sK - lane, 32 * K, lane);
               }
-              double mm[SF];
-              double csum = 0.0, msum = 0.0;
+              double q[SF];
+              double qsum = 0.0;
 #pragma unroll
               for (int s = 0; s < SF; s++) {
-                mm[s] = 0.0;
+                q[s] = 0.0;
                 if (valid[s]) {
-                  const double fk = emission_of(ptc[s], j + t * step, nn);
-                  double c = la * fk, m = lb * fk;
-                  if (hasv) { c *= v[s]; m *= v[s]; }
-                  csum += c;
-                  msum += m;
-                  mm[s] = m;
+                  q[s] = emission_of(ptc[s], j + t * step, nn) * v[s];
+                  qsum += q[s];
                 }
               }
-              warp_sum2(csum, msum);
-              const double inv = 1.0 / ((double)K * csum + msum);   // sum_k (const_msg + msg_k)
+              const double S = warp_sum(qsum);
+              const double c2 = lb * (1.0 / (S * lw));
               bool ne = false;
 #pragma unroll
               for (int s = 0; s < SF; s++) {
                 if (valid[s]) {
-                  const double nv = (csum + mm[s]) * inv;
+                  const double nv = lr1 + c2 * q[s];
                   diff += fabs(nv - oldv[s]);
                   ne |= (nv != oldv[s]);
                   v[s] = nv;
@@ -378,12 +371,12 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
 #pragma unroll
                 for (int s = 0; s < SF; s++) if (valid[s]) dp[s * 32] = v[s];
               }
-              hasv = true;
               pp += sK;
               dp += sK;
               lp += step;
-              la = lan;
               lb = lbn;
+              lw = lwn;
+              lr1 = lr1n;
 #pragma unroll
               for (int s = 0; s < SF; s++) ptc[s] = ptn[s];
               if (!full && !ch) { t++; break; }   // bit-identical message: everything further along this chain is clean
@@ -416,36 +409,34 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             const double *prevg = dstb + rowo - (ptrdiff_t)step * K;   // own chain, one locus back in sweep order
             const bool prev_sm = (comp_prev >> i) & 1u;
             double msg[SF], oldv[SF];
-            double csum = 0.0, msum = 0.0;
+            double qsum = 0.0;
 #pragma unroll
             for (int s = 0; s < SF; s++) {
               const int k = s * 32 + lane;
               msg[s] = 0.0;
               oldv[s] = 0.0;
               if (k < K) {
-                const double fk = emission_of(pat_base[rowo + k], j, nn);
+                double q = emission_of(pat_base[rowo + k], j, nn);
                 oldv[s] = full ? p0 : dstb[rowo + k];
-                double c = lc.a_bp * fk, m = lc.b * fk;
-                if (has_prev) { const double v = prev_sm ? pm[i * KP + k] : prevg[k]; c *= v; m *= v; }
+                if (has_prev) q *= prev_sm ? pm[i * KP + k] : prevg[k];
                 if (dir == 0) {
-                  for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
-                  for (int t = 0; t < ndr; t++) { const double v = full ? p0 : ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
+                  for (int t = 0; t < ndl; t++) q *= mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k];
+                  for (int t = 0; t < ndr; t++) q *= full ? p0 : ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k];
                 } else {
-                  for (int t = 0; t < ndr; t++) { const double v = ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k]; c *= v; m *= v; }
-                  for (int t = 0; t < ndl; t++) { const double v = mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k]; c *= v; m *= v; }
+                  for (int t = 0; t < ndr; t++) q *= ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k];
+                  for (int t = 0; t < ndl; t++) q *= mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k];
                 }
-                msg[s] = m;
-                csum += c;
-                msum += m;
+                msg[s] = q;
+                qsum += q;
               }
             }
-            warp_sum2(csum, msum);
-            const double inv = 1.0 / ((double)K * csum + msum);   // sum_k (const_msg + msg_k)
+            const double S = warp_sum(qsum);
+            const double c2 = lc.b * (1.0 / (S * lc.w));
             bool ne = false;
 #pragma unroll
             for (int s = 0; s < SF; s++) {
               if (s * 32 + lane < K) {
-                const double nv = (csum + msg[s]) * inv;
+                const double nv = lc.r1 + c2 * msg[s];
                 diff += fabs(nv - oldv[s]);
                 ne |= (nv != oldv[s]);
                 msg[s] = nv;
