@@ -18,8 +18,10 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -31,60 +33,77 @@ namespace {
 
 enum { BGEN_BAD_HEADER = 1, BGEN_BAD_PLOIDY = 2, BGEN_BAD_PROB = 4 };
 
-// One warp: 32 output haplotypes (lane = haplotype) x 128 output loci (4 words, one 16-byte store per lane).
-// Consecutive lanes read consecutive haplotype values of the same variant block (coalesced when the kept
-// samples are consecutive in the file, the usual case).
-__global__ void __launch_bounds__(256) bgen_unpack_kernel(const uint8_t *__restrict__ blocks, const long long *__restrict__ col_off,
+// Pass 1, one thread per output column: checks the block header and leaves (offset of the probability stream |
+// B << 56) for pass 2.
+__global__ void __launch_bounds__(256) bgen_header_kernel(const uint8_t *__restrict__ blocks, const long long *__restrict__ col_off,
+                                                          int n_samples_bgen, int p, unsigned long long *__restrict__ colinfo,
+                                                          int *__restrict__ status) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p) return;
+  const uint8_t *blk = blocks + col_off[j];
+  const uint32_t nfile = (uint32_t)blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+  const uint32_t nall = (uint32_t)blk[4] | ((uint32_t)blk[5] << 8);
+  const uint32_t pmin = blk[6], pmax = blk[7];
+  uint32_t phased = 0, B = 0;
+  if (nfile == (uint32_t)n_samples_bgen) { phased = blk[8 + n_samples_bgen]; B = blk[9 + n_samples_bgen]; }
+  if (nfile != (uint32_t)n_samples_bgen || nall != 2u || pmin != 2u || pmax != 2u || phased != 1u || B < 1u || B > 32u) {
+    atomicOr(status, BGEN_BAD_HEADER);
+    B = 0;
+  }
+  colinfo[j] = (unsigned long long)(col_off[j] + 10 + n_samples_bgen) | ((unsigned long long)B << 56);
+}
+
+// Pass 2.  One warp: 32 output haplotypes (lane = haplotype) x 128 output loci (4 words, one 16-byte store per
+// lane); the 128 column descriptors of the CTA sit in shared memory.  Consecutive lanes read consecutive
+// haplotype values of the same variant block (coalesced when the kept samples are consecutive in the file, the
+// usual case); per (haplotype, variant) the kernel loads the sample's ploidy byte and its B-bit value.
+__global__ void __launch_bounds__(256) bgen_unpack_kernel(const uint8_t *__restrict__ blocks, const unsigned long long *__restrict__ colinfo,
                                                           const int32_t *__restrict__ sample_idx, int n_samples_bgen, int n_haps,
                                                           int p, int stride_w, uint32_t *__restrict__ Hw, int *__restrict__ status) {
+  __shared__ unsigned long long info[128];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int hap = (blockIdx.y * 8 + warp) * 32 + lane;
-  const int w0 = blockIdx.x * 4;   // first 32-locus word of this warp's 128 loci
+  const int w0 = blockIdx.x * 4;   // first 32-locus word of this CTA's 128 loci
+  if (threadIdx.x < 128) {
+    const int j = (w0 << 5) + threadIdx.x;
+    info[threadIdx.x] = (j < p) ? colinfo[j] : 0ull;
+  }
+  __syncthreads();
   const bool live = hap < n_haps;
   const int s_file = live ? sample_idx[hap >> 1] : 0;
   const long long q = 2ll * s_file + (hap & 1);   // index of the haplotype's value in a block
   int bad = 0;
   uint32_t words[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-  for (int ww = 0; ww < 4; ww++) {
-    const int jbase = (w0 + ww) << 5;
-    if (jbase >= p) break;
-    const int jn = min(32, p - jbase);
-    uint32_t acc = 0;
-    for (int jj = 0; jj < jn; jj++) {
-      const uint8_t *blk = blocks + col_off[jbase + jj];
-      // block header (same for every lane: broadcast loads)
-      const uint32_t nfile = (uint32_t)blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
-      const uint32_t nall = (uint32_t)blk[4] | ((uint32_t)blk[5] << 8);
-      const uint32_t pmin = blk[6], pmax = blk[7];
-      const uint32_t phased = blk[8 + n_samples_bgen], B = blk[9 + n_samples_bgen];
-      if (nfile != (uint32_t)n_samples_bgen || nall != 2u || pmin != 2u || pmax != 2u || phased != 1u || B < 1u || B > 32u) {
-        bad |= BGEN_BAD_HEADER;
-        continue;
-      }
-      if (!live) continue;
-      if (blk[8 + s_file] != 2u) bad |= BGEN_BAD_PLOIDY;   // missing flag set or ploidy != 2
-      const uint8_t *pr = blk + 10 + n_samples_bgen;
-      uint32_t v;
-      if (B == 8u) {
-        v = pr[q];
-      } else {
-        const long long bit0 = q * (long long)B;
-        const uint8_t *b0 = pr + (bit0 >> 3);
-        const int sh = (int)(bit0 & 7);
-        const int nbytes = (sh + (int)B + 7) >> 3;   // <= 5
-        unsigned long long acc64 = 0;
-        for (int t = 0; t < nbytes; t++) acc64 |= (unsigned long long)b0[t] << (8 * t);
-        v = (uint32_t)((acc64 >> sh) & ((B == 32u) ? 0xffffffffull : ((1ull << B) - 1ull)));
-      }
-      const uint32_t ones = (B == 32u) ? 0xffffffffu : ((1u << B) - 1u);
-      if (v == 0u) acc |= 1u << jj;            // P(first allele) = 0 -> second allele -> bit 1
-      else if (v != ones) bad |= BGEN_BAD_PROB;
-    }
-    words[ww] = acc;
-  }
   if (live) {
+#pragma unroll
+    for (int ww = 0; ww < 4; ww++) {
+      uint32_t acc = 0;
+#pragma unroll 8
+      for (int jj = 0; jj < 32; jj++) {
+        const unsigned long long ci = info[ww * 32 + jj];
+        const uint32_t B = (uint32_t)(ci >> 56);
+        if (B == 0u) continue;   // beyond p, or a header pass 1 rejected
+        const uint8_t *pr = blocks + (ci & 0x00ffffffffffffffull);
+        if (pr[s_file - n_samples_bgen - 2] != 2u) bad |= BGEN_BAD_PLOIDY;   // ploidy bytes end 2 bytes before the stream
+        uint32_t v;
+        if (B == 8u) {
+          v = pr[q];
+        } else {
+          const long long bit0 = q * (long long)B;
+          const uint8_t *b0 = pr + (bit0 >> 3);
+          const int sh = (int)(bit0 & 7);
+          const int nbytes = (sh + (int)B + 7) >> 3;   // <= 5
+          unsigned long long acc64 = 0;
+          for (int t = 0; t < nbytes; t++) acc64 |= (unsigned long long)b0[t] << (8 * t);
+          v = (uint32_t)((acc64 >> sh) & ((B == 32u) ? 0xffffffffull : ((1ull << B) - 1ull)));
+        }
+        const uint32_t ones = (B == 32u) ? 0xffffffffu : ((1u << B) - 1u);
+        if (v == 0u) acc |= 1u << jj;            // P(first allele) = 0 -> second allele -> bit 1
+        else if (v != ones) bad |= BGEN_BAD_PROB;
+      }
+      words[ww] = acc;
+    }
     uint32_t *dst = Hw + (size_t)hap * stride_w + w0;
     if (w0 + 4 <= stride_w) {
       *reinterpret_cast<uint4 *>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
@@ -188,14 +207,25 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   if (rc != KGW_OK) return rc;
   for (int i = 0; i < n_samples; i++)
     if (sample_idx[i] < 0 || (uint32_t)sample_idx[i] >= nfile) return kgw_fail_(KGW_ERR_INVALID, "sample index outside the BGEN sample block");
+  // Uncompressed files go to the device as they are (one copy of the span that holds the requested blocks);
+  // compressed blocks are inflated into a staging buffer first, 16-byte aligned one after the other.
   std::vector<long long> col_off(p);
-  long long total = 0;
+  long long total = 0, span_lo = file_bytes, span_hi = 0;
   for (int j = 0; j < p; j++) {
     const int v = variant_of_col[j];
     if (v < 0 || (size_t)v >= idx.size()) return kgw_fail_(KGW_ERR_INVALID, "variant index outside the BGEN file");
     if (idx[v].raw_len < 10 + (int64_t)nfile) return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block shorter than its header");
-    col_off[j] = total;
-    total += (idx[v].raw_len + 15) & ~15ll;
+    if (compression == 0u) {
+      span_lo = std::min<long long>(span_lo, idx[v].data_off);
+      span_hi = std::max<long long>(span_hi, idx[v].data_off + idx[v].raw_len);
+    } else {
+      col_off[j] = total;
+      total += (idx[v].raw_len + 15) & ~15ll;
+    }
+  }
+  if (compression == 0u) {
+    for (int j = 0; j < p; j++) col_off[j] = idx[variant_of_col[j]].data_off - span_lo;
+    total = span_hi - span_lo;
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -204,22 +234,26 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   do {                                                                                                       \
     cudaError_t e_ = (call);                                                                                 \
     if (e_ != cudaSuccess) {                                                                                 \
-      cudaFreeHost(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus); \
+      free(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus); \
       return kgw_fail_(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
     }                                                                                                        \
   } while (0)
   uint8_t *stage = nullptr, *dblocks = nullptr;
   long long *doff = nullptr;
+  unsigned long long *dinfo = nullptr;
   int32_t *dsidx = nullptr;
   uint32_t *dH = nullptr;
   int *dstatus = nullptr;
   KGW_CUDA_B(cudaSetDevice(device));
-  KGW_CUDA_B(cudaMallocHost(&stage, (size_t)total + 16));
+  if (compression != 0u) {
+    stage = (uint8_t *)malloc((size_t)total + 16);
+    if (!stage) return kgw_fail_(KGW_ERR_NOMEM, "staging buffer for the inflated BGEN blocks");
+  }
 
   // inflate the selected blocks (host threads; the reference does this inside genfile::bgen, one variant at a time)
   const Codecs &cd = codecs();
-  if (compression == 2u && (!cd.zstd || !cd.zstd_err)) { cudaFreeHost(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zstd-compressed BGEN but libzstd.so.1 could not be loaded"); }
-  if (compression == 1u && !cd.zlib) { cudaFreeHost(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zlib-compressed BGEN but libz.so.1 could not be loaded"); }
+  if (compression == 2u && (!cd.zstd || !cd.zstd_err)) { free(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zstd-compressed BGEN but libzstd.so.1 could not be loaded"); }
+  if (compression == 1u && !cd.zlib) { free(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zlib-compressed BGEN but libz.so.1 could not be loaded"); }
   int nt = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
   nt = std::max(1, std::min(nt, std::min(p, 64)));
   std::atomic<int> next{0}, failed{0};
@@ -230,8 +264,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
       for (int j = j0; j < std::min(p, j0 + 64); j++) {
         const VariantBlock &vb = idx[variant_of_col[j]];
         uint8_t *dst = stage + col_off[j];
-        if (compression == 0u) memcpy(dst, file + vb.data_off, (size_t)vb.raw_len);
-        else if (compression == 2u) {
+        if (compression == 2u) {
           const size_t got = cd.zstd(dst, (size_t)vb.raw_len, file + vb.data_off, (size_t)vb.comp_len);
           if (cd.zstd_err(got) || got != (size_t)vb.raw_len) failed.store(1);
         } else {
@@ -241,22 +274,23 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
       }
     }
   };
-  {
+  if (compression != 0u) {
     std::vector<std::thread> th;
     for (int t = 1; t < nt; t++) th.emplace_back(worker);
     worker();
     for (auto &t : th) t.join();
   }
-  if (failed.load()) { cudaFreeHost(stage); return kgw_fail_(KGW_ERR_INVALID, "a BGEN probability block did not decompress to its stated length"); }
+  if (failed.load()) { free(stage); return kgw_fail_(KGW_ERR_INVALID, "a BGEN probability block did not decompress to its stated length"); }
 
   const int n_haps = 2 * n_samples;
   const int stride_w = (((p + 31) / 32) + 3) & ~3;   // rows padded to 16 bytes
   KGW_CUDA_B(cudaMalloc(&dblocks, (size_t)total + 16));
   KGW_CUDA_B(cudaMalloc(&doff, sizeof(long long) * p));
+  KGW_CUDA_B(cudaMalloc(&dinfo, sizeof(unsigned long long) * p));
   KGW_CUDA_B(cudaMalloc(&dsidx, sizeof(int32_t) * n_samples));
   KGW_CUDA_B(cudaMalloc(&dH, sizeof(uint32_t) * (size_t)n_haps * stride_w));
   KGW_CUDA_B(cudaMalloc(&dstatus, sizeof(int)));
-  KGW_CUDA_B(cudaMemcpy(dblocks, stage, (size_t)total, cudaMemcpyHostToDevice));
+  KGW_CUDA_B(cudaMemcpy(dblocks, compression == 0u ? file + span_lo : stage, (size_t)total, cudaMemcpyHostToDevice));
   KGW_CUDA_B(cudaMemcpy(doff, col_off.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
   KGW_CUDA_B(cudaMemcpy(dsidx, sample_idx, sizeof(int32_t) * n_samples, cudaMemcpyHostToDevice));
   KGW_CUDA_B(cudaMemset(dstatus, 0, sizeof(int)));
@@ -265,7 +299,8 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   KGW_CUDA_B(cudaEventCreate(&e1));
   const dim3 grid((unsigned)((stride_w + 3) / 4), (unsigned)((n_haps + 255) / 256));
   KGW_CUDA_B(cudaEventRecord(e0));
-  bgen_unpack_kernel<<<grid, 256>>>(dblocks, doff, dsidx, (int)nfile, n_haps, p, stride_w, dH, dstatus);
+  bgen_header_kernel<<<(p + 255) / 256, 256>>>(dblocks, doff, (int)nfile, p, dinfo, dstatus);
+  bgen_unpack_kernel<<<grid, 256>>>(dblocks, dinfo, dsidx, (int)nfile, n_haps, p, stride_w, dH, dstatus);
   KGW_CUDA_B(cudaGetLastError());
   KGW_CUDA_B(cudaEventRecord(e1));
   KGW_CUDA_B(cudaEventSynchronize(e1));
@@ -279,7 +314,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   if (st == 0)
     KGW_CUDA_B(cudaMemcpy2D(H_out, (size_t)row_bytes, dH, sizeof(uint32_t) * (size_t)stride_w, (size_t)((p + 7) / 8), (size_t)n_haps,
                             cudaMemcpyDeviceToHost));
-  cudaFreeHost(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus);
+  free(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus);
 #undef KGW_CUDA_B
   if (st & BGEN_BAD_HEADER)
     return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block is not phased diploid biallelic layout-2 data of the stated sample count");

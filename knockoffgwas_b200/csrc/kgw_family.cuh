@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
                 }
               }
               const double S = warp_sum(qsum);
-              const double c2 = lb * (1.0 / (S * lw));
+              const double c2 = lb * fast_rcp(S * lw);
               bool ne = false;
 #pragma unroll
               for (int s = 0; s < SF; s++) {
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
               }
             }
             const double S = warp_sum(qsum);
-            const double c2 = lc.b * (1.0 / (S * lc.w));
+            const double c2 = lc.b * fast_rcp(S * lc.w);
             bool ne = false;
 #pragma unroll
             for (int s = 0; s < SF; s++) {
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             if (Nv[s] < N_MIN) Nv[s] = N_MIN;
             if (k < K) nn_part += Nv[s];
           }
-          const double r_norm = 1.0 / warp_sum(nn_part);
+          const double r_norm = fast_rcp(warp_sum(nn_part));
 #pragma unroll
           for (int s = 0; s < SF; s++) {
             Nv[s] *= r_norm;
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
           }
           zk_last = zkprev;
 #pragma unroll
-          for (int s = 0; s < SF; s++) rNo[s] = 1.0 / Nv[s];
+          for (int s = 0; s < SF; s++) rNo[s] = fast_rcp(Nv[s]);
         }
       }
       __syncwarp();

@@ -8,11 +8,14 @@ from __future__ import annotations
 import numpy as np
 
 
-def partition_work(unrelated, families, world_size: int, family_cost: float = 3.0):
+FAMILY_COST = 8.0   # measured on B200: a related haplotype costs about 8 unrelated ones (the CPU reference: 2-3)
+
+
+def partition_work(unrelated, families, world_size: int, family_cost: float = FAMILY_COST):
     """Split the work list over `world_size` ranks.
 
     unrelated: sorted haplotype ids; families: list of member-id arrays (atomic units, a member costs
-    `family_cost` unrelated haplotypes -- BASELINE.md: related haplotypes cost 2-3x).
+    `family_cost` unrelated haplotypes).
     Returns a list of (unrelated ids of the rank [contiguous slice], family indices of the rank).
     Families go to the least loaded rank in descending size (the reference's own order,
     knockoffs.cpp:364-372, made cost-aware); the unrelated list is then cut so that total costs even out."""

@@ -11,7 +11,7 @@ import pytest
 
 import kgw_oracle as ko
 from kgw_testutil import load_golden
-from knockoffgwas_b200.shard import partition_work, rows_of
+from knockoffgwas_b200.shard import FAMILY_COST, partition_work, rows_of
 
 REPO = Path(__file__).resolve().parents[1]
 
@@ -35,8 +35,8 @@ def test_partition_work_properties():
         assert np.array_equal(got_u, unrelated)                       # contiguous slices, nothing lost or doubled
         got_f = sorted(f for _, fl in parts for f in fl)
         assert got_f == list(range(len(fams)))                        # every family on exactly one rank
-        cost = [len(u) + 3.0 * sum(len(fams[f]) for f in fl) for u, fl in parts]
-        assert max(cost) - min(cost) <= 3.0 * 5 + 1                   # balanced to within one family
+        cost = [len(u) + FAMILY_COST * sum(len(fams[f]) for f in fl) for u, fl in parts]
+        assert max(cost) - min(cost) <= FAMILY_COST * 5 + 1                   # balanced to within one family
         rows = [rows_of(u, fams, fl) for u, fl in parts]
         assert np.array_equal(np.sort(np.concatenate(rows)), np.arange(N))
 
