@@ -130,14 +130,21 @@ struct DevPool {
     }
     items.push_back({dev, n, p});
   }
-  // free everything parked for `dev` (all devices if dev < 0); returns the number of bytes released
-  size_t clear(int dev = -1) {
+  // bytes parked for `dev`: memory a new plan of this device can count on (take() or clear() returns it)
+  size_t parked(int dev) {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t n = 0;
+    for (const Item &it : items) if (it.dev == dev) n += it.bytes;
+    return n;
+  }
+  // free everything of at least `min_bytes` parked for `dev` (all devices if dev < 0); returns the bytes released
+  size_t clear(int dev = -1, size_t min_bytes = 0) {
     std::lock_guard<std::mutex> lk(mu);
     size_t freed = 0;
     int cur = 0;
     cudaGetDevice(&cur);
     for (size_t i = 0; i < items.size();) {
-      if (dev < 0 || items[i].dev == dev) {
+      if ((dev < 0 || items[i].dev == dev) && items[i].bytes >= min_bytes) {
         cudaSetDevice(items[i].dev);
         cudaFree(items[i].ptr);
         freed += items[i].bytes;
@@ -152,11 +159,14 @@ struct DevPool {
 };
 DevPool g_pool;
 
-// cudaMalloc through the pool; on out-of-memory the parked buffers of the device are released first
+// cudaMalloc through the pool.  A large request that no parked buffer fits belongs to a differently shaped
+// problem: the large parked buffers of the device are released first (the plan sized itself counting on
+// them); on out-of-memory everything parked is released.
 cudaError_t pool_alloc(int dev, void **out, size_t bytes, size_t *got) {
   if (bytes == 0) bytes = 16;
   *out = g_pool.take(dev, bytes, got);
   if (*out) return cudaSuccess;
+  if (bytes >= ((size_t)64 << 20)) g_pool.clear(dev, (size_t)64 << 20);
   cudaError_t e = cudaMalloc(out, bytes);
   if (e == cudaErrorMemoryAllocation && g_pool.clear(dev) > 0) {
     cudaGetLastError();
@@ -319,6 +329,9 @@ struct FamilyState {
   int32_t *dwork = nullptr;
   KgwFamRange *dranges = nullptr;
   long long *dphase = nullptr;
+  cudaStream_t side = nullptr;             // the related branch runs beside the unrelated one when both fit on the SMs
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = false;
   int32_t *dref_global = nullptr;
   KgwFamInterval *divs = nullptr;
   KgwFamOp *dops = nullptr;
@@ -332,7 +345,7 @@ struct FamilyState {
   ~FamilyState() {
     cudaFree(dfams); cudaFree(dmembers); cudaFree(divstart); cudaFree(dgroups); cudaFree(dgfirst); cudaFree(dglast);
     cudaFree(dstatus); cudaFree(dref_global); cudaFree(divs); cudaFree(dops); cudaFree(dloc); cudaFree(dko);
-    cudaFree(demtab); cudaFree(dmsg); cudaFree(dpat); cudaFree(dbytes); cudaFree(ddbg_z); cudaFree(ddbg_zk);
+    cudaFree(demtab); cudaFree(ddbg_z); cudaFree(ddbg_zk);   // dmsg / dpat / dbytes belong to the plan's pool
 #ifdef KGW_PHASES
     if (dphase) {
       long long h[8];
@@ -345,6 +358,9 @@ struct FamilyState {
     }
 #endif
     cudaFree(dwork); cudaFree(dranges);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -708,7 +724,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMemset(F->dstatus, 0, sizeof(int32_t)));
 
   // one warp per resident family, as many CTAs as the kernel's registers / shared memory keep resident;
-  // scratch slots bounded by 60 % of the free memory
+  // scratch slots bounded by 80 % of the memory still free (the sampler took at most a quarter before)
   F->SF = (K + 31) / 32 <= 1 ? 1 : ((K + 31) / 32 <= 2 ? 2 : ((K + 31) / 32 <= 4 ? 4 : 8));
   F->threads = 128;
   const int wpc = F->threads / 32;
@@ -723,15 +739,23 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   const size_t per_slot = (size_t)F->n_max * p * ((size_t)K * 17 + 2);
   size_t free_b = 0, total_b = 0;
   KGW_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const long long slots_mem = std::max<long long>(wpc, (long long)((double)free_b * 0.6 / (double)per_slot));
+  free_b += g_pool.parked(pl->device);
+  const long long slots_mem = std::max<long long>(wpc, (long long)((double)free_b * 0.8 / (double)per_slot));
   const long long want = std::min<long long>(F->n_families, (long long)dp.multiProcessorCount * ctas_per_sm * wpc);
   long long ctas = (want + wpc - 1) / wpc;
   if (ctas * wpc > slots_mem) ctas = slots_mem / wpc;
   F->grid = (int)std::max<long long>(1, ctas);
   const size_t nslots = (size_t)F->grid * wpc;
-  KGW_CUDA(cudaMalloc(&F->dmsg, sizeof(double) * 2 * F->n_max * (size_t)p * K * nslots));
-  KGW_CUDA(cudaMalloc(&F->dpat, (size_t)F->n_max * p * K * nslots));
-  KGW_CUDA(cudaMalloc(&F->dbytes, (size_t)2 * F->n_max * p * nslots));
+  {
+    const char *ov = getenv("KGW_FAMILY_OVERLAP");   // development: "0" / "1"
+    F->overlap = ov && ov[0] == '1';   // measured on B200: no gain, the persistent sampler CTAs queue behind the family CTAs
+    KGW_CUDA(cudaStreamCreateWithFlags(&F->side, cudaStreamNonBlocking));
+    KGW_CUDA(cudaEventCreateWithFlags(&F->ev_fork, cudaEventDisableTiming));
+    KGW_CUDA(cudaEventCreateWithFlags(&F->ev_join, cudaEventDisableTiming));
+  }
+  KGW_CUDA(pl->alloc(&F->dmsg, sizeof(double) * 2 * F->n_max * (size_t)p * K * nslots));   // pooled with the plan's buffers
+  KGW_CUDA(pl->alloc(&F->dpat, (size_t)F->n_max * p * K * nslots));
+  KGW_CUDA(pl->alloc(&F->dbytes, (size_t)2 * F->n_max * p * nslots));
 
   KgwFamParams &P = F->P;
   P.N = N; P.p = p; P.K = K; P.n_families = F->n_families; P.stride_w = pl->stride_w; P.n_max = F->n_max;
@@ -748,13 +772,13 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   return KGW_OK;
 }
 
-int fam_launch(kgw_plan *pl) {
+int fam_launch(kgw_plan *pl, cudaStream_t st) {
   FamilyState *F = pl->fam;
   if (!F || F->n_families == 0) return KGW_OK;
   void (*fn)(const KgwFamParams) = fam_kernel_for(F->SF, F->P.uniform_mu != 0);
   KGW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
-  KGW_CUDA(cudaMemsetAsync(F->dwork, 0, sizeof(int32_t), pl->stream));
-  fn<<<F->grid, F->threads, F->smem, pl->stream>>>(F->P);
+  KGW_CUDA(cudaMemsetAsync(F->dwork, 0, sizeof(int32_t), st));
+  fn<<<F->grid, F->threads, F->smem, st>>>(F->P);
   KGW_CUDA(cudaGetLastError());
   return KGW_OK;
 }
@@ -799,12 +823,29 @@ int upload_partition(kgw_plan *pl, const int32_t *groups, bool hmm_too) {
   return KGW_OK;
 }
 
+// The two branches write disjoint rows of Hk and share only read-only inputs, so they may run side by side
+// (KGW_FAMILY_OVERLAP=1: family kernel first on a side stream, the sampler fills the remaining registers / shared
+// memory).  Default: one after the other -- measured on a C5-shaped shard (512 pairs + 12 000 unrelated haplotypes
+// x 60 000 SNPs, K=100): 671 ms in sequence, 681 ms side by side.
 int launch(kgw_plan *pl) {
+  FamilyState *F = pl->fam;
+  const bool both = pl->n_haps > 0 && F && F->n_families > 0;
+  if (both && F->overlap) {
+    KGW_CUDA(cudaEventRecord(F->ev_fork, pl->stream));
+    KGW_CUDA(cudaStreamWaitEvent(F->side, F->ev_fork, 0));
+    int rc = fam_launch(pl, F->side);
+    if (rc != KGW_OK) return rc;
+    KGW_CUDA(cudaEventRecord(F->ev_join, F->side));
+  }
   if (pl->n_haps > 0) {
     pl->fn<<<pl->grid, pl->threads, pl->smem, pl->stream>>>(pl->P);
     KGW_CUDA(cudaGetLastError());
   }
-  return fam_launch(pl);
+  if (both && F->overlap) {
+    KGW_CUDA(cudaStreamWaitEvent(pl->stream, F->ev_join, 0));
+    return KGW_OK;
+  }
+  return fam_launch(pl, pl->stream);
 }
 
 }  // namespace
@@ -904,6 +945,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   // into segments when the per-slot scratch of a whole pass would not fit in 60 % of the free memory
   size_t free_b = 0, total_b = 0;
   KGW_CUDA_PL(cudaMemGetInfo(&free_b, &total_b));
+  free_b += g_pool.parked(pl->device);   // parked buffers are either taken back or released by pool_alloc
   const size_t hw_bytes_est = 2 * (size_t)N * (((size_t)prob->row_bytes + 15) / 16 * 16) + sizeof(int32_t) * (size_t)N * W * K;
   const KgwVariant *var = pick_variant(K, o.lanes_per_hap, B);
   const int G = 32 / var->L;
@@ -968,7 +1010,10 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   if (o.segment_loci > 0) {
     PS = std::min<size_t>(p32, (size_t)o.segment_loci);
   } else {
-    const double budget = 0.6 * (double)free_b - (double)hw_bytes_est;
+    // with IBD families in the same call most of the memory goes to their message slots (204 MB per pair at
+    // 60 000 SNPs, K=100: residency is what bounds that kernel); the sampler cuts its passes into shorter segments
+    const bool with_families = prob->families && prob->families->n_families > 0;
+    const double budget = (with_families ? 0.25 : 0.6) * (double)free_b - (double)hw_bytes_est;
     while (PS > 1024 && (double)slots * (double)(fixed_slot + seg_slot(PS)) > budget) PS = ((PS / 2) + 31) / 32 * 32;
   }
   pl->seg_loci = (int)PS;

@@ -158,6 +158,29 @@ __device__ __forceinline__ int warp_choice(const double (&w)[SF], double u, int 
   return min(cnt, K - 1);
 }
 
+// The same draw when lane l owns the CONTIGUOUS states l*SF .. l*SF+SF-1 (the final draws and the family knockoffs
+// keep their per-state values in registers only, so they are free to choose the ownership): one scan over the
+// lane totals instead of SF scans, then the state inside the lane that holds u*S.
+template <int SF>
+__device__ __forceinline__ int warp_choice_contig(const double (&w)[SF], double u, int K, int lane) {
+  double T = 0.0;
+#pragma unroll
+  for (int s = 0; s < SF; s++) T += w[s];
+  const double inc = warp_incl_scan(T, lane);
+  const double R = u * __shfl_sync(FULL, inc, 31);
+  const int L = __popc(__ballot_sync(FULL, inc <= R));   // first lane whose inclusive sum exceeds R (32: none)
+  const double r = R - (inc - T);
+  double acc = 0.0;
+  int c = 0;
+#pragma unroll
+  for (int s = 0; s < SF; s++) {
+    acc += w[s];
+    c += (acc <= r) ? 1 : 0;
+  }
+  const int k = __shfl_sync(FULL, lane * SF + min(c, SF - 1), min(L, 31));
+  return (L >= 32) ? K - 1 : min(k, K - 1);
+}
+
 // SF: states per lane; UMU: mu is the same at every locus (init_hmm, knockoffs.cpp:1520) and node emissions
 // come from the shared-memory table, else they are formed per state with pow() as the reference does
 template <int SF, bool UMU>
@@ -541,7 +564,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     // the same chain has been drawn, so messages_right[i][j-1] is the point-mass transition condition_on
     // would have stored (:243-246) and is formed from the previous draw; nothing reads the right messages
     // afterwards, so they are not written.  messages_left[i][j+1] and the pattern bytes are fetched one
-    // locus ahead of the (serial) draw.
+    // locus ahead of the (serial) draw.  Lane l owns the contiguous states l*SF .. here (warp_choice_contig).
     for (int i = 0; i < n; i++) {
       const KgwFamInterval *iv = P.ivs + ivs0[i];
       int ivj1 = iv->j1, ivnn = iv->nn;
@@ -556,7 +579,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
       unsigned pt_c[SF];
 #pragma unroll
       for (int s = 0; s < SF; s++) {
-        const int k = s * 32 + lane;
+        const int k = lane * SF + s;
         pt_c[s] = (k < K) ? ptrow[k] : 0u;
         ml_c[s] = (k < K && p > 1) ? mlrow[(size_t)K + k] : 1.0;
       }
@@ -571,7 +594,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
           unsigned pt_n[SF];
 #pragma unroll
           for (int s = 0; s < SF; s++) {   // next locus: pattern j+1, left message j+2
-            const int k = s * 32 + lane;
+            const int k = lane * SF + s;
             pt_n[s] = (k < K && j + 1 < p) ? ptrow[(size_t)(j + 1) * K + k] : 0u;
             ml_n[s] = (k < K && j + 2 < p) ? mlrow[(size_t)(j + 2) * K + k] : 1.0;
           }
@@ -594,7 +617,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             double wv[SF];
 #pragma unroll
             for (int s = 0; s < SF; s++) {
-              const int k = s * 32 + lane;
+              const int k = lane * SF + s;
               wv[s] = 0.0;
               if (k < K) {
                 double v = emission_of(pt_c[s], j, ivnn);
@@ -603,7 +626,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
                 wv[s] = v;
               }
             }
-            const int kz = warp_choice<SF>(wv, __shfl_sync(FULL, uw, q), K, lane);
+            const int kz = warp_choice_contig<SF>(wv, __shfl_sync(FULL, uw, q), K, lane);
             if (lane == 0) {
               Zb[(size_t)i * p + j] = (uint8_t)kz;
               for (int t = 0; t < ivnn; t++) Zb[(size_t)((nbpack >> (3 * t)) & 7u) * p + j] = (uint8_t)kz;
@@ -653,7 +676,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
           double part = 0.0;
 #pragma unroll
           for (int s = 0; s < SF; s++) {
-            const int k = s * 32 + lane;
+            const int k = lane * SF + s;
             double tmp = k0v.a;
             if (g > 0) {
               tmp = (k == z0) ? k0v.apb : k0v.a;
@@ -666,7 +689,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
           double nn_part = 0.0;
 #pragma unroll
           for (int s = 0; s < SF; s++) {
-            const int k = s * 32 + lane;
+            const int k = lane * SF + s;
             if (!lastg) {
               Nv[s] += k0v.vb * N_sum;
               Nv[s] += k0v.vs * tq[s];   // vstar[0] == vs of the first locus
@@ -691,14 +714,14 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             double w[SF];
 #pragma unroll
             for (int s = 0; s < SF; s++) {
-              const int k = s * 32 + lane;
+              const int k = lane * SF + s;
               double wk;
               if (j > e0) wk = (k == zkprev) ? kv.apb : kv.a;
               else wk = (g == 0) ? tq[s] * rNo[s] : tq[s];
               wk *= lastg ? kv.vb : (kv.vb + kv.vs * (double)(k == z1));
               w[s] = (k < K) ? wk : 0.0;
             }
-            zkprev = warp_choice<SF>(w, __shfl_sync(FULL, uw, j & 31), K, lane);
+            zkprev = warp_choice_contig<SF>(w, __shfl_sync(FULL, uw, j & 31), K, lane);
             if (lane == 0) zk[j] = (uint8_t)zkprev;
           }
           zk_last = zkprev;

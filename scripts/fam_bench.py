@@ -20,6 +20,7 @@ ap.add_argument("--check", type=int, default=0, help="families compared with the
 ap.add_argument("--mean-group", type=float, default=1.0)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--unrelated", action="store_true", help="also time the unrelated branch on the same haplotypes")
+ap.add_argument("--mixed", type=int, default=0, help="also time both branches in one call (that many unrelated haplotypes), one after the other and overlapped")
 a = ap.parse_args()
 
 t0 = time.time()
@@ -34,12 +35,22 @@ ref3 = sp.ref[:, None, :]
 runs = [("related only", np.zeros(0, np.int32), fams)]
 if a.unrelated:
     runs.append(("unrelated only", np.sort(members).astype(np.int32), None))
+if a.mixed:
+    rest = np.setdiff1d(np.arange(sp.N), members)[:a.mixed].astype(np.int32)
+    runs.append(("unrelated part", rest, None))
+    runs.append(("both, sequential", rest, fams))
+    runs.append(("both, overlapped", rest, fams))
+import os
 for label, unrel, fam in runs:
+    if label.startswith("both"):
+        os.environ["KGW_FAMILY_OVERLAP"] = "1" if "overlapped" in label else "0"
     plan = kg.Plan(sp.H, sp.p, sp.K, ref3, sp.b, sp.mu, sp.groups, unrelated=unrel, ref_global=sp.ref, seed=sp.seed, families=fam)
     plan.run(); plan.sync()
     ms = plan.run_timed(a.iters)
-    n = len(members)
-    print(f"  {label:16s} {ms:10.3f} ms  {n * sp.p / (ms * 1e-3):.3e} hap-SNPs/s", flush=True)
+    n = (len(members) if fam else 0) + (len(unrel) if (not fam or label.startswith("both")) else 0)
+    if label == "unrelated only":
+        n = len(unrel)
+    print(f"  {label:16s} {ms:10.3f} ms  {n * sp.p / (ms * 1e-3):.3e} hap-SNPs/s  ({n} haplotypes)", flush=True)
     if fam and a.check:
         import kgw_oracle as ko
         hk, dbg = plan.download(debug_paths=True)
