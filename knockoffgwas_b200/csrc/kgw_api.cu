@@ -319,7 +319,7 @@ namespace {
 // Related branch (generate_related, knockoffs.cpp:329-571): host pre-processing of the families into
 // the flat structures of kgw_family.cuh.
 struct FamilyState {
-  int n_families = 0, n_max = 0, members_total = 0, SF = 1, grid = 0, threads = 128;
+  int n_families = 0, n_max = 0, members_total = 0, SF = 1, grid = 0, threads = 128, rtot = 1;
   size_t smem = 0;
   std::vector<int32_t> h_members;                 // concatenated, family order
   std::vector<int32_t> h_fam_off, h_seg_off, h_seg_jmin, h_seg_jmax, h_seg_ids_off, h_seg_ids;
@@ -337,7 +337,7 @@ struct FamilyState {
   KgwFamOp *dops = nullptr;
   KgwFamLocus *dloc = nullptr;
   KgwLocusKO *dko = nullptr;
-  double *demtab = nullptr, *dmsg = nullptr;
+  double *demtab = nullptr, *dmsg = nullptr, *dmrc = nullptr;
   uint8_t *dpat = nullptr, *dbytes = nullptr;
   int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
   std::vector<KgwFamDesc> fams;                   // op_off / n_ops are refreshed by set_groups
@@ -676,9 +676,16 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     for (int b : bnd) {
       const int s0 = std::max(0, b - 2), s1 = std::min(p - 1, b + 1);
       if ((int)ranges.size() > d.rng_off && s0 <= ranges.back().s1 + 1) ranges.back().s1 = std::max(ranges.back().s1, s1);
-      else ranges.push_back(KgwFamRange{s0, s1});
+      else ranges.push_back(KgwFamRange{s0, s1, 0, 0});
     }
     d.n_rng = (int32_t)ranges.size() - d.rng_off;
+    // right messages are stored at the special loci and one locus before each range (kgw_family.cuh)
+    int stored = 0;
+    for (int r = d.rng_off; r < (int)ranges.size(); r++) {
+      ranges[r].off = stored;
+      stored += ranges[r].s1 - std::max(0, ranges[r].s0 - 1) + 1;
+    }
+    F->rtot = std::max(F->rtot, std::max(stored, 1));
   }
   // node emission table (family_bp.cpp:437-454) when mu is the same at every locus (init_hmm, knockoffs.cpp:1520)
   bool uniform = true;
@@ -728,7 +735,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   F->SF = (K + 31) / 32 <= 1 ? 1 : ((K + 31) / 32 <= 2 ? 2 : ((K + 31) / 32 <= 4 ? 4 : 8));
   F->threads = 128;
   const int wpc = F->threads / 32;
-  F->smem = (size_t)8 * 256 * sizeof(double) + (size_t)wpc * F->n_max * F->SF * 32 * sizeof(double);
+  F->smem = (size_t)8 * 256 * sizeof(double) + (size_t)wpc * 2 * F->n_max * F->SF * 32 * sizeof(double);
   int ctas_per_sm = 4;
   {
     void (*fnq)(const KgwFamParams) = fam_kernel_for(F->SF, uniform);
@@ -736,7 +743,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     KGW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fnq, F->threads, F->smem));
     ctas_per_sm = std::max(1, ctas_per_sm);
   }
-  const size_t per_slot = (size_t)F->n_max * p * ((size_t)K * 17 + 2);
+  const size_t per_slot = (size_t)F->n_max * p * ((size_t)K * 9 + 2) + (size_t)F->n_max * F->rtot * K * sizeof(double);
   size_t free_b = 0, total_b = 0;
   KGW_CUDA(cudaMemGetInfo(&free_b, &total_b));
   free_b += g_pool.parked(pl->device);
@@ -753,7 +760,8 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     KGW_CUDA(cudaEventCreateWithFlags(&F->ev_fork, cudaEventDisableTiming));
     KGW_CUDA(cudaEventCreateWithFlags(&F->ev_join, cudaEventDisableTiming));
   }
-  KGW_CUDA(pl->alloc(&F->dmsg, sizeof(double) * 2 * F->n_max * (size_t)p * K * nslots));   // pooled with the plan's buffers
+  KGW_CUDA(pl->alloc(&F->dmsg, sizeof(double) * F->n_max * (size_t)p * K * nslots));   // pooled with the plan's buffers
+  KGW_CUDA(pl->alloc(&F->dmrc, sizeof(double) * F->n_max * (size_t)F->rtot * K * nslots));
   KGW_CUDA(pl->alloc(&F->dpat, (size_t)F->n_max * p * K * nslots));
   KGW_CUDA(pl->alloc(&F->dbytes, (size_t)2 * F->n_max * p * nslots));
 
@@ -761,7 +769,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   P.N = N; P.p = p; P.K = K; P.n_families = F->n_families; P.stride_w = pl->stride_w; P.n_max = F->n_max;
   P.uniform_mu = uniform ? 1 : 0;
   P.Hw = pl->dHw; P.ref_global = F->dref_global; P.fams = F->dfams; P.members = F->dmembers; P.iv_start = F->divstart;
-  P.ivs = F->divs; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.msg = F->dmsg; P.pat = F->dpat;
+  P.ivs = F->divs; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.msg = F->dmsg; P.mrc = F->dmrc; P.rtot = F->rtot; P.pad0 = 0; P.pat = F->dpat;
   P.phase_cycles = nullptr;
 #ifdef KGW_PHASES
   KGW_CUDA(cudaMalloc(&F->dphase, sizeof(long long) * 8));

@@ -26,6 +26,13 @@
 // after a few hundred loci, so iterations after the first cost a few per cent of a full sweep (85 % of
 // the reference's message updates are such no-ops on the synthetic pairs; rule checked on the CPU
 // against the oracle: 0 violations).
+//
+// Right messages are not stored in plain stretches.  Nothing reads them there except the sweep itself (the left
+// sweep, the junction draws and the final draws use right messages only at special loci or analytically), and
+// the sweep needs the old value of a node only to measure its change: when a stretch is re-entered with a changed
+// input, the OLD chain is recomputed beside the new one from the old input (bit-identical to what a stored copy
+// would hold) until the two agree bit for bit.  A slot therefore holds 8 K + K bytes per (member, locus) instead
+// of 16 K + K, which is what bounds the number of resident families on long chromosomes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -48,7 +55,11 @@ struct KgwFamInterval {  // maximal run of loci over which neighbors[i][j] is co
   int32_t pad;
 };
 
-struct KgwFamRange { int32_t s0, s1; };  // special loci, inclusive; sorted, disjoint
+struct KgwFamRange {   // special loci s0 .. s1, inclusive; sorted, disjoint
+  int32_t s0, s1;
+  int32_t off;         // row of locus max(0, s0 - 1) in the family's stored right messages
+  int32_t pad;
+};
 
 enum { KGW_FOP_COPYZ = 0, KGW_FOP_DRAW = 1, KGW_FOP_COPYZK = 2 };
 struct KgwFamOp {  // FamilyKnockoffs::run (family_knockoffs.cpp:155-270) flattened in execution order
@@ -92,7 +103,9 @@ struct KgwFamParams {
   const int32_t *grp_last;     // [n_groups]
   const double *emtab;         // [8][256] node emission by (neighbours, match pattern); uniform mu only
   uint32_t *Hk;                // [N][stride_w]
-  double *msg;                 // [slots][2][n_max][p][K]
+  double *msg;                 // [slots][n_max][p][K]      messages_left
+  double *mrc;                 // [slots][n_max][rtot][K]   messages_right at the stored loci (special ranges + one locus before)
+  int32_t rtot, pad0;          // stored loci per member (maximum over the families)
   uint8_t *pat;                // [slots][n_max][p][K]
   uint8_t *bytes;              // [slots][2][n_max][p]   Z (255 = node still active), Zk
   int32_t *work;               // next family to hand out (zeroed before every launch)
@@ -115,6 +128,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
+}
+__device__ __forceinline__ void warp_sum2(double &a, double &b) {   // two sums in one shuffle tree
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ta = __shfl_xor_sync(FULL, a, o);
+    const double tb = __shfl_xor_sync(FULL, b, o);
+    a += ta;
+    b += tb;
+  }
 }
 __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 #pragma unroll
@@ -192,15 +214,16 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
   const int slot = blockIdx.x * wpc + wid;
   const int p = P.p, K = P.K;
   const size_t pK = (size_t)p * K;
-  double *mr_base = P.msg + (size_t)slot * 2 * P.n_max * pK;   // messages_right [n][p][K]
-  double *ml_base = mr_base + (size_t)P.n_max * pK;            // messages_left
+  double *ml_base = P.msg + (size_t)slot * P.n_max * pK;                       // messages_left [n][p][K]
+  double *mrc = P.mrc + (size_t)slot * P.n_max * (size_t)P.rtot * K;          // messages_right, stored loci only
   uint8_t *pat_base = P.pat + (size_t)slot * P.n_max * pK;
   uint8_t *Zb = P.bytes + (size_t)slot * 2 * P.n_max * p;     // 255 = not drawn yet = node still active
   uint8_t *Zkb = Zb + (size_t)P.n_max * p;
 
   extern __shared__ __align__(16) unsigned char fam_smem[];
   double *tab = reinterpret_cast<double *>(fam_smem);                       // [8][256], shared by the CTA
-  double *pm = tab + 8 * 256 + (size_t)wid * P.n_max * KP;                  // [n_max][KP] last message of each chain
+  double *pm = tab + 8 * 256 + (size_t)wid * 2 * P.n_max * KP;              // [n_max][KP] last message of each chain
+  double *pm_old = pm + (size_t)P.n_max * KP;                               // ... and its value before this sweep touched it
   if (UMU) {
     for (int t = threadIdx.x; t < 8 * 256; t += blockDim.x) tab[t] = P.emtab[t];
   }
@@ -226,6 +249,18 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
       const KgwFamInterval *iv = P.ivs + ivs0[i];
       while (iv->j1 < j) iv++;
       return iv;
+    };
+    // right message row of (i, j) inside the stored span of a range (ext0 = max(0, s0 - 1) .. s1)
+    auto mr_row = [&](int i, int j, int ext0, int off) -> double * {
+      return mrc + ((size_t)i * P.rtot + (size_t)(off + (j - ext0))) * K;
+    };
+    auto mr_find = [&](int i, int j) -> double * {   // outside the sweeps: look the range up
+      for (int r = 0; r < nrng; r++) {
+        const KgwFamRange rg = rngs[r];
+        const int ext0 = max(0, rg.s0 - 1);
+        if (j >= ext0 && j <= rg.s1) return mr_row(i, j, ext0, rg.off);
+      }
+      return mrc;   // not reached: every caller asks for a stored locus
     };
     // emission of node (i, j) for state k (family_bp.cpp:437-454)
     auto emission_of = [&](unsigned pt, int j, int nn) -> double {
@@ -313,17 +348,19 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
       int j = (dir == 0) ? 0 : p - 1;
       unsigned nnpack = 0;                    // neighbour count of every member at the current locus, 3 bits each
       for (int i = 0; i < n; i++) nnpack |= (unsigned)find_iv(i, j)->nn << (3 * i);
-      double *dstb = (dir == 0) ? mr_base : ml_base;
       bool valid[SF];
 #pragma unroll
       for (int s = 0; s < SF; s++) valid[s] = (s * 32 + lane < K);
+      int prev_ext0 = 0, prev_off = 0;        // stored span of the range behind the sweep position
 
       for (int rr = 0; rr <= nrng; rr++) {
-        int s_first = 0, s_last = -1;
+        int s_first = 0, s_last = -1, cur_ext0 = 0, cur_off = 0;
         if (rr < nrng) {
           const KgwFamRange rg = rngs[dir == 0 ? rr : nrng - 1 - rr];
           s_first = (dir == 0) ? rg.s0 : rg.s1;
           s_last = (dir == 0) ? rg.s1 : rg.s0;
+          cur_ext0 = max(0, rg.s0 - 1);
+          cur_off = rg.off;
         }
         // ---- plain stretch j .. e (sweep order)
         int e = (rr < nrng) ? s_first - step : jlast;
@@ -336,73 +373,150 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             if (!((todo >> i) & 1u)) continue;
             const int nn = (int)((nnpack >> (3 * i)) & 7u);
             const size_t rowo = ((size_t)i * p + j) * K + lane;
-            const ptrdiff_t sK = (ptrdiff_t)step * K;
+            constexpr ptrdiff_t sgn = step;
+            const ptrdiff_t sK = sgn * K;
             const uint8_t *pp = pat_base + rowo;
-            double *dp = dstb + rowo;
             const KgwFamLocus *lp = P.loc + (dir == 0 ? j + 1 : j);
             const bool hasv = (dir == 0) ? (j > 0) : (j < p - 1);
-            double v[SF];
             unsigned ptc[SF];
 #pragma unroll
-            for (int s = 0; s < SF; s++) {
-              v[s] = 1.0;   // no incoming message at the first node of the sweep
-              if (valid[s] && hasv) v[s] = ((comp_prev >> i) & 1u) ? pm[i * KP + s * 32 + lane] : dp[s * 32 - sK];
-              ptc[s] = valid[s] ? pp[s * 32] : 0u;
-            }
+            for (int s = 0; s < SF; s++) ptc[s] = valid[s] ? pp[s * 32] : 0u;
             double lb = lp->b, lw = lp->w, lr1 = lp->r1;
             bool ch = true;
             int t = 0;
-            for (; t < len; t++) {
-              // fetches for the next locus of this chain, and L2 prefetches further ahead
-              unsigned ptn[SF];
-              double oldv[SF];
-              const bool more = (t + 1 < len);
+            double v[SF];
+            if constexpr (dir == 0) {
+              // right sweep: nothing of the stretch is stored except its last locus (the next range reads it);
+              // when not `full`, vo[] follows the chain as it was before this sweep
+              double vo[SF];
+              const double *prow = (hasv && !((comp_prev >> i) & 1u)) ? mr_row(i, j - 1, prev_ext0, prev_off) : nullptr;
 #pragma unroll
               for (int s = 0; s < SF; s++) {
-                ptn[s] = (valid[s] && more) ? pp[sK + s * 32] : 0u;
-                oldv[s] = (valid[s] && !full) ? dp[s * 32] : (valid[s] ? p0 : 0.0);
-              }
-              const double lbn = more ? lp[step].b : 0.0, lwn = more ? lp[step].w : 1.0, lr1n = more ? lp[step].r1 : 0.0;
-              if ((t & 3) == 0 && t + 12 < len) {   // rows t+8 .. t+11 of this chain (contiguous in memory)
-                fam_prefetch(pp + (dir == 0 ? 8 : 11) * sK - lane, 4 * K, lane);
-                if (!full) fam_prefetch(dp + (dir == 0 ? 8 : 11) * sK - lane, 32 * K, lane);
-              }
-              double q[SF];
-              double qsum = 0.0;
-#pragma unroll
-              for (int s = 0; s < SF; s++) {
-                q[s] = 0.0;
-                if (valid[s]) {
-                  q[s] = emission_of(ptc[s], j + t * step, nn) * v[s];
-                  qsum += q[s];
+                v[s] = 1.0;   // no incoming message at the first node of the sweep
+                vo[s] = 1.0;
+                if (valid[s] && hasv) {
+                  v[s] = prow ? prow[s * 32 + lane] : pm[i * KP + s * 32 + lane];
+                  vo[s] = full ? v[s] : pm_old[i * KP + s * 32 + lane];
                 }
               }
-              const double S = warp_sum(qsum);
-              const double c2 = lb * fast_rcp(S * lw);
-              bool ne = false;
+              double *lastrow = (rr < nrng) ? mr_row(i, e, cur_ext0, cur_off) : nullptr;
+              for (; t < len; t++) {
+                unsigned ptn[SF];
+                const bool more = (t + 1 < len);
+#pragma unroll
+                for (int s = 0; s < SF; s++) ptn[s] = (valid[s] && more) ? pp[sK + s * 32] : 0u;
+                const double lbn = more ? lp[step].b : 0.0, lwn = more ? lp[step].w : 1.0, lr1n = more ? lp[step].r1 : 0.0;
+                if ((t & 3) == 0 && t + 12 < len) fam_prefetch(pp + 8 * sK - lane, 4 * K, lane);
+                double q[SF], qo[SF];
+                double qsum = 0.0, qosum = 0.0;
+#pragma unroll
+                for (int s = 0; s < SF; s++) {
+                  q[s] = 0.0;
+                  qo[s] = 0.0;
+                  if (valid[s]) {
+                    const double fk = emission_of(ptc[s], j + t, nn);
+                    q[s] = fk * v[s];
+                    qsum += q[s];
+                    if (!full) { qo[s] = fk * vo[s]; qosum += qo[s]; }
+                  }
+                }
+                bool ne = false;
+                if (full) {
+                  const double c2 = lb * fast_rcp(warp_sum(qsum) * lw);
+#pragma unroll
+                  for (int s = 0; s < SF; s++) {
+                    if (valid[s]) {
+                      v[s] = lr1 + c2 * q[s];
+                      diff += fabs(v[s] - p0);
+                    }
+                  }
+                  ch = true;
+                } else {
+                  warp_sum2(qsum, qosum);
+                  const double c2 = lb * fast_rcp(qsum * lw), c2o = lb * fast_rcp(qosum * lw);
+#pragma unroll
+                  for (int s = 0; s < SF; s++) {
+                    if (valid[s]) {
+                      v[s] = lr1 + c2 * q[s];
+                      vo[s] = lr1 + c2o * qo[s];
+                      diff += fabs(v[s] - vo[s]);
+                      ne |= (v[s] != vo[s]);
+                    }
+                  }
+                  ch = __any_sync(FULL, ne);
+                }
+                if (!more && lastrow && ch) {
+#pragma unroll
+                  for (int s = 0; s < SF; s++) if (valid[s]) lastrow[s * 32 + lane] = v[s];
+                }
+                pp += sK;
+                lp += step;
+                lb = lbn;
+                lw = lwn;
+                lr1 = lr1n;
+#pragma unroll
+                for (int s = 0; s < SF; s++) ptc[s] = ptn[s];
+                if (!full && !ch) { t++; break; }   // the two chains agree bit for bit: everything further on is clean
+              }
+            } else {
+              double *dp = ml_base + rowo;
 #pragma unroll
               for (int s = 0; s < SF; s++) {
-                if (valid[s]) {
-                  const double nv = lr1 + c2 * q[s];
-                  diff += fabs(nv - oldv[s]);
-                  ne |= (nv != oldv[s]);
-                  v[s] = nv;
+                v[s] = 1.0;
+                if (valid[s] && hasv) v[s] = ((comp_prev >> i) & 1u) ? pm[i * KP + s * 32 + lane] : dp[s * 32 - sK];
+              }
+              for (; t < len; t++) {
+                // fetches for the next locus of this chain, and L2 prefetches further ahead
+                unsigned ptn[SF];
+                double oldv[SF];
+                const bool more = (t + 1 < len);
+#pragma unroll
+                for (int s = 0; s < SF; s++) {
+                  ptn[s] = (valid[s] && more) ? pp[sK + s * 32] : 0u;
+                  oldv[s] = (valid[s] && !full) ? dp[s * 32] : (valid[s] ? p0 : 0.0);
                 }
-              }
-              ch = __any_sync(FULL, ne);
-              if (full || ch) {
+                const double lbn = more ? lp[step].b : 0.0, lwn = more ? lp[step].w : 1.0, lr1n = more ? lp[step].r1 : 0.0;
+                if ((t & 3) == 0 && t + 12 < len) {   // rows t+8 .. t+11 of this chain (contiguous in memory)
+                  fam_prefetch(pp + 11 * sK - lane, 4 * K, lane);
+                  if (!full) fam_prefetch(dp + 11 * sK - lane, 32 * K, lane);
+                }
+                double q[SF];
+                double qsum = 0.0;
 #pragma unroll
-                for (int s = 0; s < SF; s++) if (valid[s]) dp[s * 32] = v[s];
-              }
-              pp += sK;
-              dp += sK;
-              lp += step;
-              lb = lbn;
-              lw = lwn;
-              lr1 = lr1n;
+                for (int s = 0; s < SF; s++) {
+                  q[s] = 0.0;
+                  if (valid[s]) {
+                    q[s] = emission_of(ptc[s], j - t, nn) * v[s];
+                    qsum += q[s];
+                  }
+                }
+                const double S = warp_sum(qsum);
+                const double c2 = lb * fast_rcp(S * lw);
+                bool ne = false;
 #pragma unroll
-              for (int s = 0; s < SF; s++) ptc[s] = ptn[s];
-              if (!full && !ch) { t++; break; }   // bit-identical message: everything further along this chain is clean
+                for (int s = 0; s < SF; s++) {
+                  if (valid[s]) {
+                    const double nv = lr1 + c2 * q[s];
+                    diff += fabs(nv - oldv[s]);
+                    ne |= (nv != oldv[s]);
+                    v[s] = nv;
+                  }
+                }
+                ch = __any_sync(FULL, ne);
+                if (full || ch) {
+#pragma unroll
+                  for (int s = 0; s < SF; s++) if (valid[s]) dp[s * 32] = v[s];
+                }
+                pp += sK;
+                dp += sK;
+                lp += step;
+                lb = lbn;
+                lw = lwn;
+                lr1 = lr1n;
+#pragma unroll
+                for (int s = 0; s < SF; s++) ptc[s] = ptn[s];
+                if (!full && !ch) { t++; break; }   // bit-identical message: everything further along this chain is clean
+              }
             }
             if (t == len) {   // the chain reached the end of the stretch: hand its last message to the next range
 #pragma unroll
@@ -429,7 +543,9 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             const int ndl = (j == iv->j0 && j > 0) ? iv->ndl : 0;
             const int ndr = (j == iv->j1 && j < p - 1) ? iv->ndr : 0;
             const size_t rowo = ((size_t)i * p + j) * K;
-            const double *prevg = dstb + rowo - (ptrdiff_t)step * K;   // own chain, one locus back in sweep order
+            double *dst = (dir == 0) ? mr_row(i, j, cur_ext0, cur_off) : ml_base + rowo;
+            // own chain, one locus back in sweep order (for the right sweep: inside the stored span of this range)
+            const double *prevg = (dir == 0) ? mr_row(i, j - 1, cur_ext0, cur_off) : ml_base + rowo + K;
             const bool prev_sm = (comp_prev >> i) & 1u;
             double msg[SF], oldv[SF];
             double qsum = 0.0;
@@ -440,14 +556,14 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
               oldv[s] = 0.0;
               if (k < K) {
                 double q = emission_of(pat_base[rowo + k], j, nn);
-                oldv[s] = full ? p0 : dstb[rowo + k];
+                oldv[s] = full ? p0 : dst[k];
                 if (has_prev) q *= prev_sm ? pm[i * KP + k] : prevg[k];
                 if (dir == 0) {
-                  for (int t = 0; t < ndl; t++) q *= mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k];
+                  for (int t = 0; t < ndl; t++) q *= mr_row(iv->dl[t], j - 1, cur_ext0, cur_off)[k];
                   for (int t = 0; t < ndr; t++) q *= full ? p0 : ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k];
                 } else {
                   for (int t = 0; t < ndr; t++) q *= ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k];
-                  for (int t = 0; t < ndl; t++) q *= mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k];
+                  for (int t = 0; t < ndl; t++) q *= mr_row(iv->dl[t], j - 1, cur_ext0, cur_off)[k];
                 }
                 msg[s] = q;
                 qsum += q;
@@ -470,8 +586,9 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             for (int s = 0; s < SF; s++) {
               const int k = s * 32 + lane;
               if (k < K) {
-                if (full || ch) dstb[rowo + k] = msg[s];
+                if (full || ch) dst[k] = msg[s];
                 pm[i * KP + k] = msg[s];
+                if (dir == 0) pm_old[i * KP + k] = oldv[s];
               }
             }
             comp_cur |= 1u << i;
@@ -480,6 +597,8 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
           comp_prev = comp_cur;
           chg_prev = chg_cur;
         }
+        prev_ext0 = cur_ext0;
+        prev_off = cur_off;
       }
       return diff;
     };
@@ -504,7 +623,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
       for (int l = lane; l < K; l += 32) {
         if (j < p - 1) {
           const KgwFamLocus lc = P.loc[j + 1];
-          mr_base[((size_t)i * p + j) * K + l] = lc.a_al + lc.b * (double)(l == kz);
+          mr_find(i, j)[l] = lc.a_al + lc.b * (double)(l == kz);
         }
         if (j > 0) {
           const KgwFamLocus lc = P.loc[j];
@@ -525,8 +644,8 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
         if (k < K) {
           double v = emission_of(pat_base[((size_t)i * p + j) * K + k], j, iv->nn);
           if (j > 0) {
-            v *= mr_base[((size_t)i * p + j - 1) * K + k];
-            for (int t = 0; t < ndl; t++) v *= mr_base[((size_t)iv->dl[t] * p + j - 1) * K + k];
+            v *= mr_find(i, j - 1)[k];
+            for (int t = 0; t < ndl; t++) v *= mr_find(iv->dl[t], j - 1)[k];
           }
           if (j < p - 1) {
             v *= ml_base[((size_t)i * p + j + 1) * K + k];
