@@ -171,3 +171,53 @@ def write_bgen_image(H: np.ndarray, p: int, compression: int = 0, level: int = 1
             blk = struct.pack("<II", len(z) + 4, len(raw)) + z
         parts.append(ident + blk)
     return np.frombuffer(b"".join(parts), dtype=np.uint8)
+
+
+def add_ibd_families(prob: SynthProblem, n_families: int, size: int = 3, segments: int = 4, seed: int = 9,
+                     min_len_bp: int = 100_000) -> SynthProblem:
+    """Families of `size` haplotypes (different samples) sharing `segments` IBD segments, each among a random subset of
+    at least two members: nodes with several neighbours, members joining and leaving at different loci.  Segments of
+    a family neither overlap nor touch (two loci apart at least) and span >= `min_len_bp`, so they are already what
+    IbdCluster::tidy (ibd.cpp:99-189) would return; order: fewer indices first, then index set, then j_min
+    (IbdSeg::operator<, ibd.cpp:482-509).  Alleles of the subset's first member are copied onto the others."""
+    rng = np.random.default_rng([prob.seed, seed, size])
+    N, p = prob.N, prob.p
+    taken = {int(x) for m, _ in prob.families for x in m}
+    free_samples = [s for s in rng.permutation(N // 2) if 2 * s not in taken and 2 * s + 1 not in taken]
+    if len(free_samples) < n_families * size:
+        raise ValueError("not enough unrelated samples left")
+    fams = list(prob.families)
+    for f in range(n_families):
+        mem = np.sort(np.array([2 * free_samples[f * size + t] + int(rng.integers(2)) for t in range(size)], dtype=np.int32))
+        cuts = np.sort(rng.choice(np.arange(2, p - 2), size=2 * segments, replace=False))
+        segs = []
+        for q in range(segments):
+            j0, j1 = int(cuts[2 * q]) + 1, int(cuts[2 * q + 1]) - 1
+            if j1 - j0 < 3 or prob.bp[j1] - prob.bp[j0] < min_len_bp:
+                continue
+            ids = np.sort(rng.choice(mem, size=int(rng.integers(2, size + 1)), replace=False)).astype(np.int32)
+            src = np.unpackbits(prob.H[ids[0]], bitorder="little")
+            for other in ids[1:]:
+                row = np.unpackbits(prob.H[other], bitorder="little")
+                row[j0:j1 + 1] = src[j0:j1 + 1]
+                prob.H[other] = np.packbits(row, bitorder="little")
+            segs.append((j0, j1, ids))
+        if not segs:
+            continue
+        linked = set()
+        for _, _, ids in segs:
+            linked |= {int(x) for x in ids}
+        mem = np.array(sorted(linked), dtype=np.int32)     # members without any segment are not part of the family
+        segs.sort(key=lambda sg: (len(sg[2]), tuple(int(x) for x in sg[2]), sg[0]))
+        for me in mem:                                      # relatives are never references
+            for other in mem:
+                hit = np.flatnonzero(prob.ref[me] == other)
+                if me != other and len(hit):
+                    cand = int(other)
+                    while cand in mem or cand in prob.ref[me]:
+                        cand = int(rng.integers(max(0, me - 2000), min(N, me + 2000)))
+                    prob.ref[me, hit[0]] = cand
+                    prob.ref[me].sort()
+        fams.append((mem, segs))
+    prob.families = fams
+    return prob

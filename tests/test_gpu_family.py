@@ -110,3 +110,27 @@ def test_family_kernel_synthetic_pairs(K, mean_group):
         assert np.array_equal(dbg.fam_zk[row:row + 2], r.zk), f"Zk of pair {mem.tolist()}"
         assert np.array_equal(hk[mem], r.hk), f"Hk of pair {mem.tolist()}"
         row += 2
+
+
+@pytest.mark.parametrize("size,K", [(3, 20), (4, 50), (6, 12)])
+def test_family_kernel_synthetic_larger_families(size, K):
+    """Families of 3-6 haplotypes whose segments involve changing subsets of the members (nodes with up to 5
+    neighbours, several members joining / leaving at one junction): the generic junction paths, the special-range
+    bookkeeping and the recomputed right messages against the oracle."""
+    from knockoffgwas_b200 import synth
+    sp = synth.make_problem(400, 1600, K, seed=21, n_founders=40, mean_dist_cm=0.02)
+    synth.add_ibd_families(sp, 6, size=size, segments=5)
+    assert len(sp.families) >= 4 and max(len(m) for m, _ in sp.families) >= 3
+    prob = ko.Problem(H=sp.H, p=sp.p, K=K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu,
+                      groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
+    hk, dbg = kg.generate(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=np.zeros(0, np.int32),
+                          ref_global=sp.ref, seed=sp.seed, families=sp.families, debug_paths=True)
+    rng, _ = ko.make_rng(prob, mode="philox")
+    row = 0
+    for mem, segs in sp.families:
+        r = ko.run_family(prob, mem, [(s[0], s[1], 0, 0, s[2]) for s in segs], rng)
+        n = len(mem)
+        assert np.array_equal(dbg.fam_z[row:row + n], r.z), f"Z of family {mem.tolist()}"
+        assert np.array_equal(dbg.fam_zk[row:row + n], r.zk), f"Zk of family {mem.tolist()}"
+        assert np.array_equal(hk[mem], r.hk), f"Hk of family {mem.tolist()}"
+        row += n

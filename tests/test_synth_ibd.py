@@ -41,3 +41,24 @@ def test_oracle_runs_synthetic_pair_and_shares_paths_on_segments():
         for j0, j1, _ in segs:                                   # one latent path / knockoff path inside a segment
             assert np.array_equal(r.z[0, j0:j1 + 1], r.z[1, j0:j1 + 1])
             assert np.array_equal(r.zk[0, j0:j1 + 1], r.zk[1, j0:j1 + 1])
+
+
+def test_larger_families_are_tidy_and_identical_on_segments():
+    sp = synth.make_problem(300, 1200, 10, seed=2, n_founders=30, mean_dist_cm=0.02)
+    synth.add_ibd_families(sp, 5, size=4, segments=5)
+    bits = np.unpackbits(sp.H, axis=1, bitorder="little")[:, :sp.p]
+    assert sp.families
+    for mem, segs in sp.families:
+        assert len({int(m) // 2 for m in mem}) == len(mem)               # one haplotype per sample
+        spans = sorted((j0, j1) for j0, j1, _ in segs)
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert b0 > a1 + 1                                              # neither overlapping nor touching
+        keys = [(len(ids), tuple(int(x) for x in ids), j0) for j0, _, ids in segs]
+        assert keys == sorted(keys)                                         # std::set<IbdSeg> order
+        for j0, j1, ids in segs:
+            assert set(int(x) for x in ids) <= set(int(x) for x in mem) and len(ids) >= 2
+            assert sp.bp[j1] - sp.bp[j0] >= 100_000
+            for other in ids[1:]:
+                assert np.array_equal(bits[ids[0], j0:j1 + 1], bits[other, j0:j1 + 1])
+        for me in mem:
+            assert not (set(int(x) for x in sp.ref[me]) & set(int(x) for x in mem))
