@@ -36,8 +36,8 @@ enum { BGEN_BAD_HEADER = 1, BGEN_BAD_PLOIDY = 2, BGEN_BAD_PROB = 4 };
 // Pass 1, one thread per output column: checks the block header and leaves (offset of the probability stream |
 // B << 56) for pass 2.
 __global__ void __launch_bounds__(256) bgen_header_kernel(const uint8_t *__restrict__ blocks, const long long *__restrict__ col_off,
-                                                          int n_samples_bgen, int p, unsigned long long *__restrict__ colinfo,
-                                                          int *__restrict__ status) {
+                                                          const long long *__restrict__ col_len, int n_samples_bgen, int p,
+                                                          unsigned long long *__restrict__ colinfo, int *__restrict__ status) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p) return;
   const uint8_t *blk = blocks + col_off[j];
@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(256) bgen_header_kernel(const uint8_t *__restr
   const uint32_t pmin = blk[6], pmax = blk[7];
   uint32_t phased = 0, B = 0;
   if (nfile == (uint32_t)n_samples_bgen) { phased = blk[8 + n_samples_bgen]; B = blk[9 + n_samples_bgen]; }
-  if (nfile != (uint32_t)n_samples_bgen || nall != 2u || pmin != 2u || pmax != 2u || phased != 1u || B < 1u || B > 32u) {
+  // the block must hold its header, the ploidy bytes and 2 N values of B bits
+  const long long need = 10ll + n_samples_bgen + ((2ll * n_samples_bgen * (long long)B + 7) >> 3);
+  if (nfile != (uint32_t)n_samples_bgen || nall != 2u || pmin != 2u || pmax != 2u || phased != 1u || B < 1u || B > 32u ||
+      col_len[j] < need) {
     atomicOr(status, BGEN_BAD_HEADER);
     B = 0;
   }
@@ -209,12 +212,13 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
     if (sample_idx[i] < 0 || (uint32_t)sample_idx[i] >= nfile) return kgw_fail_(KGW_ERR_INVALID, "sample index outside the BGEN sample block");
   // Uncompressed files go to the device as they are (one copy of the span that holds the requested blocks);
   // compressed blocks are inflated into a staging buffer first, 16-byte aligned one after the other.
-  std::vector<long long> col_off(p);
+  std::vector<long long> col_off(p), col_len(p);
   long long total = 0, span_lo = file_bytes, span_hi = 0;
   for (int j = 0; j < p; j++) {
     const int v = variant_of_col[j];
     if (v < 0 || (size_t)v >= idx.size()) return kgw_fail_(KGW_ERR_INVALID, "variant index outside the BGEN file");
     if (idx[v].raw_len < 10 + (int64_t)nfile) return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block shorter than its header");
+    col_len[j] = idx[v].raw_len;
     if (compression == 0u) {
       span_lo = std::min<long long>(span_lo, idx[v].data_off);
       span_hi = std::max<long long>(span_hi, idx[v].data_off + idx[v].raw_len);
@@ -234,12 +238,12 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   do {                                                                                                       \
     cudaError_t e_ = (call);                                                                                 \
     if (e_ != cudaSuccess) {                                                                                 \
-      free(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus); \
+      free(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dlen); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus); \
       return kgw_fail_(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
     }                                                                                                        \
   } while (0)
   uint8_t *stage = nullptr, *dblocks = nullptr;
-  long long *doff = nullptr;
+  long long *doff = nullptr, *dlen = nullptr;
   unsigned long long *dinfo = nullptr;
   int32_t *dsidx = nullptr;
   uint32_t *dH = nullptr;
@@ -287,6 +291,8 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   KGW_CUDA_B(cudaMalloc(&dblocks, (size_t)total + 16));
   KGW_CUDA_B(cudaMalloc(&doff, sizeof(long long) * p));
   KGW_CUDA_B(cudaMalloc(&dinfo, sizeof(unsigned long long) * p));
+  KGW_CUDA_B(cudaMalloc(&dlen, sizeof(long long) * p));
+  KGW_CUDA_B(cudaMemcpy(dlen, col_len.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
   KGW_CUDA_B(cudaMalloc(&dsidx, sizeof(int32_t) * n_samples));
   KGW_CUDA_B(cudaMalloc(&dH, sizeof(uint32_t) * (size_t)n_haps * stride_w));
   KGW_CUDA_B(cudaMalloc(&dstatus, sizeof(int)));
@@ -299,7 +305,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   KGW_CUDA_B(cudaEventCreate(&e1));
   const dim3 grid((unsigned)((stride_w + 3) / 4), (unsigned)((n_haps + 255) / 256));
   KGW_CUDA_B(cudaEventRecord(e0));
-  bgen_header_kernel<<<(p + 255) / 256, 256>>>(dblocks, doff, (int)nfile, p, dinfo, dstatus);
+  bgen_header_kernel<<<(p + 255) / 256, 256>>>(dblocks, doff, dlen, (int)nfile, p, dinfo, dstatus);
   bgen_unpack_kernel<<<grid, 256>>>(dblocks, dinfo, dsidx, (int)nfile, n_haps, p, stride_w, dH, dstatus);
   KGW_CUDA_B(cudaGetLastError());
   KGW_CUDA_B(cudaEventRecord(e1));
@@ -314,7 +320,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   if (st == 0)
     KGW_CUDA_B(cudaMemcpy2D(H_out, (size_t)row_bytes, dH, sizeof(uint32_t) * (size_t)stride_w, (size_t)((p + 7) / 8), (size_t)n_haps,
                             cudaMemcpyDeviceToHost));
-  free(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus);
+  free(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dlen); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus);
 #undef KGW_CUDA_B
   if (st & BGEN_BAD_HEADER)
     return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block is not phased diploid biallelic layout-2 data of the stated sample count");

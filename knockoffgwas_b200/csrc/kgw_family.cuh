@@ -24,8 +24,8 @@
 // very first iteration, (2) the special loci, (3) a node whose own-chain input changed bits earlier in
 // the same sweep; all other nodes are skipped.  The perturbation from a junction dies out bit for bit
 // after a few hundred loci, so iterations after the first cost a few per cent of a full sweep (85 % of
-// the reference's message updates are such no-ops on the synthetic pairs; rule checked on the CPU
-// against the oracle: 0 violations).
+// the reference's message updates are such no-ops on the synthetic pairs; the rule is audited on the CPU
+// by tests/test_family_skip_rule.py: 0 violations).
 //
 // Right messages are not stored in plain stretches.  Nothing reads them there except the sweep itself (the left
 // sweep, the junction draws and the final draws use right messages only at special loci or analytically), and

@@ -79,6 +79,10 @@ typedef struct {
  * taus88 mode they are consumed in the reference's call order.
  * Returns 0, -10 / -11 where the reference aborts ("Missing knockoff variants" /
  * "Inconsistency found on Zk", family_knockoffs.cpp:272-291), other negatives on bad input. */
+/* audit of the CUDA kernel's BP work-skipping rule (see kgw_oracle_family.c); stats = messages, skippable, violations */
+void kgw_oracle_family_audit(int enable);
+void kgw_oracle_family_audit_get(int64_t out[3]);
+
 int kgw_oracle_family_run(const kgw_oracle_problem *P, kgw_oracle_rng *rng, const kgw_oracle_family *F,
                           int32_t *z, int32_t *zk, uint8_t *hk, int64_t *bp_sweeps);
 

@@ -566,3 +566,14 @@ def bgen_write(bits: np.ndarray, rsids, B: int = 8, compression: int = 1, missin
     flags = compression | (2 << 2)
     header = struct.pack("<III", 20, p, n) + b"bgen" + struct.pack("<I", flags)
     return struct.pack("<I", 20) + header + body
+
+
+def family_audit(enable: bool) -> None:
+    """Switch the audit of the CUDA kernel's BP work-skipping rule on / off (and zero its counters)."""
+    lib().kgw_oracle_family_audit(C.c_int(1 if enable else 0))
+
+
+def family_audit_stats() -> dict:
+    out = (C.c_int64 * 3)()
+    lib().kgw_oracle_family_audit_get(out)
+    return {"messages": int(out[0]), "skippable": int(out[1]), "violations": int(out[2])}

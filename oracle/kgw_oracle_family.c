@@ -35,6 +35,7 @@ typedef struct {
   double *mr, *ml;      /* [n][p][K]    messages_right / messages_left */
   double *message, *f_j, *weights;
   int64_t bp_sweeps;
+  int bp_runs;          /* run_bp calls so far (audit only) */
 } fam_ctx;
 
 #define NBC(c, i, j) ((c)->nb_cnt[(int64_t)(i) * (c)->p + (j)])
@@ -206,34 +207,83 @@ static double send_messages_left(fam_ctx *c, int i1, int j, const int32_t *ndl, 
   return diff;
 }
 
+/* ---- audit of the CUDA kernel's work-skipping rule (knockoffgwas_b200/csrc/kgw_family.cuh) --------------------
+ * The kernel recomputes a BP message only (1) in the first iteration of the first run_bp, (2) at the "special"
+ * loci [b-2, b+1] around every locus b where some member's neighbour list changes, (3) when the message one locus
+ * back on the same chain changed bits earlier in the same sweep.  With the audit on, run_bp below still computes
+ * EVERY message exactly as the reference does, and counts the messages the rule would have skipped and, among
+ * them, those whose recomputation did not return the stored bits ("violations": must stay 0).  Results of the
+ * oracle are unaffected. */
+static int g_audit = 0;
+static int64_t g_audit_stats[3]; /* messages, skippable, violations */
+void kgw_oracle_family_audit(int enable) {
+  g_audit = enable;
+  g_audit_stats[0] = g_audit_stats[1] = g_audit_stats[2] = 0;
+}
+void kgw_oracle_family_audit_get(int64_t out[3]) {
+  out[0] = g_audit_stats[0];
+  out[1] = g_audit_stats[1];
+  out[2] = g_audit_stats[2];
+}
+
 /* run_bp (family_bp.cpp:318-419) */
 static int run_bp(fam_ctx *c) {
   const int it_max = 20;
   const int n = c->n, p = c->p, K = c->K;
   int32_t *ndl = (int32_t *)malloc(sizeof(int32_t) * (size_t)(c->NB + 1));
   int32_t *ndr = (int32_t *)malloc(sizeof(int32_t) * (size_t)(c->NB + 1));
+  uint8_t *special = NULL;
+  if (g_audit) {
+    special = (uint8_t *)calloc((size_t)p, 1);
+    for (int b = 1; b < p; b++) {
+      int boundary = 0;
+      for (int i = 0; i < n; i++) boundary |= nb_differ(c, i, b, b - 1);
+      if (boundary)
+        for (int j = b - 2; j <= b + 1; j++)
+          if (j >= 0 && j < p) special[j] = 1;
+    }
+  }
+  const int first_run = (c->bp_runs++ == 0);
   int converged = 0, it = 0;
   while (!converged && (it++ < it_max)) {
     double diff = 0;
+    const int full = first_run && it == 1;
     for (int dir = 0; dir < 2; dir++) { /* "right" then "left" */
       for (int k = 0; k < K; k++) { c->message[k] = 1.0; c->f_j[k] = 1.0; } /* :350-351 */
       double diff_tmp = 0;
+      unsigned changed_prev = 0; /* audit: members whose message one locus back changed bits in this sweep */
       for (int jj = 0; jj < p; jj++) {
         const int j = (dir == 0) ? jj : p - 1 - jj;
+        unsigned changed_cur = 0;
         for (int i = 0; i < n; i++) {
           if (c->inactive[(int64_t)i * p + j]) continue;
           int nl, nr;
           neighbor_diffs(c, i, j, ndl, &nl, ndr, &nr);
+          double *dst = NULL;
+          double d = 0;
           if (dir == 0) {
-            diff_tmp += send_messages_right(c, i, j, ndl, nl, ndr, nr);
+            d = send_messages_right(c, i, j, ndl, nl, ndr, nr);
             /* the reference copies `message` even when send_messages_right returned early (j == p-1) */
-            memcpy(MR(c, i, j), c->message, sizeof(double) * (size_t)K);
+            dst = MR(c, i, j);
           } else {
             if (j <= 0) continue;
-            diff_tmp += send_messages_left(c, i, j, ndl, nl, ndr, nr);
-            memcpy(ML(c, i, j), c->message, sizeof(double) * (size_t)K);
+            d = send_messages_left(c, i, j, ndl, nl, ndr, nr);
+            dst = ML(c, i, j);
           }
+          if (g_audit && !(dir == 0 && j >= p - 1)) {
+            const int same = memcmp(dst, c->message, sizeof(double) * (size_t)K) == 0;
+            const int rule_computes = full || special[j] || (i < 32 && ((changed_prev >> i) & 1u));
+            g_audit_stats[0]++;
+            if (!rule_computes) {
+              g_audit_stats[1]++;
+              if (!same || d != 0.0) g_audit_stats[2]++;
+            }
+            if (!same && i < 32) changed_cur |= 1u << i;
+          }
+          diff_tmp += d;
+          memcpy(dst, c->message, sizeof(double) * (size_t)K);
         }
+        changed_prev = changed_cur;
       }
       diff_tmp /= (double)((size_t)p * (size_t)n);
       diff += diff_tmp;
@@ -243,6 +293,7 @@ static int run_bp(fam_ctx *c) {
   }
   free(ndl);
   free(ndr);
+  free(special);
   return converged ? it : -1;
 }
 

@@ -90,3 +90,22 @@ def test_gpu_reader_mirror_and_errors(tmp_path):
     assert kg.read_bgen_image(np.frombuffer(mis, np.uint8), np.arange(5), np.arange(100)).shape == (10, 13)
     with pytest.raises(kg.KgwError):
         kg.read_bgen_image(np.frombuffer(img, np.uint8), np.array([20]), np.arange(100))   # sample outside the file
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_truncated_probability_block():
+    """A block whose stated length cannot hold 2 N values of B bits is refused (no out-of-bounds read on the device)."""
+    import struct
+    kg = pytest.importorskip("knockoffgwas_b200")
+    bits, rsids, img = _synthetic(n=16, p=3, B=8, compression=0)
+    b = bytearray(img)
+    # first variant block: identifying data, then u32 length C, then C bytes; claim 16-bit probabilities instead of 8
+    pos = 4 + 20
+    for _ in range(3):
+        (l,) = struct.unpack_from("<H", b, pos); pos += 2 + l
+    pos += 6 + 5 + 5
+    (c,) = struct.unpack_from("<I", b, pos)
+    assert c == 10 + 16 + 32
+    b[pos + 4 + 9 + 16] = 16
+    with pytest.raises(kg.KgwError):
+        kg.read_bgen_image(np.frombuffer(bytes(b), np.uint8), np.arange(16), np.arange(3))
