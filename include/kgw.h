@@ -215,6 +215,18 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
                       const int32_t *variant_of_col, int32_t host_threads, int32_t device, int64_t row_bytes, uint8_t *H_out,
                       float *kernel_ms);
 
+/* ---- `.haps` text -> packed haplotype matrix (text input) -------------------
+ * Replaces the data loop of HapsReader::read (haps_reader.cpp:93-124).  `text` is the whole .haps file: one row per
+ * SNP (rows as std::getline splits them), tokens separated by blanks / tabs as sutils::tokenize (utils.cpp:234-246)
+ * splits them, a trailing '\r' ignored on the last token of a row; haplotype a of file sample s is token 2s + a
+ * (:79-81) and its allele is 1 exactly when that token is "1" (:109).
+ *   sample_idx [n_samples]  row of the .sample file for output sample i (the std::find of :73-85)
+ *   row_of_col [p]          file row of the SNP stored in output column j (the std::find of :98-104 on legend ids)
+ * H_out [2 n_samples][row_bytes] chaplotype rows.  A requested row with fewer tokens than a requested column
+ * returns KGW_ERR_INVALID (the reference indexes past the end of `tokens`). */
+int32_t kgw_haps_read(const uint8_t *text, int64_t text_bytes, int32_t n_samples, const int32_t *sample_idx, int32_t p,
+                      const int32_t *row_of_col, int32_t device, int64_t row_bytes, uint8_t *H_out, float *kernel_ms);
+
 /* A destroyed plan parks its scratch slab (tens of GB) for the next plan on the same device, because
  * Knockoffs::generate() runs once per resolution (main.cpp:159-181); this frees the parked slabs. */
 void kgw_release_workspace(void);

@@ -123,6 +123,9 @@ def load_library():
         L.kgw_bgen_read.restype = C.c_int32
         L.kgw_bgen_read.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int64, C.c_void_p, C.POINTER(C.c_float)]
+        L.kgw_haps_read.restype = C.c_int32
+        L.kgw_haps_read.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
+                                    C.c_void_p, C.POINTER(C.c_float)]
         L.kgw_assign_references.restype = C.c_int32
         L.kgw_assign_references.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
@@ -436,6 +439,57 @@ def read_bgen_image(image, sample_idx, variant_of_col, device=0, host_threads=0,
     ms = C.c_float()
     _check(L.kgw_bgen_read(image.ctypes.data, image.nbytes, len(sidx), sidx.ctypes.data, p, vcol.ctypes.data, int(host_threads),
                            int(device), H.shape[1], H.ctypes.data, C.byref(ms)))
+    return (H, float(ms.value)) if return_ms else H
+
+
+class HapsReader:
+    """Host mirror of the reference's HapsReader (haps_reader.h, haps_reader.cpp:8-35): `<prefix>.haps` (one row per SNP),
+    `<prefix>.legend` (header, then the variant id in the first column), `<prefix>.sample` (two header lines, then
+    `ID_1 ...`); `read(sample_ids, snp_ids)` returns the packed haplotype matrix through kgw_haps_read."""
+
+    def __init__(self, prefix):
+        prefix = str(prefix)
+        self.text = np.fromfile(prefix + ".haps", dtype=np.uint8)
+        with open(prefix + ".legend") as fh:
+            self.variant_ids = [ln.split()[0] for ln in fh.read().splitlines()[1:] if ln.strip()]
+        with open(prefix + ".sample") as fh:
+            self.sample_ids = [ln.split()[0] for ln in fh.read().splitlines()[2:] if ln.strip()]
+
+    def read(self, sample_ids=None, snp_ids=None, device=0, return_ms=False):
+        if sample_ids is None:
+            sidx = np.arange(len(self.sample_ids), dtype=np.int32)
+        else:
+            where = {}
+            for i, sid in enumerate(self.sample_ids):
+                where.setdefault(sid, i)
+            try:
+                sidx = np.array([where[str(x)] for x in sample_ids], dtype=np.int32)
+            except KeyError as e:
+                raise KgwError(-1, f"Error parsing HAPS file. Could not find sample {e.args[0]}") from None   # haps_reader.cpp:82-84
+        if snp_ids is None:
+            rows = np.arange(len(self.variant_ids), dtype=np.int32)
+        else:
+            first = {}
+            for r, vid in enumerate(self.variant_ids):
+                first.setdefault(vid, r)
+            try:
+                rows = np.array([first[str(x)] for x in snp_ids], dtype=np.int32)
+            except KeyError as e:
+                raise KgwError(-1, f"variant {e.args[0]} is not in the legend") from None
+        return read_haps_text(self.text, sidx, rows, device=device, return_ms=return_ms)
+
+
+def read_haps_text(text, sample_idx, row_of_col, device=0, return_ms=False):
+    """kgw_haps_read on an in-memory .haps file: uint8 [2 n_samples][ceil(p/8)] chaplotype rows."""
+    L = load_library()
+    text = np.ascontiguousarray(np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text, dtype=np.uint8)
+    sidx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+    rows = np.ascontiguousarray(row_of_col, dtype=np.int32)
+    p = len(rows)
+    H = np.zeros((2 * len(sidx), (p + 7) // 8), dtype=np.uint8)
+    ms = C.c_float()
+    _check(L.kgw_haps_read(text.ctypes.data, text.nbytes, len(sidx), sidx.ctypes.data, p, rows.ctypes.data, int(device),
+                           H.shape[1], H.ctypes.data, C.byref(ms)))
     return (H, float(ms.value)) if return_ms else H
 
 

@@ -577,3 +577,30 @@ def family_audit_stats() -> dict:
     out = (C.c_int64 * 3)()
     lib().kgw_oracle_family_audit_get(out)
     return {"messages": int(out[0]), "skippable": int(out[1]), "violations": int(out[2])}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# `.haps` text -> haplotype matrix.  Restates the data loop of HapsReader::read (snpknock2/src/haps_reader.cpp:93-124)
+# with sutils::tokenize (utils.cpp:234-246).
+def haps_tokenize(line: bytes) -> list:
+    import re
+    toks = [t for t in re.split(rb"[ \t]+", line) if t != b""]       # maximal runs of non-blank characters
+    if toks and toks[-1].endswith(b"\r"):                               # utils.cpp:243-244, last token only
+        toks[-1] = toks[-1][:-1]
+    return toks
+
+
+def haps_read(text, sample_idx, row_of_col) -> np.ndarray:
+    """uint8 [2 len(sample_idx)][ceil(p/8)]: H[2i + a][j] = (token 2 sample_idx[i] + a of file row row_of_col[j] == "1");
+    raises IndexError where the reference would index past the end of `tokens`."""
+    lines = bytes(text).split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()                                                     # std::getline yields no row after the last '\n'
+    sample_idx = np.asarray(sample_idx, dtype=np.int64)
+    bits = np.zeros((2 * len(sample_idx), len(row_of_col)), dtype=np.uint8)
+    for j, r in enumerate(row_of_col):
+        toks = haps_tokenize(lines[int(r)])
+        for i, s in enumerate(sample_idx):
+            bits[2 * i, j] = toks[2 * s] == b"1"
+            bits[2 * i + 1, j] = toks[2 * s + 1] == b"1"
+    return pack_bits(bits)
