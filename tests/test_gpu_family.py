@@ -134,3 +134,32 @@ def test_family_kernel_synthetic_larger_families(size, K):
         assert np.array_equal(dbg.fam_zk[row:row + n], r.zk), f"Zk of family {mem.tolist()}"
         assert np.array_equal(hk[mem], r.hk), f"Hk of family {mem.tolist()}"
         row += n
+
+
+@pytest.mark.parametrize("segs", [
+    [(0, 40), (43, 45), (48, 48), (300, 599)],          # chromosome ends, a 3-locus gap, a one-locus segment
+    [(0, 599)],                                         # one segment over the whole chromosome: no junction at all
+    [(1, 1), (4, 5), (597, 598)],                       # junctions next to both ends
+    [(0, 0), (2, 2), (599, 599)],
+])
+def test_family_kernel_segment_edge_cases(segs):
+    """Hand-made pairs whose segments touch the chromosome ends, sit two loci apart (special ranges merge) or are one
+    locus long: the stored spans of the right messages and the junction bookkeeping at the boundaries."""
+    from knockoffgwas_b200 import synth
+    sp = synth.make_problem(80, 600, 12, seed=17, n_founders=10, mean_dist_cm=0.05)
+    ids = np.array([10, 33], dtype=np.int32)
+    bits = np.unpackbits(sp.H, axis=1, bitorder="little")
+    for j0, j1 in segs:
+        bits[33, j0:j1 + 1] = bits[10, j0:j1 + 1]
+    sp.H = np.packbits(bits, axis=1, bitorder="little")[:, :sp.H.shape[1]]
+    for me, other in ((10, 33), (33, 10)):
+        sp.ref[me][sp.ref[me] == other] = 79 if 79 not in sp.ref[me] else 78
+        sp.ref[me].sort()
+    fams = [(ids, [(j0, j1, ids) for j0, j1 in segs])]
+    prob = ko.Problem(H=sp.H, p=sp.p, K=sp.K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu,
+                      groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
+    hk, dbg = kg.generate(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=np.zeros(0, np.int32),
+                          ref_global=sp.ref, seed=sp.seed, families=fams, debug_paths=True)
+    rng, _ = ko.make_rng(prob, mode="philox")
+    r = ko.run_family(prob, ids, [(j0, j1, 0, 0, ids) for j0, j1 in segs], rng)
+    assert np.array_equal(dbg.fam_z, r.z) and np.array_equal(dbg.fam_zk, r.zk) and np.array_equal(hk[ids], r.hk)
