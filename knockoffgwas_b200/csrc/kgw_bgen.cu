@@ -31,7 +31,7 @@ int kgw_fail_(int code, const std::string &msg);   // kgw_api.cu
 
 namespace {
 
-enum { BGEN_BAD_HEADER = 1, BGEN_BAD_PLOIDY = 2, BGEN_BAD_PROB = 4 };
+enum { BGEN_BAD_HEADER = 1, BGEN_BAD_PLOIDY = 2, BGEN_BAD_PROB = 4, BGEN_NOT_8BIT = 8 /* not an error: selects the general kernel */ };
 
 // Pass 1, one thread per output column: checks the block header and leaves (offset of the probability stream |
 // B << 56) for pass 2.
@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) bgen_header_kernel(const uint8_t *__restr
     atomicOr(status, BGEN_BAD_HEADER);
     B = 0;
   }
+  if (B != 8u) atomicOr(status, BGEN_NOT_8BIT);
   colinfo[j] = (unsigned long long)(col_off[j] + 10 + n_samples_bgen) | ((unsigned long long)B << 56);
 }
 
@@ -107,6 +108,80 @@ __global__ void __launch_bounds__(256) bgen_unpack_kernel(const uint8_t *__restr
       }
       words[ww] = acc;
     }
+    uint32_t *dst = Hw + (size_t)hap * stride_w + w0;
+    if (w0 + 4 <= stride_w) {
+      *reinterpret_cast<uint4 *>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+    } else {
+      for (int ww = 0; ww < 4 && w0 + ww < stride_w; ww++) dst[ww] = words[ww];
+    }
+  }
+  if (bad) atomicOr(status, bad);
+}
+
+// Pass 2, fast path: 8-bit probabilities (what UK Biobank and qctool write) and kept samples that are consecutive in the
+// file (sample_idx[i] = s0 + i).  A CTA owns 256 consecutive haplotypes x 128 loci; for 64 variants at a time it
+// copies the 256 value bytes and the 128 ploidy bytes of its haplotypes to shared memory with 16-byte loads
+// (aligned down; the slack bytes are skipped when reading), then every thread packs the bits of its haplotype.
+constexpr int BG_TILE = 64;          // variants staged at a time
+constexpr int BG_VAL_CHUNKS = 17;    // 16-byte chunks covering 256 bytes at any alignment
+constexpr int BG_PL_CHUNKS = 9;      // ... 128 bytes
+__global__ void __launch_bounds__(256) bgen_unpack8_kernel(const uint8_t *__restrict__ blocks, const unsigned long long *__restrict__ colinfo,
+                                                           int s0, int n_samples_bgen, int n_haps, int p, int stride_w,
+                                                           uint32_t *__restrict__ Hw, int *__restrict__ status) {
+  __shared__ uint4 sval[BG_TILE][BG_VAL_CHUNKS];
+  __shared__ uint4 spl[BG_TILE][BG_PL_CHUNKS];
+  __shared__ unsigned long long info[BG_TILE];
+  const int tid = threadIdx.x;
+  const int hap0 = blockIdx.y * 256;           // first output haplotype of the CTA (even)
+  const int hap = hap0 + tid;
+  const int w0 = blockIdx.x * 4;
+  const long long q0 = 2ll * s0 + hap0;        // its value index in a block; its sample is s0 + hap0 / 2
+  const long long pl0 = (long long)s0 + hap0 / 2 - n_samples_bgen - 2;   // offset of that sample's ploidy byte from the stream
+  int bad = 0;
+  uint32_t words[4] = {0u, 0u, 0u, 0u};
+  for (int half = 0; half < 2; half++) {
+    const int jbase = (w0 + 2 * half) << 5;
+    __syncthreads();
+    if (tid < BG_TILE) info[tid] = (jbase + tid < p) ? colinfo[jbase + tid] : 0ull;
+    __syncthreads();
+    for (int x = tid; x < BG_TILE * BG_VAL_CHUNKS; x += 256) {
+      const int v = x / BG_VAL_CHUNKS, c = x - v * BG_VAL_CHUNKS;
+      const unsigned long long ci = info[v];
+      if ((ci >> 56) != 0ull) {
+        const unsigned long long a = ((ci & 0x00ffffffffffffffull) + (unsigned long long)q0) & ~15ull;
+        sval[v][c] = *reinterpret_cast<const uint4 *>(blocks + a + 16ull * c);
+      }
+    }
+    for (int x = tid; x < BG_TILE * BG_PL_CHUNKS; x += 256) {
+      const int v = x / BG_PL_CHUNKS, c = x - v * BG_PL_CHUNKS;
+      const unsigned long long ci = info[v];
+      if ((ci >> 56) != 0ull) {
+        const unsigned long long a = (unsigned long long)((long long)(ci & 0x00ffffffffffffffull) + pl0) & ~15ull;
+        spl[v][c] = *reinterpret_cast<const uint4 *>(blocks + a + 16ull * c);
+      }
+    }
+    __syncthreads();
+    if (hap < n_haps) {
+#pragma unroll
+      for (int ww = 0; ww < 2; ww++) {
+        uint32_t acc = 0;
+#pragma unroll 8
+        for (int jj = 0; jj < 32; jj++) {
+          const int v = ww * 32 + jj;
+          const unsigned long long ci = info[v];
+          if ((ci >> 56) == 0ull) continue;
+          const unsigned long long st = ci & 0x00ffffffffffffffull;
+          const unsigned val = reinterpret_cast<const uint8_t *>(&sval[v][0])[((st + (unsigned long long)q0) & 15ull) + tid];
+          const unsigned pl = reinterpret_cast<const uint8_t *>(&spl[v][0])[((unsigned long long)((long long)st + pl0) & 15ull) + (tid >> 1)];
+          if (pl != 2u) bad |= BGEN_BAD_PLOIDY;
+          if (val == 0u) acc |= 1u << jj;
+          else if (val != 255u) bad |= BGEN_BAD_PROB;
+        }
+        words[2 * half + ww] = acc;
+      }
+    }
+  }
+  if (hap < n_haps) {
     uint32_t *dst = Hw + (size_t)hap * stride_w + w0;
     if (w0 + 4 <= stride_w) {
       *reinterpret_cast<uint4 *>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
@@ -288,7 +363,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
 
   const int n_haps = 2 * n_samples;
   const int stride_w = (((p + 31) / 32) + 3) & ~3;   // rows padded to 16 bytes
-  KGW_CUDA_B(cudaMalloc(&dblocks, (size_t)total + 16));
+  KGW_CUDA_B(cudaMalloc(&dblocks, (size_t)total + 1024));   // the staged 16-byte loads of the fast path may run past the last block
   KGW_CUDA_B(cudaMalloc(&doff, sizeof(long long) * p));
   KGW_CUDA_B(cudaMalloc(&dinfo, sizeof(unsigned long long) * p));
   KGW_CUDA_B(cudaMalloc(&dlen, sizeof(long long) * p));
@@ -306,7 +381,14 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   const dim3 grid((unsigned)((stride_w + 3) / 4), (unsigned)((n_haps + 255) / 256));
   KGW_CUDA_B(cudaEventRecord(e0));
   bgen_header_kernel<<<(p + 255) / 256, 256>>>(dblocks, doff, dlen, (int)nfile, p, dinfo, dstatus);
-  bgen_unpack_kernel<<<grid, 256>>>(dblocks, dinfo, dsidx, (int)nfile, n_haps, p, stride_w, dH, dstatus);
+  int st_hdr = 0;
+  KGW_CUDA_B(cudaMemcpy(&st_hdr, dstatus, sizeof(int), cudaMemcpyDeviceToHost));
+  bool consecutive = true;
+  for (int i = 1; i < n_samples; i++) consecutive &= (sample_idx[i] == sample_idx[0] + i);
+  if (!(st_hdr & BGEN_NOT_8BIT) && consecutive)
+    bgen_unpack8_kernel<<<grid, 256>>>(dblocks, dinfo, sample_idx[0], (int)nfile, n_haps, p, stride_w, dH, dstatus);
+  else
+    bgen_unpack_kernel<<<grid, 256>>>(dblocks, dinfo, dsidx, (int)nfile, n_haps, p, stride_w, dH, dstatus);
   KGW_CUDA_B(cudaGetLastError());
   KGW_CUDA_B(cudaEventRecord(e1));
   KGW_CUDA_B(cudaEventSynchronize(e1));
@@ -317,6 +399,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   if (kernel_ms) *kernel_ms = ms;
   int st = 0;
   KGW_CUDA_B(cudaMemcpy(&st, dstatus, sizeof(int), cudaMemcpyDeviceToHost));
+  st &= ~BGEN_NOT_8BIT;
   if (st == 0)
     KGW_CUDA_B(cudaMemcpy2D(H_out, (size_t)row_bytes, dH, sizeof(uint32_t) * (size_t)stride_w, (size_t)((p + 7) / 8), (size_t)n_haps,
                             cudaMemcpyDeviceToHost));

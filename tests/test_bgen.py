@@ -58,14 +58,17 @@ def test_gpu_reads_reference_toy_bgen_like_the_reference():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,compression,n,p", [(8, 1, 37, 301), (16, 0, 130, 129), (5, 1, 300, 31), (1, 0, 64, 1024), (32, 1, 9, 200)])
+@pytest.mark.parametrize("B,compression,n,p", [(8, 1, 37, 301), (8, 0, 700, 130), (16, 0, 130, 129), (5, 1, 300, 31), (1, 0, 64, 1024), (32, 1, 9, 200)])
 def test_gpu_matches_oracle_on_synthetic_images(B, compression, n, p):
     kg = pytest.importorskip("knockoffgwas_b200")
     bits, rsids, img = _synthetic(n=n, p=p, B=B, compression=compression, seed=B)
     image = np.frombuffer(img, np.uint8)
     rng = np.random.default_rng(2)
     for sidx, vcol in ((np.arange(n), np.arange(p)),
-                       (rng.permutation(n)[:max(1, n // 2)], rng.permutation(p)[:max(1, 2 * p // 3)])):
+                       (rng.permutation(n)[:max(1, n // 2)], rng.permutation(p)[:max(1, 2 * p // 3)]),
+                       (np.arange(n // 3, n - 1), rng.permutation(p))):      # consecutive samples from s0 > 0: staged fast path at B = 8
+        if len(sidx) == 0:
+            continue
         assert np.array_equal(kg.read_bgen_image(image, sidx, vcol), ko.bgen_read(image, sidx, vcol))
 
 
