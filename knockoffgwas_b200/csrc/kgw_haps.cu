@@ -38,21 +38,34 @@ __global__ void __launch_bounds__(TOK_THREADS) haps_tokenize_kernel(const uint8_
   typedef cub::BlockScan<int, TOK_THREADS> Scan;
   __shared__ typename Scan::TempStorage tmp;
   const int j = blockIdx.x;
-  const uint8_t *line = text + row_off[j];
+  const long long abs0 = row_off[j];
+  const uint8_t *line = text + abs0;
   const int len = row_len[j];
   uint32_t *bits = rowbits + (size_t)j * tok_words;
   int running = 0;
-  for (int base = 0; base < len; base += TOK_THREADS * TOK_ITEMS) {
+  // tiles are aligned to 16 bytes of the text buffer (cudaMalloc'ed, so 16-byte aligned itself): one 16-byte load per
+  // thread and tile plus the single bytes either side; positions below are relative to the start of the row
+  const int lead = (int)(abs0 & 15);   // bytes of the first chunk that belong to the previous row
+  for (int base = -lead; base < len; base += TOK_THREADS * TOK_ITEMS) {
     const int b0 = base + threadIdx.x * TOK_ITEMS;
     unsigned c[TOK_ITEMS + 2];   // c[0] = byte before the thread's first, c[TOK_ITEMS + 1] = byte after its last
+    if (b0 < len && b0 + TOK_ITEMS > 0) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(line + b0);
+      const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int q = 0; q < TOK_ITEMS + 2; q++) {
-      const int b = b0 - 1 + q;
-      c[q] = (b >= 0 && b < len) ? line[b] : ' ';
+      for (int q = 0; q < TOK_ITEMS; q++) {
+        const int b = b0 + q;
+        c[q + 1] = (b >= 0 && b < len) ? ((w[q >> 2] >> (8 * (q & 3))) & 0xffu) : ' ';
+      }
+      c[0] = (b0 - 1 >= 0 && b0 - 1 < len) ? line[b0 - 1] : ' ';
+      c[TOK_ITEMS + 1] = (b0 + TOK_ITEMS < len) ? line[b0 + TOK_ITEMS] : ' ';
+    } else {
+#pragma unroll
+      for (int q = 0; q < TOK_ITEMS + 2; q++) c[q] = ' ';
     }
     int starts = 0;
 #pragma unroll
-    for (int q = 1; q <= TOK_ITEMS; q++) starts += (b0 + q - 1 < len && !is_blank(c[q]) && is_blank(c[q - 1])) ? 1 : 0;
+    for (int q = 1; q <= TOK_ITEMS; q++) starts += (!is_blank(c[q]) && is_blank(c[q - 1])) ? 1 : 0;
     int before = 0, total = 0;
     Scan(tmp).ExclusiveSum(starts, before, total);
     __syncthreads();
@@ -60,7 +73,7 @@ __global__ void __launch_bounds__(TOK_THREADS) haps_tokenize_kernel(const uint8_
 #pragma unroll
     for (int q = 1; q <= TOK_ITEMS; q++) {
       const int b = b0 + q - 1;
-      if (b < len && !is_blank(c[q]) && is_blank(c[q - 1])) {
+      if (!is_blank(c[q]) && is_blank(c[q - 1])) {
         bool one = false;
         if (c[q] == '1') {
           // the token ends after this character, or it is "1\r" and nothing but blanks follows (last token of the row)
@@ -166,7 +179,7 @@ int32_t kgw_haps_read(const uint8_t *text, int64_t text_bytes, int32_t n_samples
   const int n_haps = 2 * n_samples;
   const int stride_w = (((p + 31) / 32) + 3) & ~3;
   KGW_CUDA_H(cudaSetDevice(device));
-  KGW_CUDA_H(cudaMalloc(&dtext, (size_t)text_bytes));
+  KGW_CUDA_H(cudaMalloc(&dtext, (size_t)text_bytes + 32));   // the tokenizer reads whole 16-byte chunks
   KGW_CUDA_H(cudaMalloc(&doff, sizeof(long long) * p));
   KGW_CUDA_H(cudaMalloc(&dlen, sizeof(int) * p));
   KGW_CUDA_H(cudaMalloc(&dntok, sizeof(int) * p));
