@@ -657,26 +657,41 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
       return warp_choice<SF>(w, fam_uniform(P, mem[i], STREAM_Z, j), K, lane);
     };
 
-    // ---- FamilyBP::run (family_bp.cpp:79-100) and sample_posterior (:160-230)
-    run_bp(true);
-    // junction nodes first, (member, locus) ascending; they sit at interval ends (:168-193)
-    for (int i = 0; i < n; i++) {
-      const KgwFamInterval *iv_end = P.ivs + ivs0[i + 1];
-      for (const KgwFamInterval *iv = P.ivs + ivs0[i]; iv < iv_end; iv++) {
-        for (int e = 0; e < 2; e++) {
-          const int j = (e == 0) ? iv->j0 : iv->j1;
-          if (e == 1 && iv->j1 == iv->j0) break;
-          const bool jl = (j == iv->j0) && j > 0 && iv->ndl > 0, jr = (j == iv->j1) && j < p - 1 && iv->ndr > 0;
+    // ---- FamilyBP::run (family_bp.cpp:79-100) and sample_posterior (:160-230): BP, then the junction nodes in
+    //      (member, locus) order -- they sit at interval ends (:168-193) -- each followed by a BP re-run (:194-211).
+    //      One loop with a cursor over (member, interval, end), so that run_bp is instantiated once.
+    {
+      int ci = 0, ce = 0;
+      const KgwFamInterval *civ = P.ivs + ivs0[0];
+      bool first = true;
+      for (;;) {
+        run_bp(first);
+        first = false;
+        int fj = -1;
+        while (ci < n) {
+          if (civ >= P.ivs + ivs0[ci + 1]) {
+            ci++;
+            if (ci < n) civ = P.ivs + ivs0[ci];
+            ce = 0;
+            continue;
+          }
+          if (ce >= 2) { civ++; ce = 0; continue; }
+          const int e = ce++;
+          if (e == 1 && civ->j1 == civ->j0) continue;
+          const int j = (e == 0) ? civ->j0 : civ->j1;
+          const bool jl = (j == civ->j0) && j > 0 && civ->ndl > 0, jr = (j == civ->j1) && j < p - 1 && civ->ndr > 0;
           if (!(jl || jr)) continue;
-          if (Zb[(size_t)i * p + j] != 255) continue;
-          const int kz = draw_junction(i, j, iv);
-          __syncwarp();
-          condition_on(i, j, kz);
-          for (int t = 0; t < iv->nn; t++) condition_on(iv->nb[t], j, kz);
-          __syncwarp();
-          KGW_FAM_PHASE(3);
-          run_bp(false);
+          if (Zb[(size_t)ci * p + j] != 255) continue;
+          fj = j;
+          break;
         }
+        if (fj < 0) break;
+        const int kz = draw_junction(ci, fj, civ);
+        __syncwarp();
+        condition_on(ci, fj, kz);
+        for (int t = 0; t < civ->nn; t++) condition_on(civ->nb[t], fj, kz);
+        __syncwarp();
+        KGW_FAM_PHASE(3);
       }
     }
     // every remaining node, member by member, loci ascending (:217-229).  By then every node to the left on
