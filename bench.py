@@ -213,6 +213,11 @@ def run_b200_arm(a, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
+    # stdout carries the JSON line only: whatever the libraries print while the job runs (NCCL writes its version line
+    # to stdout at communicator creation) is sent to stderr; the real stdout comes back for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -478,10 +483,13 @@ def run_b200_arm(a, rank, local_rank, world):
         except Exception as e:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(e)[:300]}
     plan.close()
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 def main():
