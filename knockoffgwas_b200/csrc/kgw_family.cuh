@@ -8,8 +8,10 @@
 //
 // Mapping: one warp per IBD family (families are independent, knockoffs.cpp:440-445), families handed out
 // through an atomic counter; lane l owns the HMM states k = l, l+32, ... (SF = ceil(K/32) per lane), so
-// no message entry is ever touched by two lanes.  The BP messages of a family, double [2][members][p][K],
-// and the per-(member, locus, state) emission pattern bytes live in an HBM scratch slot owned by the
+// no message entry is ever touched by two lanes (the final draws and the family knockoffs, which keep their
+// per-state values in registers, use lane l = states l*SF .. l*SF+SF-1 instead: one scan per draw).  The left
+// BP messages of a family, double [members][p][K], the right messages at the loci where something reads them
+// (see below) and the per-(member, locus, state) emission pattern bytes live in an HBM scratch slot owned by the
 // warp; neighbour sets are piecewise constant along the chromosome and come from the host as intervals
 // (with the junction differences of family_bp.cpp:352-378 precomputed).  Node emissions are table
 // look-ups: the reference's pow(prod, 1/(n+1)) (family_bp.cpp:441-454) takes one of 2^(n+1) values,
