@@ -371,6 +371,87 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
         if (len > 0) {
           const unsigned todo = full ? ((1u << n) - 1u) : chg_prev;
           unsigned comp_new = 0, chg_new = 0;
+          const bool has_in = (dir == 0) ? (j > 0) : (j < p - 1);
+          if (full && n == 2 && (!has_in || comp_prev == 3u)) {
+            // First iteration of a pair (the common family): the two chains of the stretch are independent, so they
+            // run in lockstep -- one loop, one set of locus constants, one shuffle tree for both sums, and twice
+            // the instruction-level parallelism.  Nothing is compared (the old value of every message is 1/K).
+            const int nnA = (int)(nnpack & 7u), nnB = (int)((nnpack >> 3) & 7u);
+            constexpr ptrdiff_t sgn = step;
+            const ptrdiff_t sK = sgn * K;
+            const uint8_t *ppA = pat_base + (size_t)j * K + lane, *ppB = ppA + pK;
+            double *dpA = ml_base + (size_t)j * K + lane, *dpB = dpA + pK;   // left sweep: every row is stored
+            const KgwFamLocus *lp = P.loc + (dir == 0 ? j + 1 : j);
+            double vA[SF], vB[SF];
+            unsigned pcA[SF], pcB[SF];
+#pragma unroll
+            for (int s = 0; s < SF; s++) {
+              vA[s] = 1.0;
+              vB[s] = 1.0;
+              if (valid[s] && has_in) { vA[s] = pm[s * 32 + lane]; vB[s] = pm[KP + s * 32 + lane]; }
+              pcA[s] = valid[s] ? ppA[s * 32] : 0u;
+              pcB[s] = valid[s] ? ppB[s * 32] : 0u;
+            }
+            double lb = lp->b, lw = lp->w, lr1 = lp->r1;
+            for (int t = 0; t < len; t++) {
+              unsigned pnA[SF], pnB[SF];
+              const bool more = (t + 1 < len);
+#pragma unroll
+              for (int s = 0; s < SF; s++) {
+                pnA[s] = (valid[s] && more) ? ppA[sK + s * 32] : 0u;
+                pnB[s] = (valid[s] && more) ? ppB[sK + s * 32] : 0u;
+              }
+              const double lbn = more ? lp[step].b : 0.0, lwn = more ? lp[step].w : 1.0, lr1n = more ? lp[step].r1 : 0.0;
+              if ((t & 3) == 0 && t + 12 < len) {
+                fam_prefetch(ppA + (dir == 0 ? 8 : 11) * sK - lane, 4 * K, lane);
+                fam_prefetch(ppB + (dir == 0 ? 8 : 11) * sK - lane, 4 * K, lane);
+              }
+              double qA[SF], qB[SF];
+              double sA = 0.0, sB = 0.0;
+#pragma unroll
+              for (int s = 0; s < SF; s++) {
+                qA[s] = 0.0;
+                qB[s] = 0.0;
+                if (valid[s]) {
+                  qA[s] = emission_of(pcA[s], j + t * step, nnA) * vA[s];
+                  qB[s] = emission_of(pcB[s], j + t * step, nnB) * vB[s];
+                  sA += qA[s];
+                  sB += qB[s];
+                }
+              }
+              warp_sum2(sA, sB);
+              const double cA = lb * fast_rcp(sA * lw), cB = lb * fast_rcp(sB * lw);
+#pragma unroll
+              for (int s = 0; s < SF; s++) {
+                if (valid[s]) {
+                  vA[s] = lr1 + cA * qA[s];
+                  vB[s] = lr1 + cB * qB[s];
+                  diff += fabs(vA[s] - p0);
+                  diff += fabs(vB[s] - p0);
+                  if (dir == 1) { dpA[s * 32] = vA[s]; dpB[s * 32] = vB[s]; }
+                }
+              }
+              if (dir == 0 && !more && rr < nrng) {   // the next range reads the last plain row
+                double *rowA = mr_row(0, e, cur_ext0, cur_off), *rowB = mr_row(1, e, cur_ext0, cur_off);
+#pragma unroll
+                for (int s = 0; s < SF; s++) if (valid[s]) { rowA[s * 32 + lane] = vA[s]; rowB[s * 32 + lane] = vB[s]; }
+              }
+              ppA += sK;
+              ppB += sK;
+              dpA += sK;
+              dpB += sK;
+              lp += step;
+              lb = lbn;
+              lw = lwn;
+              lr1 = lr1n;
+#pragma unroll
+              for (int s = 0; s < SF; s++) { pcA[s] = pnA[s]; pcB[s] = pnB[s]; }
+            }
+#pragma unroll
+            for (int s = 0; s < SF; s++) if (valid[s]) { pm[s * 32 + lane] = vA[s]; pm[KP + s * 32 + lane] = vB[s]; }
+            comp_new = 3u;
+            chg_new = 3u;
+          } else
           for (int i = 0; i < n; i++) {
             if (!((todo >> i) & 1u)) continue;
             const int nn = (int)((nnpack >> (3 * i)) & 7u);

@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 
 
-FAMILY_COST = 8.0   # measured on B200: a related haplotype costs about 8 unrelated ones (the CPU reference: 2-3)
+FAMILY_COST = 7.0   # measured on B200: a related haplotype costs about 7 unrelated ones (the CPU reference: 2-3)
 
 
 def partition_work(unrelated, families, world_size: int, family_cost: float = FAMILY_COST):
