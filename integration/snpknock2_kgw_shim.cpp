@@ -1,0 +1,159 @@
+// integration/snpknock2_kgw_shim.cpp -- the reference-side binding of include/kgw.h, compiled.
+//
+// INTEGRATION.md section 2 shows the body a maintainer pastes into Knockoffs::generate
+// (snpknock2/src/knockoffs.cpp:311).  This file is the same code as a link-time replacement, so that the
+// drop-in can be built and run without touching a reference source file: GNU ld --wrap puts
+// wrap_generate() below in front of Knockoffs::generate in the UNMODIFIED reference objects
+// (integration/build_dropin.sh -> oracle/_ref/snpknock2_kgw).  Everything else -- the CLI, the BGEN / HAPS
+// readers, metadata, kinship clusters and reference selection, IBD tidying, partitions, the PLINK / text
+// writers -- is the reference's own code, unchanged; only the sampler runs in libkgw.so on the B200.
+//
+// KGW_SHIM_DUMP=<dir>: additionally writes the kgw_problem the shim assembled as raw little-endian arrays
+// (tests/test_dropin_shim.py compares them with the inputs the probe recorded from the reference).
+// every standard header the reference pulls in comes first: `private` is redefined for the reference's own headers only
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <sys/stat.h>
+
+#define private public
+#define protected public
+#include "knockoffs.h"
+#undef private
+#undef protected
+
+#include "kgw.h"
+
+#ifndef KGW_GEN_SYM
+#error "KGW_GEN_SYM (mangled Knockoffs::generate) must be defined by the build script"
+#endif
+#define KGW_STR2(x) #x
+#define KGW_STR(x) KGW_STR2(x)
+
+void wrap_generate(Knockoffs *self, int num_threads) asm("__wrap_" KGW_STR(KGW_GEN_SYM));
+
+namespace {
+
+template <typename T>
+void dump(const std::string &dir, const char *name, const std::vector<T> &v) {
+  FILE *f = fopen((dir + "/" + name).c_str(), "wb");
+  if (!f) return;
+  if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f);
+  fclose(f);
+}
+
+int g_call = 0;
+
+}  // namespace
+
+void wrap_generate(Knockoffs *self, int /*num_threads*/) {
+  Knockoffs &k = *self;
+  k.reset_knockoffs();                                   // unchanged: alpha := 1/K, Hk := 0  (knockoffs.cpp:72)
+  const int num_haps = k.num_haps, num_snps = k.num_snps, K = k.K;
+  const int num_windows = k.metadata.windows.num_windows;
+  const size_t row_bytes = (size_t)(num_snps + 7) / 8;
+
+  // chaplotype rows -> one flat bit matrix (same LSB-first byte layout, chaplotype.h:25)
+  std::vector<uint8_t> Hflat((size_t)num_haps * row_bytes, 0), Hkflat(Hflat.size(), 0);
+  for (int i = 0; i < num_haps; i++)
+    std::copy(k.H[i].data.begin(), k.H[i].data.begin() + row_bytes, Hflat.begin() + (size_t)i * row_bytes);
+
+  std::vector<int32_t> rl((size_t)num_haps * num_windows * K), rg((size_t)num_haps * K);
+  for (int i = 0; i < num_haps; i++) {
+    for (int w = 0; w < num_windows; w++)
+      std::copy(k.references_local[i][w].begin(), k.references_local[i][w].end(), rl.begin() + ((size_t)i * num_windows + w) * K);
+    std::copy(k.references_global[i].begin(), k.references_global[i].end(), rg.begin() + (size_t)i * K);
+  }
+  std::vector<int32_t> grp(k.groups.begin(), k.groups.end());
+  std::vector<int32_t> ws(k.metadata.windows.start.begin(), k.metadata.windows.start.end());
+  std::vector<int32_t> we(k.metadata.windows.end.begin(), k.metadata.windows.end.end());
+  std::vector<int32_t> unrel(k.metadata.unrelated.begin(), k.metadata.unrelated.end());   // std::set: ascending
+  std::vector<double> b(k.b.begin(), k.b.end()), mu(k.mut_rates.begin(), k.mut_rates.end());
+
+  kgw_problem P = {};
+  P.abi_version = KGW_ABI_VERSION;
+  P.N = num_haps;  P.p = num_snps;  P.K = K;  P.W = num_windows;
+  P.row_bytes = (int64_t)row_bytes;
+  P.H = Hflat.data();  P.ref_local = rl.data();  P.ref_global = rg.data();
+  P.b = b.data();      P.mu = mu.data();  P.groups = grp.data();
+  P.win_start = ws.data();  P.win_end = we.data();
+  P.unrelated = unrel.data();  P.n_unrelated = (int32_t)unrel.size();
+  P.seed = (uint64_t)k.seed;
+
+  // related haplotypes (generate_related, knockoffs.cpp:329-571): the host still dedups the families
+  // (:331-342) and tidies their IBD segments (IbdCluster, :474-481, ibd.cpp:99-189); the device runs
+  // FamilyBP, FamilyKnockoffs and sample_emission on them
+  std::set<std::vector<int>> fams;
+  for (auto &f : k.metadata.related_families)
+    if (f.size() > 1) fams.insert(std::vector<int>(f.begin(), f.end()));
+  std::vector<int32_t> fam_off{0}, fam_mem, seg_off{0}, seg_jmin, seg_jmax, seg_ids_off{0}, seg_ids;
+  for (auto &fam : fams) {
+    fam_mem.insert(fam_mem.end(), fam.begin(), fam.end());
+    fam_off.push_back((int32_t)fam_mem.size());
+    std::set<IbdSeg> segs;
+    for (int i : fam)
+      for (auto &sg : k.metadata.ibd_segments[i]) segs.insert(sg);
+    IbdCluster cluster(segs);                            // constructor runs tidy()
+    for (int s = 0; s < cluster.size(); s++) {
+      IbdSeg sg;
+      cluster.get(s, sg);
+      seg_jmin.push_back(sg.j_min);
+      seg_jmax.push_back(sg.j_max);
+      seg_ids.insert(seg_ids.end(), sg.indices.begin(), sg.indices.end());
+      seg_ids_off.push_back((int32_t)seg_ids.size());
+    }
+    seg_off.push_back((int32_t)seg_jmin.size());
+  }
+  kgw_families F = {};
+  F.n_families = (int32_t)fams.size();
+  F.fam_off = fam_off.data();  F.fam_members = fam_mem.data();  F.seg_off = seg_off.data();
+  F.seg_jmin = seg_jmin.data();  F.seg_jmax = seg_jmax.data();
+  F.seg_ids_off = seg_ids_off.data();  F.seg_ids = seg_ids.data();
+  if (F.n_families > 0) P.families = &F;
+
+  if (const char *dd = getenv("KGW_SHIM_DUMP")) {
+    const std::string dir = std::string(dd) + "/call" + std::to_string(g_call);
+    mkdir(dd, 0777);
+    mkdir(dir.c_str(), 0777);
+    std::vector<int64_t> dims = {num_haps, num_snps, K, num_windows, (int64_t)row_bytes, (int64_t)k.seed};
+    dump(dir, "dims.i64", dims);
+    dump(dir, "H.u8", Hflat);
+    dump(dir, "ref_local.i32", rl);
+    dump(dir, "ref_global.i32", rg);
+    dump(dir, "b.f64", b);
+    dump(dir, "mu.f64", mu);
+    dump(dir, "groups.i32", grp);
+    dump(dir, "win_start.i32", ws);
+    dump(dir, "win_end.i32", we);
+    dump(dir, "unrelated.i32", unrel);
+    dump(dir, "fam_off.i32", fam_off);
+    dump(dir, "fam_members.i32", fam_mem);
+    dump(dir, "seg_off.i32", seg_off);
+    dump(dir, "seg_jmin.i32", seg_jmin);
+    dump(dir, "seg_jmax.i32", seg_jmax);
+    dump(dir, "seg_ids_off.i32", seg_ids_off);
+    dump(dir, "seg_ids.i32", seg_ids);
+  }
+  g_call++;
+
+  kgw_options O = {};                                    // device 0; one process per GPU passes its LOCAL_RANK
+  if (kgw_generate(&P, &O, Hkflat.data(), nullptr) != KGW_OK) {
+    std::cerr << "Error: " << kgw_last_error() << std::endl;      // same convention as throw_error_bug (utils.cpp:700)
+    exit(-1);
+  }
+  auto take_row = [&](int i) {                           // == set_Hk(i, hk)  (knockoffs.cpp:299)
+    k.Hk[i].data.assign(Hkflat.begin() + (size_t)i * row_bytes, Hkflat.begin() + (size_t)(i + 1) * row_bytes);
+  };
+  for (int i : k.metadata.unrelated) take_row(i);
+  for (int i : fam_mem) take_row(i);
+}

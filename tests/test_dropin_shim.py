@@ -1,0 +1,103 @@
+"""The drop-in, end to end: oracle/_ref/snpknock2_kgw is the UNMODIFIED reference (CLI, BGEN reader, metadata, kinship
+clusters and reference selection, IBD tidying, partitions, PLINK writer) linked with integration/snpknock2_kgw_shim.cpp
+in front of Knockoffs::generate (GNU ld --wrap) and with libkgw.so (integration/build_dropin.sh; the binary exists
+only where /root/reference was available to build it and travels to the GPU box with oracle/_ref/).
+
+CPU: the kgw_problem the shim assembles from the reference's objects equals, array for array, what the probe
+recorded from the reference itself (tests/golden/toy_chr22_K10_res2.npz), and without a GPU the binary stops with
+the library's "no CPU fallback" error instead of producing output.
+GPU: the `.bed` the binary writes is the reference's own writer applied to (H, Hk) with Hk = this library's knockoffs
+for that problem -- byte for byte."""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from kgw_testutil import load_golden
+
+REPO = Path(__file__).resolve().parents[1]
+BINARY = REPO / "oracle" / "_ref" / "snpknock2_kgw"
+GOLD = Path(__file__).resolve().parent / "golden"
+
+needs_binary = pytest.mark.skipif(not BINARY.exists(), reason="oracle/_ref/snpknock2_kgw not built (needs /root/reference)")
+
+
+def _lay_out_inputs(d: Path) -> dict:
+    f = np.load(GOLD / "toy_chr22_inputs.npz")
+    (d / "example_chr22.bgen").write_bytes(np.load(GOLD / "bgen_toy_chr22.npz")["image"].tobytes())
+    (d / "example_chr22.sample").write_bytes(f["sample"].tobytes())
+    (d / "example_chr22.bim").write_bytes(f["bim"].tobytes())
+    for k in ("keep", "extract", "map", "part", "ibd"):
+        (d / f"{k}.txt").write_bytes(f[k].tobytes())
+    return {k: str(d / f"{k}.txt") for k in ("keep", "extract", "map", "part", "ibd")} | {"bgen": str(d / "example_chr22")}
+
+
+def _run(tmp_path: Path, dump: bool):
+    (tmp_path / "in").mkdir()
+    (tmp_path / "out").mkdir()
+    fl = _lay_out_inputs(tmp_path / "in")
+    args = [str(BINARY), "--bgen", fl["bgen"], "--keep", fl["keep"], "--extract", fl["extract"], "--map", fl["map"],
+            "--part", fl["part"], "--ibd", fl["ibd"], "--K", "10", "--cluster_size_min", "1000", "--cluster_size_max", "10000",
+            "--n_threads", "1", "--seed", "2020", "--hmm-rho", "1", "--hmm-lambda", "1e-3", "--windows", "0",
+            "--resolution", "2", "--compute-references", "--generate-knockoffs", "--out", str(tmp_path / "out" / "ko")]
+    env = dict(os.environ)
+    if dump:
+        env["KGW_SHIM_DUMP"] = str(tmp_path / "dump")
+    return subprocess.run(args, env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=900)
+
+
+def _cuda_device_present() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@needs_binary
+def test_shim_assembles_the_problem_the_reference_hands_to_generate(tmp_path):
+    r = _run(tmp_path, dump=True)
+    prob, _ = load_golden("toy_chr22_K10_res2")
+    d = tmp_path / "dump" / "call0"
+    rd = lambda name, t: np.fromfile(d / name, dtype=t)
+    N, p, K, W, rb, seed = (int(x) for x in rd("dims.i64", np.int64))
+    assert (N, p, K, W, seed) == (prob.N, prob.p, prob.K, 1, prob.seed)
+    assert np.array_equal(rd("H.u8", np.uint8).reshape(N, rb), prob.H)
+    assert np.array_equal(rd("ref_local.i32", np.int32).reshape(N, W, K), prob.ref_local)
+    assert np.array_equal(rd("ref_global.i32", np.int32).reshape(N, K), prob.ref_global)
+    assert np.array_equal(rd("b.f64", np.float64), prob.b) and np.array_equal(rd("mu.f64", np.float64), prob.mu)
+    assert np.array_equal(rd("groups.i32", np.int32), prob.groups)
+    assert np.array_equal(rd("unrelated.i32", np.int32), prob.unrelated)
+    fam_off, mem = rd("fam_off.i32", np.int32), rd("fam_members.i32", np.int32)
+    seg_off, jmin, jmax = rd("seg_off.i32", np.int32), rd("seg_jmin.i32", np.int32), rd("seg_jmax.i32", np.int32)
+    ids_off, ids = rd("seg_ids_off.i32", np.int32), rd("seg_ids.i32", np.int32)
+    got = {}
+    for fi in range(len(fam_off) - 1):
+        m = tuple(mem[fam_off[fi]:fam_off[fi + 1]].tolist())
+        got[m] = [(int(jmin[s]), int(jmax[s]), tuple(ids[ids_off[s]:ids_off[s + 1]].tolist())) for s in range(seg_off[fi], seg_off[fi + 1])]
+    want = {tuple(int(x) for x in m): [(int(s[0]), int(s[1]), tuple(int(x) for x in s[4])) for s in segs] for m, segs in prob.fam_clusters}
+    assert got == want                                   # families and their tidied IBD segments, in the reference's order
+    if not _cuda_device_present():                        # no silent fallback: the reference's error convention, exit(-1)
+        assert r.returncode != 0
+        assert "no CPU fallback" in r.stderr
+        assert not list((tmp_path / "out").glob("*.bed"))
+
+
+@pytest.mark.gpu
+@needs_binary
+def test_dropin_binary_writes_the_librarys_knockoffs(tmp_path):
+    kg = pytest.importorskip("knockoffgwas_b200")
+    r = _run(tmp_path, dump=False)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    beds = sorted((tmp_path / "out").glob("*_res2.bed"))
+    assert len(beds) == 1, [b.name for b in (tmp_path / "out").iterdir()]
+    bed = np.fromfile(beds[0], dtype=np.uint8)
+    assert bytes(bed[:3]) == b"\x6c\x1b\x01"
+    prob, _ = load_golden("toy_chr22_K10_res2")
+    fams = [(m, [(s[0], s[1], s[4]) for s in segs]) for m, segs in prob.fam_clusters]
+    hk, _ = kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, unrelated=prob.unrelated,
+                        ref_global=prob.ref_global, seed=prob.seed, families=fams)
+    want = kg.bed_encode(prob.H, hk, prob.p)              # == the reference's writeBED on (H, Hk), tests/test_bed.py
+    assert np.array_equal(bed[3:].reshape(want.shape), want), "the .bed of the drop-in binary is not (H, this library's Hk)"
