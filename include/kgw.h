@@ -211,6 +211,9 @@ int32_t kgw_assign_references(int32_t N, int32_t p, int64_t row_bytes, const uin
  * `host_threads` host threads (0 = all; system libzstd.so.1 / libz.so.1, loaded on first use) and decoded and
  * transposed on the device; kernel_ms (may be NULL) receives the device time of that kernel. */
 int32_t kgw_bgen_variant_count(const uint8_t *file, int64_t file_bytes, int32_t *n_variants, int32_t *n_samples);
+/* rsid of every variant in file order as (offset into `file`, length): what BgenParser::read_variant hands to the
+ * std::find calls of read_worker (bgen_reader.cpp:176-183); the caller builds its id -> position map from it */
+int32_t kgw_bgen_rsids(const uint8_t *file, int64_t file_bytes, int32_t n_variants, int64_t *rsid_off, int32_t *rsid_len);
 int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples, const int32_t *sample_idx, int32_t p,
                       const int32_t *variant_of_col, int32_t host_threads, int32_t device, int64_t row_bytes, uint8_t *H_out,
                       float *kernel_ms);

@@ -34,13 +34,114 @@
 
 #include "kgw.h"
 
-#ifndef KGW_GEN_SYM
-#error "KGW_GEN_SYM (mangled Knockoffs::generate) must be defined by the build script"
+#include "bgen_reader.h"
+#include "plink_interface.h"
+#include <random>
+#include <unordered_map>
+
+#if !defined(KGW_GEN_SYM) || !defined(KGW_BGEN_SYM) || !defined(KGW_WB_SYM)
+#error "KGW_GEN_SYM / KGW_BGEN_SYM / KGW_WB_SYM (mangled Knockoffs::generate, BgenReader::read, plink::write_binary) must be defined by the build script"
 #endif
 #define KGW_STR2(x) #x
 #define KGW_STR(x) KGW_STR2(x)
 
 void wrap_generate(Knockoffs *self, int num_threads) asm("__wrap_" KGW_STR(KGW_GEN_SYM));
+// the two neighbours of the path; KGW_SHIM_IO=0 leaves them to the reference
+void real_bgen_read(BgenReader *self, const vector<string> &sample_ids, const vector<string> &snp_ids, vector<chaplotype> &H,
+                    bool verbose, int nthreads) asm("__real_" KGW_STR(KGW_BGEN_SYM));
+void wrap_bgen_read(BgenReader *self, const vector<string> &sample_ids, const vector<string> &snp_ids, vector<chaplotype> &H,
+                    bool verbose, int nthreads) asm("__wrap_" KGW_STR(KGW_BGEN_SYM));
+void real_write_binary(const string &basename, const Metadata &metadata, const vector<chaplotype> &H, const vector<chaplotype> &Hk,
+                       bool random) asm("__real_" KGW_STR(KGW_WB_SYM));
+void wrap_write_binary(const string &basename, const Metadata &metadata, const vector<chaplotype> &H, const vector<chaplotype> &Hk,
+                       bool random) asm("__wrap_" KGW_STR(KGW_WB_SYM));
+void writeBIM(const string &basename, const Metadata &metadata, bool include_genotypes, const vector<bool> &swap);   // plink_interface.cpp:105
+void writeFAM(const string &basename, const Metadata &metadata);                                                      // plink_interface.cpp:162
+
+namespace {
+bool shim_io() {
+  const char *e = getenv("KGW_SHIM_IO");
+  return !(e && e[0] == '0');
+}
+}  // namespace
+
+// BgenReader::read (bgen_reader.cpp:66-80 -> read_mt -> read_worker :139-261): same bookkeeping, data loop on the device
+void wrap_bgen_read(BgenReader *self, const vector<string> &sample_ids, const vector<string> &snp_ids, vector<chaplotype> &H,
+                    bool verbose, int nthreads) {
+  if (!shim_io()) { real_bgen_read(self, sample_ids, snp_ids, H, verbose, nthreads); return; }
+  std::ifstream fd(self->filename, std::ios::binary | std::ios::ate);
+  if (!fd.is_open()) { std::cout << "Exception occurred while trying to open BGEN file " << self->filename << std::endl; exit(1); }
+  std::vector<uint8_t> image((size_t)fd.tellg());
+  fd.seekg(0);
+  fd.read((char *)image.data(), (std::streamsize)image.size());
+  const int num_samples = (int)sample_ids.size(), num_snps = (int)snp_ids.size();
+  vector<int> sample_idx(num_samples, -1);
+  match_indices(self->sample.ID, sample_ids, sample_idx);            // unchanged (:167-168)
+  int32_t M = 0, Nfile = 0;
+  if (kgw_bgen_variant_count(image.data(), (int64_t)image.size(), &M, &Nfile) != KGW_OK) { std::cerr << kgw_last_error() << std::endl; exit(1); }
+  std::vector<int64_t> roff(M);
+  std::vector<int32_t> rlen(M);
+  if (kgw_bgen_rsids(image.data(), (int64_t)image.size(), M, roff.data(), rlen.data()) != KGW_OK) { std::cerr << kgw_last_error() << std::endl; exit(1); }
+  std::unordered_map<std::string, int32_t> where;                    // rsid -> position in file order (first occurrence, as std::find)
+  for (int32_t v = 0; v < M; v++) where.emplace(std::string((const char *)image.data() + roff[v], (size_t)rlen[v]), v);
+  std::vector<int32_t> variant_of_col(num_snps), sidx(sample_idx.begin(), sample_idx.end());
+  for (int j = 0; j < num_snps; j++) {
+    auto it = where.find(snp_ids[j]);
+    if (it == where.end()) { cerr << "Error loading BGEN file. Some requested variants were not found."; exit(1); }   // :238-241
+    variant_of_col[j] = it->second;
+  }
+  const int64_t row_bytes = (num_snps + 7) / 8;
+  std::vector<uint8_t> Hflat((size_t)2 * num_samples * row_bytes);
+  if (kgw_bgen_read(image.data(), (int64_t)image.size(), num_samples, sidx.data(), num_snps, variant_of_col.data(), nthreads,
+                    /*device=*/0, row_bytes, Hflat.data(), nullptr) != KGW_OK) {
+    std::cerr << "Error: " << kgw_last_error() << std::endl;         // incl. prob_to_hap's "Incorrect input" (:48-63)
+    exit(1);
+  }
+  H.clear();
+  H = vector<chaplotype>(2 * num_samples, chaplotype(num_snps));     // as BgenReader::read (:76-77)
+  for (int i = 0; i < 2 * num_samples; i++)
+    std::copy(Hflat.begin() + (size_t)i * row_bytes, Hflat.begin() + (size_t)(i + 1) * row_bytes, H[i].data.begin());
+}
+
+// plink::write_binary(basename, metadata, H, Hk, random) (plink_interface.cpp:255-284): the .bed body comes from the device
+void wrap_write_binary(const string &basename, const Metadata &metadata, const vector<chaplotype> &H, const vector<chaplotype> &Hk,
+                       bool random) {
+  if (!shim_io()) { real_write_binary(basename, metadata, H, Hk, random); return; }
+  const int num_haps = (int)H.size(), num_snps = (int)H[0].size();
+  int seed = 2019;                                                   // coin flips as before (:262-274)
+  std::mt19937_64 rng(seed);
+  std::uniform_int_distribution<int> coin_flip(0, 1);
+  vector<bool> swap(num_snps, 0);
+  std::vector<uint8_t> swap8(num_snps);
+  for (int j = 0; j < num_snps; j++) { swap[j] = coin_flip(rng); swap8[j] = swap[j] ? 1 : 0; }
+  const int64_t row_bytes = (num_snps + 7) / 8;
+  std::vector<uint8_t> Hflat((size_t)num_haps * row_bytes), Hkflat(Hflat.size());
+  for (int i = 0; i < num_haps; i++) {
+    std::copy(H[i].data.begin(), H[i].data.begin() + row_bytes, Hflat.begin() + (size_t)i * row_bytes);
+    std::copy(Hk[i].data.begin(), Hk[i].data.begin() + row_bytes, Hkflat.begin() + (size_t)i * row_bytes);
+  }
+  std::vector<uint8_t> body((size_t)2 * num_snps * kgw_bed_column_bytes(num_haps));
+  if (kgw_bed_encode(num_haps, num_snps, row_bytes, Hflat.data(), Hkflat.data(), swap8.data(), /*device=*/0, body.data()) != KGW_OK) {
+    std::cerr << "Error: " << kgw_last_error() << std::endl;
+    exit(-1);
+  }
+  std::ofstream file(basename + ".bed", std::ios_base::binary);
+  if (!file.is_open()) {
+    cerr << "Problem creating the output file: " << basename << ".bed";
+    cerr << "Either the directory does not exist or you do not have write permissions." << endl;
+    exit(1);
+  }
+  const unsigned char magic[3] = {0x6c, 0x1b, 0x01};               // :56
+  file.write((const char *)magic, 3);
+  file.write((const char *)body.data(), (std::streamsize)body.size());
+  file.close();
+  writeBIM(basename, metadata, true, swap);                          // unchanged text files
+  writeFAM(basename, metadata);
+  cout << "Output (binary) written to:" << endl;
+  cout << "  " << basename << ".bed" << endl;
+  cout << "  " << basename << ".bim" << endl;
+  cout << "  " << basename << ".fam" << endl;
+}
 
 namespace {
 

@@ -273,6 +273,38 @@ int32_t kgw_bgen_variant_count(const uint8_t *file, int64_t file_bytes, int32_t 
   return KGW_OK;
 }
 
+int32_t kgw_bgen_rsids(const uint8_t *file, int64_t file_bytes, int32_t n_variants, int64_t *rsid_off, int32_t *rsid_len) {
+  if (!file || !rsid_off || !rsid_len || file_bytes < 24) return kgw_fail_(KGW_ERR_INVALID, "null argument or BGEN image shorter than its header");
+  const uint32_t offset = rd32(file), M = rd32(file + 8);
+  if ((uint32_t)n_variants != M) return kgw_fail_(KGW_ERR_INVALID, "n_variants differs from the BGEN header");
+  const uint32_t hlen = rd32(file + 4);
+  if (hlen < 20 || 4ll + hlen > file_bytes || 4ll + offset > file_bytes) return kgw_fail_(KGW_ERR_INVALID, "BGEN header lengths outside the file");
+  const uint32_t flags = rd32(file + 4 + hlen - 4);
+  if (((flags >> 2) & 15u) != 2u) return kgw_fail_(KGW_ERR_UNSUPPORTED, "only BGEN layout 2 (v1.2) is built");
+  int64_t pos = 4ll + offset;
+  for (uint32_t v = 0; v < M; v++) {
+    if (pos + 2 > file_bytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+    pos += 2 + rd16(file + pos);                               // variant id
+    if (pos + 2 > file_bytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+    rsid_len[v] = rd16(file + pos);
+    rsid_off[v] = pos + 2;
+    pos += 2 + rsid_len[v];
+    if (pos + 2 > file_bytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+    pos += 2 + rd16(file + pos);                               // chromosome
+    if (pos + 6 > file_bytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+    const uint16_t nall = rd16(file + pos + 4);
+    pos += 6;
+    for (uint16_t a = 0; a < nall; a++) {
+      if (pos + 4 > file_bytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+      pos += 4 + (int64_t)rd32(file + pos);
+    }
+    if (pos + 4 > file_bytes) return kgw_fail_(KGW_ERR_INVALID, "truncated BGEN variant block");
+    pos += 4 + (int64_t)rd32(file + pos);
+    if (pos > file_bytes) return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block runs past the end of the file");
+  }
+  return KGW_OK;
+}
+
 int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples, const int32_t *sample_idx, int32_t p,
                       const int32_t *variant_of_col, int32_t host_threads, int32_t device, int64_t row_bytes, uint8_t *H_out,
                       float *kernel_ms) {

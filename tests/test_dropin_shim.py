@@ -3,6 +3,8 @@ clusters and reference selection, IBD tidying, partitions, PLINK writer) linked 
 in front of Knockoffs::generate (GNU ld --wrap) and with libkgw.so (integration/build_dropin.sh; the binary exists
 only where /root/reference was available to build it and travels to the GPU box with oracle/_ref/).
 
+The shim also replaces BgenReader::read (-> kgw_bgen_read) and plink::write_binary (-> kgw_bed_encode) unless KGW_SHIM_IO=0.
+
 CPU: the kgw_problem the shim assembles from the reference's objects equals, array for array, what the probe
 recorded from the reference itself (tests/golden/toy_chr22_K10_res2.npz), and without a GPU the binary stops with
 the library's "no CPU fallback" error instead of producing output.
@@ -34,15 +36,16 @@ def _lay_out_inputs(d: Path) -> dict:
     return {k: str(d / f"{k}.txt") for k in ("keep", "extract", "map", "part", "ibd")} | {"bgen": str(d / "example_chr22")}
 
 
-def _run(tmp_path: Path, dump: bool):
-    (tmp_path / "in").mkdir()
-    (tmp_path / "out").mkdir()
+def _run(tmp_path: Path, dump: bool, shim_io: bool = True):
+    (tmp_path / "in").mkdir(exist_ok=True)
+    (tmp_path / "out").mkdir(exist_ok=True)
     fl = _lay_out_inputs(tmp_path / "in")
     args = [str(BINARY), "--bgen", fl["bgen"], "--keep", fl["keep"], "--extract", fl["extract"], "--map", fl["map"],
             "--part", fl["part"], "--ibd", fl["ibd"], "--K", "10", "--cluster_size_min", "1000", "--cluster_size_max", "10000",
             "--n_threads", "1", "--seed", "2020", "--hmm-rho", "1", "--hmm-lambda", "1e-3", "--windows", "0",
             "--resolution", "2", "--compute-references", "--generate-knockoffs", "--out", str(tmp_path / "out" / "ko")]
     env = dict(os.environ)
+    env["KGW_SHIM_IO"] = "1" if shim_io else "0"          # 1: BgenReader::read and plink::write_binary also go through libkgw
     if dump:
         env["KGW_SHIM_DUMP"] = str(tmp_path / "dump")
     return subprocess.run(args, env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=900)
@@ -58,7 +61,7 @@ def _cuda_device_present() -> bool:
 
 @needs_binary
 def test_shim_assembles_the_problem_the_reference_hands_to_generate(tmp_path):
-    r = _run(tmp_path, dump=True)
+    r = _run(tmp_path, dump=True, shim_io=False)         # the reference reads the BGEN itself: possible without a GPU
     prob, _ = load_golden("toy_chr22_K10_res2")
     d = tmp_path / "dump" / "call0"
     rd = lambda name, t: np.fromfile(d / name, dtype=t)
@@ -83,18 +86,25 @@ def test_shim_assembles_the_problem_the_reference_hands_to_generate(tmp_path):
         assert r.returncode != 0
         assert "no CPU fallback" in r.stderr
         assert not list((tmp_path / "out").glob("*.bed"))
+        r2 = _run(tmp_path, dump=False, shim_io=True)    # with the reader replaced too the stop comes at the BGEN ingest
+        assert r2.returncode != 0 and "no CPU fallback" in r2.stderr
 
 
 @pytest.mark.gpu
 @needs_binary
 def test_dropin_binary_writes_the_librarys_knockoffs(tmp_path):
     kg = pytest.importorskip("knockoffgwas_b200")
-    r = _run(tmp_path, dump=False)
+    r = _run(tmp_path, dump=False, shim_io=True)          # BGEN ingest, sampler and .bed body all on the device
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     beds = sorted((tmp_path / "out").glob("*_res2.bed"))
     assert len(beds) == 1, [b.name for b in (tmp_path / "out").iterdir()]
     bed = np.fromfile(beds[0], dtype=np.uint8)
     assert bytes(bed[:3]) == b"\x6c\x1b\x01"
+    bim = (tmp_path / "out" / beds[0].name.replace(".bed", ".bim")).read_bytes()
+    r0 = _run(tmp_path, dump=False, shim_io=False)        # the reference's own reader and writer around the device sampler
+    assert r0.returncode == 0, r0.stdout[-2000:] + r0.stderr[-2000:]
+    assert np.array_equal(np.fromfile(beds[0], dtype=np.uint8), bed), "the two forms of the drop-in write different .bed files"
+    assert (tmp_path / "out" / beds[0].name.replace(".bed", ".bim")).read_bytes() == bim
     prob, _ = load_golden("toy_chr22_K10_res2")
     fams = [(m, [(s[0], s[1], s[4]) for s in segs]) for m, segs in prob.fam_clusters]
     hk, _ = kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, unrelated=prob.unrelated,
