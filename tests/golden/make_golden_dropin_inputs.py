@@ -19,5 +19,5 @@ files = {
     "part": REF / "partitions/example_chr22.txt",
     "ibd": REF / "ibd/example_chr22.txt",
 }
-np.savez_compressed(OUT / "toy_chr22_inputs.npz", **{k: np.frombuffer(p.read_bytes(), np.uint8) for k, p in files.items()})
-print("wrote", OUT / "toy_chr22_inputs.npz", {k: p.stat().st_size for k, p in files.items()})
+np.savez_compressed(OUT / "dropin_chr22_inputs.npz", **{k: np.frombuffer(p.read_bytes(), np.uint8) for k, p in files.items()})
+print("wrote", OUT / "dropin_chr22_inputs.npz", {k: p.stat().st_size for k, p in files.items()})

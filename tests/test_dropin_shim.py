@@ -27,7 +27,7 @@ needs_binary = pytest.mark.skipif(not BINARY.exists(), reason="oracle/_ref/snpkn
 
 
 def _lay_out_inputs(d: Path) -> dict:
-    f = np.load(GOLD / "toy_chr22_inputs.npz")
+    f = np.load(GOLD / "dropin_chr22_inputs.npz")
     (d / "example_chr22.bgen").write_bytes(np.load(GOLD / "bgen_toy_chr22.npz")["image"].tobytes())
     (d / "example_chr22.sample").write_bytes(f["sample"].tobytes())
     (d / "example_chr22.bim").write_bytes(f["bim"].tobytes())
