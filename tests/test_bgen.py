@@ -112,3 +112,22 @@ def test_gpu_rejects_truncated_probability_block():
     b[pos + 4 + 9 + 16] = 16
     with pytest.raises(kg.KgwError):
         kg.read_bgen_image(np.frombuffer(bytes(b), np.uint8), np.arange(16), np.arange(3))
+
+
+def test_reader_mirror_id_bookkeeping_without_gpu(tmp_path):
+    """The host part of api.BgenReader (variant ids from the container, sample ids from the .sample file, the reference's
+    error for a variant that is not in the file) needs no device."""
+    kg = pytest.importorskip("knockoffgwas_b200")
+    bits, rsids, img = _synthetic(n=6, p=9)
+    (tmp_path / "x.bgen").write_bytes(img)
+    (tmp_path / "x.sample").write_text("ID_1 ID_2 missing sex\n0 0 0 D\n" + "".join(f"s{i} s{i} 0 1\n" for i in range(6)))
+    rd = kg.BgenReader(tmp_path / "x")
+    assert (rd.n_samples, rd.n_variants) == (6, 9) and rd.variant_ids == rsids and rd.sample_ids == [f"s{i}" for i in range(6)]
+    with pytest.raises(kg.KgwError, match="requested variants were not found"):
+        rd.read(snp_ids=["rs1", "nope"])
+    with pytest.raises(kg.KgwError, match="not in the BGEN sample file"):
+        rd.read(sample_ids=["s1", "nobody"])
+    (tmp_path / "y.bgen").write_bytes(img)
+    (tmp_path / "y.sample").write_text("ID_1 ID_2 missing sex\n0 0 0 D\ns0 s0 0 1\n")
+    with pytest.raises(kg.KgwError, match="number of samples does not match"):
+        kg.BgenReader(tmp_path / "y")
