@@ -7,6 +7,7 @@
  */
 #include "kgw_oracle.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -322,4 +323,104 @@ int kgw_oracle_unrelated(const kgw_oracle_problem *P, kgw_oracle_rng *rng, const
   free(grp_first); free(grp_last); free(z); free(zk); free(hk_tmp); free(hk); free(backward);
   free(weights); free(N); free(N_old); free(vstar); free(vbar);
   return 0;
+}
+
+/* ---- --estimate-hmm (restated ahead of the CUDA work) ---------------------------------------
+ * Knockoffs::EM / EM_step / EM_worker (knockoffs.cpp:706-960), single-threaded.  As the reference stands, the
+ * recombination scale is NOT updated (`new_rho = rho`, :929-930; EM_solve_rho is commented out) and the Xi
+ * accumulation (:803-830) feeds nothing, so one EM step is: for every haplotype, backward and forward passes
+ * (compute_hmm_backward :1041-1075, compute_hmm_forward :1087-1125), posterior marginals (:777-787), expected
+ * mismatches gamma_j (:789-798); then mu_j := clamp(mean gamma_j, 1e-6, 1e-3) (:917-926, update_hmm :1550-1561).
+ * Iterations stop when the root-mean-square relative change of mu falls below 5e-2, or after 20 (:716-736).
+ * mu_init: what Knockoffs::init_hmm(K, rho) leaves (:1527-1548; compute_maf, haplotypes.cpp:101-111, adds 1.0 for
+ * every haplotype whatever its allele, so maf_j = min(1, 1 - 1) and every mu_j starts at the lower clamp 1e-5). */
+static void hmm_forward(const kgw_oracle_problem *P, int i, const int32_t *ref, double *forward, int j_start, int j_end) {
+  const int K = P->K;
+  const double alpha = 1.0 / K;
+  double forwardSum_0 = 0.0;
+  const int h0 = hap_bit(P, i, j_start);
+  double *f0 = forward + (int64_t)j_start * K;
+  for (int k = 0; k < K; k++) {
+    const int h0_ref = hap_bit(P, ref[k], j_start);
+    if (h0 == h0_ref) f0[k] = alpha * (1.0 - P->mu[j_start]);
+    else f0[k] = alpha * P->mu[j_start];
+    forwardSum_0 += f0[k];
+  }
+  for (int k = 0; k < K; k++) f0[k] /= forwardSum_0;
+  for (int j = j_start + 1; j < j_end; j++) {
+    const int h = hap_bit(P, i, j);
+    const double bj = P->b[j];
+    const double mut_j = P->mu[j];
+    double forwardSum = 0.0;
+    const double *prev = forward + (int64_t)(j - 1) * K;
+    double *cur = forward + (int64_t)j * K;
+    for (int k = 0; k < K; k++) {
+      const double a_j_k = (1.0 - bj) * alpha;
+      cur[k] = a_j_k + bj * prev[k];
+      const int h_ref = hap_bit(P, ref[k], j);
+      if (h == h_ref) cur[k] *= (1.0 - mut_j);
+      else cur[k] *= mut_j;
+      forwardSum += cur[k];
+    }
+    for (int k = 0; k < K; k++) cur[k] /= forwardSum;
+  }
+}
+
+int kgw_oracle_em(const kgw_oracle_problem *P0, const double *mu_init, double *mu_out, int32_t *iterations, double *deltas) {
+  const int N = P0->N, p = P0->p, K = P0->K;
+  kgw_oracle_problem P = *P0;
+  double *mu = (double *)malloc(sizeof(double) * (size_t)p);
+  double *gamma = (double *)malloc(sizeof(double) * (size_t)p);
+  double *backward = (double *)malloc(sizeof(double) * (size_t)p * K);
+  double *forward = (double *)malloc(sizeof(double) * (size_t)p * K);
+  double *marginal = (double *)malloc(sizeof(double) * (size_t)K);
+  if (!mu || !gamma || !backward || !forward || !marginal) return -1;
+  memcpy(mu, mu_init, sizeof(double) * (size_t)p);
+  P.mu = mu;
+  const double delta_min = 5e-2;
+  const int it_max = 20;
+  const double n_inv = 1.0 / (double)N;
+  int it = 0, converged = 0;
+  for (it = 0; it < it_max; it++) {
+    for (int j = 0; j < p; j++) gamma[j] = 0.0;
+    for (int i = 0; i < N; i++) { /* every haplotype, related or not (:862-864) */
+      for (int w = 0; w < P.W; w++) {
+        const int32_t *ref = P.ref_local + ((int64_t)i * P.W + w) * K;
+        int js, je;
+        window_pad(&P, w, &js, &je);
+        hmm_backward(&P, i, ref, backward, js, je);
+        hmm_forward(&P, i, ref, forward, js, je);
+        for (int j = P.win_start[w]; j < P.win_end[w]; j++) {
+          double marginal_sum = 0;
+          for (int k = 0; k < K; k++) {
+            marginal[k] = backward[(int64_t)j * K + k] * forward[(int64_t)j * K + k];
+            marginal_sum += marginal[k];
+          }
+          for (int k = 0; k < K; k++) marginal[k] /= marginal_sum;
+          const int h_real = hap_bit(&P, i, j);
+          for (int k = 0; k < K; k++)
+            if (h_real != hap_bit(&P, ref[k], j)) gamma[j] += marginal[k];
+        }
+      }
+    }
+    double delta_mutation = 0;
+    for (int j = 0; j < p; j++) {
+      double g = 0.0 + gamma[j] * n_inv; /* :908-914 with one worker */
+      g = (g > 1e-6) ? g : 1e-6;         /* std::max(1e-6, gamma) */
+      g = (g < 1e-3) ? g : 1e-3;         /* std::min(1e-3, gamma) */
+      const double denom = (mu[j] > 1e-5) ? mu[j] : 1e-5;
+      const double delta_j = fabs(g - mu[j]) / denom;
+      delta_mutation += delta_j * delta_j;
+      gamma[j] = g;
+    }
+    delta_mutation = sqrt(delta_mutation / (double)p);
+    const double delta_parameters = (0.0 > delta_mutation) ? 0.0 : delta_mutation; /* max(delta_recomb = 0, .) */
+    for (int j = 0; j < p; j++) mu[j] = gamma[j];
+    if (deltas) deltas[it] = delta_parameters;
+    if (delta_parameters < delta_min) { converged = 1; break; }
+  }
+  memcpy(mu_out, mu, sizeof(double) * (size_t)p);
+  if (iterations) *iterations = converged ? it + 1 : it;
+  free(mu); free(gamma); free(backward); free(forward); free(marginal);
+  return converged ? 0 : 1;
 }

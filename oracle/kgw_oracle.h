@@ -60,6 +60,11 @@ int kgw_oracle_unrelated(const kgw_oracle_problem *P, kgw_oracle_rng *rng,
                          const int32_t *haps, int32_t n,
                          int32_t *z, int32_t *zk, uint8_t *hk, double *beta);
 
+/* --estimate-hmm as the reference runs it (Knockoffs::EM, knockoffs.cpp:706-960): mutation rates only, rho fixed.
+ * mu_init, mu_out: double [p]; deltas (may be NULL): double [20], the change reported by every step; *iterations =
+ * steps run.  Returns 0 when converged, 1 when the 20 steps ran out, negative on error. */
+int kgw_oracle_em(const kgw_oracle_problem *P, const double *mu_init, double *mu_out, int32_t *iterations, double *deltas);
+
 /* One IBD-sharing family as generate_related_cluster() sees it (knockoffs.cpp:465-481):
  * member list + TIDIED segments (the unchanged host code runs IbdCluster::tidy, ibd.cpp:99-189). */
 typedef struct {

@@ -604,3 +604,21 @@ def haps_read(text, sample_idx, row_of_col) -> np.ndarray:
             bits[2 * i, j] = toks[2 * s] == b"1"
             bits[2 * i + 1, j] = toks[2 * s + 1] == b"1"
     return pack_bits(bits)
+
+
+def run_em(prob: Problem, mu_init=None):
+    """Restated Knockoffs::EM (--estimate-hmm): returns (mu after EM, steps run, per-step deltas, converged)."""
+    L = lib()
+    L.kgw_oracle_em.restype = C.c_int
+    p = prob.p
+    mu0 = np.ascontiguousarray(np.full(p, 1e-5) if mu_init is None else mu_init, dtype=np.float64)
+    out = np.zeros(p, dtype=np.float64)
+    deltas = np.zeros(20, dtype=np.float64)
+    it = C.c_int32(0)
+    P = prob._c()
+    rc = L.kgw_oracle_em(C.byref(P), C.c_void_p(mu0.ctypes.data), C.c_void_p(out.ctypes.data), C.byref(it),
+                         C.c_void_p(deltas.ctypes.data))
+    if rc < 0:
+        raise RuntimeError(f"kgw_oracle_em failed with {rc}")
+    n = int(it.value)
+    return out, n, deltas[:max(n, 1)].copy(), rc == 0
