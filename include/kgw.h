@@ -88,8 +88,9 @@ typedef struct kgw_problem {
   int32_t n_unrelated;
   int32_t reserved1;
   uint64_t seed;              /* Knockoffs::seed                            knockoffs.h:71           */
-  /* test hook: if non-NULL, U[N][3][p] doubles in [0,1) replace the generator for the
-   * unrelated branch (stream order KGW_STREAM_Z, _ZK, _HK; indexed by absolute haplotype). */
+  /* test hook: if non-NULL, U[N][W][3][p] doubles in [0,1) replace the generator (window pass w, stream order
+   * KGW_STREAM_Z, _ZK, _HK; indexed by absolute haplotype and absolute locus -- the padded passes of
+   * knockoffs.cpp:1222-1226 overlap, so every pass has its own block; the related branch reads block 0). */
   const double *injected_u;
   /* related haplotypes (NULL or n_families == 0: none).  Needs ref_global.  Their draws use the same
    * keyed generator: (member haplotype, KGW_STREAM_Z / _ZK / _HK, locus). */
@@ -99,7 +100,7 @@ typedef struct kgw_problem {
 typedef struct kgw_options {
   int32_t device;        /* CUDA device ordinal (one process per GPU: pass LOCAL_RANK)        */
   int32_t block_loci;    /* 0 = default (4); 2, 4 or 8: spacing of the stored backward-message rows */
-  int32_t lanes_per_hap; /* 0 = auto; 4, 8, 16 or 32 lanes cooperate on one haplotype         */
+  int32_t lanes_per_hap; /* 0 = auto; 1, 2, 4 or 8 lanes cooperate on one haplotype (K <= 32 lanes) */
   int32_t ctas_per_sm;   /* 0 = auto (occupancy query)                                        */
   void *stream;          /* cudaStream_t to launch on (caller-owned); NULL = the plan creates
                             its own non-blocking stream                                       */

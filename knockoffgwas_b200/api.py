@@ -176,12 +176,18 @@ class _Held:
         self.mu = np.ascontiguousarray(mu, dtype=np.float64)
         self.groups = np.ascontiguousarray(groups, dtype=np.int32)
         assert self.b.shape == (self.p,) and self.mu.shape == (self.p,) and self.groups.shape == (self.p,)
-        self.unrelated = np.arange(self.N, dtype=np.int32) if unrelated is None else np.ascontiguousarray(unrelated, dtype=np.int32)
+        if unrelated is None:
+            # every haplotype without IBD relatives (metadata.unrelated, metadata.cpp:242-293)
+            unrelated = np.arange(self.N, dtype=np.int32)
+            if families:
+                related = np.concatenate([np.asarray(m, dtype=np.int32) for m, _ in families])
+                unrelated = np.setdiff1d(unrelated, related).astype(np.int32)
+        self.unrelated = np.ascontiguousarray(unrelated, dtype=np.int32)
         self.seed = int(seed)
         self.injected_u = None
         if injected_u is not None:
             self.injected_u = np.ascontiguousarray(injected_u, dtype=np.float64)
-            assert self.injected_u.shape == (self.N, 3, self.p)
+            assert self.injected_u.shape in ((self.N, self.W, 3, self.p),) + (((self.N, 3, self.p),) if self.W == 1 else ())
         self.fam = None
         if families:
             # families: [(members, [(j_min, j_max, ..., ids) | (j_min, j_max, ids), ...]), ...] -- member lists in

@@ -8,6 +8,7 @@
 #include "kgw_device.cuh"
 #include "kgw_variants.h"
 #include "kgw_family.cuh"
+#include "kgw_common.h"
 
 #include <cmath>
 #include <chrono>
@@ -486,7 +487,7 @@ void fam_build_ops(const FamilyState &F, int f, const int32_t *groups, const std
 }  // namespace
 
 struct kgw_plan {
-  int device = 0;
+  int device = 0, sm_count = 148;
   int N = 0, p = 0, K = 0, W = 0, n_haps = 0;
   int64_t row_bytes = 0;
   int stride_w = 0;
@@ -635,6 +636,17 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   F->h_seg_ids.assign(fi->seg_ids, fi->seg_ids + F->h_seg_ids_off.back());
   F->members_total = (int)F->h_members.size();
   for (int id : F->h_members) if (id < 0 || id >= N) return fail(KGW_ERR_INVALID, "family member out of range");
+  {
+    // metadata.unrelated and metadata.related_families are disjoint (metadata.cpp:242-293) and a haplotype belongs
+    // to one family: both branches write the member's row of Hk
+    std::vector<uint8_t> seen(N, 0);
+    for (int id : pl->haps) seen[id] = 1;
+    for (int id : F->h_members) {
+      if (seen[id] == 1) return fail(KGW_ERR_INVALID, "a family member is also listed in `unrelated`");
+      if (seen[id] == 2) return fail(KGW_ERR_INVALID, "a haplotype is listed in two families (or twice in one)");
+      seen[id] = 2;
+    }
+  }
   for (size_t t = 0; t < (size_t)N * K; t++)
     if (prob->ref_global[t] < 0 || prob->ref_global[t] >= N) return fail(KGW_ERR_INVALID, "global reference index out of range");
 
@@ -769,7 +781,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   P.N = N; P.p = p; P.K = K; P.n_families = F->n_families; P.stride_w = pl->stride_w; P.n_max = F->n_max;
   P.uniform_mu = uniform ? 1 : 0;
   P.Hw = pl->dHw; P.ref_global = F->dref_global; P.fams = F->dfams; P.members = F->dmembers; P.iv_start = F->divstart;
-  P.ivs = F->divs; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.msg = F->dmsg; P.mrc = F->dmrc; P.rtot = F->rtot; P.pad0 = 0; P.pat = F->dpat;
+  P.ivs = F->divs; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.msg = F->dmsg; P.mrc = F->dmrc; P.rtot = F->rtot; P.W = pl->W; P.pat = F->dpat;
   P.phase_cycles = nullptr;
 #ifdef KGW_PHASES
   KGW_CUDA(cudaMalloc(&F->dphase, sizeof(long long) * 8));
@@ -858,7 +870,19 @@ int launch(kgw_plan *pl) {
 
 }  // namespace
 
-// shared with kgw_bed.cu
+// shared with the other translation units (kgw_common.h)
+cudaError_t kgw_dev_malloc_(void **out, size_t bytes) {
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_pool.clear(dev) > 0) {
+      cudaGetLastError();
+      e = cudaMalloc(out, bytes);
+    }
+  }
+  return e;
+}
 int kgw_fail_(int code, const std::string &msg) { return fail(code, msg); }
 void *kgw_plan_device_h_(kgw_plan *pl, int *N, int *p, int *stride_w, int *device, void **stream) {
   *N = pl->N; *p = pl->p; *stride_w = pl->stride_w; *device = pl->device; *stream = (void *)pl->stream;
@@ -888,7 +912,6 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
     return fail(KGW_ERR_INVALID, "null input buffer");
   if (prob->n_unrelated < 0 || (prob->n_unrelated > 0 && !prob->unrelated))
     return fail(KGW_ERR_INVALID, "bad unrelated list");
-  if (prob->injected_u && W != 1) return fail(KGW_ERR_UNSUPPORTED, "injected uniforms are defined for a single window only");
   if (K > 256) return fail(KGW_ERR_UNSUPPORTED, "K > 256 is not built (latent states are stored as bytes)");
   kgw_options o{};
   if (opt) o = *opt;
@@ -921,6 +944,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
 
   kgw_plan *pl = new kgw_plan();
   pl->device = o.device;
+  pl->sm_count = dp.multiProcessorCount;
   pl->N = N; pl->p = p; pl->K = K; pl->W = W;
   pl->n_haps = prob->n_unrelated;
   pl->row_bytes = prob->row_bytes;
@@ -1047,7 +1071,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   if (pl->n_haps)
     KGW_CUDA_PL(cudaMemcpyAsync(pl->dhaps, pl->haps.data(), sizeof(int32_t) * pl->n_haps, cudaMemcpyHostToDevice, pl->stream));
   if (prob->injected_u) {
-    const size_t ub = sizeof(double) * (size_t)N * 3 * p;
+    const size_t ub = sizeof(double) * (size_t)N * W * 3 * p;
     KGW_CUDA_PL(pl->alloc(&pl->dinj, ub));
     KGW_CUDA_PL(cudaMemcpyAsync(pl->dinj, prob->injected_u, ub, cudaMemcpyHostToDevice, pl->stream));
   }
@@ -1267,7 +1291,7 @@ int32_t kgw_plan_download(kgw_plan *pl, uint8_t *hk_out, kgw_debug *dbg) {
       KGW_CUDA(pl->alloc(&pl->dout_rows, sizeof(int32_t) * n));
       KGW_CUDA(cudaMemcpyAsync(pl->dout_rows, rows.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, pl->stream));
     }
-    rows_from_pitched<<<148 * 8, 256, 0, pl->stream>>>((const uint8_t *)pl->dHk, (size_t)pl->stride_w * 4,
+    rows_from_pitched<<<pl->sm_count * 8, 256, 0, pl->stream>>>((const uint8_t *)pl->dHk, (size_t)pl->stride_w * 4,
                                                        contiguous ? nullptr : pl->dout_rows, rows[0], pl->dstage, rb, n);
     KGW_CUDA(cudaGetLastError());
     if (contiguous && (size_t)pl->row_bytes == rb) {

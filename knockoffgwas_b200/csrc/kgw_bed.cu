@@ -13,6 +13,7 @@
 // four 2-bit codes of 4 samples = exactly one .bed byte.  The CTA assembles 32 contiguous output bytes per
 // locus in shared memory and writes them as 16-byte (or 4-byte / single-byte) stores, one full 32-byte
 // sector per (locus, tile).
+#include "kgw_common.h"
 #include "../../include/kgw.h"
 
 #include <cuda_runtime.h>
@@ -121,10 +122,10 @@ int encode_on_device(const uint32_t *dH, const uint32_t *dHk, int N, int p, int 
   const size_t out_bytes = (size_t)ncols * (size_t)nb;
   uint8_t *dswap = nullptr, *dout = out_dev_in;
   if (swap_host && dH && dHk) {
-    BED_CUDA(cudaMalloc(&dswap, (size_t)p));
+    BED_CUDA(kgw_malloc(&dswap, (size_t)p));
     BED_CUDA(cudaMemcpyAsync(dswap, swap_host, (size_t)p, cudaMemcpyHostToDevice, st));
   }
-  if (!dout) BED_CUDA(cudaMalloc(&dout, out_bytes));
+  if (!dout) BED_CUDA(kgw_malloc(&dout, out_bytes));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
   const dim3 grid((unsigned)((p + BED_LOCI - 1) / BED_LOCI), (unsigned)((N + BED_HAPS - 1) / BED_HAPS));
@@ -175,7 +176,7 @@ int32_t kgw_bed_encode(int32_t N, int32_t p, int64_t row_bytes, const uint8_t *H
   const uint8_t *src[2] = {H, Hk};
   for (int m = 0; m < 2; m++) {
     if (!src[m]) continue;
-    BED_CUDA(cudaMalloc(&d[m], bytes));
+    BED_CUDA(kgw_malloc(&d[m], bytes));
     BED_CUDA(cudaMemset(d[m], 0, bytes));
     BED_CUDA(cudaMemcpy2D(d[m], (size_t)stride_w * 4, src[m], (size_t)row_bytes, (size_t)(p + 7) / 8, N, cudaMemcpyHostToDevice));
   }

@@ -13,6 +13,7 @@
 //   prob_to_hap: P(first allele) == 1 -> bit 0;  == 0 -> bit 1;  anything else (or a missing sample) is
 //   "Incorrect input" in the reference (a throw that nothing catches) and an error status here.
 // HBM-bound byte work: per variant ~ (2 B/8 + 1) N bytes read, 2N/8 bytes written.
+#include "kgw_common.h"
 #include "../../include/kgw.h"
 
 #include <cuda_runtime.h>
@@ -395,14 +396,14 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
 
   const int n_haps = 2 * n_samples;
   const int stride_w = (((p + 31) / 32) + 3) & ~3;   // rows padded to 16 bytes
-  KGW_CUDA_B(cudaMalloc(&dblocks, (size_t)total + 1024));   // the staged 16-byte loads of the fast path may run past the last block
-  KGW_CUDA_B(cudaMalloc(&doff, sizeof(long long) * p));
-  KGW_CUDA_B(cudaMalloc(&dinfo, sizeof(unsigned long long) * p));
-  KGW_CUDA_B(cudaMalloc(&dlen, sizeof(long long) * p));
+  KGW_CUDA_B(kgw_malloc(&dblocks, (size_t)total + 1024));   // the staged 16-byte loads of the fast path may run past the last block
+  KGW_CUDA_B(kgw_malloc(&doff, sizeof(long long) * p));
+  KGW_CUDA_B(kgw_malloc(&dinfo, sizeof(unsigned long long) * p));
+  KGW_CUDA_B(kgw_malloc(&dlen, sizeof(long long) * p));
   KGW_CUDA_B(cudaMemcpy(dlen, col_len.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
-  KGW_CUDA_B(cudaMalloc(&dsidx, sizeof(int32_t) * n_samples));
-  KGW_CUDA_B(cudaMalloc(&dH, sizeof(uint32_t) * (size_t)n_haps * stride_w));
-  KGW_CUDA_B(cudaMalloc(&dstatus, sizeof(int)));
+  KGW_CUDA_B(kgw_malloc(&dsidx, sizeof(int32_t) * n_samples));
+  KGW_CUDA_B(kgw_malloc(&dH, sizeof(uint32_t) * (size_t)n_haps * stride_w));
+  KGW_CUDA_B(kgw_malloc(&dstatus, sizeof(int)));
   KGW_CUDA_B(cudaMemcpy(dblocks, compression == 0u ? file + span_lo : stage, (size_t)total, cudaMemcpyHostToDevice));
   KGW_CUDA_B(cudaMemcpy(doff, col_off.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
   KGW_CUDA_B(cudaMemcpy(dsidx, sample_idx, sizeof(int32_t) * n_samples, cudaMemcpyHostToDevice));

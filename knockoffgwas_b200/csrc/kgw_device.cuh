@@ -102,7 +102,7 @@ struct KgwParams {
   uint8_t *zbuf, *zkbuf;     // [slots][p32][G]
   unsigned long long z_stride;
   unsigned long long seed;
-  const double *injected_u;  // [N][3][p] or null
+  const double *injected_u;  // [N][W][3][p] (indexed by absolute locus) or null
   int32_t *dbg_z, *dbg_zk;   // [n_haps][p] or null
   double *dbg_beta;          // [n_haps][nblk][K] or null (last pass)
   int32_t dbg_nblk;
@@ -279,7 +279,7 @@ struct UniformSrc {
   kgw_u32x4 blk;
   int cur;
   __device__ __forceinline__ void init(const KgwParams &P, int hap_, int stream_, int w) {
-    inj = P.injected_u ? P.injected_u + ((size_t)hap_ * 3 + stream_) * (size_t)P.p : nullptr;
+    inj = P.injected_u ? P.injected_u + (((size_t)hap_ * P.W + w) * 3 + stream_) * (size_t)P.p : nullptr;
     seed = P.seed;
     hap = (uint32_t)hap_;
     stream = (uint32_t)(stream_ | (w << 2));

@@ -107,12 +107,12 @@ struct KgwFamParams {
   uint32_t *Hk;                // [N][stride_w]
   double *msg;                 // [slots][n_max][p][K]      messages_left
   double *mrc;                 // [slots][n_max][rtot][K]   messages_right at the stored loci (special ranges + one locus before)
-  int32_t rtot, pad0;          // stored loci per member (maximum over the families)
+  int32_t rtot, W;             // stored loci per member (maximum over the families); windows of the problem (injected_u layout)
   uint8_t *pat;                // [slots][n_max][p][K]
   uint8_t *bytes;              // [slots][2][n_max][p]   Z (255 = node still active), Zk
   int32_t *work;               // next family to hand out (zeroed before every launch)
   unsigned long long seed;
-  const double *injected_u;    // [N][3][p] or null
+  const double *injected_u;    // [N][W][3][p] or null (the related branch reads window block 0)
   int32_t *dbg_z, *dbg_zk;     // [members total][p] or null
   int32_t *status;             // 0 ok; -10 missing knockoff variants; -11 inconsistency on Zk
   long long *phase_cycles;     // -DKGW_PHASES: [8] summed lane-0 clock64 deltas per phase, else null
@@ -155,7 +155,7 @@ __device__ __forceinline__ void fam_prefetch(const void *ptr, int bytes, int lan
 }
 
 __device__ __forceinline__ double fam_uniform(const KgwFamParams &P, int hap, int stream, int j) {
-  if (P.injected_u) return P.injected_u[((size_t)hap * 3 + stream) * (size_t)P.p + j];
+  if (P.injected_u) return P.injected_u[((size_t)hap * P.W * 3 + stream) * (size_t)P.p + j];   // window block 0 of [N][W][3][p]
   const kgw_u32x4 r = kgw_philox_block(P.seed, (uint32_t)hap, (uint32_t)stream, (uint32_t)(j >> 2));
   const int q = j & 3;
   return kgw_word_to_uniform(q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w)));

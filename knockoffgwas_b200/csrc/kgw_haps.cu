@@ -11,6 +11,7 @@
 // with a block-wide prefix sum and leaves one bit per token (token == "1"); pass 2 gathers the requested token
 // columns and transposes them into the [2 n_samples][stride] bit matrix (lane = haplotype, 128 loci per warp, one
 // 16-byte store per lane).  HBM-bound byte work: ~2 bytes read per (file haplotype, SNP), 1 bit written per cell.
+#include "kgw_common.h"
 #include "../../include/kgw.h"
 
 #include <cub/block/block_scan.cuh>
@@ -179,14 +180,14 @@ int32_t kgw_haps_read(const uint8_t *text, int64_t text_bytes, int32_t n_samples
   const int n_haps = 2 * n_samples;
   const int stride_w = (((p + 31) / 32) + 3) & ~3;
   KGW_CUDA_H(cudaSetDevice(device));
-  KGW_CUDA_H(cudaMalloc(&dtext, (size_t)text_bytes + 32));   // the tokenizer reads whole 16-byte chunks
-  KGW_CUDA_H(cudaMalloc(&doff, sizeof(long long) * p));
-  KGW_CUDA_H(cudaMalloc(&dlen, sizeof(int) * p));
-  KGW_CUDA_H(cudaMalloc(&dntok, sizeof(int) * p));
-  KGW_CUDA_H(cudaMalloc(&dstatus, sizeof(int)));
-  KGW_CUDA_H(cudaMalloc(&dsidx, sizeof(int32_t) * n_samples));
-  KGW_CUDA_H(cudaMalloc(&dbits, sizeof(uint32_t) * (size_t)p * tok_words));
-  KGW_CUDA_H(cudaMalloc(&dH, sizeof(uint32_t) * (size_t)n_haps * stride_w));
+  KGW_CUDA_H(kgw_malloc(&dtext, (size_t)text_bytes + 32));   // the tokenizer reads whole 16-byte chunks
+  KGW_CUDA_H(kgw_malloc(&doff, sizeof(long long) * p));
+  KGW_CUDA_H(kgw_malloc(&dlen, sizeof(int) * p));
+  KGW_CUDA_H(kgw_malloc(&dntok, sizeof(int) * p));
+  KGW_CUDA_H(kgw_malloc(&dstatus, sizeof(int)));
+  KGW_CUDA_H(kgw_malloc(&dsidx, sizeof(int32_t) * n_samples));
+  KGW_CUDA_H(kgw_malloc(&dbits, sizeof(uint32_t) * (size_t)p * tok_words));
+  KGW_CUDA_H(kgw_malloc(&dH, sizeof(uint32_t) * (size_t)n_haps * stride_w));
   KGW_CUDA_H(cudaMemcpy(dtext, text, (size_t)text_bytes, cudaMemcpyHostToDevice));
   KGW_CUDA_H(cudaMemcpy(doff, col_off.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
   KGW_CUDA_H(cudaMemcpy(dlen, col_len.data(), sizeof(int) * p, cudaMemcpyHostToDevice));

@@ -18,6 +18,7 @@
 //   select_kernel    one warp per haplotype: two-level 10-bit radix histogram finds the K-th smallest distance,
 //                    an ordered ballot compaction takes everything below it plus the first ties in cluster order,
 //                    a bitonic sort of the <= 256 (distance, position) keys gives the reference's output order.
+#include "kgw_common.h"
 #include "../../include/kgw.h"
 
 #include <cuda_runtime.h>
@@ -256,25 +257,25 @@ extern "C" int32_t kgw_assign_references(int32_t N, int32_t p, int64_t row_bytes
     cudaFree(dout); cudaFree(ddoff); cudaFree(dtiles);
   };
 #define REF_TRY(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { cleanup(); return kgw_fail_(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e2_)); } } while (0)
-  REF_TRY(cudaMalloc(&dH, (size_t)N * row_bytes));
+  REF_TRY(kgw_malloc(&dH, (size_t)N * row_bytes));
   REF_TRY(cudaMemcpy(dH, H, (size_t)N * row_bytes, cudaMemcpyHostToDevice));
-  REF_TRY(cudaMalloc(&dHt, sizeof(uint32_t) * (size_t)N * stride_t));
-  REF_TRY(cudaMalloc(&dmem, sizeof(int32_t) * n_rows));
+  REF_TRY(kgw_malloc(&dHt, sizeof(uint32_t) * (size_t)N * stride_t));
+  REF_TRY(kgw_malloc(&dmem, sizeof(int32_t) * n_rows));
   REF_TRY(cudaMemcpy(dmem, clust_members, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice));
-  REF_TRY(cudaMalloc(&doffc, sizeof(int32_t) * (n_clusters + 1)));
+  REF_TRY(kgw_malloc(&doffc, sizeof(int32_t) * (n_clusters + 1)));
   REF_TRY(cudaMemcpy(doffc, clust_off, sizeof(int32_t) * (n_clusters + 1), cudaMemcpyHostToDevice));
   if (family_of) {
-    REF_TRY(cudaMalloc(&dfam, sizeof(int32_t) * N));
+    REF_TRY(kgw_malloc(&dfam, sizeof(int32_t) * N));
     REF_TRY(cudaMemcpy(dfam, family_of, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
   }
   std::vector<int32_t> rowc(n_rows);
   for (int c = 0; c < n_clusters; c++)
     for (int r = clust_off[c]; r < clust_off[c + 1]; r++) rowc[r] = c;
-  REF_TRY(cudaMalloc(&drowc, sizeof(int32_t) * n_rows));
+  REF_TRY(kgw_malloc(&drowc, sizeof(int32_t) * n_rows));
   REF_TRY(cudaMemcpy(drowc, rowc.data(), sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice));
-  REF_TRY(cudaMalloc(&dout, sizeof(int32_t) * (size_t)N * K));
+  REF_TRY(kgw_malloc(&dout, sizeof(int32_t) * (size_t)N * K));
   REF_TRY(cudaMemset(dout, 0xff, sizeof(int32_t) * (size_t)N * K));
-  REF_TRY(cudaMalloc(&ddoff, sizeof(long long) * n_clusters));
+  REF_TRY(kgw_malloc(&ddoff, sizeof(long long) * n_clusters));
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaEventCreate(&e0);
@@ -306,8 +307,8 @@ extern "C" int32_t kgw_assign_references(int32_t N, int32_t p, int64_t row_bytes
     cudaFree(dD); dD = nullptr;
     cudaFree(dtiles); dtiles = nullptr;
     if (!tiles.empty()) {
-      REF_TRY(cudaMalloc(&dD, std::max<size_t>(words, 1) * 4));
-      REF_TRY(cudaMalloc(&dtiles, sizeof(TileDesc) * tiles.size()));
+      REF_TRY(kgw_malloc(&dD, std::max<size_t>(words, 1) * 4));
+      REF_TRY(kgw_malloc(&dtiles, sizeof(TileDesc) * tiles.size()));
       REF_TRY(cudaMemcpy(dtiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice));
       REF_TRY(cudaMemcpy(ddoff, doff.data(), sizeof(long long) * n_clusters, cudaMemcpyHostToDevice));
       distance_kernel<<<(unsigned)tiles.size(), 256>>>(dHt, stride_t, nwords, dtiles, doffc, dmem, dfam, ddoff, dD);

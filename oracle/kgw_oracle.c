@@ -26,7 +26,7 @@ double kgw_oracle_next_uniform(kgw_oracle_rng *rng, int hap, int stream, int loc
   double u;
   switch (rng->mode) {
     case KGW_ORACLE_RNG_INJECTED:
-      u = rng->injected[((int64_t)hap * 3 + stream) * p + locus];
+      u = rng->injected[(((int64_t)hap * (rng->n_windows > 1 ? rng->n_windows : 1) + (rng->n_windows > 1 ? w : 0)) * 3 + stream) * p + locus];
       break;
     case KGW_ORACLE_RNG_TAUS88:
       u = kgw_taus88_uniform(&rng->taus);
@@ -36,7 +36,7 @@ double kgw_oracle_next_uniform(kgw_oracle_rng *rng, int hap, int stream, int loc
        * knockoffs.cpp:1222-1226 never reuse a uniform (include/kgw.h) */
       u = kgw_oracle_philox_uniform(rng->seed, (uint32_t)hap, (uint32_t)stream | ((uint32_t)w << 2), (uint32_t)locus);
   }
-  if (rng->record) rng->record[((int64_t)hap * 3 + stream) * p + locus] = u;
+  if (rng->record) rng->record[(((int64_t)hap * (rng->n_windows > 1 ? rng->n_windows : 1) + (rng->n_windows > 1 ? w : 0)) * 3 + stream) * p + locus] = u;
   return u;
 }
 

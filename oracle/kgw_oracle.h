@@ -47,6 +47,9 @@ typedef struct {
   double *record;           /* optional U[N][3][p]: every uniform handed out is also written at
                                its (haplotype, stream, locus) key (lets a sequential taus88 replay
                                be re-fed to the CUDA path as injected uniforms)                     */
+  int32_t n_windows;        /* > 1: `injected` / `record` are U[N][W][3][p], one block per padded window pass
+                               (the passes of knockoffs.cpp:1222-1226 overlap); 0 or 1: U[N][3][p]           */
+  int32_t reserved;
 } kgw_oracle_rng;
 
 /* Unrelated haplotypes (generate_unrelated_worker, knockoffs.cpp:636-700).

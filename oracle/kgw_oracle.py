@@ -39,6 +39,7 @@ class _Rng(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("injected", C.c_void_p), ("taus", _Taus),
         ("seed", C.c_uint64), ("n_draws", C.c_int64), ("record", C.c_void_p),
+        ("n_windows", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -237,7 +238,7 @@ class Result:
 
 
 def run_unrelated(prob: Problem, haps=None, *, mode="philox", seed=None, injected=None,
-                  taus_seed=None, taus_state=None, want_beta=False) -> Result:
+                  taus_seed=None, taus_state=None, want_beta=False, record=None) -> Result:
     """Run the restated unrelated-haplotype sampler for `haps` (default: prob.unrelated).
 
     mode: "philox" (key = seed), "injected" (U[N][3][p], indexed by absolute haplotype id),
@@ -245,22 +246,8 @@ def run_unrelated(prob: Problem, haps=None, *, mode="philox", seed=None, injecte
     L = lib()
     haps = prob.unrelated if haps is None else np.ascontiguousarray(haps, dtype=np.int32)
     n = len(haps)
-    R = _Rng()
-    keep = None
-    if mode == "injected":
-        keep = np.ascontiguousarray(injected, dtype=np.float64)
-        assert keep.shape == (prob.N, 3, prob.p)
-        R.mode, R.injected = RNG_INJECTED, keep.ctypes.data
-    elif mode == "taus88":
-        R.mode = RNG_TAUS88
-        if taus_state is not None:
-            R.taus.v1, R.taus.v2, R.taus.v3 = taus_state
-        else:
-            L.kgw_taus88_seed(C.byref(R.taus), 341 if taus_seed is None else int(taus_seed) & 0xFFFFFFFF)
-    elif mode == "philox":
-        R.mode, R.seed = RNG_PHILOX, int(prob.seed if seed is None else seed)
-    else:
-        raise ValueError(mode)
+    R, keep = make_rng(prob, mode=mode, seed=seed, injected=injected, taus_seed=taus_seed, taus_state=taus_state,
+                       record=record)   # `record`: float64 [N][3][p] or [N][W][3][p], receives every uniform handed out
     z = np.zeros((n, prob.p), dtype=np.int32)
     zk = np.zeros((n, prob.p), dtype=np.int32)
     hk = np.zeros((n, prob.row_bytes), dtype=np.uint8)
@@ -282,11 +269,18 @@ def make_rng(prob: Problem, mode="philox", seed=None, injected=None, taus_seed=N
     R = _Rng()
     keep = None
     if record is not None:
-        assert record.dtype == np.float64 and record.flags.c_contiguous and record.shape == (prob.N, 3, prob.p)
+        assert record.dtype == np.float64 and record.flags.c_contiguous
+        if record.shape == (prob.N, prob.W, 3, prob.p):
+            R.n_windows = prob.W
+        else:
+            assert record.shape == (prob.N, 3, prob.p)
         R.record = record.ctypes.data
     if mode == "injected":
         keep = np.ascontiguousarray(injected, dtype=np.float64)
-        assert keep.shape == (prob.N, 3, prob.p)
+        if keep.shape == (prob.N, prob.W, 3, prob.p):
+            R.n_windows = prob.W
+        else:
+            assert keep.shape == (prob.N, 3, prob.p)
         R.mode, R.injected = RNG_INJECTED, keep.ctypes.data
     elif mode == "taus88":
         R.mode = RNG_TAUS88

@@ -79,3 +79,37 @@ def synthetic_problem(N=64, p=200, K=8, seed=0, mean_group=1.0, rho=1.0, lam=1e-
         win_start, win_end, ref_local = None, None, ref[:, None, :]
     return ko.Problem(H=H, p=p, K=K, ref_local=ref_local, ref_global=ref, b=b, mu=mu, groups=groups,
                       win_start=win_start, win_end=win_end, seed=2020 + seed)
+
+
+def host_threads() -> int:
+    import os
+    return max(1, min(64, (os.cpu_count() or 1)))
+
+
+def oracle_unrelated_rows(prob, haps, chunk=32, mode="philox"):
+    """Packed knockoff rows of `haps` from the CPU oracle, run on every host core (the ctypes call releases the
+    GIL; the keyed generator makes the chunks independent).  Returns uint8 [len(haps)][row_bytes]."""
+    from concurrent.futures import ThreadPoolExecutor
+    haps = np.ascontiguousarray(haps, dtype=np.int32)
+    out = np.zeros((len(haps), prob.row_bytes), dtype=np.uint8)
+
+    def work(c0):
+        out[c0:c0 + chunk] = ko.run_unrelated(prob, haps=haps[c0:c0 + chunk], mode=mode).hk
+
+    with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+        list(ex.map(work, range(0, len(haps), chunk)))
+    return out
+
+
+def oracle_families(prob, families):
+    """[(FamilyResult)] of the CPU oracle for `families` = [(members, [(j_min, j_max, ids), ...])], one host thread
+    per family (keyed generator: no state is carried from one family to the next)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def work(fam):
+        mem, segs = fam
+        rng, _ = ko.make_rng(prob, mode="philox")
+        return ko.run_family(prob, mem, [(s[0], s[1], 0, 0, s[-1]) for s in segs], rng)
+
+    with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+        return list(ex.map(work, families))

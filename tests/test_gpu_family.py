@@ -83,6 +83,12 @@ def test_family_errors():
     with pytest.raises(kg.KgwError):   # a segment listing haplotypes outside its family
         kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, ref_global=prob.ref_global,
                     families=bad)
+    with pytest.raises(kg.KgwError, match="also listed in `unrelated`"):   # the two branches would write the same rows
+        kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, ref_global=prob.ref_global,
+                    families=fam, unrelated=np.arange(prob.N, dtype=np.int32))
+    with pytest.raises(kg.KgwError, match="two families"):
+        kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, ref_global=prob.ref_global,
+                    families=fam + fam[:1], unrelated=np.zeros(0, np.int32))
 
 
 def _synthetic_pairs(n_haps, p, K, pairs, mean_group=1.0, seed=3):

@@ -172,3 +172,19 @@ def test_error_behaviour():
         kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, bad)
     with pytest.raises(kg.KgwError):
         kg.generate(prob.H, prob.p, 300, np.zeros((16, 1, 300), np.int32), prob.b, prob.mu, prob.groups)
+
+
+def test_kernel_reproduces_reference_binary_with_windows():
+    """--windows > 0: the padded passes (knockoffs.cpp:1222-1226) overlap, so the reference consumes several uniforms
+    for one (haplotype, stream, locus).  The oracle replays the reference's taus88 stream on the windows fixture (it
+    reproduces the binary there, tests/test_oracle_vs_reference.py) and records every uniform under (haplotype, window
+    pass, stream, locus); the kernel fed that record must return the reference binary's Z, Zk and Hk."""
+    prob, f = load_golden("toy_chr22_K10_res1_windows")
+    assert prob.W > 1
+    U = np.zeros((prob.N, prob.W, 3, prob.p))
+    res = ko.run_unrelated(prob, mode="taus88", record=U)
+    assert np.array_equal(res.hk, f["Hk"][prob.unrelated]), "the oracle replay is not the reference's output"
+    hk, dbg = _run(prob, injected_u=U, debug_paths=True)
+    assert np.array_equal(dbg.z, f["z_unrelated"].astype(np.int32)), "Z differs from the reference"
+    assert np.array_equal(dbg.zk, f["zk_unrelated"].astype(np.int32)), "Zk differs from the reference"
+    assert np.array_equal(hk[prob.unrelated], f["Hk"][prob.unrelated]), "Hk differs from the reference"
