@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGW_ABI_VERSION 3
+#define KGW_ABI_VERSION 4
 
 /* status codes (negative = error; kgw_last_error() has the text) */
 enum {
@@ -107,6 +107,16 @@ typedef struct kgw_options {
   int32_t reserved;
   int32_t segment_loci;  /* 0 = auto (whole chromosome when the scratch fits); otherwise a multiple of
                             32: loci per segment of the backward/forward sweeps                */
+  /* Several GPUs in one process -- the counterpart of the reference's worker threads inside generate(num_threads)
+   * (knockoffs.cpp:573-634 unrelated slices, :329-431 families).  n_devices > 1: the sorted unrelated list is cut
+   * into contiguous, cost-balanced slices and the IBD families are dealt out whole (largest first, least loaded
+   * device); every device holds H and the references, runs on its own stream from its own host thread and copies
+   * its rows of Hk straight into the caller's hk_out (disjoint rows, no exchange between devices).  The result
+   * does not depend on n_devices (keyed generator).  `devices` lists the CUDA ordinals (NULL = 0 .. n_devices-1);
+   * `device` and `stream` are ignored / must be NULL then.  n_devices 0 or 1: one GPU, `device`. */
+  int32_t n_devices;
+  int32_t reserved2;
+  const int32_t *devices;
 } kgw_options;
 
 /* Optional debug outputs (any pointer may be NULL); rows follow `unrelated` order. */
@@ -126,6 +136,16 @@ typedef struct kgw_debug {
 typedef struct kgw_plan kgw_plan;
 
 int32_t kgw_abi_version(void);
+/* CUDA devices visible to the process (0 when there is none: every compute entry point then fails, there is no
+ * CPU fallback) */
+int32_t kgw_device_count(void);
+/* The split kgw_options.n_devices applies, for callers that shard across processes themselves (one process per
+ * GPU): unrelated_cut[n_devices+1] are positions in the sorted unrelated list (device d takes
+ * [cut[d], cut[d+1])), family_device[f] the device of family f.  A family member counts as 7 unrelated haplotypes
+ * (measured cost of the related branch); families go largest first to the least loaded device, as the reference
+ * deals them to its worker threads in descending size (knockoffs.cpp:364-372).  Host only, no device needed. */
+int32_t kgw_partition_work(int32_t n_unrelated, int32_t n_families, const int32_t *fam_off, int32_t n_devices,
+                           int32_t *unrelated_cut, int32_t *family_device);
 const char *kgw_last_error(void);
 
 /* One-shot drop-in for Knockoffs::generate(): host buffers in, host buffer out.
@@ -146,7 +166,9 @@ int32_t kgw_plan_run_timed(kgw_plan *plan, int32_t iters, float *ms_out);
 int32_t kgw_plan_sync(kgw_plan *plan);
 /* D2H of the packed knockoff rows (same layout as kgw_generate's hk_out). */
 int32_t kgw_plan_download(kgw_plan *plan, uint8_t *hk_out, kgw_debug *dbg);
-/* Device pointer of the packed knockoff matrix [N][row_bytes] (for NCCL gathers etc.). */
+/* Device pointer of the packed knockoff matrix, rows kgw_plan_info().row_stride_bytes apart (for NCCL gathers
+ * etc.).  Multi-device plan: the rows of the other devices are first brought to the first device's matrix (packed
+ * on the source device, one peer copy per device over NVLink, scattered on arrival) and that pointer is returned. */
 void *kgw_plan_device_hk(kgw_plan *plan);
 /* Introspection for bench.py. */
 typedef struct kgw_plan_info_t {

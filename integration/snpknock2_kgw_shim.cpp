@@ -247,8 +247,54 @@ void wrap_generate(Knockoffs *self, int /*num_threads*/) {
   }
   g_call++;
 
-  kgw_options O = {};                                    // device 0; one process per GPU passes its LOCAL_RANK
-  if (kgw_generate(&P, &O, Hkflat.data(), nullptr) != KGW_OK) {
+  // One resident plan per Knockoffs object: main.cpp:159-181 calls set_partition(r) + generate() once per resolution
+  // on the same object, so H, the references and the scratch stay in HBM and only the per-locus knockoff tables
+  // change (kgw_plan_set_groups).  The plan is keyed by a fingerprint of everything except the partition.
+  // Devices: every visible GPU (the counterpart of --n_threads), or KGW_DEVICES="0,2,3".
+  uint64_t fp = 1469598103934665603ull;
+  auto mix = [&](const void *ptr, size_t bytes) {
+    const uint64_t *w = (const uint64_t *)ptr;
+    for (size_t i = 0; i < bytes / 8; i++) { fp ^= w[i]; fp *= 1099511628211ull; }
+    const uint8_t *t = (const uint8_t *)ptr + (bytes / 8) * 8;
+    for (size_t i = 0; i < bytes % 8; i++) { fp ^= t[i]; fp *= 1099511628211ull; }
+  };
+  const int64_t dims[6] = {num_haps, num_snps, K, num_windows, (int64_t)k.seed, (int64_t)F.n_families};
+  mix(dims, sizeof(dims));
+  mix(Hflat.data(), Hflat.size());
+  mix(rl.data(), rl.size() * 4);  mix(rg.data(), rg.size() * 4);
+  mix(b.data(), b.size() * 8);    mix(mu.data(), mu.size() * 8);
+  mix(ws.data(), ws.size() * 4);  mix(we.data(), we.size() * 4);
+  mix(unrel.data(), unrel.size() * 4);
+  mix(fam_mem.data(), fam_mem.size() * 4);  mix(seg_jmin.data(), seg_jmin.size() * 4);  mix(seg_jmax.data(), seg_jmax.size() * 4);
+  mix(seg_ids.data(), seg_ids.size() * 4);
+  static kgw_plan *plan = nullptr;
+  static uint64_t plan_fp = 0;
+  static Knockoffs *plan_owner = nullptr;
+  int rc = KGW_OK;
+  if (plan && plan_owner == self && plan_fp == fp) {
+    rc = kgw_plan_set_groups(plan, grp.data());
+  } else {
+    if (plan) { kgw_plan_destroy(plan); plan = nullptr; }
+    std::vector<int32_t> devs;
+    if (const char *dv = getenv("KGW_DEVICES")) {
+      std::stringstream ss(dv);
+      std::string tok;
+      while (std::getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(std::atoi(tok.c_str()));
+    } else {
+      for (int d = 0; d < kgw_device_count(); d++) devs.push_back(d);
+    }
+    kgw_options O = {};
+    O.n_devices = (int32_t)devs.size();
+    O.devices = devs.data();
+    rc = kgw_plan_create(&P, &O, &plan);
+    plan_fp = fp;
+    plan_owner = self;
+    static bool registered = false;
+    if (!registered) { registered = true; atexit([]() { if (plan) { kgw_plan_destroy(plan); plan = nullptr; } kgw_release_workspace(); }); }
+  }
+  if (rc == KGW_OK) rc = kgw_plan_run(plan);
+  if (rc == KGW_OK) rc = kgw_plan_download(plan, Hkflat.data(), nullptr);
+  if (rc != KGW_OK) {
     std::cerr << "Error: " << kgw_last_error() << std::endl;      // same convention as throw_error_bug (utils.cpp:700)
     exit(-1);
   }

@@ -15,7 +15,7 @@ import numpy as np
 _PKG = Path(__file__).resolve().parent
 _LIB = None
 
-KGW_ABI_VERSION = 3
+KGW_ABI_VERSION = 4
 STREAM_Z, STREAM_ZK, STREAM_HK, STREAM_FAMILY = 0, 1, 2, 3
 
 
@@ -45,7 +45,8 @@ class _Problem(C.Structure):
 
 class _Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("block_loci", C.c_int32), ("lanes_per_hap", C.c_int32),
-                ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p), ("reserved", C.c_int32), ("segment_loci", C.c_int32)]
+                ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p), ("reserved", C.c_int32), ("segment_loci", C.c_int32),
+                ("n_devices", C.c_int32), ("reserved2", C.c_int32), ("devices", C.c_void_p)]
 
 
 class _PlanInfo(C.Structure):
@@ -68,9 +69,13 @@ class Options:
     stream: int = 0   # cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); 0 = plan-owned
     segment_loci: int = 0  # 0 = auto; multiple of 32: loci per segment of the backward/forward sweeps
     skip_sweeps: int = 0  # development timing experiments only: bit s set = skip sweep s+1 (results invalid)
+    devices: tuple = ()   # several GPUs in one process (kgw_options.devices): CUDA ordinals; empty = `device` only
 
     def _c(self) -> _Options:
         o = _Options()
+        if len(self.devices) > 0:
+            self._dev = np.ascontiguousarray(self.devices, dtype=np.int32)   # kept alive by this object
+            o.n_devices, o.devices = len(self._dev), self._dev.ctypes.data
         o.device, o.block_loci, o.lanes_per_hap, o.ctas_per_sm = self.device, self.block_loci, self.lanes_per_hap, self.ctas_per_sm
         o.stream = self.stream or None
         o.reserved = self.skip_sweeps
@@ -79,7 +84,9 @@ class Options:
 
 
 def lib_path() -> Path:
-    return _PKG / "lib" / "libkgw.so"
+    import os
+    alt = os.environ.get("KGW_LIB")   # development: an alternative build of the same library (knockoffgwas_b200/build.py)
+    return Path(alt) if alt else _PKG / "lib" / "libkgw.so"
 
 
 def load_library():
@@ -92,6 +99,9 @@ def load_library():
                                f"(python -m knockoffgwas_b200.build); there is no CPU fallback")
         L = C.CDLL(str(pth))
         L.kgw_abi_version.restype = C.c_int32
+        L.kgw_device_count.restype = C.c_int32
+        L.kgw_partition_work.restype = C.c_int32
+        L.kgw_partition_work.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.kgw_last_error.restype = C.c_char_p
         L.kgw_uniform.restype = C.c_double
         L.kgw_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -135,6 +145,21 @@ def load_library():
             raise KgwError(-1, "libkgw.so ABI version mismatch")
         _LIB = L
     return _LIB
+
+
+def device_count() -> int:
+    return int(load_library().kgw_device_count())
+
+
+def partition_work(n_unrelated: int, family_sizes, n_devices: int):
+    """kgw_partition_work: (cut int32 [n_devices+1] into the sorted unrelated list, device of every family)."""
+    sizes = np.asarray(family_sizes, dtype=np.int64)
+    off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(sizes)]), dtype=np.int32)
+    cut = np.zeros(n_devices + 1, dtype=np.int32)
+    dev = np.zeros(max(1, len(sizes)), dtype=np.int32)
+    _check(load_library().kgw_partition_work(int(n_unrelated), len(sizes), off.ctypes.data, int(n_devices), cut.ctypes.data,
+                                             dev.ctypes.data))
+    return cut, dev[:len(sizes)]
 
 
 def abi_version() -> int:

@@ -48,7 +48,15 @@ def _compile(args):
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """One object per translation unit, compiled in parallel (the kernel instantiations are split by
-    lanes-per-haplotype so that the build takes about as long as its slowest unit), then one link."""
+    lanes-per-haplotype so that the build takes about as long as its slowest unit), then one link.
+    Development: KGW_BUILD_TAG=<tag> builds lib/libkgw_<tag>.so from its own object directory (e.g. with KGW_PHASES=1);
+    KGW_LIB=<path> makes api.load_library() pick it up."""
+    import os
+    global LIB, OBJDIR
+    tag = os.environ.get("KGW_BUILD_TAG")
+    if tag:
+        LIB = LIBDIR / f"libkgw_{tag}.so"
+        OBJDIR = PKG / f"build_{tag}"
     if not force and not needs_build():
         return LIB
     from concurrent.futures import ThreadPoolExecutor

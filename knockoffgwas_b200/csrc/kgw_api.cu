@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
+#include <numeric>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -526,6 +528,10 @@ struct kgw_plan {
   std::vector<int32_t> haps;
   FamilyState *fam = nullptr;      // related branch (null when the problem has no families)
   std::vector<int32_t> out_rows;   // rows of Hk written by this plan: unrelated + family members
+  // multi-device plan (kgw_options.n_devices > 1): this object only holds one ordinary plan per device, each with
+  // its shard of the work list (every device keeps the whole H and the references; Hk rows are disjoint)
+  std::vector<kgw_plan *> subs;
+  bool primary_has_all = false;    // the first device's Hk already holds the other devices' rows
 
   std::vector<std::pair<void *, size_t>> owned;   // pooled device buffers of this plan
   template <typename T>
@@ -545,6 +551,10 @@ struct kgw_plan {
   }
 
   ~kgw_plan() {
+    if (!subs.empty()) {
+      for (kgw_plan *s : subs) delete s;
+      return;
+    }
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
 #ifdef KGW_PHASES
@@ -870,6 +880,185 @@ int launch(kgw_plan *pl) {
 
 }  // namespace
 
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Several GPUs in one process (kgw_options.n_devices > 1).  The reference fans Knockoffs::generate out over
+// worker threads inside the call (generate_unrelated, knockoffs.cpp:573-634: contiguous slices of the sorted
+// unrelated list; generate_related, :329-431: families dealt out in descending size); here the same split goes
+// over devices.  Haplotypes are independent given H, the references and the tables (:654-692) and families are
+// independent of each other (:440-445), so there is no exchange between devices: every device holds H and the
+// references, runs an ordinary plan on its share and copies its rows of Hk straight into the caller's buffer
+// (disjoint rows).  A family costs KGW_FAMILY_COST unrelated haplotypes per member (measured).
+constexpr double KGW_FAMILY_COST = 7.0;
+
+struct SubProblem {
+  kgw_problem prob;
+  kgw_families fam;
+  std::vector<int32_t> fam_off, fam_members, seg_off, seg_jmin, seg_jmax, seg_ids_off, seg_ids;
+};
+
+// the split itself (also exported as kgw_partition_work): cut[nd+1] into the sorted unrelated list, fam_dev[nf]
+void partition_work(int nu, int nf, const int32_t *fam_off, int nd, std::vector<int> &cut, std::vector<int> &fam_dev) {
+  std::vector<double> load(nd, 0.0);
+  fam_dev.assign(nf, 0);
+  std::vector<int> order(nf);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fam_off[a + 1] - fam_off[a] > fam_off[b + 1] - fam_off[b]; });
+  for (int f : order) {   // largest family first, to the least loaded device
+    const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+    fam_dev[f] = d;
+    load[d] += KGW_FAMILY_COST * (fam_off[f + 1] - fam_off[f]);
+  }
+  const double total = std::accumulate(load.begin(), load.end(), 0.0) + nu;
+  std::vector<double> want(nd);
+  double wsum = 0.0;
+  for (int d = 0; d < nd; d++) { want[d] = std::max(0.0, total / nd - load[d]); wsum += want[d]; }
+  cut.assign(nd + 1, 0);
+  double acc = 0.0;
+  for (int d = 0; d < nd; d++) {
+    acc += wsum > 0.0 ? want[d] * (nu / wsum) : (double)nu / nd;
+    cut[d + 1] = std::max(cut[d], std::min(nu, (int)std::llround(acc)));
+  }
+  cut[nd] = nu;
+}
+
+void split_work(const kgw_problem *prob, int nd, std::vector<SubProblem> &out) {
+  out.assign(nd, SubProblem());
+  const kgw_families *fi = (prob->families && prob->families->n_families > 0) ? prob->families : nullptr;
+  const int nf = fi ? fi->n_families : 0;
+  std::vector<int> cut, fam_dev;
+  partition_work(prob->n_unrelated, nf, fi ? fi->fam_off : nullptr, nd, cut, fam_dev);
+  std::vector<std::vector<int>> fam_of(nd);
+  for (int f = 0; f < nf; f++) fam_of[fam_dev[f]].push_back(f);   // the caller's family order inside a device
+  for (int d = 0; d < nd; d++) {
+    SubProblem &S = out[d];
+    S.prob = *prob;
+    S.prob.unrelated = prob->unrelated ? prob->unrelated + cut[d] : nullptr;
+    S.prob.n_unrelated = cut[d + 1] - cut[d];
+    S.prob.families = nullptr;
+    if (fam_of[d].empty()) continue;
+    S.fam_off.push_back(0); S.seg_off.push_back(0); S.seg_ids_off.push_back(0);
+    for (int f : fam_of[d]) {
+      S.fam_members.insert(S.fam_members.end(), fi->fam_members + fi->fam_off[f], fi->fam_members + fi->fam_off[f + 1]);
+      S.fam_off.push_back((int32_t)S.fam_members.size());
+      for (int sg = fi->seg_off[f]; sg < fi->seg_off[f + 1]; sg++) {
+        S.seg_jmin.push_back(fi->seg_jmin[sg]);
+        S.seg_jmax.push_back(fi->seg_jmax[sg]);
+        S.seg_ids.insert(S.seg_ids.end(), fi->seg_ids + fi->seg_ids_off[sg], fi->seg_ids + fi->seg_ids_off[sg + 1]);
+        S.seg_ids_off.push_back((int32_t)S.seg_ids.size());
+      }
+      S.seg_off.push_back((int32_t)S.seg_jmin.size());
+    }
+    S.fam = kgw_families{};
+    S.fam.n_families = (int32_t)fam_of[d].size();
+    S.fam.fam_off = S.fam_off.data(); S.fam.fam_members = S.fam_members.data(); S.fam.seg_off = S.seg_off.data();
+    S.fam.seg_jmin = S.seg_jmin.data(); S.fam.seg_jmax = S.seg_jmax.data();
+    S.fam.seg_ids_off = S.seg_ids_off.data(); S.fam.seg_ids = S.seg_ids.data();
+  }
+  for (int d = 0; d < nd; d++) if (!out[d].fam_off.empty()) out[d].prob.families = &out[d].fam;   // (after the vector stopped moving)
+}
+
+// fn(d) on one host thread per device; the first failure's code and message are returned in the caller's thread
+template <typename F>
+int for_each_device(int nd, F fn) {
+  std::vector<int> rc(nd, KGW_OK);
+  std::vector<std::string> msg(nd);
+  std::vector<std::thread> th;
+  for (int d = 0; d < nd; d++)
+    th.emplace_back([&, d]() {
+      rc[d] = fn(d);
+      if (rc[d] != KGW_OK) msg[d] = g_err;   // thread-local text of this worker
+    });
+  for (auto &t : th) t.join();
+  for (int d = 0; d < nd; d++)
+    if (rc[d] != KGW_OK) return fail(rc[d], "device shard " + std::to_string(d) + ": " + msg[d]);
+  return KGW_OK;
+}
+
+int create_multi(const kgw_problem *prob, const kgw_options &o, kgw_plan **plan_out) {
+  const int nd = o.n_devices;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(KGW_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (o.stream) return fail(KGW_ERR_INVALID, "a caller stream belongs to one device: leave `stream` NULL with n_devices > 1");
+  if (prob->injected_u == nullptr && prob->n_unrelated > 0 && !prob->unrelated) return fail(KGW_ERR_INVALID, "bad unrelated list");
+  std::vector<int> devs(nd);
+  for (int d = 0; d < nd; d++) {
+    devs[d] = o.devices ? o.devices[d] : d;
+    if (devs[d] < 0 || devs[d] >= ndev) return fail(KGW_ERR_INVALID, "bad device ordinal in `devices`");
+  }
+  std::vector<SubProblem> sp;
+  split_work(prob, nd, sp);
+  kgw_plan *pl = new kgw_plan();
+  pl->subs.assign(nd, nullptr);
+  pl->N = prob->N; pl->p = prob->p; pl->K = prob->K; pl->W = prob->W; pl->row_bytes = prob->row_bytes;
+  pl->n_haps = prob->n_unrelated;
+  int rc = for_each_device(nd, [&](int d) {
+    kgw_options od = o;
+    od.device = devs[d];
+    od.n_devices = 0;
+    od.devices = nullptr;
+    return (int)kgw_plan_create(&sp[d].prob, &od, &pl->subs[d]);
+  });
+  if (rc != KGW_OK) { delete pl; return rc; }
+  pl->device = devs[0];
+  *plan_out = pl;
+  return KGW_OK;
+}
+
+// Hk rows of the other devices -> the first device's matrix (what a .bed writer or an NCCL sender on that device
+// needs): rows packed on the source device, one peer copy over NVLink by the copy engines, scattered on arrival
+__global__ void rows_scatter_pitched(const uint8_t *__restrict__ src, size_t row_len, const int32_t *__restrict__ rows,
+                                     uint8_t *__restrict__ dst, size_t dst_pitch, size_t n_rows) {
+  const size_t total = n_rows * row_len;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / row_len, c = i - r * row_len;
+    dst[(size_t)rows[r] * dst_pitch + c] = src[i];
+  }
+}
+
+int gather_to_primary(kgw_plan *pl) {
+  if (pl->primary_has_all) return KGW_OK;
+  kgw_plan *p0 = pl->subs[0];
+  const size_t rb = (size_t)(pl->p + 7) / 8;
+  for (size_t d = 1; d < pl->subs.size(); d++) {
+    kgw_plan *ps = pl->subs[d];
+    const size_t n = ps->out_rows.size();
+    if (n == 0) continue;
+    KGW_CUDA(cudaSetDevice(ps->device));
+    if (n * rb > ps->stage_bytes) {
+      ps->release(ps->dstage);
+      KGW_CUDA(ps->alloc(&ps->dstage, n * rb));
+      ps->stage_bytes = n * rb;
+    }
+    if (!ps->dout_rows) {
+      KGW_CUDA(ps->alloc(&ps->dout_rows, sizeof(int32_t) * n));
+      KGW_CUDA(cudaMemcpyAsync(ps->dout_rows, ps->out_rows.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ps->stream));
+    }
+    rows_from_pitched<<<ps->sm_count * 8, 256, 0, ps->stream>>>((const uint8_t *)ps->dHk, (size_t)ps->stride_w * 4, ps->dout_rows, 0,
+                                                                 ps->dstage, rb, n);
+    KGW_CUDA(cudaGetLastError());
+    KGW_CUDA(cudaStreamSynchronize(ps->stream));
+    KGW_CUDA(cudaSetDevice(p0->device));
+    uint8_t *tmp = nullptr;
+    int32_t *trows = nullptr;
+    KGW_CUDA(kgw_malloc(&tmp, n * rb));
+    KGW_CUDA(kgw_malloc(&trows, sizeof(int32_t) * n));
+    KGW_CUDA(cudaMemcpyPeerAsync(tmp, p0->device, ps->dstage, ps->device, n * rb, p0->stream));
+    KGW_CUDA(cudaMemcpyAsync(trows, ps->out_rows.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, p0->stream));
+    rows_scatter_pitched<<<p0->sm_count * 8, 256, 0, p0->stream>>>(tmp, rb, trows, (uint8_t *)p0->dHk, (size_t)p0->stride_w * 4, n);
+    KGW_CUDA(cudaGetLastError());
+    KGW_CUDA(cudaStreamSynchronize(p0->stream));
+    cudaFree(tmp);
+    cudaFree(trows);
+  }
+  pl->primary_has_all = true;
+  return KGW_OK;
+}
+
+}  // namespace
+
 // shared with the other translation units (kgw_common.h)
 cudaError_t kgw_dev_malloc_(void **out, size_t bytes) {
   cudaError_t e = cudaMalloc(out, bytes);
@@ -885,6 +1074,7 @@ cudaError_t kgw_dev_malloc_(void **out, size_t bytes) {
 }
 int kgw_fail_(int code, const std::string &msg) { return fail(code, msg); }
 void *kgw_plan_device_h_(kgw_plan *pl, int *N, int *p, int *stride_w, int *device, void **stream) {
+  if (!pl->subs.empty()) pl = pl->subs[0];   // every device holds the whole H
   *N = pl->N; *p = pl->p; *stride_w = pl->stride_w; *device = pl->device; *stream = (void *)pl->stream;
   return (void *)pl->dHw;
 }
@@ -892,6 +1082,21 @@ void *kgw_plan_device_h_(kgw_plan *pl, int *N, int *p, int *stride_w, int *devic
 extern "C" {
 
 int32_t kgw_abi_version(void) { return KGW_ABI_VERSION; }
+int32_t kgw_partition_work(int32_t n_unrelated, int32_t n_families, const int32_t *fam_off, int32_t n_devices,
+                           int32_t *unrelated_cut, int32_t *family_device) {
+  if (n_unrelated < 0 || n_families < 0 || n_devices < 1 || !unrelated_cut || (n_families > 0 && (!fam_off || !family_device)))
+    return fail(KGW_ERR_INVALID, "bad argument");
+  std::vector<int> cut, fam_dev;
+  partition_work(n_unrelated, n_families, fam_off, n_devices, cut, fam_dev);
+  for (int d = 0; d <= n_devices; d++) unrelated_cut[d] = cut[d];
+  for (int f = 0; f < n_families; f++) family_device[f] = fam_dev[f];
+  return KGW_OK;
+}
+int32_t kgw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 const char *kgw_last_error(void) { return g_err.c_str(); }
 
 double kgw_uniform(uint64_t seed, uint32_t hap, uint32_t stream, uint32_t locus) {
@@ -915,6 +1120,9 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   if (K > 256) return fail(KGW_ERR_UNSUPPORTED, "K > 256 is not built (latent states are stored as bytes)");
   kgw_options o{};
   if (opt) o = *opt;
+  if (o.n_devices < 0 || o.n_devices > 64) return fail(KGW_ERR_INVALID, "bad n_devices");
+  if (o.n_devices > 1) return create_multi(prob, o, plan_out);
+  if (o.n_devices == 1 && o.devices) o.device = o.devices[0];
   if (o.lanes_per_hap != 0 && o.lanes_per_hap != 1 && o.lanes_per_hap != 2 && o.lanes_per_hap != 4 && o.lanes_per_hap != 8)
     return fail(KGW_ERR_INVALID, "lanes_per_hap must be 0 (auto), 1, 2, 4 or 8");
   if (o.block_loci != 0 && o.block_loci != 2 && o.block_loci != 4 && o.block_loci != 8)
@@ -1157,18 +1365,56 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
 
 int32_t kgw_plan_set_groups(kgw_plan *pl, const int32_t *groups) {
   if (!pl || !groups) return fail(KGW_ERR_INVALID, "null argument");
+  if (!pl->subs.empty()) {
+    pl->primary_has_all = false;
+    return for_each_device((int)pl->subs.size(), [&](int d) { return (int)kgw_plan_set_groups(pl->subs[d], groups); });
+  }
   KGW_CUDA(cudaSetDevice(pl->device));
   return upload_partition(pl, groups, false);
 }
 
 int32_t kgw_plan_run(kgw_plan *pl) {
   if (!pl) return fail(KGW_ERR_INVALID, "null plan");
+  if (!pl->subs.empty()) {   // launches are asynchronous: one after the other from this thread
+    pl->primary_has_all = false;
+    for (kgw_plan *s : pl->subs) {
+      int rc = kgw_plan_run(s);
+      if (rc != KGW_OK) return rc;
+    }
+    return KGW_OK;
+  }
   KGW_CUDA(cudaSetDevice(pl->device));
   return launch(pl);
 }
 
 int32_t kgw_plan_run_timed(kgw_plan *pl, int32_t iters, float *ms_out) {
   if (!pl || iters <= 0 || !ms_out) return fail(KGW_ERR_INVALID, "bad argument");
+  if (!pl->subs.empty()) {   // every device times its own stream; the job takes as long as the slowest device
+    pl->primary_has_all = false;
+    for (kgw_plan *s : pl->subs) {
+      KGW_CUDA(cudaSetDevice(s->device));
+      KGW_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    for (kgw_plan *s : pl->subs) {
+      KGW_CUDA(cudaSetDevice(s->device));
+      KGW_CUDA(cudaEventRecord(s->ev0, s->stream));
+      for (int i = 0; i < iters; i++) {
+        int rc = launch(s);
+        if (rc != KGW_OK) return rc;
+      }
+      KGW_CUDA(cudaEventRecord(s->ev1, s->stream));
+    }
+    float worst = 0.f;
+    for (kgw_plan *s : pl->subs) {
+      KGW_CUDA(cudaSetDevice(s->device));
+      KGW_CUDA(cudaEventSynchronize(s->ev1));
+      float ms = 0.f;
+      KGW_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+      worst = std::max(worst, ms);
+    }
+    *ms_out = worst / iters;
+    return KGW_OK;
+  }
   KGW_CUDA(cudaSetDevice(pl->device));
   KGW_CUDA(cudaStreamSynchronize(pl->stream));
   KGW_CUDA(cudaEventRecord(pl->ev0, pl->stream));
@@ -1186,15 +1432,43 @@ int32_t kgw_plan_run_timed(kgw_plan *pl, int32_t iters, float *ms_out) {
 
 int32_t kgw_plan_sync(kgw_plan *pl) {
   if (!pl) return fail(KGW_ERR_INVALID, "null plan");
+  if (!pl->subs.empty()) {
+    for (kgw_plan *s : pl->subs) {
+      int rc = kgw_plan_sync(s);
+      if (rc != KGW_OK) return rc;
+    }
+    return KGW_OK;
+  }
   KGW_CUDA(cudaSetDevice(pl->device));
   KGW_CUDA(cudaStreamSynchronize(pl->stream));
   return KGW_OK;
 }
 
-void *kgw_plan_device_hk(kgw_plan *pl) { return pl ? (void *)pl->dHk : nullptr; }
+void *kgw_plan_device_hk(kgw_plan *pl) {
+  if (!pl) return nullptr;
+  if (!pl->subs.empty()) {   // rows of the other devices are brought to the first device's matrix first
+    for (kgw_plan *s : pl->subs) if (kgw_plan_sync(s) != KGW_OK) return nullptr;
+    if (gather_to_primary(pl) != KGW_OK) return nullptr;
+    return (void *)pl->subs[0]->dHk;
+  }
+  return (void *)pl->dHk;
+}
 
 int32_t kgw_plan_info(kgw_plan *pl, kgw_plan_info_t *out) {
   if (!pl || !out) return fail(KGW_ERR_INVALID, "null argument");
+  if (!pl->subs.empty()) {   // shape of the first device's plan; launches and scratch summed over the devices
+    int rc = kgw_plan_info(pl->subs[0], out);
+    if (rc != KGW_OK) return rc;
+    for (size_t d = 1; d < pl->subs.size(); d++) {
+      kgw_plan_info_t t;
+      rc = kgw_plan_info(pl->subs[d], &t);
+      if (rc != KGW_OK) return rc;
+      out->launches_per_run += t.launches_per_run;
+      out->scratch_bytes += t.scratch_bytes;
+    }
+    out->reserved = (int32_t)pl->subs.size();
+    return KGW_OK;
+  }
   out->launches_per_run = (pl->n_haps > 0 ? 1 : 0) + ((pl->fam && pl->fam->n_families > 0) ? 1 : 0);
   out->grid = pl->grid;
   out->block = pl->threads;
@@ -1263,6 +1537,12 @@ static int run_debug(kgw_plan *pl, kgw_debug *dbg) {
 
 int32_t kgw_plan_download(kgw_plan *pl, uint8_t *hk_out, kgw_debug *dbg) {
   if (!pl) return fail(KGW_ERR_INVALID, "null plan");
+  if (!pl->subs.empty()) {
+    if (dbg && (dbg->z || dbg->zk || dbg->beta_ckpt || dbg->fam_z || dbg->fam_zk))
+      return fail(KGW_ERR_UNSUPPORTED, "debug outputs are per device: ask for them with n_devices <= 1");
+    // every device copies its own rows into the caller's matrix (disjoint rows), one host thread per device
+    return for_each_device((int)pl->subs.size(), [&](int d) { return (int)kgw_plan_download(pl->subs[d], hk_out, nullptr); });
+  }
   KGW_CUDA(cudaSetDevice(pl->device));
   if (dbg && (dbg->z || dbg->zk || dbg->beta_ckpt || dbg->fam_z || dbg->fam_zk)) {
     int rc = run_debug(pl, dbg);

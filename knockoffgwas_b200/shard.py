@@ -19,23 +19,12 @@ def partition_work(unrelated, families, world_size: int, family_cost: float = FA
     Returns a list of (unrelated ids of the rank [contiguous slice], family indices of the rank).
     Families go to the least loaded rank in descending size (the reference's own order,
     knockoffs.cpp:364-372, made cost-aware); the unrelated list is then cut so that total costs even out."""
+    from . import api
     unrelated = np.asarray(unrelated, dtype=np.int32)
-    fam_sizes = np.array([len(f) for f in families], dtype=np.int64)
-    fam_of_rank = [[] for _ in range(world_size)]
-    load = np.zeros(world_size)
-    for f in np.argsort(-fam_sizes, kind="stable"):
-        r = int(np.argmin(load))
-        fam_of_rank[r].append(int(f))
-        load[r] += family_cost * fam_sizes[f]
-    total = load.sum() + len(unrelated)
-    target = total / world_size
-    want = np.maximum(0.0, target - load)
-    if want.sum() > 0:
-        want = want * (len(unrelated) / want.sum())
-    cuts = np.rint(np.concatenate([[0.0], np.cumsum(want)])).astype(np.int64)
-    cuts[-1] = len(unrelated)
-    cuts = np.maximum.accumulate(np.clip(cuts, 0, len(unrelated)))
-    return [(unrelated[cuts[r]:cuts[r + 1]], sorted(fam_of_rank[r])) for r in range(world_size)]
+    if family_cost != FAMILY_COST:
+        raise ValueError("the family cost is a constant of the library (kgw_partition_work)")
+    cut, dev = api.partition_work(len(unrelated), [len(f) for f in families], world_size)
+    return [(unrelated[cut[r]:cut[r + 1]], [f for f in range(len(families)) if dev[f] == r]) for r in range(world_size)]
 
 
 def rows_of(unrelated_r, families, fam_idx_r):

@@ -36,15 +36,19 @@ def _lay_out_inputs(d: Path) -> dict:
     return {k: str(d / f"{k}.txt") for k in ("keep", "extract", "map", "part", "ibd")} | {"bgen": str(d / "example_chr22")}
 
 
-def _run(tmp_path: Path, dump: bool, shim_io: bool = True):
+def _run(tmp_path: Path, dump: bool, shim_io: bool = True, resolution="2", devices=None):
     (tmp_path / "in").mkdir(exist_ok=True)
     (tmp_path / "out").mkdir(exist_ok=True)
     fl = _lay_out_inputs(tmp_path / "in")
     args = [str(BINARY), "--bgen", fl["bgen"], "--keep", fl["keep"], "--extract", fl["extract"], "--map", fl["map"],
             "--part", fl["part"], "--ibd", fl["ibd"], "--K", "10", "--cluster_size_min", "1000", "--cluster_size_max", "10000",
             "--n_threads", "1", "--seed", "2020", "--hmm-rho", "1", "--hmm-lambda", "1e-3", "--windows", "0",
-            "--resolution", "2", "--compute-references", "--generate-knockoffs", "--out", str(tmp_path / "out" / "ko")]
+            "--compute-references", "--generate-knockoffs", "--out", str(tmp_path / "out" / "ko")]
+    if resolution is not None:
+        args += ["--resolution", resolution]
     env = dict(os.environ)
+    if devices is not None:
+        env["KGW_DEVICES"] = devices
     env["KGW_SHIM_IO"] = "1" if shim_io else "0"          # 1: BgenReader::read and plink::write_binary also go through libkgw
     if dump:
         env["KGW_SHIM_DUMP"] = str(tmp_path / "dump")
@@ -111,3 +115,28 @@ def test_dropin_binary_writes_the_librarys_knockoffs(tmp_path):
                         ref_global=prob.ref_global, seed=prob.seed, families=fams)
     want = kg.bed_encode(prob.H, hk, prob.p)              # == the reference's writeBED on (H, Hk), tests/test_bed.py
     assert np.array_equal(bed[3:].reshape(want.shape), want), "the .bed of the drop-in binary is not (H, this library's Hk)"
+
+
+@pytest.mark.gpu
+@needs_binary
+def test_dropin_binary_all_resolutions_one_plan_sharded(tmp_path):
+    """The reference's loop over every partition of the --part file (main.cpp:159-181) through the drop-in: the shim keeps
+    ONE plan for the Knockoffs object and only replaces the partition between resolutions (kgw_plan_set_groups), and it
+    shards the work list over the devices of KGW_DEVICES (here the same GPU twice).  Every `_res<r>.bed` whose inputs
+    exist as a fixture must be (H, this library's Hk for that partition)."""
+    kg = pytest.importorskip("knockoffgwas_b200")
+    r = _run(tmp_path, dump=False, shim_io=True, resolution=None, devices="0,0")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    checked = 0
+    for res in (0, 2, 4, 6):
+        prob, _ = load_golden(f"toy_chr22_K10_res{res}")
+        beds = sorted((tmp_path / "out").glob(f"*_res{res}.bed"))
+        assert len(beds) == 1, [b.name for b in (tmp_path / "out").iterdir()]
+        bed = np.fromfile(beds[0], dtype=np.uint8)
+        fams = [(m, [(s[0], s[1], s[4]) for s in segs]) for m, segs in prob.fam_clusters]
+        hk, _ = kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, unrelated=prob.unrelated,
+                            ref_global=prob.ref_global, seed=prob.seed, families=fams)
+        want = kg.bed_encode(prob.H, hk, prob.p)
+        assert np.array_equal(bed[3:].reshape(want.shape), want), f"resolution {res}"
+        checked += 1
+    assert checked == 4
