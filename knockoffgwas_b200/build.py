@@ -37,6 +37,8 @@ def _compile(args):
     fast = ["-DKGW_FAST"] if os.environ.get("KGW_FAST") == "1" else []   # development: benchmark variants only
     if os.environ.get("KGW_PHASES") == "1":
         fast.append("-DKGW_PHASES")
+    if os.environ.get("KGW_CFLAGS"):
+        fast += os.environ["KGW_CFLAGS"].split()
     if os.environ.get("KGW_FAM_MINB"):
         fast.append("-DKGW_FAM_MINB=" + os.environ["KGW_FAM_MINB"])
     if os.environ.get("KGW_M_OVERRIDE") and src.stem.endswith("_L" + os.environ.get("KGW_M_OVERRIDE_L", "4")):

@@ -510,7 +510,7 @@ struct kgw_plan {
   uint32_t *dHw = nullptr, *dHk = nullptr;
   int32_t *dref = nullptr, *dhaps = nullptr;
   KgwLocusHMM *dhmm = nullptr;
-  KgwLocusKO *dko = nullptr;
+  KgwLocusKO *dko = nullptr, *dko_base = nullptr;   // dko = dko_base + 32 rows of padding
   KgwEmit *demit = nullptr;
   KgwPass *dpass = nullptr;
   double *dckpt = nullptr, *dinj = nullptr, *dse = nullptr, *dcs = nullptr, *dsegck = nullptr;
@@ -829,16 +829,24 @@ int upload_partition(kgw_plan *pl, const int32_t *groups, bool hmm_too) {
                         pl->win_end.data(), T, hmm_too);
   if (rc != KGW_OK) return rc;
   if (hmm_too) {
-    KGW_CUDA(pl->alloc(&pl->dhmm, sizeof(KgwLocusHMM) * pl->p));
-    KGW_CUDA(pl->alloc(&pl->demit, sizeof(KgwEmit) * pl->p));
+    // the kernel stages whole 32-locus words of the per-locus tables with bulk copies: padded to whole words
+    const size_t p32 = ((size_t)pl->p + 31) / 32 * 32;
+    KGW_CUDA(pl->alloc(&pl->dhmm, sizeof(KgwLocusHMM) * p32));
+    KGW_CUDA(pl->alloc(&pl->demit, sizeof(KgwEmit) * p32));
+    KGW_CUDA(cudaMemsetAsync(pl->dhmm, 0, sizeof(KgwLocusHMM) * p32, pl->stream));
+    KGW_CUDA(cudaMemsetAsync(pl->demit, 0, sizeof(KgwEmit) * p32, pl->stream));
     KGW_CUDA(cudaMemcpyAsync(pl->dhmm, T.hmm.data(), sizeof(KgwLocusHMM) * pl->p, cudaMemcpyHostToDevice, pl->stream));
     KGW_CUDA(cudaMemcpyAsync(pl->demit, T.emit.data(), sizeof(KgwEmit) * pl->p, cudaMemcpyHostToDevice, pl->stream));
     KGW_CUDA(pl->alloc(&pl->dpass, sizeof(KgwPass) * pl->W));
   }
   if (T.ko.size() > pl->ko_capacity) {
+    // 32 rows of padding on either side: the kernel copies whole words of a pass's rows, and a pass may start or end
+    // inside a word (the padding rows are never used)
     KGW_CUDA(cudaStreamSynchronize(pl->stream));
-    pl->release(pl->dko);
-    KGW_CUDA(pl->alloc(&pl->dko, sizeof(KgwLocusKO) * T.ko.size()));
+    pl->release(pl->dko_base);
+    KGW_CUDA(pl->alloc(&pl->dko_base, sizeof(KgwLocusKO) * (T.ko.size() + 64)));
+    KGW_CUDA(cudaMemsetAsync(pl->dko_base, 0, sizeof(KgwLocusKO) * (T.ko.size() + 64), pl->stream));
+    pl->dko = pl->dko_base + 32;
     pl->ko_capacity = T.ko.size();
   }
   KGW_CUDA(cudaMemcpyAsync(pl->dko, T.ko.data(), sizeof(KgwLocusKO) * T.ko.size(), cudaMemcpyHostToDevice, pl->stream));
@@ -1201,15 +1209,15 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
     // warps per SM (the 1 KB per-CTA shared-memory reservation is paid once) and are used when the single-warp
     // grid cannot hold every haplotype batch at once.
     const int n_tasks = (pl->n_haps + G - 1) / G;
-    auto shape = [&](kgw_kernel_fn fn, int *wpc_out, int *occ_out) -> cudaError_t {
-      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(var->smem_warp * var->max_wpc));
+    auto shape = [&](kgw_kernel_fn fn, size_t smem_warp, int *wpc_out, int *occ_out) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_warp * var->max_wpc));
       if (e != cudaSuccess) return e;
       int wpc = 1, occ = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, var->smem_warp);
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smem_warp);
       if (e != cudaSuccess) return e;
       if (occ * dp.multiProcessorCount < n_tasks && var->max_wpc > 1) {
         int occ2 = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, 32 * var->max_wpc, var->smem_warp * var->max_wpc);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, 32 * var->max_wpc, smem_warp * var->max_wpc);
         if (e != cudaSuccess) return e;
         if (occ2 * var->max_wpc > occ) { wpc = var->max_wpc; occ = occ2; }
       }
@@ -1217,24 +1225,25 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
       return cudaSuccess;
     };
     int wpc = 1, occ = 0, wpc_w = 1, occ_w = 0;
-    KGW_CUDA_PL(shape(var->fn, &wpc, &occ));
+    KGW_CUDA_PL(shape(var->fn, var->smem_warp, &wpc, &occ));
     if (occ <= 0) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
     pl->fn = var->fn;
+    size_t smem_warp = var->smem_warp;
     if (var->fn_wide != var->fn) {
-      KGW_CUDA_PL(shape(var->fn_wide, &wpc_w, &occ_w));
+      KGW_CUDA_PL(shape(var->fn_wide, var->smem_warp_wide, &wpc_w, &occ_w));
       const char *force = getenv("KGW_FORCE_WIDE");   // development: "0" / "1"
       if (occ_w > 0) {
         const double slots_d = (double)occ * wpc * dp.multiProcessorCount, slots_w = (double)occ_w * wpc_w * dp.multiProcessorCount;
         const double cost_d = std::ceil(n_tasks / slots_d) * 1.0, cost_w = std::ceil(n_tasks / slots_w) * 0.65;
         const bool wide = force ? (force[0] == '1') : (cost_w < cost_d);
-        if (wide) { pl->fn = var->fn_wide; wpc = wpc_w; occ = occ_w; }
+        if (wide) { pl->fn = var->fn_wide; wpc = wpc_w; occ = occ_w; smem_warp = var->smem_warp_wide; }
       }
     }
     if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
     const int grid = std::max(1, std::min(occ * dp.multiProcessorCount, (n_tasks + wpc - 1) / wpc));
     slots = (size_t)grid * wpc;
     pl->threads = 32 * wpc;
-    pl->smem = var->smem_warp * wpc;
+    pl->smem = smem_warp * wpc;
     pl->var = var; pl->B = B; pl->G = G; pl->n_tasks = n_tasks; pl->grid = grid;
     pl->nblk = (int)((p + B - 1) / B);
   }

@@ -226,6 +226,45 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier.  Every staged tile of this kernel is
+// one contiguous, 16-byte aligned run of the slot scratch or of a per-locus table, so one elected lane moves it with
+// ONE instruction and the other lanes keep their issue slots for arithmetic; each buffer has its own barrier, so a
+// wait covers exactly the bytes it needs (cp.async.wait_all also waited for the far-ahead prefetches).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tKGW_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra KGW_DONE;\n\t"
+               "bra KGW_WAIT;\n\tKGW_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Warp barrier that every lane passes only once the shared-memory loads feeding `x` have RETURNED.  A bulk copy that
+// refills a buffer is issued by lane 0 through the async proxy and does not queue behind the other lanes' LDS in the
+// load/store unit: when that unit is backed up (every warp of the SM leaves its gather at the same time) a refill from
+// L2 can land before loads issued ahead of it have read the old contents.  __syncwarp() alone does not wait for
+// outstanding loads; the vote needs `x` and therefore does.
+__device__ __forceinline__ void syncwarp_after_loads(unsigned x) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %0, 0x80000001;\n\tvote.sync.any.pred p, p, 0xffffffff;\n\t}" ::"r"(x) : "memory");
+}
+
+// generic-proxy writes (global scratch, shared rows) before async-proxy accesses of the same bytes.  The bulk copies
+// are issued by lane 0 and read what every lane of the warp stored a moment ago (sweep 1 starts at the word the gather
+// wrote last): each lane first makes its own stores visible device-wide, then orders them against the async proxy; the
+// caller follows with __syncwarp() before lane 0 issues.
+__device__ __forceinline__ void fence_async_proxy() {
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+  asm volatile("fence.proxy.async;" ::: "memory");   // ... and the issuing lane once more after it has synchronised with the writers
+}
+
 // streaming stores / loads of the scratch (written once, read once: keep it out of L1)
 __device__ __forceinline__ void st_cg(double2 *p, double x, double y) {
   asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
@@ -247,7 +286,7 @@ __device__ __forceinline__ double ld_cg(const double *p) {
   return v;
 }
 
-template <int L, int S, int B>
+template <int L, int S, int B, int D>
 struct Cfg {
   static constexpr int G = 32 / L;
   static constexpr int KP = L * S;
@@ -260,16 +299,18 @@ struct Cfg {
   static constexpr int ROW = L * SPR * G;       // doubles per message row
   static constexpr int TILE = L * SPW * G;      // 32-bit words per match-word tile
   // per-warp shared memory: two message rows (sweep 2: staged top rows of two blocks; sweep 3: the
-  // reciprocal row and the two latent-path tiles), one match-word tile, the staging buffers of sweep 2
-  // (sweep 3 lays the reciprocal row, its two latent-path tiles and the 32 knockoff-table rows of the
-  // current word over the same bytes)
+  // reciprocal row, the two latent-path tiles and the 32 knockoff-table rows of the current word; sweeps 0/1: the
+  // table rows of two words), one match-word tile, a ring of D loci of partial sums (sweep 2; sweep 3 keeps the
+  // emission rows of the word there when it holds 4 KB), totals + table rows of two blocks, 16 mbarriers
   static constexpr size_t s3_bytes = (size_t)ROW * 8 + 4 * 32 * G + 32 * sizeof(KgwLocusKO);
   static constexpr size_t rows_bytes = (size_t)2 * ROW * 8 > s3_bytes ? (size_t)2 * ROW * 8 : s3_bytes;
   static constexpr size_t tiles_bytes = (size_t)TILE * 4;
-  // sweep-2 staging: partial sums of one locus (+ injected uniforms), totals and table rows of one block
-  static constexpr size_t stage_bytes = (size_t)128 * 8 + (size_t)G * 8 + (size_t)B * G * 8 + (size_t)B * 16;
-  __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + tiles_bytes + stage_bytes; }
+  static constexpr size_t ring_bytes = (size_t)D * 1024;
+  static constexpr size_t blk_bytes = (size_t)2 * ((size_t)B * G * 8 + (size_t)B * 16);
+  static constexpr size_t bar_bytes = 128;
+  __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + tiles_bytes + ring_bytes + blk_bytes + bar_bytes; }
 };
+enum { BAR_S1 = 0, BAR_TILE2 = 1, BAR_BLK = 2, BAR_CS = 4, BAR_W3 = 12, BAR_ZT = 13, BAR_EM = 14, KGW_NBARS = 16 };
 
 // uniform of (hap, stream, locus j): Philox block cached per 4 loci
 struct UniformSrc {
@@ -308,9 +349,10 @@ __device__ __forceinline__ HmmConsts hmm_consts(const KgwLocusHMM h, double alph
 }
 
 // PAD = false asserts K == L*S (no padded states: the per-state guards compile away)
-template <int L, int S, int B, bool PAD, int MINB>
+template <int L, int S, int B, bool PAD, int MINB, int D>
 __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __grid_constant__ KgwParams P) {
-  using C = Cfg<L, S, B>;
+  using C = Cfg<L, S, B, D>;
+  static_assert(D >= 2 && D <= 8, "ring depth");
   constexpr int G = C::G;
   constexpr int SPR = C::SPR, SPW = C::SPW, NQ = C::NQ, NP = C::NP, CS = C::CS, NC = C::NC, ROW = C::ROW, TILE = C::TILE;
   constexpr int NCT = L * NC;  // chunks per haplotype
@@ -330,15 +372,29 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
   unsigned char *smem_raw = smem_all + (size_t)(threadIdx.x >> 5) * C::warp_bytes();
   double *rowbuf = reinterpret_cast<double *>(smem_raw);                         // [2][ROW]
   uint32_t *mwt = reinterpret_cast<uint32_t *>(smem_raw + C::rows_bytes);        // [TILE]
-  double *loc_cs = reinterpret_cast<double *>(smem_raw + C::rows_bytes + C::tiles_bytes);   // [2][32][2]   (sweep 2)
-  double *loc_u = loc_cs + 128;                                                   // [G]
-  double *blk_se = loc_u + G;                                                     // [B][G]
-  KgwLocusHMM *blk_h = reinterpret_cast<KgwLocusHMM *>(blk_se + B * G);           // [B]
+  double *ring = reinterpret_cast<double *>(smem_raw + C::rows_bytes + C::tiles_bytes);     // [D][2][32][2] (sweep 2)
+  double *blk_se = reinterpret_cast<double *>(smem_raw + C::rows_bytes + C::tiles_bytes + C::ring_bytes);   // [2][B][G]
+  KgwLocusHMM *blk_h = reinterpret_cast<KgwLocusHMM *>(blk_se + 2 * B * G);       // [2][B]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + C::rows_bytes + C::tiles_bytes + C::ring_bytes + C::blk_bytes);
   uint8_t *ztile3 = reinterpret_cast<uint8_t *>(rowbuf + ROW);                   // [2][32][G] (sweep 3, after row 0)
   uint8_t *zktile3 = ztile3 + 2 * 32 * G;                                        // [2][32][G]
   KgwLocusKO *kot = reinterpret_cast<KgwLocusKO *>(zktile3 + 2 * 32 * G);        // [32]       (sweep 3)
-  uint32_t *z1slot = reinterpret_cast<uint32_t *>(loc_cs);                       // [32]       (sweep 3)
-  double *uslot = loc_cs + 16;                                                   // [32]       (sweep 3, test mode)
+  uint32_t *z1slot = reinterpret_cast<uint32_t *>(blk_se);                       // [32]       (sweep 3)
+  static_assert(C::blk_bytes >= 128, "z1 slots");
+  // one mbarrier per staged buffer (one arrival: the elected lane's expect_tx); `ph` holds the phase parity every
+  // lane expects next on each of them.  Every copy that is issued is waited for exactly once.
+  unsigned ph = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < KGW_NBARS; i++) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_proxy();
+  __syncwarp();
+  auto wait_bar = [&](int i) {
+    mbar_wait(bars + i, (ph >> i) & 1u);
+    ph ^= 1u << i;
+  };
 
   uint32_t *mw = P.mwbuf + (size_t)slot * P.mw_stride;   // [stride_w][TILE]
   double *ck = P.ckpt + (size_t)slot * P.ckpt_stride;    // [seg_loci/B][ROW]
@@ -412,13 +468,9 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
       __syncwarp();
 
       KGW_PH(0);   // gather
-      // asynchronous copy of this lane's quads of match-word tile `w` into buffer `buf`
-      auto prefetch_tile = [&](int w) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(mw + (size_t)w * TILE) + mwoff;
-        uint4 *dst = reinterpret_cast<uint4 *>(mwt) + mwoff;
-#pragma unroll
-        for (int q = 0; q < NQ; q++) cp_async16(dst + q * G, src + q * G);
-      };
+      // match-word tile of word `w` -> shared memory: one bulk copy on barrier `bar` (elected lane; the caller adds
+      // the tile's bytes to that barrier's expect_tx)
+      auto bulk_tile = [&](int w, int bar) { bulk_g2s(mwt, mw + (size_t)w * TILE, TILE * 4, bars + bar); };
       // this lane's match words of the staged tile -> registers
       auto load_mw = [&](uint32_t (&mwr)[S]) {
         const uint4 *src = reinterpret_cast<const uint4 *>(mwt) + mwoff;
@@ -430,6 +482,13 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
           if (4 * q + 2 < S) mwr[(4 * q + 2 < S) ? 4 * q + 2 : 0] = t.z;
           if (4 * q + 3 < S) mwr[(4 * q + 3 < S) ? 4 * q + 3 : 0] = t.w;
         }
+      };
+      // a value that depends on every 16-byte load of load_mw
+      auto mw_any = [&](const uint32_t (&mwr)[S]) {
+        unsigned x = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) x |= mwr[4 * q];
+        return x;
       };
       // message row registers -> global row (this lane's pairs; padded slots are written as zero)
       auto store_row = [&](const double (&beta)[S], double *row) {
@@ -445,23 +504,30 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
         uint32_t mwr[S];
         int wi = hi_m >> 5;
         const int wl = lo_m >> 5;
-        // table rows of the 32 loci of word w -> hmt[w & 1] (the row buffers are idle during sweeps 0 and 1)
+        // match-word tile and table rows of the 32 loci of word w -> shared memory (table rows: hmt[w & 1]; the row
+        // buffers are idle during sweeps 0 and 1; the table is padded to whole words)
         KgwLocusHMM *hmt = reinterpret_cast<KgwLocusHMM *>(rowbuf);   // [2][32]
-        auto stage_hmm = [&](int w) { cp_async16(hmt + (w & 1) * 32 + lane, P.hmm + min(max((w << 5) + lane, lo_m), hi_m)); };
+        auto stage_word = [&](int w) {
+          if (lane == 0) {
+            mbar_expect_tx(bars + BAR_S1, TILE * 4 + 32 * (unsigned)sizeof(KgwLocusHMM));
+            bulk_tile(w, BAR_S1);
+            bulk_g2s(hmt + (w & 1) * 32, P.hmm + (w << 5), 32 * (unsigned)sizeof(KgwLocusHMM), bars + BAR_S1);
+          }
+        };
+        fence_async_proxy();   // the scratch and the row buffers were last written through the generic proxy
         __syncwarp();
-        prefetch_tile(wi);
-        stage_hmm(wi);
-        cp_async_wait_all();
-        __syncwarp();
+        stage_word(wi);
+        wait_bar(BAR_S1);
         load_mw(mwr);
-        if (wi > wl) { prefetch_tile(wi - 1); stage_hmm(wi - 1); }   // this lane's quads are in registers: the tile buffer is free
+        syncwarp_after_loads(mw_any(mwr));   // every lane HOLDS its quads in registers: the tile buffer is free
+        if (wi > wl) stage_word(wi - 1);
         for (int m = hi_m; m >= lo_m; m--) {
           if ((m >> 5) != wi) {
             wi = m >> 5;
-            cp_async_wait_all();
-            __syncwarp();
+            wait_bar(BAR_S1);
             load_mw(mwr);
-            if (wi > wl) { prefetch_tile(wi - 1); stage_hmm(wi - 1); }
+            syncwarp_after_loads(mw_any(mwr));
+            if (wi > wl) stage_word(wi - 1);
           }
           const HmmConsts h = hmm_consts(hmt[(wi & 1) * 32 + (m & 31)], P.alpha);
           const uint32_t bm = 1u << (m & 31);
@@ -574,52 +640,56 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
         // so that no scoreboard wait of the draw's arithmetic is tied to a load in flight.
         if (!(P.skip_sweeps & 2)) {
           int wi = slo >> 5;
-          // top row of block n (in segment-relative block index) -> row buffer (n & 1), this lane's pairs
-          auto prefetch_row = [&](int n) {
-            const double2 *src = reinterpret_cast<const double2 *>(ck + (size_t)(n - seg0 / B) * ROW) + rowoff;
-            double2 *dst = reinterpret_cast<double2 *>(rowbuf + (size_t)(n & 1) * ROW) + rowoff;
-#pragma unroll
-            for (int q = 0; q < NP; q++) cp_async16(dst + q * G, src + q * G);
-          };
-          // table rows and locus totals of the loci nb0 .. nb0+B-1 (clamped into the segment) -> blk_*
-          auto stage_block = [&](int nb0) {
-            if (lane < B) cp_async16(blk_h + lane, P.hmm + min(max(nb0 + lane, slo), shi - 1));
-            if (lig == 0) {
-#pragma unroll
-              for (int mm = 0; mm < B; mm++) {
-                const int m = min(max(nb0 + mm, slo), shi - 1);
-                cp_async8(blk_se + mm * G + g, seb + (size_t)(m - seg0) * G + g);
-              }
+          // row, locus totals and table rows of block n -> buffers n & 1, one barrier per buffer pair
+          auto stage_block = [&](int n) {
+            if (lane == 0) {
+              unsigned long long *bar = bars + BAR_BLK + (n & 1);
+              mbar_expect_tx(bar, ROW * 8 + B * G * 8 + B * (unsigned)sizeof(KgwLocusHMM));
+              bulk_g2s(rowbuf + (size_t)(n & 1) * ROW, ck + (size_t)(n - seg0 / B) * ROW, ROW * 8, bar);
+              bulk_g2s(blk_se + (n & 1) * B * G, seb + (size_t)(n * B - seg0) * G, B * G * 8, bar);
+              bulk_g2s(blk_h + (n & 1) * B, P.hmm + n * B, B * (unsigned)sizeof(KgwLocusHMM), bar);
             }
           };
-          // partial sums (and the injected uniform, test mode) of locus j -> loc_*
+          // partial sums of locus j -> ring slot j % D
           auto stage_locus = [&](int j) {
-            const double2 *d = reinterpret_cast<const double2 *>(csb + (size_t)(j - seg0) * 128);
-            double2 *t = reinterpret_cast<double2 *>(loc_cs);
-            cp_async16(t + lane, d + lane);
-            cp_async16(t + 32 + lane, d + 32 + lane);
-            if (usz.inj != nullptr && lig == 0) cp_async8(loc_u + g, usz.inj + j);
+            if (lane == 0) {
+              unsigned long long *bar = bars + BAR_CS + (j % D);
+              mbar_expect_tx(bar, 1024);
+              bulk_g2s(ring + (j % D) * 128, csb + (size_t)(j - seg0) * 128, 1024, bar);
+            }
           };
+          auto stage_tile2 = [&](int w) {
+            if (lane == 0) {
+              mbar_expect_tx(bars + BAR_TILE2, TILE * 4);
+              bulk_tile(w, BAR_TILE2);
+            }
+          };
+          fence_async_proxy();   // sweep 1 wrote the scratch through the generic proxy
           __syncwarp();
-          prefetch_tile(wi);
-          prefetch_row(slo / B);
-          stage_block((slo / B) * B);
-          stage_locus(slo);
+          stage_tile2(wi);
+          bool tile_pending = true;
+          stage_block(slo / B);
+#pragma unroll
+          for (int d = 0; d < D; d++)
+            if (slo + d < shi) stage_locus(slo + d);
           uint32_t hw = __ldg(P.Hw + hoff + wi);
           const int n_last = (shi - 1) / B;
           for (int n = slo / B; n <= n_last; n++) {
             const int nb = n * B;
             const int lo = max(nb, slo);
             const int top = min(nb + B, shi) - 1;
+            __syncwarp();   // every lane is done with block n - 1 (its row buffer is refilled below) and with the tile
             if ((lo >> 5) != wi) {
-              // next 32-locus word (the barrier keeps the old match-word tile intact until every lane is done)
               wi = lo >> 5;
               hw = __ldg(P.Hw + hoff + wi);
-              __syncwarp();
-              prefetch_tile(wi);
+              stage_tile2(wi);
+              tile_pending = true;
             }
-            cp_async_wait_all();
-            __syncwarp();
+            if (n < n_last) stage_block(n + 1);
+            wait_bar(BAR_BLK + (n & 1));
+            if (tile_pending) { wait_bar(BAR_TILE2); tile_pending = false; }
+            const double *bse = blk_se + (n & 1) * B * G;
+            const KgwLocusHMM *bh = blk_h + (n & 1) * B;
             // constants of the recurrence beta_{m-1}(k) = (b_m E_m(k)) beta_m(k) + a_m Se_m for the loci of the
             // block (loci above `top` get the identity step); the staged table rows and totals stay in shared
             // memory until the block's last locus
@@ -628,9 +698,9 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
             for (int mm = 1; mm < B; mm++) {
               const int m = nb + mm;
               if (m >= lo && m <= top) {
-                const HmmConsts h = hmm_consts(blk_h[mm], P.alpha);
+                const HmmConsts h = hmm_consts(bh[mm], P.alpha);
                 tbo[mm] = h.b * h.omm; tbm[mm] = h.b * h.mu;
-                tcm[mm] = h.a * blk_se[mm * G + g];
+                tcm[mm] = h.a * bse[mm * G + g];
               } else {
                 tbo[mm] = 1.0; tbm[mm] = 1.0; tcm[mm] = 0.0;
               }
@@ -643,29 +713,21 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
             for (int jj = 0; jj < B; jj++) {
               const int j = nb + jj;
               if (j < lo || j > top) continue;
-              if (j > lo) {
-                cp_async_wait_all();
-                __syncwarp();
-              }
+              wait_bar(BAR_CS + (j % D));
               // partial sums of this locus: the L lanes of the haplotype, four chunks each
               double csv[NCT];
+              {
+                const double2 *slot = reinterpret_cast<const double2 *>(ring + (j % D) * 128);
 #pragma unroll
-              for (int lg = 0; lg < L; lg++) {
-                const double2 t0 = reinterpret_cast<const double2 *>(loc_cs)[lg * G + g];
-                const double2 t1 = reinterpret_cast<const double2 *>(loc_cs)[32 + lg * G + g];
-                csv[lg * NC + 0] = t0.x; csv[lg * NC + 1] = t0.y; csv[lg * NC + 2] = t1.x; csv[lg * NC + 3] = t1.y;
+                for (int lg = 0; lg < L; lg++) {
+                  const double2 t0 = slot[lg * G + g];
+                  const double2 t1 = slot[32 + lg * G + g];
+                  csv[lg * NC + 0] = t0.x; csv[lg * NC + 1] = t0.y; csv[lg * NC + 2] = t1.x; csv[lg * NC + 3] = t1.y;
+                }
               }
-              const double u = (usz.inj != nullptr) ? loc_u[g] : usz.get(j);
-              const HmmConsts hj = hmm_consts(blk_h[jj], P.alpha);
-              const double sej = blk_se[jj * G + g];
-              __syncwarp();   // the staging buffers of the locus have been read by every lane
-              if (j + 1 < shi) stage_locus(j + 1);
-              if (j + 6 < shi) prefetch_l2(csb + (size_t)(j + 6 - seg0) * 128 + lane * 4);   // HBM -> L2, six loci ahead
-              if (j == lo && n < n_last) {
-                prefetch_row(n + 1);
-                if (lig == 0 && lane < B) prefetch_l2(seb + (size_t)(min(nb + B + lane, shi - 1) - seg0) * G);
-              }
-              if (j == top && n < n_last) stage_block(nb + B);   // every lane is past its reads of this block's rows
+              const double u = usz.get(j);
+              const HmmConsts hj = hmm_consts(bh[jj], P.alpha);
+              const double sej = bse[jj * G + g];
               KGW_PH(2);   // sweep 2: waits + staging reads
               const int bit = bit0 + jj;
               const bool hbit = (hw >> bit) & 1u;
@@ -706,6 +768,9 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               const int cz = lgz * NC + (zprev - lgz * S) / CS;
               const int csel = (CA > cz) ? CB : CA;
               const int cst = min(csel, NCT - 1);
+              // `cst` depends on every partial sum of the slot: all lanes have their values, refill it D loci ahead
+              syncwarp_after_loads((unsigned)cst);
+              if (j + D < shi) stage_locus(j + D);
               double Tb = 0.0;
 #pragma unroll
               for (int c = 0; c < NCT - 1; c++) add_if_lt(Tb, c, cst, csv[c]);
@@ -774,13 +839,18 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
         int z0 = 0, z0k = 0, zkprev = 0;
         if (js > 0) { z0 = zb[(size_t)(js - 1) * G + g]; z0k = zkb[(size_t)(js - 1) * G + g]; }
         const KgwLocusKO *ko_tab = P.ko + ps.ko_off - js;
-        // As in sweep 2, everything the per-locus loop reads from global memory arrives by cp.async:
-        // the latent-path tiles of the next word, the knockoff-table rows of the word, the byte z1 of the
-        // next group (one group ahead) and, in test mode, the injected uniform of the next locus.
+        // As in sweep 2, everything the per-locus loop reads from global memory is staged in shared memory: bulk
+        // copies per word (latent-path tiles a word ahead; match-word tile, knockoff-table rows and emission rows of
+        // the word -- the tables are padded to whole words on either side), and the byte z1 of the next group by a
+        // per-lane cp.async one group ahead.
+        constexpr bool EMIT_IN_RING = C::ring_bytes >= 32 * sizeof(KgwEmit);
+        static_assert(sizeof(KgwEmit) == sizeof(KgwLocusKO), "the two per-locus tables may share a shared-memory tile");
+        KgwEmit *emt = EMIT_IN_RING ? reinterpret_cast<KgwEmit *>(ring) : reinterpret_cast<KgwEmit *>(kot);   // [32], indexed by bit
         auto stage_ztiles = [&](int w) {
-          for (int i = lane; i < 2 * G; i += 32) {
-            cp_async16(ztile3 + (size_t)(w & 1) * 32 * G + 16 * i, zb + (size_t)(w << 5) * G + 16 * i);
-            cp_async16(zktile3 + (size_t)(w & 1) * 32 * G + 16 * i, zkb + (size_t)(w << 5) * G + 16 * i);
+          if (lane == 0) {
+            mbar_expect_tx(bars + BAR_ZT, 2 * 32 * G);
+            bulk_g2s(ztile3 + (size_t)(w & 1) * 32 * G, zb + (size_t)(w << 5) * G, 32 * G, bars + BAR_ZT);
+            bulk_g2s(zktile3 + (size_t)(w & 1) * 32 * G, zkb + (size_t)(w << 5) * G, 32 * G, bars + BAR_ZT);
           }
         };
         int z1 = 0, z1_byte = 0;
@@ -789,26 +859,26 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
           z1_byte = (int)(off & 3);
           cp_async4(z1slot + lane, zb + (off & ~(size_t)3));
         };
+        fence_async_proxy();   // sweep 2 wrote the latent path, earlier sweeps the row buffers, through the generic proxy
         __syncwarp();
         {
           const int zi = ko_tab[js].z1_idx;
           if (zi >= 0) stage_z1(zi);
         }
-        if (us.inj != nullptr) cp_async8(uslot + lane, us.inj + js);
         stage_ztiles(wlo);
         for (int wi = wlo; wi <= whi; wi++) {
           const int lo = max(wi << 5, js), hi = min((wi << 5) + 32, je);
           __syncwarp();   // the previous word is finished in every lane (tile reads of its allele draws)
-          prefetch_tile(wi);   // needed by the allele draws at the end of this word
-          {
-            // knockoff-table rows of this word's loci (8 x 16 bytes each)
-            const uint4 *src = reinterpret_cast<const uint4 *>(ko_tab + lo);
-            uint4 *dst = reinterpret_cast<uint4 *>(kot + (lo & 31));
-            const int n16 = (hi - lo) * (int)(sizeof(KgwLocusKO) / 16);
-            for (int i = lane; i < n16; i += 32) cp_async16(dst + i, src + i);
+          if (lane == 0) {
+            // match words (for the allele draws at the end of the word), knockoff-table rows and, when the ring can
+            // hold them, the emission rows of the word's 32 loci
+            mbar_expect_tx(bars + BAR_W3, TILE * 4 + 32 * (unsigned)sizeof(KgwLocusKO) + (EMIT_IN_RING ? 32 * (unsigned)sizeof(KgwEmit) : 0u));
+            bulk_tile(wi, BAR_W3);
+            bulk_g2s(kot, ko_tab + (wi << 5), 32 * (unsigned)sizeof(KgwLocusKO), bars + BAR_W3);
+            if (EMIT_IN_RING) bulk_g2s(emt, P.emit + (wi << 5), 32 * (unsigned)sizeof(KgwEmit), bars + BAR_W3);
           }
-          cp_async_wait_all();
-          __syncwarp();
+          wait_bar(BAR_ZT);
+          wait_bar(BAR_W3);
           if (wi < whi) stage_ztiles(wi + 1);
           uint8_t *zt = ztile3 + (size_t)(wi & 1) * 32 * G, *zkt = zktile3 + (size_t)(wi & 1) * 32 * G;
           for (int j = lo; j < hi; j++) {
@@ -816,14 +886,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
             const int bit = j & 31;
             const int zj = zt[bit * G + g];
             const bool lastg = k.flags & KGW_KO_LASTGRP;
-            double u;
-            if (us.inj != nullptr) {
-              cp_async_wait_all();
-              u = uslot[lane];
-              if (j + 1 < je) cp_async8(uslot + lane, us.inj + j + 1);
-            } else {
-              u = us.get(j);
-            }
+            const double u = us.get(j);
             int zk;
             if (k.flags & KGW_KO_FIRST) {
               cp_async_wait_all();   // z1 of this group was requested at the first locus of the previous one
@@ -984,7 +1047,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
             if (k.flags & KGW_KO_LASTINGRP) { z0 = zj; z0k = zk; }
             if (lig == 0) zkt[bit * G + g] = (uint8_t)zk;
           }
-          cp_async_wait_all();
+          fence_async_proxy();   // this word's zk tile was written through the generic proxy; a bulk copy refills it two words on
           __syncwarp();
           // flush the zk tile, then knockoff alleles of the core loci of this word (:1469-1502)
           for (int i = lane; i < 8 * G; i += 32)
@@ -993,17 +1056,14 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
           const uint32_t *tile = mwt;
           unsigned bits = 0u, mask = 0u;
           const int elo = max(lo, ps.cs), ehi = min(hi, ps.ce);
-          // emission-table rows of the word's core loci -> over the knockoff-table rows (done for this word)
-          static_assert(sizeof(KgwEmit) == sizeof(KgwLocusKO), "the two per-locus tables share a shared-memory tile");
-          KgwEmit *emt = reinterpret_cast<KgwEmit *>(kot);   // [32], indexed by bit
-          if (ehi > elo) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(P.emit + elo);
-            uint4 *dst = reinterpret_cast<uint4 *>(emt + (elo & 31));
-            const int n16 = (ehi - elo) * (int)(sizeof(KgwEmit) / 16);
-            for (int i = lane; i < n16; i += 32) cp_async16(dst + i, src + i);
+          if (!EMIT_IN_RING) {
+            // emission-table rows of the word -> over the knockoff-table rows (done for this word)
+            if (lane == 0) {
+              mbar_expect_tx(bars + BAR_EM, 32 * (unsigned)sizeof(KgwEmit));
+              bulk_g2s(emt, P.emit + (wi << 5), 32 * (unsigned)sizeof(KgwEmit), bars + BAR_EM);
+            }
+            wait_bar(BAR_EM);
           }
-          cp_async_wait_all();
-          __syncwarp();
           // a lane draws the alleles of whole groups of four loci (one Philox block each)
           for (int q4 = lig; q4 < 8; q4 += L) {
 #pragma unroll
@@ -1031,6 +1091,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
             else *dst = (*dst & ~mask) | bits;
           }
         }
+        cp_async_wait_all();
       }
       __syncwarp();
     }  // passes
