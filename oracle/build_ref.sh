@@ -96,4 +96,10 @@ g++ -O2 -std=c++11 -w $(echo "$APPFLAGS" | sed 's/-Ofast//') -I"$REF/src" \
     -c "$SHIM/wrap_probe.cpp" -o "$OBJ/wrap_probe.o"
 g++ -Ofast -std=c++11 -o "$OUT/snpknock2_probe" "$OBJ"/src/*.o "$OBJ/wrap_probe.o" \
     -Wl,--wrap="$GEN_SYM" -Wl,--wrap="$WC_SYM" $LIBS
+# the binary bench.py times: the same reference objects with the std::chrono timer around Knockoffs::generate and
+# nothing else in the way (weighted_choice is the reference's own symbol here)
+g++ -O2 -std=c++11 -w $(echo "$APPFLAGS" | sed 's/-Ofast//') -I"$REF/src" \
+    -DKGW_GEN_SYM="$GEN_SYM" -DKGW_TIMER_ONLY \
+    -c "$SHIM/wrap_probe.cpp" -o "$OBJ/wrap_timer.o"
+g++ -Ofast -std=c++11 -o "$OUT/snpknock2_timer" "$OBJ"/src/*.o "$OBJ/wrap_timer.o" -Wl,--wrap="$GEN_SYM" $LIBS
 echo "build_ref.sh: done -> $OUT"

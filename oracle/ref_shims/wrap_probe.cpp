@@ -45,7 +45,7 @@
 #ifndef KGW_GEN_SYM
 #error "KGW_GEN_SYM (mangled Knockoffs::generate) must be defined by the build script"
 #endif
-#ifndef KGW_WC_SYM
+#if !defined(KGW_WC_SYM) && !defined(KGW_TIMER_ONLY)
 #error "KGW_WC_SYM (mangled weighted_choice) must be defined by the build script"
 #endif
 #define KGW_STR2(x) #x
@@ -53,8 +53,10 @@
 
 void real_generate(Knockoffs *self, int num_threads) asm("__real_" KGW_STR(KGW_GEN_SYM));
 void wrap_generate(Knockoffs *self, int num_threads) asm("__wrap_" KGW_STR(KGW_GEN_SYM));
+#ifndef KGW_TIMER_ONLY   // snpknock2_timer (the binary bench.py times) wraps Knockoffs::generate only
 int real_weighted_choice(const std::vector<double> &w, boost::random::taus88 &rng) asm("__real_" KGW_STR(KGW_WC_SYM));
 int wrap_weighted_choice(const std::vector<double> &w, boost::random::taus88 &rng) asm("__wrap_" KGW_STR(KGW_WC_SYM));
+#endif
 
 namespace {
 
@@ -82,6 +84,7 @@ void dump_rows(const std::string &path, const std::vector<chaplotype> &rows, int
 
 }  // namespace
 
+#ifndef KGW_TIMER_ONLY
 int wrap_weighted_choice(const std::vector<double> &w, boost::random::taus88 &rng) {
   const int r = real_weighted_choice(w, rng);
   if (g_trace) {
@@ -90,6 +93,7 @@ int wrap_weighted_choice(const std::vector<double> &w, boost::random::taus88 &rn
   }
   return r;
 }
+#endif
 
 void wrap_generate(Knockoffs *self, int num_threads) {
   const char *dir_env = getenv("KGW_PROBE_DIR");

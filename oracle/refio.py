@@ -20,6 +20,11 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 PROBE = HERE / "_ref" / "snpknock2_probe"
+TIMER = HERE / "_ref" / "snpknock2_timer"   # timer around Knockoffs::generate only (no weighted_choice wrapper): the timed arm
+
+
+def timed_binary() -> Path:
+    return TIMER if TIMER.exists() and os.access(TIMER, os.X_OK) else PROBE
 
 
 def available() -> bool:
@@ -102,7 +107,7 @@ def run_reference_all_resolutions(files: dict, out_dir: Path, *, rho: float, lam
     the --part file (main.cpp:159-181).  Returns the generate() wall times, one per call."""
     out_dir = Path(out_dir)
     out_dir.mkdir(parents=True, exist_ok=True)
-    args = [str(PROBE), "--haps", files["prefix"], "--map", files["map"], "--part", files["part"],
+    args = [str(timed_binary()), "--haps", files["prefix"], "--map", files["map"], "--part", files["part"],
             "--ref", files["ref"], "--lref", files["lref"], "--hmm-rho", repr(float(rho)),
             "--hmm-lambda", repr(float(lam)), "--windows", "0", "--seed", str(seed),
             "--n_threads", str(n_threads), "--generate-knockoffs", "--out", str(out_dir / "ko"),

@@ -22,7 +22,7 @@ def _cuda() -> bool:
 @pytest.mark.skipif(not (REPO / "oracle" / "_ref" / "snpknock2_probe").exists(), reason="oracle/_ref not built")
 def test_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--cpu-threads", "2", "--snps", "600"], capture_output=True, text=True, timeout=600, cwd=str(REPO))
+                        "--cpu-threads", "2", "--snps", "600", "--haps", "600"], capture_output=True, text=True, timeout=600, cwd=str(REPO))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
