@@ -70,7 +70,10 @@ typedef struct kgw_problem {
   int32_t abi_version;        /* = KGW_ABI_VERSION                                                   */
   int32_t N;                  /* Haplotypes::num_haps                       haplotypes.h:38          */
   int32_t p;                  /* Haplotypes::num_snps                       haplotypes.h:37          */
-  int32_t K;                  /* Knockoffs::K                               knockoffs.h:138          */
+  int32_t K;                  /* Knockoffs::K                               knockoffs.h:138
+                                 Bound of this build: K <= 256 (latent states are stored as bytes), K <= 255
+                                 when `families` is given; larger K returns KGW_ERR_UNSUPPORTED.  The
+                                 reference's default is 100 (arguments.cpp), module_2_knockoffs.sh uses 50.  */
   int32_t W;                  /* metadata.windows.num_windows               windows.h:17             */
   int32_t reserved0;
   int64_t row_bytes;          /* bytes per packed row of H / Hk, >= ceil(p/8)                        */

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <numeric>
 #include <cstdio>
 #include <cstring>
@@ -321,15 +322,25 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // Related branch (generate_related, knockoffs.cpp:329-571): host pre-processing of the families into
 // the flat structures of kgw_family.cuh.
-struct FamilyState {
-  int n_families = 0, n_max = 0, members_total = 0, SF = 1, grid = 0, threads = 128, rtot = 1;
+// One of the two compiled classes of the family kernel (kgw_family.cuh): its families, launch shape and slot scratch
+struct FamClass {
+  int count = 0, n_max = 0, rtot = 1, grid = 0, threads = 128;
   size_t smem = 0;
+  std::vector<int32_t> list;                      // descriptor indices of the class
+  int32_t *dlist = nullptr, *dwork = nullptr, *dflg = nullptr;
+  double *dmsg = nullptr, *dmrc = nullptr, *dpmg = nullptr;   // (pooled with the plan's buffers)
+  uint8_t *dpat = nullptr, *dbytes = nullptr;
+};
+
+struct FamilyState {
+  int n_families = 0, members_total = 0, SF = 1;
+  FamClass cls[2];                                // [0] small families (registers / shared memory), [1] everything else
   std::vector<int32_t> h_members;                 // concatenated, family order
   std::vector<int32_t> h_fam_off, h_seg_off, h_seg_jmin, h_seg_jmax, h_seg_ids_off, h_seg_ids;
   // device
   KgwFamDesc *dfams = nullptr;
   int32_t *dmembers = nullptr, *divstart = nullptr, *dgroups = nullptr, *dgfirst = nullptr, *dglast = nullptr, *dstatus = nullptr;
-  int32_t *dwork = nullptr;
+  int32_t *divlist = nullptr;
   KgwFamRange *dranges = nullptr;
   long long *dphase = nullptr;
   cudaStream_t side = nullptr;             // the related branch runs beside the unrelated one when both fit on the SMs
@@ -340,8 +351,7 @@ struct FamilyState {
   KgwFamOp *dops = nullptr;
   KgwFamLocus *dloc = nullptr;
   KgwLocusKO *dko = nullptr;
-  double *demtab = nullptr, *dmsg = nullptr, *dmrc = nullptr;
-  uint8_t *dpat = nullptr, *dbytes = nullptr;
+  double *demtab = nullptr;
   int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
   std::vector<KgwFamDesc> fams;                   // op_off / n_ops are refreshed by set_groups
   KgwFamParams P{};
@@ -360,7 +370,8 @@ struct FamilyState {
       cudaFree(dphase);
     }
 #endif
-    cudaFree(dwork); cudaFree(dranges);
+    cudaFree(divlist); cudaFree(dranges);
+    for (FamClass &c : cls) { cudaFree(c.dlist); cudaFree(c.dwork); }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
@@ -368,22 +379,27 @@ struct FamilyState {
 };
 
 // std::set_difference on the inputs as they are (family_bp.cpp:365-378)
-int fam_set_difference(const std::vector<int> &A, const std::vector<int> &B, int32_t *out) {
+int fam_set_difference(const std::vector<int> &A, const std::vector<int> &B, std::vector<int32_t> &out) {
   size_t ia = 0, ib = 0;
   int no = 0;
   while (ia < A.size() && ib < B.size()) {
-    if (A[ia] < B[ib]) out[no++] = A[ia++];
+    if (A[ia] < B[ib]) { out.push_back(A[ia++]); no++; }
     else if (B[ib] < A[ia]) ib++;
     else { ia++; ib++; }
   }
-  while (ia < A.size()) out[no++] = A[ia++];
+  while (ia < A.size()) { out.push_back(A[ia++]); no++; }
   return no;
 }
 
 // neighbour intervals of every member of family f (family_bp.cpp:41-61 run-length encoded along j)
-int fam_build_intervals(const FamilyState &F, int f, int p, std::vector<std::vector<KgwFamInterval>> &out) {
+// (lists of any length: the intervals point into `ivlist`; *max_nn = the largest neighbour count of the family)
+int fam_build_intervals(const FamilyState &F, int f, int p, std::vector<std::vector<KgwFamInterval>> &out,
+                        std::vector<int32_t> &ivlist, int *max_nn) {
   const int m0 = F.h_fam_off[f], n = F.h_fam_off[f + 1] - m0;
-  auto local = [&](int id) { for (int i = 0; i < n; i++) if (F.h_members[m0 + i] == id) return i; return -1; };
+  std::unordered_map<int, int> local_of;
+  for (int i = n - 1; i >= 0; i--) local_of[F.h_members[m0 + i]] = i;
+  auto local = [&](int id) { auto it = local_of.find(id); return it == local_of.end() ? -1 : it->second; };
+  *max_nn = 0;
   const int s0 = F.h_seg_off[f], s1 = F.h_seg_off[f + 1];
   out.assign(n, {});
   for (int i = 0; i < n; i++) {
@@ -416,14 +432,16 @@ int fam_build_intervals(const FamilyState &F, int f, int p, std::vector<std::vec
       else { lists.push_back(nb); ranges.push_back({j0, j1}); }
     }
     for (size_t c = 0; c < lists.size(); c++) {
-      if ((int)lists[c].size() > KGW_FAM_MAXNB)
-        return fail(KGW_ERR_UNSUPPORTED, "a node with more than 7 IBD neighbours is not built");
       KgwFamInterval iv;
       memset(&iv, 0, sizeof(iv));
       iv.j0 = ranges[c].first; iv.j1 = ranges[c].second; iv.nn = (int)lists[c].size();
-      for (int t = 0; t < iv.nn; t++) iv.nb[t] = lists[c][t];
-      if (c > 0) iv.ndl = fam_set_difference(lists[c], lists[c - 1], iv.dl);
-      if (c + 1 < lists.size()) iv.ndr = fam_set_difference(lists[c], lists[c + 1], iv.dr);
+      *max_nn = std::max(*max_nn, iv.nn);
+      iv.nb_off = (int32_t)ivlist.size();
+      ivlist.insert(ivlist.end(), lists[c].begin(), lists[c].end());
+      iv.dl_off = (int32_t)ivlist.size();
+      if (c > 0) iv.ndl = fam_set_difference(lists[c], lists[c - 1], ivlist);
+      iv.dr_off = (int32_t)ivlist.size();
+      if (c + 1 < lists.size()) iv.ndr = fam_set_difference(lists[c], lists[c + 1], ivlist);
       out[i].push_back(iv);
     }
   }
@@ -487,6 +505,9 @@ void fam_build_ops(const FamilyState &F, int f, const int32_t *groups, const std
 }
 
 }  // namespace
+
+typedef void (*kgw_fam_kernel_fn)(const KgwFamParams);
+kgw_fam_kernel_fn kgw_family_kernel_big_(int SF, bool uniform_mu);   // kgw_family_big.cu
 
 struct kgw_plan {
   int device = 0, sm_count = 148;
@@ -620,17 +641,19 @@ int fam_upload_partition(kgw_plan *pl, const int32_t *groups) {
 
 struct DevInfo { int major = 0, minor = 0, multiProcessorCount = 0; };
 
-typedef void (*fam_kernel_fn)(const KgwFamParams);
-fam_kernel_fn fam_kernel_for(int SF, bool uniform_mu) {
+typedef ::kgw_fam_kernel_fn fam_kernel_fn;
+fam_kernel_fn fam_kernel_for(int SF, bool uniform_mu, bool big) {
+  if (big) return kgw_family_kernel_big_(SF, uniform_mu);
   if (uniform_mu)
-    return SF == 1 ? kgw::family_kernel<1, true> : (SF == 2 ? kgw::family_kernel<2, true> : (SF == 4 ? kgw::family_kernel<4, true> : kgw::family_kernel<8, true>));
-  return SF == 1 ? kgw::family_kernel<1, false> : (SF == 2 ? kgw::family_kernel<2, false> : (SF == 4 ? kgw::family_kernel<4, false> : kgw::family_kernel<8, false>));
+    return SF == 1 ? kgw::family_kernel<1, true, false> : (SF == 2 ? kgw::family_kernel<2, true, false> : (SF == 4 ? kgw::family_kernel<4, true, false> : kgw::family_kernel<8, true, false>));
+  return SF == 1 ? kgw::family_kernel<1, false, false> : (SF == 2 ? kgw::family_kernel<2, false, false> : (SF == 4 ? kgw::family_kernel<4, false, false> : kgw::family_kernel<8, false, false>));
 }
 
 int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   const kgw_families *fi = prob->families;
   const int p = pl->p, K = pl->K, N = pl->N;
   if (!prob->ref_global) return fail(KGW_ERR_INVALID, "families need ref_global (references_global, knockoffs.h:141)");
+  if (K > 255) return fail(KGW_ERR_UNSUPPORTED, "K > 255 with IBD families is not built (the related branch keeps 255 as its 'not drawn yet' state)");
   if (!fi->fam_off || !fi->fam_members || !fi->seg_off || !fi->seg_jmin || !fi->seg_jmax || !fi->seg_ids_off || !fi->seg_ids)
     return fail(KGW_ERR_INVALID, "null array in kgw_families");
   FamilyState *F = new FamilyState();
@@ -672,26 +695,27 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     }
   }
   std::vector<KgwFamInterval> ivs;
-  std::vector<int32_t> iv_start;
+  std::vector<int32_t> iv_start, ivlist;
   std::vector<KgwFamRange> ranges;
   F->fams.resize(F->n_families);
   for (int f = 0; f < F->n_families; f++) {
     const int n = F->h_fam_off[f + 1] - F->h_fam_off[f];
-    if (n < 1 || n > KGW_FAM_MAXN) return fail(KGW_ERR_UNSUPPORTED, "families of more than 8 haplotypes are not built");
-    F->n_max = std::max(F->n_max, n);
+    if (n < 1) return fail(KGW_ERR_INVALID, "empty family");
     std::vector<std::vector<KgwFamInterval>> per;
-    int rc = fam_build_intervals(*F, f, p, per);
+    int max_nn = 0;
+    int rc = fam_build_intervals(*F, f, p, per, ivlist, &max_nn);
     if (rc != KGW_OK) return rc;
     KgwFamDesc &d = F->fams[f];
     memset(&d, 0, sizeof(d));
     d.n = n; d.mem_off = F->h_fam_off[f]; d.out_off = F->h_fam_off[f];
+    d.ivs_off = (int32_t)iv_start.size();
     std::vector<int> bnd;   // loci b > 0 where some member's neighbour list changes between b-1 and b
     for (int i = 0; i < n; i++) {
       iv_start.push_back((int32_t)ivs.size());
       ivs.insert(ivs.end(), per[i].begin(), per[i].end());
       for (const KgwFamInterval &iv : per[i]) if (iv.j0 > 0) bnd.push_back(iv.j0);
     }
-    iv_start.push_back((int32_t)ivs.size());  // sentinel: iv_start index = mem_off + f + i
+    iv_start.push_back((int32_t)ivs.size());  // sentinel
     // special loci [b-2, b+1] (kgw_family.cuh): junction nodes, pinned nodes and their consumers
     std::sort(bnd.begin(), bnd.end());
     d.rng_off = (int32_t)ranges.size();
@@ -707,7 +731,12 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
       ranges[r].off = stored;
       stored += ranges[r].s1 - std::max(0, ranges[r].s0 - 1) + 1;
     }
-    F->rtot = std::max(F->rtot, std::max(stored, 1));
+    // class of the family: registers / shared memory / pattern bytes suffice for small ones (kgw_family.cuh)
+    FamClass &C = F->cls[(n > KGW_FAM_MAXN || max_nn > KGW_FAM_MAXNB) ? 1 : 0];
+    C.list.push_back(f);
+    C.count++;
+    C.n_max = std::max(C.n_max, n);
+    C.rtot = std::max(C.rtot, std::max(stored, 1));
   }
   // node emission table (family_bp.cpp:437-454) when mu is the same at every locus (init_hmm, knockoffs.cpp:1520)
   bool uniform = true;
@@ -741,7 +770,13 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMalloc(&F->demtab, sizeof(double) * emtab.size()));
   KGW_CUDA(cudaMalloc(&F->dref_global, sizeof(int32_t) * (size_t)N * K));
   KGW_CUDA(cudaMalloc(&F->dstatus, sizeof(int32_t)));
-  KGW_CUDA(cudaMalloc(&F->dwork, sizeof(int32_t)));
+  KGW_CUDA(cudaMalloc(&F->divlist, sizeof(int32_t) * std::max<size_t>(ivlist.size(), 1)));
+  KGW_CUDA(cudaMemcpy(F->divlist, ivlist.data(), sizeof(int32_t) * ivlist.size(), cudaMemcpyHostToDevice));
+  for (FamClass &C : F->cls) {
+    KGW_CUDA(cudaMalloc(&C.dwork, sizeof(int32_t)));
+    KGW_CUDA(cudaMalloc(&C.dlist, sizeof(int32_t) * std::max<size_t>(C.list.size(), 1)));
+    KGW_CUDA(cudaMemcpy(C.dlist, C.list.data(), sizeof(int32_t) * C.list.size(), cudaMemcpyHostToDevice));
+  }
   KGW_CUDA(cudaMalloc(&F->dranges, sizeof(KgwFamRange) * std::max<size_t>(ranges.size(), 1)));
   KGW_CUDA(cudaMemcpy(F->dranges, ranges.data(), sizeof(KgwFamRange) * ranges.size(), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->dmembers, F->h_members.data(), sizeof(int32_t) * F->members_total, cudaMemcpyHostToDevice));
@@ -753,28 +788,48 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMemset(F->dstatus, 0, sizeof(int32_t)));
 
   // one warp per resident family, as many CTAs as the kernel's registers / shared memory keep resident;
-  // scratch slots bounded by 80 % of the memory still free (the sampler took at most a quarter before)
+  // scratch slots bounded by 80 % of the memory still free (the sampler took at most a quarter before).  The big
+  // class is sized first (few families, large slots: at most 40 % of the free memory), the small class takes the rest.
   F->SF = (K + 31) / 32 <= 1 ? 1 : ((K + 31) / 32 <= 2 ? 2 : ((K + 31) / 32 <= 4 ? 4 : 8));
-  F->threads = 128;
-  const int wpc = F->threads / 32;
-  F->smem = (size_t)8 * 256 * sizeof(double) + (size_t)wpc * 2 * F->n_max * F->SF * 32 * sizeof(double);
-  int ctas_per_sm = 4;
-  {
-    void (*fnq)(const KgwFamParams) = fam_kernel_for(F->SF, uniform);
-    KGW_CUDA(cudaFuncSetAttribute(fnq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
-    KGW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fnq, F->threads, F->smem));
-    ctas_per_sm = std::max(1, ctas_per_sm);
-  }
-  const size_t per_slot = (size_t)F->n_max * p * ((size_t)K * 9 + 2) + (size_t)F->n_max * F->rtot * K * sizeof(double);
+  const size_t KP = (size_t)F->SF * 32;
   size_t free_b = 0, total_b = 0;
   KGW_CUDA(cudaMemGetInfo(&free_b, &total_b));
   free_b += g_pool.parked(pl->device);
-  const long long slots_mem = std::max<long long>(wpc, (long long)((double)free_b * 0.8 / (double)per_slot));
-  const long long want = std::min<long long>(F->n_families, (long long)dp.multiProcessorCount * ctas_per_sm * wpc);
-  long long ctas = (want + wpc - 1) / wpc;
-  if (ctas * wpc > slots_mem) ctas = slots_mem / wpc;
-  F->grid = (int)std::max<long long>(1, ctas);
-  const size_t nslots = (size_t)F->grid * wpc;
+  for (int c = 1; c >= 0; c--) {
+    FamClass &C = F->cls[c];
+    if (C.count == 0) continue;
+    const bool big = (c == 1);
+    size_t per_slot = (size_t)C.n_max * p * ((size_t)K * 9 + 2) + (size_t)C.n_max * C.rtot * K * sizeof(double);
+    if (big) per_slot += (size_t)2 * C.n_max * KP * sizeof(double) + (size_t)5 * C.n_max * sizeof(int32_t);
+    const double budget = (double)free_b * (big ? 0.4 : 0.8);
+    // CTAs of four warps; a big class whose slots are too large for four of them runs single-warp CTAs
+    C.threads = (big && (double)per_slot * 4 > budget) ? 32 : 128;
+    const int wpc = C.threads / 32;
+    C.smem = (size_t)8 * 256 * sizeof(double) + (big ? 0 : (size_t)wpc * 2 * C.n_max * KP * sizeof(double));
+    int ctas_per_sm = 4;
+    {
+      fam_kernel_fn fnq = fam_kernel_for(F->SF, uniform, big);
+      KGW_CUDA(cudaFuncSetAttribute(fnq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
+      KGW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fnq, C.threads, C.smem));
+      ctas_per_sm = std::max(1, ctas_per_sm);
+    }
+    const long long slots_mem = (long long)(budget / (double)per_slot);
+    if (slots_mem < wpc) return fail(KGW_ERR_NOMEM, "not enough device memory for the message tables of one IBD family");
+    const long long want = std::min<long long>(C.count, (long long)dp.multiProcessorCount * ctas_per_sm * wpc);
+    long long ctas = (want + wpc - 1) / wpc;
+    if (ctas * wpc > slots_mem) ctas = slots_mem / wpc;
+    C.grid = (int)std::max<long long>(1, ctas);
+    const size_t nslots = (size_t)C.grid * wpc;
+    KGW_CUDA(pl->alloc(&C.dmsg, sizeof(double) * C.n_max * (size_t)p * K * nslots));   // pooled with the plan's buffers
+    KGW_CUDA(pl->alloc(&C.dmrc, sizeof(double) * C.n_max * (size_t)C.rtot * K * nslots));
+    KGW_CUDA(pl->alloc(&C.dpat, (size_t)C.n_max * p * K * nslots));
+    KGW_CUDA(pl->alloc(&C.dbytes, (size_t)2 * C.n_max * p * nslots));
+    if (big) {
+      KGW_CUDA(pl->alloc(&C.dpmg, sizeof(double) * 2 * C.n_max * KP * nslots));
+      KGW_CUDA(pl->alloc(&C.dflg, sizeof(int32_t) * 5 * C.n_max * nslots));
+    }
+    free_b -= std::min(free_b, per_slot * nslots);
+  }
   {
     const char *ov = getenv("KGW_FAMILY_OVERLAP");   // development: "0" / "1"
     F->overlap = ov && ov[0] == '1';   // measured on B200: no gain, the persistent sampler CTAs queue behind the family CTAs
@@ -782,34 +837,37 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     KGW_CUDA(cudaEventCreateWithFlags(&F->ev_fork, cudaEventDisableTiming));
     KGW_CUDA(cudaEventCreateWithFlags(&F->ev_join, cudaEventDisableTiming));
   }
-  KGW_CUDA(pl->alloc(&F->dmsg, sizeof(double) * F->n_max * (size_t)p * K * nslots));   // pooled with the plan's buffers
-  KGW_CUDA(pl->alloc(&F->dmrc, sizeof(double) * F->n_max * (size_t)F->rtot * K * nslots));
-  KGW_CUDA(pl->alloc(&F->dpat, (size_t)F->n_max * p * K * nslots));
-  KGW_CUDA(pl->alloc(&F->dbytes, (size_t)2 * F->n_max * p * nslots));
 
   KgwFamParams &P = F->P;
-  P.N = N; P.p = p; P.K = K; P.n_families = F->n_families; P.stride_w = pl->stride_w; P.n_max = F->n_max;
+  P.N = N; P.p = p; P.K = K; P.n_families = 0; P.stride_w = pl->stride_w; P.n_max = 0;   // (class fields: fam_launch)
   P.uniform_mu = uniform ? 1 : 0;
   P.Hw = pl->dHw; P.ref_global = F->dref_global; P.fams = F->dfams; P.members = F->dmembers; P.iv_start = F->divstart;
-  P.ivs = F->divs; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.msg = F->dmsg; P.mrc = F->dmrc; P.rtot = F->rtot; P.W = pl->W; P.pat = F->dpat;
+  P.ivs = F->divs; P.ivlist = F->divlist; P.loc = F->dloc; P.emtab = F->demtab; P.Hk = pl->dHk; P.W = pl->W;
   P.phase_cycles = nullptr;
 #ifdef KGW_PHASES
   KGW_CUDA(cudaMalloc(&F->dphase, sizeof(long long) * 8));
   KGW_CUDA(cudaMemset(F->dphase, 0, sizeof(long long) * 8));
   P.phase_cycles = F->dphase;
 #endif
-  P.bytes = F->dbytes; P.work = F->dwork; P.ranges = F->dranges; P.seed = pl->P.seed; P.injected_u = pl->dinj; P.dbg_z = P.dbg_zk = nullptr; P.status = F->dstatus;
+  P.ranges = F->dranges; P.seed = pl->P.seed; P.injected_u = pl->dinj; P.dbg_z = P.dbg_zk = nullptr; P.status = F->dstatus;
   return KGW_OK;
 }
 
 int fam_launch(kgw_plan *pl, cudaStream_t st) {
   FamilyState *F = pl->fam;
   if (!F || F->n_families == 0) return KGW_OK;
-  void (*fn)(const KgwFamParams) = fam_kernel_for(F->SF, F->P.uniform_mu != 0);
-  KGW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
-  KGW_CUDA(cudaMemsetAsync(F->dwork, 0, sizeof(int32_t), st));
-  fn<<<F->grid, F->threads, F->smem, st>>>(F->P);
-  KGW_CUDA(cudaGetLastError());
+  for (int c = 0; c < 2; c++) {   // one launch per class that has families
+    FamClass &C = F->cls[c];
+    if (C.count == 0) continue;
+    fam_kernel_fn fn = fam_kernel_for(F->SF, F->P.uniform_mu != 0, c == 1);
+    KGW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
+    KGW_CUDA(cudaMemsetAsync(C.dwork, 0, sizeof(int32_t), st));
+    KgwFamParams Pc = F->P;
+    Pc.n_families = C.count; Pc.fam_list = C.dlist; Pc.n_max = C.n_max; Pc.rtot = C.rtot;
+    Pc.msg = C.dmsg; Pc.mrc = C.dmrc; Pc.pat = C.dpat; Pc.bytes = C.dbytes; Pc.pmg = C.dpmg; Pc.flg = C.dflg; Pc.work = C.dwork;
+    fn<<<C.grid, C.threads, C.smem, st>>>(Pc);
+    KGW_CUDA(cudaGetLastError());
+  }
   return KGW_OK;
 }
 
@@ -1478,7 +1536,7 @@ int32_t kgw_plan_info(kgw_plan *pl, kgw_plan_info_t *out) {
     out->reserved = (int32_t)pl->subs.size();
     return KGW_OK;
   }
-  out->launches_per_run = (pl->n_haps > 0 ? 1 : 0) + ((pl->fam && pl->fam->n_families > 0) ? 1 : 0);
+  out->launches_per_run = (pl->n_haps > 0 ? 1 : 0) + (pl->fam ? (pl->fam->cls[0].count > 0) + (pl->fam->cls[1].count > 0) : 0);
   out->grid = pl->grid;
   out->block = pl->threads;
   out->lanes_per_hap = pl->var->L;

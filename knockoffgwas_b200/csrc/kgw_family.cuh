@@ -41,8 +41,14 @@
 #include <type_traits>
 #include "kgw_device.cuh"
 
-#define KGW_FAM_MAXN 8   // members per family
-#define KGW_FAM_MAXNB 7  // neighbours of a node
+// Two compiled classes of the kernel (template parameter BIG).  The SMALL class keeps the per-member bookkeeping of a
+// sweep in registers (bit masks, 3-bit neighbour counts) and the running messages in shared memory, and looks node
+// emissions up by an 8-bit match pattern: families of at most KGW_FAM_MAXN haplotypes whose nodes have at most
+// KGW_FAM_MAXNB neighbours -- pairs, trios, sibships.  Everything else goes to the BIG class, which has no limit (the
+// reference has none, family_bp.cpp:41-61): bookkeeping and running messages live in the slot's HBM scratch and a node
+// with more than KGW_FAM_MAXNB neighbours forms its emission from the packed rows directly.
+#define KGW_FAM_MAXN 8   // members per family, SMALL class
+#define KGW_FAM_MAXNB 7  // neighbours of a node whose emission is a table look-up / pattern byte
 #ifndef KGW_FAM_MINB
 #define KGW_FAM_MINB 4   // resident CTAs of 4 warps per SM the register allocation aims at
 #endif
@@ -50,11 +56,10 @@
 struct KgwFamInterval {  // maximal run of loci over which neighbors[i][j] is constant (family_bp.cpp:41-61)
   int32_t j0, j1;        // inclusive
   int32_t nn;            // number of neighbours
-  int32_t nb[KGW_FAM_MAXNB];   // family-local indices, reference push_back order
   int32_t ndl, ndr;      // sizes of neigh_diff_left at j0 / neigh_diff_right at j1 (family_bp.cpp:365-378)
-  int32_t dl[KGW_FAM_MAXNB];
-  int32_t dr[KGW_FAM_MAXNB];
-  int32_t pad;
+  int32_t nb_off;        // into KgwFamParams::ivlist: nn family-local indices, reference push_back order
+  int32_t dl_off;        // ... ndl indices
+  int32_t dr_off;        // ... ndr indices
 };
 
 struct KgwFamRange {   // special loci s0 .. s1, inclusive; sorted, disjoint
@@ -72,11 +77,11 @@ struct KgwFamOp {  // FamilyKnockoffs::run (family_knockoffs.cpp:155-270) flatte
 
 struct KgwFamDesc {
   int32_t n;          // members
-  int32_t mem_off;    // into members[] and iv_start[] (iv_start has one extra entry per family)
+  int32_t mem_off;    // into members[]
   int32_t op_off, n_ops;
   int32_t out_off;    // row offset of this family in the debug outputs
   int32_t rng_off, n_rng;   // special ranges of this family
-  int32_t pad;
+  int32_t ivs_off;    // into iv_start[]: n + 1 entries for this family
 };
 
 struct KgwFamLocus {  // per locus
@@ -93,9 +98,11 @@ struct KgwFamParams {
   const uint32_t *Hw;
   const int32_t *ref_global;   // [N][K]
   const KgwFamDesc *fams;
+  const int32_t *fam_list;     // [n_families] descriptors of this launch's class
   const int32_t *members;      // absolute ids
   const int32_t *iv_start;     // per (family, member): first interval; one sentinel per family
   const KgwFamInterval *ivs;
+  const int32_t *ivlist;       // neighbour / junction-difference lists of the intervals
   const KgwFamRange *ranges;
   const KgwFamOp *ops;
   const KgwFamLocus *loc;      // [p]
@@ -110,6 +117,8 @@ struct KgwFamParams {
   int32_t rtot, W;             // stored loci per member (maximum over the families); windows of the problem (injected_u layout)
   uint8_t *pat;                // [slots][n_max][p][K]
   uint8_t *bytes;              // [slots][2][n_max][p]   Z (255 = node still active), Zk
+  double *pmg;                 // BIG class: [slots][2][n_max][KP] running messages of a sweep (SMALL: shared memory)
+  int32_t *flg;                // BIG class: [slots][5][n_max] per-member bookkeeping of a sweep (SMALL: registers)
   int32_t *work;               // next family to hand out (zeroed before every launch)
   unsigned long long seed;
   const double *injected_u;    // [N][W][3][p] or null (the related branch reads window block 0)
@@ -207,7 +216,7 @@ __device__ __forceinline__ int warp_choice_contig(const double (&w)[SF], double 
 
 // SF: states per lane; UMU: mu is the same at every locus (init_hmm, knockoffs.cpp:1520) and node emissions
 // come from the shared-memory table, else they are formed per state with pow() as the reference does
-template <int SF, bool UMU>
+template <int SF, bool UMU, bool BIG>
 __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_constant__ KgwFamParams P) {
   constexpr int KP = SF * 32;
   const int lane = threadIdx.x & 31;
@@ -224,8 +233,13 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
 
   extern __shared__ __align__(16) unsigned char fam_smem[];
   double *tab = reinterpret_cast<double *>(fam_smem);                       // [8][256], shared by the CTA
-  double *pm = tab + 8 * 256 + (size_t)wid * 2 * P.n_max * KP;              // [n_max][KP] last message of each chain
-  double *pm_old = pm + (size_t)P.n_max * KP;                               // ... and its value before this sweep touched it
+  // [n_max][KP] last message of each chain, and its value before this sweep touched it
+  double *pm = BIG ? P.pmg + (size_t)slot * 2 * P.n_max * KP : tab + 8 * 256 + (size_t)wid * 2 * P.n_max * KP;
+  double *pm_old = pm + (size_t)P.n_max * KP;
+  // BIG class: per-member bookkeeping of a sweep, [5][n_max]: neighbour count at the sweep position, message one locus
+  // back computed / changed in this sweep, and the same two for the stretch or locus being processed
+  int32_t *fl_nn = BIG ? P.flg + (size_t)slot * 5 * P.n_max : nullptr;
+  int32_t *fl_cp = fl_nn + P.n_max, *fl_gp = fl_cp + P.n_max, *fl_cn = fl_gp + P.n_max, *fl_gn = fl_cn + P.n_max;
   if (UMU) {
     for (int t = threadIdx.x; t < 8 * 256; t += blockDim.x) tab[t] = P.emtab[t];
   }
@@ -237,10 +251,13 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     if (lane == 0) f = atomicAdd(P.work, 1);
     f = __shfl_sync(FULL, f, 0);
     if (f >= P.n_families) break;
-    const KgwFamDesc fd = P.fams[f];
+    const KgwFamDesc fd = P.fams[P.fam_list[f]];
     const int n = fd.n;
     const int32_t *mem = P.members + fd.mem_off;
-    const int32_t *ivs0 = P.iv_start + fd.mem_off + f;   // n+1 entries for this family
+    const int32_t *ivs0 = P.iv_start + fd.ivs_off;   // n+1 entries for this family
+    auto nbl = [&](const KgwFamInterval *iv, int t) -> int { return __ldg(P.ivlist + iv->nb_off + t); };
+    auto dll = [&](const KgwFamInterval *iv, int t) -> int { return __ldg(P.ivlist + iv->dl_off + t); };
+    auto drl = [&](const KgwFamInterval *iv, int t) -> int { return __ldg(P.ivlist + iv->dr_off + t); };
     const KgwFamRange *rngs = P.ranges + fd.rng_off;
     const int nrng = fd.n_rng;
 #ifdef KGW_PHASES
@@ -274,6 +291,22 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
       return v;
     };
 
+    // emission of a node with more than KGW_FAM_MAXNB neighbours (BIG class): the same product in the same order
+    // (family_bp.cpp:441-454), match bits read from the packed rows
+    auto emission_big = [&](int i, const KgwFamInterval *iv, int j, int k) -> double {
+      const double mu = P.loc[j].mu;
+      const uint32_t rw = __ldg(P.Hw + (size_t)__ldg(P.ref_global + (size_t)mem[i] * K + k) * P.stride_w + (j >> 5));
+      auto same = [&](int m) { return ((~(rw ^ __ldg(P.Hw + (size_t)mem[m] * P.stride_w + (j >> 5)))) >> (j & 31)) & 1u; };
+      double v = same(i) ? 1.0 - mu : mu;
+      for (int t = 0; t < iv->nn; t++) v *= same(nbl(iv, t)) ? 1.0 - mu : mu;
+      return pow(v, 1.0 / (double)(iv->nn + 1));
+    };
+    // emission of node (i, j) at state k: pattern byte `pt` when the node has few neighbours
+    auto emission_at = [&](unsigned pt, int i, const KgwFamInterval *iv, int nn, int j, int k) -> double {
+      if (BIG && nn > KGW_FAM_MAXNB) return emission_big(i, iv, j, k);
+      return emission_of(pt, j, nn);
+    };
+
     // ---- initialise: nothing drawn, match patterns.  The messages are NOT written: the first BP
     //      iteration substitutes their initial value 1/K wherever the reference would read it.
     for (int i = 0; i < n; i++) {
@@ -290,8 +323,9 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
           const int jlo = w << 5, jhi = min(jlo + 32, p);
           uint8_t *dst = pat_base + ((size_t)i * p + jlo) * K + k;
           while (ivj1 < jlo) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
+          const int nnp = min(ivnn, KGW_FAM_MAXNB);   // nodes with more neighbours do not use their pattern byte
           if (ivj1 >= jhi - 1 && ivnn <= 1) {   // one neighbour list for the whole word, pairs
-            const uint32_t m1 = (ivnn == 1) ? ~(rw ^ __ldg(P.Hw + (size_t)mem[iv->nb[0]] * P.stride_w + w)) : 0u;
+            const uint32_t m1 = (ivnn == 1) ? ~(rw ^ __ldg(P.Hw + (size_t)mem[nbl(iv, 0)] * P.stride_w + w)) : 0u;
             for (int j = jlo; j < jhi; j++) {
               const int q = j & 31;
               *dst = (uint8_t)(((m0 >> q) & 1u) | (((m1 >> q) & 1u) << 1));
@@ -301,7 +335,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             uint32_t mt[KGW_FAM_MAXNB];
 #pragma unroll
             for (int t = 0; t < KGW_FAM_MAXNB; t++)
-              mt[t] = (t < ivnn) ? ~(rw ^ __ldg(P.Hw + (size_t)mem[iv->nb[t]] * P.stride_w + w)) : 0u;
+              mt[t] = (t < nnp) ? ~(rw ^ __ldg(P.Hw + (size_t)mem[nbl(iv, t)] * P.stride_w + w)) : 0u;
             for (int j = jlo; j < jhi; j++) {
               const int q = j & 31;
               unsigned pt = (m0 >> q) & 1u;
@@ -314,8 +348,8 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             for (int j = jlo; j < jhi; j++) {
               while (ivj1 < j) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
               unsigned pt = (m0 >> (j & 31)) & 1u;
-              for (int t = 0; t < ivnn; t++) {
-                const uint32_t hw2 = __ldg(P.Hw + (size_t)mem[iv->nb[t]] * P.stride_w + w);
+              for (int t = 0; t < min(ivnn, KGW_FAM_MAXNB); t++) {
+                const uint32_t hw2 = __ldg(P.Hw + (size_t)mem[nbl(iv, t)] * P.stride_w + w);
                 pt |= ((~(rw ^ hw2) >> (j & 31)) & 1u) << (t + 1);
               }
               *dst = (uint8_t)pt;
@@ -349,7 +383,18 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
       const int jlast = (dir == 0) ? p - 2 : 1;   // last locus of the sweep
       int j = (dir == 0) ? 0 : p - 1;
       unsigned nnpack = 0;                    // neighbour count of every member at the current locus, 3 bits each
-      for (int i = 0; i < n; i++) nnpack |= (unsigned)find_iv(i, j)->nn << (3 * i);
+      // (BIG class: the same bookkeeping in the slot's scratch, one int per member; every lane writes the same values)
+      auto nn_get = [&](int i) -> int { return BIG ? fl_nn[i] : (int)((nnpack >> (3 * i)) & 7u); };
+      auto nn_set = [&](int i, int v) {
+        if (BIG) fl_nn[i] = v;
+        else nnpack = (nnpack & ~(7u << (3 * i))) | ((unsigned)v << (3 * i));
+      };
+      auto cp_get = [&](int i) -> bool { return BIG ? (fl_cp[i] != 0) : (((comp_prev >> i) & 1u) != 0); };
+      auto gp_get = [&](int i) -> bool { return BIG ? (fl_gp[i] != 0) : (((chg_prev >> i) & 1u) != 0); };
+      for (int i = 0; i < n; i++) {
+        nn_set(i, find_iv(i, j)->nn);
+        if (BIG) { fl_cp[i] = 0; fl_gp[i] = 0; }
+      }
       bool valid[SF];
 #pragma unroll
       for (int s = 0; s < SF; s++) valid[s] = (s * 32 + lane < K);
@@ -369,10 +414,10 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
         if (dir == 0 ? (e > jlast) : (e < jlast)) e = jlast;
         const int len = (e - j) * step + 1;
         if (len > 0) {
-          const unsigned todo = full ? ((1u << n) - 1u) : chg_prev;
           unsigned comp_new = 0, chg_new = 0;
+          if (BIG) for (int i = 0; i < n; i++) { fl_cn[i] = 0; fl_gn[i] = 0; }
           const bool has_in = (dir == 0) ? (j > 0) : (j < p - 1);
-          if (full && n == 2 && (!has_in || comp_prev == 3u)) {
+          if (!BIG && full && n == 2 && (!has_in || comp_prev == 3u)) {
             // First iteration of a pair (the common family): the two chains of the stretch are independent, so they
             // run in lockstep -- one loop, one set of locus constants, one shuffle tree for both sums, and twice
             // the instruction-level parallelism.  Nothing is compared (the old value of every message is 1/K).
@@ -453,8 +498,9 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             chg_new = 3u;
           } else
           for (int i = 0; i < n; i++) {
-            if (!((todo >> i) & 1u)) continue;
-            const int nn = (int)((nnpack >> (3 * i)) & 7u);
+            if (!(full || gp_get(i))) continue;
+            const int nn = nn_get(i);
+            const KgwFamInterval *ivp = (BIG && nn > KGW_FAM_MAXNB) ? find_iv(i, j) : nullptr;   // constant over a plain stretch
             const size_t rowo = ((size_t)i * p + j) * K + lane;
             constexpr ptrdiff_t sgn = step;
             const ptrdiff_t sK = sgn * K;
@@ -472,7 +518,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
               // right sweep: nothing of the stretch is stored except its last locus (the next range reads it);
               // when not `full`, vo[] follows the chain as it was before this sweep
               double vo[SF];
-              const double *prow = (hasv && !((comp_prev >> i) & 1u)) ? mr_row(i, j - 1, prev_ext0, prev_off) : nullptr;
+              const double *prow = (hasv && !cp_get(i)) ? mr_row(i, j - 1, prev_ext0, prev_off) : nullptr;
 #pragma unroll
               for (int s = 0; s < SF; s++) {
                 v[s] = 1.0;   // no incoming message at the first node of the sweep
@@ -497,7 +543,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
                   q[s] = 0.0;
                   qo[s] = 0.0;
                   if (valid[s]) {
-                    const double fk = emission_of(ptc[s], j + t, nn);
+                    const double fk = emission_at(ptc[s], i, ivp, nn, j + t, s * 32 + lane);
                     q[s] = fk * v[s];
                     qsum += q[s];
                     if (!full) { qo[s] = fk * vo[s]; qosum += qo[s]; }
@@ -546,7 +592,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
 #pragma unroll
               for (int s = 0; s < SF; s++) {
                 v[s] = 1.0;
-                if (valid[s] && hasv) v[s] = ((comp_prev >> i) & 1u) ? pm[i * KP + s * 32 + lane] : dp[s * 32 - sK];
+                if (valid[s] && hasv) v[s] = cp_get(i) ? pm[i * KP + s * 32 + lane] : dp[s * 32 - sK];
               }
               for (; t < len; t++) {
                 // fetches for the next locus of this chain, and L2 prefetches further ahead
@@ -569,7 +615,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
                 for (int s = 0; s < SF; s++) {
                   q[s] = 0.0;
                   if (valid[s]) {
-                    q[s] = emission_of(ptc[s], j - t, nn) * v[s];
+                    q[s] = emission_at(ptc[s], i, ivp, nn, j - t, s * 32 + lane) * v[s];
                     qsum += q[s];
                   }
                 }
@@ -604,12 +650,17 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             if (t == len) {   // the chain reached the end of the stretch: hand its last message to the next range
 #pragma unroll
               for (int s = 0; s < SF; s++) if (valid[s]) pm[i * KP + s * 32 + lane] = v[s];
-              comp_new |= 1u << i;
-              if (ch) chg_new |= 1u << i;
+              if (BIG) { fl_cn[i] = 1; fl_gn[i] = ch ? 1 : 0; }
+              else { comp_new |= 1u << i; if (ch) chg_new |= 1u << i; }
             }
           }
           comp_prev = comp_new;
           chg_prev = chg_new;
+          if (BIG) {
+            __syncwarp();
+            for (int i = 0; i < n; i++) { fl_cp[i] = fl_cn[i]; fl_gp[i] = fl_gn[i]; }
+            __syncwarp();
+          }
           j = e + step;
         }
         if (rr == nrng) break;
@@ -621,7 +672,8 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
           for (int i = 0; i < n; i++) {
             const KgwFamInterval *iv = find_iv(i, j);
             const int nn = iv->nn;
-            nnpack = (nnpack & ~(7u << (3 * i))) | ((unsigned)nn << (3 * i));
+            nn_set(i, nn);
+            if (BIG) { fl_cn[i] = 0; fl_gn[i] = 0; }
             if (Zb[(size_t)i * p + j] != 255) continue;   // pinned by condition_on: inactive node
             const int ndl = (j == iv->j0 && j > 0) ? iv->ndl : 0;
             const int ndr = (j == iv->j1 && j < p - 1) ? iv->ndr : 0;
@@ -629,7 +681,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             double *dst = (dir == 0) ? mr_row(i, j, cur_ext0, cur_off) : ml_base + rowo;
             // own chain, one locus back in sweep order (for the right sweep: inside the stored span of this range)
             const double *prevg = (dir == 0) ? mr_row(i, j - 1, cur_ext0, cur_off) : ml_base + rowo + K;
-            const bool prev_sm = (comp_prev >> i) & 1u;
+            const bool prev_sm = cp_get(i);
             double msg[SF], oldv[SF];
             double qsum = 0.0;
 #pragma unroll
@@ -638,15 +690,15 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
               msg[s] = 0.0;
               oldv[s] = 0.0;
               if (k < K) {
-                double q = emission_of(pat_base[rowo + k], j, nn);
+                double q = emission_at(pat_base[rowo + k], i, iv, nn, j, k);
                 oldv[s] = full ? p0 : dst[k];
                 if (has_prev) q *= prev_sm ? pm[i * KP + k] : prevg[k];
                 if (dir == 0) {
-                  for (int t = 0; t < ndl; t++) q *= mr_row(iv->dl[t], j - 1, cur_ext0, cur_off)[k];
-                  for (int t = 0; t < ndr; t++) q *= full ? p0 : ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k];
+                  for (int t = 0; t < ndl; t++) q *= mr_row(dll(iv, t), j - 1, cur_ext0, cur_off)[k];
+                  for (int t = 0; t < ndr; t++) q *= full ? p0 : ml_base[((size_t)drl(iv, t) * p + j + 1) * K + k];
                 } else {
-                  for (int t = 0; t < ndr; t++) q *= ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k];
-                  for (int t = 0; t < ndl; t++) q *= mr_row(iv->dl[t], j - 1, cur_ext0, cur_off)[k];
+                  for (int t = 0; t < ndr; t++) q *= ml_base[((size_t)drl(iv, t) * p + j + 1) * K + k];
+                  for (int t = 0; t < ndl; t++) q *= mr_row(dll(iv, t), j - 1, cur_ext0, cur_off)[k];
                 }
                 msg[s] = q;
                 qsum += q;
@@ -674,11 +726,16 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
                 if (dir == 0) pm_old[i * KP + k] = oldv[s];
               }
             }
-            comp_cur |= 1u << i;
-            if (ch) chg_cur |= 1u << i;
+            if (BIG) { fl_cn[i] = 1; fl_gn[i] = ch ? 1 : 0; }
+            else { comp_cur |= 1u << i; if (ch) chg_cur |= 1u << i; }
           }
           comp_prev = comp_cur;
           chg_prev = chg_cur;
+          if (BIG) {
+            __syncwarp();
+            for (int i = 0; i < n; i++) { fl_cp[i] = fl_cn[i]; fl_gp[i] = fl_gn[i]; }
+            __syncwarp();
+          }
         }
         prev_ext0 = cur_ext0;
         prev_off = cur_off;
@@ -725,14 +782,14 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
         const int k = s * 32 + lane;
         w[s] = 0.0;
         if (k < K) {
-          double v = emission_of(pat_base[((size_t)i * p + j) * K + k], j, iv->nn);
+          double v = emission_at(pat_base[((size_t)i * p + j) * K + k], i, iv, iv->nn, j, k);
           if (j > 0) {
             v *= mr_find(i, j - 1)[k];
-            for (int t = 0; t < ndl; t++) v *= mr_find(iv->dl[t], j - 1)[k];
+            for (int t = 0; t < ndl; t++) v *= mr_find(dll(iv, t), j - 1)[k];
           }
           if (j < p - 1) {
             v *= ml_base[((size_t)i * p + j + 1) * K + k];
-            for (int t = 0; t < ndr; t++) v *= ml_base[((size_t)iv->dr[t] * p + j + 1) * K + k];
+            for (int t = 0; t < ndr; t++) v *= ml_base[((size_t)drl(iv, t) * p + j + 1) * K + k];
           }
           w[s] = v;
         }
@@ -772,7 +829,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
         const int kz = draw_junction(ci, fj, civ);
         __syncwarp();
         condition_on(ci, fj, kz);
-        for (int t = 0; t < civ->nn; t++) condition_on(civ->nb[t], fj, kz);
+        for (int t = 0; t < civ->nn; t++) condition_on(nbl(civ, t), fj, kz);
         __syncwarp();
         KGW_FAM_PHASE(3);
       }
@@ -785,8 +842,8 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     for (int i = 0; i < n; i++) {
       const KgwFamInterval *iv = P.ivs + ivs0[i];
       int ivj1 = iv->j1, ivnn = iv->nn;
-      unsigned nbpack = 0;
-      for (int t = 0; t < ivnn; t++) nbpack |= (unsigned)iv->nb[t] << (3 * t);
+      unsigned nbpack = 0;   // SMALL class: the neighbour list of the current interval, 3 bits each
+      if (!BIG) for (int t = 0; t < ivnn; t++) nbpack |= (unsigned)nbl(iv, t) << (3 * t);
       const uint8_t *zrow = Zb + (size_t)i * p;
       const double *mlrow = ml_base + (size_t)i * pK;
       const uint8_t *ptrow = pat_base + (size_t)i * pK;
@@ -829,7 +886,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
               ivj1 = iv->j1;
               ivnn = iv->nn;
               nbpack = 0;
-              for (int t = 0; t < ivnn; t++) nbpack |= (unsigned)iv->nb[t] << (3 * t);
+              if (!BIG) for (int t = 0; t < ivnn; t++) nbpack |= (unsigned)nbl(iv, t) << (3 * t);
             }
             double wv[SF];
 #pragma unroll
@@ -837,7 +894,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
               const int k = lane * SF + s;
               wv[s] = 0.0;
               if (k < K) {
-                double v = emission_of(pt_c[s], j, ivnn);
+                double v = emission_at(pt_c[s], i, iv, ivnn, j, k);
                 if (j > 0) v *= la_c + lb_c * (double)(k == zprev);
                 if (j < p - 1) v *= ml_c[s];
                 wv[s] = v;
@@ -846,7 +903,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
             const int kz = warp_choice_contig<SF>(wv, __shfl_sync(FULL, uw, q), K, lane);
             if (lane == 0) {
               Zb[(size_t)i * p + j] = (uint8_t)kz;
-              for (int t = 0; t < ivnn; t++) Zb[(size_t)((nbpack >> (3 * t)) & 7u) * p + j] = (uint8_t)kz;
+              for (int t = 0; t < ivnn; t++) Zb[(size_t)(BIG ? nbl(iv, t) : (int)((nbpack >> (3 * t)) & 7u)) * p + j] = (uint8_t)kz;
             }
             zprev = kz;
           }
@@ -960,7 +1017,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
       for (; iv < P.ivs + ivs0[i + 1]; iv++) {
         for (int t = 0; t < iv->nn; t++)
           for (int j = iv->j0 + lane; j <= iv->j1; j += 32)
-            if (Zkb[(size_t)i * p + j] != Zkb[(size_t)iv->nb[t] * p + j]) bad |= 2;
+            if (Zkb[(size_t)i * p + j] != Zkb[(size_t)nbl(iv, t) * p + j]) bad |= 2;
       }
     }
     bad = __reduce_or_sync(FULL, bad);

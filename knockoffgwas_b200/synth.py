@@ -271,3 +271,57 @@ def add_ibd_families(prob: SynthProblem, n_families: int, size: int = 3, segment
         fams.append((mem, segs))
     prob.families = fams
     return prob
+
+
+def add_big_family(prob: SynthProblem, size: int, segments: int, max_subset: int = 12, seed: int = 13,
+                   min_len_bp: int = 100_000) -> SynthProblem:
+    """One IBD family of `size` haplotypes (different samples) with `segments` disjoint segments.  Every member has a
+    home segment (so that all of them are linked), segments then take random extra members up to `max_subset`: nodes
+    with many neighbours, members joining and leaving at every boundary -- the shapes union-find over RaPID pairs
+    produces on biobank data (metadata.cpp:242-293).  Segments neither overlap nor touch, are at least `min_len_bp`
+    long and are listed in IbdSeg order (fewer indices first, then index set, then j_min; ibd.cpp:482-509)."""
+    rng = np.random.default_rng([prob.seed, seed, size, segments])
+    N, p = prob.N, prob.p
+    taken = {int(x) for m, _ in prob.families for x in m}
+    free_samples = [s for s in rng.permutation(N // 2) if 2 * s not in taken and 2 * s + 1 not in taken]
+    if len(free_samples) < size:
+        raise ValueError("not enough unrelated samples left")
+    mem = np.sort(np.array([2 * free_samples[t] + int(rng.integers(2)) for t in range(size)], dtype=np.int32))
+    home = np.array_split(rng.permutation(mem), segments)
+    for _ in range(200):
+        cuts = np.sort(rng.choice(np.arange(2, p - 2), size=2 * segments, replace=False))
+        ok = all(cuts[2 * q + 1] - 1 - (cuts[2 * q] + 1) >= 3 and prob.bp[cuts[2 * q + 1] - 1] - prob.bp[cuts[2 * q] + 1] >= min_len_bp
+                 for q in range(segments))
+        if ok:
+            break
+    else:
+        raise ValueError("could not place the segments: chromosome too short for min_len_bp")
+    segs = []
+    for q in range(segments):
+        j0, j1 = int(cuts[2 * q]) + 1, int(cuts[2 * q + 1]) - 1
+        ids = set(int(x) for x in home[q])
+        extra = int(rng.integers(0, max(1, max_subset - len(ids) + 1)))
+        others = [int(x) for x in rng.permutation(mem) if int(x) not in ids][:extra]
+        ids |= set(others)
+        if len(ids) < 2:
+            ids.add(int(next(x for x in mem if int(x) not in ids)))
+        ids = np.array(sorted(ids), dtype=np.int32)
+        src = np.unpackbits(prob.H[ids[0]], bitorder="little")
+        for other in ids[1:]:
+            row = np.unpackbits(prob.H[other], bitorder="little")
+            row[j0:j1 + 1] = src[j0:j1 + 1]
+            prob.H[other] = np.packbits(row, bitorder="little")
+        segs.append((j0, j1, ids))
+    segs.sort(key=lambda sg: (len(sg[2]), tuple(int(x) for x in sg[2]), sg[0]))
+    memset = set(int(x) for x in mem)
+    for me in mem:                                      # relatives are never references
+        bad = [t for t in range(prob.ref.shape[1]) if int(prob.ref[me, t]) in memset]
+        for t in bad:
+            cand = int(me)
+            while cand in memset or cand in prob.ref[me]:
+                cand = int(rng.integers(0, N))
+            prob.ref[me, t] = cand
+        if bad:
+            prob.ref[me].sort()
+    prob.families = list(prob.families) + [(mem, segs)]
+    return prob

@@ -90,6 +90,10 @@ def test_argument_validation_precedes_device_probe(lib):
     with pytest.raises(kg.KgwError) as ei:  # row_bytes < ceil(p/8)
         kg.generate(prob.H[:, :3], prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups)
     assert ei.value.code == -1
+    big = synthetic_problem(N=300, p=16, K=257, seed=2)
+    with pytest.raises(kg.KgwError) as ei:  # the stated bound on K (include/kgw.h)
+        kg.generate(big.H, big.p, big.K, big.ref_local, big.b, big.mu, big.groups)
+    assert ei.value.code == -2 and "K > 256" in str(ei.value)
     bad_ref = prob.ref_local.copy()
     bad_ref[3, 0, 1] = 99
     with pytest.raises(kg.KgwError) as ei:

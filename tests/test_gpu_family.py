@@ -86,6 +86,12 @@ def test_family_errors():
     with pytest.raises(kg.KgwError, match="also listed in `unrelated`"):   # the two branches would write the same rows
         kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, ref_global=prob.ref_global,
                     families=fam, unrelated=np.arange(prob.N, dtype=np.int32))
+    from kgw_testutil import synthetic_problem
+    wide = synthetic_problem(N=300, p=40, K=256, seed=3)   # K = 256 runs for unrelated haplotypes but not with families
+    with pytest.raises(kg.KgwError, match="K > 255"):
+        kg.generate(wide.H, wide.p, wide.K, wide.ref_local, wide.b, wide.mu, wide.groups, ref_global=wide.ref_global,
+                    unrelated=np.arange(4, 300, dtype=np.int32),
+                    families=[(np.array([0, 2], np.int32), [(5, 30, np.array([0, 2], np.int32))])])
     with pytest.raises(kg.KgwError, match="two families"):
         kg.generate(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups, ref_global=prob.ref_global,
                     families=fam + fam[:1], unrelated=np.zeros(0, np.int32))
@@ -169,3 +175,40 @@ def test_family_kernel_segment_edge_cases(segs):
     rng, _ = ko.make_rng(prob, mode="philox")
     r = ko.run_family(prob, ids, [(j0, j1, 0, 0, ids) for j0, j1 in segs], rng)
     assert np.array_equal(dbg.fam_z, r.z) and np.array_equal(dbg.fam_zk, r.zk) and np.array_equal(hk[ids], r.hk)
+
+
+@pytest.mark.parametrize("size,segments,p,K,max_subset,uniform_mu", [
+    (12, 6, 1200, 20, 9, True),        # more than 8 members, nodes with up to 8 neighbours
+    (32, 10, 1000, 12, 10, True),
+    (100, 20, 800, 8, 12, True),       # a family as union-find over RaPID pairs builds them on biobank data
+    (20, 8, 900, 40, 12, False),       # per-locus mutation rates (--hmm file): emissions formed with pow() on the device
+])
+def test_family_kernel_large_families(size, segments, p, K, max_subset, uniform_mu):
+    """Families beyond the small class of the kernel (more than 8 haplotypes, nodes with more than 7 IBD neighbours): the
+    reference has no limit (family_bp.cpp:41-61 pushes neighbours without bound, knockoffs.cpp:329-372 takes any family).
+    One big family and a few pairs in the same call (both compiled classes launch), against the oracle."""
+    from knockoffgwas_b200 import synth
+    sp = synth.make_problem_fast(600, p, K, seed=71, n_founders=60, mean_dist_cm=0.05, mean_group=2.0)
+    if not uniform_mu:
+        sp.mu = np.random.default_rng(3).uniform(1e-6, 1e-3, size=p)
+    synth.add_ibd_pairs(sp, 5)
+    synth.add_big_family(sp, size, segments, max_subset=max_subset)
+    mem, segs = sp.families[-1]
+    assert len(mem) == size and (size > 8 or max(len(s[2]) for s in segs) > 8)
+    prob = ko.Problem(H=sp.H, p=sp.p, K=K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu,
+                      groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
+    plan = kg.Plan(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=np.zeros(0, np.int32), ref_global=sp.ref,
+                   seed=sp.seed, families=sp.families)
+    assert plan.info()["launches_per_run"] == 2
+    plan.run()
+    hk, dbg = plan.download(debug_paths=True)
+    plan.close()
+    rng, _ = ko.make_rng(prob, mode="philox")
+    row = 0
+    for m, sl in sp.families:
+        r = ko.run_family(prob, m, [(s[0], s[1], 0, 0, s[2]) for s in sl], rng)
+        n = len(m)
+        assert np.array_equal(dbg.fam_z[row:row + n], r.z), f"Z of the family of {n}"
+        assert np.array_equal(dbg.fam_zk[row:row + n], r.zk), f"Zk of the family of {n}"
+        assert np.array_equal(hk[m], r.hk), f"Hk of the family of {n}"
+        row += n
