@@ -278,7 +278,7 @@ def leg_c3_shard(torch, kg, synth, dev, stream, flush, a):
     north-star target (>= 50 % of the HBM roofline per GPU) is quoted on."""
     N, p, K = 87500, 60000, 50
     prob = synth.make_problem_fast(N, p, K, seed=2021, rho=RHO, lam=LAMBDA)
-    opts = kg.Options(device=dev.index, stream=stream.cuda_stream)
+    opts = kg.Options(device=dev.index, stream=stream.cuda_stream, lanes_per_hap=a.lanes, block_loci=a.block_loci)
     plan = kg.Plan(prob.H, p, K, prob.ref[:, None, :], prob.b, prob.mu, prob.groups, seed=prob.seed, options=opts)
     info = plan.info()
     total_ms, kern, clocks = timed_runs(torch, plan, stream, dev, 3, 1, flush)

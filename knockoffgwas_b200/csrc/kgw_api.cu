@@ -352,6 +352,7 @@ struct FamilyState {
   KgwFamLocus *dloc = nullptr;
   KgwLocusKO *dko = nullptr;
   double *demtab = nullptr;
+  size_t cap_ops = 0, cap_gfirst = 0, cap_glast = 0;   // bytes behind dops / dgfirst / dglast (grow-only)
   int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
   std::vector<KgwFamDesc> fams;                   // op_off / n_ops are refreshed by set_groups
   KgwFamParams P{};
@@ -619,21 +620,29 @@ int fam_upload_partition(kgw_plan *pl, const int32_t *groups) {
     F->fams[f].n_ops = (int)ops.size() - F->fams[f].op_off;
   }
   std::vector<int32_t> gf(gfirst.begin(), gfirst.end()), gl(glast.begin(), glast.end());
+  // grow-only device buffers (a plan sees one partition after the other, main.cpp:159-181) and copies on the
+  // plan's stream; one synchronisation at the end because the host vectors go out of scope
+  auto grow = [&](auto **ptr, size_t *cap, size_t need) -> cudaError_t {
+    if (need <= *cap && *ptr) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(pl->stream);   // a launch in flight may still read the old buffer
+    if (e != cudaSuccess) return e;
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = need + need / 4 + 64;
+    return kgw_malloc(ptr, *cap);
+  };
+  KGW_CUDA(grow(&F->dops, &F->cap_ops, sizeof(KgwFamOp) * std::max<size_t>(ops.size(), 1)));
+  KGW_CUDA(grow(&F->dgfirst, &F->cap_gfirst, sizeof(int32_t) * G));
+  KGW_CUDA(grow(&F->dglast, &F->cap_glast, sizeof(int32_t) * G));
+  if (!F->dko) KGW_CUDA(kgw_malloc(&F->dko, sizeof(KgwLocusKO) * p));
+  if (!F->dgroups) KGW_CUDA(kgw_malloc(&F->dgroups, sizeof(int32_t) * p));
+  KGW_CUDA(cudaMemcpyAsync(F->dops, ops.data(), sizeof(KgwFamOp) * ops.size(), cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA(cudaMemcpyAsync(F->dgfirst, gf.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA(cudaMemcpyAsync(F->dglast, gl.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA(cudaMemcpyAsync(F->dko, T.ko.data(), sizeof(KgwLocusKO) * p, cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA(cudaMemcpyAsync(F->dgroups, groups, sizeof(int32_t) * p, cudaMemcpyHostToDevice, pl->stream));
+  KGW_CUDA(cudaMemcpyAsync(F->dfams, F->fams.data(), sizeof(KgwFamDesc) * F->n_families, cudaMemcpyHostToDevice, pl->stream));
   KGW_CUDA(cudaStreamSynchronize(pl->stream));
-  cudaFree(F->dops); F->dops = nullptr;
-  cudaFree(F->dgfirst); F->dgfirst = nullptr;
-  cudaFree(F->dglast); F->dglast = nullptr;
-  KGW_CUDA(cudaMalloc(&F->dops, sizeof(KgwFamOp) * std::max<size_t>(ops.size(), 1)));
-  KGW_CUDA(cudaMalloc(&F->dgfirst, sizeof(int32_t) * G));
-  KGW_CUDA(cudaMalloc(&F->dglast, sizeof(int32_t) * G));
-  if (!F->dko) KGW_CUDA(cudaMalloc(&F->dko, sizeof(KgwLocusKO) * p));
-  if (!F->dgroups) KGW_CUDA(cudaMalloc(&F->dgroups, sizeof(int32_t) * p));
-  KGW_CUDA(cudaMemcpy(F->dops, ops.data(), sizeof(KgwFamOp) * ops.size(), cudaMemcpyHostToDevice));
-  KGW_CUDA(cudaMemcpy(F->dgfirst, gf.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice));
-  KGW_CUDA(cudaMemcpy(F->dglast, gl.data(), sizeof(int32_t) * G, cudaMemcpyHostToDevice));
-  KGW_CUDA(cudaMemcpy(F->dko, T.ko.data(), sizeof(KgwLocusKO) * p, cudaMemcpyHostToDevice));
-  KGW_CUDA(cudaMemcpy(F->dgroups, groups, sizeof(int32_t) * p, cudaMemcpyHostToDevice));
-  KGW_CUDA(cudaMemcpy(F->dfams, F->fams.data(), sizeof(KgwFamDesc) * F->n_families, cudaMemcpyHostToDevice));
   F->P.ops = F->dops; F->P.grp_first = F->dgfirst; F->P.grp_last = F->dglast; F->P.ko = F->dko;
   F->P.groups = F->dgroups; F->P.n_groups = G;
   return KGW_OK;
@@ -1253,55 +1262,77 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   KGW_CUDA_PL(cudaMemGetInfo(&free_b, &total_b));
   free_b += g_pool.parked(pl->device);   // parked buffers are either taken back or released by pool_alloc
   const size_t hw_bytes_est = 2 * (size_t)N * (((size_t)prob->row_bytes + 15) / 16 * 16) + sizeof(int32_t) * (size_t)N * W * K;
-  const KgwVariant *var = pick_variant(K, o.lanes_per_hap, B);
+  // Variant (lanes per haplotype, states per lane), compiled form and CTA shape: the candidate with the lowest
+  // modelled time.  Each form is compiled twice -- `fn` for the densest residency (12 or 16 warps per SM, 168 / 128
+  // registers) and `fn_wide` for 8 warps per SM with the full register budget -- and K in (32, 50] can also run with
+  // ONE lane per haplotype (50 states per lane, 32 haplotypes per warp, no lane of a haplotype repeating the draw
+  // logic of another: 62 instead of 76 warp instructions per haplotype-SNP, but 40 KB of shared memory per warp).
+  // Model: rounds x time of a warp, where rounds = ceil(batches / resident warps) and the time of a warp grows with
+  // the number of warps that share its scheduler (measured on B200 at K = 50, ms per 10 000 loci):
+  //   two lanes, wide   20.0 alone, 28.2 with a second warp      two lanes, dense   31.6 (two), 38.4 (three)
+  //   one lane          26.7 alone, 35.5 with a second warp
+  // The one-lane form is only taken when every batch is resident at once (its residency is a third of the others').
+  struct Choice { const KgwVariant *var; kgw_kernel_fn fn; size_t smem_warp; int wpc, occ; double cost; };
+  auto evaluate = [&](const KgwVariant *v, bool one_round_only, Choice *best) -> cudaError_t {
+    const int Gv = 32 / v->L;
+    const int n_tasks = (pl->n_haps + Gv - 1) / Gv;
+    const char *force = getenv("KGW_FORCE_WIDE");   // development: "0" / "1"
+    for (int form = 0; form < 2; form++) {
+      kgw_kernel_fn fn = form ? v->fn_wide : v->fn;
+      const size_t smem_warp = form ? v->smem_warp_wide : v->smem_warp;
+      if (form == 1 && v->fn_wide == v->fn) continue;
+      if (force && v->fn_wide != v->fn && (force[0] == '1') != (form == 1)) continue;
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_warp * v->max_wpc));
+      if (e != cudaSuccess) return e;
+      // single-warp CTAs spread a partial wave most evenly over the SMs; CTAs of max_wpc warps fit more warps per SM
+      // (the 1 KB per-CTA shared-memory reservation is paid once) and are used when the single-warp grid cannot hold
+      // every haplotype batch at once
+      int wpc = 1, occ = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smem_warp);
+      if (e != cudaSuccess) return e;
+      if (occ * dp.multiProcessorCount < n_tasks && v->max_wpc > 1) {
+        int occ2 = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, 32 * v->max_wpc, smem_warp * v->max_wpc);
+        if (e != cudaSuccess) return e;
+        if (occ2 * v->max_wpc > occ) { wpc = v->max_wpc; occ = occ2; }
+      }
+      if (occ <= 0) continue;
+      if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
+      const double slots = (double)occ * wpc * dp.multiProcessorCount;
+      const double rounds = std::ceil(n_tasks / slots);
+      if (one_round_only && rounds > 1.0) continue;
+      const double per_sm = std::min<double>(n_tasks, slots) / dp.multiProcessorCount;
+      const double w = std::max(1.0, std::ceil(per_sm / 4.0));          // warps sharing the busiest scheduler
+      const bool wide_regs = (form == 1) || (v->fn_wide == v->fn);
+      const double t1 = (v->L == 1 && v->S > 32) ? 26.7 : (wide_regs ? 20.0 : 24.8);
+      const double al = (v->L == 1 && v->S > 32) ? 0.33 : (wide_regs ? 0.41 : 0.274);
+      const double cost = rounds * t1 * (1.0 + al * (w - 1.0));
+      if (!best->var || cost < best->cost) *best = Choice{v, fn, smem_warp, wpc, occ, cost};
+    }
+    return cudaSuccess;
+  };
+  Choice ch{nullptr, nullptr, 0, 1, 0, 0.0};
+  KGW_CUDA_PL(evaluate(pick_variant(K, o.lanes_per_hap, B), false, &ch));
+  if (o.lanes_per_hap == 0 && K > 32 && K <= 50) {
+    const KgwVariant *v1 = pick_variant(K, 1, B);
+    if (v1) KGW_CUDA_PL(evaluate(v1, true, &ch));
+  }
+  if (!ch.var) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
+  const KgwVariant *var = ch.var;
   const int G = 32 / var->L;
   const size_t p32 = ((size_t)p + 31) / 32 * 32;
   const size_t SPR = (size_t)(var->S + 1) / 2 * 2, SPW = (size_t)(var->S + 3) / 4 * 4;
   const size_t ROW = (size_t)var->L * SPR * G, TILE = (size_t)var->L * SPW * G;
+  const size_t CSW = (var->S <= 32 ? 4 : 8) * 32;   // partial sums per locus and warp (kgw::Cfg::CSW)
   size_t slots = 0;
   {
-    // Two compiled forms of the kernel: `fn` for the densest residency (12 or 16 warps per SM, 168 / 128
-    // registers) and `fn_wide` for 8 warps per SM with 255 registers, whose warps finish a batch in about 0.65
-    // of the time (measured, K = 50).  Pick the form with the lower modelled time: waves x time per batch.
-    // CTA shape: single-warp CTAs spread a partial wave most evenly over the SMs; CTAs of max_wpc warps fit more
-    // warps per SM (the 1 KB per-CTA shared-memory reservation is paid once) and are used when the single-warp
-    // grid cannot hold every haplotype batch at once.
     const int n_tasks = (pl->n_haps + G - 1) / G;
-    auto shape = [&](kgw_kernel_fn fn, size_t smem_warp, int *wpc_out, int *occ_out) -> cudaError_t {
-      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_warp * var->max_wpc));
-      if (e != cudaSuccess) return e;
-      int wpc = 1, occ = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, smem_warp);
-      if (e != cudaSuccess) return e;
-      if (occ * dp.multiProcessorCount < n_tasks && var->max_wpc > 1) {
-        int occ2 = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, 32 * var->max_wpc, smem_warp * var->max_wpc);
-        if (e != cudaSuccess) return e;
-        if (occ2 * var->max_wpc > occ) { wpc = var->max_wpc; occ = occ2; }
-      }
-      *wpc_out = wpc; *occ_out = occ;
-      return cudaSuccess;
-    };
-    int wpc = 1, occ = 0, wpc_w = 1, occ_w = 0;
-    KGW_CUDA_PL(shape(var->fn, var->smem_warp, &wpc, &occ));
-    if (occ <= 0) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
-    pl->fn = var->fn;
-    size_t smem_warp = var->smem_warp;
-    if (var->fn_wide != var->fn) {
-      KGW_CUDA_PL(shape(var->fn_wide, var->smem_warp_wide, &wpc_w, &occ_w));
-      const char *force = getenv("KGW_FORCE_WIDE");   // development: "0" / "1"
-      if (occ_w > 0) {
-        const double slots_d = (double)occ * wpc * dp.multiProcessorCount, slots_w = (double)occ_w * wpc_w * dp.multiProcessorCount;
-        const double cost_d = std::ceil(n_tasks / slots_d) * 1.0, cost_w = std::ceil(n_tasks / slots_w) * 0.65;
-        const bool wide = force ? (force[0] == '1') : (cost_w < cost_d);
-        if (wide) { pl->fn = var->fn_wide; wpc = wpc_w; occ = occ_w; smem_warp = var->smem_warp_wide; }
-      }
-    }
-    if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
-    const int grid = std::max(1, std::min(occ * dp.multiProcessorCount, (n_tasks + wpc - 1) / wpc));
+    const int wpc = ch.wpc;
+    const int grid = std::max(1, std::min(ch.occ * dp.multiProcessorCount, (n_tasks + wpc - 1) / wpc));
     slots = (size_t)grid * wpc;
+    pl->fn = ch.fn;
     pl->threads = 32 * wpc;
-    pl->smem = smem_warp * wpc;
+    pl->smem = ch.smem_warp * wpc;
     pl->var = var; pl->B = B; pl->G = G; pl->n_tasks = n_tasks; pl->grid = grid;
     pl->nblk = (int)((p + B - 1) / B);
   }
@@ -1310,7 +1341,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   const size_t fixed_slot = up(sizeof(uint32_t) * (size_t)pl->stride_w * TILE) + 2 * up(p32 * G);
   auto seg_slot = [&](size_t ps) {   // rows every B loci, partial sums, totals, segment-top rows
     const size_t nseg = (p32 + ps - 1) / ps;
-    return up(sizeof(double) * (ps / B) * ROW) + up(sizeof(double) * ps * 128) + up(sizeof(double) * ps * G) +
+    return up(sizeof(double) * (ps / B) * ROW) + up(sizeof(double) * ps * CSW) + up(sizeof(double) * ps * G) +
            up(sizeof(double) * (nseg > 1 ? nseg : 1) * ROW);
   };
   size_t PS = p32;
@@ -1354,7 +1385,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   // scratch, one slot per resident warp
   const size_t mw_stride = up(sizeof(uint32_t) * (size_t)pl->stride_w * TILE) / sizeof(uint32_t);
   const size_t ckpt_stride = up(sizeof(double) * (PS / B) * ROW) / sizeof(double);
-  const size_t cs_stride = up(sizeof(double) * PS * 128) / sizeof(double);
+  const size_t cs_stride = up(sizeof(double) * PS * CSW) / sizeof(double);
   const size_t se_stride = up(sizeof(double) * PS * G) / sizeof(double);
   const size_t segck_stride = up(sizeof(double) * (pl->nseg > 1 ? pl->nseg : 1) * ROW) / sizeof(double);
   const size_t z_stride = up(p32 * G);

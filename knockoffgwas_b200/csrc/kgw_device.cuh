@@ -95,7 +95,7 @@ struct KgwParams {
   unsigned long long ckpt_stride;
   double *segck;             // [slots][nseg][ROW]              message rows at segment tops (sweep 0)
   unsigned long long segck_stride;
-  double *csbuf;             // [slots][seg_loci][2][32][2]     partial sums of sweep 1
+  double *csbuf;             // [slots][seg_loci][NC/2][32][2]  partial sums of sweep 1 (NC chunks per lane)
   unsigned long long cs_stride;
   double *sebuf;             // [slots][seg_loci][G]            locus totals of sweep 1
   unsigned long long se_stride;
@@ -294,8 +294,10 @@ struct Cfg {
   static constexpr int SPW = (S + 3) / 4 * 4;   // state slots per lane in a match-word tile
   static constexpr int NQ = SPW / 4;            // 16-byte units of a lane in a match-word tile
   static constexpr int NP = SPR / 2;            // 16-byte units of a lane in a message row
-  static constexpr int CS = S <= 16 ? 4 : 8;    // states per chunk (4 chunks per lane)
-  static constexpr int NC = 4;
+  static constexpr int CS = S <= 16 ? 4 : 8;    // states per chunk
+  static constexpr int NC = S <= 32 ? 4 : 8;    // chunks per lane (a lane holds at most 64 states)
+  static_assert(S <= 64, "at most 64 states per lane");
+  static constexpr int CSW = NC * 32;           // partial sums per locus and warp: [NC/2][32 lanes][2]
   static constexpr int ROW = L * SPR * G;       // doubles per message row
   static constexpr int TILE = L * SPW * G;      // 32-bit words per match-word tile
   // per-warp shared memory: two message rows (sweep 2: staged top rows of two blocks; sweep 3: the
@@ -305,7 +307,7 @@ struct Cfg {
   static constexpr size_t s3_bytes = (size_t)ROW * 8 + 4 * 32 * G + 32 * sizeof(KgwLocusKO);
   static constexpr size_t rows_bytes = (size_t)2 * ROW * 8 > s3_bytes ? (size_t)2 * ROW * 8 : s3_bytes;
   static constexpr size_t tiles_bytes = (size_t)TILE * 4;
-  static constexpr size_t ring_bytes = (size_t)D * 1024;
+  static constexpr size_t ring_bytes = (size_t)D * CSW * 8;
   static constexpr size_t blk_bytes = (size_t)2 * ((size_t)B * G * 8 + (size_t)B * 16);
   static constexpr size_t bar_bytes = 128;
   __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + tiles_bytes + ring_bytes + blk_bytes + bar_bytes; }
@@ -356,6 +358,17 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
   constexpr int G = C::G;
   constexpr int SPR = C::SPR, SPW = C::SPW, NQ = C::NQ, NP = C::NP, CS = C::CS, NC = C::NC, ROW = C::ROW, TILE = C::TILE;
   constexpr int NCT = L * NC;  // chunks per haplotype
+  constexpr int CSW = C::CSW;  // partial sums per locus and warp
+  auto chunk_total = [](const double (&cs)[NC]) {   // balanced tree over the chunk sums of a lane
+    double t[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) t[c] = cs[c];
+#pragma unroll
+    for (int w = NC / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int c = 0; c < w; c++) t[c] = t[2 * c] + t[2 * c + 1];
+    return t[0];
+  };
   static_assert(RESCALE % B == 0 && 32 % B == 0, "blocks must not straddle words or rescale points");
   const int lane = threadIdx.x & 31;
   const int g = lane % G;
@@ -543,12 +556,12 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
             beta[s] = e;
             cs[s / CS] += e;
           }
-          const double pl = (cs[0] + cs[1]) + (cs[2] + cs[3]);
+          const double pl = chunk_total(cs);
           const double Se = group_sum<L>(pl);
           if (fullstore) {
-            double2 *d = reinterpret_cast<double2 *>(csb + (size_t)(m - seg0) * 128);
-            st_cg(d + lane, cs[0], cs[1]);
-            st_cg(d + 32 + lane, cs[2], cs[3]);
+            double2 *d = reinterpret_cast<double2 *>(csb + (size_t)(m - seg0) * CSW);
+#pragma unroll
+            for (int h = 0; h < NC / 2; h++) st_cg(d + h * 32 + lane, cs[2 * h], cs[2 * h + 1]);
             if (lig == 0) st_cg(seb + (size_t)(m - seg0) * G + g, Se);
           }
           if (m == lo_m) break;
@@ -654,8 +667,8 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
           auto stage_locus = [&](int j) {
             if (lane == 0) {
               unsigned long long *bar = bars + BAR_CS + (j % D);
-              mbar_expect_tx(bar, 1024);
-              bulk_g2s(ring + (j % D) * 128, csb + (size_t)(j - seg0) * 128, 1024, bar);
+              mbar_expect_tx(bar, CSW * 8);
+              bulk_g2s(ring + (j % D) * CSW, csb + (size_t)(j - seg0) * CSW, CSW * 8, bar);
             }
           };
           auto stage_tile2 = [&](int w) {
@@ -717,12 +730,14 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               // partial sums of this locus: the L lanes of the haplotype, four chunks each
               double csv[NCT];
               {
-                const double2 *slot = reinterpret_cast<const double2 *>(ring + (j % D) * 128);
+                const double2 *slot = reinterpret_cast<const double2 *>(ring + (j % D) * CSW);
 #pragma unroll
                 for (int lg = 0; lg < L; lg++) {
-                  const double2 t0 = slot[lg * G + g];
-                  const double2 t1 = slot[32 + lg * G + g];
-                  csv[lg * NC + 0] = t0.x; csv[lg * NC + 1] = t0.y; csv[lg * NC + 2] = t1.x; csv[lg * NC + 3] = t1.y;
+#pragma unroll
+                  for (int h = 0; h < NC / 2; h++) {
+                    const double2 t = slot[h * 32 + lg * G + g];
+                    csv[lg * NC + 2 * h] = t.x; csv[lg * NC + 2 * h + 1] = t.y;
+                  }
                 }
               }
               const double u = usz.get(j);
@@ -935,7 +950,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               }
               KGW_PH(7);   // sweep 3: specials
               double Sr;
-              const double base0 = group_total_excl<L>((cs[0] + cs[1]) + (cs[2] + cs[3]), lane, Sr);
+              const double base0 = group_total_excl<L>(chunk_total(cs), lane, Sr);
               const double Nsum = (k.flags & KGW_KO_GSTART) ? k.sa : k.tg * Sr;  // :1345-1358
               const double c2 = k.vb * Nsum;
               // pass B: partition function update, normalised (:1360-1390).  The last group keeps N (zero

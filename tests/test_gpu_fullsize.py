@@ -22,8 +22,9 @@ def workload():
     return synth.make_problem(N, P, K, seed=2020, mean_group=1.0, rho=1.0, lam=1e-3, hap_seed=0)
 
 
-def _run(sp, unrelated=None):
-    plan = kg.Plan(sp.H, sp.p, sp.K, sp.ref[:, None, :], sp.b, sp.mu, sp.groups, seed=sp.seed, unrelated=unrelated)
+def _run(sp, unrelated=None, lanes=0):
+    plan = kg.Plan(sp.H, sp.p, sp.K, sp.ref[:, None, :], sp.b, sp.mu, sp.groups, seed=sp.seed, unrelated=unrelated,
+                   options=kg.Options(lanes_per_hap=lanes))
     plan.run()
     hk, _ = plan.download()
     info = plan.info()
@@ -34,14 +35,17 @@ def _run(sp, unrelated=None):
 def test_full_size_rows_match_oracle_and_forms_agree(workload, monkeypatch):
     sp = workload
     monkeypatch.setenv("KGW_FORCE_WIDE", "0")
-    dense, info = _run(sp)
+    dense, info = _run(sp, lanes=2)
     assert info["lanes_per_hap"] == 2 and info["states_per_lane"] == 25
-    again, _ = _run(sp)
+    again, _ = _run(sp, lanes=2)
     assert np.array_equal(dense, again), "two runs of the same plan input differ"
     monkeypatch.setenv("KGW_FORCE_WIDE", "1")
-    wide, _ = _run(sp)
+    wide, _ = _run(sp, lanes=2)
     assert np.array_equal(dense, wide), "dense and wide forms of the sampler kernel differ"
     monkeypatch.delenv("KGW_FORCE_WIDE")
+    auto, info = _run(sp)   # what the library picks for this shape: one lane per haplotype, every batch resident at once
+    assert info["lanes_per_hap"] == 1 and info["states_per_lane"] == 50
+    assert np.array_equal(dense, auto), "the one-lane and two-lane layouts of the sampler kernel differ"
 
     rows = np.array([0, 1, 15, 16, 17, 31, 32, 4999, 5000, 9471, 9472, 12345, 18943, 18944, 19983, 19984, 19998, 19999], dtype=np.int32)
     prob = ko.Problem(H=sp.H, p=P, K=K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu, groups=sp.groups,

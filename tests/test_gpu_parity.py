@@ -71,6 +71,9 @@ CASES = [
     dict(N=90, p=200, K=50, mean_group=1.0, lanes=8, block=2),
     dict(N=90, p=230, K=50, mean_group=4.0, lanes=2, block=8),
     dict(N=70, p=200, K=25, mean_group=1.0, lanes=1),
+    dict(N=90, p=260, K=50, mean_group=1.0, lanes=1),             # one lane per haplotype, 50 states, eight chunks
+    dict(N=90, p=230, K=50, mean_group=4.0, lanes=1, block=8),
+    dict(N=70, p=200, K=41, mean_group=2.0, lanes=1),             # padded: 41 of 50 states
     dict(N=70, p=200, K=32, mean_group=3.0, lanes=1, block=8),
     dict(N=33, p=70, K=10, mean_group=1.0, lanes=1),
     dict(N=33, p=70, K=10, mean_group=2.0, lanes=8),
