@@ -256,6 +256,23 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
 int32_t kgw_haps_read(const uint8_t *text, int64_t text_bytes, int32_t n_samples, const int32_t *sample_idx, int32_t p,
                       const int32_t *row_of_col, int32_t device, int64_t row_bytes, uint8_t *H_out, float *kernel_ms);
 
+/* ---- `--estimate-hmm` ---------------------------------------------------------
+ * Replaces Knockoffs::EM (knockoffs.cpp:706-748 -> EM_step :830-960 -> EM_worker :750-828), called from main.cpp
+ * when --estimate-hmm is given, after init_hmm(K, rho) (:1527-1548).  As the reference stands only the mutation
+ * rates are re-estimated (new_rho = rho, :929-930): per step and haplotype the backward and forward messages over
+ * the local references of every window pass, the posterior marginals, the expected mismatches gamma_j; then
+ * mu_j = clamp(mean gamma_j, 1e-6, 1e-3); at most 20 steps, stopping when the root mean square relative change
+ * falls below 5e-2.  Reads prob->H, ref_local, b, the windows (groups / mu / unrelated / families are ignored: every
+ * haplotype takes part, :862-864).
+ *   mu_init [p]   the rates to start from (init_hmm leaves 1e-5 everywhere, see oracle/kgw_oracle.c)
+ *   mu_out  [p]   the rates after the last step (what update_hmm, :1550-1561, installs)
+ *   iterations    steps run;  deltas [20] (may be NULL): the change printed per step (:724-728)
+ * Returns KGW_OK when converged, 1 when 20 steps did not converge (the reference warns and goes on, :739-748),
+ * negative on error.  Floating-point sums over haplotypes are order dependent at the last bits: results agree
+ * with the reference to ~1e-12 relative, not bit for bit. */
+int32_t kgw_estimate_hmm(const kgw_problem *prob, const kgw_options *opt, const double *mu_init, double *mu_out,
+                         int32_t *iterations, double *deltas);
+
 /* A destroyed plan parks its scratch slab (tens of GB) for the next plan on the same device, because
  * Knockoffs::generate() runs once per resolution (main.cpp:159-181); this frees the parked slabs. */
 void kgw_release_workspace(void);

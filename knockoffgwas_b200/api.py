@@ -100,6 +100,8 @@ def load_library():
         L = C.CDLL(str(pth))
         L.kgw_abi_version.restype = C.c_int32
         L.kgw_device_count.restype = C.c_int32
+        L.kgw_estimate_hmm.restype = C.c_int32
+        L.kgw_estimate_hmm.argtypes = [C.POINTER(_Problem), C.POINTER(_Options), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
         L.kgw_partition_work.restype = C.c_int32
         L.kgw_partition_work.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.kgw_last_error.restype = C.c_char_p
@@ -323,6 +325,24 @@ def generate_into(H, p, K, ref_local, b, mu, groups, *, out, win_start=None, win
     o = (options or Options())._c()
     _check(L.kgw_generate(C.byref(P), C.byref(o), out.ctypes.data, None))
     return out
+
+
+def estimate_hmm(H, p, K, ref_local, b, *, mu_init=None, win_start=None, win_end=None, options: Options | None = None):
+    """kgw_estimate_hmm (Knockoffs::EM, knockoffs.cpp:706-960): returns (mu after EM, steps run, per-step deltas, converged)."""
+    L = load_library()
+    p = int(p)
+    held = _Held(H, p, K, ref_local, b, np.full(p, 1e-5), np.arange(p, dtype=np.int32), win_start, win_end)
+    P = held.c()
+    o = (options or Options())._c()
+    mu0 = np.ascontiguousarray(np.full(p, 1e-5) if mu_init is None else mu_init, dtype=np.float64)
+    out = np.zeros(p, dtype=np.float64)
+    deltas = np.zeros(20, dtype=np.float64)
+    it = C.c_int32(0)
+    rc = L.kgw_estimate_hmm(C.byref(P), C.byref(o), mu0.ctypes.data, out.ctypes.data, C.byref(it), deltas.ctypes.data)
+    if rc < 0:
+        _check(rc)
+    n = int(it.value)
+    return out, n, deltas[:max(n, 1)].copy(), rc == 0
 
 
 def swap_flags(num_snps: int, seed: int = 2019) -> np.ndarray:
@@ -683,6 +703,16 @@ class Knockoffs:
         self.rec_rates = np.asarray(rec_rates, dtype=np.float64).copy()
         self.b = np.exp(-self.rec_rates)
         self.mut_rates = np.maximum(1e-6, np.minimum(np.asarray(mut_rates, dtype=np.float64), 1e-3))
+
+    def EM(self, num_threads=1):
+        """Knockoffs::EM (knockoffs.cpp:706-748): re-estimates the mutation rates on the device and installs them
+        (update_hmm, :1550-1561).  Returns (steps run, per-step deltas, converged)."""
+        assert self.references_local is not None and self.b is not None
+        mu, steps, deltas, conv = estimate_hmm(self.H, self.num_snps, self.K, self.references_local, self.b,
+                                               mu_init=self.mut_rates, win_start=self.win_start, win_end=self.win_end,
+                                               options=self.options)
+        self.mut_rates = mu
+        return steps, deltas, conv
 
     def set_partition(self, r):
         self.set_groups(self.partitions[r])

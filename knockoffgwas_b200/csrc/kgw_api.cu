@@ -810,7 +810,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     const bool big = (c == 1);
     size_t per_slot = (size_t)C.n_max * p * ((size_t)K * 9 + 2) + (size_t)C.n_max * C.rtot * K * sizeof(double);
     if (big) per_slot += (size_t)2 * C.n_max * KP * sizeof(double) + (size_t)5 * C.n_max * sizeof(int32_t);
-    const double budget = (double)free_b * (big ? 0.4 : 0.8);
+    const double budget = (double)free_b * (big ? 0.4 : 0.95);   // (the sampler sized its scratch with the families in mind)
     // CTAs of four warps; a big class whose slots are too large for four of them runs single-warp CTAs
     C.threads = (big && (double)per_slot * 4 > budget) ? 32 : 128;
     const int wpc = C.threads / 32;
@@ -1348,10 +1348,22 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   if (o.segment_loci > 0) {
     PS = std::min<size_t>(p32, (size_t)o.segment_loci);
   } else {
-    // with IBD families in the same call most of the memory goes to their message slots (204 MB per pair at
-    // 60 000 SNPs, K=100: residency is what bounds that kernel); the sampler cuts its passes into shorter segments
+    // With IBD families in the same call most of the memory goes to their message slots (108 MB per pair at
+    // 60 000 SNPs, K=100): residency is what bounds that kernel -- a family that is not resident waits for a whole
+    // family-time -- while the sampler loses only a few per cent when its passes are cut into short segments
+    // (487 ms instead of 467 ms for 3 744 instead of 30 016 loci per segment, C5-shaped shard).  So the families'
+    // wish comes first: one slot per family up to the kernel's residency; the sampler takes what is left, between
+    // 6 % and 25 % of the free memory.
     const bool with_families = prob->families && prob->families->n_families > 0;
-    const double budget = (with_families ? 0.25 : 0.6) * (double)free_b - (double)hw_bytes_est;
+    double budget = 0.6 * (double)free_b - (double)hw_bytes_est;
+    if (with_families) {
+      const kgw_families *fi = prob->families;
+      double want = 0.0;
+      long long resident = (long long)dp.multiProcessorCount * 16;   // 4 CTAs of 4 warps per SM
+      for (int f = 0; f < fi->n_families && resident > 0; f++, resident--)
+        want += (double)(fi->fam_off[f + 1] - fi->fam_off[f]) * (double)p * ((double)K * 9 + 2) * 1.02;
+      budget = std::max(0.06 * (double)free_b, std::min(0.25 * (double)free_b, 0.9 * (double)free_b - want)) - (double)hw_bytes_est;
+    }
     while (PS > 1024 && (double)slots * (double)(fixed_slot + seg_slot(PS)) > budget) PS = ((PS / 2) + 31) / 32 * 32;
   }
   pl->seg_loci = (int)PS;
