@@ -1271,7 +1271,8 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   // the number of warps that share its scheduler (measured on B200 at K = 50, ms per 10 000 loci):
   //   two lanes, wide   20.0 alone, 28.2 with a second warp      two lanes, dense   31.6 (two), 38.4 (three)
   //   one lane          26.7 alone, 35.5 with a second warp
-  // The one-lane form is only taken when every batch is resident at once (its residency is a third of the others').
+  //   one lane, slim    about 8 % more than the line above (the message row of a block is fetched when the block starts)
+  // Times of a warp count per batch, and a one-lane batch holds twice the haplotypes of a two-lane batch.
   struct Choice { const KgwVariant *var; kgw_kernel_fn fn; size_t smem_warp; int wpc, occ; double cost; };
   auto evaluate = [&](const KgwVariant *v, bool one_round_only, Choice *best) -> cudaError_t {
     const int Gv = 32 / v->L;
@@ -1300,12 +1301,15 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
       if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
       const double slots = (double)occ * wpc * dp.multiProcessorCount;
       const double rounds = std::ceil(n_tasks / slots);
-      if (one_round_only && rounds > 1.0) continue;
+      const bool one_lane = (v->L == 1 && v->S > 32);
+      // one lane per haplotype: the double-buffered form keeps 5 warps per SM and is only taken when every batch is
+      // resident at once; the slim form (one message-row buffer, 8 warps per SM) runs long lists of batches
+      if (one_round_only && one_lane && form == 1 && rounds > 1.0) continue;
       const double per_sm = std::min<double>(n_tasks, slots) / dp.multiProcessorCount;
       const double w = std::max(1.0, std::ceil(per_sm / 4.0));          // warps sharing the busiest scheduler
       const bool wide_regs = (form == 1) || (v->fn_wide == v->fn);
-      const double t1 = (v->L == 1 && v->S > 32) ? 26.7 : (wide_regs ? 20.0 : 24.8);
-      const double al = (v->L == 1 && v->S > 32) ? 0.33 : (wide_regs ? 0.41 : 0.274);
+      const double t1 = one_lane ? (form == 0 ? 26.7 * 1.08 : 26.7) : (wide_regs ? 20.0 : 24.8);
+      const double al = one_lane ? 0.33 : (wide_regs ? 0.41 : 0.274);
       const double cost = rounds * t1 * (1.0 + al * (w - 1.0));
       if (!best->var || cost < best->cost) *best = Choice{v, fn, smem_warp, wpc, occ, cost};
     }

@@ -286,7 +286,10 @@ __device__ __forceinline__ double ld_cg(const double *p) {
   return v;
 }
 
-template <int L, int S, int B, int D>
+// SLIM: the shared-memory diet that lets the one-lane layout keep two warps per scheduler (8 per SM) on long runs of
+// batches: ONE message-row buffer in sweep 2 (the row of the next block is fetched when the block starts instead of a
+// block ahead), and in sweep 3 the knockoff-table rows in the ring, ONE pair of latent-path tiles in the block buffers.
+template <int L, int S, int B, int D, bool SLIM = false>
 struct Cfg {
   static constexpr int G = 32 / L;
   static constexpr int KP = L * S;
@@ -305,14 +308,16 @@ struct Cfg {
   // table rows of two words), one match-word tile, a ring of D loci of partial sums (sweep 2; sweep 3 keeps the
   // emission rows of the word there when it holds 4 KB), totals + table rows of two blocks, 16 mbarriers
   static constexpr size_t s3_bytes = (size_t)ROW * 8 + 4 * 32 * G + 32 * sizeof(KgwLocusKO);
-  static constexpr size_t rows_bytes = (size_t)2 * ROW * 8 > s3_bytes ? (size_t)2 * ROW * 8 : s3_bytes;
+  static constexpr size_t rows_bytes = SLIM ? (size_t)ROW * 8 : ((size_t)2 * ROW * 8 > s3_bytes ? (size_t)2 * ROW * 8 : s3_bytes);
   static constexpr size_t tiles_bytes = (size_t)TILE * 4;
   static constexpr size_t ring_bytes = (size_t)D * CSW * 8;
   static constexpr size_t blk_bytes = (size_t)2 * ((size_t)B * G * 8 + (size_t)B * 16);
   static constexpr size_t bar_bytes = 128;
+  static_assert(!SLIM || (ring_bytes >= 32 * sizeof(KgwLocusKO) && blk_bytes >= 128 + 2 * 32 * G && ROW * 8 >= 1024),
+                "slim layout: knockoff-table rows in the ring, one pair of latent-path tiles in the block buffers");
   __host__ __device__ static constexpr size_t warp_bytes() { return rows_bytes + tiles_bytes + ring_bytes + blk_bytes + bar_bytes; }
 };
-enum { BAR_S1 = 0, BAR_TILE2 = 1, BAR_BLK = 2, BAR_CS = 4, BAR_W3 = 12, BAR_ZT = 13, BAR_EM = 14, KGW_NBARS = 16 };
+enum { BAR_S1 = 0, BAR_TILE2 = 1, BAR_BLK = 2, BAR_CS = 4, BAR_W3 = 12, BAR_ZT = 13, BAR_EM = 14, BAR_ROW = 15, KGW_NBARS = 16 };
 
 // uniform of (hap, stream, locus j): Philox block cached per 4 loci
 struct UniformSrc {
@@ -351,9 +356,9 @@ __device__ __forceinline__ HmmConsts hmm_consts(const KgwLocusHMM h, double alph
 }
 
 // PAD = false asserts K == L*S (no padded states: the per-state guards compile away)
-template <int L, int S, int B, bool PAD, int MINB, int D>
+template <int L, int S, int B, bool PAD, int MINB, int D, bool SLIM = false>
 __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __grid_constant__ KgwParams P) {
-  using C = Cfg<L, S, B, D>;
+  using C = Cfg<L, S, B, D, SLIM>;
   static_assert(D >= 2 && D <= 8, "ring depth");
   constexpr int G = C::G;
   constexpr int SPR = C::SPR, SPW = C::SPW, NQ = C::NQ, NP = C::NP, CS = C::CS, NC = C::NC, ROW = C::ROW, TILE = C::TILE;
@@ -389,9 +394,10 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
   double *blk_se = reinterpret_cast<double *>(smem_raw + C::rows_bytes + C::tiles_bytes + C::ring_bytes);   // [2][B][G]
   KgwLocusHMM *blk_h = reinterpret_cast<KgwLocusHMM *>(blk_se + 2 * B * G);       // [2][B]
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + C::rows_bytes + C::tiles_bytes + C::ring_bytes + C::blk_bytes);
-  uint8_t *ztile3 = reinterpret_cast<uint8_t *>(rowbuf + ROW);                   // [2][32][G] (sweep 3, after row 0)
-  uint8_t *zktile3 = ztile3 + 2 * 32 * G;                                        // [2][32][G]
-  KgwLocusKO *kot = reinterpret_cast<KgwLocusKO *>(zktile3 + 2 * 32 * G);        // [32]       (sweep 3)
+  constexpr int ZB = SLIM ? 1 : 2;   // buffers of the latent-path tiles in sweep 3
+  uint8_t *ztile3 = SLIM ? reinterpret_cast<uint8_t *>(blk_se) + 128 : reinterpret_cast<uint8_t *>(rowbuf + ROW);   // [ZB][32][G] (sweep 3)
+  uint8_t *zktile3 = ztile3 + ZB * 32 * G;                                       // [ZB][32][G]
+  KgwLocusKO *kot = SLIM ? reinterpret_cast<KgwLocusKO *>(ring) : reinterpret_cast<KgwLocusKO *>(zktile3 + 2 * 32 * G);   // [32] (sweep 3)
   uint32_t *z1slot = reinterpret_cast<uint32_t *>(blk_se);                       // [32]       (sweep 3)
   static_assert(C::blk_bytes >= 128, "z1 slots");
   // one mbarrier per staged buffer (one arrival: the elected lane's expect_tx); `ph` holds the phase parity every
@@ -404,6 +410,9 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
   }
   fence_async_proxy();
   __syncwarp();
+  // barrier between lanes that share a shared-memory row of one haplotype; with one lane per haplotype every lane reads
+  // and writes its own entries only and the compiler is free to overlap the draw with the partition-function passes
+  auto sync_lanes = [&]() { if (L > 1) __syncwarp(); };
   auto wait_bar = [&](int i) {
     mbar_wait(bars + i, (ph >> i) & 1u);
     ph ^= 1u << i;
@@ -654,13 +663,20 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
         if (!(P.skip_sweeps & 2)) {
           int wi = slo >> 5;
           // row, locus totals and table rows of block n -> buffers n & 1, one barrier per buffer pair
+          // (slim layout: the row has one buffer and its own barrier; it is fetched when its block starts)
           auto stage_block = [&](int n) {
             if (lane == 0) {
               unsigned long long *bar = bars + BAR_BLK + (n & 1);
-              mbar_expect_tx(bar, ROW * 8 + B * G * 8 + B * (unsigned)sizeof(KgwLocusHMM));
-              bulk_g2s(rowbuf + (size_t)(n & 1) * ROW, ck + (size_t)(n - seg0 / B) * ROW, ROW * 8, bar);
+              mbar_expect_tx(bar, (SLIM ? 0 : ROW * 8) + B * G * 8 + B * (unsigned)sizeof(KgwLocusHMM));
+              if (!SLIM) bulk_g2s(rowbuf + (size_t)(n & 1) * ROW, ck + (size_t)(n - seg0 / B) * ROW, ROW * 8, bar);
               bulk_g2s(blk_se + (n & 1) * B * G, seb + (size_t)(n * B - seg0) * G, B * G * 8, bar);
               bulk_g2s(blk_h + (n & 1) * B, P.hmm + n * B, B * (unsigned)sizeof(KgwLocusHMM), bar);
+            }
+          };
+          auto stage_row = [&](int n) {
+            if (lane == 0) {
+              mbar_expect_tx(bars + BAR_ROW, ROW * 8);
+              bulk_g2s(rowbuf, ck + (size_t)(n - seg0 / B) * ROW, ROW * 8, bars + BAR_ROW);
             }
           };
           // partial sums of locus j -> ring slot j % D
@@ -698,8 +714,10 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               stage_tile2(wi);
               tile_pending = true;
             }
+            if (SLIM) stage_row(n);   // every lane is past block n - 1 (the barrier above)
             if (n < n_last) stage_block(n + 1);
             wait_bar(BAR_BLK + (n & 1));
+            if (SLIM) wait_bar(BAR_ROW);
             if (tile_pending) { wait_bar(BAR_TILE2); tile_pending = false; }
             const double *bse = blk_se + (n & 1) * B * G;
             const KgwLocusHMM *bh = blk_h + (n & 1) * B;
@@ -718,7 +736,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
                 tbo[mm] = 1.0; tbm[mm] = 1.0; tcm[mm] = 0.0;
               }
             }
-            const double *row = rowbuf + (size_t)(n & 1) * ROW;
+            const double *row = rowbuf + (size_t)(SLIM ? 0 : (n & 1)) * ROW;
             const uint32_t *tile = mwt;
             const int bit0 = nb & 31;
 
@@ -727,7 +745,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               const int j = nb + jj;
               if (j < lo || j > top) continue;
               wait_bar(BAR_CS + (j % D));
-              // partial sums of this locus: the L lanes of the haplotype, four chunks each
+              // partial sums of this locus: the L lanes of the haplotype, NC chunks each
               double csv[NCT];
               {
                 const double2 *slot = reinterpret_cast<const double2 *>(ring + (j % D) * CSW);
@@ -858,14 +876,14 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
         // copies per word (latent-path tiles a word ahead; match-word tile, knockoff-table rows and emission rows of
         // the word -- the tables are padded to whole words on either side), and the byte z1 of the next group by a
         // per-lane cp.async one group ahead.
-        constexpr bool EMIT_IN_RING = C::ring_bytes >= 32 * sizeof(KgwEmit);
+        constexpr bool EMIT_IN_RING = !SLIM && C::ring_bytes >= 32 * sizeof(KgwEmit);
         static_assert(sizeof(KgwEmit) == sizeof(KgwLocusKO), "the two per-locus tables may share a shared-memory tile");
         KgwEmit *emt = EMIT_IN_RING ? reinterpret_cast<KgwEmit *>(ring) : reinterpret_cast<KgwEmit *>(kot);   // [32], indexed by bit
         auto stage_ztiles = [&](int w) {
           if (lane == 0) {
             mbar_expect_tx(bars + BAR_ZT, 2 * 32 * G);
-            bulk_g2s(ztile3 + (size_t)(w & 1) * 32 * G, zb + (size_t)(w << 5) * G, 32 * G, bars + BAR_ZT);
-            bulk_g2s(zktile3 + (size_t)(w & 1) * 32 * G, zkb + (size_t)(w << 5) * G, 32 * G, bars + BAR_ZT);
+            bulk_g2s(ztile3 + (size_t)(w & (ZB - 1)) * 32 * G, zb + (size_t)(w << 5) * G, 32 * G, bars + BAR_ZT);
+            bulk_g2s(zktile3 + (size_t)(w & (ZB - 1)) * 32 * G, zkb + (size_t)(w << 5) * G, 32 * G, bars + BAR_ZT);
           }
         };
         int z1 = 0, z1_byte = 0;
@@ -880,10 +898,11 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
           const int zi = ko_tab[js].z1_idx;
           if (zi >= 0) stage_z1(zi);
         }
-        stage_ztiles(wlo);
+        if (!SLIM) stage_ztiles(wlo);
         for (int wi = wlo; wi <= whi; wi++) {
           const int lo = max(wi << 5, js), hi = min((wi << 5) + 32, je);
           __syncwarp();   // the previous word is finished in every lane (tile reads of its allele draws)
+          if (SLIM) stage_ztiles(wi);   // one pair of latent-path tiles: fetched with the word
           if (lane == 0) {
             // match words (for the allele draws at the end of the word), knockoff-table rows and, when the ring can
             // hold them, the emission rows of the word's 32 loci
@@ -894,8 +913,8 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
           }
           wait_bar(BAR_ZT);
           wait_bar(BAR_W3);
-          if (wi < whi) stage_ztiles(wi + 1);
-          uint8_t *zt = ztile3 + (size_t)(wi & 1) * 32 * G, *zkt = zktile3 + (size_t)(wi & 1) * 32 * G;
+          if (!SLIM && wi < whi) stage_ztiles(wi + 1);
+          uint8_t *zt = ztile3 + (size_t)(wi & (ZB - 1)) * 32 * G, *zkt = zktile3 + (size_t)(wi & (ZB - 1)) * 32 * G;
           for (int j = lo; j < hi; j++) {
             const KgwLocusKO &k = kot[j & 31];
             const int bit = j & 31;
@@ -921,7 +940,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
                 cs[s0 / CS] += r0;
                 if (s1 < S) cs[((s1 < S) ? s1 : 0) / CS] += r1;
               }
-              __syncwarp();
+              sync_lanes();
               KGW_PH(6);   // sweep 3: loop head + pass A
               // Special states, read by every lane of the haplotype.  k == z0 / z0k carry T_k(z0)*T_k(z0k) != tg
               // (:1350-1354) in the N update and in the draw; k == z1 carries the extra vstar term in the draw
@@ -934,7 +953,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
               const double rz = (!gz && z1 == z0) ? n0 : ((!gz && z1 == z0k) ? n0k : rz1);
               const double nz = rz * k.fz1;
               const double d1 = lastg ? 0.0 : nz - rz;
-              __syncwarp();   // every lane has read the unpatched row
+              sync_lanes();   // every lane has read the unpatched row
               const int lg0 = lane_of(z0), lg0k = lane_of(z0k), lg1 = lane_of(z1);
               {
                 // the owner lane patches its entries (it re-reads them in pass B) and its chunk sums
@@ -991,7 +1010,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
 #pragma unroll
                 for (int c = 0; c < NC; c++) add_if_eq(cs[c], c1, c, d1);
               }
-              __syncwarp();
+              sync_lanes();
               KGW_PH(9);   // sweep 3: pass B + clamp + z1 patch
               // two-level inverse-CDF search (weighted_choice, utils.cpp:690-698)
               const double St = Sr + d1;
@@ -1028,7 +1047,7 @@ __global__ void __launch_bounds__(32 * KGW_WPC, MINB) sampler_kernel(const __gri
                 }
               }
               zk = min(lgs * S + ci * CS + c2n, K - 1);
-              __syncwarp();   // the row is rewritten at the next group
+              sync_lanes();   // the row is rewritten at the next group
               KGW_PH(10);  // sweep 3: draw
             } else {
               // inside a group every state has weight a*vb except k == zk_{j-1} and k == z1 (:1397-1419)

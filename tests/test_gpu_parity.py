@@ -191,3 +191,14 @@ def test_kernel_reproduces_reference_binary_with_windows():
     assert np.array_equal(dbg.z, f["z_unrelated"].astype(np.int32)), "Z differs from the reference"
     assert np.array_equal(dbg.zk, f["zk_unrelated"].astype(np.int32)), "Zk differs from the reference"
     assert np.array_equal(hk[prob.unrelated], f["Hk"][prob.unrelated]), "Hk differs from the reference"
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_one_lane_forms_match_oracle(wide, monkeypatch):
+    """K = 50 with one lane per haplotype in both compiled forms: the slim shared-memory layout (one message-row buffer,
+    knockoff-table rows in the ring, one pair of latent-path tiles; KGW_FORCE_WIDE=0) and the double-buffered one."""
+    monkeypatch.setenv("KGW_FORCE_WIDE", wide)
+    prob = synthetic_problem(N=120, p=333, K=50, seed=17, mean_group=2.5)
+    res = ko.run_unrelated(prob, mode="philox")
+    hk, dbg = _run(prob, options=kg.Options(lanes_per_hap=1, segment_loci=128), debug_paths=True)
+    assert np.array_equal(dbg.z, res.z) and np.array_equal(dbg.zk, res.zk) and np.array_equal(hk, res.hk)
