@@ -1266,7 +1266,8 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   // modelled time.  Each form is compiled twice -- `fn` for the densest residency (12 or 16 warps per SM, 168 / 128
   // registers) and `fn_wide` for 8 warps per SM with the full register budget -- and K in (32, 50] can also run with
   // ONE lane per haplotype (50 states per lane, 32 haplotypes per warp, no lane of a haplotype repeating the draw
-  // logic of another: 62 instead of 76 warp instructions per haplotype-SNP, but 40 KB of shared memory per warp).
+  // logic of another: 62 instead of 76 warp instructions per haplotype-SNP, but 40 KB of shared memory per warp);
+  // likewise K in (64, 100] on two lanes and K in (128, 200] on four.
   // Model: rounds x time of a warp, where rounds = ceil(batches / resident warps) and the time of a warp grows with
   // the number of warps that share its scheduler (measured on B200 at K = 50, ms per 10 000 loci):
   //   two lanes, wide   20.0 alone, 28.2 with a second warp      two lanes, dense   31.6 (two), 38.4 (three)
@@ -1301,7 +1302,7 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
       if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
       const double slots = (double)occ * wpc * dp.multiProcessorCount;
       const double rounds = std::ceil(n_tasks / slots);
-      const bool one_lane = (v->L == 1 && v->S > 32);
+      const bool one_lane = (v->S > 32);   // "fat" lanes: 50 states each (one lane per haplotype at K <= 50, two at K <= 100, four at K <= 200)
       // one lane per haplotype: the double-buffered form keeps 5 warps per SM and is only taken when every batch is
       // resident at once; the slim form (one message-row buffer, 8 warps per SM) runs long lists of batches
       if (one_round_only && one_lane && form == 1 && rounds > 1.0) continue;
@@ -1317,9 +1318,13 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   };
   Choice ch{nullptr, nullptr, 0, 1, 0, 0.0};
   KGW_CUDA_PL(evaluate(pick_variant(K, o.lanes_per_hap, B), false, &ch));
-  if (o.lanes_per_hap == 0 && K > 32 && K <= 50) {
-    const KgwVariant *v1 = pick_variant(K, 1, B);
-    if (v1) KGW_CUDA_PL(evaluate(v1, true, &ch));
+  if (o.lanes_per_hap == 0) {
+    // the same K on half the lanes, 50 states per lane, where that fits (K in (32, 50], (64, 100], (128, 200])
+    const KgwVariant *v0 = pick_variant(K, 0, B);
+    if (v0 && v0->L > 1 && (K + v0->L / 2 - 1) / (v0->L / 2) <= 50) {
+      const KgwVariant *v1 = pick_variant(K, v0->L / 2, B);
+      if (v1) KGW_CUDA_PL(evaluate(v1, true, &ch));
+    }
   }
   if (!ch.var) return guard_fail(fail(KGW_ERR_CUDA, "kernel does not fit on an SM"));
   const KgwVariant *var = ch.var;

@@ -74,6 +74,10 @@ CASES = [
     dict(N=90, p=260, K=50, mean_group=1.0, lanes=1),             # one lane per haplotype, 50 states, eight chunks
     dict(N=90, p=230, K=50, mean_group=4.0, lanes=1, block=8),
     dict(N=70, p=200, K=41, mean_group=2.0, lanes=1),             # padded: 41 of 50 states
+    dict(N=150, p=170, K=100, mean_group=1.0, lanes=2),           # 50 states per lane on two lanes
+    dict(N=150, p=170, K=87, mean_group=3.0, lanes=2),
+    dict(N=220, p=130, K=200, mean_group=1.0, lanes=4),           # ... and on four
+    dict(N=220, p=130, K=150, mean_group=2.0, lanes=4),
     dict(N=70, p=200, K=32, mean_group=3.0, lanes=1, block=8),
     dict(N=33, p=70, K=10, mean_group=1.0, lanes=1),
     dict(N=33, p=70, K=10, mean_group=2.0, lanes=8),
