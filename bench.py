@@ -282,10 +282,21 @@ def leg_c3_shard(torch, kg, synth, dev, stream, flush, a):
     plan = kg.Plan(prob.H, p, K, prob.ref[:, None, :], prob.b, prob.mu, prob.groups, seed=prob.seed, options=opts)
     info = plan.info()
     total_ms, kern, clocks = timed_runs(torch, plan, stream, dev, 3, 1, flush)
+    # the row after the path at this size: .bed body of (H, Hk), 2 x 656 MB in, 1.3 GB out
+    bed = None
+    try:
+        body, _ = plan.encode_bed()
+        body, bed_ms = plan.encode_bed(out=body)
+        rb = (p + 7) // 8
+        bed = {"kernel_ms": bed_ms, "input_bytes": int(2 * N * rb), "output_bytes": int(body.nbytes),
+               "kernel_GBps": (body.nbytes + 2 * N * rb) / (bed_ms * 1e-3) / 1e9, "frac_of_hbm_peak": (body.nbytes + 2 * N * rb) / (bed_ms * 1e-3) / 1e9 / hbm_peak()[0]}
+        del body
+    except Exception as e:
+        bed = {"error": repr(e)[:200]}
     plan.close()
     kg.release_workspace()
     k_ms = float(np.mean(kern))
-    return {"workload": f"{N} haplotypes x {p} SNPs, K={K}, singleton groups, unrelated (1/8 of 700k x 60k)", "steps": 3, "warmup": 1,
+    return {"workload": f"{N} haplotypes x {p} SNPs, K={K}, singleton groups, unrelated (1/8 of 700k x 60k)", "steps": 3, "warmup": 1, "bed_writer": bed,
             "ms_per_step": total_ms / 3, "value": N * p * 3 / (total_ms * 1e-3), "unit": UNIT, "clocks": clocks,
             "roofline": roofline_dict(N * p, K, k_ms, "kgw::sampler_kernel", SAMPLER_NOTE),
             "kernel": {k: info[k] for k in ("grid", "block", "lanes_per_hap", "states_per_lane", "scratch_bytes", "block_loci", "segment_loci")}}

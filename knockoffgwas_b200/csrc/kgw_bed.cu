@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -27,9 +28,10 @@ void *kgw_plan_device_h_(kgw_plan *pl, int *N, int *p, int *stride_w, int *devic
 
 namespace {
 
-constexpr int BED_LOCI = 256;   // loci per tile (four 64-bit chunks per row)
-constexpr int BED_HAPS = 256;   // haplotypes per tile (32 groups of 8 = 32 output bytes per column)
-constexpr int BED_THREADS = 128;
+constexpr int BED_LOCI = 512;    // loci per tile: 64 contiguous bytes of every input row
+constexpr int BED_HAPS = 1024;   // haplotypes per tile: 128 groups of 8 = 128 contiguous bytes of every output column
+constexpr int BED_THREADS = 256;
+constexpr int BED_PITCH = BED_HAPS / 8;        // bytes per locus row of the shared tile
 
 // 8x8 bit-matrix transpose of a 64-bit word whose byte r holds row r, bit c = column c (LSB first):
 // afterwards byte c holds column c, bit r = row r  (Hacker's Delight 7-3).
@@ -43,70 +45,83 @@ __device__ __forceinline__ unsigned long long transpose8x8(unsigned long long x)
 // Hw / Hkw: [N][stride_w] packed rows (LSB-first, stride_w a multiple of 4 words); either may be null.
 // out: [ncols][nb] with nb = ceil(N/2/4); col_of(j, which) = 2j + (which ^ swap[j]) when both matrices are
 // written, j when only one is.
+// Persistent grid over (matrix, haplotype tile, locus tile).  A tile is 1024 haplotypes x 512 loci: every input row
+// contributes 64 contiguous bytes (two full 32-byte sectors) and every output column receives 128 contiguous bytes (a
+// full line) -- partial-sector writes into columns that lie N/8 bytes apart were what held the first version of this
+// kernel to 0.43 TB/s on a 87 500 x 60 000 matrix.
 __global__ void __launch_bounds__(BED_THREADS) bed_encode_kernel(const uint32_t *__restrict__ Hw, const uint32_t *__restrict__ Hkw,
                                                                  const uint8_t *__restrict__ swap, uint8_t *__restrict__ out, int N,
                                                                  int p, int stride_w, long long nb) {
-  __shared__ __align__(16) uint8_t tile[BED_LOCI][BED_HAPS / 8];   // [locus][haplotype group] = one .bed byte each
-  const int gq = threadIdx.x & 31;    // haplotype group within the tile (8 haplotypes)
-  const int cq = threadIdx.x >> 5;    // 64-locus chunk within the tile
-  const long long h0 = (long long)blockIdx.y * BED_HAPS;
-  const long long chunk = (long long)blockIdx.x * (BED_LOCI / 64) + cq;   // 64-bit chunk index within a row
-  const int chunks_per_row = stride_w / 2;
+  extern __shared__ __align__(16) uint8_t tile[];   // [BED_LOCI][BED_PITCH]: [locus][haplotype group] = one .bed byte each
+  const int chunks_per_row = stride_w / 2;           // 64-bit chunks in a packed row
   const bool both = (Hw != nullptr) && (Hkw != nullptr);
-  for (int which = 0; which < 2; which++) {
+  const long long tiles_l = ((long long)p + BED_LOCI - 1) / BED_LOCI, tiles_h = ((long long)N + BED_HAPS - 1) / BED_HAPS;
+  const long long n_tiles = tiles_l * tiles_h * 2;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int which = (int)(t / (tiles_l * tiles_h));
     const uint32_t *M = which == 0 ? Hw : Hkw;
     if (M == nullptr) continue;
-    // rows of the thread's 8 haplotypes, 64 loci each
-    uint32_t lo[8], hi[8];
+    const long long tl = (t % (tiles_l * tiles_h)) % tiles_l, th = (t % (tiles_l * tiles_h)) / tiles_l;
+    const long long h0 = th * BED_HAPS;
+    __syncthreads();   // the previous tile has been written out
+    // a task = 8 haplotypes x 64 loci: (BED_HAPS / 8) x (BED_LOCI / 64) of them per tile; consecutive threads take
+    // consecutive 64-locus chunks of the same rows (one warp reads 4 haplotype groups x 64 contiguous bytes per row).
+    // The eight chunks of a warp write tile rows that lie 64 rows apart (the same bank): the 32-bit words of a tile row
+    // are stored at word index w ^ (chunk << 2), undone when the row is read out.
+    constexpr int CH = BED_LOCI / 64;
+    for (int task = threadIdx.x; task < (BED_HAPS / 8) * CH; task += BED_THREADS) {
+      const int cq = task % CH, gq = task / CH;
+      const long long chunk = tl * CH + cq;
+      uint32_t lo[8], hi[8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const long long hap = h0 + 8 * gq + r;
-      uint2 v = make_uint2(0u, 0u);
-      if (hap < N && chunk < chunks_per_row) v = __ldg(reinterpret_cast<const uint2 *>(M + (size_t)hap * stride_w) + chunk);
-      lo[r] = v.x;
-      hi[r] = v.y;
-    }
+      for (int r = 0; r < 8; r++) {
+        const long long hap = h0 + 8 * gq + r;
+        uint2 v = make_uint2(0u, 0u);
+        if (hap < N && chunk < chunks_per_row) v = __ldg(reinterpret_cast<const uint2 *>(M + (size_t)hap * stride_w) + chunk);
+        lo[r] = v.x;
+        hi[r] = v.y;
+      }
 #pragma unroll
-    for (int b = 0; b < 8; b++) {
-      // byte b of every row -> one 64-bit word (byte r = haplotype r, bit c = locus 8b + c)
-      const uint32_t *w = (b < 4) ? lo : hi;
-      const unsigned sel = (unsigned)(b & 3) | ((4u + (unsigned)(b & 3)) << 4);
-      const uint32_t t01 = __byte_perm(w[0], w[1], sel), t23 = __byte_perm(w[2], w[3], sel);
-      const uint32_t t45 = __byte_perm(w[4], w[5], sel), t67 = __byte_perm(w[6], w[7], sel);
-      const unsigned long long x = (unsigned long long)__byte_perm(t01, t23, 0x5410) |
-                                   ((unsigned long long)__byte_perm(t45, t67, 0x5410) << 32);
-      const unsigned long long y = transpose8x8(x);   // byte c = the 8 haplotypes' bits at locus 8b + c
-      const unsigned long long even = y & 0x5555555555555555ull, odd = (y >> 1) & 0x5555555555555555ull;
-      const unsigned long long code = (even & odd) | ((even | odd) << 1);   // four 2-bit genotypes per byte (:20-28)
+      for (int b = 0; b < 8; b++) {
+        // byte b of every row -> one 64-bit word (byte r = haplotype r, bit c = locus 8b + c)
+        const uint32_t *w = (b < 4) ? lo : hi;
+        const unsigned sel = (unsigned)(b & 3) | ((4u + (unsigned)(b & 3)) << 4);
+        const uint32_t t01 = __byte_perm(w[0], w[1], sel), t23 = __byte_perm(w[2], w[3], sel);
+        const uint32_t t45 = __byte_perm(w[4], w[5], sel), t67 = __byte_perm(w[6], w[7], sel);
+        const unsigned long long x = (unsigned long long)__byte_perm(t01, t23, 0x5410) |
+                                     ((unsigned long long)__byte_perm(t45, t67, 0x5410) << 32);
+        const unsigned long long y = transpose8x8(x);   // byte c = the 8 haplotypes' bits at locus 8b + c
+        const unsigned long long even = y & 0x5555555555555555ull, odd = (y >> 1) & 0x5555555555555555ull;
+        const unsigned long long code = (even & odd) | ((even | odd) << 1);   // four 2-bit genotypes per byte (:20-28)
 #pragma unroll
-      for (int c = 0; c < 8; c++) tile[64 * cq + 8 * b + c][gq] = (uint8_t)(code >> (8 * c));
-    }
-    __syncthreads();
-    // 256 loci x 32 bytes: thread t writes the rows of loci t and t + 128
-#pragma unroll
-    for (int r = 0; r < BED_LOCI / BED_THREADS; r++) {
-      const int l = threadIdx.x + BED_THREADS * r;
-      const long long j = (long long)blockIdx.x * BED_LOCI + l;
-      const long long byte0 = h0 / 8;   // first output byte of this tile within the column
-      if (j < p && byte0 < nb) {
-        const long long col = both ? 2 * j + (which ^ ((swap != nullptr && swap[j]) ? 1 : 0)) : j;
-        uint8_t *dst = out + (size_t)col * (size_t)nb + (size_t)byte0;
-        const int n = (int)((nb - byte0) < (BED_HAPS / 8) ? (nb - byte0) : (BED_HAPS / 8));
-        const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
-        if (n == BED_HAPS / 8 && (a & 15) == 0) {
-          reinterpret_cast<uint4 *>(dst)[0] = reinterpret_cast<const uint4 *>(tile[l])[0];
-          reinterpret_cast<uint4 *>(dst)[1] = reinterpret_cast<const uint4 *>(tile[l])[1];
-        } else if (n == BED_HAPS / 8 && (a & 3) == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(tile[l])[i];
-        } else {
-          for (int i = 0; i < n; i++) dst[i] = tile[l][i];
-        }
+        for (int c = 0; c < 8; c++)
+          tile[(size_t)(64 * cq + 8 * b + c) * BED_PITCH + 4 * ((gq >> 2) ^ (cq << 2)) + (gq & 3)] = (uint8_t)(code >> (8 * c));
       }
     }
     __syncthreads();
+    // BED_LOCI columns x 128 bytes: a warp writes one column piece per instruction (32 lanes x 4 bytes = one line)
+    const long long byte0 = h0 / 8;   // first output byte of this tile within the column
+    const int n = (int)((nb - byte0) < (BED_HAPS / 8) ? (nb - byte0) : (BED_HAPS / 8));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int l = wid; l < BED_LOCI; l += BED_THREADS / 32) {
+      const long long j = tl * BED_LOCI + l;
+      if (j >= p || n <= 0) continue;
+      const long long col = both ? 2 * j + (which ^ ((swap != nullptr && swap[j]) ? 1 : 0)) : j;
+      uint8_t *dst = out + (size_t)col * (size_t)nb + (size_t)byte0;
+      const uint8_t *src = tile + (size_t)l * BED_PITCH;
+      const int sw = ((l >> 6) & 7) << 2;   // word swizzle of this tile row
+      if (n == BED_HAPS / 8 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        reinterpret_cast<uint32_t *>(dst)[lane] = reinterpret_cast<const uint32_t *>(src)[lane ^ sw];
+      } else {
+        for (int i = lane; i < n; i += 32) dst[i] = src[4 * ((i >> 2) ^ sw) + (i & 3)];
+      }
+    }
   }
 }
+
+}  // namespace
+
+namespace {
 
 #define BED_CUDA(call)                                                                                 \
   do {                                                                                                 \
@@ -128,8 +143,18 @@ int encode_on_device(const uint32_t *dH, const uint32_t *dHk, int N, int p, int 
   if (!dout) BED_CUDA(kgw_malloc(&dout, out_bytes));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-  const dim3 grid((unsigned)((p + BED_LOCI - 1) / BED_LOCI), (unsigned)((N + BED_HAPS - 1) / BED_HAPS));
-  bed_encode_kernel<<<grid, BED_THREADS, 0, st>>>(dH, dHk, dswap, dout, N, p, stride_w, nb);
+  static bool attr_set = false;
+  const size_t smem = (size_t)BED_LOCI * BED_PITCH;
+  if (!attr_set) {
+    BED_CUDA(cudaFuncSetAttribute(bed_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (((long long)p + BED_LOCI - 1) / BED_LOCI) * (((long long)N + BED_HAPS - 1) / BED_HAPS) * 2;
+  const int grid = (int)std::min<long long>(n_tiles, (long long)sms * 3);   // persistent: 3 CTAs of 72 KB per SM
+  bed_encode_kernel<<<grid, BED_THREADS, smem, st>>>(dH, dHk, dswap, dout, N, p, stride_w, nb);
   BED_CUDA(cudaGetLastError());
   if (kernel_ms) {
     cudaEventRecord(e1, st);
