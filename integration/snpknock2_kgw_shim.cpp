@@ -36,11 +36,15 @@
 
 #include "bgen_reader.h"
 #include "plink_interface.h"
+#define private public
+#include "haps_reader.h"
+#include "kinship_computer.h"
+#undef private
 #include <random>
 #include <unordered_map>
 
-#if !defined(KGW_GEN_SYM) || !defined(KGW_BGEN_SYM) || !defined(KGW_WB_SYM)
-#error "KGW_GEN_SYM / KGW_BGEN_SYM / KGW_WB_SYM (mangled Knockoffs::generate, BgenReader::read, plink::write_binary) must be defined by the build script"
+#if !defined(KGW_GEN_SYM) || !defined(KGW_BGEN_SYM) || !defined(KGW_WB_SYM) || !defined(KGW_HAPS_SYM) || !defined(KGW_AR_SYM)
+#error "KGW_GEN_SYM / KGW_BGEN_SYM / KGW_WB_SYM / KGW_HAPS_SYM / KGW_AR_SYM (mangled Knockoffs::generate, BgenReader::read, plink::write_binary, HapsReader::read, KinshipComputer::assign_references) must be defined by the build script"
 #endif
 #define KGW_STR2(x) #x
 #define KGW_STR(x) KGW_STR2(x)
@@ -55,6 +59,12 @@ void real_write_binary(const string &basename, const Metadata &metadata, const v
                        bool random) asm("__real_" KGW_STR(KGW_WB_SYM));
 void wrap_write_binary(const string &basename, const Metadata &metadata, const vector<chaplotype> &H, const vector<chaplotype> &Hk,
                        bool random) asm("__wrap_" KGW_STR(KGW_WB_SYM));
+void real_haps_read(HapsReader *self, const vector<string> &sample_ids, const vector<string> &snp_ids, vector<chaplotype> &H,
+                    bool verbose) asm("__real_" KGW_STR(KGW_HAPS_SYM));
+void wrap_haps_read(HapsReader *self, const vector<string> &sample_ids, const vector<string> &snp_ids, vector<chaplotype> &H,
+                    bool verbose) asm("__wrap_" KGW_STR(KGW_HAPS_SYM));
+ivector3d real_assign_references(const KinshipComputer *self, const int K, const int chr, const Windows &windows) asm("__real_" KGW_STR(KGW_AR_SYM));
+ivector3d wrap_assign_references(const KinshipComputer *self, const int K, const int chr, const Windows &windows) asm("__wrap_" KGW_STR(KGW_AR_SYM));
 void writeBIM(const string &basename, const Metadata &metadata, bool include_genotypes, const vector<bool> &swap);   // plink_interface.cpp:105
 void writeFAM(const string &basename, const Metadata &metadata);                                                      // plink_interface.cpp:162
 
@@ -101,6 +111,97 @@ void wrap_bgen_read(BgenReader *self, const vector<string> &sample_ids, const ve
   H = vector<chaplotype>(2 * num_samples, chaplotype(num_snps));     // as BgenReader::read (:76-77)
   for (int i = 0; i < 2 * num_samples; i++)
     std::copy(Hflat.begin() + (size_t)i * row_bytes, Hflat.begin() + (size_t)(i + 1) * row_bytes, H[i].data.begin());
+}
+
+// HapsReader::read (haps_reader.cpp:37-132): same sample / variant look-ups, the text is tokenized and transposed on the device
+void wrap_haps_read(HapsReader *self, const vector<string> &sample_ids, const vector<string> &snp_ids, vector<chaplotype> &H,
+                    bool verbose) {
+  if (!shim_io()) { real_haps_read(self, sample_ids, snp_ids, H, verbose); return; }
+  std::ifstream fd(self->filename, std::ios::binary | std::ios::ate);
+  if (!fd.is_open()) { real_haps_read(self, sample_ids, snp_ids, H, verbose); return; }   // the reference's own error path
+  std::vector<uint8_t> text((size_t)fd.tellg());
+  fd.seekg(0);
+  fd.read((char *)text.data(), (std::streamsize)text.size());
+  if (text.size() >= 2 && text[0] == 0x1f && text[1] == 0x8b) { real_haps_read(self, sample_ids, snp_ids, H, verbose); return; }   // gzip: the reference's ifile inflates
+  const int num_samples = (int)sample_ids.size(), num_snps = (int)snp_ids.size();
+  std::vector<int32_t> sidx(num_samples);
+  for (int i = 0; i < num_samples; i++) {                              // :73-85
+    auto it = std::find(self->sample.ID.begin(), self->sample.ID.end(), sample_ids[i]);
+    if (it == self->sample.ID.end()) { cerr << "Error parsing HAPS file. Could not find sample " << sample_ids[i] << endl; exit(1); }
+    sidx[i] = (int32_t)std::distance(self->sample.ID.begin(), it);
+  }
+  // a file row goes to the column of the first requested id equal to its legend id (:98-104); rows are visited in file
+  // order, so the last such row wins a column
+  std::unordered_map<std::string, int32_t> col_of;
+  for (int j = num_snps - 1; j >= 0; j--) col_of[snp_ids[j]] = j;
+  std::vector<int32_t> row_of_col(num_snps, -1);
+  for (size_t r = 0; r < self->legend.ID.size(); r++) {
+    auto it = col_of.find(self->legend.ID[r]);
+    if (it != col_of.end()) row_of_col[it->second] = (int32_t)r;
+  }
+  for (int j = 0; j < num_snps; j++)
+    if (row_of_col[j] < 0) { real_haps_read(self, sample_ids, snp_ids, H, verbose); return; }   // a column no row fills stays 0 in the reference
+  const int64_t row_bytes = (num_snps + 7) / 8;
+  std::vector<uint8_t> Hflat((size_t)2 * num_samples * row_bytes);
+  if (kgw_haps_read(text.data(), (int64_t)text.size(), num_samples, sidx.data(), num_snps, row_of_col.data(), /*device=*/0, row_bytes,
+                    Hflat.data(), nullptr) != KGW_OK) {
+    std::cerr << "Error: " << kgw_last_error() << std::endl;
+    exit(1);
+  }
+  H.clear();
+  H = vector<chaplotype>(2 * num_samples, chaplotype(num_snps));
+  for (int i = 0; i < 2 * num_samples; i++)
+    std::copy(Hflat.begin() + (size_t)i * row_bytes, Hflat.begin() + (size_t)(i + 1) * row_bytes, H[i].data.begin());
+}
+
+// KinshipComputer::assign_references (kinship_computer.cpp:836-931): the worker loop over findNeighbors (:174-233, all-pairs
+// Hamming distances inside the kinship cluster and the K smallest) runs on the device; the merge inside IBD families
+// (combine_references_families, :765-835) and the sanity checks stay the reference's.  With --windows > 0 the reference
+// path is kept (include/kgw.h says why).
+ivector3d wrap_assign_references(const KinshipComputer *self, const int K, const int chr, const Windows &windows) {
+  if (!shim_io() || windows.num_windows > 1) return real_assign_references(self, K, chr, windows);
+  const int num_haps = self->num_haps;
+  const Haplotypes *hp = self->chromosomes[chr];                      // the thinned chromosome the distances are taken on
+  const int p = hp->get_num_snps();
+  const int64_t row_bytes = (p + 7) / 8;
+  std::vector<uint8_t> Hflat((size_t)num_haps * row_bytes);
+  for (int i = 0; i < num_haps; i++)
+    std::copy(hp->H[i].data.begin(), hp->H[i].data.begin() + row_bytes, Hflat.begin() + (size_t)i * row_bytes);
+  std::vector<int32_t> clust_off{0}, clust_members, family_of(num_haps, -1);
+  for (auto &c : self->clusters[chr]) {
+    clust_members.insert(clust_members.end(), c.begin(), c.end());
+    clust_off.push_back((int32_t)clust_members.size());
+  }
+  for (int i = 0; i < num_haps; i++) {
+    const vector<int> &fam = self->metadata[chr].related_families[i];
+    if (fam.size() > 1) family_of[i] = *std::min_element(fam.begin(), fam.end());
+  }
+  cout << "Assigning references for the whole chromosome on the GPU: " << endl;
+  std::vector<int32_t> nn((size_t)num_haps * K, -1);
+  if (kgw_assign_references(num_haps, p, row_bytes, Hflat.data(), K, /*compression=*/1, (int32_t)self->clusters[chr].size(), clust_off.data(),
+                            clust_members.data(), family_of.data(), /*device=*/0, nn.data(), nullptr) != KGW_OK) {
+    std::cerr << "Error: " << kgw_last_error() << std::endl;
+    exit(-1);
+  }
+  ivector3d ref(num_haps, ivector2d(1, vector<int>(K, -1)));
+  for (int i = 0; i < num_haps; i++)
+    for (int k = 0; k < K; k++) ref[i][0][k] = nn[(size_t)i * K + k];
+  ref = self->combine_references_families(chr, ref);                   // unchanged (:765-835)
+  for (int i1 = 0; i1 < num_haps; i1++) {                              // the reference's sanity checks (:883-928)
+    const vector<int> &ibd_family = self->metadata[chr].related_families[i1];
+    if (ibd_family.size() > 1)
+      for (int i2 : ibd_family)
+        if (ref[i1][0] != ref[i2][0]) { cerr << "Error: references for haplotypes " << i1 << " and " << i2 << " do not match!" << endl; exit(-1); }
+    for (int k = 0; k < K; k++) {
+      const int j = ref[i1][0][k];
+      if (j < 0) { cerr << "Error: could not assign all references for lack of sufficient samples. Try decreasing K." << endl; exit(-1); }
+      if (ibd_family.size() > 1 && std::count(ibd_family.begin(), ibd_family.end(), j) > 0) {
+        cerr << "Error: could not assign all references for lack of sufficient unrelated samples. Try decreasing K." << endl;
+        exit(-1);
+      }
+    }
+  }
+  return ref;
 }
 
 // plink::write_binary(basename, metadata, H, Hk, random) (plink_interface.cpp:255-284): the .bed body comes from the device

@@ -140,3 +140,36 @@ def test_dropin_binary_all_resolutions_one_plan_sharded(tmp_path):
         assert np.array_equal(bed[3:].reshape(want.shape), want), f"resolution {res}"
         checked += 1
     assert checked == 4
+
+
+@pytest.mark.gpu
+@needs_binary
+def test_dropin_binary_haps_input(tmp_path):
+    """The same drop-in fed `--haps` text input (HapsReader::read replaced by kgw_haps_read in the shim) and preloaded
+    references: the `.bed` must be (H, this library's Hk) for the synthetic population that was written to the text files."""
+    kg = pytest.importorskip("knockoffgwas_b200")
+    import sys
+    sys.path.insert(0, str(REPO / "oracle"))
+    import refio
+    from knockoffgwas_b200 import synth
+    sp = synth.make_problem_fast(240, 500, 10, seed=33, n_founders=30, mean_group=3.0, mean_dist_cm=0.02)
+    files = refio.write_inputs(tmp_path / "in", sp.H, sp.p, sp.ref, sp.groups, sp.cm, sp.bp)
+    out = tmp_path / "out"
+    out.mkdir()
+    args = [str(BINARY), "--haps", files["prefix"], "--map", files["map"], "--part", files["part"], "--ref", files["ref"],
+            "--lref", files["lref"], "--hmm-rho", "1.0", "--hmm-lambda", "0.001", "--windows", "0", "--resolution", "0",
+            "--seed", str(sp.seed), "--n_threads", "1", "--generate-knockoffs", "--out", str(out / "ko")]
+    got = {}
+    for io in ("1", "0"):                                 # shim reader / writer, then the reference's own around the device sampler
+        env = dict(os.environ, KGW_SHIM_IO=io)
+        r = subprocess.run(args, env=env, capture_output=True, text=True, cwd=str(out), timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        beds = sorted(out.glob("*_res0.bed"))
+        assert len(beds) == 1
+        got[io] = np.fromfile(beds[0], dtype=np.uint8)
+    assert np.array_equal(got["1"], got["0"]), "the shim's HAPS reader / .bed writer and the reference's give different files"
+    # the reference's init_hmm(rho, lambda) on the spline-interpolated map: b agrees with the synthetic table to ~1e-15, which
+    # cannot move a draw here; the knockoffs must be the library's for (H, references, groups) as they were written
+    hk, _ = kg.generate(sp.H, sp.p, sp.K, sp.ref[:, None, :], sp.b, sp.mu, sp.groups, seed=sp.seed)
+    want = kg.bed_encode(sp.H, hk, sp.p)
+    assert np.array_equal(got["1"][3:].reshape(want.shape), want)
