@@ -324,7 +324,8 @@ namespace {
 // the flat structures of kgw_family.cuh.
 // One of the two compiled classes of the family kernel (kgw_family.cuh): its families, launch shape and slot scratch
 struct FamClass {
-  int count = 0, n_max = 0, rtot = 1, grid = 0, threads = 128;
+  int count = 0, n_max = 0, rtot = 1, grid = 0, threads = 128, members = 0;
+  size_t nslots = 0;
   size_t smem = 0;
   std::vector<int32_t> list;                      // descriptor indices of the class
   int32_t *dlist = nullptr, *dwork = nullptr, *dflg = nullptr;
@@ -334,7 +335,8 @@ struct FamClass {
 
 struct FamilyState {
   int n_families = 0, members_total = 0, SF = 1;
-  FamClass cls[2];                                // [0] small families (registers / shared memory), [1] everything else
+  FamClass cls[3];                                // [0] small families (registers / shared memory), [1] everything else,
+                                                  // [2] pairs: phases split over launches (kgw_pairs.cuh)
   std::vector<int32_t> h_members;                 // concatenated, family order
   std::vector<int32_t> h_fam_off, h_seg_off, h_seg_jmin, h_seg_jmax, h_seg_ids_off, h_seg_ids;
   // device
@@ -346,6 +348,11 @@ struct FamilyState {
   cudaStream_t side = nullptr;             // the related branch runs beside the unrelated one when both fit on the SMs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = false;
+  bool pair_kernels = true;                // the pair class runs its final draws / knockoffs in kgw_pairs.cuh's kernels
+  bool pair_ops_ok = false;                // ... the knockoffs only when every pair's operation list allows it (fam_upload_partition)
+  std::vector<int32_t> pair_op_start;      // per batch of the pair class: first DRAW operation in dpair_ops (+ end)
+  KgwPairOp *dpair_ops = nullptr;
+  size_t cap_pair_ops = 0;
   int32_t *dref_global = nullptr;
   KgwFamInterval *divs = nullptr;
   KgwFamOp *dops = nullptr;
@@ -360,6 +367,7 @@ struct FamilyState {
     cudaFree(dfams); cudaFree(dmembers); cudaFree(divstart); cudaFree(dgroups); cudaFree(dgfirst); cudaFree(dglast);
     cudaFree(dstatus); cudaFree(dref_global); cudaFree(divs); cudaFree(dops); cudaFree(dloc); cudaFree(dko);
     cudaFree(demtab); cudaFree(ddbg_z); cudaFree(ddbg_zk);   // dmsg / dpat / dbytes belong to the plan's pool
+    cudaFree(dpair_ops);
 #ifdef KGW_PHASES
     if (dphase) {
       long long h[8];
@@ -509,6 +517,8 @@ void fam_build_ops(const FamilyState &F, int f, const int32_t *groups, const std
 
 typedef void (*kgw_fam_kernel_fn)(const KgwFamParams);
 kgw_fam_kernel_fn kgw_family_kernel_big_(int SF, bool uniform_mu);   // kgw_family_big.cu
+int kgw_pair_draw_launch(const KgwFamParams &P, cudaStream_t st);   // kgw_pairs.cu
+int kgw_pair_ko_launch(const KgwFamParams &P, const KgwPairOp *ops, int n_ops, int sm_count, cudaStream_t st);
 
 struct kgw_plan {
   int device = 0, sm_count = 148;
@@ -619,6 +629,56 @@ int fam_upload_partition(kgw_plan *pl, const int32_t *groups) {
     fam_build_ops(*F, f, groups, gfirst, glast, ops);
     F->fams[f].n_ops = (int)ops.size() - F->fams[f].op_off;
   }
+  // Pair class (kgw_pairs.cuh): the DRAW operations of a batch run side by side in one kernel, the copies afterwards.
+  // That is the reference's result when, per pair, (1) nothing written by a DRAW or copied by a COPYZK is written again
+  // later, (2) the source of a COPYZK is not written after the copy; a COPYZ whose groups a later operation overwrites
+  // is dropped.  The reference's lists for pairs always qualify (the DRAW ranges avoid the boundary groups unless they
+  // start at group 0 / end at the last one, family_knockoffs.cpp:172-193); checked here all the same, and if one does
+  // not, the class runs its operation lists in order inside family_kernel.
+  std::vector<KgwPairOp> pair_ops;
+  F->pair_op_start.assign(1, 0);
+  F->pair_ops_ok = true;
+  {
+    FamClass &C = F->cls[2];
+    struct Rg { int i, a, b; };   // member, loci a..b
+    auto range_of = [&](const KgwFamOp &op) -> Rg {
+      if (op.kind == KGW_FOP_DRAW) return Rg{op.i, gfirst[op.a], glast[op.b]};
+      return Rg{op.i, op.a, op.b};
+    };
+    auto hits = [](const Rg &x, int i, int a, int b) { return x.i == i && x.a <= b && a <= x.b; };
+    std::vector<char> drop;
+    for (int t = 0; t < C.count && F->pair_ops_ok; t++) {
+      KgwFamDesc &d = F->fams[C.list[t]];
+      const int o0 = d.op_off, o1 = d.op_off + d.n_ops;
+      drop.assign(d.n_ops, 0);
+      for (int a = o0; a < o1 && F->pair_ops_ok; a++) {
+        const Rg ra = range_of(ops[a]);
+        for (int b = a + 1; b < o1; b++) {
+          const Rg rb = range_of(ops[b]);
+          const bool over = hits(rb, ra.i, ra.a, ra.b);
+          if (ops[a].kind == KGW_FOP_COPYZ) { if (over) drop[a - o0] = 1; }
+          else if (over) F->pair_ops_ok = false;
+          if (ops[a].kind == KGW_FOP_COPYZK && hits(rb, ops[a].src, ra.a, ra.b)) F->pair_ops_ok = false;
+        }
+      }
+      if (!F->pair_ops_ok) break;
+      for (int a = o0; a < o1; a++) if (drop[a - o0]) { ops[a].a = 0; ops[a].b = -1; }   // an empty copy
+    }
+    if (F->pair_ops_ok && C.count > 0) {
+      const int nsl = (int)std::max<size_t>(C.nslots, 1);
+      for (int f0 = 0; f0 < C.count; f0 += nsl) {
+        const size_t first = pair_ops.size();
+        for (int t = f0; t < std::min(C.count, f0 + nsl); t++) {
+          const KgwFamDesc &d = F->fams[C.list[t]];
+          for (int a = d.op_off; a < d.op_off + d.n_ops; a++)
+            if (ops[a].kind == KGW_FOP_DRAW) pair_ops.push_back(KgwPairOp{t, ops[a].i, gfirst[ops[a].a], glast[ops[a].b]});
+        }
+        std::stable_sort(pair_ops.begin() + first, pair_ops.end(),
+                         [](const KgwPairOp &x, const KgwPairOp &y) { return x.j1 - x.j0 > y.j1 - y.j0; });   // longest first
+        F->pair_op_start.push_back((int32_t)pair_ops.size());
+      }
+    }
+  }
   std::vector<int32_t> gf(gfirst.begin(), gfirst.end()), gl(glast.begin(), glast.end());
   // grow-only device buffers (a plan sees one partition after the other, main.cpp:159-181) and copies on the
   // plan's stream; one synchronisation at the end because the host vectors go out of scope
@@ -632,6 +692,8 @@ int fam_upload_partition(kgw_plan *pl, const int32_t *groups) {
     return kgw_malloc(ptr, *cap);
   };
   KGW_CUDA(grow(&F->dops, &F->cap_ops, sizeof(KgwFamOp) * std::max<size_t>(ops.size(), 1)));
+  KGW_CUDA(grow(&F->dpair_ops, &F->cap_pair_ops, sizeof(KgwPairOp) * std::max<size_t>(pair_ops.size(), 1)));
+  KGW_CUDA(cudaMemcpyAsync(F->dpair_ops, pair_ops.data(), sizeof(KgwPairOp) * pair_ops.size(), cudaMemcpyHostToDevice, pl->stream));
   KGW_CUDA(grow(&F->dgfirst, &F->cap_gfirst, sizeof(int32_t) * G));
   KGW_CUDA(grow(&F->dglast, &F->cap_glast, sizeof(int32_t) * G));
   if (!F->dko) KGW_CUDA(kgw_malloc(&F->dko, sizeof(KgwLocusKO) * p));
@@ -707,6 +769,9 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   std::vector<int32_t> iv_start, ivlist;
   std::vector<KgwFamRange> ranges;
   F->fams.resize(F->n_families);
+  bool pair_class = true;   // development: KGW_PAIR_CLASS=0 sends pairs through the one-launch family kernel
+  { const char *e = getenv("KGW_PAIR_CLASS"); if (e && e[0] == '0') pair_class = false; }
+  { const char *e = getenv("KGW_PAIR_KERNELS"); if (e && e[0] == '0') F->pair_kernels = false; }   // development: phases split, old code
   for (int f = 0; f < F->n_families; f++) {
     const int n = F->h_fam_off[f + 1] - F->h_fam_off[f];
     if (n < 1) return fail(KGW_ERR_INVALID, "empty family");
@@ -741,9 +806,11 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
       stored += ranges[r].s1 - std::max(0, ranges[r].s0 - 1) + 1;
     }
     // class of the family: registers / shared memory / pattern bytes suffice for small ones (kgw_family.cuh)
-    FamClass &C = F->cls[(n > KGW_FAM_MAXN || max_nn > KGW_FAM_MAXNB) ? 1 : 0];
+    const bool big_family = (n > KGW_FAM_MAXN || max_nn > KGW_FAM_MAXNB);
+    FamClass &C = F->cls[big_family ? 1 : ((n == 2 && pair_class) ? 2 : 0)];
     C.list.push_back(f);
     C.count++;
+    C.members += n;
     C.n_max = std::max(C.n_max, n);
     C.rtot = std::max(C.rtot, std::max(stored, 1));
   }
@@ -761,7 +828,8 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
         emtab[nn * 256 + pt] = v;
       }
   }
-  std::vector<KgwFamLocus> loc(p);
+  std::vector<KgwFamLocus> loc(p + 1);   // (one zero entry behind the last locus: kgw_pairs.cuh reads a locus ahead)
+  memset(&loc[p], 0, sizeof(KgwFamLocus));
   const double alpha = 1.0 / K;
   for (int j = 0; j < p; j++) {
     loc[j].b = pl->b[j];
@@ -775,7 +843,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMalloc(&F->dmembers, sizeof(int32_t) * F->members_total));
   KGW_CUDA(cudaMalloc(&F->divstart, sizeof(int32_t) * iv_start.size()));
   KGW_CUDA(cudaMalloc(&F->divs, sizeof(KgwFamInterval) * ivs.size()));
-  KGW_CUDA(cudaMalloc(&F->dloc, sizeof(KgwFamLocus) * p));
+  KGW_CUDA(cudaMalloc(&F->dloc, sizeof(KgwFamLocus) * (p + 1)));
   KGW_CUDA(cudaMalloc(&F->demtab, sizeof(double) * emtab.size()));
   KGW_CUDA(cudaMalloc(&F->dref_global, sizeof(int32_t) * (size_t)N * K));
   KGW_CUDA(cudaMalloc(&F->dstatus, sizeof(int32_t)));
@@ -791,7 +859,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMemcpy(F->dmembers, F->h_members.data(), sizeof(int32_t) * F->members_total, cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->divstart, iv_start.data(), sizeof(int32_t) * iv_start.size(), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->divs, ivs.data(), sizeof(KgwFamInterval) * ivs.size(), cudaMemcpyHostToDevice));
-  KGW_CUDA(cudaMemcpy(F->dloc, loc.data(), sizeof(KgwFamLocus) * p, cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dloc, loc.data(), sizeof(KgwFamLocus) * (p + 1), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->demtab, emtab.data(), sizeof(double) * emtab.size(), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->dref_global, prob->ref_global, sizeof(int32_t) * (size_t)N * K, cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemset(F->dstatus, 0, sizeof(int32_t)));
@@ -804,13 +872,17 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   size_t free_b = 0, total_b = 0;
   KGW_CUDA(cudaMemGetInfo(&free_b, &total_b));
   free_b += g_pool.parked(pl->device);
-  for (int c = 1; c >= 0; c--) {
+  static const int class_order[3] = {1, 0, 2};
+  for (int ci = 0; ci < 3; ci++) {
+    const int c = class_order[ci];
     FamClass &C = F->cls[c];
     if (C.count == 0) continue;
-    const bool big = (c == 1);
+    const bool big = (c == 1), pairs = (c == 2);
     size_t per_slot = (size_t)C.n_max * p * ((size_t)K * 9 + 2) + (size_t)C.n_max * C.rtot * K * sizeof(double);
     if (big) per_slot += (size_t)2 * C.n_max * KP * sizeof(double) + (size_t)5 * C.n_max * sizeof(int32_t);
-    const double budget = (double)free_b * (big ? 0.4 : 0.95);   // (the sampler sized its scratch with the families in mind)
+    // (the sampler sized its scratch with the families in mind); the small class leaves the pairs their share
+    double budget = (double)free_b * (big ? 0.4 : 0.95);
+    if (c == 0 && F->cls[2].count > 0) budget *= (double)C.members / (double)(C.members + F->cls[2].members);
     // CTAs of four warps; a big class whose slots are too large for four of them runs single-warp CTAs
     C.threads = (big && (double)per_slot * 4 > budget) ? 32 : 128;
     const int wpc = C.threads / 32;
@@ -824,15 +896,23 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     }
     const long long slots_mem = (long long)(budget / (double)per_slot);
     if (slots_mem < wpc) return fail(KGW_ERR_NOMEM, "not enough device memory for the message tables of one IBD family");
-    const long long want = std::min<long long>(C.count, (long long)dp.multiProcessorCount * ctas_per_sm * wpc);
-    long long ctas = (want + wpc - 1) / wpc;
-    if (ctas * wpc > slots_mem) ctas = slots_mem / wpc;
-    C.grid = (int)std::max<long long>(1, ctas);
-    const size_t nslots = (size_t)C.grid * wpc;
-    KGW_CUDA(pl->alloc(&C.dmsg, sizeof(double) * C.n_max * (size_t)p * K * nslots));   // pooled with the plan's buffers
+    size_t nslots;
+    if (pairs) {
+      // a slot per pair of the batch in flight (the phases are separate launches): as many as fit, whole CTAs
+      nslots = (size_t)std::min<long long>(C.count, slots_mem);
+      C.grid = (int)((nslots + wpc - 1) / wpc);
+    } else {
+      const long long want = std::min<long long>(C.count, (long long)dp.multiProcessorCount * ctas_per_sm * wpc);
+      long long ctas = (want + wpc - 1) / wpc;
+      if (ctas * wpc > slots_mem) ctas = slots_mem / wpc;
+      C.grid = (int)std::max<long long>(1, ctas);
+      nslots = (size_t)C.grid * wpc;
+    }
+    C.nslots = nslots;
+    KGW_CUDA(pl->alloc(&C.dmsg, sizeof(double) * (C.n_max * (size_t)p * K * nslots + 2 * (size_t)K + 64)));   // (two rows of padding: kgw_pairs.cuh)   // pooled with the plan's buffers
     KGW_CUDA(pl->alloc(&C.dmrc, sizeof(double) * C.n_max * (size_t)C.rtot * K * nslots));
-    KGW_CUDA(pl->alloc(&C.dpat, (size_t)C.n_max * p * K * nslots));
-    KGW_CUDA(pl->alloc(&C.dbytes, (size_t)2 * C.n_max * p * nslots));
+    KGW_CUDA(pl->alloc(&C.dpat, (size_t)C.n_max * p * K * nslots + 2 * (size_t)K + 64));
+    KGW_CUDA(pl->alloc(&C.dbytes, (size_t)2 * C.n_max * p * nslots + 64));
     if (big) {
       KGW_CUDA(pl->alloc(&C.dpmg, sizeof(double) * 2 * C.n_max * KP * nslots));
       KGW_CUDA(pl->alloc(&C.dflg, sizeof(int32_t) * 5 * C.n_max * nslots));
@@ -865,17 +945,46 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
 int fam_launch(kgw_plan *pl, cudaStream_t st) {
   FamilyState *F = pl->fam;
   if (!F || F->n_families == 0) return KGW_OK;
-  for (int c = 0; c < 2; c++) {   // one launch per class that has families
+  for (int c = 0; c < 3; c++) {   // one launch per class that has families (pairs: one per phase and batch)
     FamClass &C = F->cls[c];
     if (C.count == 0) continue;
     fam_kernel_fn fn = fam_kernel_for(F->SF, F->P.uniform_mu != 0, c == 1);
     KGW_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem));
-    KGW_CUDA(cudaMemsetAsync(C.dwork, 0, sizeof(int32_t), st));
     KgwFamParams Pc = F->P;
     Pc.n_families = C.count; Pc.fam_list = C.dlist; Pc.n_max = C.n_max; Pc.rtot = C.rtot;
     Pc.msg = C.dmsg; Pc.mrc = C.dmrc; Pc.pat = C.dpat; Pc.bytes = C.dbytes; Pc.pmg = C.dpmg; Pc.flg = C.dflg; Pc.work = C.dwork;
-    fn<<<C.grid, C.threads, C.smem, st>>>(Pc);
-    KGW_CUDA(cudaGetLastError());
+    Pc.phase_mask = KGW_FPH_ALL; Pc.slot_by_family = 0; Pc.f_base = 0;
+    if (c != 2) {
+      KGW_CUDA(cudaMemsetAsync(C.dwork, 0, sizeof(int32_t), st));
+      fn<<<C.grid, C.threads, C.smem, st>>>(Pc);
+      KGW_CUDA(cudaGetLastError());
+      continue;
+    }
+    // pairs: batches of as many pairs as there are slots; belief propagation one warp per pair, then the two
+    // chain-sequential phases with several chains per warp (kgw_pairs.cuh), then checks and alleles
+    Pc.slot_by_family = 1;
+    const int wpc = C.threads / 32;
+    for (int f0 = 0; f0 < C.count; f0 += (int)C.nslots) {
+      const int f1 = std::min<int>(C.count, f0 + (int)C.nslots);
+      const int grid = (f1 - f0 + wpc - 1) / wpc;
+      Pc.f_base = f0; Pc.n_families = f1;
+      const bool fast_ko = F->pair_kernels && F->pair_ops_ok;
+      const int masks[4] = {KGW_FPH_INIT | KGW_FPH_BP, KGW_FPH_DRAW, KGW_FPH_KO, KGW_FPH_OUT | (fast_ko ? KGW_FPH_KOCOPY : 0)};
+      for (int ph = 0; ph < 4; ph++) {
+        Pc.phase_mask = masks[ph];
+        if (ph == 1 && F->pair_kernels) { int rc = kgw_pair_draw_launch(Pc, st); if (rc != KGW_OK) return fail(rc, "launch of the pair draw kernel failed"); continue; }
+        KGW_CUDA(cudaMemsetAsync(C.dwork, 0, sizeof(int32_t), st));
+        if (ph == 2 && fast_ko) {
+          const int b = f0 / (int)C.nslots;
+          const int o0 = F->pair_op_start[b], o1 = F->pair_op_start[b + 1];
+          int rc = kgw_pair_ko_launch(Pc, F->dpair_ops + o0, o1 - o0, pl->sm_count, st);
+          if (rc != KGW_OK) return fail(rc, "launch of the pair knockoff kernel failed");
+          continue;
+        }
+        fn<<<grid, C.threads, C.smem, st>>>(Pc);
+        KGW_CUDA(cudaGetLastError());
+      }
+    }
   }
   return KGW_OK;
 }
@@ -1588,7 +1697,7 @@ int32_t kgw_plan_info(kgw_plan *pl, kgw_plan_info_t *out) {
     out->reserved = (int32_t)pl->subs.size();
     return KGW_OK;
   }
-  out->launches_per_run = (pl->n_haps > 0 ? 1 : 0) + (pl->fam ? (pl->fam->cls[0].count > 0) + (pl->fam->cls[1].count > 0) : 0);
+  out->launches_per_run = (pl->n_haps > 0 ? 1 : 0) + (pl->fam ? (pl->fam->cls[0].count > 0) + (pl->fam->cls[1].count > 0) + 4 * (int)((pl->fam->cls[2].count + std::max<size_t>(pl->fam->cls[2].nslots, 1) - 1) / std::max<size_t>(pl->fam->cls[2].nslots, 1)) : 0);
   out->grid = pl->grid;
   out->block = pl->threads;
   out->lanes_per_hap = pl->var->L;

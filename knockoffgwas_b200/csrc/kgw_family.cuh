@@ -68,11 +68,20 @@ struct KgwFamRange {   // special loci s0 .. s1, inclusive; sorted, disjoint
   int32_t pad;
 };
 
+// phases of a family (KgwFamParams::phase_mask); KOCOPY: only the copy operations of FamilyKnockoffs::run (the pair
+// class draws in a kernel of its own, kgw_pairs.cuh)
+enum { KGW_FPH_INIT = 1, KGW_FPH_BP = 2, KGW_FPH_DRAW = 4, KGW_FPH_KO = 8, KGW_FPH_OUT = 16, KGW_FPH_ALL = 31, KGW_FPH_KOCOPY = 32 };
 enum { KGW_FOP_COPYZ = 0, KGW_FOP_DRAW = 1, KGW_FOP_COPYZK = 2 };
 struct KgwFamOp {  // FamilyKnockoffs::run (family_knockoffs.cpp:155-270) flattened in execution order
   int32_t kind;    // COPYZ: Zk[i][a..b] = Z[i][a..b];  DRAW: sample_knockoff_MC(i, groups a..b);  COPYZK: Zk[i][a..b] = Zk[src][a..b]
   int32_t i, a, b, src;
   int32_t pad[3];
+};
+
+struct KgwPairOp {   // one DRAW operation of a pair (kgw_pairs.cuh)
+  int32_t f;         // the pair: index into fam_list
+  int32_t i;         // member
+  int32_t j0, j1;    // loci grp_first[g_begin] .. grp_last[g_end]
 };
 
 struct KgwFamDesc {
@@ -120,6 +129,10 @@ struct KgwFamParams {
   double *pmg;                 // BIG class: [slots][2][n_max][KP] running messages of a sweep (SMALL: shared memory)
   int32_t *flg;                // BIG class: [slots][5][n_max] per-member bookkeeping of a sweep (SMALL: registers)
   int32_t *work;               // next family to hand out (zeroed before every launch)
+  int32_t phase_mask;          // KGW_FPH_* phases this launch runs
+  int32_t slot_by_family;      // scratch slot = family's index in the batch (phases split over launches) instead of the warp's
+  int32_t f_base;              // first family (index into fam_list) of this launch's batch; n_families = one past its last
+  int32_t pad_;
   unsigned long long seed;
   const double *injected_u;    // [N][W][3][p] or null (the related branch reads window block 0)
   int32_t *dbg_z, *dbg_zk;     // [members total][p] or null
@@ -216,6 +229,10 @@ __device__ __forceinline__ int warp_choice_contig(const double (&w)[SF], double 
 
 // SF: states per lane; UMU: mu is the same at every locus (init_hmm, knockoffs.cpp:1520) and node emissions
 // come from the shared-memory table, else they are formed per state with pow() as the reference does
+// P.phase_mask selects the phases a launch runs (KGW_FPH_*).  The PAIR class (kgw_pairs.cuh) runs belief propagation
+// here, one warp per pair, and the chain-sequential phases (final draws, family knockoffs) in kernels of their own with
+// several chains per warp; the state between the launches lives in the scratch slot, which is then the family's index
+// in the batch (P.slot_by_family) instead of the resident warp's.
 template <int SF, bool UMU, bool BIG>
 __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_constant__ KgwFamParams P) {
   constexpr int KP = SF * 32;
@@ -225,11 +242,6 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
   const int slot = blockIdx.x * wpc + wid;
   const int p = P.p, K = P.K;
   const size_t pK = (size_t)p * K;
-  double *ml_base = P.msg + (size_t)slot * P.n_max * pK;                       // messages_left [n][p][K]
-  double *mrc = P.mrc + (size_t)slot * P.n_max * (size_t)P.rtot * K;          // messages_right, stored loci only
-  uint8_t *pat_base = P.pat + (size_t)slot * P.n_max * pK;
-  uint8_t *Zb = P.bytes + (size_t)slot * 2 * P.n_max * p;     // 255 = not drawn yet = node still active
-  uint8_t *Zkb = Zb + (size_t)P.n_max * p;
 
   extern __shared__ __align__(16) unsigned char fam_smem[];
   double *tab = reinterpret_cast<double *>(fam_smem);                       // [8][256], shared by the CTA
@@ -246,11 +258,13 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
   __syncthreads();
   const double p0 = 1.0 / ((double)K);   // initial value of every message (family_bp.cpp:421-427)
 
-  for (;;) {
-    int f = 0;
-    if (lane == 0) f = atomicAdd(P.work, 1);
-    f = __shfl_sync(FULL, f, 0);
-    if (f >= P.n_families) break;
+  // the phases `mask` of family `f` (index into this launch's list) in scratch slot `sub` of the warp
+  auto family_phases = [&](const int f, const size_t fslot, const unsigned mask) {
+    double *ml_base = P.msg + fslot * P.n_max * pK;                       // messages_left [n][p][K]
+    double *mrc = P.mrc + fslot * P.n_max * (size_t)P.rtot * K;          // messages_right, stored loci only
+    uint8_t *pat_base = P.pat + fslot * P.n_max * pK;
+    uint8_t *Zb = P.bytes + fslot * 2 * P.n_max * p;     // 255 = not drawn yet = node still active
+    uint8_t *Zkb = Zb + (size_t)P.n_max * p;
     const KgwFamDesc fd = P.fams[P.fam_list[f]];
     const int n = fd.n;
     const int32_t *mem = P.members + fd.mem_off;
@@ -309,10 +323,17 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
 
     // ---- initialise: nothing drawn, match patterns.  The messages are NOT written: the first BP
     //      iteration substitutes their initial value 1/K wherever the reference would read it.
+    if (mask & KGW_FPH_INIT)
     for (int i = 0; i < n; i++) {
       const int i_abs = mem[i];
       const int32_t *ref = P.ref_global + (size_t)i_abs * K;
       for (int j = lane; j < p; j += 32) { Zb[(size_t)i * p + j] = 255; Zkb[(size_t)i * p + j] = 255; }
+      // row 0 of a member's left messages is never touched by belief propagation (the left sweep ends at locus 1);
+      // it is row p of the member before it: ones, the empty product a draw at the last locus sees (kgw_pairs.cuh)
+      for (int k = lane; k < K; k += 32) {
+        ml_base[(size_t)i * pK + k] = 1.0;
+        if (i == n - 1) ml_base[(size_t)n * pK + k] = 1.0;   // (row 0 of the next slot, or the padding behind the last one)
+      }
       for (int k = lane; k < K; k += 32) {
         const size_t rrow = (size_t)__ldg(ref + k) * P.stride_w;
         const KgwFamInterval *iv = P.ivs + ivs0[i];
@@ -800,7 +821,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     // ---- FamilyBP::run (family_bp.cpp:79-100) and sample_posterior (:160-230): BP, then the junction nodes in
     //      (member, locus) order -- they sit at interval ends (:168-193) -- each followed by a BP re-run (:194-211).
     //      One loop with a cursor over (member, interval, end), so that run_bp is instantiated once.
-    {
+    if (mask & KGW_FPH_BP) {
       int ci = 0, ce = 0;
       const KgwFamInterval *civ = P.ivs + ivs0[0];
       bool first = true;
@@ -839,6 +860,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     // would have stored (:243-246) and is formed from the previous draw; nothing reads the right messages
     // afterwards, so they are not written.  messages_left[i][j+1] and the pattern bytes are fetched one
     // locus ahead of the (serial) draw.  Lane l owns the contiguous states l*SF .. here (warp_choice_contig).
+    if (mask & KGW_FPH_DRAW)
     for (int i = 0; i < n; i++) {
       const KgwFamInterval *iv = P.ivs + ivs0[i];
       int ivj1 = iv->j1, ivnn = iv->nn;
@@ -919,8 +941,10 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     KGW_FAM_PHASE(4);
     // ---- FamilyKnockoffs::run (family_knockoffs.cpp:77-293) as a flat op list
     const KgwFamOp *ops = P.ops + fd.op_off;
+    if (mask & (KGW_FPH_KO | KGW_FPH_KOCOPY))
     for (int q = 0; q < fd.n_ops; q++) {
       const KgwFamOp op = ops[q];
+      if (op.kind == KGW_FOP_DRAW && !(mask & KGW_FPH_KO)) continue;
       if (op.kind == KGW_FOP_COPYZ) {
         for (int j = op.a + lane; j <= op.b; j += 32) Zkb[(size_t)op.i * p + j] = Zb[(size_t)op.i * p + j];
       } else if (op.kind == KGW_FOP_COPYZK) {
@@ -1007,6 +1031,7 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     }
 
     KGW_FAM_PHASE(5);
+    if (!(mask & KGW_FPH_OUT)) return;
     // ---- the reference's final checks (family_knockoffs.cpp:272-291)
     int bad = 0;
     for (int i = 0; i < n; i++) {
@@ -1053,6 +1078,14 @@ __global__ void __launch_bounds__(128, KGW_FAM_MINB) family_kernel(const __grid_
     }
     __syncwarp();
     KGW_FAM_PHASE(6);
+  };
+
+  for (;;) {
+    int f = 0;
+    if (lane == 0) f = atomicAdd(P.work, 1);
+    f = __shfl_sync(FULL, f, 0) + P.f_base;
+    if (f >= P.n_families) break;
+    family_phases(f, P.slot_by_family ? (size_t)(f - P.f_base) : (size_t)slot, (unsigned)P.phase_mask);
   }
 }
 

@@ -199,7 +199,7 @@ def test_family_kernel_large_families(size, segments, p, K, max_subset, uniform_
                       groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
     plan = kg.Plan(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=np.zeros(0, np.int32), ref_global=sp.ref,
                    seed=sp.seed, families=sp.families)
-    assert plan.info()["launches_per_run"] == 2
+    assert plan.info()["launches_per_run"] == 5   # the big class's kernel + the four phase launches of the pairs' batch
     plan.run()
     hk, dbg = plan.download(debug_paths=True)
     plan.close()
