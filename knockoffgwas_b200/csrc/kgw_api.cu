@@ -909,9 +909,9 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
       nslots = (size_t)C.grid * wpc;
     }
     C.nslots = nslots;
-    KGW_CUDA(pl->alloc(&C.dmsg, sizeof(double) * (C.n_max * (size_t)p * K * nslots + 2 * (size_t)K + 64)));   // (two rows of padding: kgw_pairs.cuh)   // pooled with the plan's buffers
+    KGW_CUDA(pl->alloc(&C.dmsg, sizeof(double) * (C.n_max * (size_t)p * K * nslots + 8 * (size_t)K + 64)));   // (rows of padding: kgw_pairs.cuh reads ahead)   // pooled with the plan's buffers
     KGW_CUDA(pl->alloc(&C.dmrc, sizeof(double) * C.n_max * (size_t)C.rtot * K * nslots));
-    KGW_CUDA(pl->alloc(&C.dpat, (size_t)C.n_max * p * K * nslots + 2 * (size_t)K + 64));
+    KGW_CUDA(pl->alloc(&C.dpat, (size_t)C.n_max * p * K * nslots + 8 * (size_t)K + 64));
     KGW_CUDA(pl->alloc(&C.dbytes, (size_t)2 * C.n_max * p * nslots + 64));
     if (big) {
       KGW_CUDA(pl->alloc(&C.dpmg, sizeof(double) * 2 * C.n_max * KP * nslots));
@@ -969,21 +969,25 @@ int fam_launch(kgw_plan *pl, cudaStream_t st) {
       const int grid = (f1 - f0 + wpc - 1) / wpc;
       Pc.f_base = f0; Pc.n_families = f1;
       const bool fast_ko = F->pair_kernels && F->pair_ops_ok;
-      const int masks[4] = {KGW_FPH_INIT | KGW_FPH_BP, KGW_FPH_DRAW, KGW_FPH_KO, KGW_FPH_OUT | (fast_ko ? KGW_FPH_KOCOPY : 0)};
-      for (int ph = 0; ph < 4; ph++) {
-        Pc.phase_mask = masks[ph];
-        if (ph == 1 && F->pair_kernels) { int rc = kgw_pair_draw_launch(Pc, st); if (rc != KGW_OK) return fail(rc, "launch of the pair draw kernel failed"); continue; }
+      auto family_phases = [&](int mask) -> int {
+        Pc.phase_mask = mask;
         KGW_CUDA(cudaMemsetAsync(C.dwork, 0, sizeof(int32_t), st));
-        if (ph == 2 && fast_ko) {
-          const int b = f0 / (int)C.nslots;
-          const int o0 = F->pair_op_start[b], o1 = F->pair_op_start[b + 1];
-          int rc = kgw_pair_ko_launch(Pc, F->dpair_ops + o0, o1 - o0, pl->sm_count, st);
-          if (rc != KGW_OK) return fail(rc, "launch of the pair knockoff kernel failed");
-          continue;
-        }
         fn<<<grid, C.threads, C.smem, st>>>(Pc);
         KGW_CUDA(cudaGetLastError());
-      }
+        return KGW_OK;
+      };
+      int rc = KGW_OK;
+      if ((rc = family_phases(KGW_FPH_INIT | KGW_FPH_BP)) != KGW_OK) return rc;
+      if (F->pair_kernels) {
+        if (kgw_pair_draw_launch(Pc, st) != KGW_OK) return fail(KGW_ERR_CUDA, "launch of the pair draw kernel failed");
+      } else if ((rc = family_phases(KGW_FPH_DRAW)) != KGW_OK) return rc;
+      if (fast_ko) {
+        const int b = f0 / (int)C.nslots;
+        const int o0 = F->pair_op_start[b], o1 = F->pair_op_start[b + 1];
+        KGW_CUDA(cudaMemsetAsync(C.dwork, 0, sizeof(int32_t), st));
+        if (kgw_pair_ko_launch(Pc, F->dpair_ops + o0, o1 - o0, pl->sm_count, st) != KGW_OK) return fail(KGW_ERR_CUDA, "launch of the pair knockoff kernel failed");
+      } else if ((rc = family_phases(KGW_FPH_KO)) != KGW_OK) return rc;
+      if ((rc = family_phases(KGW_FPH_OUT | (fast_ko ? KGW_FPH_KOCOPY : 0))) != KGW_OK) return rc;
     }
   }
   return KGW_OK;
@@ -1074,7 +1078,7 @@ namespace {
 // independent of each other (:440-445), so there is no exchange between devices: every device holds H and the
 // references, runs an ordinary plan on its share and copies its rows of Hk straight into the caller's buffer
 // (disjoint rows).  A family costs KGW_FAMILY_COST unrelated haplotypes per member (measured).
-constexpr double KGW_FAMILY_COST = 7.0;
+constexpr double KGW_FAMILY_COST = 5.0;
 
 struct SubProblem {
   kgw_problem prob;

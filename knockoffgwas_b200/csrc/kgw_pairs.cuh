@@ -22,6 +22,10 @@
 #include "kgw_family.cuh"
 #include <type_traits>
 
+#ifndef KGW_DRAW_RING
+#define KGW_DRAW_RING 2   // loci between the request of a draw's inputs and the draw (measured: 1 -> 40.6 ms, 2 -> 38.0 ms, 4 -> 50 ms
+#endif                    // on 2368 pairs x 10 000 SNPs, K=50: deeper rings put far-ahead and near-term loads on one scoreboard)
+
 namespace kgw {
 
 // sum over the L consecutive lanes of a chain
@@ -135,76 +139,84 @@ __global__ void __launch_bounds__(128) pair_draw_kernel(const __grid_constant__ 
   const uint8_t *ptp = P.pat + fslot * P.n_max * pK + (size_t)c * pK + m * S;
   const KgwFamLocus *lp = P.loc;   // [p + 1]
 
-  int zprev = -1;
-  double la_c = 1.0, lb_c = 0.0, mu_c = lp->mu;   // j == 0: no right message (factor 1)
-  double ml_c[S];
-  unsigned pt_c[S];
+  // The per-locus inputs (pattern bytes, left-message entries, transition constants, the Z byte) sit in a register
+  // ring D loci deep: a row is requested D loci before its draw, which covers an L2 hit; L2 prefetches run 12 + D ahead.
+  // Rows behind the last locus (the ring runs past it) are the next member's rows or the padding: never used.
+  constexpr int D = KGW_DRAW_RING;
+  double mlr[D][S], lar[D], lbr[D], mur[D];
+  unsigned ptr_[D][S];
+  int zr[D];
 #pragma unroll
-  for (int s = 0; s < S; s++) {
-    pt_c[s] = ptp[s];
-    ml_c[s] = mlp[(size_t)K + s];
+  for (int d = 0; d < D; d++) {
+#pragma unroll
+    for (int s = 0; s < S; s++) { ptr_[d][s] = ptp[(size_t)d * K + s]; mlr[d][s] = mlp[(size_t)(d + 1) * K + s]; }
+    lar[d] = (d == 0) ? 1.0 : lp[min(d, p)].a_al;   // j == 0: no right message (factor 1)
+    lbr[d] = (d == 0) ? 0.0 : lp[min(d, p)].b;
+    mur[d] = lp[min(d, p)].mu;
+    zr[d] = zrow[d];
   }
-  int z_c = zrow[0];
+  int zprev = -1;
   LgUniform<L> U;
   const int pf_off = m * 128;   // this lane's line of a row being prefetched
-  for (int j = 0; j < p; j++) {
-    // next locus: pattern j+1, left message j+2; L2 prefetches twelve loci ahead
-    double ml_n[S];
-    unsigned pt_n[S];
-    const double *mlp2 = mlp + (size_t)2 * K;
-    const uint8_t *ptp1 = ptp + K;
+  for (int jb = 0; jb < p; jb += D) {
 #pragma unroll
-    for (int s = 0; s < S; s++) {
-      pt_n[s] = ptp1[s];
-      ml_n[s] = mlp2[s];
-    }
-    const double la_n = lp[1].a_al, lb_n = lp[1].b, mu_n = lp[1].mu;
-    const int z_n = zrow[j + 1];
-    if (j + 12 < p) {
-      const char *row = reinterpret_cast<const char *>(mlp - m * S + (size_t)12 * K);
-      if (pf_off < K * 8) prefetch_l2(row + pf_off);
-      if (L * 128 < 256 * 8 && pf_off + L * 128 < K * 8) prefetch_l2(row + pf_off + L * 128);
-      if (m == 0) prefetch_l2(ptp + (size_t)13 * K);
-    }
-    if ((j & (4 * L - 1)) == 0) U.refill(P, i_abs, STREAM_Z, j, m);
-    const double u = U.get(j);
-    while (ivj1 < j) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
-    const bool active = (z_c == 255);
-    const double lab = la_c + lb_c * 1.0;   // the point-mass right message of the previous draw (:243-246) at k == zprev
-    const int zrel = zprev - m * S;
-    const int nnoff = ivnn * 256;
-    double wv[S];
+    for (int d = 0; d < D; d++) {
+      const int j = jb + d;
+      if (j >= p) break;
+      if (j + 12 + D < p) {
+        const char *row = reinterpret_cast<const char *>(mlp - m * S + (size_t)(12 + D) * K);
+        if (pf_off < K * 8) prefetch_l2(row + pf_off);
+        if (L * 128 < 256 * 8 && pf_off + L * 128 < K * 8) prefetch_l2(row + pf_off + L * 128);
+        if (m == 0) prefetch_l2(ptp + (size_t)(12 + D) * K);
+      }
+      if ((j & (4 * L - 1)) == 0) U.refill(P, i_abs, STREAM_Z, j, m);
+      const double u = U.get(j);
+      while (ivj1 < j) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
+      const int z_c = zr[d];
+      const bool active = (z_c == 255);
+      const double la_c = lar[d];
+      const double lab = la_c + lbr[d] * 1.0;   // the point-mass right message of the previous draw (:243-246) at k == zprev
+      const int zrel = zprev - m * S;
+      const int nnoff = ivnn * 256;
+      double wv[S];
 #pragma unroll
-    for (int s = 0; s < S; s++) {
-      double v;
-      if (UMU) v = tab[(int)pt_c[s] + nnoff + toff[s]];
-      else v = valid[s] ? pair_emission<false>(tab, pt_c[s], mu_c, ivnn) : 0.0;
-      v *= (s == zrel) ? lab : la_c;
-      wv[s] = v * ml_c[s];
-    }
-    const int kz = lg_choice<L, S>(wv, u, K, lane);
-    const int kz_o = __shfl_xor_sync(FULL, kz, L);
-    const bool act_o = __shfl_xor_sync(FULL, (int)active, L) != 0;
-    // member 0 is visited first (:217-229): its draw at a shared locus pins member 1's node as well; a draw of member 1
-    // there (member 0 pinned earlier, which belief propagation's junction draws never leave behind) overwrites Z[0][j]
-    int zst = -1;   // value to store
-    int znext = z_c;
-    if (active) { zst = kz; znext = kz; }
-    if (ivnn == 1 && act_o) {
-      if (c == 1) { zst = kz_o; znext = kz_o; }
-      else if (!active) zst = kz_o;
-    }
-    if (act && m == 0 && zst >= 0) zrow[j] = (uint8_t)zst;
-    zprev = znext;
+      for (int s = 0; s < S; s++) {
+        double v;
+        if (UMU) v = tab[(int)ptr_[d][s] + nnoff + toff[s]];
+        else v = valid[s] ? pair_emission<false>(tab, ptr_[d][s], mur[d], ivnn) : 0.0;
+        v *= (s == zrel) ? lab : la_c;
+        wv[s] = v * mlr[d][s];
+      }
+      // refill the ring entry: locus j + D (pattern, Z, constants) and left message j + D + 1
+      {
+        const uint8_t *pn = ptp + (size_t)D * K;
+        const double *mn = mlp + (size_t)(D + 1) * K;
 #pragma unroll
-    for (int s = 0; s < S; s++) { pt_c[s] = pt_n[s]; ml_c[s] = ml_n[s]; }
-    la_c = la_n;
-    lb_c = lb_n;
-    mu_c = mu_n;
-    z_c = z_n;
-    mlp += K;
-    ptp += K;
-    lp++;
+        for (int s = 0; s < S; s++) { ptr_[d][s] = pn[s]; mlr[d][s] = mn[s]; }
+        const KgwFamLocus *ln = lp + min(D, p - j);
+        lar[d] = ln->a_al;
+        lbr[d] = ln->b;
+        mur[d] = ln->mu;
+        zr[d] = zrow[j + D];
+      }
+      const int kz = lg_choice<L, S>(wv, u, K, lane);
+      const int kz_o = __shfl_xor_sync(FULL, kz, L);
+      const bool act_o = __shfl_xor_sync(FULL, (int)active, L) != 0;
+      // member 0 is visited first (:217-229): its draw at a shared locus pins member 1's node as well; a draw of member 1
+      // there (member 0 pinned earlier, which belief propagation's junction draws never leave behind) overwrites Z[0][j]
+      int zst = -1;   // value to store
+      int znext = z_c;
+      if (active) { zst = kz; znext = kz; }
+      if (ivnn == 1 && act_o) {
+        if (c == 1) { zst = kz_o; znext = kz_o; }
+        else if (!active) zst = kz_o;
+      }
+      if (act && m == 0 && zst >= 0) zrow[j] = (uint8_t)zst;
+      zprev = znext;
+      mlp += K;
+      ptp += K;
+      lp++;
+    }
   }
 }
 
