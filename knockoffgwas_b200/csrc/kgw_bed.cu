@@ -29,17 +29,25 @@ void *kgw_plan_device_h_(kgw_plan *pl, int *N, int *p, int *stride_w, int *devic
 namespace {
 
 constexpr int BED_LOCI = 512;    // loci per tile: 64 contiguous bytes of every input row
-constexpr int BED_HAPS = 1024;   // haplotypes per tile: 128 groups of 8 = 128 contiguous bytes of every output column
+constexpr int BED_HAPS = 1024;   // haplotypes a tile owns: 128 groups of 8 = 128 bytes of every output column
+constexpr int BED_OVER = 128;    // ... and reads beyond them (the 16 bytes that complete its last aligned 16-byte chunk)
 constexpr int BED_THREADS = 256;
-constexpr int BED_PITCH = BED_HAPS / 8;        // bytes per locus row of the shared tile
+constexpr int BED_PITCH = (BED_HAPS + BED_OVER) / 8;   // bytes per locus row of the shared tile (144)
+constexpr int BED_PW = BED_PITCH / 4;                  // ... in 32-bit words (36)
 
-// 8x8 bit-matrix transpose of a 64-bit word whose byte r holds row r, bit c = column c (LSB first):
-// afterwards byte c holds column c, bit r = row r  (Hacker's Delight 7-3).
-__device__ __forceinline__ unsigned long long transpose8x8(unsigned long long x) {
-  x = (x & 0xAA55AA55AA55AA55ull) | ((x & 0x00AA00AA00AA00AAull) << 7) | ((x >> 7) & 0x00AA00AA00AA00AAull);
-  x = (x & 0xCCCC3333CCCC3333ull) | ((x & 0x0000CCCC0000CCCCull) << 14) | ((x >> 14) & 0x0000CCCC0000CCCCull);
-  x = (x & 0xF0F0F0F00F0F0F0Full) | ((x & 0x00000000F0F0F0F0ull) << 28) | ((x >> 28) & 0x00000000F0F0F0F0ull);
-  return x;
+// 8x8 bit-matrix transpose of a 64-bit word (xh:xl) whose byte r holds row r, bit c = column c (LSB first): afterwards
+// byte c holds column c, bit r = row r (Hacker's Delight 7-3, the exchange form).  The first two steps never move a bit
+// across the 32-bit halves (the masks clear what a shift would carry over), the third exchanges the high nibbles of the
+// low word with the low nibbles of the high word: 22 32-bit instructions.
+__device__ __forceinline__ void transpose8x8(uint32_t &xl, uint32_t &xh) {
+  uint32_t t;
+  t = (xl ^ (xl >> 7)) & 0x00AA00AAu;  xl = xl ^ t ^ (t << 7);
+  t = (xh ^ (xh >> 7)) & 0x00AA00AAu;  xh = xh ^ t ^ (t << 7);
+  t = (xl ^ (xl >> 14)) & 0x0000CCCCu; xl = xl ^ t ^ (t << 14);
+  t = (xh ^ (xh >> 14)) & 0x0000CCCCu; xh = xh ^ t ^ (t << 14);
+  t = (xl ^ __funnelshift_r(xl, xh, 28)) & 0xF0F0F0F0u;
+  xl = xl ^ t ^ (t << 28);
+  xh = xh ^ (t >> 4);
 }
 
 // Hw / Hkw: [N][stride_w] packed rows (LSB-first, stride_w a multiple of 4 words); either may be null.
@@ -53,10 +61,14 @@ __global__ void __launch_bounds__(BED_THREADS) bed_encode_kernel(const uint32_t 
                                                                  const uint8_t *__restrict__ swap, uint8_t *__restrict__ out, int N,
                                                                  int p, int stride_w, long long nb) {
   extern __shared__ __align__(16) uint8_t tile[];   // [BED_LOCI][BED_PITCH]: [locus][haplotype group] = one .bed byte each
+  __shared__ uint8_t swp[BED_LOCI];
   const int chunks_per_row = stride_w / 2;           // 64-bit chunks in a packed row
   const bool both = (Hw != nullptr) && (Hkw != nullptr);
   const long long tiles_l = ((long long)p + BED_LOCI - 1) / BED_LOCI, tiles_h = ((long long)N + BED_HAPS - 1) / BED_HAPS;
   const long long n_tiles = tiles_l * tiles_h * 2;
+  // word w of the tile row of a locus in 64-locus chunk cq sits at (w + 4 cq) mod BED_PW: the eight chunks of a warp write
+  // rows that lie 64 rows apart (the same bank without the rotation)
+  auto rot = [](int w, int cq) { const int x = w + 4 * cq; return x >= BED_PW ? x - BED_PW : x; };
   for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int which = (int)(t / (tiles_l * tiles_h));
     const uint32_t *M = which == 0 ? Hw : Hkw;
@@ -64,12 +76,14 @@ __global__ void __launch_bounds__(BED_THREADS) bed_encode_kernel(const uint32_t 
     const long long tl = (t % (tiles_l * tiles_h)) % tiles_l, th = (t % (tiles_l * tiles_h)) / tiles_l;
     const long long h0 = th * BED_HAPS;
     __syncthreads();   // the previous tile has been written out
-    // a task = 8 haplotypes x 64 loci: (BED_HAPS / 8) x (BED_LOCI / 64) of them per tile; consecutive threads take
-    // consecutive 64-locus chunks of the same rows (one warp reads 4 haplotype groups x 64 contiguous bytes per row).
-    // The eight chunks of a warp write tile rows that lie 64 rows apart (the same bank): the 32-bit words of a tile row
-    // are stored at word index w ^ (chunk << 2), undone when the row is read out.
+    for (int l = threadIdx.x; l < BED_LOCI; l += BED_THREADS) {   // column order of the tile's loci (:92-99)
+      const long long j = tl * BED_LOCI + l;
+      swp[l] = (swap != nullptr && j < p) ? swap[j] : (uint8_t)0;
+    }
+    // a task = 8 haplotypes x 64 loci: (BED_PITCH) x (BED_LOCI / 64) of them per tile; consecutive threads take
+    // consecutive 64-locus chunks of the same rows (one warp reads 4 haplotype groups x 64 contiguous bytes per row)
     constexpr int CH = BED_LOCI / 64;
-    for (int task = threadIdx.x; task < (BED_HAPS / 8) * CH; task += BED_THREADS) {
+    for (int task = threadIdx.x; task < BED_PITCH * CH; task += BED_THREADS) {
       const int cq = task % CH, gq = task / CH;
       const long long chunk = tl * CH + cq;
       uint32_t lo[8], hi[8];
@@ -81,39 +95,78 @@ __global__ void __launch_bounds__(BED_THREADS) bed_encode_kernel(const uint32_t 
         lo[r] = v.x;
         hi[r] = v.y;
       }
+      // the genotype of sample s at a locus is b0 & b1 | (b0 | b1) << 1 (:20-28): formed on whole words first, so that the
+      // eight "rows" that go into the transpose are (and, or) of the four haplotype pairs and a transposed byte IS the
+      // .bed byte of 4 samples (bits 2s, 2s+1)
+#pragma unroll
+      for (int sidx = 0; sidx < 4; sidx++) {
+        const uint32_t a0 = lo[2 * sidx], a1 = lo[2 * sidx + 1], c0 = hi[2 * sidx], c1 = hi[2 * sidx + 1];
+        lo[2 * sidx] = a0 & a1; lo[2 * sidx + 1] = a0 | a1;
+        hi[2 * sidx] = c0 & c1; hi[2 * sidx + 1] = c0 | c1;
+      }
+      const int wcol = 4 * rot(gq >> 2, cq) + (gq & 3);
 #pragma unroll
       for (int b = 0; b < 8; b++) {
-        // byte b of every row -> one 64-bit word (byte r = haplotype r, bit c = locus 8b + c)
+        // byte b of every row -> one 64-bit word (byte r = row r, bit c = locus 8b + c)
         const uint32_t *w = (b < 4) ? lo : hi;
         const unsigned sel = (unsigned)(b & 3) | ((4u + (unsigned)(b & 3)) << 4);
         const uint32_t t01 = __byte_perm(w[0], w[1], sel), t23 = __byte_perm(w[2], w[3], sel);
         const uint32_t t45 = __byte_perm(w[4], w[5], sel), t67 = __byte_perm(w[6], w[7], sel);
-        const unsigned long long x = (unsigned long long)__byte_perm(t01, t23, 0x5410) |
-                                     ((unsigned long long)__byte_perm(t45, t67, 0x5410) << 32);
-        const unsigned long long y = transpose8x8(x);   // byte c = the 8 haplotypes' bits at locus 8b + c
-        const unsigned long long even = y & 0x5555555555555555ull, odd = (y >> 1) & 0x5555555555555555ull;
-        const unsigned long long code = (even & odd) | ((even | odd) << 1);   // four 2-bit genotypes per byte (:20-28)
+        uint32_t yl = __byte_perm(t01, t23, 0x5410), yh = __byte_perm(t45, t67, 0x5410);
+        transpose8x8(yl, yh);   // byte c = the .bed byte of the 4 samples at locus 8b + c
+        uint8_t *trow = tile + (size_t)(64 * cq + 8 * b) * BED_PITCH + wcol;
 #pragma unroll
-        for (int c = 0; c < 8; c++)
-          tile[(size_t)(64 * cq + 8 * b + c) * BED_PITCH + 4 * ((gq >> 2) ^ (cq << 2)) + (gq & 3)] = (uint8_t)(code >> (8 * c));
+        for (int c = 0; c < 4; c++) {
+          trow[(size_t)c * BED_PITCH] = (uint8_t)(yl >> (8 * c));
+          trow[(size_t)(c + 4) * BED_PITCH] = (uint8_t)(yh >> (8 * c));
+        }
       }
     }
     __syncthreads();
-    // BED_LOCI columns x 128 bytes: a warp writes one column piece per instruction (32 lanes x 4 bytes = one line)
-    const long long byte0 = h0 / 8;   // first output byte of this tile within the column
-    const int n = (int)((nb - byte0) < (BED_HAPS / 8) ? (nb - byte0) : (BED_HAPS / 8));
+    // Output.  A column is ceil(N/8) bytes long, so a tile's 128 bytes of a column start at any alignment.  The tile writes
+    // the aligned 16-byte chunks that START inside its 128 bytes -- the last one runs up to 15 bytes into the next tile's
+    // range, which is why the tile was built 128 haplotypes wider -- so interior tiles store nothing but whole chunks:
+    // eight lanes per column, one chunk per lane (four funnel shifts over five words of the tile row), four columns per
+    // warp pass.  Only the first tile of a column stores the bytes before the first boundary and only the last one those
+    // after the last whole chunk, singly.
+    const long long byte0 = h0 / 8;            // first output byte of this tile within the column
+    const int n_own = (int)((nb - byte0) < (BED_HAPS / 8) ? (nb - byte0) : (BED_HAPS / 8));   // bytes of the column this tile owns
+    const int n_have = (int)((nb - byte0) < BED_PITCH ? (nb - byte0) : BED_PITCH);            // ... and holds
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int l = wid; l < BED_LOCI; l += BED_THREADS / 32) {
-      const long long j = tl * BED_LOCI + l;
-      if (j >= p || n <= 0) continue;
-      const long long col = both ? 2 * j + (which ^ ((swap != nullptr && swap[j]) ? 1 : 0)) : j;
-      uint8_t *dst = out + (size_t)col * (size_t)nb + (size_t)byte0;
-      const uint8_t *src = tile + (size_t)l * BED_PITCH;
-      const int sw = ((l >> 6) & 7) << 2;   // word swizzle of this tile row
-      if (n == BED_HAPS / 8 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
-        reinterpret_cast<uint32_t *>(dst)[lane] = reinterpret_cast<const uint32_t *>(src)[lane ^ sw];
-      } else {
-        for (int i = lane; i < n; i += 32) dst[i] = src[4 * ((i >> 2) ^ sw) + (i & 3)];
+    const int g = lane & 7;
+    if (n_own > 0) {
+      for (int l = wid * 4 + (lane >> 3); l < BED_LOCI; l += (BED_THREADS / 32) * 4) {
+        const long long j = tl * BED_LOCI + l;
+        if (j >= p) continue;
+        const long long col = both ? 2 * j + (which ^ (int)swp[l]) : j;
+        uint8_t *dst = out + (size_t)col * (size_t)nb + (size_t)byte0;
+        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(tile + (size_t)l * BED_PITCH);
+        const uint8_t *src = tile + (size_t)l * BED_PITCH;
+        const int cql = (l >> 6) & 7;
+        const int head = (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);   // bytes before the first boundary
+        // whole chunks that start inside the owned bytes and end inside the column
+        const int c1 = n_own > head ? (n_own - head + 15) >> 4 : 0, c2 = n_have >= head ? (n_have - head) >> 4 : 0;
+        const int kk = min(8, min(c1, c2));
+        const int o = head + 16 * g;            // first tile byte of this lane's chunk
+        if (g < kk) {
+          const int q = o >> 2, sh = 8 * (o & 3);
+          uint32_t wv[5];
+#pragma unroll
+          for (int tt = 0; tt < 5; tt++) wv[tt] = srcw[rot(min(q + tt, BED_PW - 1), cql)];
+          uint4 v;
+          v.x = __funnelshift_r(wv[0], wv[1], sh);
+          v.y = __funnelshift_r(wv[1], wv[2], sh);
+          v.z = __funnelshift_r(wv[2], wv[3], sh);
+          v.w = __funnelshift_r(wv[3], wv[4], sh);
+          *reinterpret_cast<uint4 *>(dst + o) = v;
+        }
+        if (th == 0) {   // the column starts here: nothing before it writes the bytes up to the first boundary
+          for (int i = g; i < min(head, n_have); i += 8) dst[i] = src[4 * rot(i >> 2, cql) + (i & 3)];
+        }
+        const int next = head + 16 * kk;
+        if (next < n_own) {   // the column ends before the chunk that would cover these bytes does: the rest of it, singly
+          for (int i = next + g; i < n_have; i += 8) dst[i] = src[4 * rot(i >> 2, cql) + (i & 3)];
+        }
       }
     }
   }

@@ -48,7 +48,8 @@ def test_device_bed_matches_reference_file():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,p", [(2, 1), (10, 2), (254, 127), (256, 128), (258, 129), (770, 333), (4098, 1000)])
+@pytest.mark.parametrize("N,p", [(2, 1), (10, 2), (254, 127), (256, 128), (258, 129), (770, 333), (4098, 1000),
+                                 (2064, 40), (3300, 21), (8210, 70), (20000, 50), (2296, 65)])   # columns of several 128-byte tiles at every alignment
 def test_device_bed_ragged_shapes(N, p):
     rng = np.random.default_rng(N * 1000 + p)
     H = ko.pack_bits((rng.random((N, p)) < 0.4).astype(np.uint8))
