@@ -517,7 +517,7 @@ void fam_build_ops(const FamilyState &F, int f, const int32_t *groups, const std
 
 typedef void (*kgw_fam_kernel_fn)(const KgwFamParams);
 kgw_fam_kernel_fn kgw_family_kernel_big_(int SF, bool uniform_mu);   // kgw_family_big.cu
-int kgw_pair_draw_launch(const KgwFamParams &P, cudaStream_t st);   // kgw_pairs.cu
+int kgw_pair_draw_launch(const KgwFamParams &P, int sm_count, cudaStream_t st);   // kgw_pairs.cu
 int kgw_pair_ko_launch(const KgwFamParams &P, const KgwPairOp *ops, int n_ops, int sm_count, cudaStream_t st);
 
 struct kgw_plan {
@@ -828,8 +828,8 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
         emtab[nn * 256 + pt] = v;
       }
   }
-  std::vector<KgwFamLocus> loc(p + 1);   // (one zero entry behind the last locus: kgw_pairs.cuh reads a locus ahead)
-  memset(&loc[p], 0, sizeof(KgwFamLocus));
+  std::vector<KgwFamLocus> loc(p + 16);   // (zero entries behind the last locus: kgw_pairs.cuh reads whole blocks of loci)
+  memset(&loc[p], 0, 16 * sizeof(KgwFamLocus));
   const double alpha = 1.0 / K;
   for (int j = 0; j < p; j++) {
     loc[j].b = pl->b[j];
@@ -843,7 +843,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMalloc(&F->dmembers, sizeof(int32_t) * F->members_total));
   KGW_CUDA(cudaMalloc(&F->divstart, sizeof(int32_t) * iv_start.size()));
   KGW_CUDA(cudaMalloc(&F->divs, sizeof(KgwFamInterval) * ivs.size()));
-  KGW_CUDA(cudaMalloc(&F->dloc, sizeof(KgwFamLocus) * (p + 1)));
+  KGW_CUDA(cudaMalloc(&F->dloc, sizeof(KgwFamLocus) * (p + 16)));
   KGW_CUDA(cudaMalloc(&F->demtab, sizeof(double) * emtab.size()));
   KGW_CUDA(cudaMalloc(&F->dref_global, sizeof(int32_t) * (size_t)N * K));
   KGW_CUDA(cudaMalloc(&F->dstatus, sizeof(int32_t)));
@@ -859,7 +859,7 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   KGW_CUDA(cudaMemcpy(F->dmembers, F->h_members.data(), sizeof(int32_t) * F->members_total, cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->divstart, iv_start.data(), sizeof(int32_t) * iv_start.size(), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->divs, ivs.data(), sizeof(KgwFamInterval) * ivs.size(), cudaMemcpyHostToDevice));
-  KGW_CUDA(cudaMemcpy(F->dloc, loc.data(), sizeof(KgwFamLocus) * (p + 1), cudaMemcpyHostToDevice));
+  KGW_CUDA(cudaMemcpy(F->dloc, loc.data(), sizeof(KgwFamLocus) * (p + 16), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->demtab, emtab.data(), sizeof(double) * emtab.size(), cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemcpy(F->dref_global, prob->ref_global, sizeof(int32_t) * (size_t)N * K, cudaMemcpyHostToDevice));
   KGW_CUDA(cudaMemset(F->dstatus, 0, sizeof(int32_t)));
@@ -909,9 +909,9 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
       nslots = (size_t)C.grid * wpc;
     }
     C.nslots = nslots;
-    KGW_CUDA(pl->alloc(&C.dmsg, sizeof(double) * (C.n_max * (size_t)p * K * nslots + 8 * (size_t)K + 64)));   // (rows of padding: kgw_pairs.cuh reads ahead)   // pooled with the plan's buffers
+    KGW_CUDA(pl->alloc(&C.dmsg, sizeof(double) * (C.n_max * (size_t)p * K * nslots + 20 * (size_t)K + 64)));   // (rows of padding: kgw_pairs.cuh reads blocks of rows ahead)   // pooled with the plan's buffers
     KGW_CUDA(pl->alloc(&C.dmrc, sizeof(double) * C.n_max * (size_t)C.rtot * K * nslots));
-    KGW_CUDA(pl->alloc(&C.dpat, (size_t)C.n_max * p * K * nslots + 8 * (size_t)K + 64));
+    KGW_CUDA(pl->alloc(&C.dpat, (size_t)C.n_max * p * K * nslots + 20 * (size_t)K + 64));
     KGW_CUDA(pl->alloc(&C.dbytes, (size_t)2 * C.n_max * p * nslots + 64));
     if (big) {
       KGW_CUDA(pl->alloc(&C.dpmg, sizeof(double) * 2 * C.n_max * KP * nslots));
@@ -979,7 +979,7 @@ int fam_launch(kgw_plan *pl, cudaStream_t st) {
       int rc = KGW_OK;
       if ((rc = family_phases(KGW_FPH_INIT | KGW_FPH_BP)) != KGW_OK) return rc;
       if (F->pair_kernels) {
-        if (kgw_pair_draw_launch(Pc, st) != KGW_OK) return fail(KGW_ERR_CUDA, "launch of the pair draw kernel failed");
+        if (kgw_pair_draw_launch(Pc, pl->sm_count, st) != KGW_OK) return fail(KGW_ERR_CUDA, "launch of the pair draw kernel failed");
       } else if ((rc = family_phases(KGW_FPH_DRAW)) != KGW_OK) return rc;
       if (fast_ko) {
         const int b = f0 / (int)C.nslots;

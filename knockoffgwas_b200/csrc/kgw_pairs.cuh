@@ -22,9 +22,6 @@
 #include "kgw_family.cuh"
 #include <type_traits>
 
-#ifndef KGW_DRAW_RING
-#define KGW_DRAW_RING 2   // loci between the request of a draw's inputs and the draw (measured: 1 -> 40.6 ms, 2 -> 38.0 ms, 4 -> 50 ms
-#endif                    // on 2368 pairs x 10 000 SNPs, K=50: deeper rings put far-ahead and near-term loads on one scoreboard)
 
 namespace kgw {
 
@@ -104,21 +101,54 @@ __device__ __forceinline__ double pair_emission(const double *tab, unsigned pt, 
   return v;
 }
 
+// Staging of a chain's rows through shared memory (both pair kernels that walk a chain locus by locus): a block of RB
+// consecutive loci of the chain's pattern rows (and left-message rows) is ONE contiguous run of the pair's scratch slot,
+// so lane 0 moves it with one cp.async.bulk per chain and array, completing on the stage's mbarrier.  The runs start at
+// any byte (K bytes per pattern row): the copy starts at the 16-byte boundary below and the readers add the offset.
+struct PairStage {
+  // bytes a buffer needs for `bytes` payload bytes starting at any offset within a 16-byte unit
+  __host__ __device__ static constexpr unsigned buf(unsigned bytes) { return (bytes + 15u + 15u) / 16u * 16u; }
+};
+// issue: copy [src, src + bytes) -- widened to 16-byte boundaries -- to dst; returns the bytes the barrier will see
+__device__ __forceinline__ unsigned pair_stage_copy(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+  const unsigned off = (unsigned)(a & 15u), n = (off + bytes + 15u) & ~15u;
+  bulk_g2s(dst, reinterpret_cast<const void *>(a - off), n, bar);
+  return n;
+}
+__device__ __forceinline__ unsigned pair_stage_bytes(const void *src, unsigned bytes) {
+  const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+  return (off + bytes + 15u) & ~15u;
+}
+
 // ---- every remaining node of a pair (family_bp.cpp:217-229), both members at the same locus.
-// Straight-line code per state, constant offsets from one running pointer per array: a state beyond K reads past the
-// row (the next row, or the padding behind the last slot) and looks its emission up in a zero block of the table, so
-// its weight is 0; the first locus carries a unit transition factor; row p of a member's left messages -- row 0 of the
-// next member, which belief propagation never touches -- holds ones (written by the INIT phase), so the last locus
-// needs no special case either.
+// Straight-line code per state: a state beyond K carries a zero left message and looks its emission up in a zero block
+// of the table, so its weight is 0; the first locus carries a unit
+// transition factor; row p of a member's left messages -- row 0 of the next member, which belief propagation never
+// touches -- holds ones (written by the INIT phase), so the last locus needs no special case either.
+// Inputs: blocks of RB loci (pattern rows, left-message rows, per-locus constants) travel by bulk copies into a
+// two-stage shared-memory ring a block ahead of their use (register-destination loads a locus or two ahead left the
+// kernel waiting for L2: 2.9 long-scoreboard stalls per issue); the Z byte is a plain load two loci ahead.
 template <int L, int S, bool UMU>
-__global__ void __launch_bounds__(128) pair_draw_kernel(const __grid_constant__ KgwFamParams P) {
-  constexpr int PW = 32 / (2 * L);   // pairs per warp
+__global__ void __launch_bounds__(128) pair_draw_kernel(const __grid_constant__ KgwFamParams P, const int RB) {
+  constexpr int PW = 32 / (2 * L), G = 2 * PW;   // pairs, chains per warp
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const int m = lane & (L - 1), c = (lane / L) & 1, q = lane / (2 * L);
+  const int m = lane & (L - 1), c = (lane / L) & 1, q = lane / (2 * L), g = lane / L;
   const int p = P.p, K = P.K;
   const size_t pK = (size_t)p * K;
   __shared__ double tab[2 * 512];   // [2][256] emissions by (neighbours, pattern), then 512 zeros
+  extern __shared__ __align__(16) unsigned char pair_smem[];
   for (int t = threadIdx.x; t < 2 * 512; t += blockDim.x) tab[t] = (UMU && t < 512) ? P.emtab[t] : 0.0;
+  // per warp: two stages of { G left-message buffers, G pattern buffers, RB per-locus constants }, two mbarriers
+  const unsigned MLB = PairStage::buf((unsigned)RB * K * 8), PTB = PairStage::buf((unsigned)RB * K), LCB = (unsigned)RB * (unsigned)sizeof(KgwFamLocus);
+  const unsigned STB = G * (MLB + PTB) + LCB;
+  unsigned char *wbase = pair_smem + (size_t)wid * (2 * STB + 16);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(wbase + 2 * STB);
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   const int f_first = P.f_base + (blockIdx.x * wpc + wid) * PW;
   if (f_first >= P.n_families) return;
@@ -134,89 +164,123 @@ __global__ void __launch_bounds__(128) pair_draw_kernel(const __grid_constant__ 
   bool valid[S];
 #pragma unroll
   for (int s = 0; s < S; s++) { valid[s] = (m * S + s < K); toff[s] = valid[s] ? 0 : 512; }
-  // this lane's states m*S .. m*S+S-1 of the current locus's rows
-  const double *mlp = P.msg + fslot * P.n_max * pK + (size_t)c * pK + m * S;
-  const uint8_t *ptp = P.pat + fslot * P.n_max * pK + (size_t)c * pK + m * S;
-  const KgwFamLocus *lp = P.loc;   // [p + 1]
-
-  // The per-locus inputs (pattern bytes, left-message entries, transition constants, the Z byte) sit in a register
-  // ring D loci deep: a row is requested D loci before its draw, which covers an L2 hit; L2 prefetches run 12 + D ahead.
-  // Rows behind the last locus (the ring runs past it) are the next member's rows or the padding: never used.
-  constexpr int D = KGW_DRAW_RING;
-  double mlr[D][S], lar[D], lbr[D], mur[D];
-  unsigned ptr_[D][S];
-  int zr[D];
+  const double *ml_chain = P.msg + fslot * P.n_max * pK + (size_t)c * pK;   // row 0 of this chain's left messages
+  const uint8_t *pt_chain = P.pat + fslot * P.n_max * pK + (size_t)c * pK;
+  // lane 0 issues every chain's copies: the chains' base pointers, by shuffle
+  unsigned long long mlb[G], ptb[G];
 #pragma unroll
-  for (int d = 0; d < D; d++) {
-#pragma unroll
-    for (int s = 0; s < S; s++) { ptr_[d][s] = ptp[(size_t)d * K + s]; mlr[d][s] = mlp[(size_t)(d + 1) * K + s]; }
-    lar[d] = (d == 0) ? 1.0 : lp[min(d, p)].a_al;   // j == 0: no right message (factor 1)
-    lbr[d] = (d == 0) ? 0.0 : lp[min(d, p)].b;
-    mur[d] = lp[min(d, p)].mu;
-    zr[d] = zrow[d];
+  for (int t = 0; t < G; t++) {
+    mlb[t] = __shfl_sync(FULL, (unsigned long long)reinterpret_cast<uintptr_t>(ml_chain), t * L);
+    ptb[t] = __shfl_sync(FULL, (unsigned long long)reinterpret_cast<uintptr_t>(pt_chain), t * L);
   }
+  // block b = loci b*RB .. b*RB+RB-1: pattern rows and constants of those loci, left-message rows of the loci + 1.
+  // Lane 0 keeps the source addresses of the next block to request and steps them by one block per call.
+  const unsigned ml_blk = (unsigned)RB * K * 8, pt_blk = (unsigned)RB * K;
+#pragma unroll
+  for (int t = 0; t < G; t++) mlb[t] += (unsigned long long)K * 8;   // left messages: one locus on
+  unsigned long long lcsrc = (unsigned long long)reinterpret_cast<uintptr_t>(P.loc);
+  int fill_b = 0;
+  auto fill = [&]() {   // lane 0: request block fill_b
+    const int st = fill_b & 1;
+    unsigned char *sb = wbase + (size_t)st * STB;
+    unsigned tot = LCB;
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      tot += (((unsigned)mlb[t] & 15u) + ml_blk + 15u) & ~15u;
+      tot += (((unsigned)ptb[t] & 15u) + pt_blk + 15u) & ~15u;
+    }
+    mbar_expect_tx(bars + st, tot);
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      pair_stage_copy(sb + (size_t)t * MLB, reinterpret_cast<const void *>(mlb[t]), ml_blk, bars + st);
+      pair_stage_copy(sb + (size_t)G * MLB + (size_t)t * PTB, reinterpret_cast<const void *>(ptb[t]), pt_blk, bars + st);
+      mlb[t] += ml_blk;
+      ptb[t] += pt_blk;
+    }
+    bulk_g2s(sb + (size_t)G * (MLB + PTB), reinterpret_cast<const void *>(lcsrc), LCB, bars + st);
+    lcsrc += LCB;
+    fill_b++;
+  };
+  const int nblocks = (p + RB - 1) / RB;
+  if (lane == 0) {
+    fill();
+    if (nblocks > 1) fill();
+  }
+  // this lane's view of block b: pointers to its states of the block's first locus
+  const double *mls = nullptr;
+  const uint8_t *pts = nullptr;
+  const KgwFamLocus *lcs = nullptr;
+  unsigned long long am = (unsigned long long)reinterpret_cast<uintptr_t>(ml_chain + K), ap = (unsigned long long)reinterpret_cast<uintptr_t>(pt_chain);
+  auto enter = [&](int b) {   // every lane: wait for block b, point at its first locus, step the addresses to block b + 1
+    const int st = b & 1;
+    mbar_wait(bars + st, (unsigned)((b >> 1) & 1));
+    unsigned char *sb = wbase + (size_t)st * STB;
+    mls = reinterpret_cast<const double *>(sb + (size_t)g * MLB + ((unsigned)am & 15u)) + m * S;
+    pts = sb + (size_t)G * MLB + (size_t)g * PTB + ((unsigned)ap & 15u) + m * S;
+    lcs = reinterpret_cast<const KgwFamLocus *>(sb + (size_t)G * (MLB + PTB));
+    am += ml_blk;
+    ap += pt_blk;
+  };
+  enter(0);
+  double ml_c[S], la_c = 1.0, lb_c = 0.0, mu_c = lcs->mu;   // j == 0: no right message (factor 1)
+  unsigned pt_c[S];
+#pragma unroll
+  for (int s = 0; s < S; s++) { pt_c[s] = valid[s] ? (unsigned)pts[s] : 0u; ml_c[s] = valid[s] ? mls[s] : 0.0; }   // (beyond K: stale shared memory)
+  int z_c = zrow[0], z_n = zrow[1];
   int zprev = -1;
   LgUniform<L> U;
-  const int pf_off = m * 128;   // this lane's line of a row being prefetched
-  for (int jb = 0; jb < p; jb += D) {
+  int jj = 0, b = 0;            // position inside the block, block
+  for (int j = 0; j < p; j++) {
+    if ((j & (4 * L - 1)) == 0) U.refill(P, i_abs, STREAM_Z, j, m);
+    const double u = U.get(j);
+    while (ivj1 < j) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
+    const bool active = (z_c == 255);
+    const double lab = la_c + lb_c * 1.0;   // the point-mass right message of the previous draw (:243-246) at k == zprev
+    const int zrel = zprev - m * S;
+    const int nnoff = ivnn * 256;
+    double wv[S];
 #pragma unroll
-    for (int d = 0; d < D; d++) {
-      const int j = jb + d;
-      if (j >= p) break;
-      if (j + 12 + D < p) {
-        const char *row = reinterpret_cast<const char *>(mlp - m * S + (size_t)(12 + D) * K);
-        if (pf_off < K * 8) prefetch_l2(row + pf_off);
-        if (L * 128 < 256 * 8 && pf_off + L * 128 < K * 8) prefetch_l2(row + pf_off + L * 128);
-        if (m == 0) prefetch_l2(ptp + (size_t)(12 + D) * K);
-      }
-      if ((j & (4 * L - 1)) == 0) U.refill(P, i_abs, STREAM_Z, j, m);
-      const double u = U.get(j);
-      while (ivj1 < j) { iv++; ivj1 = iv->j1; ivnn = iv->nn; }
-      const int z_c = zr[d];
-      const bool active = (z_c == 255);
-      const double la_c = lar[d];
-      const double lab = la_c + lbr[d] * 1.0;   // the point-mass right message of the previous draw (:243-246) at k == zprev
-      const int zrel = zprev - m * S;
-      const int nnoff = ivnn * 256;
-      double wv[S];
-#pragma unroll
-      for (int s = 0; s < S; s++) {
-        double v;
-        if (UMU) v = tab[(int)ptr_[d][s] + nnoff + toff[s]];
-        else v = valid[s] ? pair_emission<false>(tab, ptr_[d][s], mur[d], ivnn) : 0.0;
-        v *= (s == zrel) ? lab : la_c;
-        wv[s] = v * mlr[d][s];
-      }
-      // refill the ring entry: locus j + D (pattern, Z, constants) and left message j + D + 1
-      {
-        const uint8_t *pn = ptp + (size_t)D * K;
-        const double *mn = mlp + (size_t)(D + 1) * K;
-#pragma unroll
-        for (int s = 0; s < S; s++) { ptr_[d][s] = pn[s]; mlr[d][s] = mn[s]; }
-        const KgwFamLocus *ln = lp + min(D, p - j);
-        lar[d] = ln->a_al;
-        lbr[d] = ln->b;
-        mur[d] = ln->mu;
-        zr[d] = zrow[j + D];
-      }
-      const int kz = lg_choice<L, S>(wv, u, K, lane);
-      const int kz_o = __shfl_xor_sync(FULL, kz, L);
-      const bool act_o = __shfl_xor_sync(FULL, (int)active, L) != 0;
-      // member 0 is visited first (:217-229): its draw at a shared locus pins member 1's node as well; a draw of member 1
-      // there (member 0 pinned earlier, which belief propagation's junction draws never leave behind) overwrites Z[0][j]
-      int zst = -1;   // value to store
-      int znext = z_c;
-      if (active) { zst = kz; znext = kz; }
-      if (ivnn == 1 && act_o) {
-        if (c == 1) { zst = kz_o; znext = kz_o; }
-        else if (!active) zst = kz_o;
-      }
-      if (act && m == 0 && zst >= 0) zrow[j] = (uint8_t)zst;
-      zprev = znext;
-      mlp += K;
-      ptp += K;
-      lp++;
+    for (int s = 0; s < S; s++) {
+      double v;
+      if (UMU) v = tab[(int)pt_c[s] + nnoff + toff[s]];
+      else v = valid[s] ? pair_emission<false>(tab, pt_c[s], mu_c, ivnn) : 0.0;
+      v *= (s == zrel) ? lab : la_c;
+      wv[s] = v * ml_c[s];
     }
+    // the next locus's inputs from the ring (a new block: its stage has landed; the stage left behind is refilled)
+    const int z_nn = zrow[j + 2];
+    if (++jj == RB) {
+      jj = 0;
+      b++;
+      __syncwarp();   // every lane has used the last row of the block left behind
+      if (lane == 0 && b + 1 < nblocks) fill();
+      if (b < nblocks) enter(b);
+    } else {
+      mls += K;
+      pts += K;
+      lcs++;
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++) { pt_c[s] = valid[s] ? (unsigned)pts[s] : 0u; ml_c[s] = valid[s] ? mls[s] : 0.0; }   // (beyond K: stale shared memory)
+    la_c = lcs->a_al;
+    lb_c = lcs->b;
+    mu_c = lcs->mu;
+    const int kz = lg_choice<L, S>(wv, u, K, lane);
+    const int kz_o = __shfl_xor_sync(FULL, kz, L);
+    const bool act_o = __shfl_xor_sync(FULL, (int)active, L) != 0;
+    // member 0 is visited first (:217-229): its draw at a shared locus pins member 1's node as well; a draw of member 1
+    // there (member 0 pinned earlier, which belief propagation's junction draws never leave behind) overwrites Z[0][j]
+    int zst = -1;   // value to store
+    int znext = z_c;
+    if (active) { zst = kz; znext = kz; }
+    if (ivnn == 1 && act_o) {
+      if (c == 1) { zst = kz_o; znext = kz_o; }
+      else if (!active) zst = kz_o;
+    }
+    if (act && m == 0 && zst >= 0) zrow[j] = (uint8_t)zst;
+    zprev = znext;
+    z_c = z_n;
+    z_n = z_nn;
   }
 }
 
