@@ -354,7 +354,6 @@ __global__ void __launch_bounds__(128) pair_ko_kernel(const __grid_constant__ Kg
     }
     const double u = U.get(jc);
     const bool first = (kv_flags & KGW_KO_FIRST) != 0, lastg = (kv_flags & KGW_KO_LASTGRP) != 0, gzero = (kv_flags & KGW_KO_GZERO) != 0;
-    const int z1rel_old = z1 - m * S;
 
     // first locus of a group: T_k / N_old[k] and the partition function N (:358-398, :423-436).  ALL: every lane group of
     // the warp is at such a locus (singleton groups: always), results are assigned instead of selected.
@@ -405,17 +404,51 @@ __global__ void __launch_bounds__(128) pair_ko_kernel(const __grid_constant__ Kg
       }
     };
     const bool allfirst = __all_sync(FULL, first || !run);
-    if (allfirst) group_head(std::true_type{});
-    else if (__any_sync(FULL, run && first)) group_head(std::false_type{});
-
-    const int z1rel = z1 - m * S;
-    (void)z1rel_old;
     const double vbs = fma(kv_vs, 1.0, kv_vb);   // vbar + vstar at k == z1 (vstar is 0 in the last group)
     double w[S];
     if (allfirst) {
+      // every lane group of the warp is at the first locus of a group (singleton groups: always): the same steps as
+      // group_head, in place, and the draw's weights right behind them
+      int z1_pref = 0;
+      if (run && kv_z1next >= 0) z1_pref = z[kv_z1next];
+      const bool gb = (jc == j0);
+      const double cg = (gzero || gb) ? kv_a : kv_a * kv_a;
+      const double c0 = gzero ? kv_a : (gb ? kv_apb : kv_apb * kv_a);
+      const double c1 = (zm1 == zk_last) ? kv_apb * kv_apb : kv_a * kv_apb;
+      const int z0rel = gzero ? -1000 : zm1 - m * S;
+      const int z0krel = (gzero || gb) ? -1000 : zk_last - m * S;
+      double part = 0.0;
+#pragma unroll
+      for (int s = 0; s < S; s++) {
+        double cf = (s == z0rel) ? c0 : cg;
+        cf = (s == z0krel) ? c1 : cf;
+        tq[s] = cf * rNo[s];
+        part += tq[s];
+      }
+      const double N_sum = lg_sum<L>(part);
+      const double vb_u = lastg ? 0.0 : kv_vb, vs_u = lastg ? 0.0 : kv_vs;
+      double nn_part = 0.0;
+#pragma unroll
+      for (int s = 0; s < S; s++) {
+        Nv[s] = fma(vs_u, tq[s], fma(vb_u, N_sum, Nv[s]));
+        nn_part = fma(Nv[s], vmask[s], nn_part);
+      }
+      z1 = z1n;
+      z1n = z1_pref;
+      const int z1rel = z1 - m * S;
 #pragma unroll
       for (int s = 0; s < S; s++) w[s] = tq[s] * ((s == z1rel) ? vbs : kv_vb);
+      const double r_norm = fast_rcp(lg_sum<L>(nn_part));
+      const bool tight = !(vb_u * N_sum * r_norm > 4.0 * N_MIN);
+#pragma unroll
+      for (int s = 0; s < S; s++) Nv[s] *= r_norm;
+      if (__any_sync(FULL, tight)) {
+#pragma unroll
+        for (int s = 0; s < S; s++) if (Nv[s] < N_MIN) Nv[s] = N_MIN;
+      }
     } else {
+      if (__any_sync(FULL, run && first)) group_head(std::false_type{});
+      const int z1rel = z1 - m * S;
       const int zkrel = zkprev - m * S;
 #pragma unroll
       for (int s = 0; s < S; s++) {
