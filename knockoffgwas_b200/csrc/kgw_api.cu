@@ -900,6 +900,10 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
     if (pairs) {
       // a slot per pair of the batch in flight (the phases are separate launches): as many as fit, whole CTAs
       nslots = (size_t)std::min<long long>(C.count, slots_mem);
+      if (const char *e = getenv("KGW_PAIR_SLOTS")) {   // development / tests: force several batches
+        const long long v = atoll(e);
+        if (v > 0) nslots = (size_t)std::min<long long>((long long)nslots, v);
+      }
       C.grid = (int)((nslots + wpc - 1) / wpc);
     } else {
       const long long want = std::min<long long>(C.count, (long long)dp.multiProcessorCount * ctas_per_sm * wpc);

@@ -212,3 +212,39 @@ def test_family_kernel_large_families(size, segments, p, K, max_subset, uniform_
         assert np.array_equal(dbg.fam_zk[row:row + n], r.zk), f"Zk of the family of {n}"
         assert np.array_equal(hk[m], r.hk), f"Hk of the family of {n}"
         row += n
+
+
+def test_pair_class_in_several_batches(monkeypatch):
+    """The pair class runs its phases over batches of as many pairs as have scratch slots (C5 at full size: ~1300 of a
+    GPU's 4375 pairs at a time).  Forced here to 5 slots for 17 pairs -- four batches, the last one short -- at two
+    partition resolutions on one plan: same Z, Zk, Hk as the oracle and as the one-batch run."""
+    from knockoffgwas_b200 import synth
+    sp = synth.make_problem_fast(400, 700, 20, seed=23, n_founders=40, mean_dist_cm=0.05, mean_group=1.0)
+    synth.add_ibd_pairs(sp, 17)
+    prob = ko.Problem(H=sp.H, p=sp.p, K=sp.K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu,
+                      groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
+    coarse = (np.arange(sp.p) // 3).astype(np.int32)
+    results = {}
+    for slots in ("0", "5"):
+        monkeypatch.setenv("KGW_PAIR_SLOTS", slots)
+        plan = kg.Plan(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=np.zeros(0, np.int32),
+                       ref_global=sp.ref, seed=sp.seed, families=sp.families)
+        out = []
+        for groups in (sp.groups, coarse):
+            plan.set_groups(groups)
+            plan.run()
+            hk, dbg = plan.download(debug_paths=True)
+            out.append((hk.copy(), dbg.fam_z.copy(), dbg.fam_zk.copy()))
+        plan.close()
+        results[slots] = out
+    for a, b in zip(results["0"], results["5"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    rng, _ = ko.make_rng(prob, mode="philox")
+    row = 0
+    hk, fz, fzk = results["5"][0]
+    for m, sl in sp.families:
+        r = ko.run_family(prob, m, [(s[0], s[1], 0, 0, s[2]) for s in sl], rng)
+        n = len(m)
+        assert np.array_equal(fz[row:row + n], r.z) and np.array_equal(fzk[row:row + n], r.zk) and np.array_equal(hk[m], r.hk)
+        row += n
