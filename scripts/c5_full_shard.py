@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Development helper: one GPU's FULL eighth of BASELINE.json configs[4] (350k samples = 700k haplotypes, K=100, 60 000
+SNPs, 10 % related): 78 750 unrelated haplotypes + 4 375 IBD pairs in ONE generate() call (bench.py's c5_shard leg runs a
+quarter of this so that the default run stays within minutes).
+usage: python scripts/c5_full_shard.py [--scale 1.0]"""
+import argparse, sys, time
+from pathlib import Path
+import numpy as np
+REPO = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(REPO))
+import knockoffgwas_b200 as kg
+from knockoffgwas_b200 import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--parts", action="store_true", help="also time the two branches on their own")
+a = ap.parse_args()
+N, p, K = int(87500 * a.scale) // 2 * 2, 60000, 100
+pairs = int(4375 * a.scale)
+t0 = time.time()
+prob = synth.make_problem_fast(N, p, K, seed=2022, rho=1.0, lam=1e-3)
+synth.add_ibd_pairs(prob, pairs)
+related = np.concatenate([m for m, _ in prob.families])
+unrelated = np.setdiff1d(np.arange(N, dtype=np.int32), related).astype(np.int32)
+print(f"{len(unrelated)} unrelated + {len(related)} related haplotypes ({pairs} pairs) x {p} SNPs, K={K}; built in {time.time() - t0:.0f} s", flush=True)
+plan = kg.Plan(prob.H, p, K, prob.ref[:, None, :], prob.b, prob.mu, prob.groups, unrelated=unrelated, ref_global=prob.ref,
+               seed=prob.seed, families=prob.families)
+info = plan.info()
+plan.run(); plan.sync()
+ms = plan.run_timed(2)
+print(f"one generate() call: {ms:.1f} ms = {N * p / (ms * 1e-3):.3e} hap-SNPs/s; launches per call {info['launches_per_run']}, "
+      f"sampler {info['lanes_per_hap']} lanes x {info['states_per_lane']} states, segment {info['segment_loci']} loci, scratch {info['scratch_bytes'] / 1e9:.1f} GB", flush=True)
+hk, _ = plan.download()
+plan.close()
+if a.parts:
+    for name, kw in (("unrelated only", dict(unrelated=unrelated)),
+                     ("related only", dict(unrelated=np.zeros(0, np.int32), ref_global=prob.ref, families=prob.families))):
+        pl = kg.Plan(prob.H, p, K, prob.ref[:, None, :], prob.b, prob.mu, prob.groups, seed=prob.seed, **kw)
+        pl.run(); pl.sync()
+        t = pl.run_timed(1)
+        i2 = pl.info()
+        n = len(unrelated) if name.startswith("unrel") else len(related)
+        print(f"  {name}: {t:.1f} ms = {n * p / (t * 1e-3):.3e} hap-SNPs/s (launches {i2['launches_per_run']}, segment {i2['segment_loci']})", flush=True)
+        pl.close()
+    kg.release_workspace()
+filled = int((hk[np.concatenate([unrelated, related])] != 0).any(axis=1).sum())
+print(f"rows written: {filled} of {N}")
