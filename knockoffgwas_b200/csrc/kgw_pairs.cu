@@ -3,6 +3,7 @@
 #include "kgw_pairs.cuh"
 #include "../../include/kgw.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -26,7 +27,8 @@ int pair_dispatch(int K, bool wide, F &&fn) {
 int kgw_pair_draw_launch(const KgwFamParams &P, int sm_count, cudaStream_t st) {
   const int nb = P.n_families - P.f_base;
   if (nb <= 0) return KGW_OK;
-  const bool wide = nb / 2 < 3 * 4 * sm_count;   // fewer than three warps per scheduler with two pairs per warp
+  bool wide = nb / 2 < 3 * 4 * sm_count;   // fewer than three warps per scheduler with two pairs per warp
+  if (const char *e = getenv("KGW_PAIR_WIDE")) wide = (e[0] == '1');   // development / tests: force either form
   return pair_dispatch(P.K, wide, [&](auto Lc, auto Sc) -> int {
     constexpr int L = decltype(Lc)::value, S = decltype(Sc)::value;
     constexpr int PW = 32 / (2 * L), G = 2 * PW;

@@ -248,3 +248,26 @@ def test_pair_class_in_several_batches(monkeypatch):
         n = len(m)
         assert np.array_equal(fz[row:row + n], r.z) and np.array_equal(fzk[row:row + n], r.zk) and np.array_equal(hk[m], r.hk)
         row += n
+
+
+@pytest.mark.parametrize("K,wide", [(50, "0"), (50, "1"), (100, "0"), (100, "1"), (24, "0"), (120, "0"), (200, "0")])
+def test_pair_kernels_both_forms(monkeypatch, K, wide):
+    """The pair draw kernel has two forms -- eight lanes per chain and two pairs per warp (long lists of pairs), sixteen
+    lanes and one pair per warp (short lists) -- and lane widths for K up to 255; the launcher picks by list length.
+    Both forced here on the same pairs, against the oracle."""
+    from knockoffgwas_b200 import synth
+    monkeypatch.setenv("KGW_PAIR_WIDE", wide)
+    sp = synth.make_problem_fast(300, 500, K, seed=K, n_founders=40, mean_dist_cm=0.05, mean_group=1.5)
+    synth.add_ibd_pairs(sp, 7)
+    prob = ko.Problem(H=sp.H, p=sp.p, K=sp.K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu,
+                      groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
+    hk, dbg = kg.generate(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=np.zeros(0, np.int32),
+                          ref_global=sp.ref, seed=sp.seed, families=sp.families, debug_paths=True)
+    rng, _ = ko.make_rng(prob, mode="philox")
+    row = 0
+    for m, sl in sp.families:
+        r = ko.run_family(prob, m, [(s[0], s[1], 0, 0, s[2]) for s in sl], rng)
+        n = len(m)
+        assert np.array_equal(dbg.fam_z[row:row + n], r.z) and np.array_equal(dbg.fam_zk[row:row + n], r.zk)
+        assert np.array_equal(hk[m], r.hk)
+        row += n
