@@ -664,6 +664,7 @@ int fam_upload_partition(kgw_plan *pl, const int32_t *groups) {
       if (!F->pair_ops_ok) break;
       for (int a = o0; a < o1; a++) if (drop[a - o0]) { ops[a].a = 0; ops[a].b = -1; }   // an empty copy
     }
+    if (const char *e = getenv("KGW_PAIR_KO_GENERIC")) { if (e[0] == '1') F->pair_ops_ok = false; }   // tests: the in-order path
     if (F->pair_ops_ok && C.count > 0) {
       const int nsl = (int)std::max<size_t>(C.nslots, 1);
       for (int f0 = 0; f0 < C.count; f0 += nsl) {

@@ -225,8 +225,11 @@ def test_pair_class_in_several_batches(monkeypatch):
                       groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
     coarse = (np.arange(sp.p) // 3).astype(np.int32)
     results = {}
-    for slots in ("0", "5"):
-        monkeypatch.setenv("KGW_PAIR_SLOTS", slots)
+    for slots in ("0", "5", "generic"):
+        # "generic": the operation lists run in order inside family_kernel (the path taken when a pair's list does not
+        # allow "all DRAWs, then the copies")
+        monkeypatch.setenv("KGW_PAIR_SLOTS", "5" if slots == "generic" else slots)
+        monkeypatch.setenv("KGW_PAIR_KO_GENERIC", "1" if slots == "generic" else "0")
         plan = kg.Plan(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=np.zeros(0, np.int32),
                        ref_global=sp.ref, seed=sp.seed, families=sp.families)
         out = []
@@ -237,9 +240,10 @@ def test_pair_class_in_several_batches(monkeypatch):
             out.append((hk.copy(), dbg.fam_z.copy(), dbg.fam_zk.copy()))
         plan.close()
         results[slots] = out
-    for a, b in zip(results["0"], results["5"]):
-        for x, y in zip(a, b):
-            assert np.array_equal(x, y)
+    for other in ("5", "generic"):
+        for a, b in zip(results["0"], results[other]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
     rng, _ = ko.make_rng(prob, mode="philox")
     row = 0
     hk, fz, fzk = results["5"][0]
