@@ -48,7 +48,11 @@ int kgw_pair_draw_launch(const KgwFamParams &P, int sm_count, cudaStream_t st) {
 // the DRAW operations ops[0 .. n_ops) of the same batch; P.work is zero
 int kgw_pair_ko_launch(const KgwFamParams &P, const KgwPairOp *ops, int n_ops, int sm_count, cudaStream_t st) {
   if (n_ops <= 0) return KGW_OK;
-  return pair_dispatch(P.K, false, [&](auto Lc, auto Sc) -> int {
+  // sixteen lanes per operation beyond 56 states: thirteen or more states per lane cost 230+ registers (two warps per
+  // scheduler) and a long chain of dependent adds per draw, and the kernel then waits instead of issuing
+  bool wide = P.K > 56;
+  if (const char *e = getenv("KGW_PAIR_KO_WIDE")) wide = (e[0] == '1');   // development
+  return pair_dispatch(P.K, wide, [&](auto Lc, auto Sc) -> int {
     constexpr int L = decltype(Lc)::value, S = decltype(Sc)::value;
     constexpr int GW = 32 / L;   // lane groups per warp
     int per_sm = 4;
