@@ -246,6 +246,13 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
   }
   T.passes.clear();
   T.ko.clear();
+  // sum_k (1 - b_j) * alpha, K terms added one after the other as the reference does (:1326-1328, :1348-1349).  The
+  // same sum is needed for every locus: K passes over the loci instead of p chains of K dependent additions -- each
+  // locus still sees its K additions in order, but the inner loop runs over independent loci (vector units).
+  std::vector<double> sum_a_of(p, 0.0), term(p);
+  for (int j = 0; j < p; j++) term[j] = (1.0 - b[j]) * alpha;
+  for (int l = 0; l < K; l++)
+    for (int j = 0; j < p; j++) sum_a_of[j] += term[j];
   std::vector<double> vstar, vbar;
   for (int w = 0; w < W; w++) {
     KgwPass ps;
@@ -274,9 +281,8 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
         else vstar[t] = (g < g_end - 1) ? b[e0] : 0.0;
       }
       for (int t = m - 1; t >= 0; t--) {  // :1315-1339
-        double sum_a = 0;
         if (t < m - 1) {
-          for (int l = 0; l < K; l++) sum_a += (1.0 - b[e0 + t + 1]) * alpha;
+          const double sum_a = sum_a_of[e0 + t + 1];
           vbar[t] = vbar[t + 1] * (sum_a + b[e0 + t + 1]);
           vbar[t] += vstar[t + 1] * (1.0 - b[e0 + t + 1]) * alpha;
         } else {
@@ -296,9 +302,7 @@ int build_tables(int p, int K, int W, const double *b, const double *mu, const i
         k.f1 = ab / aa;
         k.f2 = bb / aa;
         k.fz1 = (g < g_end - 1) ? 1.0 + k.vs / k.vb : 0.0;
-        double sa = 0;
-        for (int l = 0; l < K; l++) sa += (1.0 - b[j]) * alpha;  // :1348-1349
-        k.sa = sa;
+        k.sa = sum_a_of[j];  // :1348-1349
         k.vstg = vstar[0] * k.tg;                                // :1364 / :1373 (only read when t == 0)
         k.gw = k.a * k.vb;
         k.rgw = 1.0 / k.gw;
