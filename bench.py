@@ -20,7 +20,7 @@ N > 1    : (torchrun, one rank per GPU, weak scaling) ONE population of N x 20 0
            every other rank's shard on its own GPU and requires them to equal the gathered rows.
 Beside the headline the N = 1 line carries one leg per north-star configuration (BASELINE.json configs[2..4]):
 `c3_shard` (one GPU's eighth of 700k x 60k, K=50), `c4_resolutions` (six partition levels through
-kgw_plan_set_groups on one resident plan) and `c5_shard` (K=100, 60k SNPs, 10 % related haplotypes in the same
+kgw_plan_set_groups on one resident plan) and `c5_shard` (one GPU's eighth of configs[4]: K=100, 60k SNPs, 10 % related haplotypes in the same
 call), each with its own roofline dict and clocks, and the rows either side of the path.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -323,17 +323,16 @@ def leg_c4_resolutions(torch, kg, synth, plan, prob, dev, stream, flush):
 
 
 def leg_c5_shard(torch, kg, synth, dev, stream, flush, a):
-    """A shard of BASELINE.json configs[4] (350k samples, K=100, 10 % related haplotypes): unrelated haplotypes and IBD
-    pairs in ONE generate() call, 60k SNPs.  (A GPU's full eighth is 78 750 + 8 750 haplotypes; this leg runs a quarter
-    of that so that the default bench stays within minutes -- both branches are linear in haplotypes.)"""
-    N, p, K, pairs = 21876, 60000, 100, 1094
+    """One GPU's eighth of BASELINE.json configs[4] (350k samples = 700k haplotypes, K=100, 10 % related haplotypes):
+    78 750 unrelated haplotypes and 4 375 IBD pairs in ONE generate() call, 60k SNPs."""
+    N, p, K, pairs = 87500, 60000, 100, 4375
     prob = synth.make_problem_fast(N, p, K, seed=2022, rho=RHO, lam=LAMBDA)
     synth.add_ibd_pairs(prob, pairs)
     related = np.concatenate([m for m, _ in prob.families])
     unrelated = np.setdiff1d(np.arange(N, dtype=np.int32), related).astype(np.int32)
     opts = kg.Options(device=dev.index, stream=stream.cuda_stream)
     out = {"workload": f"{len(unrelated)} unrelated + {len(related)} related haplotypes ({len(prob.families)} IBD pairs) x {p} SNPs, "
-                       f"K={K}, singleton groups, one generate() call (quarter of one GPU's eighth of 700k haplotypes)"}
+                       f"K={K}, singleton groups, one generate() call (one GPU's eighth of 700k haplotypes)"}
     plan = kg.Plan(prob.H, p, K, prob.ref[:, None, :], prob.b, prob.mu, prob.groups, unrelated=unrelated, ref_global=prob.ref,
                    seed=prob.seed, families=prob.families, options=opts)
     total_ms, kern, clocks = timed_runs(torch, plan, stream, dev, 2, 1, flush)
