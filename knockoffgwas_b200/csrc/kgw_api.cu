@@ -556,6 +556,19 @@ struct kgw_plan {
   int32_t *dout_rows = nullptr;
   unsigned char *slab = nullptr;      // one allocation behind the per-slot scratch arrays
   size_t slab_bytes = 0;
+  size_t slab_off[6] = {};            // offsets of dckpt, dcs, dse, dsegck, dz, dzk behind dmw
+  size_t z_bytes = 0;                 // bytes of each of dz / dzk
+  // The sampler's scratch and the family classes' message slots are never in use at the same time (the two branches run
+  // one after the other on one stream): with IBD families in the call the scratch lives INSIDE the largest message
+  // buffer, and the families get the memory it would have taken (fam_create).  The latent-path bytes the sampler
+  // expects zeroed are cleared before every launch then.
+  bool scratch_aliased = false;
+  void point_scratch(unsigned char *base) {
+    dmw = (uint32_t *)base;
+    dckpt = (double *)(base + slab_off[0]); dcs = (double *)(base + slab_off[1]); dse = (double *)(base + slab_off[2]);
+    dsegck = (double *)(base + slab_off[3]); dz = base + slab_off[4]; dzk = base + slab_off[5];
+    P.mwbuf = dmw; P.ckpt = dckpt; P.csbuf = dcs; P.sebuf = dse; P.segck = dsegck; P.zbuf = dz; P.zkbuf = dzk;
+  }
   uint8_t *dz = nullptr, *dzk = nullptr;
   int32_t *ddbg_z = nullptr, *ddbg_zk = nullptr;
   double *ddbg_beta = nullptr;
@@ -874,6 +887,15 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
   // class is sized first (few families, large slots: at most 40 % of the free memory), the small class takes the rest.
   F->SF = (K + 31) / 32 <= 1 ? 1 : ((K + 31) / 32 <= 2 ? 2 : ((K + 31) / 32 <= 4 ? 4 : 8));
   const size_t KP = (size_t)F->SF * 32;
+  // the sampler's scratch moves into the largest message buffer (kgw_plan::scratch_aliased): its slab goes back first,
+  // so that the families are sized with that memory
+  bool alias = pl->n_haps > 0 && pl->slab != nullptr;
+  { const char *e = getenv("KGW_ALIAS_SCRATCH"); if (e && e[0] == '0') alias = false; }            // development
+  { const char *e = getenv("KGW_FAMILY_OVERLAP"); if (e && e[0] == '1') alias = false; }           // (both kernels at once)
+  if (alias) {
+    KGW_CUDA(cudaStreamSynchronize(pl->stream));   // (the memsets of the latent-path bytes)
+    pl->release(pl->slab);
+  }
   size_t free_b = 0, total_b = 0;
   KGW_CUDA(cudaMemGetInfo(&free_b, &total_b));
   free_b += g_pool.parked(pl->device);
@@ -927,6 +949,23 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
       KGW_CUDA(pl->alloc(&C.dflg, sizeof(int32_t) * 5 * C.n_max * nslots));
     }
     free_b -= std::min(free_b, per_slot * nslots);
+  }
+  if (alias) {
+    FamClass *big = nullptr;
+    size_t big_bytes = 0;
+    for (FamClass &C : F->cls) {
+      const size_t bts = C.dmsg ? sizeof(double) * C.n_max * (size_t)p * K * C.nslots : 0;
+      if (bts > big_bytes) { big_bytes = bts; big = &C; }
+    }
+    if (big && big_bytes >= pl->slab_bytes) {
+      pl->point_scratch(reinterpret_cast<unsigned char *>(big->dmsg));
+      pl->scratch_aliased = true;
+    } else {   // few families: the scratch keeps a buffer of its own after all
+      KGW_CUDA(pl->alloc(&pl->slab, pl->slab_bytes));
+      pl->point_scratch(pl->slab);
+      KGW_CUDA(cudaMemsetAsync(pl->dz, 0, pl->z_bytes, pl->stream));
+      KGW_CUDA(cudaMemsetAsync(pl->dzk, 0, pl->z_bytes, pl->stream));
+    }
   }
   {
     const char *ov = getenv("KGW_FAMILY_OVERLAP");   // development: "0" / "1"
@@ -1065,6 +1104,10 @@ int launch(kgw_plan *pl) {
     KGW_CUDA(cudaEventRecord(F->ev_join, F->side));
   }
   if (pl->n_haps > 0) {
+    if (pl->scratch_aliased) {   // the family kernels of the previous run wrote over the latent-path bytes
+      KGW_CUDA(cudaMemsetAsync(pl->dz, 0, pl->z_bytes, pl->stream));
+      KGW_CUDA(cudaMemsetAsync(pl->dzk, 0, pl->z_bytes, pl->stream));
+    }
     pl->fn<<<pl->grid, pl->threads, pl->smem, pl->stream>>>(pl->P);
     KGW_CUDA(cudaGetLastError());
   }
@@ -1539,6 +1582,9 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
     const size_t need = b_mw + b_ck + b_cs + b_se + b_sg + 2 * b_z;
     KGW_CUDA_PL(pl->alloc(&pl->slab, need));
     pl->slab_bytes = need;
+    pl->slab_off[0] = b_mw; pl->slab_off[1] = b_mw + b_ck; pl->slab_off[2] = b_mw + b_ck + b_cs;
+    pl->slab_off[3] = b_mw + b_ck + b_cs + b_se; pl->slab_off[4] = pl->slab_off[3] + b_sg; pl->slab_off[5] = pl->slab_off[4] + b_z;
+    pl->z_bytes = b_z;
     unsigned char *base = (unsigned char *)pl->slab;
     pl->dmw = (uint32_t *)base; base += b_mw;
     pl->dckpt = (double *)base; base += b_ck;

@@ -275,3 +275,40 @@ def test_pair_kernels_both_forms(monkeypatch, K, wide):
         assert np.array_equal(dbg.fam_z[row:row + n], r.z) and np.array_equal(dbg.fam_zk[row:row + n], r.zk)
         assert np.array_equal(hk[m], r.hk)
         row += n
+
+
+def test_mixed_plan_reuse_with_shared_scratch(monkeypatch):
+    """Unrelated haplotypes and pairs on ONE plan over three runs (two partitions, the first one again): with IBD families
+    in the call the sampler's scratch lives inside the families' message buffer (the two branches never run at the same
+    time), so every run must start from a clean slate.  Same rows as with separate buffers and as the oracle."""
+    from knockoffgwas_b200 import synth
+    sp = synth.make_problem_fast(400, 700, 20, seed=31, n_founders=40, mean_dist_cm=0.05, mean_group=1.0)
+    synth.add_ibd_pairs(sp, 40)
+    related = np.concatenate([m for m, _ in sp.families])
+    unrelated = np.setdiff1d(np.arange(sp.N, dtype=np.int32), related)[:70].astype(np.int32)
+    prob = ko.Problem(H=sp.H, p=sp.p, K=sp.K, ref_local=sp.ref[:, None, :], ref_global=sp.ref, b=sp.b, mu=sp.mu,
+                      groups=sp.groups, win_start=None, win_end=None, seed=sp.seed)
+    coarse = (np.arange(sp.p) // 4).astype(np.int32)
+    runs = {}
+    for alias in ("1", "0"):
+        monkeypatch.setenv("KGW_ALIAS_SCRATCH", alias)
+        plan = kg.Plan(sp.H, sp.p, sp.K, prob.ref_local, sp.b, sp.mu, sp.groups, unrelated=unrelated, ref_global=sp.ref,
+                       seed=sp.seed, families=sp.families)
+        out = []
+        for groups in (sp.groups, coarse, sp.groups):
+            plan.set_groups(groups)
+            plan.run()
+            hk, _ = plan.download()
+            out.append(hk.copy())
+        plan.close()
+        runs[alias] = out
+    for a, b in zip(runs["1"], runs["0"]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(runs["1"][0], runs["1"][2])
+    assert not np.array_equal(runs["1"][0], runs["1"][1])
+    r = ko.run_unrelated(prob, unrelated[:8])
+    assert np.array_equal(runs["1"][0][unrelated[:8]], r.hk)
+    rng, _ = ko.make_rng(prob, mode="philox")
+    for m, sl in sp.families[:6]:
+        rf = ko.run_family(prob, m, [(s[0], s[1], 0, 0, s[2]) for s in sl], rng)
+        assert np.array_equal(runs["1"][0][m], rf.hk)
