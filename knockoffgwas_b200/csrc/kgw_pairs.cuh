@@ -116,11 +116,6 @@ __device__ __forceinline__ unsigned pair_stage_copy(void *dst, const void *src, 
   bulk_g2s(dst, reinterpret_cast<const void *>(a - off), n, bar);
   return n;
 }
-__device__ __forceinline__ unsigned pair_stage_bytes(const void *src, unsigned bytes) {
-  const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
-  return (off + bytes + 15u) & ~15u;
-}
-
 // ---- every remaining node of a pair (family_bp.cpp:217-229), both members at the same locus.
 // Straight-line code per state: a state beyond K carries a zero left message and looks its emission up in a zero block
 // of the table, so its weight is 0; the first locus carries a unit
