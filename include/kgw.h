@@ -223,6 +223,30 @@ int32_t kgw_assign_references(int32_t N, int32_t p, int64_t row_bytes, const uin
                               int32_t n_clusters, const int32_t *clust_off, const int32_t *clust_members,
                               const int32_t *family_of, int32_t device, int32_t *ref_out, float *kernel_ms);
 
+/* ---- kinship clusters: the data passes of the bifurcating k-means ----------
+ * KinshipComputer::bifurcating_kmeans (kinship_computer.cpp:511-691) splits the haplotypes into clusters of at most
+ * cluster_size_max by repeated 2-means on the thinned genotypes; the clusters feed assign_references above.  Its two
+ * data passes run on the device, on a matrix that is uploaded once per run:
+ *   kgw_kinship_create      H [N][row_bytes]: the thinned rows of ALL chromosomes side by side (packed, LSB first,
+ *                           p loci in chromosome order), N even (haplotypes 2s, 2s+1 = sample s)
+ *   kgw_kinship_distances   update_assignments' distances (:314-336 with distance :239-250): for member t (a haplotype
+ *                           index i) d0[t] = sum_j (H[i0][j]-mu0[j])^2 + sum_j (H[i1][j]-mu0[j])^2 over the loci with
+ *                           use[j] != 0 (NULL = all; zeros on the chromosome left out), i0 = 2*(i/2), i1 = i0+1; d1 with
+ *                           mu1.  Sequential fp64 sums in locus order, no fused multiply-add: the numbers a strict-IEEE
+ *                           build of the reference compares in `dist_0 < dist_1` (:331).
+ *   kgw_kinship_centroids   update_centroids (:368-405): column means of the members with assign 0 / 1 (exact counts,
+ *                           one division per locus as the reference divides); n0_out / n1_out (may be NULL): the sizes.
+ * The control flow around them -- initial centroids from the reference's random stream (:252-312), the size
+ * rebalancing (:338-362), acceptance of a split and the list of unfinished clusters (:620-676) -- is integer bookkeeping
+ * that stays on the host (integration/snpknock2_kgw_shim.cpp keeps the reference's order of operations). */
+typedef struct kgw_kinship kgw_kinship;
+int32_t kgw_kinship_create(int32_t N, int32_t p, int64_t row_bytes, const uint8_t *H, int32_t device, kgw_kinship **out);
+void kgw_kinship_destroy(kgw_kinship *k);
+int32_t kgw_kinship_distances(kgw_kinship *k, const int32_t *members, int32_t n, const double *mu0, const double *mu1,
+                              const uint8_t *use, double *d0, double *d1);
+int32_t kgw_kinship_centroids(kgw_kinship *k, const int32_t *members, const int32_t *assign, int32_t n, double *mu0, double *mu1,
+                              int32_t *n0_out, int32_t *n1_out);
+
 /* ---- phased BGEN -> packed haplotype matrix -----------------------------
  * Replaces the data loop of BgenReader::read_worker (bgen_reader.cpp:139-261) behind BgenReader::read
  * (:66-80), the producer of Haplotypes::H (dataset.cpp).  `file` is the whole .bgen image (v1.2, layout 2,

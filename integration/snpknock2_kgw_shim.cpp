@@ -65,6 +65,15 @@ void wrap_haps_read(HapsReader *self, const vector<string> &sample_ids, const ve
                     bool verbose) asm("__wrap_" KGW_STR(KGW_HAPS_SYM));
 ivector3d real_assign_references(const KinshipComputer *self, const int K, const int chr, const Windows &windows) asm("__real_" KGW_STR(KGW_AR_SYM));
 ivector3d wrap_assign_references(const KinshipComputer *self, const int K, const int chr, const Windows &windows) asm("__wrap_" KGW_STR(KGW_AR_SYM));
+#ifdef KGW_KC_SYM
+// KinshipComputer::KinshipComputer(metadata, compression, cluster_size_min, cluster_size_max, num_threads)
+// (kinship_computer.cpp:12-36), the caller of the bifurcating k-means; its call of cluster() stays inside
+// kinship_computer.o, so the seam that can be wrapped is the constructor itself
+void real_kc_ctor(KinshipComputer *self, const vector<Metadata> &metadata, int compression, int cluster_size_min, int cluster_size_max,
+                  int num_threads) asm("__real_" KGW_STR(KGW_KC_SYM));
+void wrap_kc_ctor(KinshipComputer *self, const vector<Metadata> &metadata, int compression, int cluster_size_min, int cluster_size_max,
+                  int num_threads) asm("__wrap_" KGW_STR(KGW_KC_SYM));
+#endif
 void writeBIM(const string &basename, const Metadata &metadata, bool include_genotypes, const vector<bool> &swap);   // plink_interface.cpp:105
 void writeFAM(const string &basename, const Metadata &metadata);                                                      // plink_interface.cpp:162
 
@@ -153,6 +162,209 @@ void wrap_haps_read(HapsReader *self, const vector<string> &sample_ids, const ve
   for (int i = 0; i < 2 * num_samples; i++)
     std::copy(Hflat.begin() + (size_t)i * row_bytes, Hflat.begin() + (size_t)(i + 1) * row_bytes, H[i].data.begin());
 }
+
+#ifdef KGW_KC_SYM
+// ---- `--compute-references`, clustering half: the bifurcating k-means (kinship_computer.cpp:511-691) with its two data
+// passes -- update_assignments' distances and update_centroids (:239-250, :314-405) -- on the device (kgw_kinship_*).
+// Everything else keeps the reference's order of operations: the 100 candidate pairs of init_centroids drawn from the
+// reference's own putils::getRandom stream (:252-312), the size rebalancing through multimaps (:338-362), the acceptance
+// of a split and the list of unfinished clusters (:620-676), the convergence test on the centroids (:593-617).  With
+// several chromosomes the reference solves one leave-one-out problem per chromosome on racing threads that share
+// that random stream; here they run one after the other (the reference's result with one thread).
+namespace {
+struct KinDevice {
+  kgw_kinship *h = nullptr;
+  std::vector<int> off;   // first concatenated locus of every chromosome (+ end)
+  int P = 0;
+};
+
+void kin_fail() { std::cerr << "Error: " << kgw_last_error() << std::endl; exit(-1); }
+
+void kin_use_mask(const KinDevice &D, int chr_out, std::vector<uint8_t> &use) {
+  use.assign(D.P, 1);
+  if (chr_out >= 0) std::fill(use.begin() + D.off[chr_out], use.begin() + D.off[chr_out + 1], 0);
+}
+
+// init_centroids (:252-312), genetic data only
+void kin_init_centroids(const KinshipComputer *self, const KinDevice &D, int c, int chr_out, const vector<vector<int>> &clust_chr,
+                        std::vector<double> &mu0, std::vector<double> &mu1) {
+  const int clust_size = clust_chr[c].size();
+  int dil_max = 0, i_best = 0, l_best = 0;
+  for (int pr = 0; pr < 100; pr++) {
+    int i = clust_chr[c][putils::getRandom(clust_size)];
+    int i0 = 2 * (i / 2), i1 = 2 * (i / 2) + 1;
+    int l = i;
+    while ((l == i0) || (l == i1)) l = clust_chr[c][putils::getRandom(clust_size)];
+    int result = 0;   // distance_leaveout (:106-124): an int accumulator
+    for (int chr = 0; chr < self->num_chrs; chr++)
+      if (chr != chr_out)
+        result += self->chromosomes[chr]->distance(2 * (i / 2), 2 * (l / 2)) + self->chromosomes[chr]->distance(2 * (i / 2) + 1, 2 * (l / 2) + 1);
+    int dil = result;
+    if (dil > dil_max) { i_best = i; l_best = l; dil_max = dil; }
+  }
+  mu0.assign(D.P, 0.0);
+  mu1.assign(D.P, 0.0);
+  for (int chr = 0; chr < self->num_chrs; chr++) {
+    if (chr == chr_out) continue;
+    const int num_snps = self->chromosomes[chr]->get_num_snps();
+    for (int j = 0; j < num_snps; j++) {
+      mu0[D.off[chr] + j] = (double)(self->chromosomes[chr]->H[i_best][j]);
+      mu1[D.off[chr] + j] = (double)(self->chromosomes[chr]->H[l_best][j]);
+    }
+  }
+}
+
+// distance(mu, mu_old) (:156-170): chromosome by chromosome, then their sum
+double kin_centroid_shift(const KinDevice &D, int num_chrs, const std::vector<double> &a, const std::vector<double> &b) {
+  double dist = 0.0;
+  for (int chr = 0; chr < num_chrs; chr++) {
+    double d = 0.0;
+    for (int j = D.off[chr]; j < D.off[chr + 1]; j++) d += std::pow(a[j] - b[j], 2);
+    dist += d;
+  }
+  return dist;
+}
+
+// kmeans_core (:593-617) with update_assignments (:314-362) and update_centroids (:368-405)
+void kin_kmeans_core(const KinshipComputer *self, const KinDevice &D, int c, int chr_out, vector<vector<int>> &clust_chr,
+                     vector<int> &new_assignments) {
+  std::vector<double> mu0, mu1;
+  kin_init_centroids(self, D, c, chr_out, clust_chr, mu0, mu1);
+  std::vector<double> mu0_old = mu0, mu1_old = mu1;
+  std::vector<uint8_t> use;
+  kin_use_mask(D, chr_out, use);
+  const int n = clust_chr[c].size();
+  std::vector<int32_t> members(clust_chr[c].begin(), clust_chr[c].end()), asg(n);
+  std::vector<double> d0(n), d1(n);
+  const int cluster_size_min = self->cluster_size_min;
+  for (int it = 0; it < 50; it++) {
+    if (kgw_kinship_distances(D.h, members.data(), n, mu0.data(), mu1.data(), use.data(), d0.data(), d1.data()) != KGW_OK) kin_fail();
+    std::multimap<double, int> distances0, distances1;
+    int csize0 = 0, csize1 = 0;
+    for (int idx = 0; idx < n; idx++) {
+      const double dist_0 = d0[idx], dist_1 = d1[idx];
+      if (dist_0 < dist_1) { new_assignments[idx] = 0; csize0++; distances0.emplace(dist_0, idx); }
+      else { new_assignments[idx] = 1; csize1++; distances1.emplace(dist_1, idx); }
+    }
+    if (csize0 < cluster_size_min) {
+      int n_missing = cluster_size_min - csize0;
+      for (auto itr = distances1.rbegin(); itr != std::next(distances1.rbegin(), n_missing); ++itr) new_assignments[(*itr).second] = 0;
+    }
+    if (csize1 < cluster_size_min) {
+      int n_missing = cluster_size_min - csize1;
+      for (auto itr = distances0.rbegin(); itr != std::next(distances0.rbegin(), n_missing); ++itr) new_assignments[(*itr).second] = 1;
+    }
+    for (int idx = 0; idx < n; idx++) asg[idx] = new_assignments[idx];
+    if (kgw_kinship_centroids(D.h, members.data(), asg.data(), n, mu0.data(), mu1.data(), nullptr, nullptr) != KGW_OK) kin_fail();
+    if (chr_out >= 0) {   // the chromosome left out keeps zero centroids (:375-379)
+      std::fill(mu0.begin() + D.off[chr_out], mu0.begin() + D.off[chr_out + 1], 0.0);
+      std::fill(mu1.begin() + D.off[chr_out], mu1.begin() + D.off[chr_out + 1], 0.0);
+    }
+    const double delta_mu0 = kin_centroid_shift(D, self->num_chrs, mu0, mu0_old), delta_mu1 = kin_centroid_shift(D, self->num_chrs, mu1, mu1_old);
+    mu0_old = mu0;
+    mu1_old = mu1;
+    if ((delta_mu0 < 1e-3) && (delta_mu1 < 1e-3)) break;
+  }
+}
+
+// kmeans (:620-676)
+void kin_kmeans(const KinshipComputer *self, const KinDevice &D, int c, int chr_out, vector<vector<int>> &clust_chr, vector<int> &assign_chr,
+                vector<int> &unfinished_clusters) {
+  const int clust_size = clust_chr[c].size();
+  vector<int> new_assign_chr(clust_size, 0);
+  kin_kmeans_core(self, D, c, chr_out, clust_chr, new_assign_chr);
+  int clust_size_0 = 0, clust_size_1 = 0;
+  for (int idx = 0; idx < clust_size; idx++) { if (new_assign_chr[idx] == 0) clust_size_0++; else clust_size_1++; }
+  const int cluster_size_min = self->cluster_size_min;
+  if (std::min(clust_size_0, clust_size_1) >= cluster_size_min) {
+    int num_clust = clust_chr.size();
+    vector<int> new_cluster_0, new_cluster_1;
+    for (int idx = 0; idx < clust_size; idx++) {
+      int i = clust_chr[c][idx];
+      if (new_assign_chr[idx] == 0) { new_assign_chr[idx] = c; new_cluster_0.push_back(i); }
+      else { new_assign_chr[idx] = num_clust; new_cluster_1.push_back(i); }
+      assign_chr[i] = new_assign_chr[idx];
+    }
+    clust_chr.erase(clust_chr.begin() + c);
+    clust_chr.insert(clust_chr.begin() + c, new_cluster_0);
+    clust_chr.push_back(new_cluster_1);
+    if (clust_size_0 <= cluster_size_min) {
+      auto it = find(unfinished_clusters.begin(), unfinished_clusters.end(), c);
+      unfinished_clusters.erase(it);
+    }
+    if (clust_size_1 >= cluster_size_min) unfinished_clusters.push_back(num_clust);
+  }
+}
+
+// bifurcating_kmeans (:511-591)
+void kin_bifurcating_kmeans(const KinshipComputer *self, const KinDevice &D, int chr_out, vector<int> &assign_chr, vector<vector<int>> &clust_chr) {
+  const int num_haps = self->num_haps;
+  assign_chr.resize(num_haps);
+  std::fill(assign_chr.begin(), assign_chr.end(), 0);
+  vector<int> clust_chr_tmp(num_haps);
+  std::iota(clust_chr_tmp.begin(), clust_chr_tmp.end(), 0);
+  clust_chr.clear();
+  clust_chr.push_back(clust_chr_tmp);
+  vector<int> unfinished_clusters;
+  unfinished_clusters.push_back(0);
+  int step = 0;
+  const int max_steps = 10000;
+  while ((unfinished_clusters.size() > 0) && (step++ < max_steps)) {
+    int c = unfinished_clusters[0];
+    if ((int)clust_chr[c].size() <= self->cluster_size_max) {
+      auto it = find(unfinished_clusters.begin(), unfinished_clusters.end(), c);
+      unfinished_clusters.erase(it);
+      continue;
+    }
+    kin_kmeans(self, D, c, chr_out, clust_chr, assign_chr, unfinished_clusters);
+  }
+  cerr << "Bifurcating K-means on the GPU";
+  if (chr_out != -1) cerr << " (leaving out chromosome " << chr_out + 1 << ")";
+  cerr << ": " << clust_chr.size() << " clusters after " << step - 1 << " steps." << endl;
+}
+}  // namespace
+
+void wrap_kc_ctor(KinshipComputer *self, const vector<Metadata> &metadata, int compression, int cluster_size_min, int cluster_size_max,
+                  int num_threads) {
+  if (!shim_io()) { real_kc_ctor(self, metadata, compression, cluster_size_min, cluster_size_max, num_threads); return; }
+  new (self) KinshipComputer(metadata);                 // the members, default-constructed (:9-10)
+  self->covariates_available = false;
+  self->genomes = Dataset(metadata, num_threads, compression);
+  self->num_chrs = self->genomes.num_chrs();
+  for (int chr = 0; chr < self->num_chrs; chr++) self->chromosomes.push_back(&(self->genomes.chromosomes[chr]));
+  self->num_haps = self->chromosomes[0]->get_num_haps();
+  self->cluster_size_min = cluster_size_min;
+  self->cluster_size_max = cluster_size_max;
+  self->num_threads = num_threads;
+  // the thinned rows of all chromosomes side by side, uploaded once
+  KinDevice D;
+  D.off.assign(1, 0);
+  for (int chr = 0; chr < self->num_chrs; chr++) D.off.push_back(D.off.back() + self->chromosomes[chr]->get_num_snps());
+  D.P = D.off.back();
+  const int num_haps = self->num_haps;
+  const int64_t row_bytes = (D.P + 7) / 8;
+  std::vector<uint8_t> Hflat((size_t)num_haps * row_bytes, 0);
+  for (int chr = 0; chr < self->num_chrs; chr++) {
+    const Haplotypes *hp = self->chromosomes[chr];
+    const int ps = hp->get_num_snps();
+    for (int i = 0; i < num_haps; i++)
+      for (int j = 0; j < ps; j++)
+        if (hp->H[i][j]) { const int g = D.off[chr] + j; Hflat[(size_t)i * row_bytes + (g >> 3)] |= (uint8_t)(1u << (g & 7)); }
+  }
+  if (kgw_kinship_create(num_haps, D.P, row_bytes, Hflat.data(), /*device=*/0, &D.h) != KGW_OK) kin_fail();
+  // cluster(true) (:407-478)
+  self->assignments.resize(self->num_chrs);
+  self->clusters.resize(self->num_chrs);
+  if (self->num_chrs > 1) {
+    cout << "Solving " << self->num_chrs << " bifurcating K-means problems on the GPU." << endl;
+    for (int chr = 0; chr < self->num_chrs; chr++) kin_bifurcating_kmeans(self, D, chr, self->assignments[chr], self->clusters[chr]);
+  } else {
+    kin_bifurcating_kmeans(self, D, -1, self->assignments[0], self->clusters[0]);
+  }
+  cout << endl;
+  kgw_kinship_destroy(D.h);
+}
+#endif  // KGW_KC_SYM
 
 // KinshipComputer::assign_references (kinship_computer.cpp:836-931): the worker loop over findNeighbors (:174-233, all-pairs
 // Hamming distances inside the kinship cluster and the K smallest) runs on the device; the merge inside IBD families

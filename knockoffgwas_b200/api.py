@@ -143,6 +143,14 @@ def load_library():
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
         L.kgw_bed_encode.restype = C.c_int32
         L.kgw_bed_encode.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.kgw_kinship_create.restype = C.c_int32
+        L.kgw_kinship_create.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.kgw_kinship_destroy.restype = None
+        L.kgw_kinship_destroy.argtypes = [C.c_void_p]
+        L.kgw_kinship_distances.restype = C.c_int32
+        L.kgw_kinship_distances.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kgw_kinship_centroids.restype = C.c_int32
+        L.kgw_kinship_centroids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         if L.kgw_abi_version() != KGW_ABI_VERSION:
             raise KgwError(-1, "libkgw.so ABI version mismatch")
         _LIB = L
@@ -414,6 +422,50 @@ def assign_references(H, p, K, clusters, family_of=None, compression=10, device=
                                    off.ctypes.data, mem.ctypes.data, None if fam is None else fam.ctypes.data,
                                    int(device), out.ctypes.data, C.byref(ms)))
     return out, float(ms.value)
+
+
+class KinshipMatrix:
+    """The thinned rows of all chromosomes resident in HBM for the data passes of the bifurcating k-means
+    (kgw_kinship_*; KinshipComputer::update_assignments / update_centroids, kinship_computer.cpp:314-405)."""
+
+    def __init__(self, H, p, device=0):
+        self._L = load_library()
+        self.H = np.ascontiguousarray(H, dtype=np.uint8)
+        self.N, self.row_bytes = (int(x) for x in self.H.shape)
+        self.p = int(p)
+        self._h = C.c_void_p()
+        _check(self._L.kgw_kinship_create(self.N, self.p, self.row_bytes, self.H.ctypes.data, int(device), C.byref(self._h)))
+
+    def distances(self, members, mu0, mu1, use=None):
+        """(d0, d1): distance of every member's sample (both haplotypes) to the two centroids, sequential fp64 sums."""
+        mem = np.ascontiguousarray(members, dtype=np.int32)
+        a = np.ascontiguousarray(mu0, dtype=np.float64)
+        b = np.ascontiguousarray(mu1, dtype=np.float64)
+        assert a.shape == (self.p,) and b.shape == (self.p,)
+        u = None if use is None else np.ascontiguousarray(use, dtype=np.uint8)
+        d0, d1 = np.empty(len(mem)), np.empty(len(mem))
+        _check(self._L.kgw_kinship_distances(self._h, mem.ctypes.data, len(mem), a.ctypes.data, b.ctypes.data,
+                                             None if u is None else u.ctypes.data, d0.ctypes.data, d1.ctypes.data))
+        return d0, d1
+
+    def centroids(self, members, assign):
+        """(mu0, mu1): column means of the members with assign 0 / 1."""
+        mem = np.ascontiguousarray(members, dtype=np.int32)
+        asg = np.ascontiguousarray(assign, dtype=np.int32)
+        mu0, mu1 = np.empty(self.p), np.empty(self.p)
+        _check(self._L.kgw_kinship_centroids(self._h, mem.ctypes.data, asg.ctypes.data, len(mem), mu0.ctypes.data, mu1.ctypes.data, None, None))
+        return mu0, mu1
+
+    def close(self):
+        if self._h:
+            self._L.kgw_kinship_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BgenReader:

@@ -616,3 +616,39 @@ def run_em(prob: Problem, mu_init=None):
         raise RuntimeError(f"kgw_oracle_em failed with {rc}")
     n = int(it.value)
     return out, n, deltas[:max(n, 1)].copy(), rc == 0
+
+
+# ---- kinship k-means data passes (test infrastructure; kinship_computer.cpp:239-250, 314-336, 368-405) -------------
+def kinship_distances(H, p, members, mu0, mu1, use=None):
+    """update_assignments' distances restated: for member i (a haplotype index) the squared distance of BOTH haplotypes
+    of its sample to each centroid, one accumulator per haplotype walked in locus order (distance(), :239-250), then
+    distance(i0) + distance(i1) (:327-328).  Returns (d0, d1)."""
+    bits = np.unpackbits(np.ascontiguousarray(H, dtype=np.uint8), axis=1, bitorder="little")[:, :p].astype(np.float64)
+    members = np.asarray(members, dtype=np.int64)
+    use = np.ones(p, dtype=bool) if use is None else np.asarray(use).astype(bool)
+    out = []
+    for mu in (np.asarray(mu0, dtype=np.float64), np.asarray(mu1, dtype=np.float64)):
+        tot = []
+        for h in (0, 1):
+            rows = bits[2 * (members // 2) + h]
+            acc = np.zeros(len(members))
+            for j in range(p):                      # sequential in j: the order of the reference's single accumulator
+                if use[j]:
+                    d = rows[:, j] - mu[j]
+                    acc = acc + d * d
+            tot.append(acc)
+        out.append(tot[0] + tot[1])
+    return out[0], out[1]
+
+
+def kinship_centroids(H, p, members, assign):
+    """update_centroids restated (:368-405): sums of 0.0 / 1.0 over the members of each side, divided by the side's size."""
+    bits = np.unpackbits(np.ascontiguousarray(H, dtype=np.uint8), axis=1, bitorder="little")[:, :p].astype(np.float64)
+    members = np.asarray(members, dtype=np.int64)
+    assign = np.asarray(assign)
+    mus = []
+    for side in (0, 1):
+        sel = members[assign == side]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mus.append(bits[sel].sum(axis=0) / float(len(sel)) if len(sel) else np.full(p, np.nan))
+    return mus[0], mus[1]

@@ -36,12 +36,12 @@ def _lay_out_inputs(d: Path) -> dict:
     return {k: str(d / f"{k}.txt") for k in ("keep", "extract", "map", "part", "ibd")} | {"bgen": str(d / "example_chr22")}
 
 
-def _run(tmp_path: Path, dump: bool, shim_io: bool = True, resolution="2", devices=None):
+def _run(tmp_path: Path, dump: bool, shim_io: bool = True, resolution="2", devices=None, cluster_sizes=("1000", "10000")):
     (tmp_path / "in").mkdir(exist_ok=True)
     (tmp_path / "out").mkdir(exist_ok=True)
     fl = _lay_out_inputs(tmp_path / "in")
     args = [str(BINARY), "--bgen", fl["bgen"], "--keep", fl["keep"], "--extract", fl["extract"], "--map", fl["map"],
-            "--part", fl["part"], "--ibd", fl["ibd"], "--K", "10", "--cluster_size_min", "1000", "--cluster_size_max", "10000",
+            "--part", fl["part"], "--ibd", fl["ibd"], "--K", "10", "--cluster_size_min", cluster_sizes[0], "--cluster_size_max", cluster_sizes[1],
             "--n_threads", "1", "--seed", "2020", "--hmm-rho", "1", "--hmm-lambda", "1e-3", "--windows", "0",
             "--compute-references", "--generate-knockoffs", "--out", str(tmp_path / "out" / "ko")]
     if resolution is not None:
@@ -105,8 +105,12 @@ def test_dropin_binary_writes_the_librarys_knockoffs(tmp_path):
     bed = np.fromfile(beds[0], dtype=np.uint8)
     assert bytes(bed[:3]) == b"\x6c\x1b\x01"
     bim = (tmp_path / "out" / beds[0].name.replace(".bed", ".bim")).read_bytes()
-    r0 = _run(tmp_path, dump=False, shim_io=False)        # the reference's own reader and writer around the device sampler
+    clust = {f.name: f.read_bytes() for f in sorted((tmp_path / "out").glob("*_clust.txt"))}   # k-means with its data passes on the device
+    assert clust and "GPU" in r.stderr, "the kinship clusters were not computed through the library"
+    r0 = _run(tmp_path, dump=False, shim_io=False)        # the reference's own reader, k-means and writer around the device sampler
     assert r0.returncode == 0, r0.stdout[-2000:] + r0.stderr[-2000:]
+    assert {f.name: f.read_bytes() for f in sorted((tmp_path / "out").glob("*_clust.txt"))} == clust, \
+        "the kinship clusters of the device k-means differ from the reference's"
     assert np.array_equal(np.fromfile(beds[0], dtype=np.uint8), bed), "the two forms of the drop-in write different .bed files"
     assert (tmp_path / "out" / beds[0].name.replace(".bed", ".bim")).read_bytes() == bim
     prob, _ = load_golden("toy_chr22_K10_res2")
@@ -173,3 +177,29 @@ def test_dropin_binary_haps_input(tmp_path):
     hk, _ = kg.generate(sp.H, sp.p, sp.K, sp.ref[:, None, :], sp.b, sp.mu, sp.groups, seed=sp.seed)
     want = kg.bed_encode(sp.H, hk, sp.p)
     assert np.array_equal(got["1"][3:].reshape(want.shape), want)
+
+
+@pytest.mark.gpu
+@needs_binary
+def test_dropin_binary_kmeans_on_device(tmp_path):
+    """`--compute-references` with cluster sizes that make the bifurcating k-means split the 2000 toy haplotypes several
+    times (kinship_computer.cpp:511-691): with the data passes of the k-means on the device (kgw_kinship_*) the drop-in
+    writes the clusters, the references and the knockoffs the reference's own k-means leads to."""
+    pytest.importorskip("knockoffgwas_b200")
+    outs = {}
+    for io in (True, False):
+        r = _run(tmp_path, dump=False, shim_io=io, cluster_sizes=("100", "300"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        if io:
+            assert "Bifurcating K-means on the GPU" in r.stderr
+        files = {}
+        for pat in ("*_clust.txt", "*_lref.txt", "*_ref.txt", "*_res2.bed"):
+            got = sorted((tmp_path / "out").glob(pat))
+            assert got, pat
+            files.update({f.name: f.read_bytes() for f in got})
+        outs[io] = files
+    clust = next(v for k, v in outs[True].items() if k.endswith("_clust.txt"))
+    assert len(set(clust.split())) >= 4, "the k-means did not split anything: the test exercises nothing"
+    assert outs[True].keys() == outs[False].keys()
+    for k in outs[True]:
+        assert outs[True][k] == outs[False][k], k
