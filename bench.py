@@ -584,7 +584,21 @@ def run_b200_arm(a, rank, local_rank, world):
             nn, ref_ms = kg.assign_references(prob.H, p, K, clusters)
             pt = (p + 9) // 10
             pair_words = float(sum(len(c) ** 2 for c in clusters)) * ((pt + 31) // 32)
+            # the clustering half: one k-means iteration (distances to two centroids + new centroids) over all haplotypes
+            # on the thinned matrix (every 10th SNP), kgw_kinship_* (kinship_computer.cpp:314-405)
+            bits = np.unpackbits(prob.H, axis=1, bitorder="little")[:, :p][:, ::10]
+            Ht = np.packbits(bits, axis=1, bitorder="little")
+            km = kg.KinshipMatrix(Ht, bits.shape[1])
+            members = np.arange(N, dtype=np.int32)
+            mu0, mu1 = km.centroids(members, (members % 2).astype(np.int32))
+            km.distances(members, mu0, mu1)                                # warm-up
+            t0 = time.perf_counter()
+            d0, d1 = km.distances(members, mu0, mu1)
+            km.centroids(members, (d0 < d1).astype(np.int32) ^ 1)
+            kmeans_ms = (time.perf_counter() - t0) * 1e3
+            km.close()
             return {"device_ms": ref_ms, "pairs": float(sum(len(c) ** 2 for c in clusters)),
+                    "kmeans_iteration_call_ms": kmeans_ms,
                     "thinned_snps": pt, "Gpair_words_per_s": pair_words / (ref_ms * 1e-3) / 1e9,
                     "note": "thin + all-pairs Hamming (xor/popc) + K-smallest with ties in cluster order; "
                             "device time incl. kernel launches, excl. H2D of H; not part of `value`"}

@@ -11,8 +11,8 @@
 //   kin_distance_kernel  one thread per (member, centroid): the same additions in the same order (fp64, no fused
 //                        multiply-add), so the comparison dist_0 < dist_1 (:331) sees the reference's numbers as a
 //                        strict-IEEE build computes them;
-//   kin_centroid_kernel  one thread per 32 loci: integer counts of set bits over the members of each side (exact in any
-//                        order), divided once per locus as the reference divides its sums (:399-402).
+//   kin_centroid_kernel  one thread per (32 loci, 64 members): integer counts of set bits over the members of each side
+//                        (atomics; exact in any order), divided once per locus as the reference divides its sums (:399-402).
 // The control flow around them (initial centroids from the reference's own random stream, the size rebalancing by
 // multimap, acceptance of a split, the list of unfinished clusters) is integer bookkeeping and stays on the host.
 #include "../../include/kgw.h"
@@ -73,15 +73,22 @@ __global__ void kin_distance_kernel(const uint32_t *__restrict__ H, int stride_w
   out[(size_t)side * cap + m] = __dadd_rn(tot[0], tot[1]);   // distance(i0, ...) + distance(i1, ...), :327-328
 }
 
-// thread w: loci 32 w .. 32 w + 31; counts of set bits among the members of each side
+// thread (w, chunk): loci 32 w .. 32 w + 31 of KIN_CHUNK members; counts of set bits among the members of each side,
+// added to the totals with integer atomics (exact in any order)
+constexpr int KIN_CHUNK = 64;
 __global__ void kin_centroid_kernel(const uint32_t *__restrict__ H, int stride_w, int p, const int32_t *__restrict__ members,
                                     const int32_t *__restrict__ assign, int n, unsigned int *__restrict__ cnt) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w * 32 >= p) return;
+  const int nw = (p + 31) / 32;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = (int)(t % nw);
+  const long long chunk = t / nw;
+  const long long m0 = chunk * KIN_CHUNK;
+  if (m0 >= n) return;
+  const int m1 = (int)min((long long)n, m0 + KIN_CHUNK);
   unsigned int c0[32], c1[32];
 #pragma unroll
   for (int q = 0; q < 32; q++) { c0[q] = 0u; c1[q] = 0u; }
-  for (int m = 0; m < n; m++) {
+  for (int m = (int)m0; m < m1; m++) {
     const uint32_t bits = H[(size_t)members[m] * stride_w + w];
     const int a = assign[m];
 #pragma unroll
@@ -94,7 +101,10 @@ __global__ void kin_centroid_kernel(const uint32_t *__restrict__ H, int stride_w
 #pragma unroll
   for (int q = 0; q < 32; q++) {
     const int j = w * 32 + q;
-    if (j < p) { cnt[j] = c0[q]; cnt[(size_t)p + j] = c1[q]; }
+    if (j < p) {
+      if (c0[q]) atomicAdd(cnt + j, c0[q]);
+      if (c1[q]) atomicAdd(cnt + (size_t)p + j, c1[q]);
+    }
   }
 }
 
@@ -176,7 +186,9 @@ int32_t kgw_kinship_centroids(kgw_kinship *k, const int32_t *members, const int3
   KIN_CUDA(cudaMemcpy(k->dmem, members, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
   KIN_CUDA(cudaMemcpy(k->dasg, assign, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
   const int nw = (p + 31) / 32;
-  kin_centroid_kernel<<<(nw + 63) / 64, 64>>>(k->dH, k->stride_w, p, k->dmem, k->dasg, n, k->dcnt);
+  KIN_CUDA(cudaMemset(k->dcnt, 0, sizeof(unsigned int) * 2 * (size_t)p));
+  const long long threads = (long long)nw * ((n + KIN_CHUNK - 1) / KIN_CHUNK);
+  kin_centroid_kernel<<<(unsigned)((threads + 127) / 128), 128>>>(k->dH, k->stride_w, p, k->dmem, k->dasg, n, k->dcnt);
   KIN_CUDA(cudaGetLastError());
   std::vector<unsigned int> cnt(2 * (size_t)p);
   KIN_CUDA(cudaMemcpy(cnt.data(), k->dcnt, sizeof(unsigned int) * 2 * (size_t)p, cudaMemcpyDeviceToHost));
