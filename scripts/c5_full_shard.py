@@ -14,6 +14,7 @@ from knockoffgwas_b200 import synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--parts", action="store_true", help="also time the two branches on their own")
+ap.add_argument("--devices", type=int, default=1, help="GPUs of this process (kgw_options.devices); with --scale 8: the whole of configs[4]")
 a = ap.parse_args()
 N, p, K = int(87500 * a.scale) // 2 * 2, 60000, 100
 pairs = int(4375 * a.scale)
@@ -23,14 +24,19 @@ synth.add_ibd_pairs(prob, pairs)
 related = np.concatenate([m for m, _ in prob.families])
 unrelated = np.setdiff1d(np.arange(N, dtype=np.int32), related).astype(np.int32)
 print(f"{len(unrelated)} unrelated + {len(related)} related haplotypes ({pairs} pairs) x {p} SNPs, K={K}; built in {time.time() - t0:.0f} s", flush=True)
+opts = kg.Options(devices=tuple(range(a.devices))) if a.devices > 1 else None
+t0 = time.time()
 plan = kg.Plan(prob.H, p, K, prob.ref[:, None, :], prob.b, prob.mu, prob.groups, unrelated=unrelated, ref_global=prob.ref,
-               seed=prob.seed, families=prob.families)
+               seed=prob.seed, families=prob.families, options=opts)
+print(f"plan created in {time.time() - t0:.1f} s ({a.devices} device(s))", flush=True)
 info = plan.info()
 plan.run(); plan.sync()
-ms = plan.run_timed(2)
+ms = plan.run_timed(2)   # CUDA events on every device's stream, the slowest device counts (kgw_plan_run_timed)
 print(f"one generate() call: {ms:.1f} ms = {N * p / (ms * 1e-3):.3e} hap-SNPs/s; launches per call {info['launches_per_run']}, "
       f"sampler {info['lanes_per_hap']} lanes x {info['states_per_lane']} states, segment {info['segment_loci']} loci, scratch {info['scratch_bytes'] / 1e9:.1f} GB", flush=True)
+t0 = time.time()
 hk, _ = plan.download()
+print(f"download of the {hk.nbytes / 1e9:.2f} GB of knockoff rows: {time.time() - t0:.1f} s", flush=True)
 plan.close()
 if a.parts:
     for name, kw in (("unrelated only", dict(unrelated=unrelated)),
