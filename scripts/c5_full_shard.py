@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Development helper: one GPU's FULL eighth of BASELINE.json configs[4] (350k samples = 700k haplotypes, K=100, 60 000
+"""Development helper (--K 50 --pairs-per-gpu 0: the same for configs[2], 700k unrelated haplotypes): one GPU's FULL eighth of BASELINE.json configs[4] (350k samples = 700k haplotypes, K=100, 60 000
 SNPs, 10 % related): 78 750 unrelated haplotypes + 4 375 IBD pairs in ONE generate() call (bench.py's c5_shard leg runs a
 quarter of this so that the default run stays within minutes).
 usage: python scripts/c5_full_shard.py [--scale 1.0]"""
@@ -14,20 +14,24 @@ from knockoffgwas_b200 import synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--parts", action="store_true", help="also time the two branches on their own")
+ap.add_argument("--K", type=int, default=100)
+ap.add_argument("--pairs-per-gpu", type=int, default=4375, help="IBD pairs per GPU's eighth (0: configs[2], unrelated haplotypes only)")
 ap.add_argument("--devices", type=int, default=1, help="GPUs of this process (kgw_options.devices); with --scale 8: the whole of configs[4]")
 a = ap.parse_args()
-N, p, K = int(87500 * a.scale) // 2 * 2, 60000, 100
-pairs = int(4375 * a.scale)
+N, p, K = int(87500 * a.scale) // 2 * 2, 60000, a.K
+pairs = int(a.pairs_per_gpu * a.scale)
 t0 = time.time()
 prob = synth.make_problem_fast(N, p, K, seed=2022, rho=1.0, lam=1e-3)
-synth.add_ibd_pairs(prob, pairs)
-related = np.concatenate([m for m, _ in prob.families])
+if pairs > 0:
+    synth.add_ibd_pairs(prob, pairs)
+fams = prob.families if pairs > 0 else None
+related = np.concatenate([m for m, _ in prob.families]) if pairs > 0 else np.zeros(0, np.int32)
 unrelated = np.setdiff1d(np.arange(N, dtype=np.int32), related).astype(np.int32)
 print(f"{len(unrelated)} unrelated + {len(related)} related haplotypes ({pairs} pairs) x {p} SNPs, K={K}; built in {time.time() - t0:.0f} s", flush=True)
 opts = kg.Options(devices=tuple(range(a.devices))) if a.devices > 1 else None
 t0 = time.time()
 plan = kg.Plan(prob.H, p, K, prob.ref[:, None, :], prob.b, prob.mu, prob.groups, unrelated=unrelated, ref_global=prob.ref,
-               seed=prob.seed, families=prob.families, options=opts)
+               seed=prob.seed, families=fams, options=opts)
 print(f"plan created in {time.time() - t0:.1f} s ({a.devices} device(s))", flush=True)
 info = plan.info()
 plan.run(); plan.sync()
