@@ -493,9 +493,12 @@ def run_b200_arm(a, rank, local_rank, world):
         for _ in range(3):
             call()  # warm-up: first touch of pinned pages, module load, device buffer pool primed (W >= 3)
         barrier()
+        per_call = []
         t0 = time.perf_counter()
         for _ in range(a.e2e_steps):
+            tc = time.perf_counter()
             call()
+            per_call.append(round((time.perf_counter() - tc) * 1e3, 2))
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -507,7 +510,7 @@ def run_b200_arm(a, rank, local_rank, world):
         tables = p * (16 + 128 + 128)  # KgwLocusHMM + KgwLocusKO + KgwEmit rows
         e2e = {"value": a.haps * world * p * a.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(prob.H.nbytes + prob.ref.nbytes + tables + 4 * len(mine)),
-               "d2h_bytes_per_step": int(len(mine) * rb), "steps": a.e2e_steps,
+               "d2h_bytes_per_step": int(len(mine) * rb), "steps": a.e2e_steps, "ms_per_call": per_call,
                "call": "kgw_generate (one-shot: plan create + H2D + kernel + D2H + destroy), pinned host buffers"}
 
     # ---- roofline of the dominant (only) kernel, live CUDA-event durations

@@ -110,6 +110,9 @@ struct DevPool {
   struct Item { int dev; size_t bytes; void *ptr; };
   std::mutex mu;
   std::vector<Item> items;
+  long long live[64] = {};   // bytes handed out by pool_alloc and not given back, per device (under `mu`)
+  void add_live(int dev, long long d) { std::lock_guard<std::mutex> lk(mu); if (dev >= 0 && dev < 64) live[dev] += d; }
+  long long live_bytes(int dev) { std::lock_guard<std::mutex> lk(mu); return (dev >= 0 && dev < 64) ? live[dev] : 0; }
   // a buffer of at least `need` bytes and at most 1.25 x that (exact shapes in practice), or nullptr
   void *take(int dev, size_t need, size_t *got) {
     std::lock_guard<std::mutex> lk(mu);
@@ -126,6 +129,7 @@ struct DevPool {
   void give(int dev, void *p, size_t n) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64) live[dev] -= (long long)n;
     if (items.size() >= 64) {   // bounded: drop the oldest entry
       cudaSetDevice(items[0].dev);
       cudaFree(items[0].ptr);
@@ -166,18 +170,56 @@ DevPool g_pool;
 // cudaMalloc through the pool.  A large request that no parked buffer fits belongs to a differently shaped
 // problem: the large parked buffers of the device are released first (the plan sized itself counting on
 // them); on out-of-memory everything parked is released.
+void mem_cache_invalidate(int dev);
 cudaError_t pool_alloc(int dev, void **out, size_t bytes, size_t *got) {
   if (bytes == 0) bytes = 16;
   *out = g_pool.take(dev, bytes, got);
-  if (*out) return cudaSuccess;
+  if (*out) { g_pool.add_live(dev, (long long)*got); return cudaSuccess; }
   if (bytes >= ((size_t)64 << 20)) g_pool.clear(dev, (size_t)64 << 20);
   cudaError_t e = cudaMalloc(out, bytes);
-  if (e == cudaErrorMemoryAllocation && g_pool.clear(dev) > 0) {
-    cudaGetLastError();
-    e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    mem_cache_invalidate(dev);   // the cached figure of mem_available() was too optimistic
+    if (g_pool.clear(dev) > 0) {
+      cudaGetLastError();
+      e = cudaMalloc(out, bytes);
+    }
   }
   *got = bytes;
+  if (e == cudaSuccess) g_pool.add_live(dev, (long long)bytes);
   return e;
+}
+
+// Free device memory a new plan can count on: cudaMemGetInfo's figure plus the parked buffers.  cudaMemGetInfo now and
+// then takes 5-70 ms on a device that holds tens of GB (measured: the one-shot kgw_generate of C2, 38.5 ms, then takes
+// 50-110 ms), so for small plans the figure is derived from a cached query: free + parked + live (the bytes the pool has
+// handed out) does not change under anything the pool does.  Other allocations in the process do change it: a plan that
+// needs a large share of the memory, every 64th call, and any out-of-memory answer go back to the driver.
+struct MemCache { std::mutex mu; bool valid[64] = {}; long long f0[64] = {}; size_t total[64] = {}; int uses[64] = {}; } g_memcache;
+void mem_cache_invalidate(int dev) {
+  std::lock_guard<std::mutex> lk(g_memcache.mu);
+  if (dev >= 0 && dev < 64) g_memcache.valid[dev] = false;
+}
+cudaError_t mem_available(int dev, double rough_need, size_t *avail, size_t *total) {
+  const long long live = g_pool.live_bytes(dev);
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lk(g_memcache.mu);
+    if (g_memcache.valid[dev] && ++g_memcache.uses[dev] < 64) {
+      const long long a = g_memcache.f0[dev] - live;
+      if (a > 0 && rough_need < 0.4 * (double)a) { *avail = (size_t)a; *total = g_memcache.total[dev]; return cudaSuccess; }
+    }
+  }
+  size_t free_b = 0, total_b = 0;
+  cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
+  if (e != cudaSuccess) return e;
+  const size_t parked = g_pool.parked(dev);
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lk(g_memcache.mu);
+    g_memcache.valid[dev] = true; g_memcache.uses[dev] = 0; g_memcache.total[dev] = total_b;
+    g_memcache.f0[dev] = (long long)free_b + (long long)parked + g_pool.live_bytes(dev);
+  }
+  *avail = free_b + parked;
+  *total = total_b;
+  return cudaSuccess;
 }
 
 struct Tables {
@@ -1423,9 +1465,13 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
 
   // variant, occupancy-driven persistent grid (one scratch slot per resident warp); the chromosome is cut
   // into segments when the per-slot scratch of a whole pass would not fit in 60 % of the free memory
-  size_t free_b = 0, total_b = 0;
-  KGW_CUDA_PL(cudaMemGetInfo(&free_b, &total_b));
-  free_b += g_pool.parked(pl->device);   // parked buffers are either taken back or released by pool_alloc
+  size_t free_b = 0, total_b = 0;   // free memory incl. the parked buffers (taken back or released by pool_alloc)
+  {
+    const bool fam = prob->families && prob->families->n_families > 0;
+    const double rough = fam ? 1e30 : (double)prob->n_unrelated * (double)p * (4.0 * K + 16.0) + 2.0 * (double)N * (double)prob->row_bytes;
+    KGW_CUDA_PL(mem_available(pl->device, rough, &free_b, &total_b));
+  }
+  tm.lap("free memory");
   const size_t hw_bytes_est = 2 * (size_t)N * (((size_t)prob->row_bytes + 15) / 16 * 16) + sizeof(int32_t) * (size_t)N * W * K;
   // Variant (lanes per haplotype, states per lane), compiled form and CTA shape: the candidate with the lowest
   // modelled time.  Each form is compiled twice -- `fn` for the densest residency (12 or 16 warps per SM, 168 / 128
