@@ -811,8 +811,11 @@ int fam_create(kgw_plan *pl, const kgw_problem *prob, const DevInfo &dp) {
       seen[id] = 2;
     }
   }
-  for (size_t t = 0; t < (size_t)N * K; t++)
-    if (prob->ref_global[t] < 0 || prob->ref_global[t] >= N) return fail(KGW_ERR_INVALID, "global reference index out of range");
+  {
+    int32_t mn = 0, mx = 0;
+    for (size_t t = 0; t < (size_t)N * K; t++) { mn = std::min(mn, prob->ref_global[t]); mx = std::max(mx, prob->ref_global[t]); }
+    if (mn < 0 || mx >= N) return fail(KGW_ERR_INVALID, "global reference index out of range");
+  }
 
   for (int f = 0; f < F->n_families; f++) {
     for (int sg = F->h_seg_off[f]; sg < F->h_seg_off[f + 1]; sg++) {
@@ -1417,8 +1420,12 @@ int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_pla
   for (int i = 0; i < prob->n_unrelated; i++) {
     if (prob->unrelated[i] < 0 || prob->unrelated[i] >= N) return fail(KGW_ERR_INVALID, "unrelated index out of range");
   }
-  for (size_t t = 0; t < (size_t)N * W * K; t++) {
-    if (prob->ref_local[t] < 0 || prob->ref_local[t] >= N) return fail(KGW_ERR_INVALID, "reference index out of range");
+  {   // (minimum and maximum instead of a test per entry: the loop vectorises; N * W * K entries per call)
+    int32_t mn = 0, mx = 0;
+    const int32_t *r = prob->ref_local;
+    const size_t nref = (size_t)N * W * K;
+    for (size_t t = 0; t < nref; t++) { mn = std::min(mn, r[t]); mx = std::max(mx, r[t]); }
+    if (mn < 0 || mx >= N) return fail(KGW_ERR_INVALID, "reference index out of range");
   }
 
   int ndev = 0;
