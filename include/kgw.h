@@ -257,9 +257,11 @@ int32_t kgw_kinship_centroids(kgw_kinship *k, const int32_t *members, const int3
  * H_out [2 n_samples][row_bytes]: chaplotype rows (bit j at byte j>>3, mask 1<<(j&7)), haplotypes 2i, 2i+1 of
  * sample i as H[2*i].set / H[2*i+1].set fill them (:207-210).  A probability that is not exactly 0 or 1, a
  * missing sample or a block that is not phased / diploid / biallelic returns KGW_ERR_INVALID -- the
- * reference throws "Incorrect input" from prob_to_hap (:48-63).  The selected blocks are inflated on
- * `host_threads` host threads (0 = all; system libzstd.so.1 / libz.so.1, loaded on first use) and decoded and
- * transposed on the device; kernel_ms (may be NULL) receives the device time of that kernel. */
+ * reference throws "Incorrect input" from prob_to_hap (:48-63).  zlib blocks are inflated on the device (one warp
+ * per block; a stream that does not inflate to its stated length or fails its Adler-32 returns KGW_ERR_INVALID,
+ * the reference's uncompress() != Z_OK), zstd blocks on `host_threads` host threads (0 = all; system libzstd.so.1,
+ * loaded on first use; KGW_BGEN_HOST_INFLATE=1 sends zlib blocks the same way through libz.so.1); all are decoded
+ * and transposed on the device; kernel_ms (may be NULL) receives the device time of the kernels. */
 int32_t kgw_bgen_variant_count(const uint8_t *file, int64_t file_bytes, int32_t *n_variants, int32_t *n_samples);
 /* rsid of every variant in file order as (offset into `file`, length): what BgenParser::read_variant hands to the
  * std::find calls of read_worker (bgen_reader.cpp:176-183); the caller builds its id -> position map from it */

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <string>
 #include <thread>
 #include <vector>
@@ -198,6 +199,290 @@ typedef size_t (*zstd_decompress_fn)(void *, size_t, const void *, size_t);
 typedef unsigned (*zstd_iserror_fn)(size_t);
 typedef int (*zlib_uncompress_fn)(unsigned char *, unsigned long *, const unsigned char *, unsigned long);
 
+// ---- zlib-compressed probability blocks on the device.  Every variant's block is its own zlib stream (RFC 1950 around
+// RFC 1951 deflate; what the UK Biobank's BGEN v1.2 files use): the streams are independent, so one thread inflates one
+// block -- canonical Huffman decoding one bit at a time from the code-length counts (no look-up tables to build: the
+// per-thread state is 1.4 KB of local memory), stored / fixed / dynamic blocks, LZ77 copies within the thread's own
+// output.  Slow per stream, but a chromosome has tens of thousands of them and the compressed file is what crosses
+// PCIe.  The Adler-32 of the output is checked as zlib's uncompress() does.
+struct InflateState {
+  const uint8_t *in;
+  long long inlen, incnt;
+  uint8_t *out;
+  long long outlen, outcnt;
+  unsigned long long bitbuf;   // whole bytes of the input, not yet consumed bits from bit 0 up
+  int bitcnt;
+  int err;
+};
+struct Huff { short count[16]; short *symbol; };
+struct HuffCounts { int c[16]; };   // the counts in registers while symbols are decoded (every index is static)
+
+__device__ __forceinline__ void inf_refill(InflateState &s) {
+  while (s.bitcnt <= 56 && s.incnt < s.inlen) {
+    s.bitbuf |= (unsigned long long)s.in[s.incnt++] << s.bitcnt;
+    s.bitcnt += 8;
+  }
+}
+// gives the whole bytes still in the bit buffer back to the input (stored blocks and the trailer start on a byte boundary)
+__device__ __forceinline__ void inf_byte_align(InflateState &s) {
+  s.incnt -= s.bitcnt >> 3;
+  s.bitbuf = 0;
+  s.bitcnt = 0;
+}
+__device__ __forceinline__ int inf_bits(InflateState &s, int need) {   // need <= 13
+  if (s.bitcnt < need) {
+    inf_refill(s);
+    if (s.bitcnt < need) { s.err = 1; return 0; }
+  }
+  const int v = (int)(s.bitbuf & ((1ull << need) - 1ull));
+  s.bitbuf >>= need;
+  s.bitcnt -= need;
+  return v;
+}
+__device__ __forceinline__ void inf_counts(HuffCounts &hc, const Huff &h) {
+#pragma unroll
+  for (int len = 0; len < 16; len++) hc.c[len] = h.count[len];
+}
+// canonical Huffman decoding, one code length after the other (count[len] codes of each length, in symbol order)
+__device__ __forceinline__ int inf_decode(InflateState &s, const HuffCounts &hc, const short *symbol) {
+  if (s.bitcnt < 15) inf_refill(s);
+  unsigned bb = (unsigned)s.bitbuf;
+  int code = 0, first = 0, index = 0;
+#pragma unroll
+  for (int len = 1; len <= 15; len++) {
+    code |= (int)(bb & 1u);
+    bb >>= 1;
+    const int count = hc.c[len];
+    if (code - count < first) {
+      if (len > s.bitcnt) { s.err = 1; return -1; }   // ran into the end of the input
+      s.bitbuf >>= len;
+      s.bitcnt -= len;
+      return symbol[index + (code - first)];
+    }
+    index += count;
+    first += count;
+    first <<= 1;
+    code <<= 1;
+  }
+  s.err = 2;
+  return -1;
+}
+// canonical code from the code lengths; returns 0 for a complete code, > 0 for an incomplete one, < 0 for over-subscription
+__device__ int inf_construct(Huff &h, const short *length, int n) {
+  for (int len = 0; len <= 15; len++) h.count[len] = 0;
+  for (int sym = 0; sym < n; sym++) h.count[length[sym]]++;
+  if (h.count[0] == n) return 0;
+  int left = 1;
+  for (int len = 1; len <= 15; len++) {
+    left <<= 1;
+    left -= h.count[len];
+    if (left < 0) return left;
+  }
+  short offs[16];
+  offs[1] = 0;
+  for (int len = 1; len < 15; len++) offs[len + 1] = offs[len] + h.count[len];
+  for (int sym = 0; sym < n; sym++)
+    if (length[sym] != 0) h.symbol[offs[length[sym]]++] = (short)sym;
+  return left;
+}
+// One warp per block of one variant: lane 0 walks the bit stream (Huffman decoding is serial), every lane takes part
+// in the copies (matches, stored blocks) and in the Adler-32 of the result.  s is lane 0's; the others only use s.out.
+__device__ __forceinline__ void inf_codes(InflateState &s, const Huff &lencode, const Huff &distcode, int lane) {
+  HuffCounts lc, dc;
+  inf_counts(lc, lencode);
+  inf_counts(dc, distcode);
+  const short lens[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+  const short lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+  const short dists[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+  const short dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+  for (;;) {
+    int len = 0, dist = 0, stop = 0;
+    if (lane == 0) {
+      for (;;) {   // literals until the next match, the end of the block or an error
+        int symbol = inf_decode(s, lc, lencode.symbol);
+        if (s.err) break;
+        if (symbol < 256) {
+          if (s.outcnt == s.outlen) { s.err = 3; break; }
+          s.out[s.outcnt++] = (uint8_t)symbol;
+          continue;
+        }
+        if (symbol == 256) { stop = 1; break; }
+        symbol -= 257;
+        if (symbol >= 29) { s.err = 4; break; }
+        len = lens[symbol] + inf_bits(s, lext[symbol]);
+        symbol = inf_decode(s, dc, distcode.symbol);
+        if (s.err) break;
+        if (symbol >= 30) { s.err = 4; break; }
+        dist = dists[symbol] + inf_bits(s, dext[symbol]);
+        if (s.err) break;
+        if ((long long)dist > s.outcnt) { s.err = 5; break; }
+        if (s.outcnt + len > s.outlen) { s.err = 3; break; }
+        break;
+      }
+      if (s.err) stop = 1;
+    }
+    stop = __shfl_sync(0xffffffffu, stop, 0);
+    if (stop) return;
+    len = __shfl_sync(0xffffffffu, len, 0);
+    dist = __shfl_sync(0xffffffffu, dist, 0);
+    const long long o = __shfl_sync(0xffffffffu, s.outcnt, 0);
+    __syncwarp();   // lane 0's literals are visible to the lanes that copy from them
+    uint8_t *dst = s.out + o;
+    const uint8_t *src = dst - dist;
+    if (dist >= len) for (int i = lane; i < len; i += 32) dst[i] = src[i];
+    else for (int i = lane; i < len; i += 32) dst[i] = src[i % dist];   // an overlapping match repeats its last dist bytes
+    __syncwarp();
+    if (lane == 0) s.outcnt = o + len;
+  }
+}
+// code lengths of a dynamic block (RFC 1951 3.2.7) into the two decoding tables; s.err on a malformed header
+__device__ void inf_dynamic_tables(InflateState &s, short *lengths, Huff &lencode, Huff &distcode) {
+  const short order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  const int nlen = inf_bits(s, 5) + 257, ndist = inf_bits(s, 5) + 1, ncode = inf_bits(s, 4) + 4;
+  if (s.err) return;
+  if (nlen > 286 || ndist > 30) { s.err = 8; return; }
+  int index = 0;
+  for (; index < ncode; index++) lengths[order[index]] = (short)inf_bits(s, 3);
+  for (; index < 19; index++) lengths[order[index]] = 0;
+  if (s.err) return;
+  if (inf_construct(lencode, lengths, 19) != 0) { s.err = 8; return; }
+  HuffCounts cc;
+  inf_counts(cc, lencode);
+  index = 0;
+  while (index < nlen + ndist) {
+    int symbol = inf_decode(s, cc, lencode.symbol);
+    if (s.err) return;
+    if (symbol < 16) lengths[index++] = (short)symbol;
+    else {
+      int len = 0, rep;
+      if (symbol == 16) {
+        if (index == 0) { s.err = 8; return; }
+        len = lengths[index - 1];
+        rep = 3 + inf_bits(s, 2);
+      } else if (symbol == 17) rep = 3 + inf_bits(s, 3);
+      else rep = 11 + inf_bits(s, 7);
+      if (s.err) return;
+      if (index + rep > nlen + ndist) { s.err = 8; return; }
+      while (rep--) lengths[index++] = (short)len;
+    }
+  }
+  if (lengths[256] == 0) { s.err = 8; return; }
+  const int e1 = inf_construct(lencode, lengths, nlen);
+  if (e1 != 0 && (e1 < 0 || nlen != lencode.count[0] + lencode.count[1])) { s.err = 8; return; }   // incomplete: one 1-bit code only
+  const int e2 = inf_construct(distcode, lengths + nlen, ndist);
+  if (e2 != 0 && (e2 < 0 || ndist != distcode.count[0] + distcode.count[1])) { s.err = 8; return; }
+}
+constexpr int INF_WARPS = 4;
+__global__ void __launch_bounds__(32 * INF_WARPS) bgen_inflate_kernel(const uint8_t *__restrict__ comp, const long long *__restrict__ comp_off,
+                                                                      const long long *__restrict__ comp_len, uint8_t *blocks,
+                                                                      const long long *__restrict__ col_off, const long long *__restrict__ col_len, int p,
+                                                                      int *__restrict__ status) {
+  const int j = blockIdx.x * INF_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= p) return;
+  InflateState s;
+  s.in = comp + comp_off[j]; s.inlen = comp_len[j]; s.incnt = 0;
+  s.out = blocks + col_off[j]; s.outlen = col_len[j]; s.outcnt = 0;
+  s.bitbuf = 0; s.bitcnt = 0; s.err = 0;
+  short lengths[320], lensym[288], distsym[30];
+  Huff lencode, distcode;
+  lencode.symbol = lensym;
+  distcode.symbol = distsym;
+  // zlib header (RFC 1950): deflate, window <= 32 KB, no preset dictionary
+  if (s.inlen < 6) s.err = 1;
+  else {
+    const unsigned cmf = s.in[0], flg = s.in[1];
+    if ((cmf & 0x0f) != 8 || (cmf >> 4) > 7 || ((cmf << 8) | flg) % 31 != 0 || (flg & 0x20)) s.err = 6;
+    s.incnt = 2;
+  }
+  for (;;) {
+    int last = 0, type = -1;
+    if (lane == 0 && !s.err) {
+      last = inf_bits(s, 1);
+      type = inf_bits(s, 2);
+      if (s.err) type = -1;
+    }
+    type = __shfl_sync(0xffffffffu, type, 0);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (type < 0) break;
+    if (type == 0) {   // stored
+      unsigned len = 0xffffffffu;
+      long long ip = 0, op = 0;
+      if (lane == 0) {
+        inf_byte_align(s);
+        if (s.incnt + 4 > s.inlen) s.err = 1;
+        else {
+          const unsigned l = s.in[s.incnt] | (s.in[s.incnt + 1] << 8), nl = s.in[s.incnt + 2] | (s.in[s.incnt + 3] << 8);
+          s.incnt += 4;
+          if (l != (~nl & 0xffffu)) s.err = 7;
+          else if (s.incnt + l > s.inlen) s.err = 1;
+          else if (s.outcnt + l > s.outlen) s.err = 3;
+          else { len = l; ip = s.incnt; op = s.outcnt; s.incnt += l; s.outcnt += l; }
+        }
+      }
+      len = __shfl_sync(0xffffffffu, len, 0);
+      if (len == 0xffffffffu) break;
+      ip = __shfl_sync(0xffffffffu, ip, 0);
+      op = __shfl_sync(0xffffffffu, op, 0);
+      for (unsigned i = lane; i < len; i += 32) s.out[op + i] = s.in[ip + i];
+      __syncwarp();
+    } else if (type == 3) {
+      if (lane == 0) s.err = 9;
+      break;
+    } else {
+      if (lane == 0) {
+        if (type == 1) {   // fixed codes
+          int sym = 0;
+          for (; sym < 144; sym++) lengths[sym] = 8;
+          for (; sym < 256; sym++) lengths[sym] = 9;
+          for (; sym < 280; sym++) lengths[sym] = 7;
+          for (; sym < 288; sym++) lengths[sym] = 8;
+          inf_construct(lencode, lengths, 288);
+          for (sym = 0; sym < 30; sym++) lengths[sym] = 5;
+          inf_construct(distcode, lengths, 30);
+        } else inf_dynamic_tables(s, lengths, lencode, distcode);
+      }
+      if (__shfl_sync(0xffffffffu, s.err, 0)) break;
+      inf_codes(s, lencode, distcode, lane);
+      if (__shfl_sync(0xffffffffu, s.err, 0)) break;
+    }
+    if (last) break;
+  }
+  if (lane == 0 && !s.err && s.outcnt != s.outlen) s.err = 10;
+  if (__shfl_sync(0xffffffffu, s.err, 0) == 0) {
+    // Adler-32 of the output against the stream's trailer (big endian): every lane sums one stretch of the block,
+    // lane 0 chains the stretches (after a stretch of n bytes, a += sum d_i, b += n a + sum (n - i) d_i)
+    __syncwarp();
+    const long long L = s.outlen, chunk = (((L + 31) / 32) + 3) & ~3ll;
+    const long long lo = min(L, lane * chunk), hi = min(L, lo + chunk);
+    unsigned long long s1 = 0, s2 = 0;
+    long long i = lo;
+    for (; i + 4 <= hi; i += 4) {   // lo and the blocks are 4-byte aligned
+      const unsigned w = *reinterpret_cast<const unsigned *>(s.out + i);
+      const unsigned long long rem = (unsigned long long)(hi - i);
+      const unsigned d0 = w & 255u, d1 = (w >> 8) & 255u, d2 = (w >> 16) & 255u, d3 = w >> 24;
+      s1 += d0 + d1 + d2 + d3;
+      s2 += rem * (d0 + d1 + d2 + d3) - (d1 + 2 * d2 + 3 * d3);
+    }
+    for (; i < hi; i++) { const unsigned d = s.out[i]; s1 += d; s2 += (unsigned long long)(hi - i) * d; }
+    unsigned long long a = 1, b = 0;
+    for (int l = 0; l < 32; l++) {
+      const unsigned long long t1 = __shfl_sync(0xffffffffu, s1, l), t2 = __shfl_sync(0xffffffffu, s2, l);
+      const unsigned long long n = (unsigned long long)__shfl_sync(0xffffffffu, hi - lo, l);
+      b = (b + (n % 65521ull) * a + t2) % 65521ull;
+      a = (a + t1) % 65521ull;
+    }
+    if (lane == 0) {   // the trailer follows the deflate data at the next byte boundary
+      inf_byte_align(s);
+      if (s.incnt + 4 > s.inlen) s.err = 1;
+      else {
+        const unsigned want = ((unsigned)s.in[s.incnt] << 24) | ((unsigned)s.in[s.incnt + 1] << 16) | ((unsigned)s.in[s.incnt + 2] << 8) | s.in[s.incnt + 3];
+        if (want != (((unsigned)b << 16) | (unsigned)a)) s.err = 11;
+      }
+    }
+  }
+  if (lane == 0 && s.err) atomicOr(status, 1);
+}
+
 struct Codecs {
   zstd_decompress_fn zstd = nullptr;
   zstd_iserror_fn zstd_err = nullptr;
@@ -346,18 +631,51 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   do {                                                                                                       \
     cudaError_t e_ = (call);                                                                                 \
     if (e_ != cudaSuccess) {                                                                                 \
-      free(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dlen); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus); \
+      free(stage); cudaFree(dblocks); cudaFree(dcomp); cudaFree(dcoff); cudaFree(dclen); cudaFree(doff); cudaFree(dlen); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus); \
       return kgw_fail_(KGW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
     }                                                                                                        \
   } while (0)
   uint8_t *stage = nullptr, *dblocks = nullptr;
+  uint8_t *dcomp = nullptr;
+  long long *dcoff = nullptr, *dclen = nullptr;
   long long *doff = nullptr, *dlen = nullptr;
   unsigned long long *dinfo = nullptr;
   int32_t *dsidx = nullptr;
   uint32_t *dH = nullptr;
   int *dstatus = nullptr;
   KGW_CUDA_B(cudaSetDevice(device));
-  if (compression != 0u) {
+  // zlib blocks are inflated on the device (bgen_inflate_kernel); KGW_BGEN_HOST_INFLATE=1 keeps them on the host threads
+  bool device_inflate = (compression == 1u);
+  { const char *e = getenv("KGW_BGEN_HOST_INFLATE"); if (e && e[0] == '1') device_inflate = false; }
+  std::vector<long long> comp_off, comp_len;
+  long long total_comp = 0;
+  const uint8_t *comp_src = nullptr;   // what is uploaded for the device inflate: the file's own span, or a packed copy
+  if (device_inflate) {
+    comp_off.resize(p); comp_len.resize(p);
+    long long lo = LLONG_MAX, hi = 0, packed = 0;
+    for (int j = 0; j < p; j++) {
+      const VariantBlock &vb = idx[variant_of_col[j]];
+      comp_len[j] = vb.comp_len;
+      lo = std::min<long long>(lo, vb.data_off);
+      hi = std::max<long long>(hi, vb.data_off + vb.comp_len);
+      packed += (vb.comp_len + 15) & ~15ll;
+    }
+    if (hi - lo <= packed + packed / 2) {   // most of the span is wanted: no staging copy
+      for (int j = 0; j < p; j++) comp_off[j] = idx[variant_of_col[j]].data_off - lo;
+      comp_src = file + lo;
+      total_comp = hi - lo;
+    } else {
+      stage = (uint8_t *)malloc((size_t)packed + 16);   // the compressed blocks, one after the other
+      if (!stage) return kgw_fail_(KGW_ERR_NOMEM, "staging buffer for the compressed BGEN blocks");
+      for (int j = 0; j < p; j++) {
+        const VariantBlock &vb = idx[variant_of_col[j]];
+        comp_off[j] = total_comp;
+        memcpy(stage + total_comp, file + vb.data_off, (size_t)vb.comp_len);
+        total_comp += (vb.comp_len + 15) & ~15ll;
+      }
+      comp_src = stage;
+    }
+  } else if (compression != 0u) {
     stage = (uint8_t *)malloc((size_t)total + 16);
     if (!stage) return kgw_fail_(KGW_ERR_NOMEM, "staging buffer for the inflated BGEN blocks");
   }
@@ -365,7 +683,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   // inflate the selected blocks (host threads; the reference does this inside genfile::bgen, one variant at a time)
   const Codecs &cd = codecs();
   if (compression == 2u && (!cd.zstd || !cd.zstd_err)) { free(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zstd-compressed BGEN but libzstd.so.1 could not be loaded"); }
-  if (compression == 1u && !cd.zlib) { free(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zlib-compressed BGEN but libz.so.1 could not be loaded"); }
+  if (compression == 1u && !device_inflate && !cd.zlib) { free(stage); return kgw_fail_(KGW_ERR_UNSUPPORTED, "zlib-compressed BGEN but libz.so.1 could not be loaded"); }
   int nt = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
   nt = std::max(1, std::min(nt, std::min(p, 64)));
   std::atomic<int> next{0}, failed{0};
@@ -386,7 +704,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
       }
     }
   };
-  if (compression != 0u) {
+  if (compression != 0u && !device_inflate) {
     std::vector<std::thread> th;
     for (int t = 1; t < nt; t++) th.emplace_back(worker);
     worker();
@@ -404,15 +722,34 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   KGW_CUDA_B(kgw_malloc(&dsidx, sizeof(int32_t) * n_samples));
   KGW_CUDA_B(kgw_malloc(&dH, sizeof(uint32_t) * (size_t)n_haps * stride_w));
   KGW_CUDA_B(kgw_malloc(&dstatus, sizeof(int)));
-  KGW_CUDA_B(cudaMemcpy(dblocks, compression == 0u ? file + span_lo : stage, (size_t)total, cudaMemcpyHostToDevice));
-  KGW_CUDA_B(cudaMemcpy(doff, col_off.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
-  KGW_CUDA_B(cudaMemcpy(dsidx, sample_idx, sizeof(int32_t) * n_samples, cudaMemcpyHostToDevice));
   KGW_CUDA_B(cudaMemset(dstatus, 0, sizeof(int)));
   cudaEvent_t e0, e1;
   KGW_CUDA_B(cudaEventCreate(&e0));
   KGW_CUDA_B(cudaEventCreate(&e1));
+  KGW_CUDA_B(cudaMemcpy(doff, col_off.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
+  if (device_inflate) {
+    KGW_CUDA_B(kgw_malloc(&dcomp, (size_t)total_comp + 16));
+    KGW_CUDA_B(kgw_malloc(&dcoff, sizeof(long long) * p));
+    KGW_CUDA_B(kgw_malloc(&dclen, sizeof(long long) * p));
+    KGW_CUDA_B(cudaMemcpy(dcomp, comp_src, (size_t)total_comp, cudaMemcpyHostToDevice));
+    KGW_CUDA_B(cudaMemcpy(dcoff, comp_off.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
+    KGW_CUDA_B(cudaMemcpy(dclen, comp_len.data(), sizeof(long long) * p, cudaMemcpyHostToDevice));
+    KGW_CUDA_B(cudaEventRecord(e0));   // the reported device time covers the inflate kernel
+    bgen_inflate_kernel<<<(p + INF_WARPS - 1) / INF_WARPS, 32 * INF_WARPS>>>(dcomp, dcoff, dclen, dblocks, doff, dlen, p, dstatus);
+    KGW_CUDA_B(cudaGetLastError());
+    int st_inf = 0;
+    KGW_CUDA_B(cudaMemcpy(&st_inf, dstatus, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st_inf) {
+      free(stage); cudaFree(dblocks); cudaFree(dcomp); cudaFree(dcoff); cudaFree(dclen); cudaFree(doff); cudaFree(dlen); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus);
+      return kgw_fail_(KGW_ERR_INVALID, "a BGEN probability block did not decompress to its stated length");
+    }
+  } else {
+    KGW_CUDA_B(cudaMemcpy(dblocks, compression == 0u ? file + span_lo : stage, (size_t)total, cudaMemcpyHostToDevice));
+  }
+  KGW_CUDA_B(cudaMemcpy(dsidx, sample_idx, sizeof(int32_t) * n_samples, cudaMemcpyHostToDevice));
+  KGW_CUDA_B(cudaMemset(dstatus, 0, sizeof(int)));
   const dim3 grid((unsigned)((stride_w + 3) / 4), (unsigned)((n_haps + 255) / 256));
-  KGW_CUDA_B(cudaEventRecord(e0));
+  if (!device_inflate) KGW_CUDA_B(cudaEventRecord(e0));
   bgen_header_kernel<<<(p + 255) / 256, 256>>>(dblocks, doff, dlen, (int)nfile, p, dinfo, dstatus);
   int st_hdr = 0;
   KGW_CUDA_B(cudaMemcpy(&st_hdr, dstatus, sizeof(int), cudaMemcpyDeviceToHost));
@@ -436,7 +773,7 @@ int32_t kgw_bgen_read(const uint8_t *file, int64_t file_bytes, int32_t n_samples
   if (st == 0)
     KGW_CUDA_B(cudaMemcpy2D(H_out, (size_t)row_bytes, dH, sizeof(uint32_t) * (size_t)stride_w, (size_t)((p + 7) / 8), (size_t)n_haps,
                             cudaMemcpyDeviceToHost));
-  free(stage); cudaFree(dblocks); cudaFree(doff); cudaFree(dlen); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus);
+  free(stage); cudaFree(dblocks); cudaFree(dcomp); cudaFree(dcoff); cudaFree(dclen); cudaFree(doff); cudaFree(dlen); cudaFree(dinfo); cudaFree(dsidx); cudaFree(dH); cudaFree(dstatus);
 #undef KGW_CUDA_B
   if (st & BGEN_BAD_HEADER)
     return kgw_fail_(KGW_ERR_INVALID, "BGEN probability block is not phased diploid biallelic layout-2 data of the stated sample count");

@@ -531,7 +531,7 @@ def bgen_read(image, sample_idx, variant_of_col) -> np.ndarray:
     return pack_bits(bits)
 
 
-def bgen_write(bits: np.ndarray, rsids, B: int = 8, compression: int = 1, missing=None, bad_prob=None) -> bytes:
+def bgen_write(bits: np.ndarray, rsids, B: int = 8, compression: int = 1, missing=None, bad_prob=None, zlevel: int = -1) -> bytes:
     """Synthetic phased BGEN v1.2 image (layout 2) for tests: bits uint8 [2 n][p]; compression 0 none / 1 zlib;
     `missing` = (sample, variant) flagged missing, `bad_prob` = (haplotype, variant) given probability 1/2."""
     import struct
@@ -554,7 +554,7 @@ def bgen_write(bits: np.ndarray, rsids, B: int = 8, compression: int = 1, missin
         if compression == 0:
             blk = struct.pack("<I", len(raw)) + raw
         else:
-            z = zlib.compress(raw)
+            z = zlib.compress(raw, zlevel)   # level 0 writes stored blocks, small inputs fixed-Huffman ones
             blk = struct.pack("<II", len(z) + 4, len(raw)) + z
         body += ident + blk
     flags = compression | (2 << 2)

@@ -73,6 +73,42 @@ def test_gpu_matches_oracle_on_synthetic_images(B, compression, n, p):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("host_inflate", [False, True])
+@pytest.mark.parametrize("zlevel,n,p,B", [(0, 50, 40, 8), (1, 3, 70, 8), (9, 300, 33, 8), (6, 40000, 5, 8), (0, 40000, 3, 16), (6, 9000, 130, 1)])
+def test_gpu_inflates_every_kind_of_deflate_block(zlevel, n, p, B, host_inflate, monkeypatch):
+    """zlib blocks are inflated by bgen_inflate_kernel (one thread per variant): stored blocks (level 0; several of them
+    when a block is longer than 65 535 bytes), fixed-Huffman blocks (tiny inputs), dynamic ones, matches further back than
+    a few KB (n = 40 000 makes a 80 KB block).  KGW_BGEN_HOST_INFLATE=1 keeps libz on the host threads: same bytes."""
+    kg = pytest.importorskip("knockoffgwas_b200")
+    if host_inflate:
+        monkeypatch.setenv("KGW_BGEN_HOST_INFLATE", "1")
+    rng = np.random.default_rng(zlevel + n)
+    bits = (rng.random((2 * n, p)) < rng.random(p)[None, :] * 0.5).astype(np.uint8)     # very compressible to noisy columns
+    img = ko.bgen_write(bits, [f"rs{j}" for j in range(p)], B=B, compression=1, zlevel=zlevel)
+    image = np.frombuffer(img, np.uint8)
+    sidx = np.sort(rng.permutation(n)[:max(1, min(n, 500))])
+    rows = np.stack([2 * sidx, 2 * sidx + 1], axis=1).reshape(-1)
+    for vcol in (rng.permutation(p), rng.permutation(p)[:max(1, p // 4)]):      # the file's own span / a packed copy of the blocks
+        H = kg.read_bgen_image(image, sidx, vcol)
+        assert np.array_equal(ko.unpack_bits(H, len(vcol)), bits[rows][:, vcol])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host_inflate", [False, True])
+def test_gpu_rejects_corrupt_zlib_block(host_inflate, monkeypatch):
+    """A damaged deflate stream or a wrong Adler-32 is an error (genfile::bgen throws on uncompress() != Z_OK)."""
+    kg = pytest.importorskip("knockoffgwas_b200")
+    if host_inflate:
+        monkeypatch.setenv("KGW_BGEN_HOST_INFLATE", "1")
+    bits, rsids, img = _synthetic(n=400, p=6, B=8, compression=1)
+    for where in (-1, -40, -100):        # the last variant's block: checksum, then the stream itself
+        bad = np.frombuffer(img, np.uint8).copy()
+        bad[where] ^= 0x5a
+        with pytest.raises(kg.KgwError):
+            kg.read_bgen_image(bad, np.arange(400), np.arange(6))
+
+
+@pytest.mark.gpu
 def test_gpu_reader_mirror_and_errors(tmp_path):
     kg = pytest.importorskip("knockoffgwas_b200")
     bits, rsids, img = _synthetic(n=20, p=100)
