@@ -158,6 +158,17 @@ const char *kgw_last_error(void);
  * ("Missing knockoff variants" / "Inconsistency found on Zk", family_knockoffs.cpp:272-291). */
 int32_t kgw_generate(const kgw_problem *prob, const kgw_options *opt, uint8_t *hk_out, kgw_debug *dbg);
 
+/* Audit mode of the unrelated branch (hard part 1): the same sampler with every sum over the K
+ * states taken left to right and every product in the reference's evaluation order, correctly rounded operation by
+ * operation (backward_const / backwardSum knockoffs.cpp:1052-1073, N_sum / N_norm :1345-1390, weights_sum
+ * utils.cpp:690-698) -- the arithmetic a strict-IEEE build of the reference performs, where kgw_generate sums over
+ * lanes as a tree with fused multiply-adds.  One thread per haplotype with its p x K tables in HBM: slow, meant for
+ * checking the fast path on a sample of haplotypes (prob->unrelated lists them; families must be absent).  Same
+ * keyed generator, same injected_u hook, same outputs as kgw_generate: the listed rows of hk_out, dbg->z / zk, and
+ * in dbg->beta_ckpt EVERY backward row (n_ckpt >= p on entry, = p on return; the table the reference's worker holds
+ * after the last window pass). */
+int32_t kgw_generate_strict(const kgw_problem *prob, int32_t device, uint8_t *hk_out, kgw_debug *dbg);
+
 /* Resident-data path (bench / repeated resolutions): upload once, run many times. */
 int32_t kgw_plan_create(const kgw_problem *prob, const kgw_options *opt, kgw_plan **plan_out);
 /* Replace the partition (Knockoffs::set_partition, knockoffs.cpp:91-107) without re-uploading H. */

@@ -109,6 +109,8 @@ def load_library():
         L.kgw_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         L.kgw_generate.restype = C.c_int32
         L.kgw_generate.argtypes = [C.POINTER(_Problem), C.POINTER(_Options), C.c_void_p, C.POINTER(_Debug)]
+        L.kgw_generate_strict.restype = C.c_int32
+        L.kgw_generate_strict.argtypes = [C.POINTER(_Problem), C.c_int32, C.c_void_p, C.POINTER(_Debug)]
         L.kgw_plan_create.restype = C.c_int32
         L.kgw_plan_create.argtypes = [C.POINTER(_Problem), C.POINTER(_Options), C.POINTER(C.c_void_p)]
         L.kgw_plan_set_groups.restype = C.c_int32
@@ -318,6 +320,19 @@ def generate(H, p, K, ref_local, b, mu, groups, *, win_start=None, win_end=None,
     hk = np.zeros_like(held.H)
     d, out = _make_debug(held, debug_paths, debug_beta)
     _check(L.kgw_generate(C.byref(P), C.byref(o), hk.ctypes.data, C.byref(d) if d is not None else None))
+    return hk, _finish_debug(d, out, held)
+
+
+def generate_strict(H, p, K, ref_local, b, mu, groups, *, win_start=None, win_end=None, unrelated=None, seed=2020,
+                    injected_u=None, device=0, debug_paths=False, debug_beta=False):
+    """kgw_generate_strict(): the unrelated sampler in the reference's summation order (audit mode; one thread per
+    haplotype, slow).  Same arguments and outputs as generate(); debug_beta returns every backward row [n][p][K]."""
+    L = load_library()
+    held = _Held(H, p, K, ref_local, b, mu, groups, win_start, win_end, unrelated, None, seed, injected_u, None)
+    P = held.c()
+    hk = np.zeros_like(held.H)
+    d, out = _make_debug(held, debug_paths, debug_beta)
+    _check(L.kgw_generate_strict(C.byref(P), C.c_int32(device), hk.ctypes.data, C.byref(d) if d is not None else None))
     return hk, _finish_debug(d, out, held)
 
 
