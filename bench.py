@@ -624,6 +624,35 @@ def run_b200_arm(a, rank, local_rank, world):
                             "not part of `value`"}
         guarded("bgen_ingest", bgen_leg)
 
+        # the same file zlib-compressed (what qctool writes by default): the blocks go to the GPU compressed and
+        # bgen_inflate_kernel inflates them there (one warp per variant); beside it libz on the host threads
+        def bgen_zlib_leg():
+            import os
+            pz = min(p, 4000)
+            Hz = np.ascontiguousarray(prob.H[:, :(pz + 7) // 8]).copy()
+            if pz % 8:
+                Hz[:, -1] &= (1 << (pz % 8)) - 1
+            image = synth.write_bgen_image(Hz, pz, compression=1)
+            sidx, vcol = np.arange(N // 2, dtype=np.int32), np.arange(pz, dtype=np.int32)
+            out = {"variants": int(pz), "compressed_bytes": int(image.nbytes), "block_bytes": int(pz * (10 + N // 2 + N))}
+            prev = os.environ.get("KGW_BGEN_HOST_INFLATE")
+            try:
+                for mode in ("device", "host"):
+                    os.environ["KGW_BGEN_HOST_INFLATE"] = "1" if mode == "host" else "0"
+                    kg.read_bgen_image(image, sidx, vcol)                  # warm-up
+                    t0 = time.perf_counter()
+                    Hb, ms = kg.read_bgen_image(image, sidx, vcol, return_ms=True)
+                    out[mode + "_inflate"] = {"call_ms": (time.perf_counter() - t0) * 1e3, "kernel_ms": ms,
+                                              "identical_to_H": bool(np.array_equal(Hb, Hz))}
+            finally:
+                if prev is None:
+                    os.environ.pop("KGW_BGEN_HOST_INFLATE", None)
+                else:
+                    os.environ["KGW_BGEN_HOST_INFLATE"] = prev
+            out["note"] = "first 4000 variants of the population, zlib level 1; device: kernel_ms = inflate + header + unpack kernels; not part of `value`"
+            return out
+        guarded("bgen_zlib_ingest", bgen_zlib_leg)
+
         # the same for the text format (kgw_haps_read replaces the loop of HapsReader::read, haps_reader.cpp:93-124)
         def haps_leg():
             bits = np.unpackbits(prob.H, axis=1, bitorder="little")[:, :p]

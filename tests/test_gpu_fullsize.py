@@ -75,3 +75,15 @@ def test_full_size_complete_matrix_matches_oracle(workload):
     bad = np.flatnonzero((got != want).any(axis=1))
     print(f"C2 complete matrix: {len(bad)} of {N} rows differ from the oracle ({N * P} draws x 3 streams)")
     assert len(bad) == 0, f"rows differing from the oracle: {bad[:20].tolist()}"
+
+
+def test_full_size_sample_in_reference_summation_order(workload):
+    """The audit mode (kgw_generate_strict: the reference's summation order on the device) on 256 rows
+    spread over the benchmark workload returns the rows of the fast path."""
+    sp = workload
+    fast, _ = _run(sp)
+    rows = np.arange(37, N, N // 256, dtype=np.int32)[:256]
+    strict, _ = kg.generate_strict(sp.H, sp.p, sp.K, sp.ref[:, None, :], sp.b, sp.mu, sp.groups, seed=sp.seed, unrelated=rows)
+    assert np.array_equal(strict[rows], fast[rows])
+    rest = np.setdiff1d(np.arange(N), rows)
+    assert not strict[rest].any()
