@@ -267,6 +267,39 @@ __device__ __forceinline__ int inf_decode(InflateState &s, const HuffCounts &hc,
   s.err = 2;
   return -1;
 }
+// First decoding level: the next INF_LBITS (INF_DBITS) bits of the stream index a table of (symbol << 4 | code length)
+// in shared memory; codes longer than that, invalid codes and the end of the input take the loop above.
+constexpr int INF_LBITS = 9, INF_DBITS = 6;
+__device__ __forceinline__ int inf_decode_fast(InflateState &s, const unsigned short *tab, int bits, const HuffCounts &hc, const short *symbol) {
+  if (s.bitcnt < 15) inf_refill(s);
+  const unsigned e = tab[(unsigned)s.bitbuf & ((1u << bits) - 1u)];
+  const int l = (int)(e & 15u);
+  if (l != 0 && l <= s.bitcnt) {
+    s.bitbuf >>= l;
+    s.bitcnt -= l;
+    return (int)(e >> 4);
+  }
+  return inf_decode(s, hc, symbol);
+}
+// fills the (zeroed) table from the code lengths: canonical codes in symbol order within a length (RFC 1951 3.2.2),
+// stored bit-reversed because the stream carries Huffman codes most significant bit first
+__device__ void inf_fast_table(unsigned short *tab, int bits, const Huff &h, const short *length, int n) {
+  int next[16];
+  int code = 0;
+  next[0] = 0;
+  for (int len = 1; len <= 15; len++) {
+    code = (code + (len > 1 ? h.count[len - 1] : 0)) << 1;
+    next[len] = code;
+  }
+  for (int sym = 0; sym < n; sym++) {
+    const int l = length[sym];
+    if (l == 0) continue;
+    const unsigned c = (unsigned)next[l]++;
+    if (l > bits) continue;
+    const unsigned r = __brev(c) >> (32 - l);
+    for (unsigned idx = r; idx < (1u << bits); idx += 1u << l) tab[idx] = (unsigned short)((sym << 4) | l);
+  }
+}
 // canonical code from the code lengths; returns 0 for a complete code, > 0 for an incomplete one, < 0 for over-subscription
 __device__ int inf_construct(Huff &h, const short *length, int n) {
   for (int len = 0; len <= 15; len++) h.count[len] = 0;
@@ -287,7 +320,8 @@ __device__ int inf_construct(Huff &h, const short *length, int n) {
 }
 // One warp per block of one variant: lane 0 walks the bit stream (Huffman decoding is serial), every lane takes part
 // in the copies (matches, stored blocks) and in the Adler-32 of the result.  s is lane 0's; the others only use s.out.
-__device__ __forceinline__ void inf_codes(InflateState &s, const Huff &lencode, const Huff &distcode, int lane) {
+__device__ __forceinline__ void inf_codes(InflateState &s, const Huff &lencode, const Huff &distcode, const unsigned short *ltab,
+                                          const unsigned short *dtab, int lane) {
   HuffCounts lc, dc;
   inf_counts(lc, lencode);
   inf_counts(dc, distcode);
@@ -299,7 +333,7 @@ __device__ __forceinline__ void inf_codes(InflateState &s, const Huff &lencode, 
     int len = 0, dist = 0, stop = 0;
     if (lane == 0) {
       for (;;) {   // literals until the next match, the end of the block or an error
-        int symbol = inf_decode(s, lc, lencode.symbol);
+        int symbol = inf_decode_fast(s, ltab, INF_LBITS, lc, lencode.symbol);
         if (s.err) break;
         if (symbol < 256) {
           if (s.outcnt == s.outlen) { s.err = 3; break; }
@@ -310,7 +344,7 @@ __device__ __forceinline__ void inf_codes(InflateState &s, const Huff &lencode, 
         symbol -= 257;
         if (symbol >= 29) { s.err = 4; break; }
         len = lens[symbol] + inf_bits(s, lext[symbol]);
-        symbol = inf_decode(s, dc, distcode.symbol);
+        symbol = inf_decode_fast(s, dtab, INF_DBITS, dc, distcode.symbol);
         if (s.err) break;
         if (symbol >= 30) { s.err = 4; break; }
         dist = dists[symbol] + inf_bits(s, dext[symbol]);
@@ -336,11 +370,13 @@ __device__ __forceinline__ void inf_codes(InflateState &s, const Huff &lencode, 
   }
 }
 // code lengths of a dynamic block (RFC 1951 3.2.7) into the two decoding tables; s.err on a malformed header
-__device__ void inf_dynamic_tables(InflateState &s, short *lengths, Huff &lencode, Huff &distcode) {
+__device__ void inf_dynamic_tables(InflateState &s, short *lengths, Huff &lencode, Huff &distcode, int &nlen_out, int &ndist_out) {
   const short order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
   const int nlen = inf_bits(s, 5) + 257, ndist = inf_bits(s, 5) + 1, ncode = inf_bits(s, 4) + 4;
   if (s.err) return;
   if (nlen > 286 || ndist > 30) { s.err = 8; return; }
+  nlen_out = nlen;
+  ndist_out = ndist;
   int index = 0;
   for (; index < ncode; index++) lengths[order[index]] = (short)inf_bits(s, 3);
   for (; index < 19; index++) lengths[order[index]] = 0;
@@ -383,6 +419,8 @@ __global__ void __launch_bounds__(32 * INF_WARPS) bgen_inflate_kernel(const uint
   s.in = comp + comp_off[j]; s.inlen = comp_len[j]; s.incnt = 0;
   s.out = blocks + col_off[j]; s.outlen = col_len[j]; s.outcnt = 0;
   s.bitbuf = 0; s.bitcnt = 0; s.err = 0;
+  __shared__ unsigned short fast_tab[INF_WARPS][(1 << INF_LBITS) + (1 << INF_DBITS)];
+  unsigned short *ltab = fast_tab[threadIdx.x >> 5], *dtab = ltab + (1 << INF_LBITS);
   short lengths[320], lensym[288], distsym[30];
   Huff lencode, distcode;
   lencode.symbol = lensym;
@@ -429,6 +467,8 @@ __global__ void __launch_bounds__(32 * INF_WARPS) bgen_inflate_kernel(const uint
       if (lane == 0) s.err = 9;
       break;
     } else {
+      for (int e = lane; e < (1 << INF_LBITS) + (1 << INF_DBITS); e += 32) ltab[e] = 0;
+      __syncwarp();
       if (lane == 0) {
         if (type == 1) {   // fixed codes
           int sym = 0;
@@ -437,12 +477,21 @@ __global__ void __launch_bounds__(32 * INF_WARPS) bgen_inflate_kernel(const uint
           for (; sym < 280; sym++) lengths[sym] = 7;
           for (; sym < 288; sym++) lengths[sym] = 8;
           inf_construct(lencode, lengths, 288);
+          inf_fast_table(ltab, INF_LBITS, lencode, lengths, 288);
           for (sym = 0; sym < 30; sym++) lengths[sym] = 5;
           inf_construct(distcode, lengths, 30);
-        } else inf_dynamic_tables(s, lengths, lencode, distcode);
+          inf_fast_table(dtab, INF_DBITS, distcode, lengths, 30);
+        } else {
+          int nlen = 0, ndist = 0;
+          inf_dynamic_tables(s, lengths, lencode, distcode, nlen, ndist);
+          if (!s.err) {
+            inf_fast_table(ltab, INF_LBITS, lencode, lengths, nlen);
+            inf_fast_table(dtab, INF_DBITS, distcode, lengths + nlen, ndist);
+          }
+        }
       }
       if (__shfl_sync(0xffffffffu, s.err, 0)) break;
-      inf_codes(s, lencode, distcode, lane);
+      inf_codes(s, lencode, distcode, ltab, dtab, lane);
       if (__shfl_sync(0xffffffffu, s.err, 0)) break;
     }
     if (last) break;
