@@ -20,6 +20,7 @@
 #include <iostream>
 #include <map>
 #include <numeric>
+#include <cstring>
 #include <set>
 #include <sstream>
 #include <string>
@@ -610,6 +611,35 @@ void wrap_generate(Knockoffs *self, int /*num_threads*/) {
   if (rc != KGW_OK) {
     std::cerr << "Error: " << kgw_last_error() << std::endl;      // same convention as throw_error_bug (utils.cpp:700)
     exit(-1);
+  }
+  // KGW_AUDIT_HAPS=n: n unrelated haplotypes, evenly spaced, are sampled again in the reference's own summation order
+  // (kgw_generate_strict: sequential sums over k, no fused multiply-adds) and must equal the rows just generated
+  if (const char *au = getenv("KGW_AUDIT_HAPS")) {
+    const int want = std::atoi(au);
+    if (want > 0 && !unrel.empty()) {
+      const int n = std::min<int>(want, (int)unrel.size());
+      std::vector<int32_t> pick(n);
+      for (int t = 0; t < n; t++) pick[t] = unrel[(size_t)t * unrel.size() / n];
+      kgw_problem A = P;
+      A.unrelated = pick.data();
+      A.n_unrelated = n;
+      A.families = nullptr;
+      std::vector<uint8_t> Hs(Hflat.size(), 0);
+      const int dev0 = getenv("KGW_DEVICES") ? std::atoi(getenv("KGW_DEVICES")) : 0;
+      if (kgw_generate_strict(&A, dev0, Hs.data(), nullptr) != KGW_OK) {
+        std::cerr << "Error: " << kgw_last_error() << std::endl;
+        exit(-1);
+      }
+      int differing = 0;
+      for (int i : pick)
+        differing += std::memcmp(Hs.data() + (size_t)i * row_bytes, Hkflat.data() + (size_t)i * row_bytes, row_bytes) != 0;
+      std::cout << "[kgw] audit: " << n << " haplotypes sampled again in the reference's summation order, " << differing
+                << " differ" << std::endl;
+      if (differing) {
+        std::cerr << "Error: the audit of the knockoff sampler found differing haplotypes" << std::endl;
+        exit(-1);
+      }
+    }
   }
   auto take_row = [&](int i) {                           // == set_Hk(i, hk)  (knockoffs.cpp:299)
     k.Hk[i].data.assign(Hkflat.begin() + (size_t)i * row_bytes, Hkflat.begin() + (size_t)(i + 1) * row_bytes);

@@ -36,7 +36,7 @@ def _lay_out_inputs(d: Path) -> dict:
     return {k: str(d / f"{k}.txt") for k in ("keep", "extract", "map", "part", "ibd")} | {"bgen": str(d / "example_chr22")}
 
 
-def _run(tmp_path: Path, dump: bool, shim_io: bool = True, resolution="2", devices=None, cluster_sizes=("1000", "10000")):
+def _run(tmp_path: Path, dump: bool, shim_io: bool = True, resolution="2", devices=None, cluster_sizes=("1000", "10000"), audit=0):
     (tmp_path / "in").mkdir(exist_ok=True)
     (tmp_path / "out").mkdir(exist_ok=True)
     fl = _lay_out_inputs(tmp_path / "in")
@@ -52,6 +52,8 @@ def _run(tmp_path: Path, dump: bool, shim_io: bool = True, resolution="2", devic
     env["KGW_SHIM_IO"] = "1" if shim_io else "0"          # 1: BgenReader::read and plink::write_binary also go through libkgw
     if dump:
         env["KGW_SHIM_DUMP"] = str(tmp_path / "dump")
+    if audit:
+        env["KGW_AUDIT_HAPS"] = str(audit)
     return subprocess.run(args, env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=900)
 
 
@@ -119,6 +121,17 @@ def test_dropin_binary_writes_the_librarys_knockoffs(tmp_path):
                         ref_global=prob.ref_global, seed=prob.seed, families=fams)
     want = kg.bed_encode(prob.H, hk, prob.p)              # == the reference's writeBED on (H, Hk), tests/test_bed.py
     assert np.array_equal(bed[3:].reshape(want.shape), want), "the .bed of the drop-in binary is not (H, this library's Hk)"
+
+
+@pytest.mark.gpu
+@needs_binary
+def test_dropin_binary_audits_its_knockoffs_in_reference_order(tmp_path):
+    """KGW_AUDIT_HAPS=n: after every generate() the drop-in samples n unrelated haplotypes again with
+    kgw_generate_strict (the reference's summation order on the device) and stops if a row differs."""
+    r = _run(tmp_path, dump=False, resolution=None, audit=48)      # all seven resolutions
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("[kgw] audit:")]
+    assert len(lines) == 7 and all(l.endswith("48 haplotypes sampled again in the reference's summation order, 0 differ") for l in lines), lines
 
 
 @pytest.mark.gpu
