@@ -166,7 +166,7 @@ int32_t kgw_generate(const kgw_problem *prob, const kgw_options *opt, uint8_t *h
  * checking the fast path on a sample of haplotypes (prob->unrelated lists them; families must be absent).  Same
  * keyed generator, same injected_u hook, same outputs as kgw_generate: the listed rows of hk_out, dbg->z / zk, and
  * in dbg->beta_ckpt EVERY backward row (n_ckpt >= p on entry, = p on return; the table the reference's worker holds
- * after the last window pass). */
+ * after the last window pass).  Latent states are int32 here as in the reference: no bound on K. */
 int32_t kgw_generate_strict(const kgw_problem *prob, int32_t device, uint8_t *hk_out, kgw_debug *dbg);
 
 /* Resident-data path (bench / repeated resolutions): upload once, run many times. */

@@ -90,3 +90,18 @@ def test_strict_mode_argument_errors():
         kg.generate_strict(prob.H, prob.p, prob.K, bad, prob.b, prob.mu, prob.groups)
     hk, _ = kg.generate_strict(*_args(prob), unrelated=np.zeros(0, np.int32))
     assert not hk.any()
+
+
+def test_strict_mode_has_no_bound_on_K():
+    """The fast path keeps latent states in bytes (K <= 256, KGW_ERR_UNSUPPORTED beyond); the audit mode keeps them in
+    int32 like the reference and takes any K."""
+    prob = synthetic_problem(N=330, p=48, K=300, seed=5, mean_group=2.0)
+    haps = np.arange(0, 330, 11, dtype=np.int32)
+    sub = _sub(prob, haps)
+    res = ko.run_unrelated(sub, mode="philox", want_beta=True)
+    hk, dbg = kg.generate_strict(*_args(sub), **_kw(sub, debug_paths=True, debug_beta=True))
+    assert np.array_equal(dbg.z, res.z) and np.array_equal(dbg.zk, res.zk) and np.array_equal(hk[haps], res.hk)
+    assert np.array_equal(dbg.beta_ckpt, res.beta)
+    assert dbg.z.max() > 255
+    with pytest.raises(kg.KgwError):
+        kg.generate(*_args(sub), **_kw(sub))
