@@ -409,7 +409,7 @@ __device__ void inf_dynamic_tables(InflateState &s, short *lengths, Huff &lencod
   if (e2 != 0 && (e2 < 0 || ndist != distcode.count[0] + distcode.count[1])) { s.err = 8; return; }
 }
 constexpr int INF_WARPS = 4;
-__global__ void __launch_bounds__(32 * INF_WARPS) bgen_inflate_kernel(const uint8_t *__restrict__ comp, const long long *__restrict__ comp_off,
+__global__ void __launch_bounds__(32 * INF_WARPS, 8) bgen_inflate_kernel(const uint8_t *__restrict__ comp, const long long *__restrict__ comp_off,
                                                                       const long long *__restrict__ comp_len, uint8_t *blocks,
                                                                       const long long *__restrict__ col_off, const long long *__restrict__ col_len, int p,
                                                                       int *__restrict__ status) {
