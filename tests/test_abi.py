@@ -83,6 +83,9 @@ def test_no_cpu_fallback(lib):
     assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
     with pytest.raises(kg.KgwError):
         kg.Plan(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups)
+    with pytest.raises(kg.KgwError) as ei:      # the audit mode runs on the device as well
+        kg.generate_strict(prob.H, prob.p, prob.K, prob.ref_local, prob.b, prob.mu, prob.groups)
+    assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
 
 
 def test_argument_validation_precedes_device_probe(lib):
