@@ -799,3 +799,23 @@ class Knockoffs:
                               ref_global=self.references_global, seed=self.seed, families=self.families,
                               options=self.options)
         return self.Hk
+
+    def audit(self, n_haps=64):
+        """Samples `n_haps` evenly spaced unrelated haplotypes again in the reference's own summation order
+        (kgw_generate_strict) and returns the ones whose knockoff row differs from the last generate()'s -- an empty
+        array when the fast path drew exactly what a strict-IEEE build of the reference would."""
+        assert self.Hk is not None, "generate() first"
+        unrel = self.unrelated
+        if unrel is None:
+            unrel = np.arange(self.num_haps, dtype=np.int32)
+            if self.families:
+                unrel = np.setdiff1d(unrel, np.concatenate([np.asarray(m) for m, _ in self.families])).astype(np.int32)
+        unrel = np.asarray(unrel, dtype=np.int32)
+        n = min(int(n_haps), len(unrel))
+        if n <= 0:
+            return np.zeros(0, dtype=np.int32)
+        pick = unrel[(np.arange(n, dtype=np.int64) * len(unrel)) // n]
+        dev = self.options.device if self.options is not None else 0
+        hs, _ = generate_strict(self.H, self.num_snps, self.K, self.references_local, self.b, self.mut_rates, self.groups,
+                                win_start=self.win_start, win_end=self.win_end, unrelated=pick, seed=self.seed, device=dev)
+        return pick[(hs[pick] != self.Hk[pick]).any(axis=1)]

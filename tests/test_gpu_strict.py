@@ -105,3 +105,15 @@ def test_strict_mode_has_no_bound_on_K():
     assert dbg.z.max() > 255
     with pytest.raises(kg.KgwError):
         kg.generate(*_args(sub), **_kw(sub))
+
+
+def test_knockoffs_mirror_audits_its_last_generate():
+    prob = synthetic_problem(N=96, p=300, K=12, seed=3, mean_group=3.0)
+    k = kg.Knockoffs(prob.H, prob.p, prob.K, seed=prob.seed)
+    k.set_references(prob.ref_local)
+    k.load_hmm(-np.log(np.maximum(prob.b, 1e-300)), prob.mu)
+    k.set_groups(prob.groups)
+    k.generate()
+    assert len(k.audit(40)) == 0
+    k.Hk[55, 7] ^= 0x10                       # a flipped knockoff allele is found when its row is among the sampled ones
+    assert k.audit(96).tolist() == [55]
